@@ -1,0 +1,85 @@
+"""Pins oracle/stereo_oracle.c against the reference's 12 golden PNGs (SURVEY.md section 4.3,
+written by main.cu:162-181 from a Tsukuba run, D_MIN=-15, D_MAX=0).  CPU only."""
+import numpy as np
+import pytest
+
+import _oracle as O
+
+DMIN, SIZE_D = -15, 16
+
+
+@pytest.fixture(scope="module")
+def tsukuba(oracle):
+    L, R = O.tsukuba_rgb()
+    gl, gr = oracle.rgb_to_gray(L), oracle.rgb_to_gray(R)
+    p = oracle.params(box_mode=O.BOX_FAITHFUL, use_fma=0, nthreads=oracle.max_threads())
+    res = oracle.pipeline_gray(gl, gr, DMIN, SIZE_D, p, want_second=True)
+    res["gl"], res["gr"] = gl, gr
+    return res
+
+
+def test_gray_exact(tsukuba):
+    assert np.array_equal(tsukuba["gl"], O.load_png("image_left.png"))
+    assert np.array_equal(tsukuba["gr"], O.load_png("image_right.png"))
+
+
+def test_mean_image_exact(tsukuba):
+    # (uchar)(int)box_r9(I): pins the float32 SAT box mean incl. border clipping
+    assert np.array_equal(tsukuba["meanL"], O.load_png("image_mean_left.png"))
+    assert np.array_equal(tsukuba["meanR"], O.load_png("image_mean_right.png"))
+
+
+def test_cost_slice0(oracle, tsukuba):
+    cl = oracle.cost_volume(tsukuba["gl"], tsukuba["gr"], 1, DMIN)[0]
+    cr = oracle.cost_volume(tsukuba["gr"], tsukuba["gl"], 1, 0)[0]
+    assert np.array_equal(oracle.write_mat(cl), O.load_png("cost_lminus15.png"))
+    assert np.array_equal(oracle.write_mat(cr), O.load_png("cost_rminus15.png"))
+
+
+def test_best_cost(oracle, tsukuba):
+    # min/max-normalised to 8 bit by write_mat, so every pixel depends on the last bit of the
+    # global min and max: an exact match pins the whole float32 filter chain
+    for key, name in (("bestL", "best_costl.png"), ("bestR", "best_costr.png")):
+        assert np.array_equal(oracle.write_mat(tsukuba[key]), O.load_png(name))
+
+
+def test_disparity_labels_exact(tsukuba):
+    gl = O.load_png("disparity_mapl.png").astype(int)
+    gr = O.load_png("disparity_mapr.png").astype(int)
+    assert np.array_equal(tsukuba["dL"].astype(int), gl // 17 - 15)
+    assert np.array_equal(tsukuba["dR"].astype(int), gr // 17)
+    assert np.all(gl % 17 == 0) and np.all(gr % 17 == 0)
+
+
+def test_occlusion_and_fill_exact(tsukuba):
+    occ_png = O.load_png("occlu_mapl.png").astype(int)
+    occ = tsukuba["occ"]
+    assert np.array_equal(occ == DMIN - 100, occ_png == 0)
+    assert abs((occ_png == 0).mean() - 0.09589) < 1e-4
+    # non-occluded pixels: write_mat maps d in [-115, 0] to (d+115)*255/115
+    keep = occ_png != 0
+    assert np.array_equal(((occ[keep] + 115.0) * 255.0 / 115.0).astype(int), occ_png[keep])
+    filled_png = O.load_png("occlu_mapl_filled.png").astype(int)
+    assert np.array_equal(tsukuba["filled"].astype(int), filled_png // 17 - 15)
+
+
+def test_exact_mode_close_to_faithful(oracle, tsukuba):
+    """H1 in SURVEY.md: the float32 SAT is noisier than a true box sum; labels still agree
+    everywhere the reference's own WTA margin exceeds that noise."""
+    p = oracle.params(box_mode=O.BOX_EXACT, use_fma=0, nthreads=oracle.max_threads())
+    ex = oracle.pipeline_gray(tsukuba["gl"], tsukuba["gr"], DMIN, SIZE_D, p)
+    for lab, best, second in (("dL", "bestL", "secondL"), ("dR", "bestR", "secondR")):
+        same = ex[lab] == tsukuba[lab]
+        assert same.mean() > 0.9998
+        margin = tsukuba[second] - tsukuba[best]
+        assert np.all(same[margin > 5e-3])
+        rel = np.abs(ex[best] - tsukuba[best]) / np.maximum(np.abs(tsukuba[best]), 1e-3)
+        assert np.median(rel) < 1e-4
+
+
+def test_fma_switch_is_label_neutral(oracle, tsukuba):
+    p = oracle.params(box_mode=O.BOX_FAITHFUL, use_fma=1, nthreads=oracle.max_threads())
+    nf = oracle.pipeline_gray(tsukuba["gl"], tsukuba["gr"], DMIN, SIZE_D, p)
+    assert (nf["dL"] == tsukuba["dL"]).mean() > 0.9999
+    assert np.array_equal(oracle.cost_volume(tsukuba["gl"], tsukuba["gr"], 4, -3, oracle.params(use_fma=0)),
+                          oracle.cost_volume(tsukuba["gl"], tsukuba["gr"], 4, -3, oracle.params(use_fma=1)))
