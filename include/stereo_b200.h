@@ -1,0 +1,193 @@
+/*
+ * stereo_b200.h -- C ABI of the B200-native local stereo pipeline.
+ *
+ * Drop-in boundary for hamza1030/stereo_matching_cuda's host stage functions (the free
+ * functions declared in its .cuh headers and called from main.cu:65-155).  Every entry
+ * point below names the reference interface it replaces (paths relative to
+ * stereo_matching_cuda/ in the reference).  Differences that are deliberate:
+ *   - extern "C", int status return (0 = ok), never exit(): the reference's CHECK macro
+ *     prints and calls exit(0) (SystemIncludes.h:46-52);
+ *   - an explicit context owns the device, the stream and a workspace arena, so no entry
+ *     point cudaMallocs per call once warm (the reference allocates and frees inside every
+ *     stage: e.g. guidedFilter.cu:39-56, integral.cu:12-16);
+ *   - the reference's compile-time macros (SystemIncludes.h:6-24) are the runtime
+ *     sb200_params; sb200_default_params() yields exactly the macro values;
+ *   - `_dev` variants take device pointers and run asynchronously on the context's stream
+ *     so stages compose without PCIe round trips.  The plain variants take HOST pointers and
+ *     block, like the reference's.
+ * There is no CPU fallback: every entry point fails with SB200_ERR_CUDA if no device works.
+ *
+ * Layouts (same as the reference): images row-major, RGB interleaved with `channels` bytes
+ * per pixel, cost volumes planar D-major cost[k*w*h + y*w + x] (costVolume.cu:178),
+ * disparity labels stored as float (guidedFilter.cu:406).
+ */
+#ifndef STEREO_B200_H
+#define STEREO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB200_OK 0
+#define SB200_ERR_INVALID 1     /* bad argument (null pointer, non-positive size, ...) */
+#define SB200_ERR_CUDA 2        /* a CUDA runtime call or kernel failed; see sb200_last_error */
+#define SB200_ERR_UNSUPPORTED 3 /* valid request outside what the kernels implement */
+#define SB200_ERR_NOMEM 4
+
+#define SB200_GUIDE_GRAY 0 /* the reference's only mode (main.cu:65-66) */
+#define SB200_GUIDE_RGB 1  /* colour guided filter, SURVEY.md A.8 (not in the reference) */
+
+#define SB200_BOX_SLIDING 0 /* separable sliding-window sums (exact for the cost stage) */
+#define SB200_BOX_SAT 1     /* float32 summed-area table, bit-faithful to integral.cu */
+
+typedef struct sb200_ctx sb200_ctx;
+
+/* SystemIncludes.h:6-24 as data.  sb200_default_params() fills the macro values. */
+typedef struct sb200_params {
+    int dmin;        /* D_MIN  -15  :12 */
+    int dmax;        /* D_MAX    0  :11   size_d = dmax - dmin + 1 */
+    int radius;      /* RADIUS   9  :21 */
+    int d_lr;        /* D_LR     0  :24 */
+    double eps;      /* EPS 6.5025  :23 (double literal in the reference) */
+    float alpha;     /* ALPHA  0.9  :10 */
+    float th_color;  /* TH_color 7  :14 */
+    float th_grad;   /* TH_grad  2  :13 */
+    double r_w;      /* R_W  0.299  :7 */
+    double g_w;      /* G_W  0.587  :8 */
+    double b_w;      /* B_W 0.0721  :9 */
+    int guide_mode;  /* SB200_GUIDE_* */
+    int box_mode;    /* SB200_BOX_*   (stage entry points only; the fused pipeline is SLIDING) */
+} sb200_params;
+
+void sb200_default_params(sb200_params* p);
+
+/* ---- context ----------------------------------------------------------------------- */
+/* replaces main.cu:44-48 (cudaGetDeviceProperties / cudaSetDevice(0)) */
+int sb200_ctx_create(int device, sb200_ctx** out);
+void sb200_ctx_destroy(sb200_ctx* ctx);
+/* `stream` is a cudaStream_t (NULL = the legacy default stream).  Not owned. */
+int sb200_ctx_set_stream(sb200_ctx* ctx, void* stream);
+int sb200_ctx_synchronize(sb200_ctx* ctx);
+/* message of the last failure on this context (or of ctx_create when ctx == NULL) */
+const char* sb200_last_error(const sb200_ctx* ctx);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+uint64_t sb200_launch_count(const sb200_ctx* ctx);
+const char* sb200_version(void);
+
+/* ---- stage drop-ins, HOST pointers, blocking ----------------------------------------- */
+/* rgb_to_grayscale.cuh:7  unsigned char* rgb_to_grayscale(h_rgb, n, channels, compare).
+ * The reference returns a malloc'd buffer; here the caller provides gray[n]. channels >= 3. */
+int sb200_rgb_to_grayscale(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h_rgb, int n, int channels,
+                           uint8_t* h_gray);
+/* costVolume.cuh:7  compute_cost(i1, i2, cost, w1, w2, h1, h2, dmin, compare); size_d is the
+ * reference's macro D_MAX-D_MIN+1, here p->dmax - p->dmin + 1; `dmin` stays an argument because
+ * main.cu:80-82 passes D_MIN for the left view and -D_MAX for the right view. w1==w2, h1==h2. */
+int sb200_compute_cost(sb200_ctx* ctx, const sb200_params* p, const uint8_t* i1, const uint8_t* i2, float* cost,
+                       int w1, int w2, int h1, int h2, int dmin);
+/* costVolume.cuh:16  x_derivativeOnGPU as a host-callable stage */
+int sb200_x_derivative(sb200_ctx* ctx, const uint8_t* img, float* grad, int w, int h);
+/* integral.cuh:3  integral(image, integral, width, height): float32 SAT, sequential add order */
+int sb200_integral(sb200_ctx* ctx, const float* image, float* integral, int width, int height);
+/* guidedFilter.cuh:23  computeBoxFilterOnGPU(image, integral, mean, w, h): 4-tap SAT lookup */
+int sb200_box_filter_sat(sb200_ctx* ctx, const sb200_params* p, const float* integral, float* mean, int w, int h);
+/* box mean of a float image in p->box_mode (SAT: the two calls above; SLIDING: double-accumulated) */
+int sb200_box_filter(sb200_ctx* ctx, const sb200_params* p, const float* image, float* mean, int w, int h);
+/* filter.cuh:12  filter(image, width, height, mean, var, cuda): guide mean (uchar) + variance.
+ * Semantics are those of the live path (guidedFilter.cu:58-123), not filter.cu's dead tile kernel. */
+int sb200_filter(sb200_ctx* ctx, const sb200_params* p, const uint8_t* image, int width, int height, uint8_t* mean,
+                 float* var);
+/* guidedFilter.cuh:7  compute_guided_filter(i, cost, filter_cost, disp_map, mean, w, h, size_d, dmin, compare):
+ * guide statistics + per-slice guided filter + running WTA.  filter_cost / disp_map are IN/OUT
+ * and must be pre-initialised by the caller (main.cu:112-120). */
+int sb200_compute_guided_filter(sb200_ctx* ctx, const sb200_params* p, const uint8_t* i, const float* cost,
+                                float* filter_cost, float* disp_map, uint8_t* mean, int w, int h, int size_d,
+                                int dmin);
+/* guidedFilter.cuh:8  dispSelectOnGPU(q, filter_cost, dmap, n, label): the live winner-take-all
+ * (winner_take_all.cuh is commented out in the reference).  Update on best >= q. */
+int sb200_winner_take_all(sb200_ctx* ctx, const float* q, float* filter_cost, float* dmap, int n, int label);
+/* occlusion.cuh:8  detect_occlusion(dL, dR, dOcclusion, dmapl, dmapr, w, h); the two uchar maps
+ * are passed through untouched by the reference (occlusion.cu:40-41,55-56) and may be NULL. */
+int sb200_detect_occlusion(sb200_ctx* ctx, const sb200_params* p, float* disparityLeft, const float* disparityRight,
+                           int dOcclusion, uint8_t* dmapl, uint8_t* dmapr, int w, int h);
+/* occlusion.cuh:14  fill_occlusion(disparity, w, h, vMin) */
+int sb200_fill_occlusion(sb200_ctx* ctx, float* disparity, int w, int h, float vMin);
+
+/* ---- stage drop-ins, DEVICE pointers, asynchronous on the context's stream -------------- */
+int sb200_rgb_to_grayscale_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_rgb, int n, int channels,
+                               uint8_t* d_gray);
+int sb200_compute_cost_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_i1, const uint8_t* d_i2,
+                           float* d_cost, int w, int h, int dmin);
+int sb200_integral_dev(sb200_ctx* ctx, const float* d_image, float* d_integral, int w, int h);
+int sb200_box_filter_dev(sb200_ctx* ctx, const sb200_params* p, const float* d_image, float* d_mean, int w, int h);
+int sb200_compute_guided_filter_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_i, const float* d_cost,
+                                    float* d_filter_cost, float* d_disp_map, uint8_t* d_mean, int w, int h,
+                                    int size_d, int dmin);
+int sb200_winner_take_all_dev(sb200_ctx* ctx, const float* d_q, float* d_filter_cost, float* d_dmap, int n,
+                              int label);
+int sb200_detect_occlusion_dev(sb200_ctx* ctx, const sb200_params* p, float* d_dL, const float* d_dR, int dOcclusion,
+                               int w, int h);
+int sb200_fill_occlusion_dev(sb200_ctx* ctx, float* d_disparity, int w, int h, float vMin);
+
+/* ---- fused pipeline (replaces main.cu:65-155 as one call) -------------------------------- */
+/* Outputs; any pointer may be NULL.  All arrays are w*h. */
+typedef struct sb200_outputs {
+    float* disp_left;      /* dmapl  main.cu:133 : WTA labels of the left view, in [dmin, dmax]  */
+    float* disp_right;     /* dmapr  main.cu:134 : WTA labels of the right view, in [-dmax, -dmin] */
+    float* occlusion;      /* main.cu:150 : disp_left with occluded pixels set to dmin-100       */
+    float* filled;         /* main.cu:155 : occlusion map after scan-line fill (vMin = dmin)     */
+    float* best_left;      /* best_costl main.cu:133 : min over d of the filtered cost            */
+    float* best_right;     /* best_costr main.cu:134                                              */
+    uint8_t* gray_left;    /* I_l main.cu:65 */
+    uint8_t* gray_right;   /* I_r main.cu:66 */
+    uint8_t* mean_left;    /* mean1 main.cu:133 : (uchar)min((int)mean_I,255) debug image        */
+    uint8_t* mean_right;   /* mean2 main.cu:134 */
+} sb200_outputs;
+
+/* Row-strip geometry for multi-GPU sharding: the images passed in are rows
+ * [y0 - halo_top, y0 + rows + halo_bot) of a frame_h-row frame; outputs cover rows
+ * [y0, y0 + rows).  Zero-initialise for a whole frame (rows = h, y0 = 0, frame_h = h). */
+typedef struct sb200_strip {
+    int y0;
+    int rows;
+    int halo_top;
+    int halo_bot;
+    int frame_h;
+} sb200_strip;
+
+/* Device pointers, asynchronous.  left/right: channels==1 (gray) or >=3 (interleaved RGB).
+ * cost + guided-filter box sums + running argmin are one fused kernel per pair (both views);
+ * L/R check + fill are a second kernel.  The D-deep volume is never materialised. */
+int sb200_pipeline_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, const uint8_t* d_right,
+                       int channels, int w, int h, const sb200_outputs* d_out);
+/* same with HOST pointers, blocking (pageable or pinned; copies happen inside) */
+int sb200_pipeline(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h_left, const uint8_t* h_right, int channels,
+                   int w, int h, const sb200_outputs* h_out);
+/* n_pairs pairs of identical shape, contiguous: left + i*w*h*channels, outputs + i*w*h */
+int sb200_pipeline_batch_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, const uint8_t* d_right,
+                             int channels, int w, int h, int n_pairs, const sb200_outputs* d_out);
+/* one row strip of a taller frame; h = halo_top + rows + halo_bot rows are passed in */
+int sb200_pipeline_strip_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, const uint8_t* d_right,
+                             int channels, int w, const sb200_strip* strip, const sb200_outputs* d_out);
+/* halo rows each side that sb200_pipeline_strip_dev needs: 2*radius (two cascaded boxes) */
+int sb200_strip_halo_rows(const sb200_params* p);
+
+/* Fused view kernel alone (for measurement and for callers that only want one view):
+ * guide/other are gray images on the device; best/disp are outputs. */
+int sb200_view_disparity_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_guide, const uint8_t* d_other,
+                             int w, int h, int dmin, int size_d, float* d_best, float* d_disp, uint8_t* d_mean);
+/* L/R check + fill alone: occlusion/filled outputs from the two label maps */
+int sb200_lr_check_fill_dev(sb200_ctx* ctx, const sb200_params* p, const float* d_dL, const float* d_dR, int w, int h,
+                            int dOcclusion, float vMin, float* d_occlusion, float* d_filled);
+
+/* device timing of the last pipeline call's kernels, in milliseconds (needs
+ * sb200_ctx_enable_timing(ctx,1) before the call; adds event records, no syncs) */
+int sb200_ctx_enable_timing(sb200_ctx* ctx, int on);
+int sb200_last_timing(sb200_ctx* ctx, float* ms_prep, float* ms_fused, float* ms_merge, float* ms_occl);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STEREO_B200_H */

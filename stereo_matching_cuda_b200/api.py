@@ -1,0 +1,373 @@
+"""ctypes binding of include/stereo_b200.h and a numpy/torch-friendly mirror of the
+reference's host stage functions (same names, argument meaning and in/out conventions;
+paths below are relative to stereo_matching_cuda/ in the reference).
+
+Host entry points take numpy arrays (HOST memory), block, and return numpy arrays -- the
+reference's calling convention.  `*_dev` methods take torch CUDA tensors (or raw device
+pointers) and run asynchronously on the context's stream; torch is only used for device
+memory and streams.  Every failure raises StereoB200Error with the library's message; a
+missing or unloadable libstereo_b200.so raises immediately (there is no fallback).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+GUIDE_GRAY, GUIDE_RGB = 0, 1
+BOX_SLIDING, BOX_SAT = 0, 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class StereoB200Error(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    """sb200_params: the reference's SystemIncludes.h:6-24 macros as runtime data."""
+
+    _fields_ = [
+        ("dmin", C.c_int),
+        ("dmax", C.c_int),
+        ("radius", C.c_int),
+        ("d_lr", C.c_int),
+        ("eps", C.c_double),
+        ("alpha", C.c_float),
+        ("th_color", C.c_float),
+        ("th_grad", C.c_float),
+        ("r_w", C.c_double),
+        ("g_w", C.c_double),
+        ("b_w", C.c_double),
+        ("guide_mode", C.c_int),
+        ("box_mode", C.c_int),
+    ]
+
+    @property
+    def size_d(self):
+        return self.dmax - self.dmin + 1
+
+
+class _Outputs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("disp_left", "disp_right", "occlusion", "filled", "best_left", "best_right",
+                                          "gray_left", "gray_right", "mean_left", "mean_right")]
+
+
+class _Strip(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("y0", "rows", "halo_top", "halo_bot", "frame_h")]
+
+
+def lib_path():
+    return os.path.join(_HERE, "libstereo_b200.so")
+
+
+_LIB = None
+
+
+def load_library(path=None):
+    """Loads libstereo_b200.so (built by `python -m stereo_matching_cuda_b200.build`)."""
+    global _LIB
+    if _LIB is not None and path is None:
+        return _LIB
+    path = path or lib_path()
+    if not os.path.exists(path):
+        raise StereoB200Error(f"{path} is missing: run `python -m stereo_matching_cuda_b200.build` (nvcc, sm_100a)")
+    L = C.CDLL(path)
+    vp, ip, fp = C.c_void_p, C.c_int, C.c_float
+    PP = C.POINTER(Params)
+    sig = {
+        "sb200_default_params": (None, [PP]),
+        "sb200_ctx_create": (ip, [ip, C.POINTER(vp)]),
+        "sb200_ctx_destroy": (None, [vp]),
+        "sb200_ctx_set_stream": (ip, [vp, vp]),
+        "sb200_ctx_synchronize": (ip, [vp]),
+        "sb200_last_error": (C.c_char_p, [vp]),
+        "sb200_launch_count": (C.c_uint64, [vp]),
+        "sb200_version": (C.c_char_p, []),
+        "sb200_rgb_to_grayscale": (ip, [vp, PP, vp, ip, ip, vp]),
+        "sb200_compute_cost": (ip, [vp, PP, vp, vp, vp, ip, ip, ip, ip, ip]),
+        "sb200_x_derivative": (ip, [vp, vp, vp, ip, ip]),
+        "sb200_integral": (ip, [vp, vp, vp, ip, ip]),
+        "sb200_box_filter_sat": (ip, [vp, PP, vp, vp, ip, ip]),
+        "sb200_box_filter": (ip, [vp, PP, vp, vp, ip, ip]),
+        "sb200_filter": (ip, [vp, PP, vp, ip, ip, vp, vp]),
+        "sb200_compute_guided_filter": (ip, [vp, PP, vp, vp, vp, vp, vp, ip, ip, ip, ip]),
+        "sb200_winner_take_all": (ip, [vp, vp, vp, vp, ip, ip]),
+        "sb200_detect_occlusion": (ip, [vp, PP, vp, vp, ip, vp, vp, ip, ip]),
+        "sb200_fill_occlusion": (ip, [vp, vp, ip, ip, fp]),
+        "sb200_rgb_to_grayscale_dev": (ip, [vp, PP, vp, ip, ip, vp]),
+        "sb200_compute_cost_dev": (ip, [vp, PP, vp, vp, vp, ip, ip, ip]),
+        "sb200_integral_dev": (ip, [vp, vp, vp, ip, ip]),
+        "sb200_box_filter_dev": (ip, [vp, PP, vp, vp, ip, ip]),
+        "sb200_compute_guided_filter_dev": (ip, [vp, PP, vp, vp, vp, vp, vp, ip, ip, ip, ip]),
+        "sb200_winner_take_all_dev": (ip, [vp, vp, vp, vp, ip, ip]),
+        "sb200_detect_occlusion_dev": (ip, [vp, PP, vp, vp, ip, ip, ip]),
+        "sb200_fill_occlusion_dev": (ip, [vp, vp, ip, ip, fp]),
+        "sb200_pipeline_dev": (ip, [vp, PP, vp, vp, ip, ip, ip, C.POINTER(_Outputs)]),
+        "sb200_pipeline": (ip, [vp, PP, vp, vp, ip, ip, ip, C.POINTER(_Outputs)]),
+        "sb200_pipeline_batch_dev": (ip, [vp, PP, vp, vp, ip, ip, ip, ip, C.POINTER(_Outputs)]),
+        "sb200_pipeline_strip_dev": (ip, [vp, PP, vp, vp, ip, ip, C.POINTER(_Strip), C.POINTER(_Outputs)]),
+        "sb200_strip_halo_rows": (ip, [PP]),
+        "sb200_view_disparity_dev": (ip, [vp, PP, vp, vp, ip, ip, ip, ip, vp, vp, vp]),
+        "sb200_lr_check_fill_dev": (ip, [vp, PP, vp, vp, ip, ip, ip, fp, vp, vp]),
+        "sb200_ctx_enable_timing": (ip, [vp, ip]),
+        "sb200_last_timing": (ip, [vp] + [C.POINTER(fp)] * 4),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)  # AttributeError here means the .so does not export the header's symbol
+        fn.restype, fn.argtypes = res, args
+    L._sb_signatures = sig
+    if path == lib_path():
+        _LIB = L
+    return L
+
+
+EXPORTED_SYMBOLS = None  # filled lazily by tests from the header
+
+
+def default_params(**kw):
+    p = Params()
+    load_library().sb200_default_params(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise TypeError(f"unknown parameter {k}")
+        setattr(p, k, v)
+    return p
+
+
+def _ptr(x):
+    """device/host pointer of a numpy array, torch tensor, int or None"""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return C.c_void_p(x)
+    if isinstance(x, np.ndarray):
+        return C.c_void_p(x.ctypes.data)
+    return C.c_void_p(x.data_ptr())  # torch tensor
+
+
+def _np(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Context:
+    """One context per host thread / GPU (main.cu:44-48 replaced).  Owns the workspace arena."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.sb200_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise StereoB200Error(f"sb200_ctx_create({device}) failed [{rc}]: " +
+                                  self.lib.sb200_last_error(None).decode())
+        self.h = h
+        self.device = device
+        if stream is not None:
+            self.set_stream(stream)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sb200_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise StereoB200Error(f"[{rc}] " + self.lib.sb200_last_error(self.h).decode())
+
+    def set_stream(self, stream):
+        """stream: a raw cudaStream_t handle (int) or a torch.cuda.Stream"""
+        handle = stream if isinstance(stream, int) else stream.cuda_stream
+        self._ck(self.lib.sb200_ctx_set_stream(self.h, C.c_void_p(handle)))
+
+    def synchronize(self):
+        self._ck(self.lib.sb200_ctx_synchronize(self.h))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.sb200_launch_count(self.h))
+
+    def enable_timing(self, on=True):
+        self._ck(self.lib.sb200_ctx_enable_timing(self.h, int(on)))
+
+    def last_timing(self):
+        v = [C.c_float() for _ in range(4)]
+        self._ck(self.lib.sb200_last_timing(self.h, *[C.byref(x) for x in v]))
+        return dict(zip(("prep_ms", "fused_ms", "merge_ms", "occl_ms"), (x.value for x in v)))
+
+    # ---- reference stage functions, host arrays ------------------------------------------
+    def rgb_to_grayscale(self, h_rgb, params=None):
+        """rgb_to_grayscale.cuh:7 -- (h, w, ch>=3) uint8 -> (h, w) uint8"""
+        p = params or default_params()
+        rgb = _np(h_rgb, np.uint8)
+        h, w, ch = rgb.shape
+        gray = np.empty((h, w), np.uint8)
+        self._ck(self.lib.sb200_rgb_to_grayscale(self.h, C.byref(p), _ptr(rgb), h * w, ch, _ptr(gray)))
+        return gray
+
+    def x_derivative(self, img):
+        """costVolume.cuh:16 (x_derivativeOnGPU)"""
+        img = _np(img, np.uint8)
+        h, w = img.shape
+        out = np.empty((h, w), np.float32)
+        self._ck(self.lib.sb200_x_derivative(self.h, _ptr(img), _ptr(out), w, h))
+        return out
+
+    def compute_cost(self, i1, i2, dmin, params=None):
+        """costVolume.cuh:7 -- returns the planar (size_d, h, w) float32 volume"""
+        p = params or default_params()
+        i1, i2 = _np(i1, np.uint8), _np(i2, np.uint8)
+        h, w = i1.shape
+        cost = np.empty((p.size_d, h, w), np.float32)
+        self._ck(self.lib.sb200_compute_cost(self.h, C.byref(p), _ptr(i1), _ptr(i2), _ptr(cost), w, i2.shape[1], h,
+                                             i2.shape[0], dmin))
+        return cost
+
+    def integral(self, image):
+        """integral.cuh:3"""
+        image = _np(image, np.float32)
+        h, w = image.shape
+        out = np.empty((h, w), np.float32)
+        self._ck(self.lib.sb200_integral(self.h, _ptr(image), _ptr(out), w, h))
+        return out
+
+    def box_filter_sat(self, integral, params=None):
+        """guidedFilter.cuh:23 (computeBoxFilterOnGPU)"""
+        p = params or default_params()
+        integral = _np(integral, np.float32)
+        h, w = integral.shape
+        out = np.empty((h, w), np.float32)
+        self._ck(self.lib.sb200_box_filter_sat(self.h, C.byref(p), _ptr(integral), _ptr(out), w, h))
+        return out
+
+    def box_filter(self, image, params=None):
+        p = params or default_params()
+        image = _np(image, np.float32)
+        h, w = image.shape
+        out = np.empty((h, w), np.float32)
+        self._ck(self.lib.sb200_box_filter(self.h, C.byref(p), _ptr(image), _ptr(out), w, h))
+        return out
+
+    def filter(self, image, params=None):
+        """filter.cuh:12 -- returns (mean uint8, var float32) of the guide"""
+        p = params or default_params()
+        image = _np(image, np.uint8)
+        h, w = image.shape
+        mean, var = np.empty((h, w), np.uint8), np.empty((h, w), np.float32)
+        self._ck(self.lib.sb200_filter(self.h, C.byref(p), _ptr(image), w, h, _ptr(mean), _ptr(var)))
+        return mean, var
+
+    def compute_guided_filter(self, i, cost, filter_cost, disp_map, dmin, params=None):
+        """guidedFilter.cuh:7 -- filter_cost and disp_map are updated IN PLACE (main.cu:112-120
+        initialises them); returns the uint8 mean image."""
+        p = params or default_params()
+        i = _np(i, np.uint8)
+        cost = _np(cost, np.float32)
+        size_d, h, w = cost.shape
+        assert filter_cost.dtype == np.float32 and disp_map.dtype == np.float32
+        assert filter_cost.flags.c_contiguous and disp_map.flags.c_contiguous
+        mean = np.empty((h, w), np.uint8)
+        self._ck(self.lib.sb200_compute_guided_filter(self.h, C.byref(p), _ptr(i), _ptr(cost), _ptr(filter_cost),
+                                                      _ptr(disp_map), _ptr(mean), w, h, size_d, dmin))
+        return mean
+
+    def winner_take_all(self, q, filter_cost, dmap, label):
+        """guidedFilter.cuh:8 (dispSelectOnGPU) -- in place on filter_cost / dmap"""
+        q = _np(q, np.float32)
+        assert filter_cost.dtype == np.float32 and dmap.dtype == np.float32
+        self._ck(self.lib.sb200_winner_take_all(self.h, _ptr(q), _ptr(filter_cost), _ptr(dmap), q.size, label))
+
+    def detect_occlusion(self, disparity_left, disparity_right, d_occlusion, params=None):
+        """occlusion.cuh:8 -- in place on disparity_left"""
+        p = params or default_params()
+        assert disparity_left.dtype == np.float32 and disparity_left.flags.c_contiguous
+        dr = _np(disparity_right, np.float32)
+        h, w = disparity_left.shape
+        self._ck(self.lib.sb200_detect_occlusion(self.h, C.byref(p), _ptr(disparity_left), _ptr(dr), d_occlusion, None,
+                                                 None, w, h))
+
+    def fill_occlusion(self, disparity, v_min):
+        """occlusion.cuh:14 -- in place"""
+        assert disparity.dtype == np.float32 and disparity.flags.c_contiguous
+        h, w = disparity.shape
+        self._ck(self.lib.sb200_fill_occlusion(self.h, _ptr(disparity), w, h, float(v_min)))
+
+    # ---- fused pipeline -----------------------------------------------------------------
+    _F32 = ("disp_left", "disp_right", "occlusion", "filled", "best_left", "best_right")
+    _U8 = ("gray_left", "gray_right", "mean_left", "mean_right")
+
+    def pipeline(self, left, right, params=None, want=None):
+        """main.cu:65-155 as one call on HOST arrays: (h,w[,ch]) uint8 -> dict of numpy arrays"""
+        p = params or default_params()
+        left, right = _np(left, np.uint8), _np(right, np.uint8)
+        h, w = left.shape[:2]
+        ch = 1 if left.ndim == 2 else left.shape[2]
+        want = want or (self._F32 + self._U8)
+        res, o = {}, _Outputs()
+        for k in want:
+            res[k] = np.empty((h, w), np.float32 if k in self._F32 else np.uint8)
+            setattr(o, k, res[k].ctypes.data)
+        self._ck(self.lib.sb200_pipeline(self.h, C.byref(p), _ptr(left), _ptr(right), ch, w, h, C.byref(o)))
+        return res
+
+    def _dev_outputs(self, outs):
+        o = _Outputs()
+        for k, t in outs.items():
+            if k not in self._F32 + self._U8:
+                raise TypeError(f"unknown output {k}")
+            setattr(o, k, t if isinstance(t, int) else t.data_ptr())
+        return o
+
+    def pipeline_dev(self, d_left, d_right, channels, w, h, outs, params=None):
+        """device tensors in, device tensors out (dict name -> tensor), asynchronous"""
+        p = params or default_params()
+        o = self._dev_outputs(outs)
+        self._ck(self.lib.sb200_pipeline_dev(self.h, C.byref(p), _ptr(d_left), _ptr(d_right), channels, w, h, C.byref(o)))
+
+    def pipeline_batch_dev(self, d_left, d_right, channels, w, h, n_pairs, outs, params=None):
+        p = params or default_params()
+        o = self._dev_outputs(outs)
+        self._ck(self.lib.sb200_pipeline_batch_dev(self.h, C.byref(p), _ptr(d_left), _ptr(d_right), channels, w, h,
+                                                   n_pairs, C.byref(o)))
+
+    def pipeline_strip_dev(self, d_left, d_right, channels, w, strip, outs, params=None):
+        """strip: dict(y0, rows, halo_top, halo_bot, frame_h)"""
+        p = params or default_params()
+        o = self._dev_outputs(outs)
+        s = _Strip(**strip)
+        self._ck(self.lib.sb200_pipeline_strip_dev(self.h, C.byref(p), _ptr(d_left), _ptr(d_right), channels, w,
+                                                   C.byref(s), C.byref(o)))
+
+    def strip_halo_rows(self, params=None):
+        p = params or default_params()
+        return self.lib.sb200_strip_halo_rows(C.byref(p))
+
+    def view_disparity_dev(self, d_guide, d_other, w, h, dmin, size_d, d_best, d_disp, d_mean=None, params=None):
+        p = params or default_params()
+        self._ck(self.lib.sb200_view_disparity_dev(self.h, C.byref(p), _ptr(d_guide), _ptr(d_other), w, h, dmin, size_d,
+                                                   _ptr(d_best), _ptr(d_disp), _ptr(d_mean)))
+
+    def lr_check_fill_dev(self, d_dl, d_dr, w, h, d_occlusion, v_min, d_occ, d_filled, params=None):
+        p = params or default_params()
+        self._ck(self.lib.sb200_lr_check_fill_dev(self.h, C.byref(p), _ptr(d_dl), _ptr(d_dr), w, h, d_occlusion,
+                                                  float(v_min), _ptr(d_occ), _ptr(d_filled)))
+
+    def compute_guided_filter_dev(self, d_i, d_cost, d_filter_cost, d_disp_map, d_mean, w, h, size_d, dmin, params=None):
+        p = params or default_params()
+        self._ck(self.lib.sb200_compute_guided_filter_dev(self.h, C.byref(p), _ptr(d_i), _ptr(d_cost),
+                                                          _ptr(d_filter_cost), _ptr(d_disp_map), _ptr(d_mean), w, h,
+                                                          size_d, dmin))
+
+    def compute_cost_dev(self, d_i1, d_i2, d_cost, w, h, dmin, params=None):
+        p = params or default_params()
+        self._ck(self.lib.sb200_compute_cost_dev(self.h, C.byref(p), _ptr(d_i1), _ptr(d_i2), _ptr(d_cost), w, h, dmin))

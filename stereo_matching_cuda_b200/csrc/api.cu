@@ -1,0 +1,671 @@
+// api.cu -- the C ABI of include/stereo_b200.h: context, workspace, stage entry points and the
+// fused pipeline.  Host C++ driving CUDA; no torch types, no CPU fallback.
+#include <new>
+
+#include "common.cuh"
+
+char g_sb200_global_err[512] = {0};
+
+extern "C" {
+
+const char* sb200_version(void) { return "stereo_b200 0.1 (sm_100a)"; }
+
+void sb200_default_params(sb200_params* p) {
+    if (!p) return;
+    p->dmin = -15;
+    p->dmax = 0;
+    p->radius = 9;
+    p->d_lr = 0;
+    p->eps = 6.5025;
+    p->alpha = (float)0.9;
+    p->th_color = 7.0f;
+    p->th_grad = 2.0f;
+    p->r_w = 0.299;
+    p->g_w = 0.587;
+    p->b_w = 0.0721;
+    p->guide_mode = SB200_GUIDE_GRAY;
+    p->box_mode = SB200_BOX_SLIDING;
+}
+
+int sb200_ctx_create(int device, sb200_ctx** out) {
+    if (!out) return sb_fail(nullptr, SB200_ERR_INVALID, "ctx_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return sb_fail(nullptr, SB200_ERR_CUDA, "no CUDA device: %s (this library has no CPU fallback)",
+                       e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= ndev) return sb_fail(nullptr, SB200_ERR_INVALID, "device %d of %d", device, ndev);
+    SB_CUDA(nullptr, cudaSetDevice(device));
+    sb200_ctx* ctx = new (std::nothrow) sb200_ctx();
+    if (!ctx) return sb_fail(nullptr, SB200_ERR_NOMEM, "ctx alloc");
+    ctx->device = device;
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device);
+    ctx->sm_count = v > 0 ? v : 148;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    ctx->smem_optin = (size_t)v;
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    if (major != 10) {
+        delete ctx;
+        return sb_fail(nullptr, SB200_ERR_UNSUPPORTED, "device %d is sm_%d0; this library is built for sm_100a only", device,
+                       major);
+    }
+    bool ok = true;
+    for (int i = 0; i < 5; i++) ok = ok && (cudaEventCreate(&ctx->ev[i]) == cudaSuccess);
+    ctx->ev_valid = ok;
+    *out = ctx;
+    return SB200_OK;
+}
+
+void sb200_ctx_destroy(sb200_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->pin) cudaFreeHost(ctx->pin);
+    if (ctx->ev_valid)
+        for (int i = 0; i < 5; i++) cudaEventDestroy(ctx->ev[i]);
+    delete ctx;
+}
+
+int sb200_ctx_set_stream(sb200_ctx* ctx, void* stream) {
+    if (!ctx) return SB200_ERR_INVALID;
+    ctx->stream = (cudaStream_t)stream;
+    return SB200_OK;
+}
+
+int sb200_ctx_synchronize(sb200_ctx* ctx) {
+    if (!ctx) return SB200_ERR_INVALID;
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB200_OK;
+}
+
+const char* sb200_last_error(const sb200_ctx* ctx) { return ctx ? ctx->err : g_sb200_global_err; }
+uint64_t sb200_launch_count(const sb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int sb200_ctx_enable_timing(sb200_ctx* ctx, int on) {
+    if (!ctx) return SB200_ERR_INVALID;
+    ctx->timing = on;
+    return SB200_OK;
+}
+
+int sb200_last_timing(sb200_ctx* ctx, float* ms_prep, float* ms_fused, float* ms_merge, float* ms_occl) {
+    if (!ctx || !ctx->ev_valid) return SB200_ERR_INVALID;
+    SB_CUDA(ctx, cudaEventSynchronize(ctx->ev[4]));
+    float* outs[4] = {ms_prep, ms_fused, ms_merge, ms_occl};
+    for (int i = 0; i < 4; i++)
+        if (outs[i]) SB_CUDA(ctx, cudaEventElapsedTime(outs[i], ctx->ev[i], ctx->ev[i + 1]));
+    return SB200_OK;
+}
+
+}  // extern "C"
+
+int sb_ws_reserve(sb200_ctx* ctx, size_t bytes) {
+    SB_CUDA(ctx, cudaSetDevice(ctx->device));
+    bytes = sb_align(bytes, 1 << 20);
+    if (bytes > ctx->ws_cap) {
+        SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->ws) SB_CUDA(ctx, cudaFree(ctx->ws));
+        ctx->ws = nullptr;
+        ctx->ws_cap = 0;
+        cudaError_t e = cudaMalloc(&ctx->ws, bytes);
+        if (e != cudaSuccess) return sb_fail(ctx, SB200_ERR_NOMEM, "workspace of %zu bytes: %s", bytes, cudaGetErrorString(e));
+        ctx->ws_cap = bytes;
+    }
+    ctx->ws_off = 0;
+    return SB200_OK;
+}
+
+int sb_pin_reserve(sb200_ctx* ctx, size_t bytes) {
+    if (bytes > ctx->pin_cap) {
+        if (ctx->pin) SB_CUDA(ctx, cudaFreeHost(ctx->pin));
+        ctx->pin = nullptr;
+        ctx->pin_cap = 0;
+        SB_CUDA(ctx, cudaMallocHost(&ctx->pin, bytes));
+        ctx->pin_cap = bytes;
+    }
+    return SB200_OK;
+}
+
+namespace {
+
+#define REQUIRE(ctx, cond, msg)                                              \
+    do {                                                                     \
+        if (!(ctx)) return SB200_ERR_INVALID;                                \
+        if (!(cond)) return sb_fail(ctx, SB200_ERR_INVALID, "%s: %s", __func__, msg); \
+    } while (0)
+
+template <typename T>
+int ws_get(sb200_ctx* ctx, T** out, size_t count) {
+    *out = sb_ws_alloc<T>(ctx, count);
+    if (!*out) return sb_fail(ctx, SB200_ERR_NOMEM, "workspace arena exhausted (internal sizing bug)");
+    return SB200_OK;
+}
+
+int h2d(sb200_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    SB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return SB200_OK;
+}
+int d2h(sb200_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    SB_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return SB200_OK;
+}
+
+// box mean in the requested mode; scratch: tmp_f (n floats), sat (n floats), tmp_d (n doubles)
+struct BoxScratch {
+    float* tmp_f;
+    float* sat;
+    double* tmp_d;
+};
+int box_mean(sb200_ctx* ctx, const sb200_params* p, const float* in, float* out, int w, int h, const BoxScratch& s) {
+    if (p->box_mode == SB200_BOX_SAT) {
+        SB_TRY(sbk_integral(ctx, in, s.tmp_f, s.sat, w, h));
+        return sbk_box_from_sat(ctx, s.sat, out, w, h, p->radius);
+    }
+    return sbk_box_sliding(ctx, in, s.tmp_d, out, w, h, p->radius);
+}
+size_t box_scratch_bytes(size_t n) { return 2 * sb_align(n * 4) + sb_align(n * 8); }
+int box_scratch_get(sb200_ctx* ctx, BoxScratch* s, size_t n) {
+    SB_TRY(ws_get(ctx, &s->tmp_f, n));
+    SB_TRY(ws_get(ctx, &s->sat, n));
+    SB_TRY(ws_get(ctx, &s->tmp_d, n));
+    return SB200_OK;
+}
+
+// guide statistics as the live reference path computes them (guidedFilter.cu:58-123)
+int guide_stats(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_i, float* I, float* mean_I, float* var_I,
+                float* t0, float* t1, uint8_t* d_mean, int w, int h, const BoxScratch& bs) {
+    const size_t n = (size_t)w * h;
+    SB_TRY(sbk_u8_to_float(ctx, d_i, I, n));
+    SB_TRY(box_mean(ctx, p, I, mean_I, w, h, bs));
+    SB_TRY(sbk_mul(ctx, I, I, t0, n));
+    SB_TRY(box_mean(ctx, p, t0, t1, w, h, bs));
+    SB_TRY(sbk_mul(ctx, mean_I, mean_I, t0, n));
+    SB_TRY(sbk_sub(ctx, t1, t0, var_I, n));
+    if (d_mean) SB_TRY(sbk_float_to_u8(ctx, mean_I, d_mean, n));
+    return SB200_OK;
+}
+
+size_t gf_ws_bytes(size_t n) { return 12 * sb_align(n * 4) + box_scratch_bytes(n) + 4096; }
+
+// the body of sb200_compute_guided_filter_dev on an already reserved arena
+int guided_filter_staged(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_i, const float* d_cost, float* d_best,
+                         float* d_dmap, uint8_t* d_mean, int w, int h, int size_d, int dmin) {
+    const size_t n = (size_t)w * h;
+    float *I, *mean_I, *var_I, *t0, *t1, *mp, *mIp, *a, *b, *ma, *mb, *q;
+    SB_TRY(ws_get(ctx, &I, n));
+    SB_TRY(ws_get(ctx, &mean_I, n));
+    SB_TRY(ws_get(ctx, &var_I, n));
+    SB_TRY(ws_get(ctx, &t0, n));
+    SB_TRY(ws_get(ctx, &t1, n));
+    SB_TRY(ws_get(ctx, &mp, n));
+    SB_TRY(ws_get(ctx, &mIp, n));
+    SB_TRY(ws_get(ctx, &a, n));
+    SB_TRY(ws_get(ctx, &b, n));
+    SB_TRY(ws_get(ctx, &ma, n));
+    SB_TRY(ws_get(ctx, &mb, n));
+    SB_TRY(ws_get(ctx, &q, n));
+    BoxScratch bs;
+    SB_TRY(box_scratch_get(ctx, &bs, n));
+    SB_TRY(guide_stats(ctx, p, d_i, I, mean_I, var_I, t0, t1, d_mean, w, h, bs));
+    for (int s = 0; s < size_d; s++) {  // guidedFilter.cu:171-238
+        const float* pk = d_cost + (size_t)s * n;
+        SB_TRY(box_mean(ctx, p, pk, mp, w, h, bs));
+        SB_TRY(sbk_mul(ctx, I, pk, t0, n));
+        SB_TRY(box_mean(ctx, p, t0, mIp, w, h, bs));
+        SB_TRY(sbk_ak_bk(ctx, mean_I, var_I, mIp, mp, a, b, n, p->eps));
+        SB_TRY(box_mean(ctx, p, a, ma, w, h, bs));
+        SB_TRY(box_mean(ctx, p, b, mb, w, h, bs));
+        SB_TRY(sbk_q(ctx, I, ma, mb, q, n));
+        SB_TRY(sbk_disp_select(ctx, q, d_best, d_dmap, n, dmin + s));
+    }
+    return SB200_OK;
+}
+
+int check_params(sb200_ctx* ctx, const sb200_params* p) {
+    if (!ctx) return SB200_ERR_INVALID;
+    if (!p) return sb_fail(ctx, SB200_ERR_INVALID, "params is NULL");
+    if (p->dmax < p->dmin) return sb_fail(ctx, SB200_ERR_INVALID, "dmax < dmin");
+    if (p->radius < 1 || p->radius > 64) return sb_fail(ctx, SB200_ERR_INVALID, "radius out of range");
+    if (p->box_mode != SB200_BOX_SLIDING && p->box_mode != SB200_BOX_SAT) return sb_fail(ctx, SB200_ERR_INVALID, "box_mode");
+    return SB200_OK;
+}
+
+// pipeline core on device buffers; `held` geometry for strips
+int pipeline_core(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, const uint8_t* d_right, int channels,
+                  int w, const SbFusedGeom& g, const sb200_outputs* o, bool reserve) {
+    const int size_d = p->dmax - p->dmin + 1;
+    const size_t n_held = (size_t)w * g.h;
+    const size_t n_out = (size_t)w * g.rows_out;
+    const int dabs = max(abs(p->dmin), abs(p->dmax));
+    if (reserve) {
+        size_t bytes = sbf_workspace_bytes(ctx, w, g.h, g.rows_out, dabs, size_d, 2);
+        bytes += 2 * sb_align(n_held) + 4 * sb_align(n_out * 4) + 4096;
+        SB_TRY(sb_ws_reserve(ctx, bytes));
+    }
+    const bool full = (g.rows_out == g.h);
+    const uint8_t* gl = d_left;
+    const uint8_t* gr = d_right;
+    if (channels != 1) {
+        uint8_t *tl, *tr;
+        // gray outputs cover output rows only; write straight into them when the frame is whole
+        if (full && o->gray_left) tl = o->gray_left; else SB_TRY(ws_get(ctx, &tl, n_held));
+        if (full && o->gray_right) tr = o->gray_right; else SB_TRY(ws_get(ctx, &tr, n_held));
+        SB_TRY(sbk_rgb_to_gray(ctx, p, d_left, (int)n_held, channels, tl));
+        SB_TRY(sbk_rgb_to_gray(ctx, p, d_right, (int)n_held, channels, tr));
+        gl = tl;
+        gr = tr;
+    }
+    const size_t out_off = (size_t)g.y_out0 * w;
+    if (!(full && channels != 1)) {
+        if (o->gray_left) SB_CUDA(ctx, cudaMemcpyAsync(o->gray_left, gl + out_off, n_out, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (o->gray_right) SB_CUDA(ctx, cudaMemcpyAsync(o->gray_right, gr + out_off, n_out, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    float *dL = o->disp_left, *dR = o->disp_right;
+    if (!dL) SB_TRY(ws_get(ctx, &dL, n_out));
+    if (!dR) SB_TRY(ws_get(ctx, &dR, n_out));
+    uint8_t* mL = o->mean_left;
+    uint8_t* mR = o->mean_right;
+    uint8_t *mLh = nullptr, *mRh = nullptr;
+    if (!full) {  // mean images are produced on held rows; stage and crop
+        if (mL) SB_TRY(ws_get(ctx, &mLh, n_held));
+        if (mR) SB_TRY(ws_get(ctx, &mRh, n_held));
+    }
+    SB_TRY(sbf_pair_disparity(ctx, p, gl, gr, g, o->best_left, dL, o->best_right, dR, full ? mL : mLh, full ? mR : mRh));
+    if (!full) {
+        if (mL) SB_CUDA(ctx, cudaMemcpyAsync(mL, mLh + out_off, n_out, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (mR) SB_CUDA(ctx, cudaMemcpyAsync(mR, mRh + out_off, n_out, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    if (o->occlusion || o->filled)
+        SB_TRY(sbk_lr_check_fill(ctx, dL, dR, w, g.rows_out, p->dmin - 100, p->d_lr, (float)p->dmin, o->occlusion,
+                                 o->filled));
+    if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+    return SB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- device-pointer stage entry points -------------------------------------------------
+int sb200_rgb_to_grayscale_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_rgb, int n, int channels,
+                               uint8_t* d_gray) {
+    SB_TRY(check_params(ctx, p));
+    REQUIRE(ctx, d_rgb && d_gray && n > 0, "null pointer or n <= 0");
+    REQUIRE(ctx, channels >= 3, "channels must be >= 3 (the reference reads image[ch*i+{0,1,2}])");
+    return sbk_rgb_to_gray(ctx, p, d_rgb, n, channels, d_gray);
+}
+
+int sb200_compute_cost_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_i1, const uint8_t* d_i2,
+                           float* d_cost, int w, int h, int dmin) {
+    SB_TRY(check_params(ctx, p));
+    REQUIRE(ctx, d_i1 && d_i2 && d_cost && w > 0 && h > 0, "null pointer or empty image");
+    const size_t n = (size_t)w * h;
+    SB_TRY(sb_ws_reserve(ctx, 2 * sb_align(n * 4) + 4096));
+    float *g1, *g2;
+    SB_TRY(ws_get(ctx, &g1, n));
+    SB_TRY(ws_get(ctx, &g2, n));
+    SB_TRY(sbk_x_derivative(ctx, d_i1, g1, w, h));
+    SB_TRY(sbk_x_derivative(ctx, d_i2, g2, w, h));
+    return sbk_cost_volume(ctx, p, d_i1, d_i2, g1, g2, d_cost, w, h, p->dmax - p->dmin + 1, dmin);
+}
+
+int sb200_integral_dev(sb200_ctx* ctx, const float* d_image, float* d_integral, int w, int h) {
+    REQUIRE(ctx, d_image && d_integral && w > 0 && h > 0, "null pointer or empty image");
+    const size_t n = (size_t)w * h;
+    SB_TRY(sb_ws_reserve(ctx, sb_align(n * 4) + 4096));
+    float* tmp;
+    SB_TRY(ws_get(ctx, &tmp, n));
+    return sbk_integral(ctx, d_image, tmp, d_integral, w, h);
+}
+
+int sb200_box_filter_dev(sb200_ctx* ctx, const sb200_params* p, const float* d_image, float* d_mean, int w, int h) {
+    SB_TRY(check_params(ctx, p));
+    REQUIRE(ctx, d_image && d_mean && w > 0 && h > 0, "null pointer or empty image");
+    const size_t n = (size_t)w * h;
+    SB_TRY(sb_ws_reserve(ctx, box_scratch_bytes(n) + 4096));
+    BoxScratch bs;
+    SB_TRY(box_scratch_get(ctx, &bs, n));
+    return box_mean(ctx, p, d_image, d_mean, w, h, bs);
+}
+
+int sb200_compute_guided_filter_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_i, const float* d_cost,
+                                    float* d_filter_cost, float* d_disp_map, uint8_t* d_mean, int w, int h,
+                                    int size_d, int dmin) {
+    SB_TRY(check_params(ctx, p));
+    REQUIRE(ctx, d_i && d_cost && d_filter_cost && d_disp_map && w > 0 && h > 0 && size_d > 0, "null pointer or empty");
+    SB_TRY(sb_ws_reserve(ctx, gf_ws_bytes((size_t)w * h)));
+    return guided_filter_staged(ctx, p, d_i, d_cost, d_filter_cost, d_disp_map, d_mean, w, h, size_d, dmin);
+}
+
+int sb200_winner_take_all_dev(sb200_ctx* ctx, const float* d_q, float* d_filter_cost, float* d_dmap, int n, int label) {
+    REQUIRE(ctx, d_q && d_filter_cost && d_dmap && n > 0, "null pointer or n <= 0");
+    return sbk_disp_select(ctx, d_q, d_filter_cost, d_dmap, (size_t)n, label);
+}
+
+int sb200_detect_occlusion_dev(sb200_ctx* ctx, const sb200_params* p, float* d_dL, const float* d_dR, int dOcclusion,
+                               int w, int h) {
+    SB_TRY(check_params(ctx, p));
+    REQUIRE(ctx, d_dL && d_dR && w > 0 && h > 0, "null pointer or empty image");
+    return sbk_detect_occlusion(ctx, d_dL, d_dR, dOcclusion, p->d_lr, w, h);
+}
+
+int sb200_fill_occlusion_dev(sb200_ctx* ctx, float* d_disparity, int w, int h, float vMin) {
+    REQUIRE(ctx, d_disparity && w > 0 && h > 0, "null pointer or empty image");
+    return sbk_fill_occlusion(ctx, d_disparity, w, h, vMin);
+}
+
+int sb200_lr_check_fill_dev(sb200_ctx* ctx, const sb200_params* p, const float* d_dL, const float* d_dR, int w, int h,
+                            int dOcclusion, float vMin, float* d_occlusion, float* d_filled) {
+    SB_TRY(check_params(ctx, p));
+    REQUIRE(ctx, d_dL && d_dR && w > 0 && h > 0 && (d_occlusion || d_filled), "null pointer or empty image");
+    return sbk_lr_check_fill(ctx, d_dL, d_dR, w, h, dOcclusion, p->d_lr, vMin, d_occlusion, d_filled);
+}
+
+int sb200_view_disparity_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_guide, const uint8_t* d_other,
+                             int w, int h, int dmin, int size_d, float* d_best, float* d_disp, uint8_t* d_mean) {
+    SB_TRY(check_params(ctx, p));
+    REQUIRE(ctx, d_guide && d_other && w > 1 && h > 0 && size_d > 0 && (d_best || d_disp), "null pointer or empty");
+    const int dabs = max(abs(dmin), abs(dmin + size_d - 1));
+    SB_TRY(sb_ws_reserve(ctx, sbf_workspace_bytes(ctx, w, h, h, dabs, size_d, 1)));
+    SbFusedGeom g{w, h, 0, h, 0, h};
+    if (ctx->timing && ctx->ev_valid) {
+        int rc = sbf_view_disparity(ctx, p, d_guide, d_other, g, dmin, size_d, d_best, d_disp, d_mean);
+        if (rc == SB200_OK) SB_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
+        return rc;
+    }
+    return sbf_view_disparity(ctx, p, d_guide, d_other, g, dmin, size_d, d_best, d_disp, d_mean);
+}
+
+// ---- fused pipeline ---------------------------------------------------------------------
+int sb200_strip_halo_rows(const sb200_params* p) { return p ? 2 * p->radius : 0; }
+
+int sb200_pipeline_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, const uint8_t* d_right,
+                       int channels, int w, int h, const sb200_outputs* d_out) {
+    SB_TRY(check_params(ctx, p));
+    REQUIRE(ctx, d_left && d_right && d_out && w > 1 && h > 0, "null pointer or empty image");
+    REQUIRE(ctx, channels == 1 || channels >= 3, "channels must be 1 (gray) or >= 3");
+    SbFusedGeom g{w, h, 0, h, 0, h};
+    return pipeline_core(ctx, p, d_left, d_right, channels, w, g, d_out, true);
+}
+
+int sb200_pipeline_strip_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, const uint8_t* d_right,
+                             int channels, int w, const sb200_strip* s, const sb200_outputs* d_out) {
+    SB_TRY(check_params(ctx, p));
+    REQUIRE(ctx, d_left && d_right && d_out && s && w > 1, "null pointer or empty image");
+    REQUIRE(ctx, channels == 1 || channels >= 3, "channels must be 1 (gray) or >= 3");
+    REQUIRE(ctx, s->rows > 0 && s->halo_top >= 0 && s->halo_bot >= 0 && s->y0 >= s->halo_top &&
+                     s->y0 + s->rows + s->halo_bot <= s->frame_h,
+            "strip geometry outside the frame");
+    const int need = 2 * p->radius;
+    REQUIRE(ctx, s->halo_top >= (s->y0 < need ? s->y0 : need), "halo_top smaller than min(y0, 2*radius)");
+    const int below = s->frame_h - (s->y0 + s->rows);
+    REQUIRE(ctx, s->halo_bot >= (below < need ? below : need), "halo_bot smaller than min(rows below, 2*radius)");
+    SbFusedGeom g{w, s->halo_top + s->rows + s->halo_bot, s->halo_top, s->rows, s->y0 - s->halo_top, s->frame_h};
+    return pipeline_core(ctx, p, d_left, d_right, channels, w, g, d_out, true);
+}
+
+int sb200_pipeline_batch_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, const uint8_t* d_right,
+                             int channels, int w, int h, int n_pairs, const sb200_outputs* d_out) {
+    SB_TRY(check_params(ctx, p));
+    REQUIRE(ctx, d_left && d_right && d_out && w > 1 && h > 0 && n_pairs > 0, "null pointer or empty batch");
+    REQUIRE(ctx, channels == 1 || channels >= 3, "channels must be 1 (gray) or >= 3");
+    const size_t n = (size_t)w * h;
+    SbFusedGeom g{w, h, 0, h, 0, h};
+    for (int i = 0; i < n_pairs; i++) {
+        sb200_outputs o = *d_out;
+        float** fp[] = {&o.disp_left, &o.disp_right, &o.occlusion, &o.filled, &o.best_left, &o.best_right};
+        for (float** f : fp)
+            if (*f) *f += (size_t)i * n;
+        uint8_t** up[] = {&o.gray_left, &o.gray_right, &o.mean_left, &o.mean_right};
+        for (uint8_t** u : up)
+            if (*u) *u += (size_t)i * n;
+        // pairs run back to back on one stream and share the arena: stream order makes reuse safe
+        SB_TRY(pipeline_core(ctx, p, d_left + (size_t)i * n * channels, d_right + (size_t)i * n * channels, channels, w, g,
+                             &o, true));
+    }
+    return SB200_OK;
+}
+
+int sb200_pipeline(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h_left, const uint8_t* h_right, int channels,
+                   int w, int h, const sb200_outputs* h_out) {
+    SB_TRY(check_params(ctx, p));
+    REQUIRE(ctx, h_left && h_right && h_out && w > 1 && h > 0, "null pointer or empty image");
+    REQUIRE(ctx, channels == 1 || channels >= 3, "channels must be 1 (gray) or >= 3");
+    const size_t n = (size_t)w * h;
+    const int size_d = p->dmax - p->dmin + 1;
+    const int dabs = max(abs(p->dmin), abs(p->dmax));
+    size_t bytes = sbf_workspace_bytes(ctx, w, h, h, dabs, size_d, 2) + 2 * sb_align(n) + 4 * sb_align(n * 4) + 4096;
+    bytes += 2 * sb_align(n * channels) + 6 * sb_align(n * 4) + 4 * sb_align(n) + 4096;
+    SB_TRY(sb_ws_reserve(ctx, bytes));
+    uint8_t *dl, *dr;
+    SB_TRY(ws_get(ctx, &dl, n * channels));
+    SB_TRY(ws_get(ctx, &dr, n * channels));
+    SB_TRY(h2d(ctx, dl, h_left, n * channels));
+    SB_TRY(h2d(ctx, dr, h_right, n * channels));
+    sb200_outputs d{};
+    float* const hf[] = {h_out->disp_left, h_out->disp_right, h_out->occlusion, h_out->filled, h_out->best_left, h_out->best_right};
+    float** const df[] = {&d.disp_left, &d.disp_right, &d.occlusion, &d.filled, &d.best_left, &d.best_right};
+    for (int i = 0; i < 6; i++)
+        if (hf[i]) SB_TRY(ws_get(ctx, df[i], n));
+    uint8_t* const hu[] = {h_out->gray_left, h_out->gray_right, h_out->mean_left, h_out->mean_right};
+    uint8_t** const du[] = {&d.gray_left, &d.gray_right, &d.mean_left, &d.mean_right};
+    for (int i = 0; i < 4; i++)
+        if (hu[i]) SB_TRY(ws_get(ctx, du[i], n));
+    SbFusedGeom g{w, h, 0, h, 0, h};
+    SB_TRY(pipeline_core(ctx, p, dl, dr, channels, w, g, &d, false));
+    for (int i = 0; i < 6; i++)
+        if (hf[i]) SB_TRY(d2h(ctx, hf[i], *df[i], n * 4));
+    for (int i = 0; i < 4; i++)
+        if (hu[i]) SB_TRY(d2h(ctx, hu[i], *du[i], n));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB200_OK;
+}
+
+// ---- host-pointer stage entry points (blocking, reference calling convention) -------------
+int sb200_rgb_to_grayscale(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h_rgb, int n, int channels,
+                           uint8_t* h_gray) {
+    SB_TRY(check_params(ctx, p));
+    REQUIRE(ctx, h_rgb && h_gray && n > 0, "null pointer or n <= 0");
+    REQUIRE(ctx, channels >= 3, "channels must be >= 3 (the reference reads image[ch*i+{0,1,2}])");
+    SB_TRY(sb_ws_reserve(ctx, sb_align((size_t)n * channels) + sb_align(n) + 4096));
+    uint8_t *d_rgb, *d_gray;
+    SB_TRY(ws_get(ctx, &d_rgb, (size_t)n * channels));
+    SB_TRY(ws_get(ctx, &d_gray, (size_t)n));
+    SB_TRY(h2d(ctx, d_rgb, h_rgb, (size_t)n * channels));
+    SB_TRY(sbk_rgb_to_gray(ctx, p, d_rgb, n, channels, d_gray));
+    SB_TRY(d2h(ctx, h_gray, d_gray, n));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB200_OK;
+}
+
+int sb200_x_derivative(sb200_ctx* ctx, const uint8_t* img, float* grad, int w, int h) {
+    REQUIRE(ctx, img && grad && w > 0 && h > 0, "null pointer or empty image");
+    const size_t n = (size_t)w * h;
+    SB_TRY(sb_ws_reserve(ctx, sb_align(n) + sb_align(n * 4) + 4096));
+    uint8_t* d_i;
+    float* d_g;
+    SB_TRY(ws_get(ctx, &d_i, n));
+    SB_TRY(ws_get(ctx, &d_g, n));
+    SB_TRY(h2d(ctx, d_i, img, n));
+    SB_TRY(sbk_x_derivative(ctx, d_i, d_g, w, h));
+    SB_TRY(d2h(ctx, grad, d_g, n * 4));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB200_OK;
+}
+
+int sb200_compute_cost(sb200_ctx* ctx, const sb200_params* p, const uint8_t* i1, const uint8_t* i2, float* cost, int w1,
+                       int w2, int h1, int h2, int dmin) {
+    SB_TRY(check_params(ctx, p));
+    REQUIRE(ctx, i1 && i2 && cost && w1 > 0 && h1 > 0, "null pointer or empty image");
+    REQUIRE(ctx, w1 == w2 && h1 == h2, "the two images must have the same size (costVolume.cu assumes it)");
+    const size_t n = (size_t)w1 * h1;
+    const int size_d = p->dmax - p->dmin + 1;
+    SB_TRY(sb_ws_reserve(ctx, 2 * sb_align(n) + 2 * sb_align(n * 4) + sb_align(n * size_d * 4) + 4096));
+    uint8_t *d1, *d2;
+    float *g1, *g2, *dc;
+    SB_TRY(ws_get(ctx, &d1, n));
+    SB_TRY(ws_get(ctx, &d2, n));
+    SB_TRY(ws_get(ctx, &g1, n));
+    SB_TRY(ws_get(ctx, &g2, n));
+    SB_TRY(ws_get(ctx, &dc, n * size_d));
+    SB_TRY(h2d(ctx, d1, i1, n));
+    SB_TRY(h2d(ctx, d2, i2, n));
+    SB_TRY(sbk_x_derivative(ctx, d1, g1, w1, h1));
+    SB_TRY(sbk_x_derivative(ctx, d2, g2, w1, h1));
+    SB_TRY(sbk_cost_volume(ctx, p, d1, d2, g1, g2, dc, w1, h1, size_d, dmin));
+    SB_TRY(d2h(ctx, cost, dc, n * size_d * 4));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB200_OK;
+}
+
+int sb200_integral(sb200_ctx* ctx, const float* image, float* integral, int width, int height) {
+    REQUIRE(ctx, image && integral && width > 0 && height > 0, "null pointer or empty image");
+    const size_t n = (size_t)width * height;
+    SB_TRY(sb_ws_reserve(ctx, 3 * sb_align(n * 4) + 4096));
+    float *d_in, *d_tmp, *d_out;
+    SB_TRY(ws_get(ctx, &d_in, n));
+    SB_TRY(ws_get(ctx, &d_tmp, n));
+    SB_TRY(ws_get(ctx, &d_out, n));
+    SB_TRY(h2d(ctx, d_in, image, n * 4));
+    SB_TRY(sbk_integral(ctx, d_in, d_tmp, d_out, width, height));
+    SB_TRY(d2h(ctx, integral, d_out, n * 4));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB200_OK;
+}
+
+int sb200_box_filter_sat(sb200_ctx* ctx, const sb200_params* p, const float* integral, float* mean, int w, int h) {
+    SB_TRY(check_params(ctx, p));
+    REQUIRE(ctx, integral && mean && w > 0 && h > 0, "null pointer or empty image");
+    const size_t n = (size_t)w * h;
+    SB_TRY(sb_ws_reserve(ctx, 2 * sb_align(n * 4) + 4096));
+    float *d_s, *d_m;
+    SB_TRY(ws_get(ctx, &d_s, n));
+    SB_TRY(ws_get(ctx, &d_m, n));
+    SB_TRY(h2d(ctx, d_s, integral, n * 4));
+    SB_TRY(sbk_box_from_sat(ctx, d_s, d_m, w, h, p->radius));
+    SB_TRY(d2h(ctx, mean, d_m, n * 4));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB200_OK;
+}
+
+int sb200_box_filter(sb200_ctx* ctx, const sb200_params* p, const float* image, float* mean, int w, int h) {
+    SB_TRY(check_params(ctx, p));
+    REQUIRE(ctx, image && mean && w > 0 && h > 0, "null pointer or empty image");
+    const size_t n = (size_t)w * h;
+    SB_TRY(sb_ws_reserve(ctx, 2 * sb_align(n * 4) + box_scratch_bytes(n) + 4096));
+    float *d_i, *d_m;
+    SB_TRY(ws_get(ctx, &d_i, n));
+    SB_TRY(ws_get(ctx, &d_m, n));
+    BoxScratch bs;
+    SB_TRY(box_scratch_get(ctx, &bs, n));
+    SB_TRY(h2d(ctx, d_i, image, n * 4));
+    SB_TRY(box_mean(ctx, p, d_i, d_m, w, h, bs));
+    SB_TRY(d2h(ctx, mean, d_m, n * 4));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB200_OK;
+}
+
+int sb200_filter(sb200_ctx* ctx, const sb200_params* p, const uint8_t* image, int width, int height, uint8_t* mean,
+                 float* var) {
+    SB_TRY(check_params(ctx, p));
+    REQUIRE(ctx, image && (mean || var) && width > 0 && height > 0, "null pointer or empty image");
+    const size_t n = (size_t)width * height;
+    SB_TRY(sb_ws_reserve(ctx, 2 * sb_align(n) + 5 * sb_align(n * 4) + box_scratch_bytes(n) + 4096));
+    uint8_t *d_i, *d_m;
+    float *I, *mean_I, *var_I, *t0, *t1;
+    SB_TRY(ws_get(ctx, &d_i, n));
+    SB_TRY(ws_get(ctx, &d_m, n));
+    SB_TRY(ws_get(ctx, &I, n));
+    SB_TRY(ws_get(ctx, &mean_I, n));
+    SB_TRY(ws_get(ctx, &var_I, n));
+    SB_TRY(ws_get(ctx, &t0, n));
+    SB_TRY(ws_get(ctx, &t1, n));
+    BoxScratch bs;
+    SB_TRY(box_scratch_get(ctx, &bs, n));
+    SB_TRY(h2d(ctx, d_i, image, n));
+    SB_TRY(guide_stats(ctx, p, d_i, I, mean_I, var_I, t0, t1, d_m, width, height, bs));
+    if (mean) SB_TRY(d2h(ctx, mean, d_m, n));
+    if (var) SB_TRY(d2h(ctx, var, var_I, n * 4));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB200_OK;
+}
+
+int sb200_compute_guided_filter(sb200_ctx* ctx, const sb200_params* p, const uint8_t* i, const float* cost,
+                                float* filter_cost, float* disp_map, uint8_t* mean, int w, int h, int size_d, int dmin) {
+    SB_TRY(check_params(ctx, p));
+    REQUIRE(ctx, i && cost && filter_cost && disp_map && w > 0 && h > 0 && size_d > 0, "null pointer or empty");
+    const size_t n = (size_t)w * h;
+    SB_TRY(sb_ws_reserve(ctx, gf_ws_bytes(n) + 2 * sb_align(n) + 2 * sb_align(n * 4) + sb_align(n * size_d * 4) + 4096));
+    uint8_t *d_i, *d_m;
+    float *d_c, *d_b, *d_d;
+    SB_TRY(ws_get(ctx, &d_i, n));
+    SB_TRY(ws_get(ctx, &d_m, n));
+    SB_TRY(ws_get(ctx, &d_c, n * size_d));
+    SB_TRY(ws_get(ctx, &d_b, n));
+    SB_TRY(ws_get(ctx, &d_d, n));
+    SB_TRY(h2d(ctx, d_i, i, n));
+    SB_TRY(h2d(ctx, d_c, cost, n * size_d * 4));
+    SB_TRY(h2d(ctx, d_b, filter_cost, n * 4));
+    SB_TRY(h2d(ctx, d_d, disp_map, n * 4));
+    SB_TRY(guided_filter_staged(ctx, p, d_i, d_c, d_b, d_d, d_m, w, h, size_d, dmin));
+    SB_TRY(d2h(ctx, filter_cost, d_b, n * 4));
+    SB_TRY(d2h(ctx, disp_map, d_d, n * 4));
+    if (mean) SB_TRY(d2h(ctx, mean, d_m, n));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB200_OK;
+}
+
+int sb200_winner_take_all(sb200_ctx* ctx, const float* q, float* filter_cost, float* dmap, int n, int label) {
+    REQUIRE(ctx, q && filter_cost && dmap && n > 0, "null pointer or n <= 0");
+    const size_t nn = (size_t)n;
+    SB_TRY(sb_ws_reserve(ctx, 3 * sb_align(nn * 4) + 4096));
+    float *d_q, *d_b, *d_d;
+    SB_TRY(ws_get(ctx, &d_q, nn));
+    SB_TRY(ws_get(ctx, &d_b, nn));
+    SB_TRY(ws_get(ctx, &d_d, nn));
+    SB_TRY(h2d(ctx, d_q, q, nn * 4));
+    SB_TRY(h2d(ctx, d_b, filter_cost, nn * 4));
+    SB_TRY(h2d(ctx, d_d, dmap, nn * 4));
+    SB_TRY(sbk_disp_select(ctx, d_q, d_b, d_d, nn, label));
+    SB_TRY(d2h(ctx, filter_cost, d_b, nn * 4));
+    SB_TRY(d2h(ctx, dmap, d_d, nn * 4));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB200_OK;
+}
+
+int sb200_detect_occlusion(sb200_ctx* ctx, const sb200_params* p, float* disparityLeft, const float* disparityRight,
+                           int dOcclusion, uint8_t* dmapl, uint8_t* dmapr, int w, int h) {
+    (void)dmapl;  // passed through untouched by the reference (occlusion.cu:40-41,55-56)
+    (void)dmapr;
+    SB_TRY(check_params(ctx, p));
+    REQUIRE(ctx, disparityLeft && disparityRight && w > 0 && h > 0, "null pointer or empty image");
+    const size_t n = (size_t)w * h;
+    SB_TRY(sb_ws_reserve(ctx, 2 * sb_align(n * 4) + 4096));
+    float *d_l, *d_r;
+    SB_TRY(ws_get(ctx, &d_l, n));
+    SB_TRY(ws_get(ctx, &d_r, n));
+    SB_TRY(h2d(ctx, d_l, disparityLeft, n * 4));
+    SB_TRY(h2d(ctx, d_r, disparityRight, n * 4));
+    SB_TRY(sbk_detect_occlusion(ctx, d_l, d_r, dOcclusion, p->d_lr, w, h));
+    SB_TRY(d2h(ctx, disparityLeft, d_l, n * 4));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB200_OK;
+}
+
+int sb200_fill_occlusion(sb200_ctx* ctx, float* disparity, int w, int h, float vMin) {
+    REQUIRE(ctx, disparity && w > 0 && h > 0, "null pointer or empty image");
+    const size_t n = (size_t)w * h;
+    SB_TRY(sb_ws_reserve(ctx, sb_align(n * 4) + 4096));
+    float* d_d;
+    SB_TRY(ws_get(ctx, &d_d, n));
+    SB_TRY(h2d(ctx, d_d, disparity, n * 4));
+    SB_TRY(sbk_fill_occlusion(ctx, d_d, w, h, vMin));
+    SB_TRY(d2h(ctx, disparity, d_d, n * 4));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+// common.cuh -- context, workspace arena and launch helpers shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/stereo_b200.h"
+
+struct sb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    // workspace arena: one device allocation, bump-allocated per entry point, grown on demand
+    char* ws = nullptr;
+    size_t ws_cap = 0;
+    size_t ws_off = 0;
+    // pinned staging for the host-pointer entry points
+    char* pin = nullptr;
+    size_t pin_cap = 0;
+    uint64_t launches = 0;
+    char err[512] = {0};
+    // optional timing of the pipeline's phases
+    int timing = 0;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_valid = false;
+    bool fused_attr_set = false;
+};
+
+extern char g_sb200_global_err[512];
+
+inline int sb_fail(sb200_ctx* ctx, int code, const char* fmt, ...) {
+    char* dst = ctx ? ctx->err : g_sb200_global_err;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define SB_CUDA(ctx, call)                                                                          \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return sb_fail(ctx, SB200_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,        \
+                           cudaGetErrorString(e__));                                                \
+    } while (0)
+
+#define SB_TRY(expr)                    \
+    do {                                \
+        int rc__ = (expr);              \
+        if (rc__ != SB200_OK) return rc__; \
+    } while (0)
+
+// launch + count + immediate launch-error check (asynchronous execution errors surface at
+// the next synchronising call, which also goes through SB_CUDA)
+#define SB_LAUNCH(ctx, kernel, grid, block, smem, ...)                                              \
+    do {                                                                                            \
+        kernel<<<grid, block, smem, (ctx)->stream>>>(__VA_ARGS__);                                   \
+        (ctx)->launches++;                                                                          \
+        cudaError_t e__ = cudaGetLastError();                                                       \
+        if (e__ != cudaSuccess)                                                                     \
+            return sb_fail(ctx, SB200_ERR_CUDA, "%s:%d launch %s -> %s", __FILE__, __LINE__,        \
+                           #kernel, cudaGetErrorString(e__));                                       \
+    } while (0)
+
+inline size_t sb_align(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// Make sure the arena holds `bytes`; resets the bump pointer.  Growing synchronises the
+// stream (only happens while shapes are still growing).
+int sb_ws_reserve(sb200_ctx* ctx, size_t bytes);
+template <typename T>
+inline T* sb_ws_alloc(sb200_ctx* ctx, size_t count) {
+    size_t off = sb_align(ctx->ws_off);
+    size_t end = off + count * sizeof(T);
+    if (end > ctx->ws_cap) return nullptr;
+    ctx->ws_off = end;
+    return reinterpret_cast<T*>(ctx->ws + off);
+}
+int sb_pin_reserve(sb200_ctx* ctx, size_t bytes);
+
+inline int sb_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- stage kernels (stage_kernels.cu) ------------------------------------------------
+int sbk_rgb_to_gray(sb200_ctx* ctx, const sb200_params* p, const uint8_t* rgb, int n, int ch, uint8_t* gray);
+int sbk_x_derivative(sb200_ctx* ctx, const uint8_t* img, float* grad, int w, int h);
+int sbk_cost_volume(sb200_ctx* ctx, const sb200_params* p, const uint8_t* i1, const uint8_t* i2, const float* g1,
+                    const float* g2, float* cost, int w, int h, int size_d, int dmin);
+int sbk_integral(sb200_ctx* ctx, const float* in, float* tmp, float* out, int w, int h);
+int sbk_box_from_sat(sb200_ctx* ctx, const float* sat, float* mean, int w, int h, int r);
+int sbk_box_sliding(sb200_ctx* ctx, const float* in, double* tmp, float* mean, int w, int h, int r);
+int sbk_u8_to_float(sb200_ctx* ctx, const uint8_t* in, float* out, size_t n);
+int sbk_float_to_u8(sb200_ctx* ctx, const float* in, uint8_t* out, size_t n);
+int sbk_mul(sb200_ctx* ctx, const float* a, const float* b, float* out, size_t n);
+int sbk_sub(sb200_ctx* ctx, const float* a, const float* b, float* out, size_t n);
+int sbk_ak_bk(sb200_ctx* ctx, const float* mean, const float* var, const float* mIp, const float* mp, float* a,
+              float* b, size_t n, double eps);
+int sbk_q(sb200_ctx* ctx, const float* im, const float* a, const float* b, float* q, size_t n);
+int sbk_disp_select(sb200_ctx* ctx, const float* q, float* best, float* dmap, size_t n, int label);
+int sbk_detect_occlusion(sb200_ctx* ctx, float* dL, const float* dR, int dOcc, int d_lr, int w, int h);
+int sbk_fill_occlusion(sb200_ctx* ctx, float* disp, int w, int h, float vMin);
+int sbk_lr_check_fill(sb200_ctx* ctx, const float* dL, const float* dR, int w, int h, int dOcc, int d_lr, float vMin,
+                      float* occ, float* filled);
+int sbk_fill_f32(sb200_ctx* ctx, float* dst, float v, size_t n);
+
+// ---- fused path (fused_cvf.cu) --------------------------------------------------------
+struct SbFusedGeom {
+    int w, h;         // image width, rows held in the input buffers
+    int y_out0;       // first output row (index into the held rows)
+    int rows_out;     // number of output rows
+    int y_global0;    // frame row index of held row 0 (for clipped window areas)
+    int frame_h;      // rows of the whole frame
+};
+size_t sbf_workspace_bytes(const sb200_ctx* ctx, int w, int h_held, int rows_out, int dabs, int size_d, int n_views);
+// gray images (held rows) -> per-view best cost + labels (+ mean debug image) for BOTH views
+int sbf_pair_disparity(sb200_ctx* ctx, const sb200_params* p, const uint8_t* gray_l, const uint8_t* gray_r,
+                       const SbFusedGeom& g, float* bestL, float* dispL, float* bestR, float* dispR,
+                       uint8_t* meanL, uint8_t* meanR);
+// single view (guide, other, dmin)
+int sbf_view_disparity(sb200_ctx* ctx, const sb200_params* p, const uint8_t* guide, const uint8_t* other,
+                       const SbFusedGeom& g, int dmin, int size_d, float* best, float* disp, uint8_t* mean);

@@ -1,0 +1,657 @@
+// fused_cvf.cu -- the hot path: cost volume + guided-filter aggregation + running argmin in
+// one kernel, for both views of a pair, without ever materialising the D-deep volume.
+//
+// Replaces, per disparity slice, the reference's chain:
+//   costVolumOnGPU2 (costVolume.cu:163-190) -> copyFromBigToLittleOnGPU -> pixelMultOnGPU ->
+//   4x { rowSum + colSum (integral.cu:78-131) + computeBoxFilterOnGPU (guidedFilter.cu:297-318) }
+//   -> compute_ak_and_bk (:345-354) -> compute_q (:363-369) -> dispSelectOnGPU (:403-411)
+// and, per frame, chToFlOnGPU / the two guide-statistics box filters (guidedFilter.cu:58-123).
+//
+// Design (DESIGN.md has the long form):
+//  * A warp owns a strip of 256 image columns (8 consecutive pixels per lane) for ONE
+//    disparity and marches down the rows.  Vertical 19-row window sums are running sums in
+//    registers; the value that leaves the window comes from a 19-slot ring in shared memory
+//    that only this warp touches (no block barrier on the filter path).
+//  * Horizontal 19-column window sums never go through shared memory: each lane forms the
+//    prefix sums of its 8 pixels and the window is assembled from 16 warp shuffles of
+//    neighbouring lanes' prefixes.  216 of the 256 columns are valid after two cascaded
+//    radius-9 filters (20-column halo each side, kept 4-pixel aligned for 128-bit loads).
+//  * The cost is evaluated on an integer lattice: 20*p = 2*min(|dI|,7) + 9*min(|dG|,4) with
+//    G = 2*gradient, so the first-stage box sums of p and I*p are sums of integers below 2^24
+//    held in fp32 -- exact, order independent, identical on every tiling or GPU split.
+//  * The 4 warps of a block take 4 consecutive disparities in lockstep, exchange their
+//    filtered row through a 1 KB shared buffer and one thread per 2 columns folds them into
+//    the running (best, label) with the reference's `best >= q` rule (last slice wins ties).
+//  * Blocks tile (column strip x row band x disparity chunk x view); per-chunk (best,label)
+//    planes are merged in chunk order by a small second kernel.
+// HBM traffic is ~30 B per PIXEL per disparity group read from L2-resident prepared planes;
+// the kernel is bound by the FP32/ALU issue rate and the shuffle/LSU path, not by HBM.
+#include "common.cuh"
+
+namespace {
+
+constexpr int KPX = 8;            // pixels per lane
+constexpr int SW = 32 * KPX;      // columns per warp strip
+constexpr int HALO = 20;          // left halo (>= 2*radius, multiple of 4)
+constexpr int VALID_W = 216;      // valid output columns per strip: local [20, 236)
+constexpr int RAD = 9;
+constexpr int WIN = 2 * RAD + 1;  // 19
+constexpr int NWARP = 4;          // disparities in flight per block
+constexpr int PADY = 40;          // padding rows above/below the prepared planes
+constexpr float BEST_INIT_BITS_F = 3.3961514e38f;  // 0x7F7F7F7F, main.cu:112
+
+struct FusedArgs {
+    const unsigned* IG[2];  // per IMAGE (0 left, 1 right): padded half2 (I, G=I[x-1]-I[x+1]); -> element (0,0)
+    const float* If[2];     // per IMAGE: padded float intensity, zero padding
+    const float2* st[2];    // per VIEW (guide = image v): padded (mean_I, c/(S*area)), zero padding
+    int pitch;              // elements per padded row
+    int w;
+    int y_out0, rows_out;   // output rows, in held-row coordinates
+    int y_global0, frame_h; // frame row of held row 0; rows in the whole frame
+    int dmin[2];
+    int size_d;
+    int n_strips, n_bands, band_rows, n_chunks, chunk_d;
+    int n_views;            // 2: both views (view v guides with image v); 1: view 0 only
+    float* bestS;           // [chunk][view][rows_out][pitchS]
+    float* labS;
+    int pitchS;
+    float S;                // lattice scale: p = P / S
+    unsigned wpack;         // half2 (nI, nG): P = nI*cI + nG*cG
+    unsigned thpack;        // half2 (th_color, 2*th_grad)
+};
+
+struct SmemLayout {
+    float4 ringAB[NWARP][WIN][4][32];  // a: planes 0,1  b: planes 2,3 ; lane-contiguous 16 B
+    uint4 ringP[NWARP][WIN][32];       // 8 halfs per lane: the masked lattice cost
+    float4 qbuf[2][NWARP][2][32];      // filtered row of each warp, double buffered
+};
+
+// 19-wide horizontal window sums for the 8 consecutive pixels this lane holds.
+// Lane L holds columns 8L..8L+7.  With LP_L[i] the lane-local prefix sums and T_L the lane
+// total, the window [x-9, x+9] for pixel j of lane L is
+//   (T_{L-1} - LP_{L-1}[j-2]) + T_L + LP_{L+1}[j+1]            for 2 <= j <= 6
+// with the obvious edge forms for j = 0, 1, 7 (one pixel of lanes L-2 / L+2 is needed).
+// 16 shuffles + 26 adds per 8 pixels.  Results are valid for lanes whose neighbours exist,
+// i.e. for strip-local columns [9, 247).
+__device__ __forceinline__ void hsum19(const float (&v)[KPX], float (&h)[KPX]) {
+    const unsigned F = 0xffffffffu;
+    float lp[KPX];
+    lp[0] = v[0];
+#pragma unroll
+    for (int i = 1; i < KPX; i++) lp[i] = lp[i - 1] + v[i];
+    const float T = lp[7];
+    const float Tm1 = __shfl_up_sync(F, T, 1);
+    const float Tp1 = __shfl_down_sync(F, T, 1);
+    const float C = T + Tm1;
+    float r[7];
+#pragma unroll
+    for (int j = 0; j < 6; j++) r[j] = __shfl_down_sync(F, lp[j + 1], 1);
+    r[6] = Tp1;
+    float l[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) l[i] = __shfl_up_sync(F, lp[i], 1);
+    const float vm2 = __shfl_up_sync(F, v[7], 2);
+    const float vp2 = __shfl_down_sync(F, v[0], 2);
+    h[0] = (vm2 + C) + r[0];
+    h[1] = C + r[1];
+#pragma unroll
+    for (int j = 2; j <= 6; j++) h[j] = (C + r[j]) - l[j - 2];
+    h[7] = ((C - l[5]) + Tp1) + vp2;
+}
+
+__device__ __forceinline__ __half2 u2h2(unsigned u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ unsigned h22u(__half2 h) { return *reinterpret_cast<unsigned*>(&h); }
+
+// operands of one row step, fetched one step ahead
+struct StepOps {
+    uint4 g0, g1;        // guide (I,G) half2 x8 at row yi
+    unsigned m[KPX];     // match (I,G) half2 x8 at row yi, columns x+d
+    float4 io0, io1;     // guide intensity at row yi-19 (leaves the first-stage window)
+    float4 s0, s1, s2, s3;  // (mean_I, c2) x8 at row ya = yi-9
+    float4 iq0, iq1;     // guide intensity at row yq = yi-18
+};
+
+__device__ __forceinline__ void load_ops(StepOps& o, const unsigned* __restrict__ IGg, const unsigned* __restrict__ IGm,
+                                         const float* __restrict__ If, const float2* __restrict__ st, int pitch, int yi,
+                                         int xl, int d) {
+    const long long r0 = (long long)yi * pitch + xl;
+    const uint4* pg = reinterpret_cast<const uint4*>(IGg + r0);
+    o.g0 = __ldg(pg);
+    o.g1 = __ldg(pg + 1);
+    const unsigned* pm = IGm + r0 + d;
+#pragma unroll
+    for (int j = 0; j < KPX; j++) o.m[j] = __ldg(pm + j);
+    const float4* po = reinterpret_cast<const float4*>(If + r0 - (long long)WIN * pitch);
+    o.io0 = __ldg(po);
+    o.io1 = __ldg(po + 1);
+    const float4* ps = reinterpret_cast<const float4*>(st + r0 - (long long)RAD * pitch);
+    o.s0 = __ldg(ps);
+    o.s1 = __ldg(ps + 1);
+    o.s2 = __ldg(ps + 2);
+    o.s3 = __ldg(ps + 3);
+    const float4* pq = reinterpret_cast<const float4*>(If + r0 - (long long)(2 * RAD) * pitch);
+    o.iq0 = __ldg(pq);
+    o.iq1 = __ldg(pq + 1);
+}
+
+__device__ __forceinline__ float inv_rows(int y, int y_global0, int frame_h, float scale) {
+    // 1 / (scale * clipped window height) at held row y, 0 outside the frame
+    int yg = y + y_global0;
+    if (yg < 0 || yg >= frame_h) return 0.0f;
+    int ay = min(frame_h - 1, yg + RAD) - max(0, yg - RAD) + 1;
+    return __frcp_rn(scale * (float)ay);
+}
+
+__global__ void __launch_bounds__(NWARP * 32, 1) k_fused_cvf(const FusedArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int bid = blockIdx.x;
+    const int view = bid % A.n_views;
+    bid /= A.n_views;
+    const int chunk = bid % A.n_chunks;
+    bid /= A.n_chunks;
+    const int band = bid % A.n_bands;
+    const int strip = bid / A.n_bands;
+
+    const int xs = strip * VALID_W - HALO;
+    const int xl = xs + KPX * lane;
+    const unsigned* __restrict__ IGg = A.IG[view];
+    const unsigned* __restrict__ IGm = A.IG[1 - view];
+    const float* __restrict__ If = A.If[view];
+    const float2* __restrict__ st = A.st[view];
+    const int pitch = A.pitch;
+
+    const int dlo = A.dmin[view] + chunk * A.chunk_d;
+    const int dcnt = min(A.chunk_d, A.size_d - chunk * A.chunk_d);
+    const int ngroups = (dcnt + NWARP - 1) / NWARP;
+    const int yb0 = A.y_out0 + band * A.band_rows;
+    const int yb1 = min(yb0 + A.band_rows, A.y_out0 + A.rows_out);
+
+    // per-lane column constants
+    float rx[KPX];         // 1 / clipped window width, 0 outside the image
+    __half2 wm[KPX];       // lattice weights (nI, nG), 0 outside the image (masks the cost)
+#pragma unroll
+    for (int j = 0; j < KPX; j++) {
+        int x = xl + j;
+        bool in = (x >= 0 && x < A.w);
+        int ax = min(A.w - 1, x + RAD) - max(0, x - RAD) + 1;
+        rx[j] = in ? __frcp_rn((float)ax) : 0.0f;
+        wm[j] = in ? u2h2(A.wpack) : __float2half2_rn(0.0f);
+    }
+    const __half2 th = u2h2(A.thpack);
+
+    // merge role of this thread: strip-local columns 2t, 2t+1
+    const int mc = 2 * threadIdx.x;
+    const int mx = xs + mc;
+    const bool mvalid0 = (mc >= HALO) && (mc < HALO + VALID_W) && (mx < A.w);
+    const bool mvalid1 = (mc + 1 >= HALO) && (mc + 1 < HALO + VALID_W) && (mx + 1 < A.w);
+    const int mlane = mc >> 3, mj = mc & 7;
+    const size_t planeS = (size_t)A.rows_out * A.pitchS;
+    float* __restrict__ bestS = A.bestS + (size_t)(chunk * 2 + view) * planeS;
+    float* __restrict__ labS = A.labS + (size_t)(chunk * 2 + view) * planeS;
+
+    for (int g = 0; g < ngroups; g++) {
+        const int dk = g * NWARP + warp;
+        const bool active = dk < dcnt;
+        const int d = dlo + (active ? dk : 0);
+
+        // reset this warp's rings and running sums
+        float VP[KPX], VIP[KPX], Va[KPX], Vb[KPX];
+#pragma unroll
+        for (int j = 0; j < KPX; j++) VP[j] = VIP[j] = Va[j] = Vb[j] = 0.0f;
+        for (int s = 0; s < WIN; s++) {
+#pragma unroll
+            for (int v = 0; v < 4; v++) sm.ringAB[warp][s][v][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+            sm.ringP[warp][s][lane] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (!active) {
+            const float inf = __int_as_float(0x7f800000);
+#pragma unroll
+            for (int b = 0; b < 2; b++)
+#pragma unroll
+                for (int v = 0; v < 2; v++) sm.qbuf[b][warp][v][lane] = make_float4(inf, inf, inf, inf);
+        }
+        __syncthreads();  // previous group's merges are done with qbuf; inf fills visible
+
+        int slot = 0;
+        int obuf = 0;
+        StepOps opsA, opsB;
+        load_ops(opsA, IGg, IGm, If, st, pitch, yb0 - 2 * RAD, xl, d);
+
+        auto step = [&](const StepOps& o, StepOps& nxt, int yi) {
+            // fetch the next row's operands first: a full step of latency cover
+            if (active) load_ops(nxt, IGg, IGm, If, st, pitch, yi + 1, xl, d);
+            const int yq = yi - 2 * RAD;
+            const bool emit = (yq >= yb0);  // yq < yb1 holds by the loop bound
+            // prefetch the running (best,label) this thread will merge into
+            float pb0 = BEST_INIT_BITS_F, pb1 = BEST_INIT_BITS_F, pl0 = 0.0f, pl1 = 0.0f;
+            const size_t moff = (size_t)(yq - A.y_out0) * A.pitchS + mx;
+            if (emit && g > 0) {
+                if (mvalid0) { pb0 = bestS[moff]; pl0 = labS[moff]; }
+                if (mvalid1) { pb1 = bestS[moff + 1]; pl1 = labS[moff + 1]; }
+            }
+            if (active) {
+                // ---- first stage: lattice cost of row yi enters the window, row yi-19 leaves
+                const unsigned gg[KPX] = {o.g0.x, o.g0.y, o.g0.z, o.g0.w, o.g1.x, o.g1.y, o.g1.z, o.g1.w};
+                const float iold[KPX] = {o.io0.x, o.io0.y, o.io0.z, o.io0.w, o.io1.x, o.io1.y, o.io1.z, o.io1.w};
+                __half ph[KPX];
+                float pn[KPX];
+#pragma unroll
+                for (int j = 0; j < KPX; j++) {
+                    __half2 gv = u2h2(gg[j]);
+                    __half2 diff = __hsub2(gv, u2h2(o.m[j]));
+                    __half2 c = __hmin2(__habs2(diff), th);  // (min(|dI|,Tc), min(|dG|,2Tg))
+                    __half2 pr = __hmul2(c, wm[j]);
+                    ph[j] = __hadd(__low2half(pr), __high2half(pr));
+                    pn[j] = __half2float(ph[j]);
+                    float inew = __low2float(gv);
+                    VP[j] += pn[j];
+                    VIP[j] = fmaf(inew, pn[j], VIP[j]);
+                }
+                uint4 pold = sm.ringP[warp][slot][lane];
+                uint4 pnew;
+                pnew.x = h22u(__halves2half2(ph[0], ph[1]));
+                pnew.y = h22u(__halves2half2(ph[2], ph[3]));
+                pnew.z = h22u(__halves2half2(ph[4], ph[5]));
+                pnew.w = h22u(__halves2half2(ph[6], ph[7]));
+                sm.ringP[warp][slot][lane] = pnew;
+                const unsigned po[4] = {pold.x, pold.y, pold.z, pold.w};
+#pragma unroll
+                for (int j = 0; j < KPX; j += 2) {
+                    float2 f = __half22float2(u2h2(po[j >> 1]));
+                    VP[j] -= f.x;
+                    VP[j + 1] -= f.y;
+                    VIP[j] = fmaf(-iold[j], f.x, VIP[j]);
+                    VIP[j + 1] = fmaf(-iold[j + 1], f.y, VIP[j + 1]);
+                }
+                float SP[KPX], SIP[KPX];
+                hsum19(VP, SP);
+                hsum19(VIP, SIP);
+                // ---- a, b at row ya = yi - 9
+                const float ry1 = inv_rows(yi - RAD, A.y_global0, A.frame_h, A.S);
+                const float stt[16] = {o.s0.x, o.s0.y, o.s0.z, o.s0.w, o.s1.x, o.s1.y, o.s1.z, o.s1.w,
+                                       o.s2.x, o.s2.y, o.s2.z, o.s2.w, o.s3.x, o.s3.y, o.s3.z, o.s3.w};
+                float a[KPX], b[KPX];
+#pragma unroll
+                for (int j = 0; j < KPX; j++) {
+                    const float mI = stt[2 * j], c2 = stt[2 * j + 1];
+                    float cov = fmaf(-mI, SP[j], SIP[j]);
+                    a[j] = cov * c2;
+                    float mp = SP[j] * (rx[j] * ry1);
+                    b[j] = fmaf(-mI, a[j], mp);
+                }
+                // ---- second stage: (a,b) of row ya enter, row ya-19 leaves
+                float4 oa0 = sm.ringAB[warp][slot][0][lane], oa1 = sm.ringAB[warp][slot][1][lane];
+                float4 ob0 = sm.ringAB[warp][slot][2][lane], ob1 = sm.ringAB[warp][slot][3][lane];
+                sm.ringAB[warp][slot][0][lane] = make_float4(a[0], a[1], a[2], a[3]);
+                sm.ringAB[warp][slot][1][lane] = make_float4(a[4], a[5], a[6], a[7]);
+                sm.ringAB[warp][slot][2][lane] = make_float4(b[0], b[1], b[2], b[3]);
+                sm.ringAB[warp][slot][3][lane] = make_float4(b[4], b[5], b[6], b[7]);
+                const float ao[KPX] = {oa0.x, oa0.y, oa0.z, oa0.w, oa1.x, oa1.y, oa1.z, oa1.w};
+                const float bo[KPX] = {ob0.x, ob0.y, ob0.z, ob0.w, ob1.x, ob1.y, ob1.z, ob1.w};
+#pragma unroll
+                for (int j = 0; j < KPX; j++) {
+                    Va[j] += a[j] - ao[j];
+                    Vb[j] += b[j] - bo[j];
+                }
+                if (emit) {
+                    float SA[KPX], SB[KPX];
+                    hsum19(Va, SA);
+                    hsum19(Vb, SB);
+                    const float ry2 = inv_rows(yq, A.y_global0, A.frame_h, 1.0f);
+                    const float iq[KPX] = {o.iq0.x, o.iq0.y, o.iq0.z, o.iq0.w, o.iq1.x, o.iq1.y, o.iq1.z, o.iq1.w};
+                    float q[KPX];
+#pragma unroll
+                    for (int j = 0; j < KPX; j++) q[j] = fmaf(SA[j], iq[j], SB[j]) * (rx[j] * ry2);
+                    sm.qbuf[obuf][warp][0][lane] = make_float4(q[0], q[1], q[2], q[3]);
+                    sm.qbuf[obuf][warp][1][lane] = make_float4(q[4], q[5], q[6], q[7]);
+                }
+            }
+            slot = (slot + 1 == WIN) ? 0 : slot + 1;
+            if (emit) {
+                __syncthreads();
+                // fold the 4 disparities of this group into (best,label): ascending d, `>=`
+                const float* qb = reinterpret_cast<const float*>(&sm.qbuf[obuf][0][0][0]);
+                const int qoff = ((mj >> 2) * 32 + mlane) * 4 + (mj & 3);
+                const int dbase = dlo + g * NWARP;
+#pragma unroll
+                for (int wv = 0; wv < NWARP; wv++) {
+                    float2 qv = *reinterpret_cast<const float2*>(qb + wv * 256 + qoff);
+                    float lab = (float)(dbase + wv);
+                    if (pb0 >= qv.x) { pb0 = qv.x; pl0 = lab; }
+                    if (pb1 >= qv.y) { pb1 = qv.y; pl1 = lab; }
+                }
+                if (mvalid0) { bestS[moff] = pb0; labS[moff] = pl0; }
+                if (mvalid1) { bestS[moff + 1] = pb1; labS[moff + 1] = pl1; }
+                obuf ^= 1;
+            }
+        };
+
+        int yi = yb0 - 2 * RAD;
+        const int yend = yb1 + 2 * RAD;  // exclusive: last emitted yq = yb1 - 1
+        for (; yi + 1 < yend; yi += 2) {
+            step(opsA, opsB, yi);
+            step(opsB, opsA, yi + 1);
+        }
+        if (yi < yend) step(opsA, opsB, yi);
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Chunk merge: fold the per-chunk (best,label) planes in chunk order with the same rule.
+__global__ void k_merge_chunks(const float* __restrict__ bestS, const float* __restrict__ labS, int n_chunks, int view,
+                               int rows, int w, int pitchS, float* __restrict__ best, float* __restrict__ disp) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w) return;
+    const size_t plane = (size_t)rows * pitchS;
+    float b = BEST_INIT_BITS_F, l = 0.0f;
+    for (int c = 0; c < n_chunks; c++) {
+        size_t off = (size_t)(c * 2 + view) * plane + (size_t)y * pitchS + x;
+        float q = bestS[off];
+        if (b >= q) { b = q; l = labS[off]; }
+    }
+    if (best) best[(size_t)y * w + x] = b;
+    if (disp) disp[(size_t)y * w + x] = l;
+}
+
+// ---------------------------------------------------------------------------------------
+// Per-frame preparation (replaces chToFlOnGPU, x_derivativeOnGPU and the guide-statistics part
+// of compute_guided_filter, guidedFilter.cu:58-123): for one image writes the padded planes
+//   IG  half2 (I, G)   G = I[x-1]-I[x+1] = 2*gradient (costVolume.cu:364-378 border rule);
+//                      padding = (1024,1024) so an out-of-range match saturates both terms
+//   If  float I        zero padding
+//   st  float2 (mean_I, c/(S*area))  zero padding; mean/variance from EXACT integer window
+//       sums (<= 2^25, int32), c = (float)(1/((double)var+eps)) as guidedFilter.cu:350
+// One block computes a 32x32 tile; the 50x50 input patch is staged in shared memory.
+constexpr int PT = 32;
+constexpr int PP = PT + 2 * RAD;  // 50
+
+struct PrepArgs {
+    const uint8_t* gray;  // held rows, pitch w
+    int w, h_held, y_global0, frame_h;
+    unsigned* IG;
+    float* If;
+    float2* st;
+    uint8_t* mean_u8;  // optional, held rows pitch w
+    int pitch, padx;   // padded planes: rows [-PADY, h_held+PADY), cols [-padx, pitch-padx)
+    double eps;
+    float S;
+};
+
+__global__ void __launch_bounds__(256) k_prep(const PrepArgs P) {
+    __shared__ int sI[PP][PP + 1];
+    __shared__ int hI[PP][PT + 1];
+    __shared__ int hII[PP][PT + 1];
+    // tile origin in padded coordinates -> image coordinates
+    const int x0 = blockIdx.x * PT - P.padx;
+    const int y0 = blockIdx.y * PT - PADY;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < PP * PP; i += 256) {
+        int py = i / PP, px = i - py * PP;
+        int x = x0 + px - RAD, y = y0 + py - RAD;
+        int yg = y + P.y_global0;
+        bool in = (x >= 0 && x < P.w && y >= 0 && y < P.h_held && yg >= 0 && yg < P.frame_h);
+        sI[py][px] = in ? (int)P.gray[(size_t)y * P.w + x] : 0;
+    }
+    __syncthreads();
+    for (int i = tid; i < PP * PT; i += 256) {
+        int py = i / PT, tx = i - py * PT;
+        int s1 = 0, s2 = 0;
+#pragma unroll
+        for (int k = 0; k < WIN; k++) {
+            int v = sI[py][tx + k];
+            s1 += v;
+            s2 += v * v;
+        }
+        hI[py][tx] = s1;
+        hII[py][tx] = s2;
+    }
+    __syncthreads();
+    const int n_rows_pad = P.h_held + 2 * PADY;
+    for (int i = tid; i < PT * PT; i += 256) {
+        int ty = i / PT, tx = i - ty * PT;
+        int x = x0 + tx, y = y0 + ty;
+        if (x + P.padx >= P.pitch || y + PADY >= n_rows_pad) continue;
+        const size_t o = (size_t)(y + PADY) * P.pitch + (x + P.padx);
+        int yg = y + P.y_global0;
+        bool in = (x >= 0 && x < P.w && y >= 0 && y < P.h_held && yg >= 0 && yg < P.frame_h);
+        if (!in) {
+            __half2 pad = __floats2half2_rn(1024.0f, 1024.0f);
+            P.IG[o] = *reinterpret_cast<unsigned*>(&pad);
+            P.If[o] = 0.0f;
+            P.st[o] = make_float2(0.0f, 0.0f);
+            continue;
+        }
+        int s1 = 0, s2 = 0;
+#pragma unroll
+        for (int k = 0; k < WIN; k++) {
+            s1 += hI[ty + k][tx];
+            s2 += hII[ty + k][tx];
+        }
+        int ax = min(P.w - 1, x + RAD) - max(0, x - RAD) + 1;
+        int ay = min(P.frame_h - 1, yg + RAD) - max(0, yg - RAD) + 1;
+        float area = (float)(ax * ay);
+        float mI = __fdiv_rn((float)s1, area);
+        float mII = __fdiv_rn((float)s2, area);
+        float var = __fsub_rn(mII, __fmul_rn(mI, mI));
+        float c = (float)(1.0 / ((double)var + P.eps));
+        float rxy = __fmul_rn(__frcp_rn((float)ax), __frcp_rn(P.S * (float)ay));
+        int ic = sI[ty + RAD][tx + RAD];
+        int il = (x - 1 >= 0) ? sI[ty + RAD][tx + RAD - 1] : ic;
+        int ir = (x + 1 < P.w) ? sI[ty + RAD][tx + RAD + 1] : ic;
+        __half2 ig = __floats2half2_rn((float)ic, (float)(il - ir));
+        P.IG[o] = *reinterpret_cast<unsigned*>(&ig);
+        P.If[o] = (float)ic;
+        P.st[o] = make_float2(mI, __fmul_rn(c, rxy));
+        if (P.mean_u8) {
+            int m = (int)mI;
+            P.mean_u8[(size_t)y * P.w + x] = (m > 255) ? 255 : (unsigned char)m;
+        }
+    }
+}
+
+// Find integers (nI, nG, S) with (1-alpha) ~= nI/S and alpha/2 ~= nG/S (relative 1e-6) such
+// that the lattice cost P = nI*cI + nG*cG stays exactly representable through both box sums.
+bool find_lattice(const sb200_params* p, int* nI, int* nG, int* S) {
+    const double wI = (double)(1.0f - p->alpha), wG = (double)p->alpha / 2.0;
+    const double tc = p->th_color, tg2 = 2.0 * p->th_grad;
+    if (tc != (double)(int)tc || tg2 != (double)(int)tg2 || tc < 0 || tg2 < 0 || tc > 255 || tg2 > 1020) return false;
+    for (int s = 1; s <= 4096; s++) {
+        double a = wI * s, b = wG * s;
+        long ia = lround(a), ib = lround(b);
+        if (ia < 0 || ib < 0 || (ia == 0 && ib == 0)) continue;
+        if (fabs(a - ia) > 1e-6 * fmax(a, 1e-3) * 1.0 + 1e-9 * s && fabs(a - ia) > 2e-6 * a) continue;
+        if (fabs(b - ib) > 2e-6 * b && fabs(b - ib) > 1e-9 * s) continue;
+        double pmax = ia * tc + ib * tg2;
+        // half-exact lattice values and fp32-exact 361-element sums of I*P
+        if (pmax > 2047.0 || 361.0 * 255.0 * pmax >= 16777216.0) return false;
+        *nI = (int)ia;
+        *nG = (int)ib;
+        *S = s;
+        return true;
+    }
+    return false;
+}
+
+struct Plan {
+    int n_strips, n_bands, band_rows, n_chunks, chunk_d;
+};
+
+// Tile (strip x band x chunk x 2 views) so that the block count is close to a multiple of the
+// SM count with as little warm-up (36 extra rows per band) and group padding as possible.
+Plan make_plan(int w, int rows_out, int size_d, int sm_count, int n_views) {
+    Plan best{};
+    double best_cost = 1e300;
+    const int n_strips = (w + VALID_W - 1) / VALID_W;
+    const int groups = (size_d + NWARP - 1) / NWARP;
+    for (int n_chunks = 1; n_chunks <= groups; n_chunks++) {
+        int gpc = (groups + n_chunks - 1) / n_chunks;  // groups per chunk
+        int real_chunks = (groups + gpc - 1) / gpc;
+        if (real_chunks != n_chunks) continue;
+        for (int n_bands = 1; n_bands <= 64; n_bands++) {
+            int band_rows = (rows_out + n_bands - 1) / n_bands;
+            if (n_bands > 1 && band_rows < 64) break;
+            int real_bands = (rows_out + band_rows - 1) / band_rows;
+            if (real_bands != n_bands) continue;
+            long blocks = (long)n_strips * n_bands * n_chunks * n_views;
+            long waves = (blocks + sm_count - 1) / sm_count;
+            // time ~ waves * per-block work; per-block work ~ groups/chunk * (band_rows + 36)
+            double t = (double)waves * gpc * (band_rows + 4.0 * RAD) + 0.02 * n_chunks * rows_out / 64.0;
+            if (t < best_cost) {
+                best_cost = t;
+                best = Plan{n_strips, n_bands, band_rows, n_chunks, gpc * NWARP};
+            }
+        }
+    }
+    return best;
+}
+
+int pad_x(int dabs) { return (dabs + SW + 8 + 7) / 8 * 8; }
+
+}  // namespace
+
+size_t sbf_workspace_bytes(const sb200_ctx* ctx, int w, int h_held, int rows_out, int dabs, int size_d, int n_views) {
+    const int padx = pad_x(dabs);
+    const int pitch = (w + 2 * padx + 7) / 8 * 8;
+    const size_t plane = (size_t)pitch * (h_held + 2 * PADY);
+    const int pitchS = (w + 3) / 4 * 4;
+    Plan plan = make_plan(w, rows_out, size_d, ctx->sm_count, n_views);
+    size_t bytes = 0;
+    bytes += 2 * sb_align(plane * 4);      // IG x2
+    bytes += 2 * sb_align(plane * 4);      // If x2
+    bytes += 2 * sb_align(plane * 8);      // st x2
+    bytes += 2 * sb_align((size_t)plan.n_chunks * 2 * rows_out * pitchS * 4);  // bestS, labS
+    return bytes + 4096;
+}
+
+static int run_fused(sb200_ctx* ctx, const sb200_params* p, const uint8_t* const gray[2], const SbFusedGeom& g,
+                     const int dmin[2], int size_d, int n_views, float* const best[2], float* const disp[2],
+                     uint8_t* const mean[2]) {
+    if (p->radius != RAD)
+        return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "fused kernel is built for radius %d (got %d): use box_mode stages", RAD,
+                       p->radius);
+    if (p->guide_mode != SB200_GUIDE_GRAY)
+        return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "fused kernel: RGB guide not implemented yet");
+    int nI, nG, S;
+    if (!find_lattice(p, &nI, &nG, &S))
+        return sb_fail(ctx, SB200_ERR_UNSUPPORTED,
+                       "fused kernel: (alpha=%g, th_color=%g, th_grad=%g) has no exact integer cost lattice", p->alpha,
+                       p->th_color, p->th_grad);
+    if (size_d < 1 || g.w < 2 || g.h < 1 || g.rows_out < 1) return sb_fail(ctx, SB200_ERR_INVALID, "fused: bad shape");
+
+    int dabs = 0;
+    for (int v = 0; v < n_views; v++) dabs = max(dabs, max(abs(dmin[v]), abs(dmin[v] + size_d - 1)));
+    const int padx = pad_x(dabs);
+    const int pitch = (g.w + 2 * padx + 7) / 8 * 8;
+    const int rows_pad = g.h + 2 * PADY;
+    const size_t plane = (size_t)pitch * rows_pad;
+    const int pitchS = (g.w + 3) / 4 * 4;
+    Plan plan = make_plan(g.w, g.rows_out, size_d, ctx->sm_count, n_views);
+
+    unsigned* IG[2];
+    float* If[2];
+    float2* st[2];
+    for (int i = 0; i < 2; i++) {
+        IG[i] = sb_ws_alloc<unsigned>(ctx, plane);
+        If[i] = sb_ws_alloc<float>(ctx, plane);
+        st[i] = sb_ws_alloc<float2>(ctx, plane);
+    }
+    const size_t planeS = (size_t)g.rows_out * pitchS;
+    float* bestS = sb_ws_alloc<float>(ctx, planeS * 2 * plan.n_chunks);
+    float* labS = sb_ws_alloc<float>(ctx, planeS * 2 * plan.n_chunks);
+    if (!IG[0] || !IG[1] || !If[0] || !If[1] || !st[0] || !st[1] || !bestS || !labS)
+        return sb_fail(ctx, SB200_ERR_NOMEM, "fused: workspace arena too small (internal)");
+
+    if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    for (int i = 0; i < 2; i++) {
+        PrepArgs P;
+        P.gray = gray[i];
+        P.w = g.w;
+        P.h_held = g.h;
+        P.y_global0 = g.y_global0;
+        P.frame_h = g.frame_h;
+        P.IG = IG[i];
+        P.If = If[i];
+        P.st = st[i];
+        P.mean_u8 = mean[i];
+        P.pitch = pitch;
+        P.padx = padx;
+        P.eps = p->eps;
+        P.S = (float)S;
+        dim3 grid(sb_div_up(pitch, PT), sb_div_up(rows_pad, PT));
+        SB_LAUNCH(ctx, k_prep, grid, 256, 0, P);
+    }
+    if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+
+    FusedArgs A;
+    const size_t origin = (size_t)PADY * pitch + padx;
+    for (int i = 0; i < 2; i++) {
+        A.IG[i] = IG[i] + origin;
+        A.If[i] = If[i] + origin;
+        A.st[i] = st[i] + origin;
+        A.dmin[i] = dmin[i];
+    }
+    A.pitch = pitch;
+    A.w = g.w;
+    A.y_out0 = g.y_out0;
+    A.rows_out = g.rows_out;
+    A.y_global0 = g.y_global0;
+    A.frame_h = g.frame_h;
+    A.size_d = size_d;
+    A.n_strips = plan.n_strips;
+    A.n_bands = plan.n_bands;
+    A.band_rows = plan.band_rows;
+    A.n_chunks = plan.n_chunks;
+    A.chunk_d = plan.chunk_d;
+    A.bestS = bestS;
+    A.labS = labS;
+    A.pitchS = pitchS;
+    A.S = (float)S;
+    __half2 wp = __floats2half2_rn((float)nI, (float)nG);
+    __half2 tp = __floats2half2_rn(p->th_color, 2.0f * p->th_grad);
+    A.wpack = *reinterpret_cast<unsigned*>(&wp);
+    A.thpack = *reinterpret_cast<unsigned*>(&tp);
+
+    const size_t smem = sizeof(SmemLayout);
+    if (!ctx->fused_attr_set) {
+        SB_CUDA(ctx, cudaFuncSetAttribute(k_fused_cvf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->fused_attr_set = true;
+    }
+    A.n_views = n_views;
+    const int nblocks = plan.n_strips * plan.n_bands * plan.n_chunks * n_views;
+    SB_LAUNCH(ctx, k_fused_cvf, nblocks, NWARP * 32, smem, A);
+    if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    for (int v = 0; v < n_views; v++) {
+        if (!best[v] && !disp[v]) continue;
+        dim3 grid(sb_div_up(g.w, 256), g.rows_out);
+        SB_LAUNCH(ctx, k_merge_chunks, grid, 256, 0, bestS, labS, plan.n_chunks, v, g.rows_out, g.w, pitchS, best[v],
+                  disp[v]);
+    }
+    if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    return SB200_OK;
+}
+
+int sbf_pair_disparity(sb200_ctx* ctx, const sb200_params* p, const uint8_t* gray_l, const uint8_t* gray_r,
+                       const SbFusedGeom& g, float* bestL, float* dispL, float* bestR, float* dispR, uint8_t* meanL,
+                       uint8_t* meanR) {
+    const uint8_t* gray[2] = {gray_l, gray_r};
+    const int dmin[2] = {p->dmin, -p->dmax};  // main.cu:79-82
+    float* best[2] = {bestL, bestR};
+    float* disp[2] = {dispL, dispR};
+    uint8_t* mean[2] = {meanL, meanR};
+    return run_fused(ctx, p, gray, g, dmin, p->dmax - p->dmin + 1, 2, best, disp, mean);
+}
+
+int sbf_view_disparity(sb200_ctx* ctx, const sb200_params* p, const uint8_t* guide, const uint8_t* other,
+                       const SbFusedGeom& g, int dmin, int size_d, float* best, float* disp, uint8_t* mean) {
+    const uint8_t* gray[2] = {guide, other};
+    const int dm[2] = {dmin, dmin};
+    float* b[2] = {best, nullptr};
+    float* d[2] = {disp, nullptr};
+    uint8_t* m[2] = {mean, nullptr};
+    return run_fused(ctx, p, gray, g, dm, size_d, 1, b, d, m);
+}

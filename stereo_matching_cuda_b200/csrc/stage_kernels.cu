@@ -1,0 +1,400 @@
+// stage_kernels.cu -- stage-materialising kernels behind the per-stage drop-in entry points.
+//
+// These write every intermediate to HBM exactly where the reference's stage boundaries are,
+// and follow its float32 arithmetic operation by operation (explicit __f*_rn intrinsics, so
+// nvcc cannot contract a*b+c: the reference's goldens are reproduced by the non-contracted
+// evaluation).  They are HBM-bound streaming kernels; the
+// headline path is the fused kernel in fused_cvf.cu, which never materialises the volume.
+#include <climits>
+
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------
+// rgb_to_grayscale.cu:14-23 (sumArraysOnGPU): double luma, truncation toward zero.
+__global__ void k_rgb_to_gray(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ gray, int n, int ch, double rw,
+                              double gw, double bw) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    size_t i = (size_t)ch * idx;
+    double val = __dadd_rn(__dadd_rn(__dmul_rn(rw, (double)rgb[i]), __dmul_rn(gw, (double)rgb[i + 1])),
+                           __dmul_rn(bw, (double)rgb[i + 2]));
+    gray[idx] = (unsigned char)val;
+}
+
+int sbk_rgb_to_gray(sb200_ctx* ctx, const sb200_params* p, const uint8_t* rgb, int n, int ch, uint8_t* gray) {
+    SB_LAUNCH(ctx, k_rgb_to_gray, sb_div_up(n, 256), 256, 0, rgb, gray, n, ch, p->r_w, p->g_w, p->b_w);
+    return SB200_OK;
+}
+
+// costVolume.cu:358-381 (x_derivativeOnGPU): (left - right)/2 with one-sided (still halved) ends.
+__global__ void k_x_derivative(const uint8_t* __restrict__ in, float* __restrict__ out, int w, int h) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w) return;
+    const uint8_t* row = in + (size_t)y * w;
+    int xl = x - 1 >= 0 ? x - 1 : x;
+    int xr = x + 1 < w ? x + 1 : x;
+    if (w == 1) { xl = xr = 0; }
+    out[(size_t)y * w + x] = 1.0f * (float)((int)row[xl] - (int)row[xr]) / 2;
+}
+
+int sbk_x_derivative(sb200_ctx* ctx, const uint8_t* img, float* grad, int w, int h) {
+    dim3 grid(sb_div_up(w, 256), h);
+    SB_LAUNCH(ctx, k_x_derivative, grid, 256, 0, img, grad, w, h);
+    return SB200_OK;
+}
+
+// costVolume.cu:163-190 (costVolumOnGPU2); grid.y = slice so any size_d works (the
+// reference's block (16,size_d) caps size_d at 64, costVolume.cu:39).
+__global__ void k_cost_volume(const uint8_t* __restrict__ i1, const uint8_t* __restrict__ i2,
+                              const float* __restrict__ g1, const float* __restrict__ g2, float* __restrict__ cost,
+                              int w, int h, int dmin, float alpha, float th_color, float th_grad) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    int k = blockIdx.z;
+    if (x >= w) return;
+    int d = dmin + k;
+    size_t idx = (size_t)y * w + x;
+    float oma = __fsub_rn(1.0f, alpha);
+    float c = __fadd_rn(__fmul_rn(oma, th_color), __fmul_rn(alpha, th_grad));
+    if (x + d < w && x + d >= 0) {
+        float ci = fminf((float)abs((int)i1[idx] - (int)i2[idx + d]), th_color);
+        float cg = fminf(fabsf(__fsub_rn(g1[idx], g2[idx + d])), th_grad);
+        c = __fadd_rn(__fmul_rn(oma, ci), __fmul_rn(alpha, cg));
+    }
+    cost[(size_t)k * w * h + idx] = c;
+}
+
+int sbk_cost_volume(sb200_ctx* ctx, const sb200_params* p, const uint8_t* i1, const uint8_t* i2, const float* g1,
+                    const float* g2, float* cost, int w, int h, int size_d, int dmin) {
+    // grid.z is limited to 65535 and grid.y likewise: loop over slabs if ever needed
+    if (h > 65535 || size_d > 65535) return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "cost_volume: h or size_d > 65535");
+    dim3 grid(sb_div_up(w, 256), h, size_d);
+    SB_LAUNCH(ctx, k_cost_volume, grid, 256, 0, i1, i2, g1, g2, cost, w, h, dmin, p->alpha, p->th_color, p->th_grad);
+    return SB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// integral.cu:78-90 (rowSum): out[x] = in[x] + out[x-1], strictly sequential per row.  The
+// reference runs one thread per row over global memory; here a warp owns 32 rows, stages
+// 32x32 tiles through shared memory with coalesced loads/stores, and lane l walks row l of
+// the tile -- the add ORDER per row is unchanged, so the result is bit-identical.
+#define SCAN_WARPS 4
+__global__ void k_row_scan(const float* __restrict__ in, float* __restrict__ out, int w, int h) {
+    __shared__ float tile[SCAN_WARPS][32][33];
+    int warp = threadIdx.y, lane = threadIdx.x;
+    int row0 = (blockIdx.x * SCAN_WARPS + warp) * 32;
+    if (row0 >= h) return;
+    float carry = 0.0f;
+    for (int c0 = 0; c0 < w; c0 += 32) {
+        int x = c0 + lane;
+#pragma unroll 8
+        for (int r = 0; r < 32; r++) {
+            int y = row0 + r;
+            tile[warp][r][lane] = (y < h && x < w) ? in[(size_t)y * w + x] : 0.0f;
+        }
+        __syncwarp();
+#pragma unroll 8
+        for (int c = 0; c < 32; c++) {
+            float v = tile[warp][lane][c];
+            carry = (c0 == 0 && c == 0) ? v : __fadd_rn(v, carry);
+            tile[warp][lane][c] = carry;
+        }
+        __syncwarp();
+#pragma unroll 8
+        for (int r = 0; r < 32; r++) {
+            int y = row0 + r;
+            if (y < h && x < w) out[(size_t)y * w + x] = tile[warp][r][lane];
+        }
+        __syncwarp();
+    }
+}
+
+// integral.cu:121-131 (colSum): out[y] = in[y] + out[y-1] per column, one thread per column
+// (coalesced across the warp); loads are batched 8 rows ahead to hide latency.
+__global__ void k_col_scan(const float* __restrict__ in, float* __restrict__ out, int w, int h) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w) return;
+    float carry = in[x];
+    out[x] = carry;
+    int y = 1;
+    for (; y + 8 <= h; y += 8) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = in[(size_t)(y + i) * w + x];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            carry = __fadd_rn(v[i], carry);
+            out[(size_t)(y + i) * w + x] = carry;
+        }
+    }
+    for (; y < h; y++) {
+        carry = __fadd_rn(in[(size_t)y * w + x], carry);
+        out[(size_t)y * w + x] = carry;
+    }
+}
+
+int sbk_integral(sb200_ctx* ctx, const float* in, float* tmp, float* out, int w, int h) {
+    dim3 blk(32, SCAN_WARPS);
+    SB_LAUNCH(ctx, k_row_scan, sb_div_up(h, 32 * SCAN_WARPS), blk, 0, in, tmp, w, h);
+    SB_LAUNCH(ctx, k_col_scan, sb_div_up(w, 64), 64, 0, tmp, out, w, h);
+    return SB200_OK;
+}
+
+// guidedFilter.cu:297-318 (computeBoxFilterOnGPU / computeMeanOnGPU): same tap order, IEEE divide.
+__global__ void k_box_from_sat(const float* __restrict__ S, float* __restrict__ mean, int w, int h, int r) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int idy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (idx >= w || idy >= h) return;
+    int ymin = max(-1, idy - r - 1);
+    int ymax = min(h - 1, idy + r);
+    int xmin = max(-1, idx - r - 1);
+    int xmax = min(w - 1, idx + r);
+    float val = S[(size_t)ymax * w + xmax];
+    if (xmin >= 0) val = __fsub_rn(val, S[(size_t)ymax * w + xmin]);
+    if (ymin >= 0) val = __fsub_rn(val, S[(size_t)ymin * w + xmax]);
+    if (xmin >= 0 && ymin >= 0) val = __fadd_rn(val, S[(size_t)ymin * w + xmin]);
+    mean[(size_t)idy * w + idx] = __fdiv_rn(val, (float)((xmax - xmin) * (ymax - ymin)));
+}
+
+int sbk_box_from_sat(sb200_ctx* ctx, const float* sat, float* mean, int w, int h, int r) {
+    dim3 blk(32, 8), grid(sb_div_up(w, 32), sb_div_up(h, 8));
+    SB_LAUNCH(ctx, k_box_from_sat, grid, blk, 0, sat, mean, w, h, r);
+    return SB200_OK;
+}
+
+// Sliding-window box mean with double accumulation (the "exact" box of the tests): a
+// vertical running sum per column, then the clipped horizontal window per pixel.
+__global__ void k_box_v_f64(const float* __restrict__ in, double* __restrict__ tmp, int w, int h, int r) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w) return;
+    double s = 0.0;
+    for (int y = 0; y < min(r, h); y++) s += (double)in[(size_t)y * w + x];
+    for (int y = 0; y < h; y++) {
+        if (y + r < h) s += (double)in[(size_t)(y + r) * w + x];
+        if (y - r - 1 >= 0) s -= (double)in[(size_t)(y - r - 1) * w + x];
+        tmp[(size_t)y * w + x] = s;
+    }
+}
+__global__ void k_box_h_f64(const double* __restrict__ tmp, float* __restrict__ mean, int w, int h, int r) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w) return;
+    int x0 = max(0, x - r), x1 = min(w - 1, x + r);
+    int y0 = max(0, y - r), y1 = min(h - 1, y + r);
+    double s = 0.0;
+    for (int xx = x0; xx <= x1; xx++) s += tmp[(size_t)y * w + xx];
+    double area = (double)(x1 - x0 + 1) * (double)(y1 - y0 + 1);
+    mean[(size_t)y * w + x] = (float)(s / area);
+}
+
+int sbk_box_sliding(sb200_ctx* ctx, const float* in, double* tmp, float* mean, int w, int h, int r) {
+    SB_LAUNCH(ctx, k_box_v_f64, sb_div_up(w, 64), 64, 0, in, tmp, w, h, r);
+    dim3 grid(sb_div_up(w, 128), h);
+    SB_LAUNCH(ctx, k_box_h_f64, grid, 128, 0, tmp, mean, w, h, r);
+    return SB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// elementwise helpers of guidedFilter.cu:442-474 and the per-slice kernels :345-369,:403-411
+__global__ void k_u8_to_float(const uint8_t* __restrict__ in, float* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = 1.0f * (float)(int)in[i];
+}
+__global__ void k_float_to_u8(const float* __restrict__ in, uint8_t* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        int c = (int)in[i];
+        out[i] = (c > 255) ? 255 : (unsigned char)c;
+    }
+}
+__global__ void k_mul(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __fmul_rn(a[i], b[i]);
+}
+__global__ void k_sub(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __fsub_rn(a[i], b[i]);
+}
+// compute_ak_and_bk, guidedFilter.cu:345-354: c = 1.0f/(var+EPS) evaluated in double (EPS is a
+// double literal) and narrowed; a = (mIp - mean*mp)*c; b = mp - mean*a
+__global__ void k_ak_bk(const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ mIp,
+                        const float* __restrict__ mp, float* __restrict__ a, float* __restrict__ b, size_t n,
+                        double eps) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float c = (float)(1.0 / ((double)var[i] + eps));
+    float av = __fmul_rn(__fsub_rn(mIp[i], __fmul_rn(mean[i], mp[i])), c);
+    a[i] = av;
+    b[i] = __fsub_rn(mp[i], __fmul_rn(mean[i], av));
+}
+// compute_q, guidedFilter.cu:363-369
+__global__ void k_q(const float* __restrict__ im, const float* __restrict__ a, const float* __restrict__ b,
+                    float* __restrict__ q, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) q[i] = __fadd_rn(__fmul_rn(a[i], im[i]), b[i]);
+}
+// dispSelectOnGPU, guidedFilter.cu:403-411: the live winner-take-all; >= so the last slice wins ties
+__global__ void k_disp_select(const float* __restrict__ q, float* __restrict__ best, float* __restrict__ dmap, size_t n,
+                              int label) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        float qv = q[i];
+        if (best[i] >= qv) {
+            dmap[i] = (float)label;
+            best[i] = qv;
+        }
+    }
+}
+__global__ void k_fill_f32(float* dst, float v, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = v;
+}
+
+#define EW_LAUNCH(kernel, n, ...) SB_LAUNCH(ctx, kernel, sb_div_up((long long)(n), 256), 256, 0, __VA_ARGS__)
+int sbk_u8_to_float(sb200_ctx* ctx, const uint8_t* in, float* out, size_t n) { EW_LAUNCH(k_u8_to_float, n, in, out, n); return SB200_OK; }
+int sbk_float_to_u8(sb200_ctx* ctx, const float* in, uint8_t* out, size_t n) { EW_LAUNCH(k_float_to_u8, n, in, out, n); return SB200_OK; }
+int sbk_mul(sb200_ctx* ctx, const float* a, const float* b, float* out, size_t n) { EW_LAUNCH(k_mul, n, a, b, out, n); return SB200_OK; }
+int sbk_sub(sb200_ctx* ctx, const float* a, const float* b, float* out, size_t n) { EW_LAUNCH(k_sub, n, a, b, out, n); return SB200_OK; }
+int sbk_ak_bk(sb200_ctx* ctx, const float* mean, const float* var, const float* mIp, const float* mp, float* a,
+              float* b, size_t n, double eps) {
+    EW_LAUNCH(k_ak_bk, n, mean, var, mIp, mp, a, b, n, eps);
+    return SB200_OK;
+}
+int sbk_q(sb200_ctx* ctx, const float* im, const float* a, const float* b, float* q, size_t n) { EW_LAUNCH(k_q, n, im, a, b, q, n); return SB200_OK; }
+int sbk_disp_select(sb200_ctx* ctx, const float* q, float* best, float* dmap, size_t n, int label) {
+    EW_LAUNCH(k_disp_select, n, q, best, dmap, n, label);
+    return SB200_OK;
+}
+int sbk_fill_f32(sb200_ctx* ctx, float* dst, float v, size_t n) { EW_LAUNCH(k_fill_f32, n, dst, v, n); return SB200_OK; }
+
+// ---------------------------------------------------------------------------------------
+// occlusion.cu:3-15 (detect_occlusionOnGPU), in place on dL.  Reads of dL and writes of dL are
+// per-pixel (no cross-pixel dependency), dR is read-only, so in place is race free.
+__global__ void k_detect_occlusion(float* __restrict__ dL, const float* __restrict__ dR, int dOcc, int d_lr, int w,
+                                   int h) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w) return;
+    size_t id = (size_t)y * w + x;
+    int d = (int)dL[id];
+    if (x + d < 0 || x + d >= w || fabsf((float)d + dR[id + d]) > (float)d_lr) dL[id] = (float)dOcc;
+}
+
+int sbk_detect_occlusion(sb200_ctx* ctx, float* dL, const float* dR, int dOcc, int d_lr, int w, int h) {
+    dim3 grid(sb_div_up(w, 256), h);
+    SB_LAUNCH(ctx, k_detect_occlusion, grid, 256, 0, dL, dR, dOcc, d_lr, w, h);
+    return SB200_OK;
+}
+
+// Block-wide inclusive max-scan over one value per thread, with a carry from earlier tiles.
+// Returns the scanned value for this thread; *carry_out (same for all threads) is the
+// maximum over the whole tile and the carry.
+#define FILL_THREADS 256
+__device__ __forceinline__ int block_scan_max(int v, int carry, int* swarp, int* carry_out) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        int n = __shfl_up_sync(0xffffffffu, v, off);
+        if (lane >= off) v = max(v, n);
+    }
+    if (lane == 31) swarp[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        int t = lane < FILL_THREADS / 32 ? swarp[lane] : INT_MIN;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            int n = __shfl_up_sync(0xffffffffu, t, off);
+            if (lane >= off) t = max(t, n);
+        }
+        swarp[lane] = t;
+    }
+    __syncthreads();
+    int pre = wid > 0 ? swarp[wid - 1] : INT_MIN;
+    int total = swarp[FILL_THREADS / 32 - 1];
+    v = max(v, max(pre, carry));
+    *carry_out = max(total, carry);
+    __syncthreads();
+    return v;
+}
+
+// L/R consistency check (occlusion.cu:3-15) + scan-line fill (occlusion.cu:134-176) for one
+// image row per block.  The reference walks left and right from every occluded pixel; here the
+// nearest valid pixel at-or-left and at-or-right of every pixel comes from two block scans
+// over the row held in shared memory (a gather from the unfilled row, which SURVEY.md A.6
+// shows is what every schedule of the reference's in-place kernel computes).
+//   mode bit 0: run the L/R check (else `dL` is taken as the already-checked map)
+//   occ_out / filled_out may be NULL.
+__global__ void __launch_bounds__(FILL_THREADS)
+k_lr_check_fill(const float* dL, const float* __restrict__ dR, int w, int dOcc, int d_lr, float vMin,
+                float* occ_out, float* filled_out, int do_check) {  // dL may alias filled_out (in-place fill)
+    extern __shared__ float srow[];                 // w floats: the (checked) row
+    int* sleft = reinterpret_cast<int*>(srow + w);  // w ints: nearest valid index at-or-left
+    __shared__ int swarp[32];
+    const int y = blockIdx.x;
+    const size_t base = (size_t)y * w;
+    for (int x = threadIdx.x; x < w; x += FILL_THREADS) {
+        float v = dL[base + x];
+        if (do_check) {
+            int d = (int)v;
+            if (x + d < 0 || x + d >= w || fabsf((float)d + dR[base + x + d]) > (float)d_lr) v = (float)dOcc;
+            if (occ_out) occ_out[base + x] = v;
+        }
+        srow[x] = v;
+    }
+    __syncthreads();
+    if (!filled_out) return;
+    // forward: nearest valid (v >= vMin) index at-or-left of x
+    int carry = INT_MIN;
+    for (int t0 = 0; t0 < w; t0 += FILL_THREADS) {
+        int x = t0 + threadIdx.x;
+        int v = (x < w && srow[x] >= vMin) ? x : INT_MIN;
+        int nc;
+        v = block_scan_max(v, carry, swarp, &nc);
+        carry = nc;
+        if (x < w) sleft[x] = v;
+    }
+    // backward: nearest valid index at-or-right, as a max-scan over -x from the right end
+    carry = INT_MIN;
+    for (int t0 = 0; t0 < w; t0 += FILL_THREADS) {
+        int x = w - 1 - (t0 + threadIdx.x);
+        int v = (x >= 0 && srow[x] >= vMin) ? -x : INT_MIN;
+        int nc;
+        v = block_scan_max(v, carry, swarp, &nc);
+        carry = nc;
+        if (x >= 0) {
+            float self = srow[x];
+            float out = self;
+            int dX = (int)self;  // occlusion.cu:140-142: the self test uses the truncated int
+            if (!((float)dX >= vMin)) {
+                int l = sleft[x];
+                float dLeft = (l >= 0) ? srow[l] : vMin;
+                float dRight = (v != INT_MIN) ? srow[-v] : vMin;
+                out = fmaxf(dLeft, dRight);
+            }
+            filled_out[base + x] = out;
+        }
+    }
+}
+
+static int launch_lr(sb200_ctx* ctx, const float* dL, const float* dR, int w, int h, int dOcc, int d_lr, float vMin,
+                     float* occ, float* filled, int do_check) {
+    size_t smem = (size_t)w * 8;
+    if (smem > ctx->smem_optin)
+        return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "row of %d pixels does not fit shared memory", w);
+    if (smem > 48 * 1024)
+        SB_CUDA(ctx, cudaFuncSetAttribute(k_lr_check_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SB_LAUNCH(ctx, k_lr_check_fill, h, FILL_THREADS, smem, dL, dR, w, dOcc, d_lr, vMin, occ, filled, do_check);
+    return SB200_OK;
+}
+
+// fill_occlusion (occlusion.cu:111-132) in place: every block reads its whole row into shared
+// memory before writing any of it, and rows are independent.
+int sbk_fill_occlusion(sb200_ctx* ctx, float* disp, int w, int h, float vMin) {
+    return launch_lr(ctx, disp, nullptr, w, h, 0, 0, vMin, nullptr, disp, 0);
+}
+
+int sbk_lr_check_fill(sb200_ctx* ctx, const float* dL, const float* dR, int w, int h, int dOcc, int d_lr, float vMin,
+                      float* occ, float* filled) {
+    return launch_lr(ctx, dL, dR, w, h, dOcc, d_lr, vMin, occ, filled, 1);
+}
