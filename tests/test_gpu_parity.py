@@ -213,15 +213,17 @@ def test_fused_pipeline_shapes(ctx, oracle, w, h, dmin, dmax):
     assert np.array_equal(out["filled"], oracle.fill_occlusion(occ, dmin))
 
 
-def test_fused_tie_break_constant_image(ctx):
-    """Constant pair: every in-range slice filters to q == 0, so the label must be the LAST
-    in-range slice (guidedFilter.cu:406 `>=`), which for the left view is d = 0 everywhere."""
+def test_fused_tie_break_constant_image(ctx, oracle):
+    """Constant pair: every slice whose whole (cascaded) window is in range filters to q == 0
+    exactly, so the label must be the LAST such slice (guidedFilter.cu:406 `>=`): d = 0 everywhere
+    for the left view, and the oracle's tie resolution pixel for pixel for the right view."""
     img = np.full((60, 250), 91, np.uint8)
     out = ctx.pipeline(img, img, api.default_params(dmin=-11, dmax=0))
     assert np.all(out["disp_left"] == 0)
-    # right view searches d in [0, 11]: the last in-range slice at column x is min(11, w-1-x)
-    want = np.minimum(11, 250 - 1 - np.arange(250)).astype(np.float32)
-    assert np.array_equal(out["disp_right"], np.broadcast_to(want, (60, 250)))
+    ref = oracle.pipeline_gray(img, img, -11, 12, oracle.params(box_mode=O.BOX_EXACT))
+    assert np.array_equal(out["disp_right"], ref["dR"])
+    assert np.all(out["disp_right"][:, :200] == 11) and np.all(out["disp_right"][:, -1] == 0)
+    assert np.array_equal(out["filled"], ref["filled"])
 
 
 def test_fused_synthetic_staircase_recovers_disparity(ctx):
@@ -312,7 +314,7 @@ def test_against_reference_gpu_code(ctx, oracle, tsukuba):
     dmap = np.zeros(gl.shape, np.float32)
     ctx.compute_guided_filter(gl, ref["cost_l"], best, dmap, -15, p)
     assert (dmap == ref["dmap_l"]).mean() > 0.9999  # its device code is fma-contracted, ours is not
-    assert np.allclose(best, ref["best_l"], rtol=1e-4)
+    assert np.allclose(best, ref["best_l"], rtol=1e-3)  # contraction of mIp - mean*mp cancels ~3 digits
     out = ctx.pipeline(gl, gr)
     assert (out["disp_left"] == ref["dmap_l"]).mean() > 0.9999
     assert (out["filled"] == ref["filled"]).mean() > 0.999
