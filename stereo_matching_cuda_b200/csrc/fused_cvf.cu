@@ -19,9 +19,16 @@
 //  * The cost is evaluated on an integer lattice: 20*p = 2*min(|dI|,7) + 9*min(|dG|,4) with
 //    G = 2*gradient, so the first-stage box sums of p and I*p are sums of integers below 2^24
 //    held in fp32 -- exact, order independent, identical on every tiling or GPU split.
-//  * The 4 warps of a block take 4 consecutive disparities in lockstep, exchange their
-//    filtered row through a 1 KB shared buffer and one thread per 2 columns folds them into
-//    the running (best, label) with the reference's `best >= q` rule (last slice wins ties).
+//  * Warp specialisation: a block is 4 PAIRS of warps, one pair per disparity.  The producer
+//    warp of a pair runs the first stage (cost, vertical sums, horizontal sums) and hands the
+//    window sums (S_P, S_IP) of each row to its consumer warp through a 2-slot shared buffer
+//    and a 64-thread named barrier; the consumer runs a/b, the second box filter and q.  The
+//    two warps of a pair sit on the same SM sub-partition, so each hides the other's
+//    shuffle / shared-memory / FP32 dependency latency (round 1 ncu: one warp per scheduler
+//    left 73 % of issue slots empty).
+//  * The 4 consumer warps exchange their filtered row through a 1 KB shared buffer and one
+//    consumer thread per 2 columns folds the 4 disparities into the running (best, label)
+//    with the reference's `best >= q` rule (last slice wins ties).
 //  * Blocks tile (column strip x row band x disparity chunk x view); per-chunk (best,label)
 //    planes are merged in chunk order by a small second kernel.
 // HBM traffic is ~30 B per PIXEL per disparity group read from L2-resident prepared planes;
@@ -38,7 +45,8 @@ constexpr int HALO = 20;          // left halo (>= 2*radius, multiple of 4)
 constexpr int VALID_W = 216;      // valid output columns per strip: local [20, 236)
 constexpr int RAD = 9;
 constexpr int WIN = 2 * RAD + 1;  // 19
-constexpr int NWARP = 4;          // disparities in flight per block
+constexpr int NWARP = 4;          // disparities in flight per block (= warp pairs)
+constexpr int NTHREADS = 2 * NWARP * 32;
 constexpr int PADY = 40;          // padding rows above/below the prepared planes
 constexpr float BEST_INIT_BITS_F = 3.3961514e38f;  // 0x7F7F7F7F, main.cu:112
 
@@ -64,10 +72,15 @@ struct FusedArgs {
 };
 
 struct SmemLayout {
-    float4 ringAB[NWARP][WIN][4][32];  // a: planes 0,1  b: planes 2,3 ; lane-contiguous 16 B
-    uint4 ringP[NWARP][WIN][32];       // 8 halfs per lane: the masked lattice cost
-    float4 qbuf[2][NWARP][2][32];      // filtered row of each warp, double buffered
+    float4 ringAB[NWARP][WIN][4][32];  // consumer-private: a planes 0,1  b planes 2,3 ; lane-contiguous 16 B
+    uint4 ringP[NWARP][WIN][32];       // producer-private: 8 halfs per lane, the masked lattice cost
+    float4 hand[NWARP][2][4][32];      // producer -> consumer: S_P planes 0,1  S_IP planes 2,3, double buffered
+    float4 qbuf[2][NWARP][2][32];      // filtered row of each consumer warp, double buffered
 };
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 // 19-wide horizontal window sums for the 8 consecutive pixels this lane holds.
 // Lane L holds columns 8L..8L+7.  With LP_L[i] the lane-local prefix sums and T_L the lane
@@ -105,25 +118,28 @@ __device__ __forceinline__ void hsum19(const float (&v)[KPX], float (&h)[KPX]) {
 __device__ __forceinline__ __half2 u2h2(unsigned u) { return *reinterpret_cast<__half2*>(&u); }
 __device__ __forceinline__ unsigned h22u(__half2 h) { return *reinterpret_cast<unsigned*>(&h); }
 
-// operands of one row step, fetched one step ahead
-struct StepOps {
-    uint4 g0, g1;        // guide (I,G) half2 x8 at row yi
-    unsigned m[KPX];     // match (I,G) half2 x8 at row yi, columns x+d
-    float4 io0, io1;     // guide intensity at row yi-19 (leaves the first-stage window)
+// operands of one row step, fetched one step ahead; the producer and the consumer warp of a
+// pair each fetch only what their stage needs
+struct ProdOps {
+    uint4 g0, g1;     // guide (I,G) half2 x8 at row yi
+    unsigned m[KPX];  // match (I,G) half2 x8 at row yi, columns x+d
+    float4 io0, io1;  // guide intensity at row yi-19 (leaves the first-stage window)
+};
+struct ConsOps {
     float4 s0, s1, s2, s3;  // (mean_I, c2) x8 at row ya = yi-9
-    float4 iq0, iq1;     // guide intensity at row yq = yi-18
+    float4 iq0, iq1;        // guide intensity at row yq = yi-18
+};
+struct ProdPtrs {
+    const unsigned* g;
+    const unsigned* m;
+    const float* io;
+};
+struct ConsPtrs {
+    const float2* st;
+    const float* iq;
 };
 
-// Row pointers of the NEXT step's operands; advanced by one padded row per step.
-struct RowPtrs {
-    const unsigned* g;   // guide (I,G), row yi
-    const unsigned* m;   // match (I,G), row yi, already offset by d
-    const float* io;     // guide intensity, row yi-19
-    const float2* st;    // stats, row yi-9
-    const float* iq;     // guide intensity, row yi-18
-};
-
-__device__ __forceinline__ void load_ops(StepOps& o, const RowPtrs& p, int dep) {
+__device__ __forceinline__ void load_prod(ProdOps& o, const ProdPtrs& p, int dep) {
     const uint4* pg = reinterpret_cast<const uint4*>(p.g + dep);
     o.g0 = __ldg(pg);
     o.g1 = __ldg(pg + 1);
@@ -133,6 +149,8 @@ __device__ __forceinline__ void load_ops(StepOps& o, const RowPtrs& p, int dep) 
     const float4* po = reinterpret_cast<const float4*>(p.io + dep);
     o.io0 = __ldg(po);
     o.io1 = __ldg(po + 1);
+}
+__device__ __forceinline__ void load_cons(ConsOps& o, const ConsPtrs& p, int dep) {
     const float4* ps = reinterpret_cast<const float4*>(p.st + dep);
     o.s0 = __ldg(ps);
     o.s1 = __ldg(ps + 1);
@@ -148,12 +166,15 @@ __device__ __forceinline__ void load_ops(StepOps& o, const RowPtrs& p, int dep) 
 // wait for THIS step's operands is taken before the new loads are issued.  Without it the
 // first use of an operand waits on a scoreboard slot that the just-issued prefetch loads
 // share, i.e. on a full L2 round trip every step (ncu: 50 % of all stall samples, round 1).
-__device__ __forceinline__ int touch_ops(const StepOps& o) {
+__device__ __forceinline__ int touch(const ProdOps& o) {
     unsigned t = o.g0.x | o.g1.x;
 #pragma unroll
     for (int j = 0; j < KPX; j++) t |= o.m[j];
     t |= __float_as_uint(o.io0.x) | __float_as_uint(o.io1.x);
-    t |= __float_as_uint(o.s0.x) | __float_as_uint(o.s1.x) | __float_as_uint(o.s2.x) | __float_as_uint(o.s3.x);
+    return (int)t;
+}
+__device__ __forceinline__ int touch(const ConsOps& o) {
+    unsigned t = __float_as_uint(o.s0.x) | __float_as_uint(o.s1.x) | __float_as_uint(o.s2.x) | __float_as_uint(o.s3.x);
     t |= __float_as_uint(o.iq0.x) | __float_as_uint(o.iq1.x);
     return (int)t;
 }
@@ -166,11 +187,13 @@ __device__ __forceinline__ float inv_rows(int y, int y_global0, int frame_h, flo
     return __frcp_rn(scale * (float)ay);
 }
 
-__global__ void __launch_bounds__(NWARP * 32, 1) k_fused_cvf(const FusedArgs A) {
+__global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pair = warp & (NWARP - 1);   // warps p and p+4 share SM sub-partition p
+    const bool consumer = warp >= NWARP;
     int bid = blockIdx.x;
     const int view = bid % A.n_views;
     bid /= A.n_views;
@@ -181,93 +204,161 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_cvf(const FusedArgs A) 
 
     const int xs = strip * VALID_W - HALO;
     const int xl = xs + KPX * lane;
-    const unsigned* __restrict__ IGg = A.IG[view];
-    const unsigned* __restrict__ IGm = A.IG[1 - view];
-    const float* __restrict__ If = A.If[view];
-    const float2* __restrict__ st = A.st[view];
     const int pitch = A.pitch;
-
     const int dlo = A.dmin[view] + chunk * A.chunk_d;
     const int dcnt = min(A.chunk_d, A.size_d - chunk * A.chunk_d);
     const int ngroups = (dcnt + NWARP - 1) / NWARP;
     const int yb0 = A.y_out0 + band * A.band_rows;
     const int yb1 = min(yb0 + A.band_rows, A.y_out0 + A.rows_out);
+    const int y_first = yb0 - 2 * RAD;
+    const int nsteps = (yb1 - yb0) + 4 * RAD;  // 36 warm-up rows, then one output row per step
 
-    // per-lane column constants
-    float rx[KPX];         // 1 / clipped window width, 0 outside the image
-    __half2 wm[KPX];       // lattice weights (nI, nG), 0 outside the image (masks the cost)
+    if (!consumer) {
+        // =============================== PRODUCER: first stage ===============================
+        const unsigned* __restrict__ IGg = A.IG[view];
+        const unsigned* __restrict__ IGm = A.IG[1 - view];
+        const float* __restrict__ If = A.If[view];
+        __half2 wm[KPX];  // lattice weights (nI, nG), 0 outside the image (masks the cost)
+#pragma unroll
+        for (int j = 0; j < KPX; j++) {
+            int x = xl + j;
+            wm[j] = (x >= 0 && x < A.w) ? u2h2(A.wpack) : __float2half2_rn(0.0f);
+        }
+        const __half2 th = u2h2(A.thpack);
+        for (int g = 0; g < ngroups; g++) {
+            const int dk = g * NWARP + pair;
+            const bool active = dk < dcnt;
+            const int d = dlo + dk;
+            float VP[KPX], VIP[KPX];
+#pragma unroll
+            for (int j = 0; j < KPX; j++) VP[j] = VIP[j] = 0.0f;
+            for (int s = 0; s < WIN; s++) sm.ringP[pair][s][lane] = make_uint4(0u, 0u, 0u, 0u);
+            __syncthreads();  // group start (matches the consumers')
+            if (active) {
+                ProdPtrs rp;
+                const long long r0 = (long long)y_first * pitch + xl;
+                rp.g = IGg + r0;
+                rp.m = IGm + r0 + d;
+                rp.io = If + r0 - (long long)WIN * pitch;
+                int slot = 0;
+                ProdOps opsA, opsB;
+                load_prod(opsA, rp, 0);
+                auto step = [&](const ProdOps& o, ProdOps& nxt, int t) {
+                    rp.g += pitch;
+                    rp.m += pitch;
+                    rp.io += pitch;
+                    load_prod(nxt, rp, touch(o) & A.zero);
+                    const unsigned gg[KPX] = {o.g0.x, o.g0.y, o.g0.z, o.g0.w, o.g1.x, o.g1.y, o.g1.z, o.g1.w};
+                    const float iold[KPX] = {o.io0.x, o.io0.y, o.io0.z, o.io0.w, o.io1.x, o.io1.y, o.io1.z, o.io1.w};
+                    __half ph[KPX];
+#pragma unroll
+                    for (int j = 0; j < KPX; j++) {
+                        __half2 gv = u2h2(gg[j]);
+                        __half2 diff = __hsub2(gv, u2h2(o.m[j]));
+                        __half2 c = __hmin2(__habs2(diff), th);  // (min(|dI|,Tc), min(|dG|,2Tg))
+                        __half2 pr = __hmul2(c, wm[j]);
+                        ph[j] = __hadd(__low2half(pr), __high2half(pr));
+                        float pn = __half2float(ph[j]);
+                        float inew = __low2float(gv);
+                        VP[j] += pn;
+                        VIP[j] = fmaf(inew, pn, VIP[j]);
+                    }
+                    uint4 pold = sm.ringP[pair][slot][lane];
+                    uint4 pnew;
+                    pnew.x = h22u(__halves2half2(ph[0], ph[1]));
+                    pnew.y = h22u(__halves2half2(ph[2], ph[3]));
+                    pnew.z = h22u(__halves2half2(ph[4], ph[5]));
+                    pnew.w = h22u(__halves2half2(ph[6], ph[7]));
+                    sm.ringP[pair][slot][lane] = pnew;
+                    slot = (slot + 1 == WIN) ? 0 : slot + 1;
+                    const unsigned po[4] = {pold.x, pold.y, pold.z, pold.w};
+#pragma unroll
+                    for (int j = 0; j < KPX; j += 2) {
+                        float2 f = __half22float2(u2h2(po[j >> 1]));
+                        VP[j] -= f.x;
+                        VP[j + 1] -= f.y;
+                        VIP[j] = fmaf(-iold[j], f.x, VIP[j]);
+                        VIP[j + 1] = fmaf(-iold[j + 1], f.y, VIP[j + 1]);
+                    }
+                    float SP[KPX], SIP[KPX];
+                    hsum19(VP, SP);
+                    hsum19(VIP, SIP);
+                    float4* hd = &sm.hand[pair][t & 1][0][lane];
+                    hd[0] = make_float4(SP[0], SP[1], SP[2], SP[3]);
+                    hd[32] = make_float4(SP[4], SP[5], SP[6], SP[7]);
+                    hd[64] = make_float4(SIP[0], SIP[1], SIP[2], SIP[3]);
+                    hd[96] = make_float4(SIP[4], SIP[5], SIP[6], SIP[7]);
+                    // row t is published; the consumer finished reading the other slot before it
+                    // arrived here for row t-1, so the next row may overwrite it
+                    named_bar_sync(2 + pair, 64);
+                };
+                int t = 0;
+                for (; t + 1 < nsteps; t += 2) {
+                    step(opsA, opsB, t);
+                    step(opsB, opsA, t + 1);
+                }
+                if (t < nsteps) step(opsA, opsB, t);
+            }
+            __syncthreads();  // group end
+        }
+        return;
+    }
+
+    // ================================= CONSUMER: second stage =================================
+    const float* __restrict__ If = A.If[view];
+    const float2* __restrict__ st = A.st[view];
+    float rx[KPX];  // 1 / clipped window width, 0 outside the image
 #pragma unroll
     for (int j = 0; j < KPX; j++) {
         int x = xl + j;
-        bool in = (x >= 0 && x < A.w);
         int ax = min(A.w - 1, x + RAD) - max(0, x - RAD) + 1;
-        rx[j] = in ? __frcp_rn((float)ax) : 0.0f;
-        wm[j] = in ? u2h2(A.wpack) : __float2half2_rn(0.0f);
+        rx[j] = (x >= 0 && x < A.w) ? __frcp_rn((float)ax) : 0.0f;
     }
-    const __half2 th = u2h2(A.thpack);
-
     // merge role of this thread: strip-local columns 2t, 2t+1
-    const int mc = 2 * threadIdx.x;
+    const int mc = 2 * (threadIdx.x - NWARP * 32);
     const int mx = xs + mc;
     const bool mvalid0 = (mc >= HALO) && (mc < HALO + VALID_W) && (mx < A.w);
     const bool mvalid1 = (mc + 1 >= HALO) && (mc + 1 < HALO + VALID_W) && (mx + 1 < A.w);
     const int mlane = mc >> 3, mj = mc & 7;
+    const int qoff = ((mj >> 2) * 32 + mlane) * 4 + (mj & 3);
     const size_t planeS = (size_t)A.rows_out * A.pitchS;
     float* __restrict__ bestS = A.bestS + (size_t)(chunk * 2 + view) * planeS;
     float* __restrict__ labS = A.labS + (size_t)(chunk * 2 + view) * planeS;
 
     for (int g = 0; g < ngroups; g++) {
-        const int dk = g * NWARP + warp;
+        const int dk = g * NWARP + pair;
         const bool active = dk < dcnt;
-        const int d = dlo + (active ? dk : 0);
         const int dbase = dlo + g * NWARP;
-
-        // reset this warp's rings and running sums
-        float VP[KPX], VIP[KPX], Va[KPX], Vb[KPX];
+        float Va[KPX], Vb[KPX];
 #pragma unroll
-        for (int j = 0; j < KPX; j++) VP[j] = VIP[j] = Va[j] = Vb[j] = 0.0f;
+        for (int j = 0; j < KPX; j++) Va[j] = Vb[j] = 0.0f;
         for (int s = 0; s < WIN; s++) {
 #pragma unroll
-            for (int v = 0; v < 4; v++) sm.ringAB[warp][s][v][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-            sm.ringP[warp][s][lane] = make_uint4(0u, 0u, 0u, 0u);
+            for (int v = 0; v < 4; v++) sm.ringAB[pair][s][v][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (!active) {
             const float inf = __int_as_float(0x7f800000);
 #pragma unroll
             for (int b = 0; b < 2; b++)
 #pragma unroll
-                for (int v = 0; v < 2; v++) sm.qbuf[b][warp][v][lane] = make_float4(inf, inf, inf, inf);
+                for (int v = 0; v < 2; v++) sm.qbuf[b][pair][v][lane] = make_float4(inf, inf, inf, inf);
         }
-        __syncthreads();  // previous group's merges are done with qbuf; inf fills visible
+        __syncthreads();  // group start: previous group's merges are done with qbuf
 
-        int slot = 0;
-        int obuf = 0;
-        const int y_first = yb0 - 2 * RAD;
-        RowPtrs rp;
+        int slot = 0, obuf = 0;
+        ConsPtrs rp;
         {
             const long long r0 = (long long)y_first * pitch + xl;
-            rp.g = IGg + r0;
-            rp.m = IGm + r0 + d;
-            rp.io = If + r0 - (long long)WIN * pitch;
             rp.st = st + r0 - (long long)RAD * pitch;
             rp.iq = If + r0 - (long long)(2 * RAD) * pitch;
         }
-        auto advance = [&]() {
-            rp.g += pitch;
-            rp.m += pitch;
-            rp.io += pitch;
-            rp.st += pitch;
-            rp.iq += pitch;
-        };
-        StepOps opsA, opsB;
-        if (active) load_ops(opsA, rp, 0);
-        advance();
+        ConsOps opsA, opsB;
+        if (active) load_cons(opsA, rp, 0);
 
         // fold the 4 disparities of this group into (best,label): ascending d, `>=`
         auto merge = [&](int yq, float pb0, float pb1, float pl0, float pl1) {
             const size_t moff = (size_t)(yq - A.y_out0) * A.pitchS + mx;
             const float* qb = reinterpret_cast<const float*>(&sm.qbuf[obuf][0][0][0]);
-            const int qoff = ((mj >> 2) * 32 + mlane) * 4 + (mj & 3);
 #pragma unroll
             for (int wv = 0; wv < NWARP; wv++) {
                 float2 qv = *reinterpret_cast<const float2*>(qb + wv * 256 + qoff);
@@ -279,57 +370,32 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_cvf(const FusedArgs A) 
             if (mvalid1) { bestS[moff + 1] = pb1; labS[moff + 1] = pl1; }
             obuf ^= 1;
         };
-
-        // one row step.  EMIT: the second-stage window is complete for an output row.
-        auto step = [&](auto emit_tag, const StepOps& o, StepOps& nxt, int yi) {
-            constexpr bool EMIT = decltype(emit_tag)::value;
-            // take the scoreboard wait on this step's operands, then fetch the next row's
-            load_ops(nxt, rp, touch_ops(o) & A.zero);
-            advance();
-            const int yq = yi - 2 * RAD;
-            float pb0 = BEST_INIT_BITS_F, pb1 = BEST_INIT_BITS_F, pl0 = 0.0f, pl1 = 0.0f;
-            if (EMIT && g > 0) {  // prefetch the running (best,label) this thread will merge into
+        auto prefetch_best = [&](int yq, float& pb0, float& pb1, float& pl0, float& pl1) {
+            pb0 = pb1 = BEST_INIT_BITS_F;
+            pl0 = pl1 = 0.0f;
+            if (g > 0) {
                 const size_t moff = (size_t)(yq - A.y_out0) * A.pitchS + mx;
                 if (mvalid0) { pb0 = bestS[moff]; pl0 = labS[moff]; }
                 if (mvalid1) { pb1 = bestS[moff + 1]; pl1 = labS[moff + 1]; }
             }
-            // ---- first stage: lattice cost of row yi enters the window, row yi-19 leaves
-            const unsigned gg[KPX] = {o.g0.x, o.g0.y, o.g0.z, o.g0.w, o.g1.x, o.g1.y, o.g1.z, o.g1.w};
-            const float iold[KPX] = {o.io0.x, o.io0.y, o.io0.z, o.io0.w, o.io1.x, o.io1.y, o.io1.z, o.io1.w};
-            __half ph[KPX];
-#pragma unroll
-            for (int j = 0; j < KPX; j++) {
-                __half2 gv = u2h2(gg[j]);
-                __half2 diff = __hsub2(gv, u2h2(o.m[j]));
-                __half2 c = __hmin2(__habs2(diff), th);  // (min(|dI|,Tc), min(|dG|,2Tg))
-                __half2 pr = __hmul2(c, wm[j]);
-                ph[j] = __hadd(__low2half(pr), __high2half(pr));
-                float pn = __half2float(ph[j]);
-                float inew = __low2float(gv);
-                VP[j] += pn;
-                VIP[j] = fmaf(inew, pn, VIP[j]);
-            }
-            uint4 pold = sm.ringP[warp][slot][lane];
-            uint4 pnew;
-            pnew.x = h22u(__halves2half2(ph[0], ph[1]));
-            pnew.y = h22u(__halves2half2(ph[2], ph[3]));
-            pnew.z = h22u(__halves2half2(ph[4], ph[5]));
-            pnew.w = h22u(__halves2half2(ph[6], ph[7]));
-            sm.ringP[warp][slot][lane] = pnew;
-            const unsigned po[4] = {pold.x, pold.y, pold.z, pold.w};
-#pragma unroll
-            for (int j = 0; j < KPX; j += 2) {
-                float2 f = __half22float2(u2h2(po[j >> 1]));
-                VP[j] -= f.x;
-                VP[j + 1] -= f.y;
-                VIP[j] = fmaf(-iold[j], f.x, VIP[j]);
-                VIP[j + 1] = fmaf(-iold[j + 1], f.y, VIP[j + 1]);
-            }
-            float SP[KPX], SIP[KPX];
-            hsum19(VP, SP);
-            hsum19(VIP, SIP);
-            // ---- a, b at row ya = yi - 9
+        };
+
+        auto step = [&](auto emit_tag, const ConsOps& o, ConsOps& nxt, int t) {
+            constexpr bool EMIT = decltype(emit_tag)::value;
+            rp.st += pitch;
+            rp.iq += pitch;
+            load_cons(nxt, rp, touch(o) & A.zero);
+            const int yi = y_first + t;
+            const int yq = yi - 2 * RAD;
+            float pb0, pb1, pl0, pl1;
+            if (EMIT) prefetch_best(yq, pb0, pb1, pl0, pl1);
             const float ry1 = inv_rows(yi - RAD, A.y_global0, A.frame_h, A.S);
+            named_bar_sync(2 + pair, 64);  // the producer has published row t
+            const float4* hd = &sm.hand[pair][t & 1][0][lane];
+            const float4 p0 = hd[0], p1 = hd[32], q0 = hd[64], q1 = hd[96];
+            const float SP[KPX] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+            const float SIP[KPX] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+            // ---- a, b at row ya = yi - 9
             const float stt[16] = {o.s0.x, o.s0.y, o.s0.z, o.s0.w, o.s1.x, o.s1.y, o.s1.z, o.s1.w,
                                    o.s2.x, o.s2.y, o.s2.z, o.s2.w, o.s3.x, o.s3.y, o.s3.z, o.s3.w};
             float a[KPX], b[KPX];
@@ -342,12 +408,13 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_cvf(const FusedArgs A) 
                 b[j] = fmaf(-mI, a[j], mp);
             }
             // ---- second stage: (a,b) of row ya enter, row ya-19 leaves
-            float4 oa0 = sm.ringAB[warp][slot][0][lane], oa1 = sm.ringAB[warp][slot][1][lane];
-            float4 ob0 = sm.ringAB[warp][slot][2][lane], ob1 = sm.ringAB[warp][slot][3][lane];
-            sm.ringAB[warp][slot][0][lane] = make_float4(a[0], a[1], a[2], a[3]);
-            sm.ringAB[warp][slot][1][lane] = make_float4(a[4], a[5], a[6], a[7]);
-            sm.ringAB[warp][slot][2][lane] = make_float4(b[0], b[1], b[2], b[3]);
-            sm.ringAB[warp][slot][3][lane] = make_float4(b[4], b[5], b[6], b[7]);
+            float4 oa0 = sm.ringAB[pair][slot][0][lane], oa1 = sm.ringAB[pair][slot][1][lane];
+            float4 ob0 = sm.ringAB[pair][slot][2][lane], ob1 = sm.ringAB[pair][slot][3][lane];
+            sm.ringAB[pair][slot][0][lane] = make_float4(a[0], a[1], a[2], a[3]);
+            sm.ringAB[pair][slot][1][lane] = make_float4(a[4], a[5], a[6], a[7]);
+            sm.ringAB[pair][slot][2][lane] = make_float4(b[0], b[1], b[2], b[3]);
+            sm.ringAB[pair][slot][3][lane] = make_float4(b[4], b[5], b[6], b[7]);
+            slot = (slot + 1 == WIN) ? 0 : slot + 1;
             const float ao[KPX] = {oa0.x, oa0.y, oa0.z, oa0.w, oa1.x, oa1.y, oa1.z, oa1.w};
             const float bo[KPX] = {ob0.x, ob0.y, ob0.z, ob0.w, ob1.x, ob1.y, ob1.z, ob1.w};
 #pragma unroll
@@ -355,7 +422,6 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_cvf(const FusedArgs A) 
                 Va[j] += a[j] - ao[j];
                 Vb[j] += b[j] - bo[j];
             }
-            slot = (slot + 1 == WIN) ? 0 : slot + 1;
             if (EMIT) {
                 float SA[KPX], SB[KPX];
                 hsum19(Va, SA);
@@ -365,40 +431,34 @@ __global__ void __launch_bounds__(NWARP * 32, 1) k_fused_cvf(const FusedArgs A) 
                 float q[KPX];
 #pragma unroll
                 for (int j = 0; j < KPX; j++) q[j] = fmaf(SA[j], iq[j], SB[j]) * (rx[j] * ry2);
-                sm.qbuf[obuf][warp][0][lane] = make_float4(q[0], q[1], q[2], q[3]);
-                sm.qbuf[obuf][warp][1][lane] = make_float4(q[4], q[5], q[6], q[7]);
-                __syncthreads();
+                sm.qbuf[obuf][pair][0][lane] = make_float4(q[0], q[1], q[2], q[3]);
+                sm.qbuf[obuf][pair][1][lane] = make_float4(q[4], q[5], q[6], q[7]);
+                named_bar_sync(1, NWARP * 32);  // the 4 consumer warps
                 merge(yq, pb0, pb1, pl0, pl1);
             }
         };
 
-        const int yend = yb1 + 2 * RAD;  // exclusive: last emitted yq = yb1 - 1
         if (active) {
-            int yi = y_first;
-            // warm-up: 36 rows fill both windows, nothing is emitted (36 is even)
-            for (; yi < yb0 + 2 * RAD; yi += 2) {
-                step(std::false_type{}, opsA, opsB, yi);
-                step(std::false_type{}, opsB, opsA, yi + 1);
+            int t = 0;
+            for (; t < 4 * RAD; t += 2) {  // warm-up: 36 rows fill both windows
+                step(std::false_type{}, opsA, opsB, t);
+                step(std::false_type{}, opsB, opsA, t + 1);
             }
-            for (; yi + 1 < yend; yi += 2) {
-                step(std::true_type{}, opsA, opsB, yi);
-                step(std::true_type{}, opsB, opsA, yi + 1);
+            for (; t + 1 < nsteps; t += 2) {
+                step(std::true_type{}, opsA, opsB, t);
+                step(std::true_type{}, opsB, opsA, t + 1);
             }
-            if (yi < yend) step(std::true_type{}, opsA, opsB, yi);
+            if (t < nsteps) step(std::true_type{}, opsA, opsB, t);
         } else {
-            // a warp with no disparity in this (last, partial) group only takes part in the merge
+            // no disparity for this pair in the (last, partial) group: only take part in the merge
             for (int yq = yb0; yq < yb1; yq++) {
-                float pb0 = BEST_INIT_BITS_F, pb1 = BEST_INIT_BITS_F, pl0 = 0.0f, pl1 = 0.0f;
-                if (g > 0) {
-                    const size_t moff = (size_t)(yq - A.y_out0) * A.pitchS + mx;
-                    if (mvalid0) { pb0 = bestS[moff]; pl0 = labS[moff]; }
-                    if (mvalid1) { pb1 = bestS[moff + 1]; pl1 = labS[moff + 1]; }
-                }
-                __syncthreads();
+                float pb0, pb1, pl0, pl1;
+                prefetch_best(yq, pb0, pb1, pl0, pl1);
+                named_bar_sync(1, NWARP * 32);
                 merge(yq, pb0, pb1, pl0, pl1);
             }
         }
-        __syncthreads();
+        __syncthreads();  // group end
     }
 }
 
@@ -686,7 +746,7 @@ static int run_fused(sb200_ctx* ctx, const sb200_params* p, const uint8_t* const
     }
     A.n_views = n_views;
     const int nblocks = plan.n_strips * plan.n_bands * plan.n_chunks * n_views;
-    SB_LAUNCH(ctx, k_fused_cvf, nblocks, NWARP * 32, smem, A);
+    SB_LAUNCH(ctx, k_fused_cvf, nblocks, NTHREADS, smem, A);
     if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     for (int v = 0; v < n_views; v++) {
         if (!best[v] && !disp[v]) continue;
