@@ -47,6 +47,7 @@ constexpr int RAD = 9;
 constexpr int WIN = 2 * RAD + 1;  // 19
 constexpr int NWARP = 4;          // disparities in flight per block (= warp pairs)
 constexpr int NTHREADS = 2 * NWARP * 32;
+constexpr int ROWS = 2;           // image rows per pipeline iteration: independent horizontal work for ILP
 constexpr int PADY = 40;          // padding rows above/below the prepared planes
 constexpr float BEST_INIT_BITS_F = 3.3961514e38f;  // 0x7F7F7F7F, main.cu:112
 
@@ -74,12 +75,15 @@ struct FusedArgs {
 struct SmemLayout {
     float4 ringAB[NWARP][WIN][4][32];  // consumer-private: a planes 0,1  b planes 2,3 ; lane-contiguous 16 B
     uint4 ringP[NWARP][WIN][32];       // producer-private: 8 halfs per lane, the masked lattice cost
-    float4 hand[NWARP][2][4][32];      // producer -> consumer: S_P planes 0,1  S_IP planes 2,3, double buffered
-    float4 qbuf[2][NWARP][2][32];      // filtered row of each consumer warp, double buffered
+    float4 hand[NWARP][ROWS][4][32];   // producer -> consumer, ROWS rows: S_P planes 0,1  S_IP planes 2,3
+    float4 qbuf[2][NWARP][ROWS][2][32];  // filtered rows of each consumer warp, double buffered
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // 19-wide horizontal window sums for the 8 consecutive pixels this lane holds.
@@ -211,7 +215,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
     const int yb0 = A.y_out0 + band * A.band_rows;
     const int yb1 = min(yb0 + A.band_rows, A.y_out0 + A.rows_out);
     const int y_first = yb0 - 2 * RAD;
-    const int nsteps = (yb1 - yb0) + 4 * RAD;  // 36 warm-up rows, then one output row per step
+    // 36 warm-up rows, then one output row per input row; iterations take ROWS rows (the last
+    // one may run past the band: those rows read zero padding and are not stored)
+    const int niter = ((yb1 - yb0) + 4 * RAD + ROWS - 1) / ROWS;
+    const int BAR_FULL = 2 + pair, BAR_EMPTY = 2 + NWARP + pair;
 
     if (!consumer) {
         // =============================== PRODUCER: first stage ===============================
@@ -241,63 +248,85 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
                 rp.m = IGm + r0 + d;
                 rp.io = If + r0 - (long long)WIN * pitch;
                 int slot = 0;
-                ProdOps opsA, opsB;
-                load_prod(opsA, rp, 0);
-                auto step = [&](const ProdOps& o, ProdOps& nxt, int t) {
+                ProdOps opsA[ROWS], opsB[ROWS];
+#pragma unroll
+                for (int r = 0; r < ROWS; r++) {
+                    load_prod(opsA[r], rp, 0);
                     rp.g += pitch;
                     rp.m += pitch;
                     rp.io += pitch;
-                    load_prod(nxt, rp, touch(o) & A.zero);
-                    const unsigned gg[KPX] = {o.g0.x, o.g0.y, o.g0.z, o.g0.w, o.g1.x, o.g1.y, o.g1.z, o.g1.w};
-                    const float iold[KPX] = {o.io0.x, o.io0.y, o.io0.z, o.io0.w, o.io1.x, o.io1.y, o.io1.z, o.io1.w};
-                    __half ph[KPX];
-#pragma unroll
-                    for (int j = 0; j < KPX; j++) {
-                        __half2 gv = u2h2(gg[j]);
-                        __half2 diff = __hsub2(gv, u2h2(o.m[j]));
-                        __half2 c = __hmin2(__habs2(diff), th);  // (min(|dI|,Tc), min(|dG|,2Tg))
-                        __half2 pr = __hmul2(c, wm[j]);
-                        ph[j] = __hadd(__low2half(pr), __high2half(pr));
-                        float pn = __half2float(ph[j]);
-                        float inew = __low2float(gv);
-                        VP[j] += pn;
-                        VIP[j] = fmaf(inew, pn, VIP[j]);
-                    }
-                    uint4 pold = sm.ringP[pair][slot][lane];
-                    uint4 pnew;
-                    pnew.x = h22u(__halves2half2(ph[0], ph[1]));
-                    pnew.y = h22u(__halves2half2(ph[2], ph[3]));
-                    pnew.z = h22u(__halves2half2(ph[4], ph[5]));
-                    pnew.w = h22u(__halves2half2(ph[6], ph[7]));
-                    sm.ringP[pair][slot][lane] = pnew;
-                    slot = (slot + 1 == WIN) ? 0 : slot + 1;
-                    const unsigned po[4] = {pold.x, pold.y, pold.z, pold.w};
-#pragma unroll
-                    for (int j = 0; j < KPX; j += 2) {
-                        float2 f = __half22float2(u2h2(po[j >> 1]));
-                        VP[j] -= f.x;
-                        VP[j + 1] -= f.y;
-                        VIP[j] = fmaf(-iold[j], f.x, VIP[j]);
-                        VIP[j + 1] = fmaf(-iold[j + 1], f.y, VIP[j + 1]);
-                    }
-                    float SP[KPX], SIP[KPX];
-                    hsum19(VP, SP);
-                    hsum19(VIP, SIP);
-                    float4* hd = &sm.hand[pair][t & 1][0][lane];
-                    hd[0] = make_float4(SP[0], SP[1], SP[2], SP[3]);
-                    hd[32] = make_float4(SP[4], SP[5], SP[6], SP[7]);
-                    hd[64] = make_float4(SIP[0], SIP[1], SIP[2], SIP[3]);
-                    hd[96] = make_float4(SIP[4], SIP[5], SIP[6], SIP[7]);
-                    // row t is published; the consumer finished reading the other slot before it
-                    // arrived here for row t-1, so the next row may overwrite it
-                    named_bar_sync(2 + pair, 64);
-                };
-                int t = 0;
-                for (; t + 1 < nsteps; t += 2) {
-                    step(opsA, opsB, t);
-                    step(opsB, opsA, t + 1);
                 }
-                if (t < nsteps) step(opsA, opsB, t);
+                auto iter = [&](const ProdOps (&o)[ROWS], ProdOps (&nxt)[ROWS], int it) {
+                    int dep = 0;
+#pragma unroll
+                    for (int r = 0; r < ROWS; r++) dep |= touch(o[r]);
+                    dep &= A.zero;
+#pragma unroll
+                    for (int r = 0; r < ROWS; r++) {
+                        load_prod(nxt[r], rp, dep);
+                        rp.g += pitch;
+                        rp.m += pitch;
+                        rp.io += pitch;
+                    }
+                    float SP[ROWS][KPX], SIP[ROWS][KPX];
+#pragma unroll
+                    for (int r = 0; r < ROWS; r++) {
+                        const unsigned gg[KPX] = {o[r].g0.x, o[r].g0.y, o[r].g0.z, o[r].g0.w,
+                                                  o[r].g1.x, o[r].g1.y, o[r].g1.z, o[r].g1.w};
+                        const float iold[KPX] = {o[r].io0.x, o[r].io0.y, o[r].io0.z, o[r].io0.w,
+                                                 o[r].io1.x, o[r].io1.y, o[r].io1.z, o[r].io1.w};
+                        __half ph[KPX];
+#pragma unroll
+                        for (int j = 0; j < KPX; j++) {
+                            __half2 gv = u2h2(gg[j]);
+                            __half2 diff = __hsub2(gv, u2h2(o[r].m[j]));
+                            __half2 c = __hmin2(__habs2(diff), th);  // (min(|dI|,Tc), min(|dG|,2Tg))
+                            __half2 pr = __hmul2(c, wm[j]);
+                            ph[j] = __hadd(__low2half(pr), __high2half(pr));
+                            float pn = __half2float(ph[j]);
+                            float inew = __low2float(gv);
+                            VP[j] += pn;
+                            VIP[j] = fmaf(inew, pn, VIP[j]);
+                        }
+                        uint4 pold = sm.ringP[pair][slot][lane];
+                        uint4 pnew;
+                        pnew.x = h22u(__halves2half2(ph[0], ph[1]));
+                        pnew.y = h22u(__halves2half2(ph[2], ph[3]));
+                        pnew.z = h22u(__halves2half2(ph[4], ph[5]));
+                        pnew.w = h22u(__halves2half2(ph[6], ph[7]));
+                        sm.ringP[pair][slot][lane] = pnew;
+                        slot = (slot + 1 == WIN) ? 0 : slot + 1;
+                        const unsigned po[4] = {pold.x, pold.y, pold.z, pold.w};
+#pragma unroll
+                        for (int j = 0; j < KPX; j += 2) {
+                            float2 f = __half22float2(u2h2(po[j >> 1]));
+                            VP[j] -= f.x;
+                            VP[j + 1] -= f.y;
+                            VIP[j] = fmaf(-iold[j], f.x, VIP[j]);
+                            VIP[j + 1] = fmaf(-iold[j + 1], f.y, VIP[j + 1]);
+                        }
+                        hsum19(VP, SP[r]);
+                        hsum19(VIP, SIP[r]);
+                    }
+                    // the consumer has copied the previous rows out of the hand-off buffer
+                    if (it > 0) named_bar_sync(BAR_EMPTY, 64);
+#pragma unroll
+                    for (int r = 0; r < ROWS; r++) {
+                        float4* hd = &sm.hand[pair][r][0][lane];
+                        hd[0] = make_float4(SP[r][0], SP[r][1], SP[r][2], SP[r][3]);
+                        hd[32] = make_float4(SP[r][4], SP[r][5], SP[r][6], SP[r][7]);
+                        hd[64] = make_float4(SIP[r][0], SIP[r][1], SIP[r][2], SIP[r][3]);
+                        hd[96] = make_float4(SIP[r][4], SIP[r][5], SIP[r][6], SIP[r][7]);
+                    }
+                    __threadfence_block();
+                    named_bar_arrive(BAR_FULL, 64);
+                };
+                int it = 0;
+                for (; it + 1 < niter; it += 2) {
+                    iter(opsA, opsB, it);
+                    iter(opsB, opsA, it + 1);
+                }
+                if (it < niter) iter(opsA, opsB, it);
             }
             __syncthreads();  // group end
         }
@@ -341,7 +370,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
 #pragma unroll
             for (int b = 0; b < 2; b++)
 #pragma unroll
-                for (int v = 0; v < 2; v++) sm.qbuf[b][pair][v][lane] = make_float4(inf, inf, inf, inf);
+                for (int r = 0; r < ROWS; r++)
+#pragma unroll
+                    for (int v = 0; v < 2; v++) sm.qbuf[b][pair][r][v][lane] = make_float4(inf, inf, inf, inf);
         }
         __syncthreads();  // group start: previous group's merges are done with qbuf
 
@@ -352,110 +383,165 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
             rp.st = st + r0 - (long long)RAD * pitch;
             rp.iq = If + r0 - (long long)(2 * RAD) * pitch;
         }
-        ConsOps opsA, opsB;
-        if (active) load_cons(opsA, rp, 0);
-
-        // fold the 4 disparities of this group into (best,label): ascending d, `>=`
-        auto merge = [&](int yq, float pb0, float pb1, float pl0, float pl1) {
-            const size_t moff = (size_t)(yq - A.y_out0) * A.pitchS + mx;
-            const float* qb = reinterpret_cast<const float*>(&sm.qbuf[obuf][0][0][0]);
+        ConsOps opsA[ROWS], opsB[ROWS];
+        if (active) {
 #pragma unroll
-            for (int wv = 0; wv < NWARP; wv++) {
-                float2 qv = *reinterpret_cast<const float2*>(qb + wv * 256 + qoff);
-                float lab = (float)(dbase + wv);
-                if (pb0 >= qv.x) { pb0 = qv.x; pl0 = lab; }
-                if (pb1 >= qv.y) { pb1 = qv.y; pl1 = lab; }
+            for (int r = 0; r < ROWS; r++) {
+                load_cons(opsA[r], rp, 0);
+                rp.st += pitch;
+                rp.iq += pitch;
             }
-            if (mvalid0) { bestS[moff] = pb0; labS[moff] = pl0; }
-            if (mvalid1) { bestS[moff + 1] = pb1; labS[moff + 1] = pl1; }
+        }
+
+        struct Best { float b0, b1, l0, l1; };
+        // fold the 4 disparities of this group into (best,label): ascending d, `>=`
+        auto merge = [&](int yq0, Best (&pb)[ROWS]) {
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+                const int yq = yq0 + r;
+                const float* qb = reinterpret_cast<const float*>(&sm.qbuf[obuf][0][r][0][0]);
+                float b0 = pb[r].b0, b1 = pb[r].b1, l0 = pb[r].l0, l1 = pb[r].l1;
+#pragma unroll
+                for (int wv = 0; wv < NWARP; wv++) {
+                    float2 qv = *reinterpret_cast<const float2*>(qb + wv * (ROWS * 256) + qoff);
+                    float lab = (float)(dbase + wv);
+                    if (b0 >= qv.x) { b0 = qv.x; l0 = lab; }
+                    if (b1 >= qv.y) { b1 = qv.y; l1 = lab; }
+                }
+                if (yq < yb1) {
+                    const size_t moff = (size_t)(yq - A.y_out0) * A.pitchS + mx;
+                    if (mvalid0) { bestS[moff] = b0; labS[moff] = l0; }
+                    if (mvalid1) { bestS[moff + 1] = b1; labS[moff + 1] = l1; }
+                }
+            }
             obuf ^= 1;
         };
-        auto prefetch_best = [&](int yq, float& pb0, float& pb1, float& pl0, float& pl1) {
-            pb0 = pb1 = BEST_INIT_BITS_F;
-            pl0 = pl1 = 0.0f;
-            if (g > 0) {
-                const size_t moff = (size_t)(yq - A.y_out0) * A.pitchS + mx;
-                if (mvalid0) { pb0 = bestS[moff]; pl0 = labS[moff]; }
-                if (mvalid1) { pb1 = bestS[moff + 1]; pl1 = labS[moff + 1]; }
+        auto prefetch_best = [&](int yq0, Best (&pb)[ROWS]) {
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+                pb[r].b0 = pb[r].b1 = BEST_INIT_BITS_F;
+                pb[r].l0 = pb[r].l1 = 0.0f;
+                const int yq = yq0 + r;
+                if (g > 0 && yq < yb1) {
+                    const size_t moff = (size_t)(yq - A.y_out0) * A.pitchS + mx;
+                    if (mvalid0) { pb[r].b0 = bestS[moff]; pb[r].l0 = labS[moff]; }
+                    if (mvalid1) { pb[r].b1 = bestS[moff + 1]; pb[r].l1 = labS[moff + 1]; }
+                }
             }
         };
 
-        auto step = [&](auto emit_tag, const ConsOps& o, ConsOps& nxt, int t) {
+        auto iter = [&](auto emit_tag, const ConsOps (&o)[ROWS], ConsOps (&nxt)[ROWS], int it) {
             constexpr bool EMIT = decltype(emit_tag)::value;
-            rp.st += pitch;
-            rp.iq += pitch;
-            load_cons(nxt, rp, touch(o) & A.zero);
-            const int yi = y_first + t;
-            const int yq = yi - 2 * RAD;
-            float pb0, pb1, pl0, pl1;
-            if (EMIT) prefetch_best(yq, pb0, pb1, pl0, pl1);
-            const float ry1 = inv_rows(yi - RAD, A.y_global0, A.frame_h, A.S);
-            named_bar_sync(2 + pair, 64);  // the producer has published row t
-            const float4* hd = &sm.hand[pair][t & 1][0][lane];
-            const float4 p0 = hd[0], p1 = hd[32], q0 = hd[64], q1 = hd[96];
-            const float SP[KPX] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-            const float SIP[KPX] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-            // ---- a, b at row ya = yi - 9
-            const float stt[16] = {o.s0.x, o.s0.y, o.s0.z, o.s0.w, o.s1.x, o.s1.y, o.s1.z, o.s1.w,
-                                   o.s2.x, o.s2.y, o.s2.z, o.s2.w, o.s3.x, o.s3.y, o.s3.z, o.s3.w};
-            float a[KPX], b[KPX];
+            int dep = 0;
 #pragma unroll
-            for (int j = 0; j < KPX; j++) {
-                const float mI = stt[2 * j], c2 = stt[2 * j + 1];
-                float cov = fmaf(-mI, SP[j], SIP[j]);
-                a[j] = cov * c2;
-                float mp = SP[j] * (rx[j] * ry1);
-                b[j] = fmaf(-mI, a[j], mp);
+            for (int r = 0; r < ROWS; r++) dep |= touch(o[r]);
+            dep &= A.zero;
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+                load_cons(nxt[r], rp, dep);
+                rp.st += pitch;
+                rp.iq += pitch;
             }
-            // ---- second stage: (a,b) of row ya enter, row ya-19 leaves
-            float4 oa0 = sm.ringAB[pair][slot][0][lane], oa1 = sm.ringAB[pair][slot][1][lane];
-            float4 ob0 = sm.ringAB[pair][slot][2][lane], ob1 = sm.ringAB[pair][slot][3][lane];
-            sm.ringAB[pair][slot][0][lane] = make_float4(a[0], a[1], a[2], a[3]);
-            sm.ringAB[pair][slot][1][lane] = make_float4(a[4], a[5], a[6], a[7]);
-            sm.ringAB[pair][slot][2][lane] = make_float4(b[0], b[1], b[2], b[3]);
-            sm.ringAB[pair][slot][3][lane] = make_float4(b[4], b[5], b[6], b[7]);
-            slot = (slot + 1 == WIN) ? 0 : slot + 1;
-            const float ao[KPX] = {oa0.x, oa0.y, oa0.z, oa0.w, oa1.x, oa1.y, oa1.z, oa1.w};
-            const float bo[KPX] = {ob0.x, ob0.y, ob0.z, ob0.w, ob1.x, ob1.y, ob1.z, ob1.w};
+            const int yi0 = y_first + it * ROWS;
+            const int yq0 = yi0 - 2 * RAD;
+            Best pb[ROWS];
+            if (EMIT) prefetch_best(yq0, pb);
+            float ry1[ROWS];
 #pragma unroll
-            for (int j = 0; j < KPX; j++) {
-                Va[j] += a[j] - ao[j];
-                Vb[j] += b[j] - bo[j];
+            for (int r = 0; r < ROWS; r++) ry1[r] = inv_rows(yi0 + r - RAD, A.y_global0, A.frame_h, A.S);
+            named_bar_sync(BAR_FULL, 64);  // the producer has published rows yi0 .. yi0+ROWS-1
+            float SP[ROWS][KPX], SIP[ROWS][KPX];
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+                const float4* hd = &sm.hand[pair][r][0][lane];
+                const float4 p0 = hd[0], p1 = hd[32], q0 = hd[64], q1 = hd[96];
+                SP[r][0] = p0.x; SP[r][1] = p0.y; SP[r][2] = p0.z; SP[r][3] = p0.w;
+                SP[r][4] = p1.x; SP[r][5] = p1.y; SP[r][6] = p1.z; SP[r][7] = p1.w;
+                SIP[r][0] = q0.x; SIP[r][1] = q0.y; SIP[r][2] = q0.z; SIP[r][3] = q0.w;
+                SIP[r][4] = q1.x; SIP[r][5] = q1.y; SIP[r][6] = q1.z; SIP[r][7] = q1.w;
+            }
+            // the values are in registers (each SP/SIP feeds the arithmetic below, so the loads
+            // have completed before this point is passed): release the buffer to the producer
+            float relv = 0.0f;
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) relv += SP[r][0] + SP[r][4] + SIP[r][0] + SIP[r][4];
+            if (it + 1 < niter) {
+                if (__float_as_int(relv) == A.zero - 12345) __threadfence_block();  // keeps the loads above the arrive
+                named_bar_arrive(BAR_EMPTY, 64);
+            }
+            float SA[ROWS][KPX], SB[ROWS][KPX];
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+                // ---- a, b at row ya = yi - 9
+                const float stt[16] = {o[r].s0.x, o[r].s0.y, o[r].s0.z, o[r].s0.w, o[r].s1.x, o[r].s1.y, o[r].s1.z, o[r].s1.w,
+                                       o[r].s2.x, o[r].s2.y, o[r].s2.z, o[r].s2.w, o[r].s3.x, o[r].s3.y, o[r].s3.z, o[r].s3.w};
+                float a[KPX], b[KPX];
+#pragma unroll
+                for (int j = 0; j < KPX; j++) {
+                    const float mI = stt[2 * j], c2 = stt[2 * j + 1];
+                    float cov = fmaf(-mI, SP[r][j], SIP[r][j]);
+                    a[j] = cov * c2;
+                    float mp = SP[r][j] * (rx[j] * ry1[r]);
+                    b[j] = fmaf(-mI, a[j], mp);
+                }
+                // ---- second stage: (a,b) of row ya enter, row ya-19 leaves
+                float4 oa0 = sm.ringAB[pair][slot][0][lane], oa1 = sm.ringAB[pair][slot][1][lane];
+                float4 ob0 = sm.ringAB[pair][slot][2][lane], ob1 = sm.ringAB[pair][slot][3][lane];
+                sm.ringAB[pair][slot][0][lane] = make_float4(a[0], a[1], a[2], a[3]);
+                sm.ringAB[pair][slot][1][lane] = make_float4(a[4], a[5], a[6], a[7]);
+                sm.ringAB[pair][slot][2][lane] = make_float4(b[0], b[1], b[2], b[3]);
+                sm.ringAB[pair][slot][3][lane] = make_float4(b[4], b[5], b[6], b[7]);
+                slot = (slot + 1 == WIN) ? 0 : slot + 1;
+                const float ao[KPX] = {oa0.x, oa0.y, oa0.z, oa0.w, oa1.x, oa1.y, oa1.z, oa1.w};
+                const float bo[KPX] = {ob0.x, ob0.y, ob0.z, ob0.w, ob1.x, ob1.y, ob1.z, ob1.w};
+#pragma unroll
+                for (int j = 0; j < KPX; j++) {
+                    Va[j] += a[j] - ao[j];
+                    Vb[j] += b[j] - bo[j];
+                }
+                if (EMIT) {
+                    hsum19(Va, SA[r]);
+                    hsum19(Vb, SB[r]);
+                }
             }
             if (EMIT) {
-                float SA[KPX], SB[KPX];
-                hsum19(Va, SA);
-                hsum19(Vb, SB);
-                const float ry2 = inv_rows(yq, A.y_global0, A.frame_h, 1.0f);
-                const float iq[KPX] = {o.iq0.x, o.iq0.y, o.iq0.z, o.iq0.w, o.iq1.x, o.iq1.y, o.iq1.z, o.iq1.w};
-                float q[KPX];
 #pragma unroll
-                for (int j = 0; j < KPX; j++) q[j] = fmaf(SA[j], iq[j], SB[j]) * (rx[j] * ry2);
-                sm.qbuf[obuf][pair][0][lane] = make_float4(q[0], q[1], q[2], q[3]);
-                sm.qbuf[obuf][pair][1][lane] = make_float4(q[4], q[5], q[6], q[7]);
+                for (int r = 0; r < ROWS; r++) {
+                    const float ry2 = inv_rows(yq0 + r, A.y_global0, A.frame_h, 1.0f);
+                    const float iq[KPX] = {o[r].iq0.x, o[r].iq0.y, o[r].iq0.z, o[r].iq0.w,
+                                           o[r].iq1.x, o[r].iq1.y, o[r].iq1.z, o[r].iq1.w};
+                    float q[KPX];
+#pragma unroll
+                    for (int j = 0; j < KPX; j++) q[j] = fmaf(SA[r][j], iq[j], SB[r][j]) * (rx[j] * ry2);
+                    sm.qbuf[obuf][pair][r][0][lane] = make_float4(q[0], q[1], q[2], q[3]);
+                    sm.qbuf[obuf][pair][r][1][lane] = make_float4(q[4], q[5], q[6], q[7]);
+                }
                 named_bar_sync(1, NWARP * 32);  // the 4 consumer warps
-                merge(yq, pb0, pb1, pl0, pl1);
+                merge(yq0, pb);
             }
         };
 
+        constexpr int WARM_IT = 4 * RAD / ROWS;  // 36 warm-up rows fill both windows
+        static_assert((4 * RAD) % ROWS == 0, "ROWS must divide the warm-up length");
         if (active) {
-            int t = 0;
-            for (; t < 4 * RAD; t += 2) {  // warm-up: 36 rows fill both windows
-                step(std::false_type{}, opsA, opsB, t);
-                step(std::false_type{}, opsB, opsA, t + 1);
+            int it = 0;
+            for (; it < WARM_IT; it += 2) {
+                iter(std::false_type{}, opsA, opsB, it);
+                iter(std::false_type{}, opsB, opsA, it + 1);
             }
-            for (; t + 1 < nsteps; t += 2) {
-                step(std::true_type{}, opsA, opsB, t);
-                step(std::true_type{}, opsB, opsA, t + 1);
+            for (; it + 1 < niter; it += 2) {
+                iter(std::true_type{}, opsA, opsB, it);
+                iter(std::true_type{}, opsB, opsA, it + 1);
             }
-            if (t < nsteps) step(std::true_type{}, opsA, opsB, t);
+            if (it < niter) iter(std::true_type{}, opsA, opsB, it);
         } else {
             // no disparity for this pair in the (last, partial) group: only take part in the merge
-            for (int yq = yb0; yq < yb1; yq++) {
-                float pb0, pb1, pl0, pl1;
-                prefetch_best(yq, pb0, pb1, pl0, pl1);
+            for (int it = WARM_IT; it < niter; it++) {
+                const int yq0 = yb0 + (it - WARM_IT) * ROWS;
+                Best pb[ROWS];
+                prefetch_best(yq0, pb);
                 named_bar_sync(1, NWARP * 32);
-                merge(yq, pb0, pb1, pl0, pl1);
+                merge(yq0, pb);
             }
         }
         __syncthreads();  // group end
