@@ -73,10 +73,8 @@ struct FusedArgs {
 };
 
 struct SmemLayout {
-    float4 ringAB[NWARP][WIN][4][32];  // consumer-private: a planes 0,1  b planes 2,3 ; lane-contiguous 16 B
-    uint4 ringP[NWARP][WIN][32];       // producer-private: 8 halfs per lane, the masked lattice cost
-    float4 hand[NWARP][ROWS][4][32];   // producer -> consumer, ROWS rows: S_P planes 0,1  S_IP planes 2,3
     float4 qbuf[2][NWARP][ROWS][2][32];  // filtered rows of each consumer warp, double buffered
+    uint32_t tmem_base;
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -84,6 +82,68 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ---- Tensor Memory as per-thread scratch -------------------------------------------------
+// The 19-row rings and the producer->consumer hand-off live in TMEM (256 KB per SM, idle in a
+// kernel without tensor-core work) instead of shared memory: tcgen05.ld/st have their own data
+// path, so this traffic (72 of ~205 wavefronts per row, round-1 ncu: L1TEX data pipe at 78 %)
+// leaves the shared-memory/shuffle/L1 pipe.  With the 32x32b shape every thread of a warp owns
+// one TMEM lane (warp w may touch lanes 32*(w%4)..+31) and N consecutive 32-bit columns, i.e.
+// private scratch; warps p and p+4 (a producer/consumer pair) share a lane quarter, which is
+// what lets the producer hand its rows to the consumer through TMEM.
+// Column map of one lane (512 allocated): [0,304) ring of (a[8],b[8]) x 19 slots,
+// [304,380) ring of the lattice cost (8 halfs = 4 words) x 19 slots, [384,416) hand-off rows.
+constexpr uint32_t TM_COLS = 512;
+constexpr uint32_t TM_RING_AB = 0, TM_RING_P = 304, TM_HAND = 384;
+
+__device__ __forceinline__ void tm_alloc(uint32_t* smem_dst) {  // one converged warp
+    uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "r"(TM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tm_dealloc(uint32_t taddr) {  // the warp that allocated
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(TM_COLS) : "memory");
+}
+__device__ __forceinline__ void tm_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tm_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tm_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3])
+                 : "memory");
+}
+__device__ __forceinline__ void tm_ld16(uint32_t taddr, float (&a)[8], float (&b)[8]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+        "[%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        a[j] = __uint_as_float(r[j]);
+        b[j] = __uint_as_float(r[8 + j]);
+    }
+}
+__device__ __forceinline__ void tm_st16(uint32_t taddr, const float (&a)[8], const float (&b)[8]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16};" ::"r"(taddr),
+        "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+        "r"(__float_as_uint(a[4])), "r"(__float_as_uint(a[5])), "r"(__float_as_uint(a[6])), "r"(__float_as_uint(a[7])),
+        "r"(__float_as_uint(b[0])), "r"(__float_as_uint(b[1])), "r"(__float_as_uint(b[2])), "r"(__float_as_uint(b[3])),
+        "r"(__float_as_uint(b[4])), "r"(__float_as_uint(b[5])), "r"(__float_as_uint(b[6])), "r"(__float_as_uint(b[7]))
+        : "memory");
 }
 
 // 19-wide horizontal window sums for the 8 consecutive pixels this lane holds.
@@ -196,7 +256,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
     SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int pair = warp & (NWARP - 1);   // warps p and p+4 share SM sub-partition p
+    const int pair = warp & (NWARP - 1);   // warps p and p+4 share SM sub-partition p and TMEM lane quarter p
     const bool consumer = warp >= NWARP;
     int bid = blockIdx.x;
     const int view = bid % A.n_views;
@@ -220,6 +280,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
     const int niter = ((yb1 - yb0) + 4 * RAD + ROWS - 1) / ROWS;
     const int BAR_FULL = 2 + pair, BAR_EMPTY = 2 + NWARP + pair;
 
+    // Tensor Memory: all 512 columns of the SM, one block per SM (register-limited)
+    if (warp == 0) tm_alloc(&sm.tmem_base);
+    tm_fence_before();
+    __syncthreads();
+    tm_fence_after();
+    const uint32_t tbase = sm.tmem_base + ((uint32_t)(pair * 32) << 16);
+    const uint32_t tAB = tbase + TM_RING_AB, tP = tbase + TM_RING_P, tH = tbase + TM_HAND;
+
     if (!consumer) {
         // =============================== PRODUCER: first stage ===============================
         const unsigned* __restrict__ IGg = A.IG[view];
@@ -239,7 +307,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
             float VP[KPX], VIP[KPX];
 #pragma unroll
             for (int j = 0; j < KPX; j++) VP[j] = VIP[j] = 0.0f;
-            for (int s = 0; s < WIN; s++) sm.ringP[pair][s][lane] = make_uint4(0u, 0u, 0u, 0u);
+            {
+                const uint32_t z[4] = {0u, 0u, 0u, 0u};
+                for (int s = 0; s < WIN; s++) tm_st4(tP + 4 * s, z);
+                tm_wait_st();
+            }
             __syncthreads();  // group start (matches the consumers')
             if (active) {
                 ProdPtrs rp;
@@ -268,13 +340,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
                         rp.m += pitch;
                         rp.io += pitch;
                     }
+                    // the lattice costs that leave the window (rows yi-19), from the TMEM ring
+                    uint32_t pold[ROWS][4];
+                    int slots[ROWS];
+#pragma unroll
+                    for (int r = 0; r < ROWS; r++) {
+                        slots[r] = slot;
+                        tm_ld4(tP + 4 * slot, pold[r]);
+                        slot = (slot + 1 == WIN) ? 0 : slot + 1;
+                    }
                     float SP[ROWS][KPX], SIP[ROWS][KPX];
+                    uint32_t pnew[ROWS][4];
+                    float pn[ROWS][KPX];
 #pragma unroll
                     for (int r = 0; r < ROWS; r++) {
                         const unsigned gg[KPX] = {o[r].g0.x, o[r].g0.y, o[r].g0.z, o[r].g0.w,
                                                   o[r].g1.x, o[r].g1.y, o[r].g1.z, o[r].g1.w};
-                        const float iold[KPX] = {o[r].io0.x, o[r].io0.y, o[r].io0.z, o[r].io0.w,
-                                                 o[r].io1.x, o[r].io1.y, o[r].io1.z, o[r].io1.w};
                         __half ph[KPX];
 #pragma unroll
                         for (int j = 0; j < KPX; j++) {
@@ -283,42 +364,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
                             __half2 c = __hmin2(__habs2(diff), th);  // (min(|dI|,Tc), min(|dG|,2Tg))
                             __half2 pr = __hmul2(c, wm[j]);
                             ph[j] = __hadd(__low2half(pr), __high2half(pr));
-                            float pn = __half2float(ph[j]);
-                            float inew = __low2float(gv);
-                            VP[j] += pn;
-                            VIP[j] = fmaf(inew, pn, VIP[j]);
+                            pn[r][j] = __half2float(ph[j]);
                         }
-                        uint4 pold = sm.ringP[pair][slot][lane];
-                        uint4 pnew;
-                        pnew.x = h22u(__halves2half2(ph[0], ph[1]));
-                        pnew.y = h22u(__halves2half2(ph[2], ph[3]));
-                        pnew.z = h22u(__halves2half2(ph[4], ph[5]));
-                        pnew.w = h22u(__halves2half2(ph[6], ph[7]));
-                        sm.ringP[pair][slot][lane] = pnew;
-                        slot = (slot + 1 == WIN) ? 0 : slot + 1;
-                        const unsigned po[4] = {pold.x, pold.y, pold.z, pold.w};
+                        pnew[r][0] = h22u(__halves2half2(ph[0], ph[1]));
+                        pnew[r][1] = h22u(__halves2half2(ph[2], ph[3]));
+                        pnew[r][2] = h22u(__halves2half2(ph[4], ph[5]));
+                        pnew[r][3] = h22u(__halves2half2(ph[6], ph[7]));
+                    }
+                    tm_wait_ld();  // pold is in registers; the slots may be overwritten
+#pragma unroll
+                    for (int r = 0; r < ROWS; r++) {
+                        tm_st4(tP + 4 * slots[r], pnew[r]);
+                        const unsigned gg[KPX] = {o[r].g0.x, o[r].g0.y, o[r].g0.z, o[r].g0.w,
+                                                  o[r].g1.x, o[r].g1.y, o[r].g1.z, o[r].g1.w};
+                        const float iold[KPX] = {o[r].io0.x, o[r].io0.y, o[r].io0.z, o[r].io0.w,
+                                                 o[r].io1.x, o[r].io1.y, o[r].io1.z, o[r].io1.w};
 #pragma unroll
                         for (int j = 0; j < KPX; j += 2) {
-                            float2 f = __half22float2(u2h2(po[j >> 1]));
-                            VP[j] -= f.x;
-                            VP[j + 1] -= f.y;
+                            float2 f = __half22float2(u2h2(pold[r][j >> 1]));
+                            float i0 = __low2float(u2h2(gg[j])), i1 = __low2float(u2h2(gg[j + 1]));
+                            VP[j] += pn[r][j] - f.x;
+                            VP[j + 1] += pn[r][j + 1] - f.y;
+                            VIP[j] = fmaf(i0, pn[r][j], VIP[j]);
+                            VIP[j + 1] = fmaf(i1, pn[r][j + 1], VIP[j + 1]);
                             VIP[j] = fmaf(-iold[j], f.x, VIP[j]);
                             VIP[j + 1] = fmaf(-iold[j + 1], f.y, VIP[j + 1]);
                         }
                         hsum19(VP, SP[r]);
                         hsum19(VIP, SIP[r]);
                     }
-                    // the consumer has copied the previous rows out of the hand-off buffer
-                    if (it > 0) named_bar_sync(BAR_EMPTY, 64);
-#pragma unroll
-                    for (int r = 0; r < ROWS; r++) {
-                        float4* hd = &sm.hand[pair][r][0][lane];
-                        hd[0] = make_float4(SP[r][0], SP[r][1], SP[r][2], SP[r][3]);
-                        hd[32] = make_float4(SP[r][4], SP[r][5], SP[r][6], SP[r][7]);
-                        hd[64] = make_float4(SIP[r][0], SIP[r][1], SIP[r][2], SIP[r][3]);
-                        hd[96] = make_float4(SIP[r][4], SIP[r][5], SIP[r][6], SIP[r][7]);
+                    // the consumer has copied the previous rows out of the hand-off columns
+                    if (it > 0) {
+                        named_bar_sync(BAR_EMPTY, 64);
+                        tm_fence_after();
                     }
-                    __threadfence_block();
+#pragma unroll
+                    for (int r = 0; r < ROWS; r++) tm_st16(tH + 16 * r, SP[r], SIP[r]);
+                    tm_wait_st();
+                    tm_fence_before();
                     named_bar_arrive(BAR_FULL, 64);
                 };
                 int it = 0;
@@ -330,221 +413,217 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
             }
             __syncthreads();  // group end
         }
-        return;
-    }
-
-    // ================================= CONSUMER: second stage =================================
-    const float* __restrict__ If = A.If[view];
-    const float2* __restrict__ st = A.st[view];
-    float rx[KPX];  // 1 / clipped window width, 0 outside the image
+    } else {
+        // ================================ CONSUMER: second stage ================================
+        const float* __restrict__ If = A.If[view];
+        const float2* __restrict__ st = A.st[view];
+        float rx[KPX];  // 1 / clipped window width, 0 outside the image
 #pragma unroll
-    for (int j = 0; j < KPX; j++) {
-        int x = xl + j;
-        int ax = min(A.w - 1, x + RAD) - max(0, x - RAD) + 1;
-        rx[j] = (x >= 0 && x < A.w) ? __frcp_rn((float)ax) : 0.0f;
-    }
-    // merge role of this thread: strip-local columns 2t, 2t+1
-    const int mc = 2 * (threadIdx.x - NWARP * 32);
-    const int mx = xs + mc;
-    const bool mvalid0 = (mc >= HALO) && (mc < HALO + VALID_W) && (mx < A.w);
-    const bool mvalid1 = (mc + 1 >= HALO) && (mc + 1 < HALO + VALID_W) && (mx + 1 < A.w);
-    const int mlane = mc >> 3, mj = mc & 7;
-    const int qoff = ((mj >> 2) * 32 + mlane) * 4 + (mj & 3);
-    const size_t planeS = (size_t)A.rows_out * A.pitchS;
-    float* __restrict__ bestS = A.bestS + (size_t)(chunk * 2 + view) * planeS;
-    float* __restrict__ labS = A.labS + (size_t)(chunk * 2 + view) * planeS;
-
-    for (int g = 0; g < ngroups; g++) {
-        const int dk = g * NWARP + pair;
-        const bool active = dk < dcnt;
-        const int dbase = dlo + g * NWARP;
-        float Va[KPX], Vb[KPX];
-#pragma unroll
-        for (int j = 0; j < KPX; j++) Va[j] = Vb[j] = 0.0f;
-        for (int s = 0; s < WIN; s++) {
-#pragma unroll
-            for (int v = 0; v < 4; v++) sm.ringAB[pair][s][v][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < KPX; j++) {
+            int x = xl + j;
+            int ax = min(A.w - 1, x + RAD) - max(0, x - RAD) + 1;
+            rx[j] = (x >= 0 && x < A.w) ? __frcp_rn((float)ax) : 0.0f;
         }
-        if (!active) {
-            const float inf = __int_as_float(0x7f800000);
-#pragma unroll
-            for (int b = 0; b < 2; b++)
-#pragma unroll
-                for (int r = 0; r < ROWS; r++)
-#pragma unroll
-                    for (int v = 0; v < 2; v++) sm.qbuf[b][pair][r][v][lane] = make_float4(inf, inf, inf, inf);
-        }
-        __syncthreads();  // group start: previous group's merges are done with qbuf
+        // merge role of this thread: strip-local columns 2t, 2t+1
+        const int mc = 2 * (threadIdx.x - NWARP * 32);
+        const int mx = xs + mc;
+        const bool mvalid0 = (mc >= HALO) && (mc < HALO + VALID_W) && (mx < A.w);
+        const bool mvalid1 = (mc + 1 >= HALO) && (mc + 1 < HALO + VALID_W) && (mx + 1 < A.w);
+        const int mlane = mc >> 3, mj = mc & 7;
+        const int qoff = ((mj >> 2) * 32 + mlane) * 4 + (mj & 3);
+        const size_t planeS = (size_t)A.rows_out * A.pitchS;
+        float* __restrict__ bestS = A.bestS + (size_t)(chunk * 2 + view) * planeS;
+        float* __restrict__ labS = A.labS + (size_t)(chunk * 2 + view) * planeS;
 
-        int slot = 0, obuf = 0;
-        ConsPtrs rp;
-        {
-            const long long r0 = (long long)y_first * pitch + xl;
-            rp.st = st + r0 - (long long)RAD * pitch;
-            rp.iq = If + r0 - (long long)(2 * RAD) * pitch;
-        }
-        ConsOps opsA[ROWS], opsB[ROWS];
-        if (active) {
+        for (int g = 0; g < ngroups; g++) {
+            const int dk = g * NWARP + pair;
+            const bool active = dk < dcnt;
+            const int dbase = dlo + g * NWARP;
+            float Va[KPX], Vb[KPX];
 #pragma unroll
-            for (int r = 0; r < ROWS; r++) {
-                load_cons(opsA[r], rp, 0);
-                rp.st += pitch;
-                rp.iq += pitch;
+            for (int j = 0; j < KPX; j++) Va[j] = Vb[j] = 0.0f;
+            for (int s = 0; s < WIN; s++) tm_st16(tAB + 16 * s, Va, Vb);  // zeros
+            tm_wait_st();
+            if (!active) {
+                const float inf = __int_as_float(0x7f800000);
+#pragma unroll
+                for (int b = 0; b < 2; b++)
+#pragma unroll
+                    for (int r = 0; r < ROWS; r++)
+#pragma unroll
+                        for (int v = 0; v < 2; v++) sm.qbuf[b][pair][r][v][lane] = make_float4(inf, inf, inf, inf);
             }
-        }
+            __syncthreads();  // group start: previous group's merges are done with qbuf
 
-        struct Best { float b0, b1, l0, l1; };
-        // fold the 4 disparities of this group into (best,label): ascending d, `>=`
-        auto merge = [&](int yq0, Best (&pb)[ROWS]) {
-#pragma unroll
-            for (int r = 0; r < ROWS; r++) {
-                const int yq = yq0 + r;
-                const float* qb = reinterpret_cast<const float*>(&sm.qbuf[obuf][0][r][0][0]);
-                float b0 = pb[r].b0, b1 = pb[r].b1, l0 = pb[r].l0, l1 = pb[r].l1;
-#pragma unroll
-                for (int wv = 0; wv < NWARP; wv++) {
-                    float2 qv = *reinterpret_cast<const float2*>(qb + wv * (ROWS * 256) + qoff);
-                    float lab = (float)(dbase + wv);
-                    if (b0 >= qv.x) { b0 = qv.x; l0 = lab; }
-                    if (b1 >= qv.y) { b1 = qv.y; l1 = lab; }
-                }
-                if (yq < yb1) {
-                    const size_t moff = (size_t)(yq - A.y_out0) * A.pitchS + mx;
-                    if (mvalid0) { bestS[moff] = b0; labS[moff] = l0; }
-                    if (mvalid1) { bestS[moff + 1] = b1; labS[moff + 1] = l1; }
-                }
+            int slot = 0, obuf = 0;
+            ConsPtrs rp;
+            {
+                const long long r0 = (long long)y_first * pitch + xl;
+                rp.st = st + r0 - (long long)RAD * pitch;
+                rp.iq = If + r0 - (long long)(2 * RAD) * pitch;
             }
-            obuf ^= 1;
-        };
-        auto prefetch_best = [&](int yq0, Best (&pb)[ROWS]) {
-#pragma unroll
-            for (int r = 0; r < ROWS; r++) {
-                pb[r].b0 = pb[r].b1 = BEST_INIT_BITS_F;
-                pb[r].l0 = pb[r].l1 = 0.0f;
-                const int yq = yq0 + r;
-                if (g > 0 && yq < yb1) {
-                    const size_t moff = (size_t)(yq - A.y_out0) * A.pitchS + mx;
-                    if (mvalid0) { pb[r].b0 = bestS[moff]; pb[r].l0 = labS[moff]; }
-                    if (mvalid1) { pb[r].b1 = bestS[moff + 1]; pb[r].l1 = labS[moff + 1]; }
-                }
-            }
-        };
-
-        auto iter = [&](auto emit_tag, const ConsOps (&o)[ROWS], ConsOps (&nxt)[ROWS], int it) {
-            constexpr bool EMIT = decltype(emit_tag)::value;
-            int dep = 0;
-#pragma unroll
-            for (int r = 0; r < ROWS; r++) dep |= touch(o[r]);
-            dep &= A.zero;
-#pragma unroll
-            for (int r = 0; r < ROWS; r++) {
-                load_cons(nxt[r], rp, dep);
-                rp.st += pitch;
-                rp.iq += pitch;
-            }
-            const int yi0 = y_first + it * ROWS;
-            const int yq0 = yi0 - 2 * RAD;
-            Best pb[ROWS];
-            if (EMIT) prefetch_best(yq0, pb);
-            float ry1[ROWS];
-#pragma unroll
-            for (int r = 0; r < ROWS; r++) ry1[r] = inv_rows(yi0 + r - RAD, A.y_global0, A.frame_h, A.S);
-            named_bar_sync(BAR_FULL, 64);  // the producer has published rows yi0 .. yi0+ROWS-1
-            float SP[ROWS][KPX], SIP[ROWS][KPX];
-#pragma unroll
-            for (int r = 0; r < ROWS; r++) {
-                const float4* hd = &sm.hand[pair][r][0][lane];
-                const float4 p0 = hd[0], p1 = hd[32], q0 = hd[64], q1 = hd[96];
-                SP[r][0] = p0.x; SP[r][1] = p0.y; SP[r][2] = p0.z; SP[r][3] = p0.w;
-                SP[r][4] = p1.x; SP[r][5] = p1.y; SP[r][6] = p1.z; SP[r][7] = p1.w;
-                SIP[r][0] = q0.x; SIP[r][1] = q0.y; SIP[r][2] = q0.z; SIP[r][3] = q0.w;
-                SIP[r][4] = q1.x; SIP[r][5] = q1.y; SIP[r][6] = q1.z; SIP[r][7] = q1.w;
-            }
-            // the values are in registers (each SP/SIP feeds the arithmetic below, so the loads
-            // have completed before this point is passed): release the buffer to the producer
-            float relv = 0.0f;
-#pragma unroll
-            for (int r = 0; r < ROWS; r++) relv += SP[r][0] + SP[r][4] + SIP[r][0] + SIP[r][4];
-            if (it + 1 < niter) {
-                if (__float_as_int(relv) == A.zero - 12345) __threadfence_block();  // keeps the loads above the arrive
-                named_bar_arrive(BAR_EMPTY, 64);
-            }
-            float SA[ROWS][KPX], SB[ROWS][KPX];
-#pragma unroll
-            for (int r = 0; r < ROWS; r++) {
-                // ---- a, b at row ya = yi - 9
-                const float stt[16] = {o[r].s0.x, o[r].s0.y, o[r].s0.z, o[r].s0.w, o[r].s1.x, o[r].s1.y, o[r].s1.z, o[r].s1.w,
-                                       o[r].s2.x, o[r].s2.y, o[r].s2.z, o[r].s2.w, o[r].s3.x, o[r].s3.y, o[r].s3.z, o[r].s3.w};
-                float a[KPX], b[KPX];
-#pragma unroll
-                for (int j = 0; j < KPX; j++) {
-                    const float mI = stt[2 * j], c2 = stt[2 * j + 1];
-                    float cov = fmaf(-mI, SP[r][j], SIP[r][j]);
-                    a[j] = cov * c2;
-                    float mp = SP[r][j] * (rx[j] * ry1[r]);
-                    b[j] = fmaf(-mI, a[j], mp);
-                }
-                // ---- second stage: (a,b) of row ya enter, row ya-19 leaves
-                float4 oa0 = sm.ringAB[pair][slot][0][lane], oa1 = sm.ringAB[pair][slot][1][lane];
-                float4 ob0 = sm.ringAB[pair][slot][2][lane], ob1 = sm.ringAB[pair][slot][3][lane];
-                sm.ringAB[pair][slot][0][lane] = make_float4(a[0], a[1], a[2], a[3]);
-                sm.ringAB[pair][slot][1][lane] = make_float4(a[4], a[5], a[6], a[7]);
-                sm.ringAB[pair][slot][2][lane] = make_float4(b[0], b[1], b[2], b[3]);
-                sm.ringAB[pair][slot][3][lane] = make_float4(b[4], b[5], b[6], b[7]);
-                slot = (slot + 1 == WIN) ? 0 : slot + 1;
-                const float ao[KPX] = {oa0.x, oa0.y, oa0.z, oa0.w, oa1.x, oa1.y, oa1.z, oa1.w};
-                const float bo[KPX] = {ob0.x, ob0.y, ob0.z, ob0.w, ob1.x, ob1.y, ob1.z, ob1.w};
-#pragma unroll
-                for (int j = 0; j < KPX; j++) {
-                    Va[j] += a[j] - ao[j];
-                    Vb[j] += b[j] - bo[j];
-                }
-                if (EMIT) {
-                    hsum19(Va, SA[r]);
-                    hsum19(Vb, SB[r]);
-                }
-            }
-            if (EMIT) {
+            ConsOps opsA[ROWS], opsB[ROWS];
+            if (active) {
 #pragma unroll
                 for (int r = 0; r < ROWS; r++) {
-                    const float ry2 = inv_rows(yq0 + r, A.y_global0, A.frame_h, 1.0f);
-                    const float iq[KPX] = {o[r].iq0.x, o[r].iq0.y, o[r].iq0.z, o[r].iq0.w,
-                                           o[r].iq1.x, o[r].iq1.y, o[r].iq1.z, o[r].iq1.w};
-                    float q[KPX];
-#pragma unroll
-                    for (int j = 0; j < KPX; j++) q[j] = fmaf(SA[r][j], iq[j], SB[r][j]) * (rx[j] * ry2);
-                    sm.qbuf[obuf][pair][r][0][lane] = make_float4(q[0], q[1], q[2], q[3]);
-                    sm.qbuf[obuf][pair][r][1][lane] = make_float4(q[4], q[5], q[6], q[7]);
+                    load_cons(opsA[r], rp, 0);
+                    rp.st += pitch;
+                    rp.iq += pitch;
                 }
-                named_bar_sync(1, NWARP * 32);  // the 4 consumer warps
-                merge(yq0, pb);
             }
-        };
 
-        constexpr int WARM_IT = 4 * RAD / ROWS;  // 36 warm-up rows fill both windows
-        static_assert((4 * RAD) % ROWS == 0, "ROWS must divide the warm-up length");
-        if (active) {
-            int it = 0;
-            for (; it < WARM_IT; it += 2) {
-                iter(std::false_type{}, opsA, opsB, it);
-                iter(std::false_type{}, opsB, opsA, it + 1);
-            }
-            for (; it + 1 < niter; it += 2) {
-                iter(std::true_type{}, opsA, opsB, it);
-                iter(std::true_type{}, opsB, opsA, it + 1);
-            }
-            if (it < niter) iter(std::true_type{}, opsA, opsB, it);
-        } else {
-            // no disparity for this pair in the (last, partial) group: only take part in the merge
-            for (int it = WARM_IT; it < niter; it++) {
-                const int yq0 = yb0 + (it - WARM_IT) * ROWS;
+            struct Best { float b0, b1, l0, l1; };
+            // fold the 4 disparities of this group into (best,label): ascending d, `>=`
+            auto merge = [&](int yq0, Best (&pb)[ROWS]) {
+#pragma unroll
+                for (int r = 0; r < ROWS; r++) {
+                    const int yq = yq0 + r;
+                    const float* qb = reinterpret_cast<const float*>(&sm.qbuf[obuf][0][r][0][0]);
+                    float b0 = pb[r].b0, b1 = pb[r].b1, l0 = pb[r].l0, l1 = pb[r].l1;
+#pragma unroll
+                    for (int wv = 0; wv < NWARP; wv++) {
+                        float2 qv = *reinterpret_cast<const float2*>(qb + wv * (ROWS * 256) + qoff);
+                        float lab = (float)(dbase + wv);
+                        if (b0 >= qv.x) { b0 = qv.x; l0 = lab; }
+                        if (b1 >= qv.y) { b1 = qv.y; l1 = lab; }
+                    }
+                    if (yq < yb1) {
+                        const size_t moff = (size_t)(yq - A.y_out0) * A.pitchS + mx;
+                        if (mvalid0) { bestS[moff] = b0; labS[moff] = l0; }
+                        if (mvalid1) { bestS[moff + 1] = b1; labS[moff + 1] = l1; }
+                    }
+                }
+                obuf ^= 1;
+            };
+            auto prefetch_best = [&](int yq0, Best (&pb)[ROWS]) {
+#pragma unroll
+                for (int r = 0; r < ROWS; r++) {
+                    pb[r].b0 = pb[r].b1 = BEST_INIT_BITS_F;
+                    pb[r].l0 = pb[r].l1 = 0.0f;
+                    const int yq = yq0 + r;
+                    if (g > 0 && yq < yb1) {
+                        const size_t moff = (size_t)(yq - A.y_out0) * A.pitchS + mx;
+                        if (mvalid0) { pb[r].b0 = bestS[moff]; pb[r].l0 = labS[moff]; }
+                        if (mvalid1) { pb[r].b1 = bestS[moff + 1]; pb[r].l1 = labS[moff + 1]; }
+                    }
+                }
+            };
+
+            auto iter = [&](auto emit_tag, const ConsOps (&o)[ROWS], ConsOps (&nxt)[ROWS], int it) {
+                constexpr bool EMIT = decltype(emit_tag)::value;
+                int dep = 0;
+#pragma unroll
+                for (int r = 0; r < ROWS; r++) dep |= touch(o[r]);
+                dep &= A.zero;
+#pragma unroll
+                for (int r = 0; r < ROWS; r++) {
+                    load_cons(nxt[r], rp, dep);
+                    rp.st += pitch;
+                    rp.iq += pitch;
+                }
+                const int yi0 = y_first + it * ROWS;
+                const int yq0 = yi0 - 2 * RAD;
                 Best pb[ROWS];
-                prefetch_best(yq0, pb);
-                named_bar_sync(1, NWARP * 32);
-                merge(yq0, pb);
+                if (EMIT) prefetch_best(yq0, pb);
+                float ry1[ROWS];
+#pragma unroll
+                for (int r = 0; r < ROWS; r++) ry1[r] = inv_rows(yi0 + r - RAD, A.y_global0, A.frame_h, A.S);
+                // the (a,b) rows that leave the second-stage window, from this warp's TMEM ring
+                float ao[ROWS][KPX], bo[ROWS][KPX];
+                int slots[ROWS];
+#pragma unroll
+                for (int r = 0; r < ROWS; r++) {
+                    slots[r] = slot;
+                    tm_ld16(tAB + 16 * slot, ao[r], bo[r]);
+                    slot = (slot + 1 == WIN) ? 0 : slot + 1;
+                }
+                named_bar_sync(BAR_FULL, 64);  // the producer has published rows yi0 .. yi0+ROWS-1
+                tm_fence_after();
+                float SP[ROWS][KPX], SIP[ROWS][KPX];
+#pragma unroll
+                for (int r = 0; r < ROWS; r++) tm_ld16(tH + 16 * r, SP[r], SIP[r]);
+                tm_wait_ld();
+                if (it + 1 < niter) {  // hand-off columns are free again
+                    tm_fence_before();
+                    named_bar_arrive(BAR_EMPTY, 64);
+                }
+                float SA[ROWS][KPX], SB[ROWS][KPX];
+#pragma unroll
+                for (int r = 0; r < ROWS; r++) {
+                    // ---- a, b at row ya = yi - 9
+                    const float stt[16] = {o[r].s0.x, o[r].s0.y, o[r].s0.z, o[r].s0.w, o[r].s1.x, o[r].s1.y, o[r].s1.z, o[r].s1.w,
+                                           o[r].s2.x, o[r].s2.y, o[r].s2.z, o[r].s2.w, o[r].s3.x, o[r].s3.y, o[r].s3.z, o[r].s3.w};
+                    float a[KPX], b[KPX];
+#pragma unroll
+                    for (int j = 0; j < KPX; j++) {
+                        const float mI = stt[2 * j], c2 = stt[2 * j + 1];
+                        float cov = fmaf(-mI, SP[r][j], SIP[r][j]);
+                        a[j] = cov * c2;
+                        float mp = SP[r][j] * (rx[j] * ry1[r]);
+                        b[j] = fmaf(-mI, a[j], mp);
+                    }
+                    // ---- second stage: (a,b) of row ya enter, row ya-19 leaves
+                    tm_st16(tAB + 16 * slots[r], a, b);
+#pragma unroll
+                    for (int j = 0; j < KPX; j++) {
+                        Va[j] += a[j] - ao[r][j];
+                        Vb[j] += b[j] - bo[r][j];
+                    }
+                    if (EMIT) {
+                        hsum19(Va, SA[r]);
+                        hsum19(Vb, SB[r]);
+                    }
+                }
+                if (EMIT) {
+#pragma unroll
+                    for (int r = 0; r < ROWS; r++) {
+                        const float ry2 = inv_rows(yq0 + r, A.y_global0, A.frame_h, 1.0f);
+                        const float iq[KPX] = {o[r].iq0.x, o[r].iq0.y, o[r].iq0.z, o[r].iq0.w,
+                                               o[r].iq1.x, o[r].iq1.y, o[r].iq1.z, o[r].iq1.w};
+                        float q[KPX];
+#pragma unroll
+                        for (int j = 0; j < KPX; j++) q[j] = fmaf(SA[r][j], iq[j], SB[r][j]) * (rx[j] * ry2);
+                        sm.qbuf[obuf][pair][r][0][lane] = make_float4(q[0], q[1], q[2], q[3]);
+                        sm.qbuf[obuf][pair][r][1][lane] = make_float4(q[4], q[5], q[6], q[7]);
+                    }
+                    named_bar_sync(1, NWARP * 32);  // the 4 consumer warps
+                    merge(yq0, pb);
+                }
+                tm_wait_st();  // this iteration's ring stores are complete before the next loads
+            };
+
+            constexpr int WARM_IT = 4 * RAD / ROWS;  // 36 warm-up rows fill both windows
+            static_assert((4 * RAD) % ROWS == 0, "ROWS must divide the warm-up length");
+            if (active) {
+                int it = 0;
+                for (; it < WARM_IT; it += 2) {
+                    iter(std::false_type{}, opsA, opsB, it);
+                    iter(std::false_type{}, opsB, opsA, it + 1);
+                }
+                for (; it + 1 < niter; it += 2) {
+                    iter(std::true_type{}, opsA, opsB, it);
+                    iter(std::true_type{}, opsB, opsA, it + 1);
+                }
+                if (it < niter) iter(std::true_type{}, opsA, opsB, it);
+            } else {
+                // no disparity for this pair in the (last, partial) group: only take part in the merge
+                for (int it = WARM_IT; it < niter; it++) {
+                    const int yq0 = yb0 + (it - WARM_IT) * ROWS;
+                    Best pb[ROWS];
+                    prefetch_best(yq0, pb);
+                    named_bar_sync(1, NWARP * 32);
+                    merge(yq0, pb);
+                }
             }
+            __syncthreads();  // group end
         }
-        __syncthreads();  // group end
+    }
+    // every tcgen05 operation of this block has completed (waits above); release Tensor Memory
+    tm_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tm_fence_after();
+        tm_dealloc(sm.tmem_base);
     }
 }
 
