@@ -57,7 +57,8 @@ class _Strip(C.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libstereo_b200.so")
+    # SB200_LIB lets a developer A/B another build of the same ABI; the default is the in-tree library
+    return os.environ.get("SB200_LIB") or os.path.join(_HERE, "libstereo_b200.so")
 
 
 _LIB = None
