@@ -55,7 +55,9 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs"""
+    """nvidia-smi clocks + throttle reasons, sampled every 100 ms from before the warm-up until
+    after the timed region; samples are stamped on arrival and only those inside the timed
+    region (or, if it was shorter than the sampling period, inside the loaded window) count."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -67,7 +69,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
-                                          "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -75,37 +77,73 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+            self.lines.append((time.time(), ln.strip()))
 
-    def stop(self):
+    def stop(self, t0, t1, load0):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+
+        def parse(lo, hi):
+            sm, smax, reasons = [], [], set()
+            for ts, ln in self.lines:
+                if not (lo <= ts <= hi):
+                    continue
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    smax.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, smax, reasons
+
+        sm, smax, reasons = parse(t0, t1 + 0.1)
+        window = "timed region"
+        if len(sm) < 3:  # timed region shorter than a few sampling periods: use the whole loaded window
+            sm, smax, reasons = parse(load0, t1 + 0.1)
+            window = "warm-up + timed region"
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
-def make_inputs(w, h, size_d, channels, n_sets):
+class quiet_stdout:
+    """the reference's detect_occlusionOnCPU prints to stdout (occlusion.cu:106); keep ours to one JSON line"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        self.null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self.null, 1)
+
+    def __exit__(self, *a):
+        os.dup2(self.saved, 1)
+        os.close(self.null)
+        os.close(self.saved)
+
+
+def make_inputs(w, h, size_d, channels, n_sets, y0=0, rows=None, seed0=0):
     import synth
 
-    return [synth.make_pair(w, h, size_d, channels=channels, seed=s) for s in range(n_sets)]
+    return [synth.make_pair(w, h, size_d, channels=channels, seed=seed0 + s, y0=y0, rows=rows) for s in range(n_sets)]
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "fused_ncu.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
 
 
 def run_reference(args, w, h, size_d, desc):
@@ -132,7 +170,8 @@ def run_reference(args, w, h, size_d, desc):
         if kind == "reference":
             bl, dl, _ = lib.view_disparity_cpu(L, R, d_sample, dmin_full, init, nthreads=threads)
             br, dr, _ = lib.view_disparity_cpu(R, L, d_sample, 0, init, nthreads=threads)
-            occ = lib.detect_occlusion_cpu(dl, dr, dmin_full - 100)
+            with quiet_stdout():
+                occ = lib.detect_occlusion_cpu(dl, dr, dmin_full - 100)
             lib.fill_occlusion_cpu(occ, dmin_full)
         else:
             p = lib.params(box_mode=O.BOX_FAITHFUL, nthreads=threads)
@@ -175,7 +214,8 @@ def cpu_baseline(w, h, size_d):
         t0 = time.perf_counter()
         _, dl, _ = lib.view_disparity_cpu(L, R, d_sample, dmin_full, init, nthreads=1)
         _, dr, _ = lib.view_disparity_cpu(R, L, d_sample, 0, init, nthreads=1)
-        occ = lib.detect_occlusion_cpu(dl, dr, dmin_full - 100)
+        with quiet_stdout():
+            occ = lib.detect_occlusion_cpu(dl, dr, dmin_full - 100)
         lib.fill_occlusion_cpu(occ, dmin_full)
         dt = time.perf_counter() - t0
     else:
@@ -197,21 +237,24 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("SB200_WORKLOAD", "c3"), choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default=None, choices=["dp", "batch", "strips"],
+                    help="dp: one pair per step per GPU, weak scaling (default); batch: a fixed batch of 64 pairs "
+                         "split over the GPUs (c4); strips: one frame split into row strips with halo exchange (c5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     w, h, size_d, channels, desc = WORKLOADS[args.workload]
 
     if args.impl == "reference":
-        if args.steps > 6:
-            pass  # the sample is sized so that even 20+3 steps end within a few minutes
         run_reference(args, w, h, size_d, desc)
         return
+
+    import ctypes as C
 
     import torch
     import torch.distributed as dist
 
     import stereo_matching_cuda_b200 as S
-    from stereo_matching_cuda_b200 import api
+    from stereo_matching_cuda_b200 import api, sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -221,127 +264,172 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    mode = args.mode or {"c4": "batch", "c5": "strips" if world > 1 else "dp"}.get(args.workload, "dp")
 
     p = api.default_params(dmin=-(size_d - 1), dmax=0)
     n = w * h
-    n_sets = 4 if n * size_d < 3e9 else 2
-    pairs = make_inputs(w, h, size_d, channels, n_sets)
-    shape = (h, w) if channels == 1 else (h, w, channels)
     dev = torch.device("cuda", local)
-    d_in = [(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)) for a, b in pairs]
-    f32 = lambda: torch.empty((h, w), dtype=torch.float32, device=dev)  # noqa: E731
-    outs = {k: f32() for k in ("disp_left", "disp_right", "occlusion", "filled", "best_left", "best_right")}
     ctx = S.Context(local, stream=torch.cuda.current_stream())
-
-    def step(i):
-        a, b = d_in[i % n_sets]
-        ctx.pipeline_dev(a, b, channels, w, h, outs, p)
+    names = ("disp_left", "disp_right", "occlusion", "filled", "best_left", "best_right")
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
-        step(i)
-    barrier()
+    halo = ctx.strip_halo_rows(p)
+    if mode == "strips":
+        # one frame, rows split over the ranks; every step exchanges the 2*radius input halo rows
+        geom = sharding.strip_geometry(h, rank, world, halo)
+        n_sets = 2
+        own = make_inputs(w, h, size_d, channels, n_sets, y0=geom["y0"], rows=geom["rows"])
+        d_own = [(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)) for a, b in own]
+        outs = {k: torch.empty((geom["rows"], w), dtype=torch.float32, device=dev) for k in names}
+        pairs_per_step, cells_per_step, scaling = 1, 2.0 * w * h * size_d, "strong"
+
+        def step(i):
+            a, b = d_own[i % n_sets]
+            if world > 1:
+                a = sharding.exchange_halo_rows(a, geom, rank, world, halo)
+                b = sharding.exchange_halo_rows(b, geom, rank, world, halo)
+            ctx.pipeline_strip_dev(a, b, channels, w, geom, outs, p)
+    else:
+        n_sets = 4 if n * size_d < 3e9 else 2
+        if mode == "batch":
+            total_pairs = 64
+            mine = sharding.batch_shard(total_pairs, rank, world)
+            n_sets = min(4, len(mine))
+            pairs = [make_inputs(w, h, size_d, channels, 1, seed0=mine[k])[0] for k in range(n_sets)]
+            pairs_per_step, cells_per_step, scaling = len(mine), 2.0 * w * h * size_d * total_pairs, "strong"
+        else:
+            pairs = make_inputs(w, h, size_d, channels, n_sets)
+            pairs_per_step, cells_per_step, scaling = 1, 2.0 * w * h * size_d * world, "weak"
+        d_in = [(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)) for a, b in pairs]
+        outs = {k: torch.empty((h, w), dtype=torch.float32, device=dev) for k in names}
+
+        def step(i):
+            for k in range(pairs_per_step):
+                a, b = d_in[(i * pairs_per_step + k) % n_sets]
+                ctx.pipeline_dev(a, b, channels, w, h, outs, p)
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    load0 = time.time()
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
     l0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t0 = time.time()
     e0.record()
     for i in range(args.steps):
         step(i)
     e1.record()
     barrier()
+    t1 = time.time()
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count - l0
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    clocks = sampler.stop(t0, t1, load0) if rank == 0 else None
+    t = torch.tensor([ms, float(launches)], dtype=torch.float64, device=dev)
+    tl = t.clone()
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    cells_per_step = 2.0 * w * h * size_d
-    value = world * cells_per_step * args.steps / (ms_max * 1e-3)
+        dist.all_reduce(tl, op=dist.ReduceOp.SUM)
+    ms_max = float(t[0].item())
+    launches_all = int(tl[1].item())
+    value = cells_per_step * args.steps / (ms_max * 1e-3)
+    pairs_total_per_step = {"dp": world, "batch": 64, "strips": 1}[mode]
 
-    # --- roofline pass: device time of the dominant kernel (k_fused_cvf), CUDA events recorded by
-    # the library on the launching stream around that kernel, averaged over the same K steps
+    # --- roofline pass: device time of the dominant kernel (k_fused_cvf) from CUDA events the
+    # library records on the launching stream around that kernel, averaged over up to 10 steps
     ctx.enable_timing(True)
     fused_ms, occl_ms, prep_ms, merge_ms = [], [], [], []
     for i in range(min(args.steps, 10)):
         step(i)
-        tm = ctx.last_timing()
+        tm = ctx.last_timing()  # the step's last pair
         fused_ms.append(tm["fused_ms"])
         occl_ms.append(tm["occl_ms"])
         prep_ms.append(tm["prep_ms"])
         merge_ms.append(tm["merge_ms"])
     ctx.enable_timing(False)
     fk = statistics.mean(fused_ms)
+    rows_local = h if mode != "strips" else sharding.strip_geometry(h, rank, world, halo)["rows"]
+    cells_per_launch = 2.0 * w * rows_local * size_d
 
     # --- end to end through the host-pointer C-ABI call, pinned host buffers, copies timed
-    h_in = [(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()) for a, b in pairs]
-    names = ("disp_left", "disp_right", "occlusion", "filled")
-    h_out = {k: torch.empty((h, w), dtype=torch.float32).pin_memory() for k in names}
-    o = api._Outputs()
-    for k in names:
-        setattr(o, k, h_out[k].data_ptr())
-    import ctypes as C
+    e2e = None
+    if mode == "dp":
+        h_in = [(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()) for a, b in pairs]
+        onames = ("disp_left", "disp_right", "occlusion", "filled")
+        h_out = {k: torch.empty((h, w), dtype=torch.float32).pin_memory() for k in onames}
+        o = api._Outputs()
+        for k in onames:
+            setattr(o, k, h_out[k].data_ptr())
 
-    def e2e_step(i):
-        a, b = h_in[i % n_sets]
-        ctx._ck(ctx.lib.sb200_pipeline(ctx.h, C.byref(p), C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), channels, w,
-                                       h, C.byref(o)))
+        def e2e_step(i):
+            a, b = h_in[i % n_sets]
+            ctx._ck(ctx.lib.sb200_pipeline(ctx.h, C.byref(p), C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), channels,
+                                           w, h, C.byref(o)))
 
-    for i in range(2):
-        e2e_step(i)
-    barrier()
-    t0 = time.perf_counter()
-    n_e2e = max(3, min(args.steps, 10))
-    for i in range(n_e2e):
-        e2e_step(i)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    te = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * cells_per_step * n_e2e / float(te.item())
+        for i in range(2):
+            e2e_step(i)
+        barrier()
+        tt0 = time.perf_counter()
+        n_e2e = max(3, min(args.steps, 10))
+        for i in range(n_e2e):
+            e2e_step(i)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - tt0
+        te = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * 2.0 * w * h * size_d * n_e2e / float(te.item()), "unit": "px*d/s",
+               "h2d_bytes_per_step": int(2 * n * channels), "d2h_bytes_per_step": int(4 * n * 4),
+               "ms_per_step": 1e3 * float(te.item()) / n_e2e,
+               "api": "sb200_pipeline (host pointers, pinned, blocking; H2D of the pair and D2H of 4 float maps inside)"}
 
     if rank == 0:
         pk = peaks()
         peak_instr = 148 * 128 * pk["sm_max_mhz"] * 1e6  # FP32 lane-instructions/s at the max SM clock
-        achieved = INSTR_PER_CELL * cells_per_step / (fk * 1e-3)
+        achieved = INSTR_PER_CELL * cells_per_launch / (fk * 1e-3)
+        tr = ncu_traffic()
         line = {
             "metric": "pixel-disparities/sec", "value": value, "unit": "px*d/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "fps": world * args.steps / (ms_max * 1e-3),
+            "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "fps": pairs_total_per_step * args.steps / (ms_max * 1e-3),
             "config": {
                 "workload": desc + f" (dmin={-(size_d - 1)}), gray guide, r=9, eps=6.5025, both views + L/R check + fill; "
-                            "1 pair per step per GPU" + ("" if world == 1 else f", {world} GPUs data-parallel over pairs"),
-                "width": w, "height": h, "size_d": size_d, "channels": channels, "pairs_per_step_per_gpu": 1,
+                            + {"dp": "1 pair per step per GPU" + ("" if world == 1 else f", {world} GPUs data-parallel over pairs, no communication"),
+                               "batch": f"a batch of 64 pairs per step split over {world} GPU(s), no communication",
+                               "strips": f"one frame per step split into {world} row strips, {halo}-row input halos exchanged over NCCL send/recv"}[mode],
+                "mode": mode, "width": w, "height": h, "size_d": size_d, "channels": channels,
                 "l2": f"inputs rotate over {n_sets} distinct pairs; the per-pair working set (prepared planes + per-chunk "
                       "WTA planes, several hundred MB at 1080p D=256) exceeds the 126 MB L2",
             },
             "roofline": {
                 "bound": "fp32_pipe", "kernel": "k_fused_cvf", "achieved": achieved / 1e12, "peak": peak_instr / 1e12,
-                "unit": "T lane-instr/s", "frac": achieved / peak_instr, "traffic": None,
+                "unit": "T lane-instr/s", "frac": achieved / peak_instr,
+                "traffic": tr.get("dram_bytes_per_launch") if tr else None,
+                "traffic_src": tr.get("src") if tr else None,
                 "kernel_ms": fk, "instr_per_cell": INSTR_PER_CELL,
-                "flop_frac": FLOP_PER_CELL * cells_per_step / (fk * 1e-3) / (2 * peak_instr),
+                "flop_frac": FLOP_PER_CELL * cells_per_launch / (fk * 1e-3) / (2 * peak_instr),
                 "peak_src": f"148 SMs x 128 FP32 lanes x {pk['sm_max_mhz']:.0f} MHz (sm_max_mhz, {pk['src']})",
-                "note": "north_star names the FP32 CUDA-core pipe as this kernel's roofline (no dense contraction, ~30 B/pixel of HBM)",
+                "note": "north_star names the FP32 CUDA-core pipe as this kernel's roofline (no dense contraction; see "
+                        "hbm_frac_of_kernel_time for how little of the kernel's time its DRAM traffic explains)",
+                "hbm_frac_of_kernel_time": (tr["dram_bytes_per_launch"] / (pk["hbm_gbs"] * 1e9)) / (fk * 1e-3) if tr and mode == "dp" and args.workload == "c3" else None,
                 "other_kernels_ms": {"k_prep_x2": statistics.mean(prep_ms), "k_merge_chunks_x2": statistics.mean(merge_ms),
                                      "k_lr_check_fill": statistics.mean(occl_ms)},
-                "lr_check_fill_hbm": {"bound": "hbm", "achieved": 16.0 * n / (statistics.mean(occl_ms) * 1e-3) / 1e9,
+                "lr_check_fill_hbm": {"bound": "hbm", "achieved": 16.0 * w * rows_local / (statistics.mean(occl_ms) * 1e-3) / 1e9,
                                       "peak": pk["hbm_gbs"], "unit": "GB/s", "bytes_per_pixel": 16},
             },
-            "e2e": {"value": e2e_value, "unit": "px*d/s", "h2d_bytes_per_step": int(2 * n * channels),
-                    "d2h_bytes_per_step": int(4 * n * 4), "ms_per_step": 1e3 * float(te.item()) / n_e2e,
-                    "api": "sb200_pipeline (host pointers, pinned, blocking)"},
-            "gpu_launches": int(launches * world),
+            "gpu_launches": launches_all,
             "clocks": clocks,
         }
+        if e2e:
+            line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(w, h, size_d)
         print(json.dumps(line))

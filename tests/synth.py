@@ -30,10 +30,12 @@ def delta_rows(h, size_d):
     return (band * (size_d - 1)) // 15
 
 
-def make_pair(w, h, size_d, channels=1, seed=0):
-    """returns (left, right) uint8 arrays of shape (h, w) or (h, w, channels)"""
-    y, x = np.meshgrid(np.arange(h, dtype=np.int64), np.arange(w, dtype=np.int64), indexing="ij")
-    dl = delta_rows(h, size_d)[:, None]
+def make_pair(w, h, size_d, channels=1, seed=0, y0=0, rows=None):
+    """returns (left, right) uint8 arrays of shape (rows, w) or (rows, w, channels): rows
+    [y0, y0+rows) of an h-row frame (default: the whole frame)"""
+    rows = h - y0 if rows is None else rows
+    y, x = np.meshgrid(np.arange(y0, y0 + rows, dtype=np.int64), np.arange(w, dtype=np.int64), indexing="ij")
+    dl = delta_rows(h, size_d)[y0:y0 + rows, None]
     chans_l, chans_r = [], []
     for c in range(channels):
         chans_r.append(_tex(x, y, c, seed))

@@ -1,0 +1,74 @@
+"""N>1 host logic on CPU: world_size-2 and -3 gloo process groups exercise the row-strip halo
+exchange, the strip geometry and the batch sharding that bench.py uses on NCCL."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from stereo_matching_cuda_b200 import sharding
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, height, width, halo, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        full = torch.arange(height * width * 3, dtype=torch.int64).reshape(height, width, 3) % 251
+        full = full.to(torch.uint8)
+        geom = sharding.strip_geometry(height, rank, world, halo)
+        y0, rows = geom["y0"], geom["rows"]
+        own = full[y0:y0 + rows].clone()
+        held = sharding.exchange_halo_rows(own, geom, rank, world, halo)
+        want = full[y0 - geom["halo_top"]:y0 + rows + geom["halo_bot"]]
+        ok = held.shape == want.shape and torch.equal(held, want)
+        # gather of per-strip outputs (here: the row index) reproduces the frame
+        out = torch.arange(y0, y0 + rows, dtype=torch.float32)[:, None].expand(rows, width).contiguous()
+        allrows = sharding.gather_strips(out, rank, world, height)
+        ok = ok and allrows.shape == (height, width) and torch.equal(allrows[:, 0], torch.arange(height, dtype=torch.float32))
+        q.put((rank, bool(ok), geom))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,height", [(2, 200), (3, 330), (2, 128)])
+def test_halo_exchange_gloo(world, height):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, height, 37, 18, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, _ in res), res
+    geoms = {r: g for r, _, g in res}
+    assert geoms[0]["halo_top"] == 0 and geoms[world - 1]["halo_bot"] == 0
+    assert sum(g["rows"] for g in geoms.values()) == height
+
+
+def test_strip_bounds_and_batch_shard():
+    for h, w in ((4320, 8), (1080, 4), (200, 2), (64, 2), (1000, 3)):
+        b = sharding.strip_bounds(h, w)
+        assert b[0][0] == 0 and b[-1][1] == h
+        assert all(a[1] == c[0] for a, c in zip(b[:-1], b[1:]))
+        assert all(y0 % 64 == 0 for y0, _ in b)
+    # the same global rows start a strip whatever the rank count: 8-way bounds refine 4-way bounds
+    b4 = {y0 for y0, _ in sharding.strip_bounds(4320, 4)}
+    b8 = {y0 for y0, _ in sharding.strip_bounds(4352, 8)}
+    assert {0} <= b4 and {0} <= b8
+    idx = [sharding.batch_shard(64, r, 8) for r in range(8)]
+    assert sorted(sum(idx, [])) == list(range(64)) and all(len(i) == 8 for i in idx)
+    assert sharding.batch_shard(5, 3, 4) == [3]
