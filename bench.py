@@ -412,8 +412,8 @@ def main():
             "roofline": {
                 "bound": "fp32_pipe", "kernel": "k_fused_cvf", "achieved": achieved / 1e12, "peak": peak_instr / 1e12,
                 "unit": "T lane-instr/s", "frac": achieved / peak_instr,
-                "traffic": tr.get("dram_bytes_per_launch") if tr else None,
-                "traffic_src": tr.get("src") if tr else None,
+                "traffic": tr.get("dram_bytes_per_launch") if tr and mode == "dp" and args.workload == "c3" else None,
+                "traffic_src": tr.get("src") if tr and mode == "dp" and args.workload == "c3" else None,
                 "kernel_ms": fk, "instr_per_cell": INSTR_PER_CELL,
                 "flop_frac": FLOP_PER_CELL * cells_per_launch / (fk * 1e-3) / (2 * peak_instr),
                 "peak_src": f"148 SMs x 128 FP32 lanes x {pk['sm_max_mhz']:.0f} MHz (sm_max_mhz, {pk['src']})",
