@@ -487,3 +487,118 @@ void so_write_mat(const float* mat, unsigned char* out, int w, int h) {
         out[i] = (unsigned char)c;
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * RGB guide.  NOT in the reference (its guide is always the gray image,
+ * main.cu:65-66): PARITY UNPINNED by construction.  Definition (He et al. colour guided
+ * filter with the reference's box/border/WTA semantics): the cost stays the gray cost of
+ * costVolume.cu:163-190; guide I=(R,G,B) as float; per pixel mu=box(I), Sigma=box(I I^T)-mu mu^T,
+ * M=(Sigma+eps*U)^-1 (symmetric 3x3, adjugate); per slice mp=box(p), cov_c=box(I_c p)-mu_c mp,
+ * a=M cov, b=mp-a.mu, q=box(a).I+box(b).  Cross-check: with R=G=B it equals the gray path run
+ * with eps/3 (tests/test_rgb_guide.py). */
+typedef struct {
+    float* I[3];    /* channels as float */
+    float* mu[3];   /* box means */
+    float* M[6];    /* inverse of (Sigma + eps U): xx xy xz yy yz zz */
+} so_rgb_stats;
+
+static void so_rgb_stats_free(so_rgb_stats* s) {
+    for (int c = 0; c < 3; c++) { free(s->I[c]); free(s->mu[c]); }
+    for (int k = 0; k < 6; k++) free(s->M[k]);
+}
+
+static void so_rgb_guide_stats(const so_params* p, const unsigned char* rgb, int channels, so_rgb_stats* s, int w, int h) {
+    size_t n = (size_t)w * h;
+    float* tmp = (float*)malloc(n * sizeof(float));
+    float* cov[6];
+    for (int c = 0; c < 3; c++) {
+        s->I[c] = (float*)malloc(n * sizeof(float));
+        s->mu[c] = (float*)malloc(n * sizeof(float));
+        for (size_t i = 0; i < n; i++) s->I[c][i] = (float)rgb[i * channels + c];
+        so_box_mean(p, s->I[c], s->mu[c], w, h);
+    }
+    static const int A[6] = {0, 0, 0, 1, 1, 2}, B[6] = {0, 1, 2, 1, 2, 2};
+    for (int k = 0; k < 6; k++) {
+        cov[k] = (float*)malloc(n * sizeof(float));
+        s->M[k] = (float*)malloc(n * sizeof(float));
+        for (size_t i = 0; i < n; i++) tmp[i] = s->I[A[k]][i] * s->I[B[k]][i];
+        so_box_mean(p, tmp, cov[k], w, h);
+        for (size_t i = 0; i < n; i++) cov[k][i] = cov[k][i] - s->mu[A[k]][i] * s->mu[B[k]][i];
+    }
+    for (size_t i = 0; i < n; i++) {
+        double xx = (double)cov[0][i] + p->eps, xy = cov[1][i], xz = cov[2][i];
+        double yy = (double)cov[3][i] + p->eps, yz = cov[4][i], zz = (double)cov[5][i] + p->eps;
+        double c00 = yy * zz - yz * yz, c01 = xz * yz - xy * zz, c02 = xy * yz - xz * yy;
+        double c11 = xx * zz - xz * xz, c12 = xy * xz - xx * yz, c22 = xx * yy - xy * xy;
+        double det = xx * c00 + xy * c01 + xz * c02;
+        double id = 1.0 / det;
+        s->M[0][i] = (float)(c00 * id); s->M[1][i] = (float)(c01 * id); s->M[2][i] = (float)(c02 * id);
+        s->M[3][i] = (float)(c11 * id); s->M[4][i] = (float)(c12 * id); s->M[5][i] = (float)(c22 * id);
+    }
+    for (int k = 0; k < 6; k++) free(cov[k]);
+    free(tmp);
+}
+
+/* one slice; scratch: 10*n floats */
+static void so_rgb_guided_slice(const so_params* p, const so_rgb_stats* s, const float* pk, float* q, float* scratch,
+                                int w, int h) {
+    size_t n = (size_t)w * h;
+    float* mp = scratch;
+    float* mIp[3] = {scratch + n, scratch + 2 * n, scratch + 3 * n};
+    float* a[3] = {scratch + 4 * n, scratch + 5 * n, scratch + 6 * n};
+    float* b = scratch + 7 * n;
+    float* t = scratch + 8 * n;
+    float* acc = scratch + 9 * n;
+    so_box_mean(p, pk, mp, w, h);
+    for (int c = 0; c < 3; c++) {
+        for (size_t i = 0; i < n; i++) t[i] = s->I[c][i] * pk[i];
+        so_box_mean(p, t, mIp[c], w, h);
+    }
+    for (size_t i = 0; i < n; i++) {
+        float cx = mIp[0][i] - s->mu[0][i] * mp[i];
+        float cy = mIp[1][i] - s->mu[1][i] * mp[i];
+        float cz = mIp[2][i] - s->mu[2][i] * mp[i];
+        float ax = s->M[0][i] * cx + s->M[1][i] * cy + s->M[2][i] * cz;
+        float ay = s->M[1][i] * cx + s->M[3][i] * cy + s->M[4][i] * cz;
+        float az = s->M[2][i] * cx + s->M[4][i] * cy + s->M[5][i] * cz;
+        a[0][i] = ax; a[1][i] = ay; a[2][i] = az;
+        b[i] = mp[i] - (ax * s->mu[0][i] + ay * s->mu[1][i] + az * s->mu[2][i]);
+    }
+    so_box_mean(p, b, acc, w, h);
+    for (size_t i = 0; i < n; i++) q[i] = acc[i];
+    for (int c = 0; c < 3; c++) {
+        so_box_mean(p, a[c], t, w, h);
+        for (size_t i = 0; i < n; i++) q[i] += t[i] * s->I[c][i];
+    }
+}
+
+/* one view with an RGB guide: guide_rgb is the colour image of the view, gray_guide/gray_other
+ * the gray images the cost is computed on */
+void so_view_disparity_rgb(const so_params* p, const unsigned char* guide_rgb, int channels,
+                           const unsigned char* gray_guide, const unsigned char* gray_other, float* best, float* dmap,
+                           float* second, int w, int h, int size_d, int dmin) {
+    size_t n = (size_t)w * h;
+    so_rgb_stats s;
+    so_rgb_guide_stats(p, guide_rgb, channels, &s, w, h);
+    float* g1 = (float*)malloc(n * sizeof(float));
+    float* g2 = (float*)malloc(n * sizeof(float));
+    so_x_derivative(gray_guide, g1, w, h);
+    so_x_derivative(gray_other, g2, w, h);
+    int nt = p->nthreads > 0 ? p->nthreads : so_max_threads();
+    if (nt > size_d) nt = size_d;
+    if (nt < 1) nt = 1;
+    float* qs = (float*)malloc((size_t)nt * n * sizeof(float));
+    float* ps = (float*)malloc((size_t)nt * n * sizeof(float));
+    float* scr = (float*)malloc((size_t)nt * 10 * n * sizeof(float));
+    for (int s0 = 0; s0 < size_d; s0 += nt) {
+        int cnt = size_d - s0 < nt ? size_d - s0 : nt;
+#pragma omp parallel for num_threads(nt) schedule(static, 1)
+        for (int t = 0; t < cnt; t++) {
+            so_cost_slice(p, gray_guide, gray_other, g1, g2, ps + (size_t)t * n, w, h, dmin + s0 + t);
+            so_rgb_guided_slice(p, &s, ps + (size_t)t * n, qs + (size_t)t * n, scr + (size_t)t * 10 * n, w, h);
+        }
+        for (int t = 0; t < cnt; t++) so_disp_select(qs + (size_t)t * n, best, dmap, second, n, dmin + s0 + t);
+    }
+    free(qs); free(ps); free(scr); free(g1); free(g2);
+    so_rgb_stats_free(&s);
+}

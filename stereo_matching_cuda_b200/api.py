@@ -313,7 +313,10 @@ class Context:
         left, right = _np(left, np.uint8), _np(right, np.uint8)
         h, w = left.shape[:2]
         ch = 1 if left.ndim == 2 else left.shape[2]
-        want = want or (self._F32 + self._U8)
+        if want is None:
+            want = self._F32 + self._U8
+            if p.guide_mode == GUIDE_RGB:  # the uint8 mean images are gray-guide debug outputs
+                want = tuple(k for k in want if not k.startswith("mean_"))
         res, o = {}, _Outputs()
         for k in want:
             res[k] = np.empty((h, w), np.float32 if k in self._F32 else np.uint8)

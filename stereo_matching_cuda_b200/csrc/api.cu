@@ -224,6 +224,60 @@ int guided_filter_staged(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d
     return SB200_OK;
 }
 
+// One view with an RGB guide, staged: cost slices are generated one at a time, every
+// box filter is a pair of streaming kernels.  Correct, HBM-bound, ~50x slower than the fused gray path;
+// a fused RGB kernel is the next step.
+size_t rgb_ws_bytes(size_t n) { return 30 * sb_align(n * 4) + box_scratch_bytes(n) + 4096; }
+int view_rgb_staged(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_rgb, int channels, const uint8_t* d_gray,
+                    const uint8_t* d_other, float* d_best, float* d_disp, int w, int h, int size_d, int dmin) {
+    const size_t n = (size_t)w * h;
+    float *I[3], *mu[3], *M[6], *mIp[3], *a[3], *ma[3], *mp, *b, *mb, *t, *q, *pk, *g1, *g2;
+    for (int c = 0; c < 3; c++) {
+        SB_TRY(ws_get(ctx, &I[c], n));
+        SB_TRY(ws_get(ctx, &mu[c], n));
+        SB_TRY(ws_get(ctx, &mIp[c], n));
+        SB_TRY(ws_get(ctx, &a[c], n));
+        SB_TRY(ws_get(ctx, &ma[c], n));
+    }
+    for (int k = 0; k < 6; k++) SB_TRY(ws_get(ctx, &M[k], n));
+    SB_TRY(ws_get(ctx, &mp, n));
+    SB_TRY(ws_get(ctx, &b, n));
+    SB_TRY(ws_get(ctx, &mb, n));
+    SB_TRY(ws_get(ctx, &t, n));
+    SB_TRY(ws_get(ctx, &q, n));
+    SB_TRY(ws_get(ctx, &pk, n));
+    SB_TRY(ws_get(ctx, &g1, n));
+    SB_TRY(ws_get(ctx, &g2, n));
+    BoxScratch bs;
+    SB_TRY(box_scratch_get(ctx, &bs, n));
+    SB_TRY(sbk_rgb_split(ctx, d_rgb, channels, I[0], I[1], I[2], n));
+    for (int c = 0; c < 3; c++) SB_TRY(box_mean(ctx, p, I[c], mu[c], w, h, bs));
+    static const int A[6] = {0, 0, 0, 1, 1, 2}, B[6] = {0, 1, 2, 1, 2, 2};
+    for (int k = 0; k < 6; k++) {
+        SB_TRY(sbk_mul(ctx, I[A[k]], I[B[k]], t, n));
+        SB_TRY(box_mean(ctx, p, t, M[k], w, h, bs));
+    }
+    SB_TRY(sbk_rgb_inverse(ctx, mu, M, n, p->eps));
+    SB_TRY(sbk_x_derivative(ctx, d_gray, g1, w, h));
+    SB_TRY(sbk_x_derivative(ctx, d_other, g2, w, h));
+    SB_TRY(sbk_fill_f32(ctx, d_best, 3.3961514e38f, n));  // 0x7F7F7F7F, main.cu:112
+    SB_TRY(sbk_fill_f32(ctx, d_disp, 0.0f, n));
+    for (int s = 0; s < size_d; s++) {
+        SB_TRY(sbk_cost_volume(ctx, p, d_gray, d_other, g1, g2, pk, w, h, 1, dmin + s));
+        SB_TRY(box_mean(ctx, p, pk, mp, w, h, bs));
+        for (int c = 0; c < 3; c++) {
+            SB_TRY(sbk_mul(ctx, I[c], pk, t, n));
+            SB_TRY(box_mean(ctx, p, t, mIp[c], w, h, bs));
+        }
+        SB_TRY(sbk_rgb_ab(ctx, mu, M, mIp, mp, a, b, n));
+        for (int c = 0; c < 3; c++) SB_TRY(box_mean(ctx, p, a[c], ma[c], w, h, bs));
+        SB_TRY(box_mean(ctx, p, b, mb, w, h, bs));
+        SB_TRY(sbk_rgb_q(ctx, mb, ma, I, q, n));
+        SB_TRY(sbk_disp_select(ctx, q, d_best, d_disp, n, dmin + s));
+    }
+    return SB200_OK;
+}
+
 int check_params(sb200_ctx* ctx, const sb200_params* p) {
     if (!ctx) return SB200_ERR_INVALID;
     if (!p) return sb_fail(ctx, SB200_ERR_INVALID, "params is NULL");
@@ -241,11 +295,16 @@ int pipeline_core(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, 
     const size_t n_out = (size_t)w * g.rows_out;
     const int dabs = max(abs(p->dmin), abs(p->dmax));
     if (reserve) {
-        size_t bytes = sbf_workspace_bytes(ctx, w, g.h, g.rows_out, dabs, size_d, 2);
+        size_t bytes = p->guide_mode == SB200_GUIDE_RGB ? rgb_ws_bytes(n_held) : sbf_workspace_bytes(ctx, w, g.h, g.rows_out, dabs, size_d, 2);
         bytes += 2 * sb_align(n_held) + 4 * sb_align(n_out * 4) + 4096;
         SB_TRY(sb_ws_reserve(ctx, bytes));
     }
     const bool full = (g.rows_out == g.h);
+    const bool rgb_guide = (p->guide_mode == SB200_GUIDE_RGB);
+    if (rgb_guide && (channels < 3 || !full))
+        return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "RGB guide needs a colour input and a whole frame (no strips yet)");
+    if (rgb_guide && (o->mean_left || o->mean_right))
+        return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "mean_left/mean_right are gray-guide outputs");
     const uint8_t* gl = d_left;
     const uint8_t* gr = d_right;
     if (channels != 1) {
@@ -273,6 +332,15 @@ int pipeline_core(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, 
         if (mL) SB_TRY(ws_get(ctx, &mLh, n_held));
         if (mR) SB_TRY(ws_get(ctx, &mRh, n_held));
     }
+    if (rgb_guide) {
+        float *bL = o->best_left, *bR = o->best_right;
+        if (!bL) SB_TRY(ws_get(ctx, &bL, n_out));
+        if (!bR) SB_TRY(ws_get(ctx, &bR, n_out));
+        const size_t mark = ctx->ws_off;
+        SB_TRY(view_rgb_staged(ctx, p, d_left, channels, gl, gr, bL, dL, w, g.h, size_d, p->dmin));
+        ctx->ws_off = mark;  // the second view reuses the first view's scratch (same stream)
+        SB_TRY(view_rgb_staged(ctx, p, d_right, channels, gr, gl, bR, dR, w, g.h, size_d, -p->dmax));
+    } else
     SB_TRY(sbf_pair_disparity(ctx, p, gl, gr, g, o->best_left, dL, o->best_right, dR, full ? mL : mLh, full ? mR : mRh));
     if (!full) {
         if (mL) SB_CUDA(ctx, cudaMemcpyAsync(mL, mLh + out_off, n_out, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -437,7 +505,8 @@ int sb200_pipeline(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h_left,
     const size_t n = (size_t)w * h;
     const int size_d = p->dmax - p->dmin + 1;
     const int dabs = max(abs(p->dmin), abs(p->dmax));
-    size_t bytes = sbf_workspace_bytes(ctx, w, h, h, dabs, size_d, 2) + 2 * sb_align(n) + 4 * sb_align(n * 4) + 4096;
+    size_t bytes = (p->guide_mode == SB200_GUIDE_RGB ? rgb_ws_bytes(n) : sbf_workspace_bytes(ctx, w, h, h, dabs, size_d, 2)) +
+                   2 * sb_align(n) + 4 * sb_align(n * 4) + 4096;
     bytes += 2 * sb_align(n * channels) + 6 * sb_align(n * 4) + 4 * sb_align(n) + 4096;
     SB_TRY(sb_ws_reserve(ctx, bytes));
     uint8_t *dl, *dr;

@@ -822,7 +822,7 @@ static int run_fused(sb200_ctx* ctx, const sb200_params* p, const uint8_t* const
         return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "fused kernel is built for radius %d (got %d): use box_mode stages", RAD,
                        p->radius);
     if (p->guide_mode != SB200_GUIDE_GRAY)
-        return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "fused kernel: RGB guide not implemented yet");
+        return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "fused kernel: gray guide only (the RGB guide runs through the staged path)");
     int nI, nG, S;
     if (!find_lattice(p, &nI, &nG, &S))
         return sb_fail(ctx, SB200_ERR_UNSUPPORTED,

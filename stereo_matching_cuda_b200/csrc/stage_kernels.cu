@@ -398,3 +398,85 @@ int sbk_lr_check_fill(sb200_ctx* ctx, const float* dL, const float* dR, int w, i
                       float* occ, float* filled) {
     return launch_lr(ctx, dL, dR, w, h, dOcc, d_lr, vMin, occ, filled, 1);
 }
+
+// ---------------------------------------------------------------------------------------
+// RGB guide (not in the reference, whose guide is always gray): staged kernels.
+__global__ void k_rgb_split(const uint8_t* __restrict__ rgb, int ch, float* __restrict__ r, float* __restrict__ g,
+                            float* __restrict__ b, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    r[i] = (float)rgb[i * ch];
+    g[i] = (float)rgb[i * ch + 1];
+    b[i] = (float)rgb[i * ch + 2];
+}
+// cov[k] holds box(I_a I_b) on entry; M[k] = ((Sigma + eps U)^-1)[k] on exit, order xx xy xz yy yz zz
+__global__ void k_rgb_inverse(const float* __restrict__ mr, const float* __restrict__ mg, const float* __restrict__ mb,
+                              float* __restrict__ c0, float* __restrict__ c1, float* __restrict__ c2,
+                              float* __restrict__ c3, float* __restrict__ c4, float* __restrict__ c5, size_t n,
+                              double eps) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float mx = mr[i], my = mg[i], mz = mb[i];
+    double xx = (double)__fsub_rn(c0[i], __fmul_rn(mx, mx)) + eps, xy = __fsub_rn(c1[i], __fmul_rn(mx, my));
+    double xz = __fsub_rn(c2[i], __fmul_rn(mx, mz)), yy = (double)__fsub_rn(c3[i], __fmul_rn(my, my)) + eps;
+    double yz = __fsub_rn(c4[i], __fmul_rn(my, mz)), zz = (double)__fsub_rn(c5[i], __fmul_rn(mz, mz)) + eps;
+    double a00 = yy * zz - yz * yz, a01 = xz * yz - xy * zz, a02 = xy * yz - xz * yy;
+    double a11 = xx * zz - xz * xz, a12 = xy * xz - xx * yz, a22 = xx * yy - xy * xy;
+    double id = 1.0 / (xx * a00 + xy * a01 + xz * a02);
+    c0[i] = (float)(a00 * id); c1[i] = (float)(a01 * id); c2[i] = (float)(a02 * id);
+    c3[i] = (float)(a11 * id); c4[i] = (float)(a12 * id); c5[i] = (float)(a22 * id);
+}
+struct RgbPlanes {
+    const float* mu[3];
+    const float* M[6];
+    const float* mIp[3];
+    const float* mp;
+    float* a[3];
+    float* b;
+};
+__global__ void k_rgb_ab(RgbPlanes P, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float mp = P.mp[i], mx = P.mu[0][i], my = P.mu[1][i], mz = P.mu[2][i];
+    float cx = __fsub_rn(P.mIp[0][i], __fmul_rn(mx, mp));
+    float cy = __fsub_rn(P.mIp[1][i], __fmul_rn(my, mp));
+    float cz = __fsub_rn(P.mIp[2][i], __fmul_rn(mz, mp));
+    float ax = __fadd_rn(__fadd_rn(__fmul_rn(P.M[0][i], cx), __fmul_rn(P.M[1][i], cy)), __fmul_rn(P.M[2][i], cz));
+    float ay = __fadd_rn(__fadd_rn(__fmul_rn(P.M[1][i], cx), __fmul_rn(P.M[3][i], cy)), __fmul_rn(P.M[4][i], cz));
+    float az = __fadd_rn(__fadd_rn(__fmul_rn(P.M[2][i], cx), __fmul_rn(P.M[4][i], cy)), __fmul_rn(P.M[5][i], cz));
+    P.a[0][i] = ax; P.a[1][i] = ay; P.a[2][i] = az;
+    P.b[i] = __fsub_rn(mp, __fadd_rn(__fadd_rn(__fmul_rn(ax, mx), __fmul_rn(ay, my)), __fmul_rn(az, mz)));
+}
+__global__ void k_rgb_q(const float* __restrict__ mb, const float* __restrict__ ma0, const float* __restrict__ ma1,
+                        const float* __restrict__ ma2, const float* __restrict__ r, const float* __restrict__ g,
+                        const float* __restrict__ b, float* __restrict__ q, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = mb[i];
+    v = __fadd_rn(v, __fmul_rn(ma0[i], r[i]));
+    v = __fadd_rn(v, __fmul_rn(ma1[i], g[i]));
+    v = __fadd_rn(v, __fmul_rn(ma2[i], b[i]));
+    q[i] = v;
+}
+int sbk_rgb_split(sb200_ctx* ctx, const uint8_t* rgb, int ch, float* r, float* g, float* b, size_t n) {
+    EW_LAUNCH(k_rgb_split, n, rgb, ch, r, g, b, n);
+    return SB200_OK;
+}
+int sbk_rgb_inverse(sb200_ctx* ctx, float* const mu[3], float* const cov[6], size_t n, double eps) {
+    EW_LAUNCH(k_rgb_inverse, n, mu[0], mu[1], mu[2], cov[0], cov[1], cov[2], cov[3], cov[4], cov[5], n, eps);
+    return SB200_OK;
+}
+int sbk_rgb_ab(sb200_ctx* ctx, float* const mu[3], float* const M[6], float* const mIp[3], const float* mp,
+               float* const a[3], float* b, size_t n) {
+    RgbPlanes P;
+    for (int c = 0; c < 3; c++) { P.mu[c] = mu[c]; P.mIp[c] = mIp[c]; P.a[c] = a[c]; }
+    for (int k = 0; k < 6; k++) P.M[k] = M[k];
+    P.mp = mp;
+    P.b = b;
+    EW_LAUNCH(k_rgb_ab, n, P, n);
+    return SB200_OK;
+}
+int sbk_rgb_q(sb200_ctx* ctx, const float* mb, float* const ma[3], float* const I[3], float* q, size_t n) {
+    EW_LAUNCH(k_rgb_q, n, mb, ma[0], ma[1], ma[2], I[0], I[1], I[2], q, n);
+    return SB200_OK;
+}

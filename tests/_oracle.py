@@ -71,6 +71,8 @@ class Oracle:
         L.so_pipeline_gray.argtypes = [C.POINTER(SoParams), u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int] + [f32p] * 6 + [
             C.c_void_p] * 4
         L.so_write_mat.argtypes = [f32p, u8p, C.c_int, C.c_int]
+        L.so_view_disparity_rgb.argtypes = [C.POINTER(SoParams), u8p, C.c_int, u8p, u8p, f32p, f32p, C.c_void_p, C.c_int,
+                                            C.c_int, C.c_int, C.c_int]
 
     def params(self, box_mode=BOX_FAITHFUL, use_fma=0, nthreads=1, **kw):
         p = SoParams()
@@ -166,6 +168,17 @@ class Oracle:
         self.lib.so_view_disparity(C.byref(p), np.ascontiguousarray(guide), np.ascontiguousarray(other), best, dmap,
                                    _opt(mu8), _opt(second), w, h, size_d, dmin)
         return best, dmap, mu8, second
+
+    def view_disparity_rgb(self, guide_rgb, gray_guide, gray_other, size_d, dmin, p=None, want_second=False):
+        """RGB-guide view (not in the reference)"""
+        p = p or self.params()
+        h, w, ch = guide_rgb.shape
+        best = np.full((h, w), self.best_init(), np.float32)
+        dmap = np.zeros((h, w), np.float32)
+        second = np.full((h, w), self.best_init(), np.float32) if want_second else None
+        self.lib.so_view_disparity_rgb(C.byref(p), np.ascontiguousarray(guide_rgb), ch, np.ascontiguousarray(gray_guide),
+                                       np.ascontiguousarray(gray_other), best, dmap, _opt(second), w, h, size_d, dmin)
+        return best, dmap, second
 
     def detect_occlusion(self, dL, dR, d_occlusion, p=None):
         p = p or self.params()

@@ -318,3 +318,38 @@ def test_against_reference_gpu_code(ctx, oracle, tsukuba):
     out = ctx.pipeline(gl, gr)
     assert (out["disp_left"] == ref["dmap_l"]).mean() > 0.9999
     assert (out["filled"] == ref["filled"]).mean() > 0.999
+
+
+def test_fused_full_size_1080p_d256(ctx, oracle):
+    """BASELINE.json's headline shape: 1920x1080, D=256.  Left view against the exact-mode oracle
+    (all host threads, ~15 s), plus size-independent properties on the whole pipeline output."""
+    torch = pytest.importorskip("torch")
+    w, h, size_d = 1920, 1080, 256
+    L, R = synth.make_pair(w, h, size_d, seed=0)
+    p = api.default_params(dmin=-(size_d - 1), dmax=0)
+    out = ctx.pipeline(L, R, p, want=("disp_left", "disp_right", "best_left", "occlusion", "filled"))
+    po = oracle.params(box_mode=O.BOX_EXACT, nthreads=oracle.max_threads())
+    best, dmap, _, second = oracle.view_disparity(L, R, size_d, -(size_d - 1), po, want_second=True)
+    same = out["disp_left"] == dmap
+    assert same.mean() >= 0.999, same.mean()
+    assert np.all(same[(second - best) > 1e-3])
+    rel = np.abs(out["best_left"] - best) / np.maximum(np.abs(best), 1e-2)
+    assert rel.max() < RTOL_BEST
+    # properties: labels inside the search range, occlusion map is labels-or-sentinel, fill leaves
+    # no sentinel, is idempotent and only changes occluded pixels
+    assert out["disp_left"].min() >= -(size_d - 1) and out["disp_left"].max() <= 0
+    assert out["disp_right"].min() >= 0 and out["disp_right"].max() <= size_d - 1
+    occ = out["occlusion"]
+    sent = -(size_d - 1) - 100
+    assert np.array_equal(occ[occ != sent], out["disp_left"][occ != sent])
+    assert np.all(out["filled"] >= -(size_d - 1))
+    assert np.array_equal(out["filled"][occ != sent], occ[occ != sent])
+    again = out["filled"].copy()
+    ctx.fill_occlusion(again, -(size_d - 1))
+    assert np.array_equal(again, out["filled"])
+    assert np.array_equal(occ, oracle.detect_occlusion(out["disp_left"], out["disp_right"], sent))
+    # the staircase ground truth is recovered away from the band edges and image borders
+    truth = -synth.delta_rows(h, size_d)[:, None].astype(np.float32)
+    core = np.zeros((h, w), bool)
+    core[:, size_d + 20:-20] = True
+    assert (out["disp_left"][core] == np.broadcast_to(truth, (h, w))[core]).mean() > 0.9

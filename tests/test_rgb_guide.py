@@ -1,0 +1,50 @@
+"""RGB guide.  The reference has no colour-guide path, so parity is unpinned by
+construction: the oracle is checked through the identity "RGB path on a grey-valued RGB image ==
+gray path with eps/3" and the CUDA path is checked against that oracle."""
+import numpy as np
+import pytest
+
+import _oracle as O
+import synth
+
+
+def test_oracle_rgb_equals_gray_with_eps_over_3(oracle):
+    L, R = synth.make_pair(90, 60, 8, seed=21)
+    rgb = np.repeat(L[..., None], 3, axis=2).copy()
+    size_d, dmin = 8, -7
+    p_rgb = oracle.params(box_mode=O.BOX_EXACT, nthreads=4)
+    b_rgb, d_rgb, _ = oracle.view_disparity_rgb(rgb, L, R, size_d, dmin, p_rgb)
+    p_gray = oracle.params(box_mode=O.BOX_EXACT, nthreads=4, eps=6.5025 / 3)
+    b_gray, d_gray, _, s_gray = oracle.view_disparity(L, R, size_d, dmin, p_gray, want_second=True)
+    assert np.allclose(b_rgb, b_gray, rtol=2e-4, atol=1e-5)
+    margin = s_gray - b_gray
+    assert np.array_equal(d_rgb[margin > 1e-3], d_gray[margin > 1e-3])
+    assert (d_rgb == d_gray).mean() > 0.995
+
+
+@pytest.mark.gpu
+def test_gpu_rgb_guide_matches_oracle(oracle):
+    S = pytest.importorskip("stereo_matching_cuda_b200")
+    from stereo_matching_cuda_b200 import api
+
+    w, h, size_d = 150, 70, 12
+    L, R = synth.make_pair(w, h, size_d, channels=3, seed=5)
+    p = api.default_params(dmin=-(size_d - 1), dmax=0, guide_mode=S.GUIDE_RGB)
+    with S.Context(0) as ctx:
+        out = ctx.pipeline(L, R, p)
+        with pytest.raises(S.StereoB200Error):
+            ctx.pipeline(L[..., 0].copy(), R[..., 0].copy(), p)  # an RGB guide needs colour input
+    gl, gr = oracle.rgb_to_gray(L), oracle.rgb_to_gray(R)
+    assert np.array_equal(out["gray_left"], gl)
+    po = oracle.params(box_mode=O.BOX_EXACT, nthreads=oracle.max_threads())
+    bl, dl, sl = oracle.view_disparity_rgb(L, gl, gr, size_d, -(size_d - 1), po, want_second=True)
+    br, dr, sr = oracle.view_disparity_rgb(R, gr, gl, size_d, 0, po, want_second=True)
+    for got_d, got_b, d, b, s in ((out["disp_left"], out["best_left"], dl, bl, sl),
+                                  (out["disp_right"], out["best_right"], dr, br, sr)):
+        rel = np.abs(got_b - b) / np.maximum(np.abs(b), 1e-2)
+        assert rel.max() < 1e-4
+        assert np.array_equal(got_d[(s - b) > 2e-4], d[(s - b) > 2e-4])
+        assert (got_d == d).mean() > 0.999
+    occ = oracle.detect_occlusion(out["disp_left"], out["disp_right"], -(size_d - 1) - 100)
+    assert np.array_equal(out["occlusion"], occ)
+    assert np.array_equal(out["filled"], oracle.fill_occlusion(occ, -(size_d - 1)))
