@@ -364,3 +364,60 @@ def test_fused_full_size_1080p_d256(ctx, oracle):
     core = np.zeros((h, w), bool)
     core[:, size_d + 20:-20] = True
     assert (out["disp_left"][core] == np.broadcast_to(truth, (h, w))[core]).mean() > 0.9
+
+
+def test_cli_reproduces_the_twelve_golden_pngs(tsukuba):
+    """the driver's 12 output images decode to exactly the reference's checked-in PNGs."""
+    from stereo_matching_cuda_b200 import cli
+
+    L, R, _, _ = tsukuba
+    files = cli.run(L, R)
+    assert len(files) == 12
+    for name, img in files.items():
+        assert np.array_equal(img, O.load_png(name)), name
+    fused = cli.run(L, R, fused=True)
+    for name in ("image_left.png", "image_right.png", "cost_lminus15.png", "cost_rminus15.png"):
+        assert np.array_equal(fused[name], O.load_png(name)), name
+    for name in ("disparity_mapl.png", "disparity_mapr.png", "occlu_mapl_filled.png"):
+        assert (fused[name] == O.load_png(name)).mean() > 0.999, name
+
+
+@pytest.mark.parametrize("w,h,dmin,dmax", [(2, 1, -1, 0), (5, 3, -2, 1), (40, 1, -3, 0), (3, 50, 0, 2), (433, 65, -9, 0)])
+def test_fused_pipeline_tiny_and_ragged(ctx, oracle, w, h, dmin, dmax):
+    rng = np.random.default_rng(w * 100 + h)
+    L = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    R = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    size_d = dmax - dmin + 1
+    out = ctx.pipeline(L, R, api.default_params(dmin=dmin, dmax=dmax))
+    ref = oracle.pipeline_gray(L, R, dmin, size_d, oracle.params(box_mode=O.BOX_EXACT), want_second=True)
+    check_fused_vs_oracle(out, ref, margin_tau=2e-4, min_agree=0.99)
+
+
+def test_batch_dev_equals_single_pairs(ctx):
+    torch = pytest.importorskip("torch")
+    w, h, size_d, n = 260, 80, 10, 3
+    pairs = [synth.make_pair(w, h, size_d, seed=40 + i) for i in range(n)]
+    p = api.default_params(dmin=-(size_d - 1), dmax=0)
+    dl = torch.from_numpy(np.stack([a for a, _ in pairs])).cuda()
+    dr = torch.from_numpy(np.stack([b for _, b in pairs])).cuda()
+    outs = {k: torch.empty((n, h, w), dtype=torch.float32, device="cuda") for k in ("disp_left", "filled", "best_right")}
+    ctx.set_stream(torch.cuda.current_stream())
+    ctx.pipeline_batch_dev(dl, dr, 1, w, h, n, outs, p)
+    torch.cuda.synchronize()
+    for i, (a, b) in enumerate(pairs):
+        one = ctx.pipeline(a, b, p, want=("disp_left", "filled", "best_right"))
+        for k in outs:
+            assert np.array_equal(outs[k][i].cpu().numpy(), one[k]), (i, k)
+
+
+def test_invalid_arguments_are_reported_not_fatal(ctx):
+    img = np.zeros((30, 30), np.uint8)
+    for bad in (dict(radius=0), dict(box_mode=7)):
+        with pytest.raises(S.StereoB200Error):
+            ctx.pipeline(img, img, api.default_params(**bad))
+    with pytest.raises(S.StereoB200Error, match="same size"):
+        ctx.compute_cost(img, np.zeros((30, 31), np.uint8), -3)
+    with pytest.raises(S.StereoB200Error):
+        ctx.pipeline(np.zeros((30, 30, 2), np.uint8), np.zeros((30, 30, 2), np.uint8))
+    # the context is still usable afterwards
+    assert ctx.pipeline(img, img)["disp_left"].shape == (30, 30)
