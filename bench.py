@@ -263,6 +263,9 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        # NCCL_DEBUG=VERSION/INFO makes NCCL print to STDOUT, which would break the one-JSON-line contract
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.environ["NCCL_DEBUG_FILE"] = os.path.join("/tmp", "nccl_bench_%h_%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     mode = args.mode or {"c4": "batch", "c5": "strips" if world > 1 else "dp"}.get(args.workload, "dp")
 
