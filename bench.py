@@ -241,8 +241,13 @@ def main():
                     help="dp: one pair per step per GPU, weak scaling (default); batch: a fixed batch of 64 pairs "
                          "split over the GPUs (c4); strips: one frame split into row strips with halo exchange (c5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--guide", default="gray", choices=["gray", "rgb"],
+                    help="gray: the reference's only guide mode (fused kernel, parity pinned to its goldens); rgb: colour "
+                         "guided filter of SURVEY A.8, which the reference does not have (staged path, parity unpinned)")
     args = ap.parse_args()
     w, h, size_d, channels, desc = WORKLOADS[args.workload]
+    if args.guide == "rgb":
+        channels = 3
 
     if args.impl == "reference":
         run_reference(args, w, h, size_d, desc)
@@ -269,7 +274,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     mode = args.mode or {"c4": "batch", "c5": "strips" if world > 1 else "dp"}.get(args.workload, "dp")
 
-    p = api.default_params(dmin=-(size_d - 1), dmax=0)
+    p = api.default_params(dmin=-(size_d - 1), dmax=0, guide_mode=S.GUIDE_RGB if args.guide == "rgb" else S.GUIDE_GRAY)
     n = w * h
     dev = torch.device("cuda", local)
     ctx = S.Context(local, stream=torch.cuda.current_stream())
@@ -347,9 +352,9 @@ def main():
 
     # --- roofline pass: device time of the dominant kernel (k_fused_cvf) from CUDA events the
     # library records on the launching stream around that kernel, averaged over up to 10 steps
-    ctx.enable_timing(True)
+    ctx.enable_timing(args.guide == "gray")
     fused_ms, occl_ms, prep_ms, merge_ms = [], [], [], []
-    for i in range(min(args.steps, 10)):
+    for i in range(min(args.steps, 10) if args.guide == "gray" else 0):
         step(i)
         tm = ctx.last_timing()  # the step's last pair
         fused_ms.append(tm["fused_ms"])
@@ -357,7 +362,9 @@ def main():
         prep_ms.append(tm["prep_ms"])
         merge_ms.append(tm["merge_ms"])
     ctx.enable_timing(False)
-    fk = statistics.mean(fused_ms)
+    fk = statistics.mean(fused_ms) if fused_ms else float("nan")
+    if not fused_ms:
+        occl_ms = prep_ms = merge_ms = [float("nan")]
     rows_local = h if mode != "strips" else sharding.strip_geometry(h, rank, world, halo)["rows"]
     cells_per_launch = 2.0 * w * rows_local * size_d
 
@@ -404,7 +411,7 @@ def main():
             "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "fps": pairs_total_per_step * args.steps / (ms_max * 1e-3),
             "config": {
-                "workload": desc + f" (dmin={-(size_d - 1)}), gray guide, r=9, eps=6.5025, both views + L/R check + fill; "
+                "workload": desc + f" (dmin={-(size_d - 1)}), " + ("gray guide (the reference's only guide mode; BASELINE configs[2] names an RGB guide, which the reference does not implement: see --guide rgb)" if args.guide == "gray" else "RGB guide (SURVEY A.8; not in the reference; staged non-fused path)") + ", r=9, eps=6.5025, both views + L/R check + fill; "
                             + {"dp": "1 pair per step per GPU" + ("" if world == 1 else f", {world} GPUs data-parallel over pairs, no communication"),
                                "batch": f"a batch of 64 pairs per step split over {world} GPU(s), no communication",
                                "strips": f"one frame per step split into {world} row strips, {halo}-row input halos exchanged over NCCL send/recv"}[mode],
@@ -413,7 +420,7 @@ def main():
                       "WTA planes, several hundred MB at 1080p D=256) exceeds the 126 MB L2",
             },
             "roofline": {
-                "bound": "fp32_pipe", "kernel": "k_fused_cvf", "achieved": achieved / 1e12, "peak": peak_instr / 1e12,
+                "bound": "fp32_pipe", "kernel": "k_fused_cvf" if args.guide == "gray" else "(staged RGB path: no dominant kernel)", "achieved": achieved / 1e12, "peak": peak_instr / 1e12,
                 "unit": "T lane-instr/s", "frac": achieved / peak_instr,
                 "traffic": tr.get("dram_bytes_per_launch") if tr and mode == "dp" and args.workload == "c3" else None,
                 "traffic_src": tr.get("src") if tr and mode == "dp" and args.workload == "c3" else None,
