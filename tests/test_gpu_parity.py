@@ -421,3 +421,61 @@ def test_invalid_arguments_are_reported_not_fatal(ctx):
         ctx.pipeline(np.zeros((30, 30, 2), np.uint8), np.zeros((30, 30, 2), np.uint8))
     # the context is still usable afterwards
     assert ctx.pipeline(img, img)["disp_left"].shape == (30, 30)
+
+
+def test_full_size_c2_bike_shape_rgb(ctx, oracle):
+    """BASELINE configs[1]: 3052x1968 colour input, D=16, full pipeline incl. fill, against the exact oracle."""
+    w, h, size_d = 3052, 1968, 16
+    L, R = synth.make_pair(w, h, size_d, channels=3, seed=2)
+    out = ctx.pipeline(L, R, want=("gray_left", "gray_right", "disp_left", "disp_right", "best_left", "best_right",
+                                   "occlusion", "filled"))
+    gl, gr = oracle.rgb_to_gray(L), oracle.rgb_to_gray(R)
+    assert np.array_equal(out["gray_left"], gl) and np.array_equal(out["gray_right"], gr)
+    ref = oracle.pipeline_gray(gl, gr, -15, size_d, oracle.params(box_mode=O.BOX_EXACT, nthreads=oracle.max_threads()),
+                               want_second=True)
+    for lab, best, second, o_lab, o_best in (("dL", "bestL", "secondL", "disp_left", "best_left"),
+                                             ("dR", "bestR", "secondR", "disp_right", "best_right")):
+        same = out[o_lab] == ref[lab]
+        assert same.mean() >= 0.999
+        assert np.all(same[(ref[second] - ref[best]) > 1e-3])
+        assert (np.abs(out[o_best] - ref[best]) / np.maximum(np.abs(ref[best]), 0.1)).max() < RTOL_BEST
+    occ = oracle.detect_occlusion(out["disp_left"], out["disp_right"], -115)
+    assert np.array_equal(out["occlusion"], occ)
+    assert np.array_equal(out["filled"], oracle.fill_occlusion(occ, -15))
+
+
+def test_full_size_c5_8k_properties(ctx, oracle):
+    """BASELINE configs[4] shape: 7680x4320, D=512 on one GPU.  Too large for the CPU oracle's filter, so:
+    size-independent properties, the exact occlusion/fill functions on the produced labels, and a
+    sampled row band recomputed as a strip (with halos) that must reproduce the whole-frame labels."""
+    torch = pytest.importorskip("torch")
+    w, h, size_d = 7680, 4320, 512
+    L, R = synth.make_pair(w, h, size_d, seed=0)
+    p = api.default_params(dmin=-(size_d - 1), dmax=0)
+    out = ctx.pipeline(L, R, p, want=("disp_left", "disp_right", "occlusion", "filled"))
+    assert out["disp_left"].min() >= -(size_d - 1) and out["disp_left"].max() <= 0
+    assert out["disp_right"].min() >= 0 and out["disp_right"].max() <= size_d - 1
+    sent = -(size_d - 1) - 100
+    occ = oracle.detect_occlusion(out["disp_left"], out["disp_right"], sent)
+    assert np.array_equal(out["occlusion"], occ)
+    assert np.array_equal(out["filled"], oracle.fill_occlusion(occ, -(size_d - 1)))
+    truth = -synth.delta_rows(h, size_d)[:, None].astype(np.float32)
+    core = np.zeros((h, w), bool)
+    core[:, size_d + 20:-20] = True
+    assert (out["disp_left"][core] == np.broadcast_to(truth, (h, w))[core]).mean() > 0.9
+    # one 128-row strip in the middle of the frame, recomputed from its rows + 18-row halos
+    y0, rows, halo = 2048, 128, 18
+    dl = torch.from_numpy(L[y0 - halo:y0 + rows + halo].copy()).cuda()
+    dr = torch.from_numpy(R[y0 - halo:y0 + rows + halo].copy()).cuda()
+    so = {k: torch.empty((rows, w), dtype=torch.float32, device="cuda") for k in ("disp_left", "disp_right")}
+    ctx.set_stream(torch.cuda.current_stream())
+    ctx.pipeline_strip_dev(dl, dr, 1, w, dict(y0=y0, rows=rows, halo_top=halo, halo_bot=halo, frame_h=h), so, p)
+    torch.cuda.synchronize()
+    for k in so:
+        assert (so[k].cpu().numpy() == out[k][y0:y0 + rows]).mean() > 0.9999, k
+
+
+def test_width_one_is_rejected(ctx):
+    img = np.zeros((8, 1), np.uint8)
+    with pytest.raises(S.StereoB200Error):
+        ctx.pipeline(img, img)  # the reference's own gradient kernel reads out of bounds at w == 1
