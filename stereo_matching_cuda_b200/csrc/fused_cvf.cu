@@ -404,12 +404,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
                     tm_fence_before();
                     named_bar_arrive(BAR_FULL, 64);
                 };
-                int it = 0;
-                for (; it + 1 < niter; it += 2) {
+#pragma unroll 1
+                for (int it = 0; it < niter; it++) {
                     iter(opsA, opsB, it);
-                    iter(opsB, opsA, it + 1);
+#pragma unroll
+                    for (int r = 0; r < ROWS; r++) opsA[r] = opsB[r];
                 }
-                if (it < niter) iter(opsA, opsB, it);
             }
             __syncthreads();  // group end
         }
@@ -596,15 +596,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
             static_assert((4 * RAD) % ROWS == 0, "ROWS must divide the warm-up length");
             if (active) {
                 int it = 0;
-                for (; it < WARM_IT; it += 2) {
+#pragma unroll 1
+                for (; it < WARM_IT; it++) {
                     iter(std::false_type{}, opsA, opsB, it);
-                    iter(std::false_type{}, opsB, opsA, it + 1);
+#pragma unroll
+                    for (int r = 0; r < ROWS; r++) opsA[r] = opsB[r];
                 }
-                for (; it + 1 < niter; it += 2) {
+#pragma unroll 1
+                for (; it < niter; it++) {
                     iter(std::true_type{}, opsA, opsB, it);
-                    iter(std::true_type{}, opsB, opsA, it + 1);
+#pragma unroll
+                    for (int r = 0; r < ROWS; r++) opsA[r] = opsB[r];
                 }
-                if (it < niter) iter(std::true_type{}, opsA, opsB, it);
             } else {
                 // no disparity for this pair in the (last, partial) group: only take part in the merge
                 for (int it = WARM_IT; it < niter; it++) {
