@@ -39,7 +39,7 @@ WORKLOADS = {
     "c4": (1920, 1080, 128, 1, "synthetic 1920x1080 pairs, D=128 (batch data-parallel)"),
     "c5": (7680, 4320, 512, 1, "synthetic 7680x4320 pair, D=512"),
 }
-INSTR_PER_CELL = 35  # useful FP32 instructions per (pixel, disparity) cell, gray guide
+INSTR_PER_CELL = 35  # useful FP32 instructions per (pixel, disparity) cell, gray guide (RGB: 71)
 FLOP_PER_CELL = 39
 
 
@@ -352,9 +352,9 @@ def main():
 
     # --- roofline pass: device time of the dominant kernel (k_fused_cvf) from CUDA events the
     # library records on the launching stream around that kernel, averaged over up to 10 steps
-    ctx.enable_timing(args.guide == "gray")
+    ctx.enable_timing(True)
     fused_ms, occl_ms, prep_ms, merge_ms = [], [], [], []
-    for i in range(min(args.steps, 10) if args.guide == "gray" else 0):
+    for i in range(min(args.steps, 10)):
         step(i)
         tm = ctx.last_timing()  # the step's last pair
         fused_ms.append(tm["fused_ms"])
@@ -362,9 +362,7 @@ def main():
         prep_ms.append(tm["prep_ms"])
         merge_ms.append(tm["merge_ms"])
     ctx.enable_timing(False)
-    fk = statistics.mean(fused_ms) if fused_ms else float("nan")
-    if not fused_ms:
-        occl_ms = prep_ms = merge_ms = [float("nan")]
+    fk = statistics.mean(fused_ms)
     rows_local = h if mode != "strips" else sharding.strip_geometry(h, rank, world, halo)["rows"]
     cells_per_launch = 2.0 * w * rows_local * size_d
 
@@ -400,10 +398,42 @@ def main():
                "ms_per_step": 1e3 * float(te.item()) / n_e2e,
                "api": "sb200_pipeline (host pointers, pinned, blocking; H2D of the pair and D2H of 4 float maps inside)"}
 
+    # --- the same shape with the RGB guide BASELINE configs[2] names (the reference has no such
+    # mode, so it is reported beside the gray-guide headline rather than instead of it)
+    rgb_extra = None
+    if mode == "dp" and args.guide == "gray" and args.workload == "c3":
+        p_rgb = api.default_params(dmin=-(size_d - 1), dmax=0, guide_mode=S.GUIDE_RGB)
+        cpairs = make_inputs(w, h, size_d, 3, 2)
+        c_in = [(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)) for a, b in cpairs]
+        for i in range(3):
+            ctx.pipeline_dev(c_in[i % 2][0], c_in[i % 2][1], 3, w, h, outs, p_rgb)
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_rgb = max(3, min(args.steps, 10))
+        r0.record()
+        for i in range(n_rgb):
+            ctx.pipeline_dev(c_in[i % 2][0], c_in[i % 2][1], 3, w, h, outs, p_rgb)
+        r1.record()
+        barrier()
+        tr_ms = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tr_ms, op=dist.ReduceOp.MAX)
+        ctx.enable_timing(True)
+        ctx.pipeline_dev(c_in[0][0], c_in[0][1], 3, w, h, outs, p_rgb)
+        k_rgb = ctx.last_timing()["fused_ms"]
+        ctx.enable_timing(False)
+        ms_rgb = float(tr_ms.item()) / n_rgb
+        rgb_extra = {"value": world * 2.0 * w * h * size_d / (ms_rgb * 1e-3), "unit": "px*d/s", "ms_per_step": ms_rgb,
+                     "fps": world / (ms_rgb * 1e-3), "kernel": "k_fused_cvf_rgb", "kernel_ms": k_rgb, "instr_per_cell": 71,
+                     "roofline_frac": 71 * 2.0 * w * h * size_d / (k_rgb * 1e-3) / (148 * 128 * peaks()["sm_max_mhz"] * 1e6),
+                     "note": "colour guided filter of SURVEY A.8 on 3-channel synthetic pairs; not in the reference "
+                             "(parity unpinned; checked against the oracle's RGB port and the eps/3 identity)"}
+
     if rank == 0:
         pk = peaks()
         peak_instr = 148 * 128 * pk["sm_max_mhz"] * 1e6  # FP32 lane-instructions/s at the max SM clock
-        achieved = INSTR_PER_CELL * cells_per_launch / (fk * 1e-3)
+        ipc = INSTR_PER_CELL if args.guide == "gray" else 71
+        achieved = ipc * cells_per_launch / (fk * 1e-3)
         tr = ncu_traffic()
         line = {
             "metric": "pixel-disparities/sec", "value": value, "unit": "px*d/s", "n_gpus": world, "steps": args.steps,
@@ -411,7 +441,7 @@ def main():
             "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "fps": pairs_total_per_step * args.steps / (ms_max * 1e-3),
             "config": {
-                "workload": desc + f" (dmin={-(size_d - 1)}), " + ("gray guide (the reference's only guide mode; BASELINE configs[2] names an RGB guide, which the reference does not implement: see --guide rgb)" if args.guide == "gray" else "RGB guide (SURVEY A.8; not in the reference; staged non-fused path)") + ", r=9, eps=6.5025, both views + L/R check + fill; "
+                "workload": desc + f" (dmin={-(size_d - 1)}), " + ("gray guide (the reference's only guide mode; BASELINE configs[2] names an RGB guide, which the reference does not implement: see --guide rgb)" if args.guide == "gray" else "RGB guide (SURVEY A.8; not in the reference)") + ", r=9, eps=6.5025, both views + L/R check + fill; "
                             + {"dp": "1 pair per step per GPU" + ("" if world == 1 else f", {world} GPUs data-parallel over pairs, no communication"),
                                "batch": f"a batch of 64 pairs per step split over {world} GPU(s), no communication",
                                "strips": f"one frame per step split into {world} row strips, {halo}-row input halos exchanged over NCCL send/recv"}[mode],
@@ -420,12 +450,12 @@ def main():
                       "WTA planes, several hundred MB at 1080p D=256) exceeds the 126 MB L2",
             },
             "roofline": {
-                "bound": "fp32_pipe", "kernel": "k_fused_cvf" if args.guide == "gray" else "(staged RGB path: no dominant kernel)", "achieved": achieved / 1e12, "peak": peak_instr / 1e12,
+                "bound": "fp32_pipe", "kernel": "k_fused_cvf" if args.guide == "gray" else "k_fused_cvf_rgb", "achieved": achieved / 1e12, "peak": peak_instr / 1e12,
                 "unit": "T lane-instr/s", "frac": achieved / peak_instr,
                 "traffic": tr.get("dram_bytes_per_launch") if tr and mode == "dp" and args.workload == "c3" else None,
                 "traffic_src": tr.get("src") if tr and mode == "dp" and args.workload == "c3" else None,
-                "kernel_ms": fk, "instr_per_cell": INSTR_PER_CELL,
-                "flop_frac": FLOP_PER_CELL * cells_per_launch / (fk * 1e-3) / (2 * peak_instr),
+                "kernel_ms": fk, "instr_per_cell": ipc,
+                "flop_frac": (FLOP_PER_CELL if args.guide == "gray" else 87) * cells_per_launch / (fk * 1e-3) / (2 * peak_instr),
                 "peak_src": f"148 SMs x 128 FP32 lanes x {pk['sm_max_mhz']:.0f} MHz (sm_max_mhz, {pk['src']})",
                 "note": "north_star names the FP32 CUDA-core pipe as this kernel's roofline (no dense contraction; see "
                         "hbm_frac_of_kernel_time for how little of the kernel's time its DRAM traffic explains)",
@@ -440,6 +470,8 @@ def main():
         }
         if e2e:
             line["e2e"] = e2e
+        if rgb_extra:
+            line["rgb_guide"] = rgb_extra
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(w, h, size_d)
         print(json.dumps(line))

@@ -295,14 +295,17 @@ int pipeline_core(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, 
     const size_t n_out = (size_t)w * g.rows_out;
     const int dabs = max(abs(p->dmin), abs(p->dmax));
     if (reserve) {
-        size_t bytes = p->guide_mode == SB200_GUIDE_RGB ? rgb_ws_bytes(n_held) : sbf_workspace_bytes(ctx, w, g.h, g.rows_out, dabs, size_d, 2);
+        size_t bytes = p->guide_mode != SB200_GUIDE_RGB ? sbf_workspace_bytes(ctx, w, g.h, g.rows_out, dabs, size_d, 2)
+                       : (p->box_mode == SB200_BOX_SAT ? rgb_ws_bytes(n_held) : sbf_rgb_workspace_bytes(ctx, w, g.h, g.rows_out, dabs, size_d));
         bytes += 2 * sb_align(n_held) + 4 * sb_align(n_out * 4) + 4096;
         SB_TRY(sb_ws_reserve(ctx, bytes));
     }
     const bool full = (g.rows_out == g.h);
     const bool rgb_guide = (p->guide_mode == SB200_GUIDE_RGB);
-    if (rgb_guide && (channels < 3 || !full))
-        return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "RGB guide needs a colour input and a whole frame (no strips yet)");
+    // RGB guide: fused kernel (fused_cvf_rgb.cu); box_mode SAT selects the staged, materialising path instead
+    const bool rgb_staged = rgb_guide && p->box_mode == SB200_BOX_SAT;
+    if (rgb_guide && channels < 3) return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "RGB guide needs a colour input");
+    if (rgb_staged && !full) return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "staged RGB guide needs a whole frame");
     if (rgb_guide && (o->mean_left || o->mean_right))
         return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "mean_left/mean_right are gray-guide outputs");
     const uint8_t* gl = d_left;
@@ -332,7 +335,9 @@ int pipeline_core(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, 
         if (mL) SB_TRY(ws_get(ctx, &mLh, n_held));
         if (mR) SB_TRY(ws_get(ctx, &mRh, n_held));
     }
-    if (rgb_guide) {
+    if (rgb_guide && !rgb_staged) {
+        SB_TRY(sbf_pair_disparity_rgb(ctx, p, d_left, d_right, channels, gl, gr, g, o->best_left, dL, o->best_right, dR));
+    } else if (rgb_guide) {
         float *bL = o->best_left, *bR = o->best_right;
         if (!bL) SB_TRY(ws_get(ctx, &bL, n_out));
         if (!bR) SB_TRY(ws_get(ctx, &bR, n_out));
@@ -505,7 +510,8 @@ int sb200_pipeline(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h_left,
     const size_t n = (size_t)w * h;
     const int size_d = p->dmax - p->dmin + 1;
     const int dabs = max(abs(p->dmin), abs(p->dmax));
-    size_t bytes = (p->guide_mode == SB200_GUIDE_RGB ? rgb_ws_bytes(n) : sbf_workspace_bytes(ctx, w, h, h, dabs, size_d, 2)) +
+    size_t bytes = (p->guide_mode != SB200_GUIDE_RGB ? sbf_workspace_bytes(ctx, w, h, h, dabs, size_d, 2)
+                    : (p->box_mode == SB200_BOX_SAT ? rgb_ws_bytes(n) : sbf_rgb_workspace_bytes(ctx, w, h, h, dabs, size_d))) +
                    2 * sb_align(n) + 4 * sb_align(n * 4) + 4096;
     bytes += 2 * sb_align(n * channels) + 6 * sb_align(n * 4) + 4 * sb_align(n) + 4096;
     SB_TRY(sb_ws_reserve(ctx, bytes));

@@ -128,3 +128,8 @@ int sbf_pair_disparity(sb200_ctx* ctx, const sb200_params* p, const uint8_t* gra
 // single view (guide, other, dmin)
 int sbf_view_disparity(sb200_ctx* ctx, const sb200_params* p, const uint8_t* guide, const uint8_t* other,
                        const SbFusedGeom& g, int dmin, int size_d, float* best, float* disp, uint8_t* mean);
+// RGB guide, fused (fused_cvf_rgb.cu): colour images (interleaved, `channels` bytes per pixel) + their gray versions
+size_t sbf_rgb_workspace_bytes(const sb200_ctx* ctx, int w, int h_held, int rows_out, int dabs, int size_d);
+int sbf_pair_disparity_rgb(sb200_ctx* ctx, const sb200_params* p, const uint8_t* rgb_l, const uint8_t* rgb_r, int channels,
+                           const uint8_t* gray_l, const uint8_t* gray_r, const SbFusedGeom& g, float* bestL, float* dispL,
+                           float* bestR, float* dispR);

@@ -1,0 +1,203 @@
+// fused_dev.cuh -- device helpers and host planning shared by the fused kernels
+// (fused_cvf.cu: gray guide, fused_cvf_rgb.cu: RGB guide).
+#pragma once
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int KPX = 8;            // pixels per lane
+constexpr int SW = 32 * KPX;      // columns per warp strip
+constexpr int HALO = 20;          // left halo (>= 2*radius, multiple of 4)
+constexpr int VALID_W = 216;      // valid output columns per strip: local [20, 236)
+constexpr int RAD = 9;
+constexpr int WIN = 2 * RAD + 1;  // 19
+constexpr int NWARP = 4;          // disparities in flight per block (= warp pairs)
+constexpr int NTHREADS = 2 * NWARP * 32;
+constexpr int ROWS = 2;           // image rows per pipeline iteration: independent horizontal work for ILP
+constexpr int PADY = 40;          // padding rows above/below the prepared planes
+constexpr float BEST_INIT_BITS_F = 3.3961514e38f;  // 0x7F7F7F7F, main.cu:112
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ---- Tensor Memory as per-thread scratch -------------------------------------------------
+// The 19-row rings and the producer->consumer hand-off live in TMEM (256 KB per SM, idle in a
+// kernel without tensor-core work) instead of shared memory: tcgen05.ld/st have their own data
+// path, so this traffic (72 of ~205 wavefronts per row, round-1 ncu: L1TEX data pipe at 78 %)
+// leaves the shared-memory/shuffle/L1 pipe.  With the 32x32b shape every thread of a warp owns
+// one TMEM lane (warp w may touch lanes 32*(w%4)..+31) and N consecutive 32-bit columns, i.e.
+// private scratch; warps p and p+4 (a producer/consumer pair) share a lane quarter, which is
+// what lets the producer hand its rows to the consumer through TMEM.
+// Column map of one lane (512 allocated): [0,304) ring of (a[8],b[8]) x 19 slots,
+// [304,380) ring of the lattice cost (8 halfs = 4 words) x 19 slots, [384,416) hand-off rows.
+constexpr uint32_t TM_COLS = 512;
+constexpr uint32_t TM_RING_AB = 0, TM_RING_P = 304, TM_HAND = 384;
+
+__device__ __forceinline__ void tm_alloc(uint32_t* smem_dst) {  // one converged warp
+    uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst), "r"(TM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tm_dealloc(uint32_t taddr) {  // the warp that allocated
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(TM_COLS) : "memory");
+}
+__device__ __forceinline__ void tm_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tm_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tm_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3])
+                 : "memory");
+}
+__device__ __forceinline__ void tm_ld16(uint32_t taddr, float (&a)[8], float (&b)[8]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+        "[%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        a[j] = __uint_as_float(r[j]);
+        b[j] = __uint_as_float(r[8 + j]);
+    }
+}
+__device__ __forceinline__ void tm_st16(uint32_t taddr, const float (&a)[8], const float (&b)[8]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16};" ::"r"(taddr),
+        "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+        "r"(__float_as_uint(a[4])), "r"(__float_as_uint(a[5])), "r"(__float_as_uint(a[6])), "r"(__float_as_uint(a[7])),
+        "r"(__float_as_uint(b[0])), "r"(__float_as_uint(b[1])), "r"(__float_as_uint(b[2])), "r"(__float_as_uint(b[3])),
+        "r"(__float_as_uint(b[4])), "r"(__float_as_uint(b[5])), "r"(__float_as_uint(b[6])), "r"(__float_as_uint(b[7]))
+        : "memory");
+}
+
+// 19-wide horizontal window sums for the 8 consecutive pixels this lane holds.
+// Lane L holds columns 8L..8L+7.  With LP_L[i] the lane-local prefix sums and T_L the lane
+// total, the window [x-9, x+9] for pixel j of lane L is
+//   (T_{L-1} - LP_{L-1}[j-2]) + T_L + LP_{L+1}[j+1]            for 2 <= j <= 6
+// with the obvious edge forms for j = 0, 1, 7 (one pixel of lanes L-2 / L+2 is needed).
+// 16 shuffles + 26 adds per 8 pixels.  Results are valid for lanes whose neighbours exist,
+// i.e. for strip-local columns [9, 247).
+__device__ __forceinline__ void hsum19(const float (&v)[KPX], float (&h)[KPX]) {
+    const unsigned F = 0xffffffffu;
+    float lp[KPX];
+    lp[0] = v[0];
+#pragma unroll
+    for (int i = 1; i < KPX; i++) lp[i] = lp[i - 1] + v[i];
+    const float T = lp[7];
+    const float Tm1 = __shfl_up_sync(F, T, 1);
+    const float Tp1 = __shfl_down_sync(F, T, 1);
+    const float C = T + Tm1;
+    float r[7];
+#pragma unroll
+    for (int j = 0; j < 6; j++) r[j] = __shfl_down_sync(F, lp[j + 1], 1);
+    r[6] = Tp1;
+    float l[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) l[i] = __shfl_up_sync(F, lp[i], 1);
+    const float vm2 = __shfl_up_sync(F, v[7], 2);
+    const float vp2 = __shfl_down_sync(F, v[0], 2);
+    h[0] = (vm2 + C) + r[0];
+    h[1] = C + r[1];
+#pragma unroll
+    for (int j = 2; j <= 6; j++) h[j] = (C + r[j]) - l[j - 2];
+    h[7] = ((C - l[5]) + Tp1) + vp2;
+}
+
+__device__ __forceinline__ __half2 u2h2(unsigned u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ unsigned h22u(__half2 h) { return *reinterpret_cast<unsigned*>(&h); }
+
+// ---------------------------------------------------------------------------------------
+// Chunk merge: fold the per-chunk (best,label) planes in chunk order with the same rule.
+__global__ void k_merge_chunks(const float* __restrict__ bestS, const float* __restrict__ labS, int n_chunks, int view,
+                               int rows, int w, int pitchS, float* __restrict__ best, float* __restrict__ disp) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w) return;
+    const size_t plane = (size_t)rows * pitchS;
+    float b = BEST_INIT_BITS_F, l = 0.0f;
+    for (int c = 0; c < n_chunks; c++) {
+        size_t off = (size_t)(c * 2 + view) * plane + (size_t)y * pitchS + x;
+        float q = bestS[off];
+        if (b >= q) { b = q; l = labS[off]; }
+    }
+    if (best) best[(size_t)y * w + x] = b;
+    if (disp) disp[(size_t)y * w + x] = l;
+}
+
+// Find integers (nI, nG, S) with (1-alpha) ~= nI/S and alpha/2 ~= nG/S (relative 1e-6) such
+// that the lattice cost P = nI*cI + nG*cG stays exactly representable through both box sums.
+bool find_lattice(const sb200_params* p, int* nI, int* nG, int* S) {
+    const double wI = (double)(1.0f - p->alpha), wG = (double)p->alpha / 2.0;
+    const double tc = p->th_color, tg2 = 2.0 * p->th_grad;
+    if (tc != (double)(int)tc || tg2 != (double)(int)tg2 || tc < 0 || tg2 < 0 || tc > 255 || tg2 > 1020) return false;
+    for (int s = 1; s <= 4096; s++) {
+        double a = wI * s, b = wG * s;
+        long ia = lround(a), ib = lround(b);
+        if (ia < 0 || ib < 0 || (ia == 0 && ib == 0)) continue;
+        if (fabs(a - ia) > 1e-6 * fmax(a, 1e-3) * 1.0 + 1e-9 * s && fabs(a - ia) > 2e-6 * a) continue;
+        if (fabs(b - ib) > 2e-6 * b && fabs(b - ib) > 1e-9 * s) continue;
+        double pmax = ia * tc + ib * tg2;
+        // half-exact lattice values and fp32-exact 361-element sums of I*P
+        if (pmax > 2047.0 || 361.0 * 255.0 * pmax >= 16777216.0) return false;
+        *nI = (int)ia;
+        *nG = (int)ib;
+        *S = s;
+        return true;
+    }
+    return false;
+}
+
+struct Plan {
+    int n_strips, n_bands, band_rows, n_chunks, chunk_d;
+};
+
+// Tile (strip x band x chunk x 2 views) so that the block count is close to a multiple of the
+// SM count with as little warm-up (36 extra rows per band) and group padding as possible.
+Plan make_plan(int w, int rows_out, int size_d, int sm_count, int n_views) {
+    Plan best{};
+    double best_cost = 1e300;
+    const int n_strips = (w + VALID_W - 1) / VALID_W;
+    const int groups = (size_d + NWARP - 1) / NWARP;
+    for (int n_chunks = 1; n_chunks <= groups; n_chunks++) {
+        int gpc = (groups + n_chunks - 1) / n_chunks;  // groups per chunk
+        int real_chunks = (groups + gpc - 1) / gpc;
+        if (real_chunks != n_chunks) continue;
+        for (int n_bands = 1; n_bands <= 64; n_bands++) {
+            int band_rows = (rows_out + n_bands - 1) / n_bands;
+            if (n_bands > 1 && band_rows < 64) break;
+            int real_bands = (rows_out + band_rows - 1) / band_rows;
+            if (real_bands != n_bands) continue;
+            long blocks = (long)n_strips * n_bands * n_chunks * n_views;
+            long waves = (blocks + sm_count - 1) / sm_count;
+            // time ~ waves * per-block work; per-block work ~ groups/chunk * (band_rows + 36)
+            double t = (double)waves * gpc * (band_rows + 4.0 * RAD) + 0.02 * n_chunks * rows_out / 64.0;
+            if (t < best_cost) {
+                best_cost = t;
+                best = Plan{n_strips, n_bands, band_rows, n_chunks, gpc * NWARP};
+            }
+        }
+    }
+    return best;
+}
+
+int pad_x(int dabs) { return (dabs + SW + 8 + 7) / 8 * 8; }
+
+}  // namespace

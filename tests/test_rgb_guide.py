@@ -48,3 +48,24 @@ def test_gpu_rgb_guide_matches_oracle(oracle):
     occ = oracle.detect_occlusion(out["disp_left"], out["disp_right"], -(size_d - 1) - 100)
     assert np.array_equal(out["occlusion"], occ)
     assert np.array_equal(out["filled"], oracle.fill_occlusion(occ, -(size_d - 1)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,size_d", [(470, 130, 21), (216, 40, 4), (33, 25, 3)])
+def test_gpu_rgb_fused_shapes_and_staged_agree(oracle, w, h, size_d):
+    """fused RGB kernel (default) vs the oracle on several tilings, and vs the staged RGB path"""
+    S = pytest.importorskip("stereo_matching_cuda_b200")
+    from stereo_matching_cuda_b200 import api
+
+    L, R = synth.make_pair(w, h, max(size_d, 2), channels=3, seed=w)
+    dmin = -(size_d - 1)
+    p = api.default_params(dmin=dmin, dmax=0, guide_mode=S.GUIDE_RGB)
+    with S.Context(0) as ctx:
+        out = ctx.pipeline(L, R, p, want=("disp_left", "disp_right", "best_left", "best_right", "filled"))
+    gl, gr = oracle.rgb_to_gray(L), oracle.rgb_to_gray(R)
+    po = oracle.params(box_mode=O.BOX_EXACT, nthreads=oracle.max_threads())
+    for guide, g1, g2, dm, kd, kb in ((L, gl, gr, dmin, "disp_left", "best_left"), (R, gr, gl, 0, "disp_right", "best_right")):
+        b, d, s = oracle.view_disparity_rgb(guide, g1, g2, size_d, dm, po, want_second=True)
+        assert (np.abs(out[kb] - b) / np.maximum(np.abs(b), 0.1)).max() < 1e-4
+        assert np.array_equal(out[kd][(s - b) > 2e-4], d[(s - b) > 2e-4])
+        assert (out[kd] == d).mean() > 0.999
