@@ -302,31 +302,41 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf_rgb(const RgbArgs A) 
                 // row pointers of THIS iteration's operands (stats at ya = yi-9, colour at yq = yi-18)
                 long long rs = (long long)(y_first - RAD) * pitch + xl;
                 long long rq = (long long)(y_first - 2 * RAD) * pitch + xl;
+                // The 72 statistics words of a row are fetched right after the LAST use of the previous
+                // row's (in the same registers), i.e. most of an iteration before their first use, without
+                // a second register set.
+                float4 s1[KPX], s2[KPX];
+                float4 s3a, s3b;
+                auto load_stats = [&](long long off) {
+                    const float4* p1 = S1 + off;
+                    const float4* p2 = S2 + off;
+#pragma unroll
+                    for (int j = 0; j < KPX; j++) {
+                        s1[j] = __ldg(p1 + j);
+                        s2[j] = __ldg(p2 + j);
+                    }
+                    const float4* p3 = reinterpret_cast<const float4*>(S3 + off);
+                    s3a = __ldg(p3);
+                    s3b = __ldg(p3 + 1);
+                };
+                load_stats(rs);
 #pragma unroll 1
                 for (int it = 0; it < niter; it++, rs += pitch, rq += pitch) {
                     const bool emit = it >= 4 * RAD;
                     const int yi = y_first + it;
                     const int yq = yi - 2 * RAD;
-                    // operands of this row: issued now, first used after the producer's rows have arrived
-                    float4 s1[KPX], s2[KPX];
-                    float s3[KPX];
+                    // take the scoreboard wait on the statistics before new loads are issued (see fused_cvf.cu)
+                    unsigned tw = __float_as_uint(s3a.x) | __float_as_uint(s3b.x);
+#pragma unroll
+                    for (int j = 0; j < KPX; j++) tw |= __float_as_uint(s1[j].x) | __float_as_uint(s2[j].x);
+                    const int dep = (int)tw & A.zero;
                     uint4 cq[4];
                     {
-                        const float4* p1 = S1 + rs;
-                        const float4* p2 = S2 + rs;
-#pragma unroll
-                        for (int j = 0; j < KPX; j++) {
-                            s1[j] = __ldg(p1 + j);
-                            s2[j] = __ldg(p2 + j);
-                        }
-                        const float4* p3 = reinterpret_cast<const float4*>(S3 + rs);
-                        const float4 t0 = __ldg(p3), t1 = __ldg(p3 + 1);
-                        s3[0] = t0.x; s3[1] = t0.y; s3[2] = t0.z; s3[3] = t0.w;
-                        s3[4] = t1.x; s3[5] = t1.y; s3[6] = t1.z; s3[7] = t1.w;
-                        const uint4* pc = reinterpret_cast<const uint4*>(C2 + rq);
+                        const uint4* pc = reinterpret_cast<const uint4*>(C2 + rq + dep);
 #pragma unroll
                         for (int k = 0; k < 4; k++) cq[k] = __ldg(pc + k);
                     }
+                    const float s3[KPX] = {s3a.x, s3a.y, s3a.z, s3a.w, s3b.x, s3b.y, s3b.z, s3b.w};
                     float pb0, pb1, pl0, pl1;
                     if (emit) prefetch_best(yq, pb0, pb1, pl0, pl1);
                     const float ry1 = inv_rows_rgb(yi - RAD, A.y_global0, A.frame_h, A.S);
@@ -357,6 +367,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf_rgb(const RgbArgs A) 
                         const float mp = SP[j] * (rx[j] * ry1);
                         bb[j] = mp - fmaf(ar[j], mr, fmaf(ag[j], mg, ab[j] * mb));
                     }
+                    load_stats(rs + pitch);  // next row's statistics (padding rows past the end are zero)
                     tm_st16(tA + 16 * slot, ar, ag);
                     sm.ringB[pair][slot][0][lane] = make_float4(ab[0], ab[1], ab[2], ab[3]);
                     sm.ringB[pair][slot][1][lane] = make_float4(ab[4], ab[5], ab[6], ab[7]);
