@@ -479,3 +479,26 @@ def test_width_one_is_rejected(ctx):
     img = np.zeros((8, 1), np.uint8)
     with pytest.raises(S.StereoB200Error):
         ctx.pipeline(img, img)  # the reference's own gradient kernel reads out of bounds at w == 1
+
+
+def test_fused_vs_staged_random_shapes(ctx):
+    """Two independent CUDA implementations of the same path (fused kernel vs stage-by-stage kernels with
+    double-accumulated sliding boxes) on random shapes and disparity ranges: exercises strips, bands,
+    chunks and partial disparity groups without needing the CPU."""
+    rng = np.random.default_rng(2026)
+    for _ in range(10):
+        w = int(rng.integers(24, 900))
+        h = int(rng.integers(8, 260))
+        size_d = int(rng.integers(1, 40))
+        dmax = int(rng.integers(0, 3))
+        dmin = dmax - size_d + 1
+        L, R = synth.make_pair(w, h, max(size_d, 2), seed=int(rng.integers(1 << 20)))
+        p = api.default_params(dmin=dmin, dmax=dmax)
+        out = ctx.pipeline(L, R, p, want=("disp_left", "best_left", "disp_right", "best_right"))
+        for guide, other, dm, kd, kb in ((L, R, dmin, "disp_left", "best_left"), (R, L, -dmax, "disp_right", "best_right")):
+            cost = ctx.compute_cost(guide, other, dm, p)
+            best = np.full((h, w), 3.3961514e38, np.float32)
+            dmap = np.zeros((h, w), np.float32)
+            ctx.compute_guided_filter(guide, cost, best, dmap, dm, p)  # box_mode SLIDING: double accumulation
+            assert (np.abs(out[kb] - best) / np.maximum(np.abs(best), 0.1)).max() < RTOL_BEST, (w, h, dmin, dmax)
+            assert (out[kd] == dmap).mean() > 0.998, (w, h, dmin, dmax, (out[kd] == dmap).mean())
