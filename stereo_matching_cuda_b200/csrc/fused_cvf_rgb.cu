@@ -10,8 +10,8 @@
 // Same machinery as fused_cvf.cu (warp strips of 256 columns, producer/consumer warp pairs,
 // shuffle-built 19-wide window sums, rings and hand-off in Tensor Memory, integer cost lattice so
 // the four first-stage sums are exact), with 4 + 4 filtered quantities instead of 2 + 2:
-//   producer: cost, sums of p, R p, G p, B p            (ring: cost, TMEM)
-//   consumer: 3x3 solve, sums of a_r, a_g, a_b, b, q    (ring: a_r,a_g in TMEM; a_b,b in shared memory)
+//   producer: cost, sums of p, R p, G p, B p, 3x3 solve -> (a, b)   (ring: cost, TMEM)
+//   consumer: sums of a_r, a_g, a_b, b, q, merge                   (ring: a_r,a_g in TMEM; a_b,b in shared memory)
 // One row per pipeline iteration (the colour path needs about twice the registers per row).
 #include "fused_dev.cuh"
 
@@ -41,7 +41,7 @@ struct RgbSmem {
     uint32_t tmem_base;
 };
 // TMEM columns of one lane: [0,304) ring of (a_r[8], a_g[8]) x 19, [304,380) ring of the cost x 19,
-// [384,416) hand-off (S_P, S_RP, S_GP, S_BP)
+// [384,416) hand-off (a_r, a_g, a_b, b)
 constexpr uint32_t TMR_RING_A = 0, TMR_RING_P = 304, TMR_HAND = 384;
 
 struct RProdOps {
@@ -142,6 +142,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf_rgb(const RgbArgs A) 
             wm[j] = (x >= 0 && x < A.w) ? u2h2(A.wpack) : __float2half2_rn(0.0f);
         }
         const __half2 th = u2h2(A.thpack);
+        const float4* __restrict__ S1 = A.S1[view];
+        const float4* __restrict__ S2 = A.S2[view];
+        const float* __restrict__ S3 = A.S3[view];
+        float rx[KPX];
+#pragma unroll
+        for (int j = 0; j < KPX; j++) {
+            int x = xl + j;
+            int ax = min(A.w - 1, x + RAD) - max(0, x - RAD) + 1;
+            rx[j] = (x >= 0 && x < A.w) ? __frcp_rn((float)ax) : 0.0f;
+        }
         for (int g = 0; g < ngroups; g++) {
             const int dk = g * NWARP + pair;
             const bool active = dk < dcnt;
@@ -163,15 +173,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf_rgb(const RgbArgs A) 
                 rp.cn = C2 + r0;
                 rp.co = C2 + r0 - (long long)WIN * pitch;
                 int slot = 0;
-                RProdOps cur, nxt;
+                // Operands live in ONE register set each and are re-fetched right after their last use:
+                // the image rows (used by the cost and the vertical sums) while the four window sums
+                // run, the 72 statistics words (used by the 3x3 solve at the end of the iteration) at the
+                // end for the next row.  Each group of loads is made to depend on a word of the other
+                // group, so its scoreboard wait is taken when the other group has long completed.
+                RProdOps cur;
                 load_rprod(cur, rp, 0);
+                long long rs = (long long)(y_first - RAD) * pitch + xl;  // statistics row ya = yi - 9
+                float4 s1[KPX], s2[KPX];
+                float4 s3a, s3b;
+                auto load_stats = [&](long long off) {
+                    const float4* p1 = S1 + off;
+                    const float4* p2 = S2 + off;
+#pragma unroll
+                    for (int j = 0; j < KPX; j++) {
+                        s1[j] = __ldg(p1 + j);
+                        s2[j] = __ldg(p2 + j);
+                    }
+                    const float4* p3 = reinterpret_cast<const float4*>(S3 + off);
+                    s3a = __ldg(p3);
+                    s3b = __ldg(p3 + 1);
+                };
+                load_stats(rs);
 #pragma unroll 1
-                for (int it = 0; it < niter; it++) {
-                    rp.g += pitch;
-                    rp.m += pitch;
-                    rp.cn += pitch;
-                    rp.co += pitch;
-                    load_rprod(nxt, rp, touch(cur) & A.zero);
+                for (int it = 0; it < niter; it++, rs += pitch) {
+                    const int yi = y_first + it;
                     uint32_t pold[4];
                     tm_ld4(tP + 4 * slot, pold);
                     const unsigned gg[KPX] = {cur.g0.x, cur.g0.y, cur.g0.z, cur.g0.w, cur.g1.x, cur.g1.y, cur.g1.z, cur.g1.w};
@@ -209,21 +236,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf_rgb(const RgbArgs A) 
                         VG[j] = fmaf(-go, po, VG[j]);
                         VB[j] = fmaf(-bo, po, VB[j]);
                     }
+                    {   // image rows of the next iteration, behind the wait on this row's statistics
+                        unsigned tw = __float_as_uint(s3a.x) | __float_as_uint(s3b.x);
+#pragma unroll
+                        for (int j = 0; j < KPX; j++) tw |= __float_as_uint(s1[j].x) | __float_as_uint(s2[j].x);
+                        rp.g += pitch;
+                        rp.m += pitch;
+                        rp.cn += pitch;
+                        rp.co += pitch;
+                        load_rprod(cur, rp, (int)tw & A.zero);
+                    }
                     float SP[KPX], SR[KPX], SG[KPX], SB[KPX];
                     hsum19(VP, SP);
                     hsum19(VR, SR);
                     hsum19(VG, SG);
                     hsum19(VB, SB);
+                    // ---- a = M cov, b = mp - a.mu at row ya = yi - 9
+                    const float ry1 = inv_rows_rgb(yi - RAD, A.y_global0, A.frame_h, A.S);
+                    const float s3[KPX] = {s3a.x, s3a.y, s3a.z, s3a.w, s3b.x, s3b.y, s3b.z, s3b.w};
+                    float ar[KPX], ag[KPX], ab[KPX], bb[KPX];
+#pragma unroll
+                    for (int j = 0; j < KPX; j++) {
+                        const float mr = s1[j].x, mg = s1[j].y, mb = s1[j].z;
+                        const float cx = fmaf(-mr, SP[j], SR[j]);
+                        const float cy = fmaf(-mg, SP[j], SG[j]);
+                        const float cz = fmaf(-mb, SP[j], SB[j]);
+                        ar[j] = fmaf(s1[j].w, cx, fmaf(s2[j].x, cy, s2[j].y * cz));
+                        ag[j] = fmaf(s2[j].x, cx, fmaf(s2[j].z, cy, s2[j].w * cz));
+                        ab[j] = fmaf(s2[j].y, cx, fmaf(s2[j].w, cy, s3[j] * cz));
+                        const float mp = SP[j] * (rx[j] * ry1);
+                        bb[j] = mp - fmaf(ar[j], mr, fmaf(ag[j], mg, ab[j] * mb));
+                    }
+                    load_stats(rs + pitch + (touch(cur) & A.zero));  // next row's statistics
                     if (it > 0) {
                         named_bar_sync(BAR_EMPTY, 64);
                         tm_fence_after();
                     }
-                    tm_st16(tH, SP, SR);
-                    tm_st16(tH + 16, SG, SB);
+                    tm_st16(tH, ar, ag);
+                    tm_st16(tH + 16, ab, bb);
                     tm_wait_st();
                     tm_fence_before();
                     named_bar_arrive(BAR_FULL, 64);
-                    cur = nxt;
                 }
             }
             __syncthreads();
@@ -231,9 +284,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf_rgb(const RgbArgs A) 
     } else {
         // ============================ CONSUMER: 3x3 solve and second stage ============================
         const uint2* __restrict__ C2 = A.C2[view];
-        const float4* __restrict__ S1 = A.S1[view];
-        const float4* __restrict__ S2 = A.S2[view];
-        const float* __restrict__ S3 = A.S3[view];
         float rx[KPX];
 #pragma unroll
         for (int j = 0; j < KPX; j++) {
@@ -300,74 +350,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf_rgb(const RgbArgs A) 
 
             if (active) {
                 // row pointers of THIS iteration's operands (stats at ya = yi-9, colour at yq = yi-18)
-                long long rs = (long long)(y_first - RAD) * pitch + xl;
-                long long rq = (long long)(y_first - 2 * RAD) * pitch + xl;
-                // The 72 statistics words of a row are fetched right after the LAST use of the previous
-                // row's (in the same registers), i.e. most of an iteration before their first use, without
-                // a second register set.
-                float4 s1[KPX], s2[KPX];
-                float4 s3a, s3b;
-                auto load_stats = [&](long long off) {
-                    const float4* p1 = S1 + off;
-                    const float4* p2 = S2 + off;
-#pragma unroll
-                    for (int j = 0; j < KPX; j++) {
-                        s1[j] = __ldg(p1 + j);
-                        s2[j] = __ldg(p2 + j);
-                    }
-                    const float4* p3 = reinterpret_cast<const float4*>(S3 + off);
-                    s3a = __ldg(p3);
-                    s3b = __ldg(p3 + 1);
-                };
-                load_stats(rs);
+                long long rq = (long long)(y_first - 2 * RAD) * pitch + xl;  // colour row yq = yi - 18
 #pragma unroll 1
-                for (int it = 0; it < niter; it++, rs += pitch, rq += pitch) {
+                for (int it = 0; it < niter; it++, rq += pitch) {
                     const bool emit = it >= 4 * RAD;
                     const int yi = y_first + it;
                     const int yq = yi - 2 * RAD;
-                    // take the scoreboard wait on the statistics before new loads are issued (see fused_cvf.cu)
-                    unsigned tw = __float_as_uint(s3a.x) | __float_as_uint(s3b.x);
-#pragma unroll
-                    for (int j = 0; j < KPX; j++) tw |= __float_as_uint(s1[j].x) | __float_as_uint(s2[j].x);
-                    const int dep = (int)tw & A.zero;
-                    uint4 cq[4];
+                    uint4 cq[4];  // used at the end of the iteration
                     {
-                        const uint4* pc = reinterpret_cast<const uint4*>(C2 + rq + dep);
+                        const uint4* pc = reinterpret_cast<const uint4*>(C2 + rq);
 #pragma unroll
                         for (int k = 0; k < 4; k++) cq[k] = __ldg(pc + k);
                     }
-                    const float s3[KPX] = {s3a.x, s3a.y, s3a.z, s3a.w, s3b.x, s3b.y, s3b.z, s3b.w};
                     float pb0, pb1, pl0, pl1;
                     if (emit) prefetch_best(yq, pb0, pb1, pl0, pl1);
-                    const float ry1 = inv_rows_rgb(yi - RAD, A.y_global0, A.frame_h, A.S);
                     float aro[KPX], ago[KPX];
                     tm_ld16(tA + 16 * slot, aro, ago);
                     const float4 ob0 = sm.ringB[pair][slot][0][lane], ob1 = sm.ringB[pair][slot][1][lane];
                     const float4 ob2 = sm.ringB[pair][slot][2][lane], ob3 = sm.ringB[pair][slot][3][lane];
                     named_bar_sync(BAR_FULL, 64);
                     tm_fence_after();
-                    float SP[KPX], SR[KPX], SG[KPX], SB[KPX];
-                    tm_ld16(tH, SP, SR);
-                    tm_ld16(tH + 16, SG, SB);
+                    float ar[KPX], ag[KPX], ab[KPX], bb[KPX];  // (a, b) of row ya = yi - 9, solved by the producer
+                    tm_ld16(tH, ar, ag);
+                    tm_ld16(tH + 16, ab, bb);
                     tm_wait_ld();
                     if (it + 1 < niter) {
                         tm_fence_before();
                         named_bar_arrive(BAR_EMPTY, 64);
                     }
-                    float ar[KPX], ag[KPX], ab[KPX], bb[KPX];
-#pragma unroll
-                    for (int j = 0; j < KPX; j++) {
-                        const float mr = s1[j].x, mg = s1[j].y, mb = s1[j].z;
-                        const float cx = fmaf(-mr, SP[j], SR[j]);
-                        const float cy = fmaf(-mg, SP[j], SG[j]);
-                        const float cz = fmaf(-mb, SP[j], SB[j]);
-                        ar[j] = fmaf(s1[j].w, cx, fmaf(s2[j].x, cy, s2[j].y * cz));
-                        ag[j] = fmaf(s2[j].x, cx, fmaf(s2[j].z, cy, s2[j].w * cz));
-                        ab[j] = fmaf(s2[j].y, cx, fmaf(s2[j].w, cy, s3[j] * cz));
-                        const float mp = SP[j] * (rx[j] * ry1);
-                        bb[j] = mp - fmaf(ar[j], mr, fmaf(ag[j], mg, ab[j] * mb));
-                    }
-                    load_stats(rs + pitch);  // next row's statistics (padding rows past the end are zero)
                     tm_st16(tA + 16 * slot, ar, ag);
                     sm.ringB[pair][slot][0][lane] = make_float4(ab[0], ab[1], ab[2], ab[3]);
                     sm.ringB[pair][slot][1][lane] = make_float4(ab[4], ab[5], ab[6], ab[7]);
