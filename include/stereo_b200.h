@@ -159,7 +159,10 @@ typedef struct sb200_strip {
 
 /* Device pointers, asynchronous.  left/right: channels==1 (gray) or >=3 (interleaved RGB).
  * cost + guided-filter box sums + running argmin are one fused kernel per pair (both views);
- * L/R check + fill are a second kernel.  The D-deep volume is never materialised. */
+ * L/R check + fill are a second kernel.  The D-deep volume is never materialised.
+ * guide_mode RGB uses the colour guided filter (fused; box_mode SAT selects the staged colour path).
+ * Parameter sets the fused kernels are not built for (radius != 9, alpha/thresholds without an exact
+ * integer cost lattice) run through the stage kernels on the GPU instead (whole frames only). */
 int sb200_pipeline_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, const uint8_t* d_right,
                        int channels, int w, int h, const sb200_outputs* d_out);
 /* same with HOST pointers, blocking (pageable or pinned; copies happen inside) */

@@ -188,13 +188,23 @@ int guide_stats(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_i, float
     return SB200_OK;
 }
 
-size_t gf_ws_bytes(size_t n) { return 12 * sb_align(n * 4) + box_scratch_bytes(n) + 4096; }
+size_t gf_ws_bytes(size_t n) { return 15 * sb_align(n * 4) + box_scratch_bytes(n) + 4096; }
 
-// the body of sb200_compute_guided_filter_dev on an already reserved arena
+// the body of sb200_compute_guided_filter_dev on an already reserved arena.  d_cost == NULL: the slices
+// are generated one at a time from (d_i, d_other) instead of being read from a materialised volume.
 int guided_filter_staged(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_i, const float* d_cost, float* d_best,
-                         float* d_dmap, uint8_t* d_mean, int w, int h, int size_d, int dmin) {
+                         float* d_dmap, uint8_t* d_mean, int w, int h, int size_d, int dmin,
+                         const uint8_t* d_other = nullptr) {
     const size_t n = (size_t)w * h;
     float *I, *mean_I, *var_I, *t0, *t1, *mp, *mIp, *a, *b, *ma, *mb, *q;
+    float *pkbuf = nullptr, *g1 = nullptr, *g2 = nullptr;
+    if (!d_cost) {
+        SB_TRY(ws_get(ctx, &pkbuf, n));
+        SB_TRY(ws_get(ctx, &g1, n));
+        SB_TRY(ws_get(ctx, &g2, n));
+        SB_TRY(sbk_x_derivative(ctx, d_i, g1, w, h));
+        SB_TRY(sbk_x_derivative(ctx, d_other, g2, w, h));
+    }
     SB_TRY(ws_get(ctx, &I, n));
     SB_TRY(ws_get(ctx, &mean_I, n));
     SB_TRY(ws_get(ctx, &var_I, n));
@@ -211,7 +221,8 @@ int guided_filter_staged(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d
     SB_TRY(box_scratch_get(ctx, &bs, n));
     SB_TRY(guide_stats(ctx, p, d_i, I, mean_I, var_I, t0, t1, d_mean, w, h, bs));
     for (int s = 0; s < size_d; s++) {  // guidedFilter.cu:171-238
-        const float* pk = d_cost + (size_t)s * n;
+        const float* pk = d_cost ? d_cost + (size_t)s * n : pkbuf;
+        if (!d_cost) SB_TRY(sbk_cost_volume(ctx, p, d_i, d_other, g1, g2, pkbuf, w, h, 1, dmin + s));
         SB_TRY(box_mean(ctx, p, pk, mp, w, h, bs));
         SB_TRY(sbk_mul(ctx, I, pk, t0, n));
         SB_TRY(box_mean(ctx, p, t0, mIp, w, h, bs));
@@ -295,7 +306,7 @@ int pipeline_core(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, 
     const size_t n_out = (size_t)w * g.rows_out;
     const int dabs = max(abs(p->dmin), abs(p->dmax));
     if (reserve) {
-        size_t bytes = p->guide_mode != SB200_GUIDE_RGB ? sbf_workspace_bytes(ctx, w, g.h, g.rows_out, dabs, size_d, 2)
+        size_t bytes = p->guide_mode != SB200_GUIDE_RGB ? (sbf_fused_supported(p) ? sbf_workspace_bytes(ctx, w, g.h, g.rows_out, dabs, size_d, 2) : gf_ws_bytes(n_held) + 2 * sb_align(n_held))
                        : (p->box_mode == SB200_BOX_SAT ? rgb_ws_bytes(n_held) : sbf_rgb_workspace_bytes(ctx, w, g.h, g.rows_out, dabs, size_d));
         bytes += 2 * sb_align(n_held) + 4 * sb_align(n_out * 4) + 4096;
         SB_TRY(sb_ws_reserve(ctx, bytes));
@@ -304,6 +315,12 @@ int pipeline_core(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, 
     const bool rgb_guide = (p->guide_mode == SB200_GUIDE_RGB);
     // RGB guide: fused kernel (fused_cvf_rgb.cu); box_mode SAT selects the staged, materialising path instead
     const bool rgb_staged = rgb_guide && p->box_mode == SB200_BOX_SAT;
+    // parameter sets the fused kernels are not built for (radius != 9, no exact cost lattice) run through the
+    // stage kernels with double-accumulated sliding boxes: slower, still on the GPU, same results contract
+    const bool gray_staged = !rgb_guide && !sbf_fused_supported(p);
+    if (gray_staged && !full) return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "these parameters need the staged path, which takes whole frames only");
+    if (rgb_guide && !rgb_staged && !sbf_fused_supported(p))
+        return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "RGB guide: the fused kernel needs radius 9 and a lattice cost; use box_mode SAT for the staged path");
     if (rgb_guide && channels < 3) return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "RGB guide needs a colour input");
     if (rgb_staged && !full) return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "staged RGB guide needs a whole frame");
     if (rgb_guide && (o->mean_left || o->mean_right))
@@ -345,6 +362,20 @@ int pipeline_core(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, 
         SB_TRY(view_rgb_staged(ctx, p, d_left, channels, gl, gr, bL, dL, w, g.h, size_d, p->dmin));
         ctx->ws_off = mark;  // the second view reuses the first view's scratch (same stream)
         SB_TRY(view_rgb_staged(ctx, p, d_right, channels, gr, gl, bR, dR, w, g.h, size_d, -p->dmax));
+    } else if (gray_staged) {
+        sb200_params ps = *p;
+        ps.box_mode = SB200_BOX_SLIDING;
+        float *bL = o->best_left, *bR = o->best_right;
+        if (!bL) SB_TRY(ws_get(ctx, &bL, n_out));
+        if (!bR) SB_TRY(ws_get(ctx, &bR, n_out));
+        SB_TRY(sbk_fill_f32(ctx, bL, 3.3961514e38f, n_out));  // 0x7F7F7F7F, main.cu:112
+        SB_TRY(sbk_fill_f32(ctx, bR, 3.3961514e38f, n_out));
+        SB_TRY(sbk_fill_f32(ctx, dL, 0.0f, n_out));
+        SB_TRY(sbk_fill_f32(ctx, dR, 0.0f, n_out));
+        const size_t mark = ctx->ws_off;
+        SB_TRY(guided_filter_staged(ctx, &ps, gl, nullptr, bL, dL, mL, w, g.h, size_d, p->dmin, gr));
+        ctx->ws_off = mark;
+        SB_TRY(guided_filter_staged(ctx, &ps, gr, nullptr, bR, dR, mR, w, g.h, size_d, -p->dmax, gl));
     } else
     SB_TRY(sbf_pair_disparity(ctx, p, gl, gr, g, o->best_left, dL, o->best_right, dR, full ? mL : mLh, full ? mR : mRh));
     if (!full) {
@@ -510,7 +541,7 @@ int sb200_pipeline(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h_left,
     const size_t n = (size_t)w * h;
     const int size_d = p->dmax - p->dmin + 1;
     const int dabs = max(abs(p->dmin), abs(p->dmax));
-    size_t bytes = (p->guide_mode != SB200_GUIDE_RGB ? sbf_workspace_bytes(ctx, w, h, h, dabs, size_d, 2)
+    size_t bytes = (p->guide_mode != SB200_GUIDE_RGB ? (sbf_fused_supported(p) ? sbf_workspace_bytes(ctx, w, h, h, dabs, size_d, 2) : gf_ws_bytes(n) + 2 * sb_align(n))
                     : (p->box_mode == SB200_BOX_SAT ? rgb_ws_bytes(n) : sbf_rgb_workspace_bytes(ctx, w, h, h, dabs, size_d))) +
                    2 * sb_align(n) + 4 * sb_align(n * 4) + 4096;
     bytes += 2 * sb_align(n * channels) + 6 * sb_align(n * 4) + 4 * sb_align(n) + 4096;

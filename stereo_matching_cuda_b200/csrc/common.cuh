@@ -120,6 +120,8 @@ struct SbFusedGeom {
     int y_global0;    // frame row index of held row 0 (for clipped window areas)
     int frame_h;      // rows of the whole frame
 };
+// 1 if the fused kernels cover these parameters (radius 9, exact integer cost lattice)
+int sbf_fused_supported(const sb200_params* p);
 size_t sbf_workspace_bytes(const sb200_ctx* ctx, int w, int h_held, int rows_out, int dabs, int size_d, int n_views);
 // gray images (held rows) -> per-view best cost + labels (+ mean debug image) for BOTH views
 int sbf_pair_disparity(sb200_ctx* ctx, const sb200_params* p, const uint8_t* gray_l, const uint8_t* gray_r,

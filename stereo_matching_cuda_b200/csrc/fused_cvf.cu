@@ -610,6 +610,11 @@ __global__ void __launch_bounds__(256) k_prep(const PrepArgs P) {
 
 }  // namespace
 
+int sbf_fused_supported(const sb200_params* p) {
+    int nI, nG, S;
+    return p->radius == RAD && find_lattice(p, &nI, &nG, &S);
+}
+
 size_t sbf_workspace_bytes(const sb200_ctx* ctx, int w, int h_held, int rows_out, int dabs, int size_d, int n_views) {
     const int padx = pad_x(dabs);
     const int pitch = (w + 2 * padx + 7) / 8 * 8;

@@ -285,13 +285,51 @@ def test_strip_mode_matches_whole_frame(ctx, oracle):
 
 
 def test_unsupported_requests_fail_loudly(ctx):
+    torch = pytest.importorskip("torch")
     img = np.zeros((40, 40), np.uint8)
-    with pytest.raises(S.StereoB200Error, match="radius"):
-        ctx.pipeline(img, img, api.default_params(radius=4))
-    with pytest.raises(S.StereoB200Error, match="lattice"):
-        ctx.pipeline(img, img, api.default_params(alpha=0.8731))
     with pytest.raises(S.StereoB200Error):
         ctx.pipeline(img, img, api.default_params(dmin=3, dmax=1))
+    # the fused-kernel-only entry point refuses what the fused kernel is not built for
+    d = torch.zeros((40, 40), dtype=torch.uint8, device="cuda")
+    out = torch.empty((40, 40), dtype=torch.float32, device="cuda")
+    with pytest.raises(S.StereoB200Error, match="radius"):
+        ctx.view_disparity_dev(d, d, 40, 40, -3, 4, out, out, params=api.default_params(radius=4))
+    with pytest.raises(S.StereoB200Error, match="lattice"):
+        ctx.view_disparity_dev(d, d, 40, 40, -3, 4, out, out, params=api.default_params(alpha=0.8731))
+
+
+@pytest.mark.parametrize("kw", [dict(radius=4), dict(radius=12), dict(alpha=0.8731), dict(th_color=5.5), dict(eps=25.0)])
+def test_pipeline_other_parameters_run_staged_or_fused(ctx, oracle, kw):
+    """Parameters the fused kernel is not built for (another radius, a cost without an exact integer lattice)
+    still run through sb200_pipeline -- on the GPU, through the stage kernels -- and match the oracle."""
+    w, h, size_d = 150, 80, 9
+    L, R = synth.make_pair(w, h, size_d, seed=77)
+    p = api.default_params(dmin=-(size_d - 1), dmax=0, **kw)
+    out = ctx.pipeline(L, R, p)
+    okw = dict(kw)
+    ref = oracle.pipeline_gray(L, R, -(size_d - 1), size_d,
+                               oracle.params(box_mode=O.BOX_EXACT, nthreads=oracle.max_threads(), **okw), want_second=True)
+    check_fused_vs_oracle(out, ref, margin_tau=2e-4, min_agree=0.999)
+    occ = oracle.detect_occlusion(out["disp_left"], out["disp_right"], -(size_d - 1) - 100)
+    assert np.array_equal(out["filled"], oracle.fill_occlusion(occ, -(size_d - 1)))
+
+
+def test_compat_header_program_runs(ctx):
+    """include/stereo_b200_compat.hpp: main.cu's call sequence with the reference's C++ signatures, linked
+    against libstereo_b200.so, compiled and run on this box."""
+    import shutil
+    import subprocess
+
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    cxx = shutil.which("g++") or "/usr/bin/g++"
+    exe = os.path.join(root, "gpurun_out", "compat_smoke")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    libdir = os.path.join(root, "stereo_matching_cuda_b200")
+    subprocess.run([cxx, "-std=c++17", "-O1", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "compat_smoke.cpp"),
+                    "-o", exe, "-L", libdir, "-lstereo_b200", "-Wl,-rpath," + libdir], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "labelled -4" in r.stdout
 
 
 @pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref/libref.so not built")
