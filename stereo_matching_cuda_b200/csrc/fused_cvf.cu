@@ -40,7 +40,8 @@ namespace {
 
 struct FusedArgs {
     const unsigned* IG[2];  // per IMAGE (0 left, 1 right): padded half2 (I, G=I[x-1]-I[x+1]); -> element (0,0)
-    const float* If[2];     // per IMAGE: padded float intensity, zero padding
+    const __half* Ih[2];    // per IMAGE: padded half intensity (exact: 0..255), stored shifted by 4 elements so that a
+                            // lane's 8 pixels are one aligned 16 B load; zero padding
     const float2* st[2];    // per VIEW (guide = image v): padded (mean_I, c/(S*area)), zero padding
     int pitch;              // elements per padded row
     int w;
@@ -69,20 +70,20 @@ struct SmemLayout {
 struct ProdOps {
     uint4 g0, g1;     // guide (I,G) half2 x8 at row yi
     unsigned m[KPX];  // match (I,G) half2 x8 at row yi, columns x+d
-    float4 io0, io1;  // guide intensity at row yi-19 (leaves the first-stage window)
+    uint4 io;         // guide intensity at row yi-19 (leaves the first-stage window), 8 halfs
 };
 struct ConsOps {
     float4 s0, s1, s2, s3;  // (mean_I, c2) x8 at row ya = yi-9
-    float4 iq0, iq1;        // guide intensity at row yq = yi-18
+    uint4 iq;               // guide intensity at row yq = yi-18, 8 halfs
 };
 struct ProdPtrs {
     const unsigned* g;
     const unsigned* m;
-    const float* io;
+    const __half* io;  // half plane, shifted by 4 elements so that a lane's 8 pixels are 16 B aligned
 };
 struct ConsPtrs {
     const float2* st;
-    const float* iq;
+    const __half* iq;
 };
 
 __device__ __forceinline__ void load_prod(ProdOps& o, const ProdPtrs& p, int dep) {
@@ -92,9 +93,7 @@ __device__ __forceinline__ void load_prod(ProdOps& o, const ProdPtrs& p, int dep
     const unsigned* pm = p.m + dep;
 #pragma unroll
     for (int j = 0; j < KPX; j++) o.m[j] = __ldg(pm + j);
-    const float4* po = reinterpret_cast<const float4*>(p.io + dep);
-    o.io0 = __ldg(po);
-    o.io1 = __ldg(po + 1);
+    o.io = __ldg(reinterpret_cast<const uint4*>(p.io + dep));
 }
 __device__ __forceinline__ void load_cons(ConsOps& o, const ConsPtrs& p, int dep) {
     const float4* ps = reinterpret_cast<const float4*>(p.st + dep);
@@ -102,9 +101,7 @@ __device__ __forceinline__ void load_cons(ConsOps& o, const ConsPtrs& p, int dep
     o.s1 = __ldg(ps + 1);
     o.s2 = __ldg(ps + 2);
     o.s3 = __ldg(ps + 3);
-    const float4* pq = reinterpret_cast<const float4*>(p.iq + dep);
-    o.iq0 = __ldg(pq);
-    o.iq1 = __ldg(pq + 1);
+    o.iq = __ldg(reinterpret_cast<const uint4*>(p.iq + dep));
 }
 
 // One word of every load of `o`, OR-ed together.  The next step's loads are made to depend on
@@ -116,12 +113,12 @@ __device__ __forceinline__ int touch(const ProdOps& o) {
     unsigned t = o.g0.x | o.g1.x;
 #pragma unroll
     for (int j = 0; j < KPX; j++) t |= o.m[j];
-    t |= __float_as_uint(o.io0.x) | __float_as_uint(o.io1.x);
+    t |= o.io.x;
     return (int)t;
 }
 __device__ __forceinline__ int touch(const ConsOps& o) {
     unsigned t = __float_as_uint(o.s0.x) | __float_as_uint(o.s1.x) | __float_as_uint(o.s2.x) | __float_as_uint(o.s3.x);
-    t |= __float_as_uint(o.iq0.x) | __float_as_uint(o.iq1.x);
+    t |= o.iq.x;
     return (int)t;
 }
 
@@ -174,7 +171,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
         // =============================== PRODUCER: first stage ===============================
         const unsigned* __restrict__ IGg = A.IG[view];
         const unsigned* __restrict__ IGm = A.IG[1 - view];
-        const float* __restrict__ If = A.If[view];
+        const __half* __restrict__ If = A.Ih[view];
         __half2 wm[KPX];  // lattice weights (nI, nG), 0 outside the image (masks the cost)
 #pragma unroll
         for (int j = 0; j < KPX; j++) {
@@ -259,8 +256,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
                         tm_st4(tP + 4 * slots[r], pnew[r]);
                         const unsigned gg[KPX] = {o[r].g0.x, o[r].g0.y, o[r].g0.z, o[r].g0.w,
                                                   o[r].g1.x, o[r].g1.y, o[r].g1.z, o[r].g1.w};
-                        const float iold[KPX] = {o[r].io0.x, o[r].io0.y, o[r].io0.z, o[r].io0.w,
-                                                 o[r].io1.x, o[r].io1.y, o[r].io1.z, o[r].io1.w};
+                        const float2 io01 = __half22float2(u2h2(o[r].io.x)), io23 = __half22float2(u2h2(o[r].io.y));
+                        const float2 io45 = __half22float2(u2h2(o[r].io.z)), io67 = __half22float2(u2h2(o[r].io.w));
+                        const float iold[KPX] = {io01.x, io01.y, io23.x, io23.y, io45.x, io45.y, io67.x, io67.y};
 #pragma unroll
                         for (int j = 0; j < KPX; j += 2) {
                             float2 f = __half22float2(u2h2(pold[r][j >> 1]));
@@ -297,7 +295,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
         }
     } else {
         // ================================ CONSUMER: second stage ================================
-        const float* __restrict__ If = A.If[view];
+        const __half* __restrict__ If = A.Ih[view];
         const float2* __restrict__ st = A.st[view];
         float rx[KPX];  // 1 / clipped window width, 0 outside the image
 #pragma unroll
@@ -460,8 +458,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
 #pragma unroll
                     for (int r = 0; r < ROWS; r++) {
                         const float ry2 = inv_rows(yq0 + r, A.y_global0, A.frame_h, 1.0f);
-                        const float iq[KPX] = {o[r].iq0.x, o[r].iq0.y, o[r].iq0.z, o[r].iq0.w,
-                                               o[r].iq1.x, o[r].iq1.y, o[r].iq1.z, o[r].iq1.w};
+                        const float2 iq01 = __half22float2(u2h2(o[r].iq.x)), iq23 = __half22float2(u2h2(o[r].iq.y));
+                        const float2 iq45 = __half22float2(u2h2(o[r].iq.z)), iq67 = __half22float2(u2h2(o[r].iq.w));
+                        const float iq[KPX] = {iq01.x, iq01.y, iq23.x, iq23.y, iq45.x, iq45.y, iq67.x, iq67.y};
                         float q[KPX];
 #pragma unroll
                         for (int j = 0; j < KPX; j++) q[j] = fmaf(SA[r][j], iq[j], SB[r][j]) * (rx[j] * ry2);
@@ -517,7 +516,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
 // of compute_guided_filter, guidedFilter.cu:58-123): for one image writes the padded planes
 //   IG  half2 (I, G)   G = I[x-1]-I[x+1] = 2*gradient (costVolume.cu:364-378 border rule);
 //                      padding = (1024,1024) so an out-of-range match saturates both terms
-//   If  float I        zero padding
+//   If  I as HALF (exact for 0..255), element x stored at index x+4 of the plane; zero padding
 //   st  float2 (mean_I, c/(S*area))  zero padding; mean/variance from EXACT integer window
 //       sums (<= 2^25, int32), c = (float)(1/((double)var+eps)) as guidedFilter.cu:350
 // One block computes a 32x32 tile; the 50x50 input patch is staged in shared memory.
@@ -576,7 +575,7 @@ __global__ void __launch_bounds__(256) k_prep(const PrepArgs P) {
         if (!in) {
             __half2 pad = __floats2half2_rn(1024.0f, 1024.0f);
             P.IG[o] = *reinterpret_cast<unsigned*>(&pad);
-            P.If[o] = 0.0f;
+            reinterpret_cast<__half*>(P.If)[o + 4] = __float2half(0.0f);
             P.st[o] = make_float2(0.0f, 0.0f);
             continue;
         }
@@ -599,7 +598,7 @@ __global__ void __launch_bounds__(256) k_prep(const PrepArgs P) {
         int ir = (x + 1 < P.w) ? sI[ty + RAD][tx + RAD + 1] : ic;
         __half2 ig = __floats2half2_rn((float)ic, (float)(il - ir));
         P.IG[o] = *reinterpret_cast<unsigned*>(&ig);
-        P.If[o] = (float)ic;
+        reinterpret_cast<__half*>(P.If)[o + 4] = __float2half((float)ic);
         P.st[o] = make_float2(mI, __fmul_rn(c, rxy));
         if (P.mean_u8) {
             int m = (int)mI;
@@ -701,7 +700,7 @@ static int run_fused(sb200_ctx* ctx, const sb200_params* p, const uint8_t* const
     const size_t origin = (size_t)PADY * pitch + padx;
     for (int i = 0; i < 2; i++) {
         A.IG[i] = IG[i] + origin;
-        A.If[i] = If[i] + origin;
+        A.Ih[i] = reinterpret_cast<const __half*>(If[i]) + origin + 4;
         A.st[i] = st[i] + origin;
         A.dmin[i] = dmin[i];
     }
