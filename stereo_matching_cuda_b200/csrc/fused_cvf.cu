@@ -40,6 +40,8 @@ namespace {
 
 struct FusedArgs {
     const unsigned* IG[2];  // per IMAGE (0 left, 1 right): padded half2 (I, G=I[x-1]-I[x+1]); -> element (0,0)
+    size_t shift_stride;    // IG[i] + s*shift_stride (s = 0..3) is the same plane moved left by s elements, so the
+                            // match operands at x+d are two aligned 16 B loads from copy (d & 3)
     const __half* Ih[2];    // per IMAGE: padded half intensity (exact: 0..255), stored shifted by 4 elements so that a
                             // lane's 8 pixels are one aligned 16 B load; zero padding
     const float2* st[2];    // per VIEW (guide = image v): padded (mean_I, c/(S*area)), zero padding
@@ -69,7 +71,7 @@ struct SmemLayout {
 // pair each fetch only what their stage needs
 struct ProdOps {
     uint4 g0, g1;     // guide (I,G) half2 x8 at row yi
-    unsigned m[KPX];  // match (I,G) half2 x8 at row yi, columns x+d
+    uint4 m0, m1;     // match (I,G) half2 x8 at row yi, columns x+d (from the copy shifted by d & 3)
     uint4 io;         // guide intensity at row yi-19 (leaves the first-stage window), 8 halfs
 };
 struct ConsOps {
@@ -90,9 +92,9 @@ __device__ __forceinline__ void load_prod(ProdOps& o, const ProdPtrs& p, int dep
     const uint4* pg = reinterpret_cast<const uint4*>(p.g + dep);
     o.g0 = __ldg(pg);
     o.g1 = __ldg(pg + 1);
-    const unsigned* pm = p.m + dep;
-#pragma unroll
-    for (int j = 0; j < KPX; j++) o.m[j] = __ldg(pm + j);
+    const uint4* pm = reinterpret_cast<const uint4*>(p.m + dep);
+    o.m0 = __ldg(pm);
+    o.m1 = __ldg(pm + 1);
     o.io = __ldg(reinterpret_cast<const uint4*>(p.io + dep));
 }
 __device__ __forceinline__ void load_cons(ConsOps& o, const ConsPtrs& p, int dep) {
@@ -110,9 +112,7 @@ __device__ __forceinline__ void load_cons(ConsOps& o, const ConsPtrs& p, int dep
 // first use of an operand waits on a scoreboard slot that the just-issued prefetch loads
 // share, i.e. on a full L2 round trip every step (ncu: 50 % of all stall samples, round 1).
 __device__ __forceinline__ int touch(const ProdOps& o) {
-    unsigned t = o.g0.x | o.g1.x;
-#pragma unroll
-    for (int j = 0; j < KPX; j++) t |= o.m[j];
+    unsigned t = o.g0.x | o.g1.x | o.m0.x | o.m1.x;
     t |= o.io.x;
     return (int)t;
 }
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
                 ProdPtrs rp;
                 const long long r0 = (long long)y_first * pitch + xl;
                 rp.g = IGg + r0;
-                rp.m = IGm + r0 + d;
+                rp.m = IGm + (size_t)(d & 3) * A.shift_stride + r0 + (d - (d & 3));
                 rp.io = If + r0 - (long long)WIN * pitch;
                 int slot = 0;
                 ProdOps opsA[ROWS], opsB[ROWS];
@@ -235,11 +235,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
                     for (int r = 0; r < ROWS; r++) {
                         const unsigned gg[KPX] = {o[r].g0.x, o[r].g0.y, o[r].g0.z, o[r].g0.w,
                                                   o[r].g1.x, o[r].g1.y, o[r].g1.z, o[r].g1.w};
+                        const unsigned mm[KPX] = {o[r].m0.x, o[r].m0.y, o[r].m0.z, o[r].m0.w,
+                                                  o[r].m1.x, o[r].m1.y, o[r].m1.z, o[r].m1.w};
                         __half ph[KPX];
 #pragma unroll
                         for (int j = 0; j < KPX; j++) {
                             __half2 gv = u2h2(gg[j]);
-                            __half2 diff = __hsub2(gv, u2h2(o[r].m[j]));
+                            __half2 diff = __hsub2(gv, u2h2(mm[j]));
                             __half2 c = __hmin2(__habs2(diff), th);  // (min(|dI|,Tc), min(|dG|,2Tg))
                             __half2 pr = __hmul2(c, wm[j]);
                             ph[j] = __hadd(__low2half(pr), __high2half(pr));
@@ -527,6 +529,7 @@ struct PrepArgs {
     const uint8_t* gray;  // held rows, pitch w
     int w, h_held, y_global0, frame_h;
     unsigned* IG;
+    size_t shift_stride;  // != 0: also write the copies moved left by 1..3 elements at IG + s*shift_stride
     float* If;
     float2* st;
     uint8_t* mean_u8;  // optional, held rows pitch w
@@ -534,6 +537,15 @@ struct PrepArgs {
     double eps;
     float S;
 };
+
+__device__ __forceinline__ void store_ig(const PrepArgs& P, size_t o, unsigned v) {
+    P.IG[o] = v;
+    if (P.shift_stride) {
+#pragma unroll
+        for (int s = 1; s < 4; s++)
+            if (o >= (size_t)s) P.IG[s * P.shift_stride + o - s] = v;
+    }
+}
 
 __global__ void __launch_bounds__(256) k_prep(const PrepArgs P) {
     __shared__ int sI[PP][PP + 1];
@@ -574,7 +586,7 @@ __global__ void __launch_bounds__(256) k_prep(const PrepArgs P) {
         bool in = (x >= 0 && x < P.w && y >= 0 && y < P.h_held && yg >= 0 && yg < P.frame_h);
         if (!in) {
             __half2 pad = __floats2half2_rn(1024.0f, 1024.0f);
-            P.IG[o] = *reinterpret_cast<unsigned*>(&pad);
+            store_ig(P, o, *reinterpret_cast<unsigned*>(&pad));
             reinterpret_cast<__half*>(P.If)[o + 4] = __float2half(0.0f);
             P.st[o] = make_float2(0.0f, 0.0f);
             continue;
@@ -597,7 +609,7 @@ __global__ void __launch_bounds__(256) k_prep(const PrepArgs P) {
         int il = (x - 1 >= 0) ? sI[ty + RAD][tx + RAD - 1] : ic;
         int ir = (x + 1 < P.w) ? sI[ty + RAD][tx + RAD + 1] : ic;
         __half2 ig = __floats2half2_rn((float)ic, (float)(il - ir));
-        P.IG[o] = *reinterpret_cast<unsigned*>(&ig);
+        store_ig(P, o, *reinterpret_cast<unsigned*>(&ig));
         reinterpret_cast<__half*>(P.If)[o + 4] = __float2half((float)ic);
         P.st[o] = make_float2(mI, __fmul_rn(c, rxy));
         if (P.mean_u8) {
@@ -621,7 +633,7 @@ size_t sbf_workspace_bytes(const sb200_ctx* ctx, int w, int h_held, int rows_out
     const int pitchS = (w + 3) / 4 * 4;
     Plan plan = make_plan(w, rows_out, size_d, ctx->sm_count, n_views);
     size_t bytes = 0;
-    bytes += 2 * sb_align(plane * 4);      // IG x2
+    bytes += 2 * sb_align(plane * 4 * 4);  // IG x2, 4 shifted copies each
     bytes += 2 * sb_align(plane * 4);      // If x2
     bytes += 2 * sb_align(plane * 8);      // st x2
     bytes += 2 * sb_align((size_t)plan.n_chunks * 2 * rows_out * pitchS * 4);  // bestS, labS
@@ -629,7 +641,7 @@ size_t sbf_workspace_bytes(const sb200_ctx* ctx, int w, int h_held, int rows_out
 }
 
 static int launch_prep(sb200_ctx* ctx, const sb200_params* p, const uint8_t* gray, const SbFusedGeom& g, int pitch, int padx,
-                       float S, unsigned* IG, float* If, float2* st, uint8_t* mean) {
+                       float S, unsigned* IG, size_t shift_stride, float* If, float2* st, uint8_t* mean) {
     PrepArgs P;
     P.gray = gray;
     P.w = g.w;
@@ -637,6 +649,7 @@ static int launch_prep(sb200_ctx* ctx, const sb200_params* p, const uint8_t* gra
     P.y_global0 = g.y_global0;
     P.frame_h = g.frame_h;
     P.IG = IG;
+    P.shift_stride = shift_stride;
     P.If = If;
     P.st = st;
     P.mean_u8 = mean;
@@ -651,7 +664,7 @@ static int launch_prep(sb200_ctx* ctx, const sb200_params* p, const uint8_t* gra
 
 int sbf_prep_gray_planes(sb200_ctx* ctx, const sb200_params* p, const uint8_t* gray, const SbFusedGeom& g, int pitch, int padx,
                          float S, unsigned* IG, float* If, float2* st) {
-    return launch_prep(ctx, p, gray, g, pitch, padx, S, IG, If, st, nullptr);
+    return launch_prep(ctx, p, gray, g, pitch, padx, S, IG, 0, If, st, nullptr);
 }
 
 static int run_fused(sb200_ctx* ctx, const sb200_params* p, const uint8_t* const gray[2], const SbFusedGeom& g,
@@ -682,7 +695,7 @@ static int run_fused(sb200_ctx* ctx, const sb200_params* p, const uint8_t* const
     float* If[2];
     float2* st[2];
     for (int i = 0; i < 2; i++) {
-        IG[i] = sb_ws_alloc<unsigned>(ctx, plane);
+        IG[i] = sb_ws_alloc<unsigned>(ctx, 4 * plane);
         If[i] = sb_ws_alloc<float>(ctx, plane);
         st[i] = sb_ws_alloc<float2>(ctx, plane);
     }
@@ -693,7 +706,7 @@ static int run_fused(sb200_ctx* ctx, const sb200_params* p, const uint8_t* const
         return sb_fail(ctx, SB200_ERR_NOMEM, "fused: workspace arena too small (internal)");
 
     if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-    for (int i = 0; i < 2; i++) SB_TRY(launch_prep(ctx, p, gray[i], g, pitch, padx, (float)S, IG[i], If[i], st[i], mean[i]));
+    for (int i = 0; i < 2; i++) SB_TRY(launch_prep(ctx, p, gray[i], g, pitch, padx, (float)S, IG[i], plane, If[i], st[i], mean[i]));
     if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
 
     FusedArgs A;
@@ -704,6 +717,7 @@ static int run_fused(sb200_ctx* ctx, const sb200_params* p, const uint8_t* const
         A.st[i] = st[i] + origin;
         A.dmin[i] = dmin[i];
     }
+    A.shift_stride = plane;
     A.pitch = pitch;
     A.w = g.w;
     A.y_out0 = g.y_out0;
