@@ -62,8 +62,11 @@ struct FusedArgs {
     int zero;               // always 0; opaque to the compiler (see touch_ops)
 };
 
+constexpr int NQ = 4;     // depth of the ring of filtered rows between the consumer and the merging warps
+constexpr int MLAG = 2;   // a producer merges the rows its consumer emitted MLAG iterations ago
 struct SmemLayout {
-    float4 qbuf[2][NWARP][ROWS][2][32];  // filtered rows of each consumer warp, double buffered
+    float4 qbuf[NQ][NWARP][ROWS][2][32];  // filtered rows of each consumer warp
+    uint64_t qfull[NQ], qempty[NQ];       // mbarriers: 4 consumer warps -> 4 producer warps and back
     uint32_t tmem_base;
 };
 
@@ -122,6 +125,43 @@ __device__ __forceinline__ int touch(const ConsOps& o) {
     return (int)t;
 }
 
+// End-of-iteration hand-over of the prefetched operands.  The intensity words go through an
+// opaque move: left to itself the compiler converts them to float at the top of the iteration,
+// which frees their registers and lets it place this copy right behind the prefetch load --
+// a full L2 round trip on the critical path of every iteration (ncu, round 1: 12 % of samples).
+__device__ __forceinline__ unsigned late_mov(unsigned v) {
+    unsigned r;
+    asm volatile("mov.b32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+__device__ __forceinline__ uint4 late_mov(uint4 v) { return make_uint4(late_mov(v.x), late_mov(v.y), late_mov(v.z), late_mov(v.w)); }
+__device__ __forceinline__ void copy_ops(ProdOps (&a)[ROWS], const ProdOps (&b)[ROWS]) {
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+        a[r].g0 = b[r].g0;
+        a[r].g1 = b[r].g1;
+        a[r].m0 = b[r].m0;
+        a[r].m1 = b[r].m1;
+        a[r].io = late_mov(b[r].io);
+    }
+}
+__device__ __forceinline__ void copy_ops(ConsOps (&a)[ROWS], const ConsOps (&b)[ROWS]) {
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+        a[r].s0 = b[r].s0;
+        a[r].s1 = b[r].s1;
+        a[r].s2 = b[r].s2;
+        a[r].s3 = b[r].s3;
+        a[r].iq = late_mov(b[r].iq);
+    }
+}
+// a load the compiler may not sink towards its use
+__device__ __forceinline__ float ld_early(const float* p) {
+    float v;
+    asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ float inv_rows(int y, int y_global0, int frame_h, float scale) {
     // 1 / (scale * clipped window height) at held row y, 0 outside the frame
     int yg = y + y_global0;
@@ -157,10 +197,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
     // 36 warm-up rows, then one output row per input row; iterations take ROWS rows (the last
     // one may run past the band: those rows read zero padding and are not stored)
     const int niter = ((yb1 - yb0) + 4 * RAD + ROWS - 1) / ROWS;
+    constexpr int WARM_IT = 4 * RAD / ROWS;  // 36 warm-up rows fill both windows
+    static_assert((4 * RAD) % ROWS == 0, "ROWS must divide the warm-up length");
+    const int n_emit = niter - WARM_IT;      // emissions (iterations that output rows) per group
     const int BAR_FULL = 2 + pair, BAR_EMPTY = 2 + NWARP + pair;
 
     // Tensor Memory: all 512 columns of the SM, one block per SM (register-limited)
     if (warp == 0) tm_alloc(&sm.tmem_base);
+    if (threadIdx.x == 32) {
+#pragma unroll
+        for (int b = 0; b < NQ; b++) {
+            mbar_init(&sm.qfull[b], NWARP);
+            mbar_init(&sm.qempty[b], NWARP);
+        }
+    }
     tm_fence_before();
     __syncthreads();
     tm_fence_after();
@@ -179,10 +229,61 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
             wm[j] = (x >= 0 && x < A.w) ? u2h2(A.wpack) : __float2half2_rn(0.0f);
         }
         const __half2 th = u2h2(A.thpack);
+        // merge role of this thread: strip-local columns 2t, 2t+1 of all 4 disparities of a group
+        const int mc = 2 * threadIdx.x;
+        const int mx = xs + mc;
+        const bool mvalid0 = (mc >= HALO) && (mc < HALO + VALID_W) && (mx < A.w);
+        const bool mvalid1 = (mc + 1 >= HALO) && (mc + 1 < HALO + VALID_W) && (mx + 1 < A.w);
+        const int qoff = (((mc & 7) >> 2) * 32 + (mc >> 3)) * 4 + (mc & 3);
+        const size_t planeS = (size_t)A.rows_out * A.pitchS;
+        float* __restrict__ bestS = A.bestS + (size_t)(chunk * 2 + view) * planeS;
+        float* __restrict__ labS = A.labS + (size_t)(chunk * 2 + view) * planeS;
         for (int g = 0; g < ngroups; g++) {
             const int dk = g * NWARP + pair;
             const bool active = dk < dcnt;
             const int d = dlo + dk;
+            const int dbase = dlo + g * NWARP;
+            struct Best { float b0, b1, l0, l1; };
+            // running (best,label) of the rows of emission e, from the previous groups of this chunk
+            auto prefetch_best = [&](int e, Best (&pb)[ROWS]) {
+#pragma unroll
+                for (int r = 0; r < ROWS; r++) {
+                    pb[r].b0 = pb[r].b1 = BEST_INIT_BITS_F;
+                    pb[r].l0 = pb[r].l1 = 0.0f;
+                    const int yq = yb0 + e * ROWS + r;
+                    if (g > 0 && yq < yb1) {
+                        const size_t moff = (size_t)(yq - A.y_out0) * A.pitchS + mx;
+                        if (mvalid0) { pb[r].b0 = ld_early(bestS + moff); pb[r].l0 = ld_early(labS + moff); }
+                        if (mvalid1) { pb[r].b1 = ld_early(bestS + moff + 1); pb[r].l1 = ld_early(labS + moff + 1); }
+                    }
+                }
+            };
+            // fold the 4 disparities of this group into (best,label): ascending d, `>=` (last slice wins ties)
+            auto merge = [&](int e, const Best (&pb)[ROWS]) {
+                const int E = g * n_emit + e;
+                const int qb = E & (NQ - 1);
+                mbar_wait(&sm.qfull[qb], (unsigned)(E / NQ) & 1u);
+#pragma unroll
+                for (int r = 0; r < ROWS; r++) {
+                    const int yq = yb0 + e * ROWS + r;
+                    const float* qp = reinterpret_cast<const float*>(&sm.qbuf[qb][0][r][0][0]);
+                    float b0 = pb[r].b0, b1 = pb[r].b1, l0 = pb[r].l0, l1 = pb[r].l1;
+#pragma unroll
+                    for (int wv = 0; wv < NWARP; wv++) {
+                        float2 qv = *reinterpret_cast<const float2*>(qp + wv * (ROWS * 256) + qoff);
+                        float lab = (float)(dbase + wv);
+                        if (b0 >= qv.x) { b0 = qv.x; l0 = lab; }
+                        if (b1 >= qv.y) { b1 = qv.y; l1 = lab; }
+                    }
+                    if (yq < yb1) {
+                        const size_t moff = (size_t)(yq - A.y_out0) * A.pitchS + mx;
+                        if (mvalid0) { bestS[moff] = b0; labS[moff] = l0; }
+                        if (mvalid1) { bestS[moff + 1] = b1; labS[moff + 1] = l1; }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.qempty[qb]);
+            };
             float VP[KPX], VIP[KPX];
 #pragma unroll
             for (int j = 0; j < KPX; j++) VP[j] = VIP[j] = 0.0f;
@@ -208,6 +309,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
                     rp.io += pitch;
                 }
                 auto iter = [&](const ProdOps (&o)[ROWS], ProdOps (&nxt)[ROWS], int it) {
+                    const int em = it - WARM_IT - MLAG;
+                    Best pb[ROWS];
+                    if (em >= 0) prefetch_best(em, pb);
                     int dep = 0;
 #pragma unroll
                     for (int r = 0; r < ROWS; r++) dep |= touch(o[r]);
@@ -285,13 +389,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
                     tm_wait_st();
                     tm_fence_before();
                     named_bar_arrive(BAR_FULL, 64);
+                    if (em >= 0) merge(em, pb);
                 };
 #pragma unroll 1
                 for (int it = 0; it < niter; it++) {
                     iter(opsA, opsB, it);
-#pragma unroll
-                    for (int r = 0; r < ROWS; r++) opsA[r] = opsB[r];
+                    copy_ops(opsA, opsB);
                 }
+            }
+            // the emissions not merged inside the loop (all of them for a pair without a disparity)
+#pragma unroll 1
+            for (int e = active ? max(0, n_emit - MLAG) : 0; e < n_emit; e++) {
+                Best pb[ROWS];
+                prefetch_best(e, pb);
+                merge(e, pb);
             }
             __syncthreads();  // group end
         }
@@ -306,30 +417,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
             int ax = min(A.w - 1, x + RAD) - max(0, x - RAD) + 1;
             rx[j] = (x >= 0 && x < A.w) ? __frcp_rn((float)ax) : 0.0f;
         }
-        // merge role of this thread: strip-local columns 2t, 2t+1
-        const int mc = 2 * (threadIdx.x - NWARP * 32);
-        const int mx = xs + mc;
-        const bool mvalid0 = (mc >= HALO) && (mc < HALO + VALID_W) && (mx < A.w);
-        const bool mvalid1 = (mc + 1 >= HALO) && (mc + 1 < HALO + VALID_W) && (mx + 1 < A.w);
-        const int mlane = mc >> 3, mj = mc & 7;
-        const int qoff = ((mj >> 2) * 32 + mlane) * 4 + (mj & 3);
-        const size_t planeS = (size_t)A.rows_out * A.pitchS;
-        float* __restrict__ bestS = A.bestS + (size_t)(chunk * 2 + view) * planeS;
-        float* __restrict__ labS = A.labS + (size_t)(chunk * 2 + view) * planeS;
-
         for (int g = 0; g < ngroups; g++) {
             const int dk = g * NWARP + pair;
             const bool active = dk < dcnt;
-            const int dbase = dlo + g * NWARP;
             float Va[KPX], Vb[KPX];
 #pragma unroll
             for (int j = 0; j < KPX; j++) Va[j] = Vb[j] = 0.0f;
             for (int s = 0; s < WIN; s++) tm_st16(tAB + 16 * s, Va, Vb);  // zeros
             tm_wait_st();
-            if (!active) {
+            if (!active) {  // the previous group's merges have drained (group-end barrier)
                 const float inf = __int_as_float(0x7f800000);
 #pragma unroll
-                for (int b = 0; b < 2; b++)
+                for (int b = 0; b < NQ; b++)
 #pragma unroll
                     for (int r = 0; r < ROWS; r++)
 #pragma unroll
@@ -337,7 +436,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
             }
             __syncthreads();  // group start: previous group's merges are done with qbuf
 
-            int slot = 0, obuf = 0;
+            int slot = 0;
             ConsPtrs rp;
             {
                 const long long r0 = (long long)y_first * pitch + xl;
@@ -354,43 +453,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
                 }
             }
 
-            struct Best { float b0, b1, l0, l1; };
-            // fold the 4 disparities of this group into (best,label): ascending d, `>=`
-            auto merge = [&](int yq0, Best (&pb)[ROWS]) {
-#pragma unroll
-                for (int r = 0; r < ROWS; r++) {
-                    const int yq = yq0 + r;
-                    const float* qb = reinterpret_cast<const float*>(&sm.qbuf[obuf][0][r][0][0]);
-                    float b0 = pb[r].b0, b1 = pb[r].b1, l0 = pb[r].l0, l1 = pb[r].l1;
-#pragma unroll
-                    for (int wv = 0; wv < NWARP; wv++) {
-                        float2 qv = *reinterpret_cast<const float2*>(qb + wv * (ROWS * 256) + qoff);
-                        float lab = (float)(dbase + wv);
-                        if (b0 >= qv.x) { b0 = qv.x; l0 = lab; }
-                        if (b1 >= qv.y) { b1 = qv.y; l1 = lab; }
-                    }
-                    if (yq < yb1) {
-                        const size_t moff = (size_t)(yq - A.y_out0) * A.pitchS + mx;
-                        if (mvalid0) { bestS[moff] = b0; labS[moff] = l0; }
-                        if (mvalid1) { bestS[moff + 1] = b1; labS[moff + 1] = l1; }
-                    }
-                }
-                obuf ^= 1;
-            };
-            auto prefetch_best = [&](int yq0, Best (&pb)[ROWS]) {
-#pragma unroll
-                for (int r = 0; r < ROWS; r++) {
-                    pb[r].b0 = pb[r].b1 = BEST_INIT_BITS_F;
-                    pb[r].l0 = pb[r].l1 = 0.0f;
-                    const int yq = yq0 + r;
-                    if (g > 0 && yq < yb1) {
-                        const size_t moff = (size_t)(yq - A.y_out0) * A.pitchS + mx;
-                        if (mvalid0) { pb[r].b0 = bestS[moff]; pb[r].l0 = labS[moff]; }
-                        if (mvalid1) { pb[r].b1 = bestS[moff + 1]; pb[r].l1 = labS[moff + 1]; }
-                    }
-                }
-            };
-
             auto iter = [&](auto emit_tag, const ConsOps (&o)[ROWS], ConsOps (&nxt)[ROWS], int it) {
                 constexpr bool EMIT = decltype(emit_tag)::value;
                 int dep = 0;
@@ -405,8 +467,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
                 }
                 const int yi0 = y_first + it * ROWS;
                 const int yq0 = yi0 - 2 * RAD;
-                Best pb[ROWS];
-                if (EMIT) prefetch_best(yq0, pb);
                 float ry1[ROWS];
 #pragma unroll
                 for (int r = 0; r < ROWS; r++) ry1[r] = inv_rows(yi0 + r - RAD, A.y_global0, A.frame_h, A.S);
@@ -457,6 +517,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
                     }
                 }
                 if (EMIT) {
+                    const int E = g * n_emit + (it - WARM_IT);
+                    const int qb = E & (NQ - 1);
+                    if (E >= NQ) mbar_wait(&sm.qempty[qb], (unsigned)(E / NQ - 1) & 1u);  // merged NQ emissions ago
 #pragma unroll
                     for (int r = 0; r < ROWS; r++) {
                         const float ry2 = inv_rows(yq0 + r, A.y_global0, A.frame_h, 1.0f);
@@ -466,39 +529,34 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
                         float q[KPX];
 #pragma unroll
                         for (int j = 0; j < KPX; j++) q[j] = fmaf(SA[r][j], iq[j], SB[r][j]) * (rx[j] * ry2);
-                        sm.qbuf[obuf][pair][r][0][lane] = make_float4(q[0], q[1], q[2], q[3]);
-                        sm.qbuf[obuf][pair][r][1][lane] = make_float4(q[4], q[5], q[6], q[7]);
+                        sm.qbuf[qb][pair][r][0][lane] = make_float4(q[0], q[1], q[2], q[3]);
+                        sm.qbuf[qb][pair][r][1][lane] = make_float4(q[4], q[5], q[6], q[7]);
                     }
-                    named_bar_sync(1, NWARP * 32);  // the 4 consumer warps
-                    merge(yq0, pb);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.qfull[qb]);
                 }
                 tm_wait_st();  // this iteration's ring stores are complete before the next loads
             };
 
-            constexpr int WARM_IT = 4 * RAD / ROWS;  // 36 warm-up rows fill both windows
-            static_assert((4 * RAD) % ROWS == 0, "ROWS must divide the warm-up length");
             if (active) {
                 int it = 0;
 #pragma unroll 1
                 for (; it < WARM_IT; it++) {
                     iter(std::false_type{}, opsA, opsB, it);
-#pragma unroll
-                    for (int r = 0; r < ROWS; r++) opsA[r] = opsB[r];
+                    copy_ops(opsA, opsB);
                 }
 #pragma unroll 1
                 for (; it < niter; it++) {
                     iter(std::true_type{}, opsA, opsB, it);
-#pragma unroll
-                    for (int r = 0; r < ROWS; r++) opsA[r] = opsB[r];
+                    copy_ops(opsA, opsB);
                 }
             } else {
-                // no disparity for this pair in the (last, partial) group: only take part in the merge
-                for (int it = WARM_IT; it < niter; it++) {
-                    const int yq0 = yb0 + (it - WARM_IT) * ROWS;
-                    Best pb[ROWS];
-                    prefetch_best(yq0, pb);
-                    named_bar_sync(1, NWARP * 32);
-                    merge(yq0, pb);
+                // no disparity for this pair in the (last, partial) group: its slots hold +inf
+                for (int e = 0; e < n_emit; e++) {
+                    const int E = g * n_emit + e;
+                    const int qb = E & (NQ - 1);
+                    if (E >= NQ) mbar_wait(&sm.qempty[qb], (unsigned)(E / NQ - 1) & 1u);
+                    if (lane == 0) mbar_arrive(&sm.qfull[qb]);
                 }
             }
             __syncthreads();  // group end

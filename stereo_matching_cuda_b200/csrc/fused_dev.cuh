@@ -26,6 +26,29 @@ __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// mbarrier (shared-memory barrier object with phase parity) -- used where a producer/consumer
+// ring is deeper than the 16 hardware named barriers allow
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MB_DONE;\n"
+        "bra MB_WAIT;\n"
+        "MB_DONE:\n"
+        "}\n" ::"r"(smem_addr(b)),
+        "r"(parity)
+        : "memory");
+}
+
 // ---- Tensor Memory as per-thread scratch -------------------------------------------------
 // The 19-row rings and the producer->consumer hand-off live in TMEM (256 KB per SM, idle in a
 // kernel without tensor-core work) instead of shared memory: tcgen05.ld/st have their own data
