@@ -155,6 +155,17 @@ __device__ __forceinline__ void copy_ops(ConsOps (&a)[ROWS], const ConsOps (&b)[
         a[r].iq = late_mov(b[r].iq);
     }
 }
+// f16 x f16 + f32 -> f32 and f16 + f32 -> f32 in one FMA-pipe instruction (FHFMA / FHADD, PTX 8.6, sm_100+)
+__device__ __forceinline__ float fhfma(__half a, __half b, float c) {
+    float d;
+    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(__half_as_ushort(a)), "h"(__half_as_ushort(b)), "f"(c));
+    return d;
+}
+__device__ __forceinline__ float fhadd(__half a, float c) {
+    float d;
+    asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(d) : "h"(__half_as_ushort(a)), "f"(c));
+    return d;
+}
 // a load the compiler may not sink towards its use
 __device__ __forceinline__ float ld_early(const float* p) {
     float v;
@@ -333,49 +344,47 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
                         slot = (slot + 1 == WIN) ? 0 : slot + 1;
                     }
                     float SP[ROWS][KPX], SIP[ROWS][KPX];
-                    uint32_t pnew[ROWS][4];
-                    float pn[ROWS][KPX];
+                    uint32_t pneg[ROWS][4];
+                    __half ph[ROWS][KPX];
 #pragma unroll
                     for (int r = 0; r < ROWS; r++) {
                         const unsigned gg[KPX] = {o[r].g0.x, o[r].g0.y, o[r].g0.z, o[r].g0.w,
                                                   o[r].g1.x, o[r].g1.y, o[r].g1.z, o[r].g1.w};
                         const unsigned mm[KPX] = {o[r].m0.x, o[r].m0.y, o[r].m0.z, o[r].m0.w,
                                                   o[r].m1.x, o[r].m1.y, o[r].m1.z, o[r].m1.w};
-                        __half ph[KPX];
 #pragma unroll
                         for (int j = 0; j < KPX; j++) {
                             __half2 gv = u2h2(gg[j]);
                             __half2 diff = __hsub2(gv, u2h2(mm[j]));
                             __half2 c = __hmin2(__habs2(diff), th);  // (min(|dI|,Tc), min(|dG|,2Tg))
                             __half2 pr = __hmul2(c, wm[j]);
-                            ph[j] = __hadd(__low2half(pr), __high2half(pr));
-                            pn[r][j] = __half2float(ph[j]);
+                            ph[r][j] = __hadd(__low2half(pr), __high2half(pr));
                         }
-                        pnew[r][0] = h22u(__halves2half2(ph[0], ph[1]));
-                        pnew[r][1] = h22u(__halves2half2(ph[2], ph[3]));
-                        pnew[r][2] = h22u(__halves2half2(ph[4], ph[5]));
-                        pnew[r][3] = h22u(__halves2half2(ph[6], ph[7]));
                     }
                     tm_wait_ld();  // pold is in registers; the slots may be overwritten
 #pragma unroll
                     for (int r = 0; r < ROWS; r++) {
-                        tm_st4(tP + 4 * slots[r], pnew[r]);
                         const unsigned gg[KPX] = {o[r].g0.x, o[r].g0.y, o[r].g0.z, o[r].g0.w,
                                                   o[r].g1.x, o[r].g1.y, o[r].g1.z, o[r].g1.w};
-                        const float2 io01 = __half22float2(u2h2(o[r].io.x)), io23 = __half22float2(u2h2(o[r].io.y));
-                        const float2 io45 = __half22float2(u2h2(o[r].io.z)), io67 = __half22float2(u2h2(o[r].io.w));
-                        const float iold[KPX] = {io01.x, io01.y, io23.x, io23.y, io45.x, io45.y, io67.x, io67.y};
+                        const unsigned io[4] = {o[r].io.x, o[r].io.y, o[r].io.z, o[r].io.w};
+                        // the ring holds -P: the window update is then P + (-P_old) in packed half
+                        // (exact, |.| <= 2^11) and the f16 x f16 + f32 forms FHADD / FHFMA of sm_100
+                        // fold every half -> float conversion into the accumulation
 #pragma unroll
-                        for (int j = 0; j < KPX; j += 2) {
-                            float2 f = __half22float2(u2h2(pold[r][j >> 1]));
-                            float i0 = __low2float(u2h2(gg[j])), i1 = __low2float(u2h2(gg[j + 1]));
-                            VP[j] += pn[r][j] - f.x;
-                            VP[j + 1] += pn[r][j + 1] - f.y;
-                            VIP[j] = fmaf(i0, pn[r][j], VIP[j]);
-                            VIP[j + 1] = fmaf(i1, pn[r][j + 1], VIP[j + 1]);
-                            VIP[j] = fmaf(-iold[j], f.x, VIP[j]);
-                            VIP[j + 1] = fmaf(-iold[j + 1], f.y, VIP[j + 1]);
+                        for (int k = 0; k < KPX / 2; k++) {
+                            const __half2 pn2 = __halves2half2(ph[r][2 * k], ph[r][2 * k + 1]);
+                            const __half2 po2 = u2h2(pold[r][k]);
+                            pneg[r][k] = h22u(__hneg2(pn2));
+                            const __half2 dp = __hadd2(pn2, po2);
+                            const __half2 io2 = u2h2(io[k]);
+                            VP[2 * k] = fhadd(__low2half(dp), VP[2 * k]);
+                            VP[2 * k + 1] = fhadd(__high2half(dp), VP[2 * k + 1]);
+                            VIP[2 * k] = fhfma(__low2half(u2h2(gg[2 * k])), ph[r][2 * k], VIP[2 * k]);
+                            VIP[2 * k + 1] = fhfma(__low2half(u2h2(gg[2 * k + 1])), ph[r][2 * k + 1], VIP[2 * k + 1]);
+                            VIP[2 * k] = fhfma(__low2half(io2), __low2half(po2), VIP[2 * k]);
+                            VIP[2 * k + 1] = fhfma(__high2half(io2), __high2half(po2), VIP[2 * k + 1]);
                         }
+                        tm_st4(tP + 4 * slots[r], pneg[r]);
                         hsum19(VP, SP[r]);
                         hsum19(VIP, SIP[r]);
                     }
