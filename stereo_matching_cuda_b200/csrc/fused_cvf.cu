@@ -53,8 +53,7 @@ struct FusedArgs {
     int size_d;
     int n_strips, n_bands, band_rows, n_chunks, chunk_d;
     int n_views;            // 2: both views (view v guides with image v); 1: view 0 only
-    float* bestS;           // [chunk][view][rows_out][pitchS]
-    float* labS;
+    float2* BL;             // [chunk][view][rows_out][pitchS] running (best cost, label) of each disparity chunk
     int pitchS;
     float S;                // lattice scale: p = P / S
     unsigned wpack;         // half2 (nI, nG): P = nI*cI + nG*cG
@@ -62,11 +61,14 @@ struct FusedArgs {
     int zero;               // always 0; opaque to the compiler (see touch_ops)
 };
 
+constexpr int K3_THREADS = 3 * NWARP * 32;  // three pipeline stages (warps p, p+4, p+8) per disparity
+constexpr uint32_t TM_HAND2 = 416;          // TMEM columns [416,448): stage 1 -> stage 2 hand-off rows
 constexpr int NQ = 4;     // depth of the ring of filtered rows between the consumer and the merging warps
 constexpr int MLAG = 2;   // a producer merges the rows its consumer emitted MLAG iterations ago
 struct SmemLayout {
     float4 qbuf[NQ][NWARP][ROWS][2][32];  // filtered rows of each consumer warp
-    uint64_t qfull[NQ], qempty[NQ];       // mbarriers: 4 consumer warps -> 4 producer warps and back
+    uint64_t qfull[NQ], qempty[NQ];       // mbarriers of the q ring (4 stage-2 warps write, the same 4 warps merge)
+    uint64_t full2[NWARP], empty2[NWARP]; // mbarriers of the stage 1 -> stage 2 hand-off of each pair
     uint32_t tmem_base;
 };
 
@@ -79,7 +81,6 @@ struct ProdOps {
 };
 struct ConsOps {
     float4 s0, s1, s2, s3;  // (mean_I, c2) x8 at row ya = yi-9
-    uint4 iq;               // guide intensity at row yq = yi-18, 8 halfs
 };
 struct ProdPtrs {
     const unsigned* g;
@@ -88,7 +89,6 @@ struct ProdPtrs {
 };
 struct ConsPtrs {
     const float2* st;
-    const __half* iq;
 };
 
 __device__ __forceinline__ void load_prod(ProdOps& o, const ProdPtrs& p, int dep) {
@@ -106,7 +106,6 @@ __device__ __forceinline__ void load_cons(ConsOps& o, const ConsPtrs& p, int dep
     o.s1 = __ldg(ps + 1);
     o.s2 = __ldg(ps + 2);
     o.s3 = __ldg(ps + 3);
-    o.iq = __ldg(reinterpret_cast<const uint4*>(p.iq + dep));
 }
 
 // One word of every load of `o`, OR-ed together.  The next step's loads are made to depend on
@@ -121,7 +120,6 @@ __device__ __forceinline__ int touch(const ProdOps& o) {
 }
 __device__ __forceinline__ int touch(const ConsOps& o) {
     unsigned t = __float_as_uint(o.s0.x) | __float_as_uint(o.s1.x) | __float_as_uint(o.s2.x) | __float_as_uint(o.s3.x);
-    t |= o.iq.x;
     return (int)t;
 }
 
@@ -152,7 +150,6 @@ __device__ __forceinline__ void copy_ops(ConsOps (&a)[ROWS], const ConsOps (&b)[
         a[r].s1 = b[r].s1;
         a[r].s2 = b[r].s2;
         a[r].s3 = b[r].s3;
-        a[r].iq = late_mov(b[r].iq);
     }
 }
 // f16 x f16 + f32 -> f32 and f16 + f32 -> f32 in one FMA-pipe instruction (FHFMA / FHADD, PTX 8.6, sm_100+)
@@ -166,10 +163,15 @@ __device__ __forceinline__ float fhadd(__half a, float c) {
     asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(d) : "h"(__half_as_ushort(a)), "f"(c));
     return d;
 }
-// a load the compiler may not sink towards its use
-__device__ __forceinline__ float ld_early(const float* p) {
-    float v;
-    asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+// loads the compiler may not sink towards their use
+__device__ __forceinline__ uint4 ld_early_v4(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_early_f4(const void* p) {  // coherent: written by this block one group earlier
+    float4 v;
+    asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
     return v;
 }
 
@@ -181,13 +183,13 @@ __device__ __forceinline__ float inv_rows(int y, int y_global0, int frame_h, flo
     return __frcp_rn(scale * (float)ay);
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
+__global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int pair = warp & (NWARP - 1);   // warps p and p+4 share SM sub-partition p and TMEM lane quarter p
-    const bool consumer = warp >= NWARP;
+    const int pair = warp & (NWARP - 1);  // warps p, p+4, p+8 share SM sub-partition p and TMEM lane quarter p
+    const int stage = warp / NWARP;       // 0: first stage, 1: coefficients + vertical sums, 2: output + merge
     int bid = blockIdx.x;
     const int view = bid % A.n_views;
     bid /= A.n_views;
@@ -212,6 +214,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
     static_assert((4 * RAD) % ROWS == 0, "ROWS must divide the warm-up length");
     const int n_emit = niter - WARM_IT;      // emissions (iterations that output rows) per group
     const int BAR_FULL = 2 + pair, BAR_EMPTY = 2 + NWARP + pair;
+    // A.zero in a register the compiler cannot re-read from the constant bank: a uniform constant
+    // load inside the row loop shares its scoreboard with the loads issued just before it and
+    // then waits for their full L2 round trip (ncu: 9 % of all samples on one LOP3)
+    int zero = A.zero;
+    asm volatile("" : "+r"(zero));
 
     // Tensor Memory: all 512 columns of the SM, one block per SM (register-limited)
     if (warp == 0) tm_alloc(&sm.tmem_base);
@@ -221,18 +228,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
             mbar_init(&sm.qfull[b], NWARP);
             mbar_init(&sm.qempty[b], NWARP);
         }
+#pragma unroll
+        for (int b = 0; b < NWARP; b++) {
+            mbar_init(&sm.full2[b], 1);
+            mbar_init(&sm.empty2[b], 1);
+        }
     }
     tm_fence_before();
     __syncthreads();
     tm_fence_after();
     const uint32_t tbase = sm.tmem_base + ((uint32_t)(pair * 32) << 16);
-    const uint32_t tAB = tbase + TM_RING_AB, tP = tbase + TM_RING_P, tH = tbase + TM_HAND;
+    const uint32_t tAB = tbase + TM_RING_AB, tP = tbase + TM_RING_P, tH = tbase + TM_HAND, tH2 = tbase + TM_HAND2;
 
-    if (!consumer) {
-        // =============================== PRODUCER: first stage ===============================
+    if (stage == 0) {
+        // ====== STAGE 0: lattice cost, vertical window sums of P and I*P, their horizontal sums ======
         const unsigned* __restrict__ IGg = A.IG[view];
         const unsigned* __restrict__ IGm = A.IG[1 - view];
-        const __half* __restrict__ If = A.Ih[view];
+        const __half* __restrict__ Ih = A.Ih[view];
         __half2 wm[KPX];  // lattice weights (nI, nG), 0 outside the image (masks the cost)
 #pragma unroll
         for (int j = 0; j < KPX; j++) {
@@ -240,61 +252,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
             wm[j] = (x >= 0 && x < A.w) ? u2h2(A.wpack) : __float2half2_rn(0.0f);
         }
         const __half2 th = u2h2(A.thpack);
-        // merge role of this thread: strip-local columns 2t, 2t+1 of all 4 disparities of a group
-        const int mc = 2 * threadIdx.x;
-        const int mx = xs + mc;
-        const bool mvalid0 = (mc >= HALO) && (mc < HALO + VALID_W) && (mx < A.w);
-        const bool mvalid1 = (mc + 1 >= HALO) && (mc + 1 < HALO + VALID_W) && (mx + 1 < A.w);
-        const int qoff = (((mc & 7) >> 2) * 32 + (mc >> 3)) * 4 + (mc & 3);
-        const size_t planeS = (size_t)A.rows_out * A.pitchS;
-        float* __restrict__ bestS = A.bestS + (size_t)(chunk * 2 + view) * planeS;
-        float* __restrict__ labS = A.labS + (size_t)(chunk * 2 + view) * planeS;
         for (int g = 0; g < ngroups; g++) {
             const int dk = g * NWARP + pair;
             const bool active = dk < dcnt;
             const int d = dlo + dk;
-            const int dbase = dlo + g * NWARP;
-            struct Best { float b0, b1, l0, l1; };
-            // running (best,label) of the rows of emission e, from the previous groups of this chunk
-            auto prefetch_best = [&](int e, Best (&pb)[ROWS]) {
-#pragma unroll
-                for (int r = 0; r < ROWS; r++) {
-                    pb[r].b0 = pb[r].b1 = BEST_INIT_BITS_F;
-                    pb[r].l0 = pb[r].l1 = 0.0f;
-                    const int yq = yb0 + e * ROWS + r;
-                    if (g > 0 && yq < yb1) {
-                        const size_t moff = (size_t)(yq - A.y_out0) * A.pitchS + mx;
-                        if (mvalid0) { pb[r].b0 = ld_early(bestS + moff); pb[r].l0 = ld_early(labS + moff); }
-                        if (mvalid1) { pb[r].b1 = ld_early(bestS + moff + 1); pb[r].l1 = ld_early(labS + moff + 1); }
-                    }
-                }
-            };
-            // fold the 4 disparities of this group into (best,label): ascending d, `>=` (last slice wins ties)
-            auto merge = [&](int e, const Best (&pb)[ROWS]) {
-                const int E = g * n_emit + e;
-                const int qb = E & (NQ - 1);
-                mbar_wait(&sm.qfull[qb], (unsigned)(E / NQ) & 1u);
-#pragma unroll
-                for (int r = 0; r < ROWS; r++) {
-                    const int yq = yb0 + e * ROWS + r;
-                    const float* qp = reinterpret_cast<const float*>(&sm.qbuf[qb][0][r][0][0]);
-                    float b0 = pb[r].b0, b1 = pb[r].b1, l0 = pb[r].l0, l1 = pb[r].l1;
-#pragma unroll
-                    for (int wv = 0; wv < NWARP; wv++) {
-                        float2 qv = *reinterpret_cast<const float2*>(qp + wv * (ROWS * 256) + qoff);
-                        float lab = (float)(dbase + wv);
-                        if (b0 >= qv.x) { b0 = qv.x; l0 = lab; }
-                        if (b1 >= qv.y) { b1 = qv.y; l1 = lab; }
-                    }
-                    if (yq < yb1) {
-                        const size_t moff = (size_t)(yq - A.y_out0) * A.pitchS + mx;
-                        if (mvalid0) { bestS[moff] = b0; labS[moff] = l0; }
-                        if (mvalid1) { bestS[moff + 1] = b1; labS[moff + 1] = l1; }
-                    }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.qempty[qb]);
-            };
             float VP[KPX], VIP[KPX];
 #pragma unroll
             for (int j = 0; j < KPX; j++) VP[j] = VIP[j] = 0.0f;
@@ -303,13 +264,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
                 for (int s = 0; s < WIN; s++) tm_st4(tP + 4 * s, z);
                 tm_wait_st();
             }
-            __syncthreads();  // group start (matches the consumers')
+            __syncthreads();  // group start
             if (active) {
                 ProdPtrs rp;
                 const long long r0 = (long long)y_first * pitch + xl;
                 rp.g = IGg + r0;
                 rp.m = IGm + (size_t)(d & 3) * A.shift_stride + r0 + (d - (d & 3));
-                rp.io = If + r0 - (long long)WIN * pitch;
+                rp.io = Ih + r0 - (long long)WIN * pitch;
                 int slot = 0;
                 ProdOps opsA[ROWS], opsB[ROWS];
 #pragma unroll
@@ -320,13 +281,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
                     rp.io += pitch;
                 }
                 auto iter = [&](const ProdOps (&o)[ROWS], ProdOps (&nxt)[ROWS], int it) {
-                    const int em = it - WARM_IT - MLAG;
-                    Best pb[ROWS];
-                    if (em >= 0) prefetch_best(em, pb);
                     int dep = 0;
 #pragma unroll
                     for (int r = 0; r < ROWS; r++) dep |= touch(o[r]);
-                    dep &= A.zero;
+                    dep &= zero;
 #pragma unroll
                     for (int r = 0; r < ROWS; r++) {
                         load_prod(nxt[r], rp, dep);
@@ -334,7 +292,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
                         rp.m += pitch;
                         rp.io += pitch;
                     }
-                    // the lattice costs that leave the window (rows yi-19), from the TMEM ring
+                    // the (negated) lattice costs that leave the window (rows yi-19), from the TMEM ring
                     uint32_t pold[ROWS][4];
                     int slots[ROWS];
 #pragma unroll
@@ -388,7 +346,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
                         hsum19(VP, SP[r]);
                         hsum19(VIP, SIP[r]);
                     }
-                    // the consumer has copied the previous rows out of the hand-off columns
+                    // stage 1 has copied the previous rows out of the hand-off columns
                     if (it > 0) {
                         named_bar_sync(BAR_EMPTY, 64);
                         tm_fence_after();
@@ -398,7 +356,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
                     tm_wait_st();
                     tm_fence_before();
                     named_bar_arrive(BAR_FULL, 64);
-                    if (em >= 0) merge(em, pb);
                 };
 #pragma unroll 1
                 for (int it = 0; it < niter; it++) {
@@ -406,18 +363,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
                     copy_ops(opsA, opsB);
                 }
             }
-            // the emissions not merged inside the loop (all of them for a pair without a disparity)
-#pragma unroll 1
-            for (int e = active ? max(0, n_emit - MLAG) : 0; e < n_emit; e++) {
-                Best pb[ROWS];
-                prefetch_best(e, pb);
-                merge(e, pb);
-            }
             __syncthreads();  // group end
         }
-    } else {
-        // ================================ CONSUMER: second stage ================================
-        const __half* __restrict__ If = A.Ih[view];
+    } else if (stage == 1) {
+        // ====== STAGE 1: a, b; their vertical window sums; horizontal sums of a ======
         const float2* __restrict__ st = A.st[view];
         float rx[KPX];  // 1 / clipped window width, 0 outside the image
 #pragma unroll
@@ -434,52 +383,35 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
             for (int j = 0; j < KPX; j++) Va[j] = Vb[j] = 0.0f;
             for (int s = 0; s < WIN; s++) tm_st16(tAB + 16 * s, Va, Vb);  // zeros
             tm_wait_st();
-            if (!active) {  // the previous group's merges have drained (group-end barrier)
-                const float inf = __int_as_float(0x7f800000);
-#pragma unroll
-                for (int b = 0; b < NQ; b++)
-#pragma unroll
-                    for (int r = 0; r < ROWS; r++)
-#pragma unroll
-                        for (int v = 0; v < 2; v++) sm.qbuf[b][pair][r][v][lane] = make_float4(inf, inf, inf, inf);
-            }
-            __syncthreads();  // group start: previous group's merges are done with qbuf
+            __syncthreads();  // group start
 
             int slot = 0;
             ConsPtrs rp;
-            {
-                const long long r0 = (long long)y_first * pitch + xl;
-                rp.st = st + r0 - (long long)RAD * pitch;
-                rp.iq = If + r0 - (long long)(2 * RAD) * pitch;
-            }
+            rp.st = st + (long long)(y_first - RAD) * pitch + xl;
             ConsOps opsA[ROWS], opsB[ROWS];
             if (active) {
 #pragma unroll
                 for (int r = 0; r < ROWS; r++) {
                     load_cons(opsA[r], rp, 0);
                     rp.st += pitch;
-                    rp.iq += pitch;
                 }
             }
-
             auto iter = [&](auto emit_tag, const ConsOps (&o)[ROWS], ConsOps (&nxt)[ROWS], int it) {
                 constexpr bool EMIT = decltype(emit_tag)::value;
                 int dep = 0;
 #pragma unroll
                 for (int r = 0; r < ROWS; r++) dep |= touch(o[r]);
-                dep &= A.zero;
+                dep &= zero;
 #pragma unroll
                 for (int r = 0; r < ROWS; r++) {
                     load_cons(nxt[r], rp, dep);
                     rp.st += pitch;
-                    rp.iq += pitch;
                 }
                 const int yi0 = y_first + it * ROWS;
-                const int yq0 = yi0 - 2 * RAD;
                 float ry1[ROWS];
 #pragma unroll
                 for (int r = 0; r < ROWS; r++) ry1[r] = inv_rows(yi0 + r - RAD, A.y_global0, A.frame_h, A.S);
-                // the (a,b) rows that leave the second-stage window, from this warp's TMEM ring
+                // the (a,b) rows that leave the second-stage window, from this pair's TMEM ring
                 float ao[ROWS][KPX], bo[ROWS][KPX];
                 int slots[ROWS];
 #pragma unroll
@@ -488,7 +420,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
                     tm_ld16(tAB + 16 * slot, ao[r], bo[r]);
                     slot = (slot + 1 == WIN) ? 0 : slot + 1;
                 }
-                named_bar_sync(BAR_FULL, 64);  // the producer has published rows yi0 .. yi0+ROWS-1
+                named_bar_sync(BAR_FULL, 64);  // stage 0 has published rows yi0 .. yi0+ROWS-1
                 tm_fence_after();
                 float SP[ROWS][KPX], SIP[ROWS][KPX];
 #pragma unroll
@@ -498,7 +430,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
                     tm_fence_before();
                     named_bar_arrive(BAR_EMPTY, 64);
                 }
-                float SA[ROWS][KPX], SB[ROWS][KPX];
+                float SA[ROWS][KPX], VB[ROWS][KPX];
 #pragma unroll
                 for (int r = 0; r < ROWS; r++) {
                     // ---- a, b at row ya = yi - 9
@@ -519,34 +451,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
                     for (int j = 0; j < KPX; j++) {
                         Va[j] += a[j] - ao[r][j];
                         Vb[j] += b[j] - bo[r][j];
+                        if (EMIT) VB[r][j] = Vb[j];
                     }
-                    if (EMIT) {
-                        hsum19(Va, SA[r]);
-                        hsum19(Vb, SB[r]);
-                    }
+                    if (EMIT) hsum19(Va, SA[r]);
                 }
                 if (EMIT) {
                     const int E = g * n_emit + (it - WARM_IT);
-                    const int qb = E & (NQ - 1);
-                    if (E >= NQ) mbar_wait(&sm.qempty[qb], (unsigned)(E / NQ - 1) & 1u);  // merged NQ emissions ago
-#pragma unroll
-                    for (int r = 0; r < ROWS; r++) {
-                        const float ry2 = inv_rows(yq0 + r, A.y_global0, A.frame_h, 1.0f);
-                        const float2 iq01 = __half22float2(u2h2(o[r].iq.x)), iq23 = __half22float2(u2h2(o[r].iq.y));
-                        const float2 iq45 = __half22float2(u2h2(o[r].iq.z)), iq67 = __half22float2(u2h2(o[r].iq.w));
-                        const float iq[KPX] = {iq01.x, iq01.y, iq23.x, iq23.y, iq45.x, iq45.y, iq67.x, iq67.y};
-                        float q[KPX];
-#pragma unroll
-                        for (int j = 0; j < KPX; j++) q[j] = fmaf(SA[r][j], iq[j], SB[r][j]) * (rx[j] * ry2);
-                        sm.qbuf[qb][pair][r][0][lane] = make_float4(q[0], q[1], q[2], q[3]);
-                        sm.qbuf[qb][pair][r][1][lane] = make_float4(q[4], q[5], q[6], q[7]);
+                    if (E > 0) {  // stage 2 has copied the previous rows out of its hand-off columns
+                        mbar_wait(&sm.empty2[pair], (unsigned)(E - 1) & 1u);
+                        tm_fence_after();
                     }
+#pragma unroll
+                    for (int r = 0; r < ROWS; r++) tm_st16(tH2 + 16 * r, SA[r], VB[r]);
+                    tm_wait_st();  // (also: this iteration's ring stores are complete before the next loads)
+                    tm_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&sm.qfull[qb]);
+                    if (lane == 0) mbar_arrive(&sm.full2[pair]);
+                } else {
+                    tm_wait_st();
                 }
-                tm_wait_st();  // this iteration's ring stores are complete before the next loads
             };
-
             if (active) {
                 int it = 0;
 #pragma unroll 1
@@ -559,6 +483,129 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
                     iter(std::true_type{}, opsA, opsB, it);
                     copy_ops(opsA, opsB);
                 }
+            }
+            __syncthreads();  // group end
+        }
+    } else {
+        // ====== STAGE 2: horizontal sums of b, q = mean_a * I + mean_b, merge of the 4 disparities ======
+        const __half* __restrict__ Ih = A.Ih[view];
+        float rx[KPX];
+#pragma unroll
+        for (int j = 0; j < KPX; j++) {
+            int x = xl + j;
+            int ax = min(A.w - 1, x + RAD) - max(0, x - RAD) + 1;
+            rx[j] = (x >= 0 && x < A.w) ? __frcp_rn((float)ax) : 0.0f;
+        }
+        // merge role of this thread: strip-local columns 2t, 2t+1 of all 4 disparities of a group
+        const int mc = 2 * (threadIdx.x - 2 * NWARP * 32);
+        const int mx = xs + mc;
+        // (HALO, VALID_W and mc are even: the two columns are inside the strip's valid range together; for an odd
+        //  image width the second one may be the first padding column of the plane, which is never read)
+        const bool mvalid = (mc >= HALO) && (mc < HALO + VALID_W) && (mx < A.w);
+        const int qoff = (((mc & 7) >> 2) * 32 + (mc >> 3)) * 4 + (mc & 3);
+        const size_t planeS = (size_t)A.rows_out * A.pitchS;
+        float2* __restrict__ BL = A.BL + (size_t)(chunk * 2 + view) * planeS;
+        for (int g = 0; g < ngroups; g++) {
+            const int dk = g * NWARP + pair;
+            const bool active = dk < dcnt;
+            const int dbase = dlo + g * NWARP;
+            typedef float4 Best;  // (best, label) of columns mx and mx+1
+            // running (best,label) of the rows of emission e, from the previous groups of this chunk
+            auto prefetch_best = [&](int e, Best (&pb)[ROWS]) {
+#pragma unroll
+                for (int r = 0; r < ROWS; r++) {
+                    pb[r] = make_float4(BEST_INIT_BITS_F, 0.0f, BEST_INIT_BITS_F, 0.0f);
+                    const int yq = yb0 + e * ROWS + r;
+                    if (g > 0 && yq < yb1 && mvalid) pb[r] = ld_early_f4(BL + (size_t)(yq - A.y_out0) * A.pitchS + mx);
+                }
+            };
+            // fold the 4 disparities of this group into (best,label): ascending d, `>=` (last slice wins ties)
+            auto merge = [&](int e, const Best (&pb)[ROWS]) {
+                const int E = g * n_emit + e;
+                const int qb = E & (NQ - 1);
+                mbar_wait(&sm.qfull[qb], (unsigned)(E / NQ) & 1u);
+#pragma unroll
+                for (int r = 0; r < ROWS; r++) {
+                    const int yq = yb0 + e * ROWS + r;
+                    const float* qp = reinterpret_cast<const float*>(&sm.qbuf[qb][0][r][0][0]);
+                    float b0 = pb[r].x, l0 = pb[r].y, b1 = pb[r].z, l1 = pb[r].w;
+#pragma unroll
+                    for (int wv = 0; wv < NWARP; wv++) {
+                        float2 qv = *reinterpret_cast<const float2*>(qp + wv * (ROWS * 256) + qoff);
+                        float lab = (float)(dbase + wv);
+                        if (b0 >= qv.x) { b0 = qv.x; l0 = lab; }
+                        if (b1 >= qv.y) { b1 = qv.y; l1 = lab; }
+                    }
+                    if (yq < yb1 && mvalid)
+                        *reinterpret_cast<float4*>(BL + (size_t)(yq - A.y_out0) * A.pitchS + mx) = make_float4(b0, l0, b1, l1);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.qempty[qb]);
+            };
+            if (!active) {  // the previous group's merges have drained (group-end barrier)
+                const float inf = __int_as_float(0x7f800000);
+#pragma unroll
+                for (int b = 0; b < NQ; b++)
+#pragma unroll
+                    for (int r = 0; r < ROWS; r++)
+#pragma unroll
+                        for (int v = 0; v < 2; v++) sm.qbuf[b][pair][r][v][lane] = make_float4(inf, inf, inf, inf);
+            }
+            __syncthreads();  // group start
+            if (active) {
+                const __half* piq = Ih + (long long)yb0 * pitch + xl;  // row yq = yb0 + e*ROWS + r
+                uint4 iqA[ROWS], iqB[ROWS];
+#pragma unroll
+                for (int r = 0; r < ROWS; r++) {
+                    iqA[r] = ld_early_v4(piq);
+                    piq += pitch;
+                }
+#pragma unroll 1
+                for (int e = 0; e < n_emit; e++) {
+                    int dep = 0;
+#pragma unroll
+                    for (int r = 0; r < ROWS; r++) dep |= (int)iqA[r].x;
+                    dep &= zero;
+#pragma unroll
+                    for (int r = 0; r < ROWS; r++) {
+                        iqB[r] = ld_early_v4(piq + dep);
+                        piq += pitch;
+                    }
+                    const int em = e - MLAG;
+                    Best pb[ROWS];
+                    if (em >= 0) prefetch_best(em, pb);
+                    const int E = g * n_emit + e;
+                    mbar_wait(&sm.full2[pair], (unsigned)E & 1u);  // stage 1 has published this emission
+                    tm_fence_after();
+                    float SA[ROWS][KPX], VB[ROWS][KPX];
+#pragma unroll
+                    for (int r = 0; r < ROWS; r++) tm_ld16(tH2 + 16 * r, SA[r], VB[r]);
+                    tm_wait_ld();
+                    tm_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.empty2[pair]);
+                    const int qb = E & (NQ - 1);
+                    if (E >= NQ) mbar_wait(&sm.qempty[qb], (unsigned)(E / NQ - 1) & 1u);  // merged NQ emissions ago
+#pragma unroll
+                    for (int r = 0; r < ROWS; r++) {
+                        float SB[KPX];
+                        hsum19(VB[r], SB);
+                        const float ry2 = inv_rows(yb0 + e * ROWS + r, A.y_global0, A.frame_h, 1.0f);
+                        const float2 iq01 = __half22float2(u2h2(iqA[r].x)), iq23 = __half22float2(u2h2(iqA[r].y));
+                        const float2 iq45 = __half22float2(u2h2(iqA[r].z)), iq67 = __half22float2(u2h2(iqA[r].w));
+                        const float iq[KPX] = {iq01.x, iq01.y, iq23.x, iq23.y, iq45.x, iq45.y, iq67.x, iq67.y};
+                        float q[KPX];
+#pragma unroll
+                        for (int j = 0; j < KPX; j++) q[j] = fmaf(SA[r][j], iq[j], SB[j]) * (rx[j] * ry2);
+                        sm.qbuf[qb][pair][r][0][lane] = make_float4(q[0], q[1], q[2], q[3]);
+                        sm.qbuf[qb][pair][r][1][lane] = make_float4(q[4], q[5], q[6], q[7]);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.qfull[qb]);
+                    if (em >= 0) merge(em, pb);
+#pragma unroll
+                    for (int r = 0; r < ROWS; r++) iqA[r] = late_mov(iqB[r]);
+                }
             } else {
                 // no disparity for this pair in the (last, partial) group: its slots hold +inf
                 for (int e = 0; e < n_emit; e++) {
@@ -566,6 +613,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
                     const int qb = E & (NQ - 1);
                     if (E >= NQ) mbar_wait(&sm.qempty[qb], (unsigned)(E / NQ - 1) & 1u);
                     if (lane == 0) mbar_arrive(&sm.qfull[qb]);
+                    Best pb[ROWS];
+                    prefetch_best(e, pb);
+                    merge(e, pb);
+                }
+            }
+            // the emissions not merged inside the loop
+            if (active) {
+#pragma unroll 1
+                for (int e = max(0, n_emit - MLAG); e < n_emit; e++) {
+                    Best pb[ROWS];
+                    prefetch_best(e, pb);
+                    merge(e, pb);
                 }
             }
             __syncthreads();  // group end
@@ -578,6 +637,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused_cvf(const FusedArgs A) {
         tm_fence_after();
         tm_dealloc(sm.tmem_base);
     }
+}
+
+// Chunk merge: fold the per-chunk (best,label) planes in chunk order with the same rule.
+__global__ void k_merge_chunks_bl(const float2* __restrict__ BL, int n_chunks, int view, int rows, int w, int pitchS,
+                                  float* __restrict__ best, float* __restrict__ disp) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (x >= w) return;
+    const size_t plane = (size_t)rows * pitchS;
+    float b = BEST_INIT_BITS_F, l = 0.0f;
+    for (int c = 0; c < n_chunks; c++) {
+        float2 q = BL[(size_t)(c * 2 + view) * plane + (size_t)y * pitchS + x];
+        if (b >= q.x) { b = q.x; l = q.y; }
+    }
+    if (best) best[(size_t)y * w + x] = b;
+    if (disp) disp[(size_t)y * w + x] = l;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -703,7 +778,7 @@ size_t sbf_workspace_bytes(const sb200_ctx* ctx, int w, int h_held, int rows_out
     bytes += 2 * sb_align(plane * 4 * 4);  // IG x2, 4 shifted copies each
     bytes += 2 * sb_align(plane * 4);      // If x2
     bytes += 2 * sb_align(plane * 8);      // st x2
-    bytes += 2 * sb_align((size_t)plan.n_chunks * 2 * rows_out * pitchS * 4);  // bestS, labS
+    bytes += sb_align((size_t)plan.n_chunks * 2 * rows_out * pitchS * 8);  // BL
     return bytes + 4096;
 }
 
@@ -767,9 +842,8 @@ static int run_fused(sb200_ctx* ctx, const sb200_params* p, const uint8_t* const
         st[i] = sb_ws_alloc<float2>(ctx, plane);
     }
     const size_t planeS = (size_t)g.rows_out * pitchS;
-    float* bestS = sb_ws_alloc<float>(ctx, planeS * 2 * plan.n_chunks);
-    float* labS = sb_ws_alloc<float>(ctx, planeS * 2 * plan.n_chunks);
-    if (!IG[0] || !IG[1] || !If[0] || !If[1] || !st[0] || !st[1] || !bestS || !labS)
+    float2* BL = sb_ws_alloc<float2>(ctx, planeS * 2 * plan.n_chunks);
+    if (!IG[0] || !IG[1] || !If[0] || !If[1] || !st[0] || !st[1] || !BL)
         return sb_fail(ctx, SB200_ERR_NOMEM, "fused: workspace arena too small (internal)");
 
     if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -797,8 +871,7 @@ static int run_fused(sb200_ctx* ctx, const sb200_params* p, const uint8_t* const
     A.band_rows = plan.band_rows;
     A.n_chunks = plan.n_chunks;
     A.chunk_d = plan.chunk_d;
-    A.bestS = bestS;
-    A.labS = labS;
+    A.BL = BL;
     A.pitchS = pitchS;
     A.S = (float)S;
     __half2 wp = __floats2half2_rn((float)nI, (float)nG);
@@ -814,13 +887,12 @@ static int run_fused(sb200_ctx* ctx, const sb200_params* p, const uint8_t* const
     }
     A.n_views = n_views;
     const int nblocks = plan.n_strips * plan.n_bands * plan.n_chunks * n_views;
-    SB_LAUNCH(ctx, k_fused_cvf, nblocks, NTHREADS, smem, A);
+    SB_LAUNCH(ctx, k_fused_cvf, nblocks, K3_THREADS, smem, A);
     if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     for (int v = 0; v < n_views; v++) {
         if (!best[v] && !disp[v]) continue;
         dim3 grid(sb_div_up(g.w, 256), g.rows_out);
-        SB_LAUNCH(ctx, k_merge_chunks, grid, 256, 0, bestS, labS, plan.n_chunks, v, g.rows_out, g.w, pitchS, best[v],
-                  disp[v]);
+        SB_LAUNCH(ctx, k_merge_chunks_bl, grid, 256, 0, BL, plan.n_chunks, v, g.rows_out, g.w, pitchS, best[v], disp[v]);
     }
     if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     return SB200_OK;
