@@ -69,6 +69,7 @@ struct SmemLayout {
     float4 qbuf[NQ][NWARP][ROWS][2][32];  // filtered rows of each consumer warp
     uint64_t qfull[NQ], qempty[NQ];       // mbarriers of the q ring (4 stage-2 warps write, the same 4 warps merge)
     uint64_t full2[NWARP], empty2[NWARP]; // mbarriers of the stage 1 -> stage 2 hand-off of each pair
+    float ry_lut[2][WIN + 1];             // [0][n] = 1/(S*n), [1][n] = 1/n for a clipped window of n rows; [.][0] = 0
     uint32_t tmem_base;
 };
 
@@ -175,12 +176,13 @@ __device__ __forceinline__ float4 ld_early_f4(const void* p) {  // coherent: wri
     return v;
 }
 
-__device__ __forceinline__ float inv_rows(int y, int y_global0, int frame_h, float scale) {
-    // 1 / (scale * clipped window height) at held row y, 0 outside the frame
+__device__ __forceinline__ float inv_rows(const float* lut, int y, int y_global0, int frame_h) {
+    // 1 / (scale * clipped window height) at held row y, 0 outside the frame: the height takes
+    // 19 values, the reciprocals come from a table in shared memory
     int yg = y + y_global0;
-    if (yg < 0 || yg >= frame_h) return 0.0f;
     int ay = min(frame_h - 1, yg + RAD) - max(0, yg - RAD) + 1;
-    return __frcp_rn(scale * (float)ay);
+    if (yg < 0 || yg >= frame_h) ay = 0;
+    return lut[ay];
 }
 
 __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) {
@@ -222,17 +224,23 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
 
     // Tensor Memory: all 512 columns of the SM, one block per SM (register-limited)
     if (warp == 0) tm_alloc(&sm.tmem_base);
+    const uint32_t mb_qfull = smem_addr(&sm.qfull[0]), mb_qempty = smem_addr(&sm.qempty[0]);
+    const uint32_t mb_full2 = smem_addr(&sm.full2[pair]), mb_empty2 = smem_addr(&sm.empty2[pair]);
     if (threadIdx.x == 32) {
 #pragma unroll
         for (int b = 0; b < NQ; b++) {
-            mbar_init(&sm.qfull[b], NWARP);
-            mbar_init(&sm.qempty[b], NWARP);
+            mbar_init(mb_qfull + 8 * b, NWARP);
+            mbar_init(mb_qempty + 8 * b, NWARP);
         }
 #pragma unroll
         for (int b = 0; b < NWARP; b++) {
-            mbar_init(&sm.full2[b], 1);
-            mbar_init(&sm.empty2[b], 1);
+            mbar_init(smem_addr(&sm.full2[b]), 1);
+            mbar_init(smem_addr(&sm.empty2[b]), 1);
         }
+    }
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + 2 * (WIN + 1)) {
+        const int t = threadIdx.x - 64, n = t % (WIN + 1);
+        sm.ry_lut[t / (WIN + 1)][n] = (n == 0) ? 0.0f : __frcp_rn((t < WIN + 1 ? A.S : 1.0f) * (float)n);
     }
     tm_fence_before();
     __syncthreads();
@@ -410,7 +418,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                 const int yi0 = y_first + it * ROWS;
                 float ry1[ROWS];
 #pragma unroll
-                for (int r = 0; r < ROWS; r++) ry1[r] = inv_rows(yi0 + r - RAD, A.y_global0, A.frame_h, A.S);
+                for (int r = 0; r < ROWS; r++) ry1[r] = inv_rows(sm.ry_lut[0], yi0 + r - RAD, A.y_global0, A.frame_h);
                 // the (a,b) rows that leave the second-stage window, from this pair's TMEM ring
                 float ao[ROWS][KPX], bo[ROWS][KPX];
                 int slots[ROWS];
@@ -458,7 +466,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                 if (EMIT) {
                     const int E = g * n_emit + (it - WARM_IT);
                     if (E > 0) {  // stage 2 has copied the previous rows out of its hand-off columns
-                        mbar_wait(&sm.empty2[pair], (unsigned)(E - 1) & 1u);
+                        mbar_wait(mb_empty2, (unsigned)(E - 1) & 1u);
                         tm_fence_after();
                     }
 #pragma unroll
@@ -466,7 +474,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                     tm_wait_st();  // (also: this iteration's ring stores are complete before the next loads)
                     tm_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&sm.full2[pair]);
+                    if (lane == 0) mbar_arrive(mb_full2);
                 } else {
                     tm_wait_st();
                 }
@@ -509,6 +517,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
             const int dk = g * NWARP + pair;
             const bool active = dk < dcnt;
             const int dbase = dlo + g * NWARP;
+            const float lab[NWARP] = {(float)dbase, (float)(dbase + 1), (float)(dbase + 2), (float)(dbase + 3)};
             typedef float4 Best;  // (best, label) of columns mx and mx+1
             // running (best,label) of the rows of emission e, from the previous groups of this chunk
             auto prefetch_best = [&](int e, Best (&pb)[ROWS]) {
@@ -523,24 +532,39 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
             auto merge = [&](int e, const Best (&pb)[ROWS]) {
                 const int E = g * n_emit + e;
                 const int qb = E & (NQ - 1);
-                mbar_wait(&sm.qfull[qb], (unsigned)(E / NQ) & 1u);
+                mbar_wait(mb_qfull + 8 * qb, (unsigned)(E / NQ) & 1u);
 #pragma unroll
                 for (int r = 0; r < ROWS; r++) {
                     const int yq = yb0 + e * ROWS + r;
                     const float* qp = reinterpret_cast<const float*>(&sm.qbuf[qb][0][r][0][0]);
                     float b0 = pb[r].x, l0 = pb[r].y, b1 = pb[r].z, l1 = pb[r].w;
+                    float2 qv[NWARP];
 #pragma unroll
-                    for (int wv = 0; wv < NWARP; wv++) {
-                        float2 qv = *reinterpret_cast<const float2*>(qp + wv * (ROWS * 256) + qoff);
-                        float lab = (float)(dbase + wv);
-                        if (b0 >= qv.x) { b0 = qv.x; l0 = lab; }
-                        if (b1 >= qv.y) { b1 = qv.y; l1 = lab; }
+                    for (int wv = 0; wv < NWARP; wv++) qv[wv] = *reinterpret_cast<const float2*>(qp + wv * (ROWS * 256) + qoff);
+                    // "minimum, the later disparity on a tie" is associative: a 2-level tournament
+                    // gives what the reference's sequential `best >= q` scan gives, with a shorter chain
+                    static_assert(NWARP == 4, "tournament written for 4 disparities per group");
+                    {
+                        const bool t01 = qv[0].x >= qv[1].x, t23 = qv[2].x >= qv[3].x;
+                        const float m01 = t01 ? qv[1].x : qv[0].x, m23 = t23 ? qv[3].x : qv[2].x;
+                        const float a01 = t01 ? lab[1] : lab[0], a23 = t23 ? lab[3] : lab[2];
+                        const bool t = m01 >= m23;
+                        const float m = t ? m23 : m01, a = t ? a23 : a01;
+                        if (b0 >= m) { b0 = m; l0 = a; }
+                    }
+                    {
+                        const bool t01 = qv[0].y >= qv[1].y, t23 = qv[2].y >= qv[3].y;
+                        const float m01 = t01 ? qv[1].y : qv[0].y, m23 = t23 ? qv[3].y : qv[2].y;
+                        const float a01 = t01 ? lab[1] : lab[0], a23 = t23 ? lab[3] : lab[2];
+                        const bool t = m01 >= m23;
+                        const float m = t ? m23 : m01, a = t ? a23 : a01;
+                        if (b1 >= m) { b1 = m; l1 = a; }
                     }
                     if (yq < yb1 && mvalid)
                         *reinterpret_cast<float4*>(BL + (size_t)(yq - A.y_out0) * A.pitchS + mx) = make_float4(b0, l0, b1, l1);
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.qempty[qb]);
+                if (lane == 0) mbar_arrive(mb_qempty + 8 * qb);
             };
             if (!active) {  // the previous group's merges have drained (group-end barrier)
                 const float inf = __int_as_float(0x7f800000);
@@ -575,7 +599,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                     Best pb[ROWS];
                     if (em >= 0) prefetch_best(em, pb);
                     const int E = g * n_emit + e;
-                    mbar_wait(&sm.full2[pair], (unsigned)E & 1u);  // stage 1 has published this emission
+                    mbar_wait(mb_full2, (unsigned)E & 1u);  // stage 1 has published this emission
                     tm_fence_after();
                     float SA[ROWS][KPX], VB[ROWS][KPX];
 #pragma unroll
@@ -583,14 +607,14 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                     tm_wait_ld();
                     tm_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&sm.empty2[pair]);
+                    if (lane == 0) mbar_arrive(mb_empty2);
                     const int qb = E & (NQ - 1);
-                    if (E >= NQ) mbar_wait(&sm.qempty[qb], (unsigned)(E / NQ - 1) & 1u);  // merged NQ emissions ago
+                    if (E >= NQ) mbar_wait(mb_qempty + 8 * qb, (unsigned)(E / NQ - 1) & 1u);  // merged NQ emissions ago
 #pragma unroll
                     for (int r = 0; r < ROWS; r++) {
                         float SB[KPX];
                         hsum19(VB[r], SB);
-                        const float ry2 = inv_rows(yb0 + e * ROWS + r, A.y_global0, A.frame_h, 1.0f);
+                        const float ry2 = inv_rows(sm.ry_lut[1], yb0 + e * ROWS + r, A.y_global0, A.frame_h);
                         const float2 iq01 = __half22float2(u2h2(iqA[r].x)), iq23 = __half22float2(u2h2(iqA[r].y));
                         const float2 iq45 = __half22float2(u2h2(iqA[r].z)), iq67 = __half22float2(u2h2(iqA[r].w));
                         const float iq[KPX] = {iq01.x, iq01.y, iq23.x, iq23.y, iq45.x, iq45.y, iq67.x, iq67.y};
@@ -601,7 +625,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                         sm.qbuf[qb][pair][r][1][lane] = make_float4(q[4], q[5], q[6], q[7]);
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&sm.qfull[qb]);
+                    if (lane == 0) mbar_arrive(mb_qfull + 8 * qb);
                     if (em >= 0) merge(em, pb);
 #pragma unroll
                     for (int r = 0; r < ROWS; r++) iqA[r] = late_mov(iqB[r]);
@@ -611,8 +635,8 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                 for (int e = 0; e < n_emit; e++) {
                     const int E = g * n_emit + e;
                     const int qb = E & (NQ - 1);
-                    if (E >= NQ) mbar_wait(&sm.qempty[qb], (unsigned)(E / NQ - 1) & 1u);
-                    if (lane == 0) mbar_arrive(&sm.qfull[qb]);
+                    if (E >= NQ) mbar_wait(mb_qempty + 8 * qb, (unsigned)(E / NQ - 1) & 1u);
+                    if (lane == 0) mbar_arrive(mb_qfull + 8 * qb);
                     Best pb[ROWS];
                     prefetch_best(e, pb);
                     merge(e, pb);

@@ -29,13 +29,14 @@ __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
 // mbarrier (shared-memory barrier object with phase parity) -- used where a producer/consumer
 // ring is deeper than the 16 hardware named barriers allow
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* b, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(b)), "r"(count) : "memory");
+// (the barriers are addressed by their 32-bit shared-window address, computed once per kernel)
+__device__ __forceinline__ void mbar_init(uint32_t b, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(b)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(b) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t b, unsigned parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -44,7 +45,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, unsigned parity) {
         "@p bra MB_DONE;\n"
         "bra MB_WAIT;\n"
         "MB_DONE:\n"
-        "}\n" ::"r"(smem_addr(b)),
+        "}\n" ::"r"(b),
         "r"(parity)
         : "memory");
 }
