@@ -42,9 +42,13 @@ struct FusedArgs {
     const unsigned* IG[2];  // per IMAGE (0 left, 1 right): padded half2 (I, G=I[x-1]-I[x+1]); -> element (0,0)
     size_t shift_stride;    // IG[i] + s*shift_stride (s = 0..3) is the same plane moved left by s elements, so the
                             // match operands at x+d are two aligned 16 B loads from copy (d & 3)
-    const __half* Ih[2];    // per IMAGE: padded half intensity (exact: 0..255), stored shifted by 4 elements so that a
-                            // lane's 8 pixels are one aligned 16 B load; zero padding
-    const float2* st[2];    // per VIEW (guide = image v): padded (mean_I, c/(S*area)), zero padding
+    // Guide operands, STRIP-TILED (see k_prep): record (strip, padded row) of each plane holds the 256 columns of the
+    // strip as [16-byte chunk c][lane][16 B], i.e. exactly the bytes lane L reads with its c-th 128-bit load, so one
+    // bulk copy per plane and row pair fills the shared-memory operand ring without bank conflicts on the read side.
+    const uint4* Tg[2];     // per IMAGE: (I,G) half2, 2 chunks per lane, 1 KB per row
+    const uint4* TI[2];     // per IMAGE: I as half (exact: 0..255), 1 chunk, 512 B per row
+    const uint4* Tst[2];    // per IMAGE: float2 (mean_I, c/(S*area)), 4 chunks, 2 KB per row
+    int rows_pad;           // padded rows per strip (held rows + 2*PADY)
     int pitch;              // elements per padded row
     int w;
     int y_out0, rows_out;   // output rows, in held-row coordinates
@@ -65,7 +69,18 @@ constexpr int K3_THREADS = 3 * NWARP * 32;  // three pipeline stages (warps p, p
 constexpr uint32_t TM_HAND2 = 416;          // TMEM columns [416,448): stage 1 -> stage 2 hand-off rows
 constexpr int NQ = 4;     // depth of the ring of filtered rows between the consumer and the merging warps
 constexpr int MLAG = 2;   // a producer merges the rows its consumer emitted MLAG iterations ago
+constexpr int NS = 16;        // slots of the operand ring (one per pipeline iteration)
+constexpr int LOAD_AHEAD = 5; // the loading warp fills the slot of iteration K + LOAD_AHEAD while it works on K
+struct Slot {                 // guide operands of one iteration, filled by 4 bulk copies (8 KB)
+    uint4 g[ROWS][2][32];     // (I,G) at rows yi
+    uint4 io[ROWS][32];       // I at rows yi-19 (leave the first-stage window)
+    uint4 iq[ROWS][32];       // I at rows yq = yi-18 (the output rows of this iteration)
+    uint4 st[ROWS][4][32];    // (mean_I, c2) at rows yi-9
+};
+constexpr uint32_t SLOT_BYTES = sizeof(Slot);
 struct SmemLayout {
+    Slot slot[NS];
+    uint64_t sfull[NS], sempty[NS];       // mbarriers of the operand ring: bulk copies -> 12 warps and back
     float4 qbuf[NQ][NWARP][ROWS][2][32];  // filtered rows of each consumer warp
     uint64_t qfull[NQ], qempty[NQ];       // mbarriers of the q ring (4 stage-2 warps write, the same 4 warps merge)
     uint64_t full2[NWARP], empty2[NWARP]; // mbarriers of the stage 1 -> stage 2 hand-off of each pair
@@ -76,82 +91,28 @@ struct SmemLayout {
 // operands of one row step, fetched one step ahead; the producer and the consumer warp of a
 // pair each fetch only what their stage needs
 struct ProdOps {
-    uint4 g0, g1;     // guide (I,G) half2 x8 at row yi
     uint4 m0, m1;     // match (I,G) half2 x8 at row yi, columns x+d (from the copy shifted by d & 3)
-    uint4 io;         // guide intensity at row yi-19 (leaves the first-stage window), 8 halfs
-};
-struct ConsOps {
-    float4 s0, s1, s2, s3;  // (mean_I, c2) x8 at row ya = yi-9
 };
 struct ProdPtrs {
-    const unsigned* g;
     const unsigned* m;
-    const __half* io;  // half plane, shifted by 4 elements so that a lane's 8 pixels are 16 B aligned
-};
-struct ConsPtrs {
-    const float2* st;
 };
 
 __device__ __forceinline__ void load_prod(ProdOps& o, const ProdPtrs& p, int dep) {
-    const uint4* pg = reinterpret_cast<const uint4*>(p.g + dep);
-    o.g0 = __ldg(pg);
-    o.g1 = __ldg(pg + 1);
     const uint4* pm = reinterpret_cast<const uint4*>(p.m + dep);
     o.m0 = __ldg(pm);
     o.m1 = __ldg(pm + 1);
-    o.io = __ldg(reinterpret_cast<const uint4*>(p.io + dep));
 }
-__device__ __forceinline__ void load_cons(ConsOps& o, const ConsPtrs& p, int dep) {
-    const float4* ps = reinterpret_cast<const float4*>(p.st + dep);
-    o.s0 = __ldg(ps);
-    o.s1 = __ldg(ps + 1);
-    o.s2 = __ldg(ps + 2);
-    o.s3 = __ldg(ps + 3);
-}
-
 // One word of every load of `o`, OR-ed together.  The next step's loads are made to depend on
 // it (masked to zero by a kernel argument the compiler cannot see through), so the scoreboard
 // wait for THIS step's operands is taken before the new loads are issued.  Without it the
 // first use of an operand waits on a scoreboard slot that the just-issued prefetch loads
 // share, i.e. on a full L2 round trip every step (ncu: 50 % of all stall samples, round 1).
 __device__ __forceinline__ int touch(const ProdOps& o) {
-    unsigned t = o.g0.x | o.g1.x | o.m0.x | o.m1.x;
-    t |= o.io.x;
-    return (int)t;
+    return (int)(o.m0.x | o.m1.x);
 }
-__device__ __forceinline__ int touch(const ConsOps& o) {
-    unsigned t = __float_as_uint(o.s0.x) | __float_as_uint(o.s1.x) | __float_as_uint(o.s2.x) | __float_as_uint(o.s3.x);
-    return (int)t;
-}
-
-// End-of-iteration hand-over of the prefetched operands.  The intensity words go through an
-// opaque move: left to itself the compiler converts them to float at the top of the iteration,
-// which frees their registers and lets it place this copy right behind the prefetch load --
-// a full L2 round trip on the critical path of every iteration (ncu, round 1: 12 % of samples).
-__device__ __forceinline__ unsigned late_mov(unsigned v) {
-    unsigned r;
-    asm volatile("mov.b32 %0, %1;" : "=r"(r) : "r"(v));
-    return r;
-}
-__device__ __forceinline__ uint4 late_mov(uint4 v) { return make_uint4(late_mov(v.x), late_mov(v.y), late_mov(v.z), late_mov(v.w)); }
 __device__ __forceinline__ void copy_ops(ProdOps (&a)[ROWS], const ProdOps (&b)[ROWS]) {
 #pragma unroll
-    for (int r = 0; r < ROWS; r++) {
-        a[r].g0 = b[r].g0;
-        a[r].g1 = b[r].g1;
-        a[r].m0 = b[r].m0;
-        a[r].m1 = b[r].m1;
-        a[r].io = late_mov(b[r].io);
-    }
-}
-__device__ __forceinline__ void copy_ops(ConsOps (&a)[ROWS], const ConsOps (&b)[ROWS]) {
-#pragma unroll
-    for (int r = 0; r < ROWS; r++) {
-        a[r].s0 = b[r].s0;
-        a[r].s1 = b[r].s1;
-        a[r].s2 = b[r].s2;
-        a[r].s3 = b[r].s3;
-    }
+    for (int r = 0; r < ROWS; r++) a[r] = b[r];
 }
 // f16 x f16 + f32 -> f32 and f16 + f32 -> f32 in one FMA-pipe instruction (FHFMA / FHADD, PTX 8.6, sm_100+)
 __device__ __forceinline__ float fhfma(__half a, __half b, float c) {
@@ -164,15 +125,25 @@ __device__ __forceinline__ float fhadd(__half a, float c) {
     asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(d) : "h"(__half_as_ushort(a)), "f"(c));
     return d;
 }
-// loads the compiler may not sink towards their use
-__device__ __forceinline__ uint4 ld_early_v4(const void* p) {
-    uint4 v;
-    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-}
+// a load the compiler may not sink towards its use
 __device__ __forceinline__ float4 ld_early_f4(const void* p) {  // coherent: written by this block one group earlier
     float4 v;
     asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
 
@@ -226,6 +197,16 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
     if (warp == 0) tm_alloc(&sm.tmem_base);
     const uint32_t mb_qfull = smem_addr(&sm.qfull[0]), mb_qempty = smem_addr(&sm.qempty[0]);
     const uint32_t mb_full2 = smem_addr(&sm.full2[pair]), mb_empty2 = smem_addr(&sm.empty2[pair]);
+    const uint32_t mb_sfull = smem_addr(&sm.sfull[0]), mb_sempty = smem_addr(&sm.sempty[0]);
+    const uint32_t slot0 = smem_addr(&sm.slot[0]) + 16 * lane;  // this lane's 16 bytes of a slot's chunk 0
+    static_assert((NS & (NS - 1)) == 0, "slot index and phase are taken from the bits of the iteration counter");
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int b = 0; b < NS; b++) {
+            mbar_init(mb_sfull + 8 * b, 1);
+            mbar_init(mb_sempty + 8 * b, 3 * NWARP);
+        }
+    }
     if (threadIdx.x == 32) {
 #pragma unroll
         for (int b = 0; b < NQ; b++) {
@@ -248,11 +229,23 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
     const uint32_t tbase = sm.tmem_base + ((uint32_t)(pair * 32) << 16);
     const uint32_t tAB = tbase + TM_RING_AB, tP = tbase + TM_RING_P, tH = tbase + TM_HAND, tH2 = tbase + TM_HAND2;
 
+    // operand ring, consumer side: every warp waits for the slot of its iteration K, reads its 16-byte chunks and
+    // releases the slot.  `t` is a word of the loaded data: the release depends on it, so it cannot be issued before
+    // the reads have completed.
+    auto slot_wait = [&](int K) -> uint32_t {
+        mbar_wait(mb_sfull + 8 * (K & (NS - 1)), (unsigned)(K / NS) & 1u);
+        return slot0 + (uint32_t)(K & (NS - 1)) * SLOT_BYTES;
+    };
+    auto slot_release = [&](int K, unsigned t) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(mb_sempty + 8 * (K & (NS - 1)) + (t & (unsigned)zero));
+    };
+    constexpr uint32_t OFF_G = offsetof(Slot, g), OFF_IO = offsetof(Slot, io), OFF_IQ = offsetof(Slot, iq),
+                       OFF_ST = offsetof(Slot, st);
+
     if (stage == 0) {
         // ====== STAGE 0: lattice cost, vertical window sums of P and I*P, their horizontal sums ======
-        const unsigned* __restrict__ IGg = A.IG[view];
         const unsigned* __restrict__ IGm = A.IG[1 - view];
-        const __half* __restrict__ Ih = A.Ih[view];
         __half2 wm[KPX];  // lattice weights (nI, nG), 0 outside the image (masks the cost)
 #pragma unroll
         for (int j = 0; j < KPX; j++) {
@@ -276,17 +269,13 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
             if (active) {
                 ProdPtrs rp;
                 const long long r0 = (long long)y_first * pitch + xl;
-                rp.g = IGg + r0;
                 rp.m = IGm + (size_t)(d & 3) * A.shift_stride + r0 + (d - (d & 3));
-                rp.io = Ih + r0 - (long long)WIN * pitch;
                 int slot = 0;
                 ProdOps opsA[ROWS], opsB[ROWS];
 #pragma unroll
                 for (int r = 0; r < ROWS; r++) {
                     load_prod(opsA[r], rp, 0);
-                    rp.g += pitch;
                     rp.m += pitch;
-                    rp.io += pitch;
                 }
                 auto iter = [&](const ProdOps (&o)[ROWS], ProdOps (&nxt)[ROWS], int it) {
                     int dep = 0;
@@ -296,9 +285,22 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
 #pragma unroll
                     for (int r = 0; r < ROWS; r++) {
                         load_prod(nxt[r], rp, dep);
-                        rp.g += pitch;
                         rp.m += pitch;
-                        rp.io += pitch;
+                    }
+                    // guide operands of this iteration from the shared-memory ring
+                    uint4 gq[ROWS][2], ioq[ROWS];
+                    {
+                        const int K = g * niter + it;
+                        const uint32_t sa = slot_wait(K);
+                        unsigned t = 0;
+#pragma unroll
+                        for (int r = 0; r < ROWS; r++) {
+                            gq[r][0] = lds128(sa + OFF_G + (r * 2 + 0) * 512);
+                            gq[r][1] = lds128(sa + OFF_G + (r * 2 + 1) * 512);
+                            ioq[r] = lds128(sa + OFF_IO + r * 512);
+                            t |= gq[r][0].x | gq[r][1].x | ioq[r].x;
+                        }
+                        slot_release(K, t);
                     }
                     // the (negated) lattice costs that leave the window (rows yi-19), from the TMEM ring
                     uint32_t pold[ROWS][4];
@@ -314,8 +316,8 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                     __half ph[ROWS][KPX];
 #pragma unroll
                     for (int r = 0; r < ROWS; r++) {
-                        const unsigned gg[KPX] = {o[r].g0.x, o[r].g0.y, o[r].g0.z, o[r].g0.w,
-                                                  o[r].g1.x, o[r].g1.y, o[r].g1.z, o[r].g1.w};
+                        const unsigned gg[KPX] = {gq[r][0].x, gq[r][0].y, gq[r][0].z, gq[r][0].w,
+                                                  gq[r][1].x, gq[r][1].y, gq[r][1].z, gq[r][1].w};
                         const unsigned mm[KPX] = {o[r].m0.x, o[r].m0.y, o[r].m0.z, o[r].m0.w,
                                                   o[r].m1.x, o[r].m1.y, o[r].m1.z, o[r].m1.w};
 #pragma unroll
@@ -330,9 +332,9 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                     tm_wait_ld();  // pold is in registers; the slots may be overwritten
 #pragma unroll
                     for (int r = 0; r < ROWS; r++) {
-                        const unsigned gg[KPX] = {o[r].g0.x, o[r].g0.y, o[r].g0.z, o[r].g0.w,
-                                                  o[r].g1.x, o[r].g1.y, o[r].g1.z, o[r].g1.w};
-                        const unsigned io[4] = {o[r].io.x, o[r].io.y, o[r].io.z, o[r].io.w};
+                        const unsigned gg[KPX] = {gq[r][0].x, gq[r][0].y, gq[r][0].z, gq[r][0].w,
+                                                  gq[r][1].x, gq[r][1].y, gq[r][1].z, gq[r][1].w};
+                        const unsigned io[4] = {ioq[r].x, ioq[r].y, ioq[r].z, ioq[r].w};
                         // the ring holds -P: the window update is then P + (-P_old) in packed half
                         // (exact, |.| <= 2^11) and the f16 x f16 + f32 forms FHADD / FHFMA of sm_100
                         // fold every half -> float conversion into the accumulation
@@ -370,12 +372,16 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                     iter(opsA, opsB, it);
                     copy_ops(opsA, opsB);
                 }
+            } else {
+                for (int it = 0; it < niter; it++) {  // a pair without a disparity still releases its share of the ring
+                    slot_wait(g * niter + it);
+                    slot_release(g * niter + it, 0u);
+                }
             }
             __syncthreads();  // group end
         }
     } else if (stage == 1) {
         // ====== STAGE 1: a, b; their vertical window sums; horizontal sums of a ======
-        const float2* __restrict__ st = A.st[view];
         float rx[KPX];  // 1 / clipped window width, 0 outside the image
 #pragma unroll
         for (int j = 0; j < KPX; j++) {
@@ -383,6 +389,30 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
             int ax = min(A.w - 1, x + RAD) - max(0, x - RAD) + 1;
             rx[j] = (x >= 0 && x < A.w) ? __frcp_rn((float)ax) : 0.0f;
         }
+        // Operand ring, producer side: the stage-1 warp of pair 0 (always active) fills the slot of iteration
+        // K + LOAD_AHEAD, for the whole block, while it works on K: 4 bulk copies of the strip-tiled guide planes.
+        const int Ktotal = ngroups * niter;
+        int fillK = 0, fill_it = 0;  // next iteration to fill, and its row iteration inside its group
+        auto fill_next = [&]() {
+            if (fillK >= Ktotal) return;
+            const int sl = fillK & (NS - 1);
+            if (fillK >= NS) mbar_wait(mb_sempty + 8 * sl, (unsigned)(fillK / NS - 1) & 1u);  // all 12 warps released it
+            if (lane == 0) {
+                const uint32_t full = mb_sfull + 8 * sl;
+                const uint32_t dst = smem_addr(&sm.slot[0]) + (uint32_t)sl * SLOT_BYTES;
+                const long long rec = (long long)strip * A.rows_pad + PADY + y_first + fill_it * ROWS;  // record of row yi0
+                mbar_expect_tx(full, SLOT_BYTES);
+                bulk_g2s(dst + OFF_G, A.Tg[view] + rec * 64, ROWS * 1024, full);
+                bulk_g2s(dst + OFF_IO, A.TI[view] + (rec - WIN) * 32, ROWS * 512, full);
+                bulk_g2s(dst + OFF_IQ, A.TI[view] + (rec - 2 * RAD) * 32, ROWS * 512, full);
+                bulk_g2s(dst + OFF_ST, A.Tst[view] + (rec - RAD) * 128, ROWS * 2048, full);
+            }
+            __syncwarp();
+            fillK++;
+            fill_it = (fill_it + 1 == niter) ? 0 : fill_it + 1;
+        };
+        if (pair == 0)
+            for (int i = 0; i < LOAD_AHEAD; i++) fill_next();
         for (int g = 0; g < ngroups; g++) {
             const int dk = g * NWARP + pair;
             const bool active = dk < dcnt;
@@ -394,26 +424,23 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
             __syncthreads();  // group start
 
             int slot = 0;
-            ConsPtrs rp;
-            rp.st = st + (long long)(y_first - RAD) * pitch + xl;
-            ConsOps opsA[ROWS], opsB[ROWS];
-            if (active) {
-#pragma unroll
-                for (int r = 0; r < ROWS; r++) {
-                    load_cons(opsA[r], rp, 0);
-                    rp.st += pitch;
-                }
-            }
-            auto iter = [&](auto emit_tag, const ConsOps (&o)[ROWS], ConsOps (&nxt)[ROWS], int it) {
+            auto iter = [&](auto emit_tag, int it) {
                 constexpr bool EMIT = decltype(emit_tag)::value;
-                int dep = 0;
+                if (pair == 0) fill_next();
+                // (mean_I, c2) of rows ya from the shared-memory ring
+                uint4 sq[ROWS][4];
+                {
+                    const int K = g * niter + it;
+                    const uint32_t sa = slot_wait(K);
+                    unsigned t = 0;
 #pragma unroll
-                for (int r = 0; r < ROWS; r++) dep |= touch(o[r]);
-                dep &= zero;
+                    for (int r = 0; r < ROWS; r++)
 #pragma unroll
-                for (int r = 0; r < ROWS; r++) {
-                    load_cons(nxt[r], rp, dep);
-                    rp.st += pitch;
+                        for (int c = 0; c < 4; c++) {
+                            sq[r][c] = lds128(sa + OFF_ST + (r * 4 + c) * 512);
+                            t |= sq[r][c].x;
+                        }
+                    slot_release(K, t);
                 }
                 const int yi0 = y_first + it * ROWS;
                 float ry1[ROWS];
@@ -442,12 +469,12 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
 #pragma unroll
                 for (int r = 0; r < ROWS; r++) {
                     // ---- a, b at row ya = yi - 9
-                    const float stt[16] = {o[r].s0.x, o[r].s0.y, o[r].s0.z, o[r].s0.w, o[r].s1.x, o[r].s1.y, o[r].s1.z, o[r].s1.w,
-                                           o[r].s2.x, o[r].s2.y, o[r].s2.z, o[r].s2.w, o[r].s3.x, o[r].s3.y, o[r].s3.z, o[r].s3.w};
+                    const unsigned stt[16] = {sq[r][0].x, sq[r][0].y, sq[r][0].z, sq[r][0].w, sq[r][1].x, sq[r][1].y, sq[r][1].z, sq[r][1].w,
+                                              sq[r][2].x, sq[r][2].y, sq[r][2].z, sq[r][2].w, sq[r][3].x, sq[r][3].y, sq[r][3].z, sq[r][3].w};
                     float a[KPX], b[KPX];
 #pragma unroll
                     for (int j = 0; j < KPX; j++) {
-                        const float mI = stt[2 * j], c2 = stt[2 * j + 1];
+                        const float mI = __uint_as_float(stt[2 * j]), c2 = __uint_as_float(stt[2 * j + 1]);
                         float cov = fmaf(-mI, SP[r][j], SIP[r][j]);
                         a[j] = cov * c2;
                         float mp = SP[r][j] * (rx[j] * ry1[r]);
@@ -482,21 +509,19 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
             if (active) {
                 int it = 0;
 #pragma unroll 1
-                for (; it < WARM_IT; it++) {
-                    iter(std::false_type{}, opsA, opsB, it);
-                    copy_ops(opsA, opsB);
-                }
+                for (; it < WARM_IT; it++) iter(std::false_type{}, it);
 #pragma unroll 1
-                for (; it < niter; it++) {
-                    iter(std::true_type{}, opsA, opsB, it);
-                    copy_ops(opsA, opsB);
+                for (; it < niter; it++) iter(std::true_type{}, it);
+            } else {
+                for (int it = 0; it < niter; it++) {  // (never pair 0, which fills the ring)
+                    slot_wait(g * niter + it);
+                    slot_release(g * niter + it, 0u);
                 }
             }
             __syncthreads();  // group end
         }
     } else {
         // ====== STAGE 2: horizontal sums of b, q = mean_a * I + mean_b, merge of the 4 disparities ======
-        const __half* __restrict__ Ih = A.Ih[view];
         float rx[KPX];
 #pragma unroll
         for (int j = 0; j < KPX; j++) {
@@ -576,24 +601,26 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                         for (int v = 0; v < 2; v++) sm.qbuf[b][pair][r][v][lane] = make_float4(inf, inf, inf, inf);
             }
             __syncthreads();  // group start
+            // the warm-up iterations only release this warp's share of the operand ring
+            for (int it = 0; it < WARM_IT; it++) {
+                slot_wait(g * niter + it);
+                slot_release(g * niter + it, 0u);
+            }
             if (active) {
-                const __half* piq = Ih + (long long)yb0 * pitch + xl;  // row yq = yb0 + e*ROWS + r
-                uint4 iqA[ROWS], iqB[ROWS];
-#pragma unroll
-                for (int r = 0; r < ROWS; r++) {
-                    iqA[r] = ld_early_v4(piq);
-                    piq += pitch;
-                }
 #pragma unroll 1
                 for (int e = 0; e < n_emit; e++) {
-                    int dep = 0;
+                    // I at the output rows yq = yb0 + e*ROWS + r, from the shared-memory ring
+                    uint4 iqA[ROWS];
+                    {
+                        const int K = g * niter + WARM_IT + e;
+                        const uint32_t sa = slot_wait(K);
+                        unsigned t = 0;
 #pragma unroll
-                    for (int r = 0; r < ROWS; r++) dep |= (int)iqA[r].x;
-                    dep &= zero;
-#pragma unroll
-                    for (int r = 0; r < ROWS; r++) {
-                        iqB[r] = ld_early_v4(piq + dep);
-                        piq += pitch;
+                        for (int r = 0; r < ROWS; r++) {
+                            iqA[r] = lds128(sa + OFF_IQ + r * 512);
+                            t |= iqA[r].x;
+                        }
+                        slot_release(K, t);
                     }
                     const int em = e - MLAG;
                     Best pb[ROWS];
@@ -627,12 +654,12 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                     __syncwarp();
                     if (lane == 0) mbar_arrive(mb_qfull + 8 * qb);
                     if (em >= 0) merge(em, pb);
-#pragma unroll
-                    for (int r = 0; r < ROWS; r++) iqA[r] = late_mov(iqB[r]);
                 }
             } else {
                 // no disparity for this pair in the (last, partial) group: its slots hold +inf
                 for (int e = 0; e < n_emit; e++) {
+                    slot_wait(g * niter + WARM_IT + e);
+                    slot_release(g * niter + WARM_IT + e, 0u);
                     const int E = g * n_emit + e;
                     const int qb = E & (NQ - 1);
                     if (E >= NQ) mbar_wait(mb_qempty + 8 * qb, (unsigned)(E / NQ - 1) & 1u);
@@ -696,8 +723,12 @@ struct PrepArgs {
     int w, h_held, y_global0, frame_h;
     unsigned* IG;
     size_t shift_stride;  // != 0: also write the copies moved left by 1..3 elements at IG + s*shift_stride
-    float* If;
+    float* If;            // optional linear planes (not used by the gray fused kernel)
     float2* st;
+    unsigned* Tg;         // optional strip-tiled planes (FusedArgs): (I,G) words, I halfs, (mean_I, c2) pairs
+    __half* TI;
+    float2* Tst;
+    int n_strips, rows_pad;
     uint8_t* mean_u8;  // optional, held rows pitch w
     int pitch, padx;   // padded planes: rows [-PADY, h_held+PADY), cols [-padx, pitch-padx)
     double eps;
@@ -710,6 +741,26 @@ __device__ __forceinline__ void store_ig(const PrepArgs& P, size_t o, unsigned v
 #pragma unroll
         for (int s = 1; s < 4; s++)
             if (o >= (size_t)s) P.IG[s * P.shift_stride + o - s] = v;
+    }
+}
+
+// One pixel of the padded frame into the strip-tiled planes.  Strip s covers columns [216 s - 20, 216 s + 236); the
+// 40 columns two strips share are stored in both.  Inside a record the 256 columns are laid out as
+// [16-byte chunk c][lane][16 B] with column = 8*lane + j: the c-th 128-bit load of lane L is uint4 c*32 + L.
+__device__ __forceinline__ void store_tiled(const PrepArgs& P, int x, int yrow, unsigned ig, __half ih, float2 st) {
+    const int xa = x + HALO;
+    if (xa < 0) return;
+    const int s1 = xa / VALID_W;
+    const int c1 = xa - s1 * VALID_W;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int s = s1 - k, cl = c1 + k * VALID_W;
+        if (s < 0 || s >= P.n_strips || cl >= SW) continue;
+        const size_t rec = (size_t)s * P.rows_pad + yrow;
+        const int L = cl >> 3, j = cl & 7;
+        P.Tg[(rec * 64 + (j >> 2) * 32 + L) * 4 + (j & 3)] = ig;
+        P.TI[(rec * 32 + L) * 8 + j] = ih;
+        P.Tst[(rec * 128 + (j >> 1) * 32 + L) * 2 + (j & 1)] = st;
     }
 }
 
@@ -753,8 +804,9 @@ __global__ void __launch_bounds__(256) k_prep(const PrepArgs P) {
         if (!in) {
             __half2 pad = __floats2half2_rn(1024.0f, 1024.0f);
             store_ig(P, o, *reinterpret_cast<unsigned*>(&pad));
-            reinterpret_cast<__half*>(P.If)[o + 4] = __float2half(0.0f);
-            P.st[o] = make_float2(0.0f, 0.0f);
+            if (P.If) reinterpret_cast<__half*>(P.If)[o + 4] = __float2half(0.0f);
+            if (P.st) P.st[o] = make_float2(0.0f, 0.0f);
+            if (P.Tg) store_tiled(P, x, y + PADY, *reinterpret_cast<unsigned*>(&pad), __float2half(0.0f), make_float2(0.0f, 0.0f));
             continue;
         }
         int s1 = 0, s2 = 0;
@@ -776,8 +828,10 @@ __global__ void __launch_bounds__(256) k_prep(const PrepArgs P) {
         int ir = (x + 1 < P.w) ? sI[ty + RAD][tx + RAD + 1] : ic;
         __half2 ig = __floats2half2_rn((float)ic, (float)(il - ir));
         store_ig(P, o, *reinterpret_cast<unsigned*>(&ig));
-        reinterpret_cast<__half*>(P.If)[o + 4] = __float2half((float)ic);
-        P.st[o] = make_float2(mI, __fmul_rn(c, rxy));
+        const float2 stv = make_float2(mI, __fmul_rn(c, rxy));
+        if (P.If) reinterpret_cast<__half*>(P.If)[o + 4] = __float2half((float)ic);
+        if (P.st) P.st[o] = stv;
+        if (P.Tg) store_tiled(P, x, y + PADY, *reinterpret_cast<unsigned*>(&ig), __float2half((float)ic), stv);
         if (P.mean_u8) {
             int m = (int)mI;
             P.mean_u8[(size_t)y * P.w + x] = (m > 255) ? 255 : (unsigned char)m;
@@ -799,15 +853,16 @@ size_t sbf_workspace_bytes(const sb200_ctx* ctx, int w, int h_held, int rows_out
     const int pitchS = (w + 3) / 4 * 4;
     Plan plan = make_plan(w, rows_out, size_d, ctx->sm_count, n_views);
     size_t bytes = 0;
+    const size_t recs = (size_t)plan.n_strips * (h_held + 2 * PADY);
     bytes += 2 * sb_align(plane * 4 * 4);  // IG x2, 4 shifted copies each
-    bytes += 2 * sb_align(plane * 4);      // If x2
-    bytes += 2 * sb_align(plane * 8);      // st x2
+    bytes += 2 * (sb_align(recs * 1024) + sb_align(recs * 512) + sb_align(recs * 2048));  // strip-tiled Tg, TI, Tst x2
     bytes += sb_align((size_t)plan.n_chunks * 2 * rows_out * pitchS * 8);  // BL
     return bytes + 4096;
 }
 
 static int launch_prep(sb200_ctx* ctx, const sb200_params* p, const uint8_t* gray, const SbFusedGeom& g, int pitch, int padx,
-                       float S, unsigned* IG, size_t shift_stride, float* If, float2* st, uint8_t* mean) {
+                       float S, unsigned* IG, size_t shift_stride, float* If, float2* st, uint8_t* mean, unsigned* Tg = nullptr,
+                       __half* TI = nullptr, float2* Tst = nullptr, int n_strips = 0) {
     PrepArgs P;
     P.gray = gray;
     P.w = g.w;
@@ -818,6 +873,11 @@ static int launch_prep(sb200_ctx* ctx, const sb200_params* p, const uint8_t* gra
     P.shift_stride = shift_stride;
     P.If = If;
     P.st = st;
+    P.Tg = Tg;
+    P.TI = TI;
+    P.Tst = Tst;
+    P.n_strips = n_strips;
+    P.rows_pad = g.h + 2 * PADY;
     P.mean_u8 = mean;
     P.pitch = pitch;
     P.padx = padx;
@@ -858,31 +918,37 @@ static int run_fused(sb200_ctx* ctx, const sb200_params* p, const uint8_t* const
     Plan plan = make_plan(g.w, g.rows_out, size_d, ctx->sm_count, n_views);
 
     unsigned* IG[2];
-    float* If[2];
-    float2* st[2];
+    unsigned* Tg[2];
+    __half* TI[2];
+    float2* Tst[2];
+    const size_t recs = (size_t)plan.n_strips * rows_pad;
     for (int i = 0; i < 2; i++) {
         IG[i] = sb_ws_alloc<unsigned>(ctx, 4 * plane);
-        If[i] = sb_ws_alloc<float>(ctx, plane);
-        st[i] = sb_ws_alloc<float2>(ctx, plane);
+        Tg[i] = sb_ws_alloc<unsigned>(ctx, recs * 256);
+        TI[i] = sb_ws_alloc<__half>(ctx, recs * 256);
+        Tst[i] = sb_ws_alloc<float2>(ctx, recs * 256);
     }
     const size_t planeS = (size_t)g.rows_out * pitchS;
     float2* BL = sb_ws_alloc<float2>(ctx, planeS * 2 * plan.n_chunks);
-    if (!IG[0] || !IG[1] || !If[0] || !If[1] || !st[0] || !st[1] || !BL)
+    if (!IG[0] || !IG[1] || !Tg[0] || !Tg[1] || !TI[0] || !TI[1] || !Tst[0] || !Tst[1] || !BL)
         return sb_fail(ctx, SB200_ERR_NOMEM, "fused: workspace arena too small (internal)");
 
     if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-    for (int i = 0; i < 2; i++) SB_TRY(launch_prep(ctx, p, gray[i], g, pitch, padx, (float)S, IG[i], plane, If[i], st[i], mean[i]));
+    for (int i = 0; i < 2; i++) SB_TRY(launch_prep(ctx, p, gray[i], g, pitch, padx, (float)S, IG[i], plane, nullptr, nullptr, mean[i], Tg[i], TI[i], Tst[i],
+                           plan.n_strips));
     if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
 
     FusedArgs A;
     const size_t origin = (size_t)PADY * pitch + padx;
     for (int i = 0; i < 2; i++) {
         A.IG[i] = IG[i] + origin;
-        A.Ih[i] = reinterpret_cast<const __half*>(If[i]) + origin + 4;
-        A.st[i] = st[i] + origin;
+        A.Tg[i] = reinterpret_cast<const uint4*>(Tg[i]);
+        A.TI[i] = reinterpret_cast<const uint4*>(TI[i]);
+        A.Tst[i] = reinterpret_cast<const uint4*>(Tst[i]);
         A.dmin[i] = dmin[i];
     }
     A.shift_stride = plane;
+    A.rows_pad = rows_pad;
     A.pitch = pitch;
     A.w = g.w;
     A.y_out0 = g.y_out0;
