@@ -67,6 +67,7 @@ struct FusedArgs {
 
 constexpr int K3_THREADS = 3 * NWARP * 32;  // three pipeline stages (warps p, p+4, p+8) per disparity
 constexpr uint32_t TM_HAND2 = 416;          // TMEM columns [416,448): stage 1 -> stage 2 hand-off rows
+constexpr int HS1_ROWS = 1;  // rows of an iteration whose horizontal sums of b are taken in stage 1 (the rest: stage 2)
 constexpr int NQ = 4;     // depth of the ring of filtered rows between the consumer and the merging warps
 constexpr int MLAG = 2;   // a producer merges the rows its consumer emitted MLAG iterations ago
 constexpr int NS = 16;        // slots of the operand ring (one per pipeline iteration)
@@ -236,9 +237,8 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
         mbar_wait(mb_sfull + 8 * (K & (NS - 1)), (unsigned)(K / NS) & 1u);
         return slot0 + (uint32_t)(K & (NS - 1)) * SLOT_BYTES;
     };
-    auto slot_release = [&](int K, unsigned t) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(mb_sempty + 8 * (K & (NS - 1)) + (t & (unsigned)zero));
+    auto slot_release = [&](int K, unsigned t) {  // (a warp-wide load returns for all lanes at once: lane 0's word is enough)
+        mbar_arrive_lane0(mb_sempty + 8 * (K & (NS - 1)) + (t & (unsigned)zero), lane);
     };
     constexpr uint32_t OFF_G = offsetof(Slot, g), OFF_IO = offsetof(Slot, io), OFF_IQ = offsetof(Slot, iq),
                        OFF_ST = offsetof(Slot, st);
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
             __syncthreads();  // group end
         }
     } else if (stage == 1) {
-        // ====== STAGE 1: a, b; their vertical window sums; horizontal sums of a ======
+        // ====== STAGE 1: a, b; their vertical and horizontal window sums ======
         float rx[KPX];  // 1 / clipped window width, 0 outside the image
 #pragma unroll
         for (int j = 0; j < KPX; j++) {
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                     tm_fence_before();
                     named_bar_arrive(BAR_EMPTY, 64);
                 }
-                float SA[ROWS][KPX], VB[ROWS][KPX];
+                float SA[ROWS][KPX], SB[ROWS][KPX];
 #pragma unroll
                 for (int r = 0; r < ROWS; r++) {
                     // ---- a, b at row ya = yi - 9
@@ -486,9 +486,18 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                     for (int j = 0; j < KPX; j++) {
                         Va[j] += a[j] - ao[r][j];
                         Vb[j] += b[j] - bo[r][j];
-                        if (EMIT) VB[r][j] = Vb[j];
                     }
-                    if (EMIT) hsum19(Va, SA[r]);
+                    if (EMIT) {
+                        hsum19(Va, SA[r]);
+                        // balance of the pipeline: the horizontal sums of b are taken here for the rows below
+                        // HS1_ROWS and in stage 2 for the others
+                        if (r < HS1_ROWS) {
+                            hsum19(Vb, SB[r]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < KPX; j++) SB[r][j] = Vb[j];
+                        }
+                    }
                 }
                 if (EMIT) {
                     const int E = g * n_emit + (it - WARM_IT);
@@ -497,11 +506,11 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                         tm_fence_after();
                     }
 #pragma unroll
-                    for (int r = 0; r < ROWS; r++) tm_st16(tH2 + 16 * r, SA[r], VB[r]);
+                    for (int r = 0; r < ROWS; r++) tm_st16(tH2 + 16 * r, SA[r], SB[r]);
                     tm_wait_st();  // (also: this iteration's ring stores are complete before the next loads)
                     tm_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(mb_full2);
+                    mbar_arrive_lane0(mb_full2, lane);
                 } else {
                     tm_wait_st();
                 }
@@ -521,7 +530,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
             __syncthreads();  // group end
         }
     } else {
-        // ====== STAGE 2: horizontal sums of b, q = mean_a * I + mean_b, merge of the 4 disparities ======
+        // ====== STAGE 2: q = mean_a * I + mean_b, merge of the 4 disparities ======
         float rx[KPX];
 #pragma unroll
         for (int j = 0; j < KPX; j++) {
@@ -538,6 +547,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
         const int qoff = (((mc & 7) >> 2) * 32 + (mc >> 3)) * 4 + (mc & 3);
         const size_t planeS = (size_t)A.rows_out * A.pitchS;
         float2* __restrict__ BL = A.BL + (size_t)(chunk * 2 + view) * planeS;
+        const size_t bl_row = (size_t)A.pitchS / 2;  // 16-byte units per row of the plane (pitchS is a multiple of 4)
         for (int g = 0; g < ngroups; g++) {
             const int dk = g * NWARP + pair;
             const bool active = dk < dcnt;
@@ -545,12 +555,15 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
             const float lab[NWARP] = {(float)dbase, (float)(dbase + 1), (float)(dbase + 2), (float)(dbase + 3)};
             typedef float4 Best;  // (best, label) of columns mx and mx+1
             // running (best,label) of the rows of emission e, from the previous groups of this chunk
-            auto prefetch_best = [&](int e, Best (&pb)[ROWS]) {
+            // merge cursor: the emissions are merged in order, so the rows of the next one to merge are at blp
+            float4* blp = reinterpret_cast<float4*>(BL + (size_t)(yb0 - A.y_out0) * A.pitchS + mx);
+            int mrows = yb1 - yb0;  // rows of the band not merged yet
+            const bool ld_ok = (g > 0) && mvalid;
+            auto prefetch_best = [&](Best (&pb)[ROWS]) {
 #pragma unroll
                 for (int r = 0; r < ROWS; r++) {
                     pb[r] = make_float4(BEST_INIT_BITS_F, 0.0f, BEST_INIT_BITS_F, 0.0f);
-                    const int yq = yb0 + e * ROWS + r;
-                    if (g > 0 && yq < yb1 && mvalid) pb[r] = ld_early_f4(BL + (size_t)(yq - A.y_out0) * A.pitchS + mx);
+                    if (ld_ok && r < mrows) pb[r] = ld_early_f4(blp + r * bl_row);
                 }
             };
             // fold the 4 disparities of this group into (best,label): ascending d, `>=` (last slice wins ties)
@@ -560,7 +573,6 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                 mbar_wait(mb_qfull + 8 * qb, (unsigned)(E / NQ) & 1u);
 #pragma unroll
                 for (int r = 0; r < ROWS; r++) {
-                    const int yq = yb0 + e * ROWS + r;
                     const float* qp = reinterpret_cast<const float*>(&sm.qbuf[qb][0][r][0][0]);
                     float b0 = pb[r].x, l0 = pb[r].y, b1 = pb[r].z, l1 = pb[r].w;
                     float2 qv[NWARP];
@@ -585,11 +597,12 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                         const float m = t ? m23 : m01, a = t ? a23 : a01;
                         if (b1 >= m) { b1 = m; l1 = a; }
                     }
-                    if (yq < yb1 && mvalid)
-                        *reinterpret_cast<float4*>(BL + (size_t)(yq - A.y_out0) * A.pitchS + mx) = make_float4(b0, l0, b1, l1);
+                    if (mvalid && r < mrows) blp[r * bl_row] = make_float4(b0, l0, b1, l1);
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(mb_qempty + 8 * qb);
+                mbar_arrive_lane0(mb_qempty + 8 * qb, lane);
+                blp += ROWS * bl_row;
+                mrows -= ROWS;
             };
             if (!active) {  // the previous group's merges have drained (group-end barrier)
                 const float inf = __int_as_float(0x7f800000);
@@ -624,35 +637,39 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                     }
                     const int em = e - MLAG;
                     Best pb[ROWS];
-                    if (em >= 0) prefetch_best(em, pb);
+                    if (em >= 0) prefetch_best(pb);
                     const int E = g * n_emit + e;
                     mbar_wait(mb_full2, (unsigned)E & 1u);  // stage 1 has published this emission
                     tm_fence_after();
-                    float SA[ROWS][KPX], VB[ROWS][KPX];
+                    float SA[ROWS][KPX], SB[ROWS][KPX];
 #pragma unroll
-                    for (int r = 0; r < ROWS; r++) tm_ld16(tH2 + 16 * r, SA[r], VB[r]);
+                    for (int r = 0; r < ROWS; r++) tm_ld16(tH2 + 16 * r, SA[r], SB[r]);
                     tm_wait_ld();
                     tm_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(mb_empty2);
+                    mbar_arrive_lane0(mb_empty2, lane);
                     const int qb = E & (NQ - 1);
                     if (E >= NQ) mbar_wait(mb_qempty + 8 * qb, (unsigned)(E / NQ - 1) & 1u);  // merged NQ emissions ago
 #pragma unroll
                     for (int r = 0; r < ROWS; r++) {
-                        float SB[KPX];
-                        hsum19(VB[r], SB);
+                        if (r >= HS1_ROWS) {
+                            float hb[KPX];
+                            hsum19(SB[r], hb);
+#pragma unroll
+                            for (int j = 0; j < KPX; j++) SB[r][j] = hb[j];
+                        }
                         const float ry2 = inv_rows(sm.ry_lut[1], yb0 + e * ROWS + r, A.y_global0, A.frame_h);
                         const float2 iq01 = __half22float2(u2h2(iqA[r].x)), iq23 = __half22float2(u2h2(iqA[r].y));
                         const float2 iq45 = __half22float2(u2h2(iqA[r].z)), iq67 = __half22float2(u2h2(iqA[r].w));
                         const float iq[KPX] = {iq01.x, iq01.y, iq23.x, iq23.y, iq45.x, iq45.y, iq67.x, iq67.y};
                         float q[KPX];
 #pragma unroll
-                        for (int j = 0; j < KPX; j++) q[j] = fmaf(SA[r][j], iq[j], SB[j]) * (rx[j] * ry2);
+                        for (int j = 0; j < KPX; j++) q[j] = fmaf(SA[r][j], iq[j], SB[r][j]) * (rx[j] * ry2);
                         sm.qbuf[qb][pair][r][0][lane] = make_float4(q[0], q[1], q[2], q[3]);
                         sm.qbuf[qb][pair][r][1][lane] = make_float4(q[4], q[5], q[6], q[7]);
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(mb_qfull + 8 * qb);
+                    mbar_arrive_lane0(mb_qfull + 8 * qb, lane);
                     if (em >= 0) merge(em, pb);
                 }
             } else {
@@ -665,7 +682,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                     if (E >= NQ) mbar_wait(mb_qempty + 8 * qb, (unsigned)(E / NQ - 1) & 1u);
                     if (lane == 0) mbar_arrive(mb_qfull + 8 * qb);
                     Best pb[ROWS];
-                    prefetch_best(e, pb);
+                    prefetch_best(pb);
                     merge(e, pb);
                 }
             }
@@ -674,7 +691,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
 #pragma unroll 1
                 for (int e = max(0, n_emit - MLAG); e < n_emit; e++) {
                     Best pb[ROWS];
-                    prefetch_best(e, pb);
+                    prefetch_best(pb);
                     merge(e, pb);
                 }
             }

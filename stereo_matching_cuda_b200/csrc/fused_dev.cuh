@@ -36,6 +36,17 @@ __device__ __forceinline__ void mbar_init(uint32_t b, unsigned count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t b) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(b) : "memory");
 }
+// arrive from lane 0 only, predicated instead of branched (the warp must be converged)
+__device__ __forceinline__ void mbar_arrive_lane0(uint32_t b, int lane) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.eq.s32 p, %1, 0;\n"
+        "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n"
+        "}\n" ::"r"(b),
+        "r"(lane)
+        : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t b, unsigned parity) {
     asm volatile(
         "{\n"
