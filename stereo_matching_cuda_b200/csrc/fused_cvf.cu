@@ -66,7 +66,7 @@ struct FusedArgs {
 };
 
 constexpr int K3_THREADS = 3 * NWARP * 32;  // three pipeline stages (warps p, p+4, p+8) per disparity
-constexpr uint32_t TM_HAND2 = 416;          // TMEM columns [416,448): stage 1 -> stage 2 hand-off rows
+constexpr uint32_t TM_HAND2 = 416;          // TMEM columns [416,480): stage 1 -> stage 2 hand-off rows, 2 slots
 constexpr int HS1_ROWS = 1;  // rows of an iteration whose horizontal sums of b are taken in stage 1 (the rest: stage 2)
 constexpr int NQ = 4;     // depth of the ring of filtered rows between the consumer and the merging warps
 constexpr int MLAG = 2;   // a producer merges the rows its consumer emitted MLAG iterations ago
@@ -84,7 +84,7 @@ struct SmemLayout {
     uint64_t sfull[NS], sempty[NS];       // mbarriers of the operand ring: bulk copies -> 12 warps and back
     float4 qbuf[NQ][NWARP][ROWS][2][32];  // filtered rows of each consumer warp
     uint64_t qfull[NQ], qempty[NQ];       // mbarriers of the q ring (4 stage-2 warps write, the same 4 warps merge)
-    uint64_t full2[NWARP], empty2[NWARP]; // mbarriers of the stage 1 -> stage 2 hand-off of each pair
+    uint64_t full2[NWARP][2], empty2[NWARP][2];  // mbarriers of the 2-slot stage 1 -> stage 2 hand-off of each pair
     float ry_lut[2][WIN + 1];             // [0][n] = 1/(S*n), [1][n] = 1/n for a clipped window of n rows; [.][0] = 0
     uint32_t tmem_base;
 };
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
     // Tensor Memory: all 512 columns of the SM, one block per SM (register-limited)
     if (warp == 0) tm_alloc(&sm.tmem_base);
     const uint32_t mb_qfull = smem_addr(&sm.qfull[0]), mb_qempty = smem_addr(&sm.qempty[0]);
-    const uint32_t mb_full2 = smem_addr(&sm.full2[pair]), mb_empty2 = smem_addr(&sm.empty2[pair]);
+    const uint32_t mb_full2 = smem_addr(&sm.full2[pair][0]), mb_empty2 = smem_addr(&sm.empty2[pair][0]);
     const uint32_t mb_sfull = smem_addr(&sm.sfull[0]), mb_sempty = smem_addr(&sm.sempty[0]);
     const uint32_t slot0 = smem_addr(&sm.slot[0]) + 16 * lane;  // this lane's 16 bytes of a slot's chunk 0
     static_assert((NS & (NS - 1)) == 0, "slot index and phase are taken from the bits of the iteration counter");
@@ -216,8 +216,10 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
         }
 #pragma unroll
         for (int b = 0; b < NWARP; b++) {
-            mbar_init(smem_addr(&sm.full2[b]), 1);
-            mbar_init(smem_addr(&sm.empty2[b]), 1);
+            for (int k = 0; k < 2; k++) {
+                mbar_init(smem_addr(&sm.full2[b][k]), 1);
+                mbar_init(smem_addr(&sm.empty2[b][k]), 1);
+            }
         }
     }
     if (threadIdx.x >= 64 && threadIdx.x < 64 + 2 * (WIN + 1)) {
@@ -501,16 +503,16 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                 }
                 if (EMIT) {
                     const int E = g * n_emit + (it - WARM_IT);
-                    if (E > 0) {  // stage 2 has copied the previous rows out of its hand-off columns
-                        mbar_wait(mb_empty2, (unsigned)(E - 1) & 1u);
+                    if (E > 1) {  // stage 2 has copied the rows of emission E-2 out of this hand-off slot
+                        mbar_wait(mb_empty2 + 8 * (E & 1), (unsigned)(E / 2 - 1) & 1u);
                         tm_fence_after();
                     }
 #pragma unroll
-                    for (int r = 0; r < ROWS; r++) tm_st16(tH2 + 16 * r, SA[r], SB[r]);
+                    for (int r = 0; r < ROWS; r++) tm_st16(tH2 + 32 * (E & 1) + 16 * r, SA[r], SB[r]);
                     tm_wait_st();  // (also: this iteration's ring stores are complete before the next loads)
                     tm_fence_before();
                     __syncwarp();
-                    mbar_arrive_lane0(mb_full2, lane);
+                    mbar_arrive_lane0(mb_full2 + 8 * (E & 1), lane);
                 } else {
                     tm_wait_st();
                 }
@@ -639,15 +641,15 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                     Best pb[ROWS];
                     if (em >= 0) prefetch_best(pb);
                     const int E = g * n_emit + e;
-                    mbar_wait(mb_full2, (unsigned)E & 1u);  // stage 1 has published this emission
+                    mbar_wait(mb_full2 + 8 * (E & 1), (unsigned)(E / 2) & 1u);  // stage 1 has published this emission
                     tm_fence_after();
                     float SA[ROWS][KPX], SB[ROWS][KPX];
 #pragma unroll
-                    for (int r = 0; r < ROWS; r++) tm_ld16(tH2 + 16 * r, SA[r], SB[r]);
+                    for (int r = 0; r < ROWS; r++) tm_ld16(tH2 + 32 * (E & 1) + 16 * r, SA[r], SB[r]);
                     tm_wait_ld();
                     tm_fence_before();
                     __syncwarp();
-                    mbar_arrive_lane0(mb_empty2, lane);
+                    mbar_arrive_lane0(mb_empty2 + 8 * (E & 1), lane);
                     const int qb = E & (NQ - 1);
                     if (E >= NQ) mbar_wait(mb_qempty + 8 * qb, (unsigned)(E / NQ - 1) & 1u);  // merged NQ emissions ago
 #pragma unroll
