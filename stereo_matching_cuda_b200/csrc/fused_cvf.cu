@@ -10,29 +10,38 @@
 // Design (DESIGN.md has the long form):
 //  * A warp owns a strip of 256 image columns (8 consecutive pixels per lane) for ONE
 //    disparity and marches down the rows.  Vertical 19-row window sums are running sums in
-//    registers; the value that leaves the window comes from a 19-slot ring in shared memory
-//    that only this warp touches (no block barrier on the filter path).
+//    registers; the values that leave the window come from 19-slot rings in Tensor Memory.
 //  * Horizontal 19-column window sums never go through shared memory: each lane forms the
 //    prefix sums of its 8 pixels and the window is assembled from 16 warp shuffles of
 //    neighbouring lanes' prefixes.  216 of the 256 columns are valid after two cascaded
 //    radius-9 filters (20-column halo each side, kept 4-pixel aligned for 128-bit loads).
 //  * The cost is evaluated on an integer lattice: 20*p = 2*min(|dI|,7) + 9*min(|dG|,4) with
 //    G = 2*gradient, so the first-stage box sums of p and I*p are sums of integers below 2^24
-//    held in fp32 -- exact, order independent, identical on every tiling or GPU split.
-//  * Warp specialisation: a block is 4 PAIRS of warps, one pair per disparity.  The producer
-//    warp of a pair runs the first stage (cost, vertical sums, horizontal sums) and hands the
-//    window sums (S_P, S_IP) of each row to its consumer warp through a 2-slot shared buffer
-//    and a 64-thread named barrier; the consumer runs a/b, the second box filter and q.  The
-//    two warps of a pair sit on the same SM sub-partition, so each hides the other's
-//    shuffle / shared-memory / FP32 dependency latency (round 1 ncu: one warp per scheduler
-//    left 73 % of issue slots empty).
-//  * The 4 consumer warps exchange their filtered row through a 1 KB shared buffer and one
-//    consumer thread per 2 columns folds the 4 disparities into the running (best, label)
-//    with the reference's `best >= q` rule (last slice wins ties).
+//    held in fp32 -- exact, order independent, identical on every tiling or GPU split.  The
+//    half-precision costs enter the fp32 sums through the f16 x f16 + f32 instructions of
+//    sm_100 (FHFMA / FHADD), without conversions.
+//  * Warp specialisation: a block is 4 TRIOS of warps (p, p+4, p+8: same SM sub-partition,
+//    same Tensor-Memory lane quarter), one trio per disparity, a 3-stage pipeline down the rows:
+//      stage 0  cost, vertical sums of P and I*P, their horizontal sums      -> (S_P, S_IP)
+//      stage 1  a, b, their vertical sums, horizontal sums                   -> (S_a, S_b)
+//      stage 2  q = mean_a*I + mean_b, merge of the block's 4 disparities into (best,label)
+//    Rows travel between stages through Tensor-Memory columns (tcgen05.st / tcgen05.ld) guarded
+//    by named barriers (0 -> 1) and mbarriers (1 -> 2, two slots); three warps per scheduler
+//    fill the issue slots one warp left empty (ncu: 27 % -> 44 % -> 58 % issue utilisation for
+//    1, 2, 3 warps per scheduler).
+//  * The guide operands every trio of a block needs -- (I,G), I, (mean_I, c2) of the strip's
+//    rows -- are fetched ONCE per block: one warp issues TMA bulk copies (cp.async.bulk) from
+//    strip-tiled planes into a 16-slot shared-memory ring, one slot (8 KB) per pipeline
+//    iteration, 5 iterations ahead; all 12 warps read their 16-byte chunks conflict-free and
+//    release the slot through an mbarrier.  Only the match operands (per disparity) are read
+//    through L1, as two aligned 128-bit loads from the copy of the (I,G) plane shifted by d&3.
+//  * The stage-2 warps leave their filtered rows in a 4-deep shared-memory ring; two iterations
+//    later each stage-2 thread folds the 4 disparities for 2 columns into the running
+//    (best,label) with the reference's `best >= q` rule (last slice wins ties; a 2-level
+//    tournament, which is the same function), one 16-byte load and store per row.
 //  * Blocks tile (column strip x row band x disparity chunk x view); per-chunk (best,label)
 //    planes are merged in chunk order by a small second kernel.
-// HBM traffic is ~30 B per PIXEL per disparity group read from L2-resident prepared planes;
-// the kernel is bound by the FP32/ALU issue rate and the shuffle/LSU path, not by HBM.
+// The kernel is latency/issue bound (58 % issue, L1TEX data pipe 65 %, DRAM ~20 % of its time).
 #include "fused_dev.cuh"
 
 namespace {
