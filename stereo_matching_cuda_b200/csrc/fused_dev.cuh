@@ -70,7 +70,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t b, unsigned parity) {
 // private scratch; warps p and p+4 (a producer/consumer pair) share a lane quarter, which is
 // what lets the producer hand its rows to the consumer through TMEM.
 // Column map of one lane (512 allocated): [0,304) ring of (a[8],b[8]) x 19 slots,
-// [304,380) ring of the lattice cost (8 halfs = 4 words) x 19 slots, [384,416) hand-off rows.
+// [304,380) ring of the lattice cost (8 halfs = 4 words) x 19 slots, [384,416) hand-off rows
+// (the gray kernel adds [416,480): two slots of rows between its second and third stage).
 constexpr uint32_t TM_COLS = 512;
 constexpr uint32_t TM_RING_AB = 0, TM_RING_P = 304, TM_HAND = 384;
 
