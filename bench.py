@@ -424,7 +424,7 @@ def main():
         ctx.enable_timing(False)
         ms_rgb = float(tr_ms.item()) / n_rgb
         rgb_extra = {"value": world * 2.0 * w * h * size_d / (ms_rgb * 1e-3), "unit": "px*d/s", "ms_per_step": ms_rgb,
-                     "fps": world / (ms_rgb * 1e-3), "kernel": "k_fused_cvf_rgb", "kernel_ms": k_rgb, "instr_per_cell": 71,
+                     "fps": world / (ms_rgb * 1e-3), "kernel": "k_fused_cvf_rgb3" if ctx.rgb_kernel == 3 else "k_fused_cvf_rgb", "kernel_ms": k_rgb, "instr_per_cell": 71,
                      "roofline_frac": 71 * 2.0 * w * h * size_d / (k_rgb * 1e-3) / (148 * 128 * peaks()["sm_max_mhz"] * 1e6),
                      "note": "colour guided filter of SURVEY A.8 on 3-channel synthetic pairs; not in the reference "
                              "(parity unpinned; checked against the oracle's RGB port and the eps/3 identity)"}
@@ -450,7 +450,7 @@ def main():
                       "WTA planes, several hundred MB at 1080p D=256) exceeds the 126 MB L2",
             },
             "roofline": {
-                "bound": "fp32_pipe", "kernel": "k_fused_cvf" if args.guide == "gray" else "k_fused_cvf_rgb", "achieved": achieved / 1e12, "peak": peak_instr / 1e12,
+                "bound": "fp32_pipe", "kernel": "k_fused_cvf" if args.guide == "gray" else ("k_fused_cvf_rgb3" if ctx.rgb_kernel == 3 else "k_fused_cvf_rgb"), "achieved": achieved / 1e12, "peak": peak_instr / 1e12,
                 "unit": "T lane-instr/s", "frac": achieved / peak_instr,
                 "traffic": tr.get("dram_bytes_per_launch") if tr and mode == "dp" and args.workload == "c3" else None,
                 "traffic_src": tr.get("src") if tr and mode == "dp" and args.workload == "c3" else None,

@@ -83,6 +83,7 @@ def load_library(path=None):
         "sb200_ctx_synchronize": (ip, [vp]),
         "sb200_last_error": (C.c_char_p, [vp]),
         "sb200_launch_count": (C.c_uint64, [vp]),
+        "sb200_ctx_rgb_kernel": (ip, [vp]),
         "sb200_version": (C.c_char_p, []),
         "sb200_rgb_to_grayscale": (ip, [vp, PP, vp, ip, ip, vp]),
         "sb200_compute_cost": (ip, [vp, PP, vp, vp, vp, ip, ip, ip, ip, ip]),
@@ -197,6 +198,11 @@ class Context:
     @property
     def launch_count(self):
         return int(self.lib.sb200_launch_count(self.h))
+
+    @property
+    def rgb_kernel(self):
+        """2: k_fused_cvf_rgb, 3: k_fused_cvf_rgb3 (SB200_RGB_KERNEL overrides the library default)"""
+        return int(self.lib.sb200_ctx_rgb_kernel(self.h))
 
     def enable_timing(self, on=True):
         self._ck(self.lib.sb200_ctx_enable_timing(self.h, int(on)))

@@ -55,6 +55,8 @@ int sb200_ctx_create(int device, sb200_ctx** out) {
     bool ok = true;
     for (int i = 0; i < 5; i++) ok = ok && (cudaEventCreate(&ctx->ev[i]) == cudaSuccess);
     ctx->ev_valid = ok;
+    // A/B switch for the RGB-guide kernel: "2" = two-stage (fused_cvf_rgb.cu), "3" = three-stage (fused_cvf_rgb3.cu)
+    if (const char* e = getenv("SB200_RGB_KERNEL")) ctx->rgb_kernel = (e[0] == '3') ? 3 : (e[0] == '2') ? 2 : ctx->rgb_kernel;
     *out = ctx;
     return SB200_OK;
 }
@@ -84,6 +86,7 @@ int sb200_ctx_synchronize(sb200_ctx* ctx) {
 
 const char* sb200_last_error(const sb200_ctx* ctx) { return ctx ? ctx->err : g_sb200_global_err; }
 uint64_t sb200_launch_count(const sb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int sb200_ctx_rgb_kernel(const sb200_ctx* ctx) { return ctx ? ctx->rgb_kernel : 0; }
 
 int sb200_ctx_enable_timing(sb200_ctx* ctx, int on) {
     if (!ctx) return SB200_ERR_INVALID;
@@ -298,6 +301,11 @@ int check_params(sb200_ctx* ctx, const sb200_params* p) {
     return SB200_OK;
 }
 
+size_t rgb_fused_ws_bytes(const sb200_ctx* ctx, int w, int h_held, int rows_out, int dabs, int size_d) {
+    return ctx->rgb_kernel == 3 ? sbf_rgb3_workspace_bytes(ctx, w, h_held, rows_out, dabs, size_d)
+                                : sbf_rgb_workspace_bytes(ctx, w, h_held, rows_out, dabs, size_d);
+}
+
 // pipeline core on device buffers; `held` geometry for strips
 int pipeline_core(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, const uint8_t* d_right, int channels,
                   int w, const SbFusedGeom& g, const sb200_outputs* o, bool reserve) {
@@ -307,7 +315,7 @@ int pipeline_core(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, 
     const int dabs = max(abs(p->dmin), abs(p->dmax));
     if (reserve) {
         size_t bytes = p->guide_mode != SB200_GUIDE_RGB ? (sbf_fused_supported(p) ? sbf_workspace_bytes(ctx, w, g.h, g.rows_out, dabs, size_d, 2) : gf_ws_bytes(n_held) + 2 * sb_align(n_held))
-                       : (p->box_mode == SB200_BOX_SAT ? rgb_ws_bytes(n_held) : sbf_rgb_workspace_bytes(ctx, w, g.h, g.rows_out, dabs, size_d));
+                       : (p->box_mode == SB200_BOX_SAT ? rgb_ws_bytes(n_held) : rgb_fused_ws_bytes(ctx, w, g.h, g.rows_out, dabs, size_d));
         bytes += 2 * sb_align(n_held) + 4 * sb_align(n_out * 4) + 4096;
         SB_TRY(sb_ws_reserve(ctx, bytes));
     }
@@ -353,7 +361,10 @@ int pipeline_core(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, 
         if (mR) SB_TRY(ws_get(ctx, &mRh, n_held));
     }
     if (rgb_guide && !rgb_staged) {
-        SB_TRY(sbf_pair_disparity_rgb(ctx, p, d_left, d_right, channels, gl, gr, g, o->best_left, dL, o->best_right, dR));
+        if (ctx->rgb_kernel == 3)
+            SB_TRY(sbf_pair_disparity_rgb3(ctx, p, d_left, d_right, channels, gl, gr, g, o->best_left, dL, o->best_right, dR));
+        else
+            SB_TRY(sbf_pair_disparity_rgb(ctx, p, d_left, d_right, channels, gl, gr, g, o->best_left, dL, o->best_right, dR));
     } else if (rgb_guide) {
         float *bL = o->best_left, *bR = o->best_right;
         if (!bL) SB_TRY(ws_get(ctx, &bL, n_out));
@@ -542,7 +553,7 @@ int sb200_pipeline(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h_left,
     const int size_d = p->dmax - p->dmin + 1;
     const int dabs = max(abs(p->dmin), abs(p->dmax));
     size_t bytes = (p->guide_mode != SB200_GUIDE_RGB ? (sbf_fused_supported(p) ? sbf_workspace_bytes(ctx, w, h, h, dabs, size_d, 2) : gf_ws_bytes(n) + 2 * sb_align(n))
-                    : (p->box_mode == SB200_BOX_SAT ? rgb_ws_bytes(n) : sbf_rgb_workspace_bytes(ctx, w, h, h, dabs, size_d))) +
+                    : (p->box_mode == SB200_BOX_SAT ? rgb_ws_bytes(n) : rgb_fused_ws_bytes(ctx, w, h, h, dabs, size_d))) +
                    2 * sb_align(n) + 4 * sb_align(n * 4) + 4096;
     bytes += 2 * sb_align(n * channels) + 6 * sb_align(n * 4) + 4 * sb_align(n) + 4096;
     SB_TRY(sb_ws_reserve(ctx, bytes));

@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/stereo_b200.h"
@@ -29,6 +30,7 @@ struct sb200_ctx {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
     bool fused_attr_set = false;
+    int rgb_kernel = 3;  // RGB-guide fused kernel: 2 = two-stage (fused_cvf_rgb.cu), 3 = three-stage (fused_cvf_rgb3.cu)
 };
 
 extern char g_sb200_global_err[512];
@@ -135,3 +137,8 @@ size_t sbf_rgb_workspace_bytes(const sb200_ctx* ctx, int w, int h_held, int rows
 int sbf_pair_disparity_rgb(sb200_ctx* ctx, const sb200_params* p, const uint8_t* rgb_l, const uint8_t* rgb_r, int channels,
                            const uint8_t* gray_l, const uint8_t* gray_r, const SbFusedGeom& g, float* bestL, float* dispL,
                            float* bestR, float* dispR);
+// RGB guide, three-stage kernel (fused_cvf_rgb3.cu): same contract
+size_t sbf_rgb3_workspace_bytes(const sb200_ctx* ctx, int w, int h_held, int rows_out, int dabs, int size_d);
+int sbf_pair_disparity_rgb3(sb200_ctx* ctx, const sb200_params* p, const uint8_t* rgb_l, const uint8_t* rgb_r, int channels,
+                            const uint8_t* gray_l, const uint8_t* gray_r, const SbFusedGeom& g, float* bestL, float* dispL,
+                            float* bestR, float* dispR);

@@ -124,48 +124,6 @@ __device__ __forceinline__ void copy_ops(ProdOps (&a)[ROWS], const ProdOps (&b)[
 #pragma unroll
     for (int r = 0; r < ROWS; r++) a[r] = b[r];
 }
-// f16 x f16 + f32 -> f32 and f16 + f32 -> f32 in one FMA-pipe instruction (FHFMA / FHADD, PTX 8.6, sm_100+)
-__device__ __forceinline__ float fhfma(__half a, __half b, float c) {
-    float d;
-    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(__half_as_ushort(a)), "h"(__half_as_ushort(b)), "f"(c));
-    return d;
-}
-__device__ __forceinline__ float fhadd(__half a, float c) {
-    float d;
-    asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(d) : "h"(__half_as_ushort(a)), "f"(c));
-    return d;
-}
-// a load the compiler may not sink towards its use
-__device__ __forceinline__ float4 ld_early_f4(const void* p) {  // coherent: written by this block one group earlier
-    float4 v;
-    asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-    return v;
-}
-
-// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(mbar)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t b, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-    return v;
-}
-
-__device__ __forceinline__ float inv_rows(const float* lut, int y, int y_global0, int frame_h) {
-    // 1 / (scale * clipped window height) at held row y, 0 outside the frame: the height takes
-    // 19 values, the reciprocals come from a table in shared memory
-    int yg = y + y_global0;
-    int ay = min(frame_h - 1, yg + RAD) - max(0, yg - RAD) + 1;
-    if (yg < 0 || yg >= frame_h) ay = 0;
-    return lut[ay];
-}
-
 __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
@@ -718,22 +676,6 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
     }
 }
 
-// Chunk merge: fold the per-chunk (best,label) planes in chunk order with the same rule.
-__global__ void k_merge_chunks_bl(const float2* __restrict__ BL, int n_chunks, int view, int rows, int w, int pitchS,
-                                  float* __restrict__ best, float* __restrict__ disp) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y;
-    if (x >= w) return;
-    const size_t plane = (size_t)rows * pitchS;
-    float b = BEST_INIT_BITS_F, l = 0.0f;
-    for (int c = 0; c < n_chunks; c++) {
-        float2 q = BL[(size_t)(c * 2 + view) * plane + (size_t)y * pitchS + x];
-        if (b >= q.x) { b = q.x; l = q.y; }
-    }
-    if (best) best[(size_t)y * w + x] = b;
-    if (disp) disp[(size_t)y * w + x] = l;
-}
-
 // ---------------------------------------------------------------------------------------
 // Per-frame preparation (replaces chToFlOnGPU, x_derivativeOnGPU and the guide-statistics part
 // of compute_guided_filter, guidedFilter.cu:58-123): for one image writes the padded planes
@@ -919,6 +861,13 @@ static int launch_prep(sb200_ctx* ctx, const sb200_params* p, const uint8_t* gra
 int sbf_prep_gray_planes(sb200_ctx* ctx, const sb200_params* p, const uint8_t* gray, const SbFusedGeom& g, int pitch, int padx,
                          float S, unsigned* IG, float* If, float2* st) {
     return launch_prep(ctx, p, gray, g, pitch, padx, S, IG, 0, If, st, nullptr);
+}
+
+// gray planes for the three-stage RGB kernel (fused_cvf_rgb3.cu): the 4 shifted (I,G) copies and the strip-tiled planes
+int sbf_prep_gray_tiled(sb200_ctx* ctx, const sb200_params* p, const uint8_t* gray, const SbFusedGeom& g, int pitch, int padx,
+                        float S, unsigned* IG, size_t shift_stride, unsigned* Tg, void* TI, float2* Tst, int n_strips) {
+    return launch_prep(ctx, p, gray, g, pitch, padx, S, IG, shift_stride, nullptr, nullptr, nullptr, Tg,
+                       reinterpret_cast<__half*>(TI), Tst, n_strips);
 }
 
 static int run_fused(sb200_ctx* ctx, const sb200_params* p, const uint8_t* const gray[2], const SbFusedGeom& g,

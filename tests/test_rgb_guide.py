@@ -69,3 +69,48 @@ def test_gpu_rgb_fused_shapes_and_staged_agree(oracle, w, h, size_d):
         assert (np.abs(out[kb] - b) / np.maximum(np.abs(b), 0.1)).max() < 1e-4
         assert np.array_equal(out[kd][(s - b) > 2e-4], d[(s - b) > 2e-4])
         assert (out[kd] == d).mean() > 0.999
+
+
+def _rgb_pipeline_with_kernel(S, api, monkeypatch, which, L, R, p):
+    monkeypatch.setenv("SB200_RGB_KERNEL", str(which))  # read by sb200_ctx_create
+    with S.Context(0) as ctx:
+        return ctx.pipeline(L, R, p, want=("disp_left", "disp_right", "best_left", "best_right", "occlusion", "filled"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,size_d", [(470, 130, 21), (216, 40, 4), (33, 25, 3), (217, 19, 1), (900, 330, 70)])
+def test_gpu_rgb_three_stage_kernel_equals_two_stage_bitwise(monkeypatch, w, h, size_d):
+    """k_fused_cvf_rgb3 (three warp roles, TMA operand ring) and k_fused_cvf_rgb (two roles, L1 loads) perform the
+    same float operations in the same order on the same exact first-stage sums: every output is bit-identical."""
+    S = pytest.importorskip("stereo_matching_cuda_b200")
+    from stereo_matching_cuda_b200 import api
+
+    L, R = synth.make_pair(w, h, max(size_d, 2), channels=3, seed=w + 1)
+    p = api.default_params(dmin=-(size_d - 1), dmax=0, guide_mode=S.GUIDE_RGB)
+    a = _rgb_pipeline_with_kernel(S, api, monkeypatch, 2, L, R, p)
+    b = _rgb_pipeline_with_kernel(S, api, monkeypatch, 3, L, R, p)
+    for k in a:
+        assert np.array_equal(a[k].view(np.uint32) if a[k].dtype == np.float32 else a[k],
+                              b[k].view(np.uint32) if b[k].dtype == np.float32 else b[k]), k
+
+
+@pytest.mark.gpu
+def test_gpu_rgb_three_stage_kernel_full_size_1080p_d256(monkeypatch):
+    """BASELINE configs[2] at full size: both RGB kernels agree bit for bit on every output map, and the left labels
+    recover the synthetic disparity staircase away from the band edges"""
+    S = pytest.importorskip("stereo_matching_cuda_b200")
+    from stereo_matching_cuda_b200 import api
+
+    w, h, size_d = 1920, 1080, 256
+    L, R = synth.make_pair(w, h, size_d, channels=3, seed=3)
+    p = api.default_params(dmin=-(size_d - 1), dmax=0, guide_mode=S.GUIDE_RGB)
+    a = _rgb_pipeline_with_kernel(S, api, monkeypatch, 2, L, R, p)
+    b = _rgb_pipeline_with_kernel(S, api, monkeypatch, 3, L, R, p)
+    for k in a:
+        assert np.array_equal(a[k].view(np.uint32) if a[k].dtype == np.float32 else a[k],
+                              b[k].view(np.uint32) if b[k].dtype == np.float32 else b[k]), k
+    truth = -synth.delta_rows(h, size_d).astype(np.float32)[:, None]
+    inner = np.zeros((h, w), bool)
+    inner[:, size_d + 20:w - 20] = True
+    ok = (b["disp_left"] == truth) & inner
+    assert ok.sum() / inner.sum() > 0.9
