@@ -76,11 +76,20 @@ struct FusedArgs {
 
 constexpr int K3_THREADS = 3 * NWARP * 32;  // three pipeline stages (warps p, p+4, p+8) per disparity
 constexpr uint32_t TM_HAND2 = 416;          // TMEM columns [416,480): stage 1 -> stage 2 hand-off rows, 2 slots
-constexpr int HS1_ROWS = 1;  // rows of an iteration whose horizontal sums of b are taken in stage 1 (the rest: stage 2)
+#ifndef FUSED_HS1_ROWS
+#define FUSED_HS1_ROWS 1
+#endif
+constexpr int HS1_ROWS = FUSED_HS1_ROWS;  // rows of an iteration whose horizontal sums of b are taken in stage 1 (the rest: stage 2)
 constexpr int NQ = 4;     // depth of the ring of filtered rows between the consumer and the merging warps
 constexpr int MLAG = 2;   // a producer merges the rows its consumer emitted MLAG iterations ago
 constexpr int NS = 16;        // slots of the operand ring (one per pipeline iteration)
-constexpr int LOAD_AHEAD = 5; // the loading warp fills the slot of iteration K + LOAD_AHEAD while it works on K
+constexpr int LOAD_AHEAD = 5; // the loading warps fill the slot of iteration K + LOAD_AHEAD while they work on K
+#ifndef FUSED_AB0
+#define FUSED_AB0 0           // 1: the coefficients a, b are computed by stage 0 (which has slack), not stage 1
+#endif
+#ifndef FUSED_SPREAD
+#define FUSED_SPREAD 0        // 1: the stage-1 warp of trio p fills the iterations K = p mod 4; 0: trio 0 fills them all
+#endif
 struct Slot {                 // guide operands of one iteration, filled by 4 bulk copies (8 KB)
     uint4 g[ROWS][2][32];     // (I,G) at rows yi
     uint4 io[ROWS][32];       // I at rows yi-19 (leave the first-stage window)
@@ -172,7 +181,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
 #pragma unroll
         for (int b = 0; b < NS; b++) {
             mbar_init(mb_sfull + 8 * b, 1);
-            mbar_init(mb_sempty + 8 * b, 3 * NWARP);
+            mbar_init(mb_sempty + 8 * b, (FUSED_AB0 ? 2 : 3) * NWARP);  // the warps that read the slot
         }
     }
     if (threadIdx.x == 32) {
@@ -222,6 +231,15 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
             wm[j] = (x >= 0 && x < A.w) ? u2h2(A.wpack) : __float2half2_rn(0.0f);
         }
         const __half2 th = u2h2(A.thpack);
+#if FUSED_AB0
+        float rx[KPX];  // 1 / clipped window width, 0 outside the image
+#pragma unroll
+        for (int j = 0; j < KPX; j++) {
+            int x = xl + j;
+            int ax = min(A.w - 1, x + RAD) - max(0, x - RAD) + 1;
+            rx[j] = (x >= 0 && x < A.w) ? __frcp_rn((float)ax) : 0.0f;
+        }
+#endif
         for (int g = 0; g < ngroups; g++) {
             const int dk = g * NWARP + pair;
             const bool active = dk < dcnt;
@@ -258,6 +276,9 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                     }
                     // guide operands of this iteration from the shared-memory ring
                     uint4 gq[ROWS][2], ioq[ROWS];
+#if FUSED_AB0
+                    uint4 sq[ROWS][4];
+#endif
                     {
                         const int K = g * niter + it;
                         const uint32_t sa = slot_wait(K);
@@ -268,6 +289,13 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                             gq[r][1] = lds128(sa + OFF_G + (r * 2 + 1) * 512);
                             ioq[r] = lds128(sa + OFF_IO + r * 512);
                             t |= gq[r][0].x | gq[r][1].x | ioq[r].x;
+#if FUSED_AB0
+#pragma unroll
+                            for (int c = 0; c < 4; c++) {
+                                sq[r][c] = lds128(sa + OFF_ST + (r * 4 + c) * 512);
+                                t |= sq[r][c].x;
+                            }
+#endif
                         }
                         slot_release(K, t);
                     }
@@ -324,6 +352,22 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                         tm_st4(tP + 4 * slots[r], pneg[r]);
                         hsum19(VP, SP[r]);
                         hsum19(VIP, SIP[r]);
+#if FUSED_AB0
+                        {   // a, b at row ya = yi - 9 (guidedFilter.cu:345-354), handed over in place of the sums
+                            const float ry1 = inv_rows(sm.ry_lut[0], y_first + it * ROWS + r - RAD, A.y_global0, A.frame_h);
+                            const unsigned stt[16] = {sq[r][0].x, sq[r][0].y, sq[r][0].z, sq[r][0].w, sq[r][1].x, sq[r][1].y, sq[r][1].z, sq[r][1].w,
+                                                      sq[r][2].x, sq[r][2].y, sq[r][2].z, sq[r][2].w, sq[r][3].x, sq[r][3].y, sq[r][3].z, sq[r][3].w};
+#pragma unroll
+                            for (int j = 0; j < KPX; j++) {
+                                const float mI = __uint_as_float(stt[2 * j]), c2 = __uint_as_float(stt[2 * j + 1]);
+                                const float cov = fmaf(-mI, SP[r][j], SIP[r][j]);
+                                const float a = cov * c2;
+                                const float mp = SP[r][j] * (rx[j] * ry1);
+                                SP[r][j] = a;
+                                SIP[r][j] = fmaf(-mI, a, mp);
+                            }
+                        }
+#endif
                     }
                     // stage 1 has copied the previous rows out of the hand-off columns
                     if (it > 0) {
@@ -351,6 +395,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
         }
     } else if (stage == 1) {
         // ====== STAGE 1: a, b; their vertical and horizontal window sums ======
+#if !FUSED_AB0
         float rx[KPX];  // 1 / clipped window width, 0 outside the image
 #pragma unroll
         for (int j = 0; j < KPX; j++) {
@@ -358,30 +403,36 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
             int ax = min(A.w - 1, x + RAD) - max(0, x - RAD) + 1;
             rx[j] = (x >= 0 && x < A.w) ? __frcp_rn((float)ax) : 0.0f;
         }
-        // Operand ring, producer side: the stage-1 warp of pair 0 (always active) fills the slot of iteration
-        // K + LOAD_AHEAD, for the whole block, while it works on K: 4 bulk copies of the strip-tiled guide planes.
+#endif
+        // Operand ring, producer side: the stage-1 warps fill the slot of iteration K + LOAD_AHEAD, for the whole block,
+        // while they work on K: 4 bulk copies of the strip-tiled guide planes.  With FUSED_SPREAD the warp of trio p
+        // fills the iterations K = p mod 4, so the ~100 instructions of a fill are shared by the four trios instead of
+        // slowing trio 0 (the trios run in step through the merge ring: the slowest one sets the pace).
         const int Ktotal = ngroups * niter;
-        int fillK = 0, fill_it = 0;  // next iteration to fill, and its row iteration inside its group
-        auto fill_next = [&]() {
-            if (fillK >= Ktotal) return;
-            const int sl = fillK & (NS - 1);
-            if (fillK >= NS) mbar_wait(mb_sempty + 8 * sl, (unsigned)(fillK / NS - 1) & 1u);  // all 12 warps released it
-            if (lane == 0) {
-                const uint32_t full = mb_sfull + 8 * sl;
-                const uint32_t dst = smem_addr(&sm.slot[0]) + (uint32_t)sl * SLOT_BYTES;
-                const long long rec = (long long)strip * A.rows_pad + PADY + y_first + fill_it * ROWS;  // record of row yi0
-                mbar_expect_tx(full, SLOT_BYTES);
-                bulk_g2s(dst + OFF_G, A.Tg[view] + rec * 64, ROWS * 1024, full);
-                bulk_g2s(dst + OFF_IO, A.TI[view] + (rec - WIN) * 32, ROWS * 512, full);
-                bulk_g2s(dst + OFF_IQ, A.TI[view] + (rec - 2 * RAD) * 32, ROWS * 512, full);
-                bulk_g2s(dst + OFF_ST, A.Tst[view] + (rec - RAD) * 128, ROWS * 2048, full);
+        constexpr int fill_step = FUSED_SPREAD ? NWARP : 1;
+        int fillK = FUSED_SPREAD ? pair : 0, fill_it = fillK;  // this warp's next iteration to fill, and its row iteration inside its group
+        const bool filler = FUSED_SPREAD || pair == 0;
+        auto fill_due = [&](int K) {  // called at the start of iteration K: fill what is due up to K + LOAD_AHEAD
+            while (fillK <= K + LOAD_AHEAD && fillK < Ktotal) {
+                const int sl = fillK & (NS - 1);
+                if (fillK >= NS) mbar_wait(mb_sempty + 8 * sl, (unsigned)(fillK / NS - 1) & 1u);  // all 12 warps released it
+                if (lane == 0) {
+                    const uint32_t full = mb_sfull + 8 * sl;
+                    const uint32_t dst = smem_addr(&sm.slot[0]) + (uint32_t)sl * SLOT_BYTES;
+                    const long long rec = (long long)strip * A.rows_pad + PADY + y_first + fill_it * ROWS;  // record of row yi0
+                    mbar_expect_tx(full, SLOT_BYTES);
+                    bulk_g2s(dst + OFF_G, A.Tg[view] + rec * 64, ROWS * 1024, full);
+                    bulk_g2s(dst + OFF_IO, A.TI[view] + (rec - WIN) * 32, ROWS * 512, full);
+                    bulk_g2s(dst + OFF_IQ, A.TI[view] + (rec - 2 * RAD) * 32, ROWS * 512, full);
+                    bulk_g2s(dst + OFF_ST, A.Tst[view] + (rec - RAD) * 128, ROWS * 2048, full);
+                }
+                __syncwarp();
+                fillK += fill_step;
+                fill_it += fill_step;
+                if (fill_it >= niter) fill_it -= niter;
             }
-            __syncwarp();
-            fillK++;
-            fill_it = (fill_it + 1 == niter) ? 0 : fill_it + 1;
         };
-        if (pair == 0)
-            for (int i = 0; i < LOAD_AHEAD; i++) fill_next();
+        if (filler) fill_due(-1);  // the slots of iterations 0 .. LOAD_AHEAD-1
         for (int g = 0; g < ngroups; g++) {
             const int dk = g * NWARP + pair;
             const bool active = dk < dcnt;
@@ -395,7 +446,8 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
             int slot = 0;
             auto iter = [&](auto emit_tag, int it) {
                 constexpr bool EMIT = decltype(emit_tag)::value;
-                if (pair == 0) fill_next();
+                if (filler) fill_due(g * niter + it);
+#if !FUSED_AB0
                 // (mean_I, c2) of rows ya from the shared-memory ring
                 uint4 sq[ROWS][4];
                 {
@@ -415,6 +467,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                 float ry1[ROWS];
 #pragma unroll
                 for (int r = 0; r < ROWS; r++) ry1[r] = inv_rows(sm.ry_lut[0], yi0 + r - RAD, A.y_global0, A.frame_h);
+#endif
                 // the (a,b) rows that leave the second-stage window, from this pair's TMEM ring
                 float ao[ROWS][KPX], bo[ROWS][KPX];
                 int slots[ROWS];
@@ -438,9 +491,16 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
 #pragma unroll
                 for (int r = 0; r < ROWS; r++) {
                     // ---- a, b at row ya = yi - 9
+                    float a[KPX], b[KPX];
+#if FUSED_AB0
+#pragma unroll
+                    for (int j = 0; j < KPX; j++) {  // computed by stage 0
+                        a[j] = SP[r][j];
+                        b[j] = SIP[r][j];
+                    }
+#else
                     const unsigned stt[16] = {sq[r][0].x, sq[r][0].y, sq[r][0].z, sq[r][0].w, sq[r][1].x, sq[r][1].y, sq[r][1].z, sq[r][1].w,
                                               sq[r][2].x, sq[r][2].y, sq[r][2].z, sq[r][2].w, sq[r][3].x, sq[r][3].y, sq[r][3].z, sq[r][3].w};
-                    float a[KPX], b[KPX];
 #pragma unroll
                     for (int j = 0; j < KPX; j++) {
                         const float mI = __uint_as_float(stt[2 * j]), c2 = __uint_as_float(stt[2 * j + 1]);
@@ -449,6 +509,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                         float mp = SP[r][j] * (rx[j] * ry1[r]);
                         b[j] = fmaf(-mI, a[j], mp);
                     }
+#endif
                     // ---- second stage: (a,b) of row ya enter, row ya-19 leaves
                     tm_st16(tAB + 16 * slots[r], a, b);
 #pragma unroll
@@ -491,9 +552,12 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
 #pragma unroll 1
                 for (; it < niter; it++) iter(std::true_type{}, it);
             } else {
-                for (int it = 0; it < niter; it++) {  // (never pair 0, which fills the ring)
+                for (int it = 0; it < niter; it++) {  // a trio without a disparity still fills and releases its share
+                    if (filler) fill_due(g * niter + it);
+#if !FUSED_AB0
                     slot_wait(g * niter + it);
                     slot_release(g * niter + it, 0u);
+#endif
                 }
             }
             __syncthreads();  // group end

@@ -11,11 +11,12 @@
 //      stage 2  their horizontal sums, q = SS_a . I + SS_b, merge of the block's 4 disparities
 //               (RGB3_HS1 moves the first one or two horizontal sums into stage 1)
 //    hand-offs through Tensor-Memory columns: named barriers (0 -> 1), mbarriers with two slots (1 -> 2);
-//  * every guide operand -- (I,G) of the row, the colour rows entering and leaving the first window and at
-//    the output row, the 72 statistics words per lane (mu, scaled inverse covariance) -- is fetched ONCE per
-//    block by TMA bulk copies from strip-tiled planes into a shared-memory ring (14.5 KB per iteration) and
-//    read with conflict-free 128-bit loads by all 12 warps; only the match operands go through L1 (two aligned
-//    128-bit loads from the (I,G) copy shifted by d & 3);
+//  * the guide operands of stages 0 and 1 -- (I,G) of the row and the colour rows entering and leaving the first
+//    window; the 72 statistics words per lane (mu, scaled inverse covariance) -- are fetched ONCE per block by
+//    TMA bulk copies from strip-tiled planes into a 4-slot shared-memory ring (13 KB per iteration; the stage-1
+//    warp of trio p fills slot p) and read with conflict-free 128-bit loads by the 8 warps of the two stages;
+//    through L1 go only the match operands (two aligned 128-bit loads from the (I,G) copy shifted by d & 3) and
+//    stage 2's colour row (three 128-bit loads, one row ahead);
 //  * rings of the marching filters: (a_r, a_g) and the cost in Tensor Memory, (a_b, b) in shared memory;
 //  * (best,label) as one interleaved float2 plane per disparity chunk, merged by k_merge_chunks_bl.
 #include "fused_dev.cuh"
@@ -41,27 +42,50 @@ struct Rgb3Args {
     int zero;               // always 0, opaque to the compiler
 };
 
-constexpr int R3_THREADS = 3 * NWARP * 32;
+#ifndef RGB3_MERGE_WG
+#define RGB3_MERGE_WG 1    // 1: a fourth group of 4 warps does the merge of the block's disparities (stage 3); 0: stage 2 does
+#endif
+constexpr int R3_THREADS = (3 + RGB3_MERGE_WG) * NWARP * 32;
+// Register budget per warp role when the merge has its own warps (16 warps x 128 registers at launch; the roles
+// trade registers with setmaxnreg, one warpgroup = the 4 warps of a role): 152 + 168 + 152 + 40 = 512 = 4 x 128
+constexpr int R3_REGS0 = 152, R3_REGS1 = 168, R3_REGS2 = 152, R3_REGS3 = 40;
+static_assert(R3_REGS0 + R3_REGS1 + R3_REGS2 + R3_REGS3 <= 512, "register file: 64 K registers per SM");
 constexpr uint32_t T3_RING_A = 0, T3_RING_P = 304, T3_HAND = 384, T3_HAND2 = 416;  // TMEM columns of a lane
 constexpr int NQ3 = 4;     // depth of the ring of filtered rows between stage 2 and the merge
 constexpr int MLAG3 = 2;   // the merge runs MLAG3 iterations behind
-constexpr int NS3 = 4;     // slots of the operand ring
-constexpr int AHEAD3 = 2;  // the loading warp fills the slot of iteration K + AHEAD3 while it works on K
+// Operand ring of stages 0 and 1: slot K & 3 holds the guide operands of iteration K.  The stage-1 warp of trio p
+// fills slot p (iterations K = p mod 4), RGB3_AHEAD iterations ahead of its own position, so the cost of issuing
+// the bulk copies (~100 instructions) is shared by the four trios instead of slowing one of them -- the trios run in
+// step through the merge ring, so the slowest one sets the pace.  Measured alternatives (1080p D=256): stage 2's
+// colour row in the slot 8.56 ms (the ring can then only be refilled as fast as the LAST stage releases it); all
+// fills by trio 0's stage-1 warp 8.29; by trio 0's stage-0 warp 9.45; one ring per stage, each filled by its own
+// stage's trio-0 warp 9.19.
+constexpr int NS3 = 4;
+#ifndef RGB3_AHEAD
+#define RGB3_AHEAD 2
+#endif
+constexpr int AHEAD3 = RGB3_AHEAD;
+constexpr int WARM3 = 4 * RAD;   // warm-up iterations (one row each) before the first output row
 #ifndef RGB3_HS1
 #define RGB3_HS1 0         // horizontal sums (of a_r, a_g) taken in stage 1; the rest in stage 2
 #endif
-constexpr int WARM3 = 4 * RAD;  // warm-up iterations (one row each) before the first output row
+#ifndef RGB3_SOLVE0
+#define RGB3_SOLVE0 0      // 1: the 3x3 solve (a, b) runs in stage 0, which then reads the statistics; 0: in stage 1
+#endif
+#ifndef RGB3_SPREAD
+#define RGB3_SPREAD 1      // 1: trio p fills slot p; 0: trio 0 fills every slot
+#endif
 
-struct Slot3 {          // guide operands of one iteration (one row), 5 bulk copies
+struct Slot3 {          // guide operands of one iteration (one row) of stages 0 and 1, 4 bulk copies (13 KB)
     uint4 g[2][32];     // (I,G) at row yi
     uint4 cn[3][32];    // colour at row yi        (enters the first-stage window)
     uint4 co[3][32];    // colour at row yi-19     (leaves it)
-    uint4 cq[3][32];    // colour at row yq = yi-18 (output row)
     uint4 st[18][32];   // statistics at row ya = yi-9
 };
 constexpr uint32_t SLOT3_BYTES = sizeof(Slot3);
+// (stage 2 reads the colour of its output row straight from the strip-tiled plane, one row ahead)
 struct Smem3 {
-    Slot3 slot[NS3];
+    Slot3 slot[NS3];                   // operand ring of stages 0 and 1
     float4 ringB[NWARP][WIN][4][32];   // stage-1 private rings: a_b (planes 0,1) and b (planes 2,3)
     float4 qbuf[NQ3][NWARP][2][32];    // filtered row of each stage-2 warp
     uint64_t sfull[NS3], sempty[NS3];
@@ -73,6 +97,40 @@ struct Smem3 {
 static_assert(sizeof(Smem3) <= 232448, "Smem3 exceeds the 227 KB a block may opt in to");
 
 __device__ __forceinline__ unsigned word_of(const uint4& v, int k) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; }
+
+// Fold the 4 disparities of a group into the running (best,label) of two columns: ascending d, `best >= q` (the last
+// slice wins ties, guidedFilter.cu:406).  "Minimum, the later index on a tie" is associative, so a 2-level tournament
+// gives what the reference's sequential scan gives, with a shorter dependency chain.  qp: this thread's two columns
+// in the q row of the group's first warp (the other warps follow at 256 floats).
+__device__ __forceinline__ float4 merge4(const float* qp, const float (&lab)[NWARP], const float4 pb) {
+    static_assert(NWARP == 4, "tournament written for 4 disparities per group");
+    float b0 = pb.x, l0 = pb.y, b1 = pb.z, l1 = pb.w;
+    float2 qv[NWARP];
+#pragma unroll
+    for (int wv = 0; wv < NWARP; wv++) qv[wv] = *reinterpret_cast<const float2*>(qp + wv * 256);
+    {
+        const bool t01 = qv[0].x >= qv[1].x, t23 = qv[2].x >= qv[3].x;
+        const float m01 = t01 ? qv[1].x : qv[0].x, m23 = t23 ? qv[3].x : qv[2].x;
+        const float a01 = t01 ? lab[1] : lab[0], a23 = t23 ? lab[3] : lab[2];
+        const bool t = m01 >= m23;
+        const float m = t ? m23 : m01, a = t ? a23 : a01;
+        if (b0 >= m) { b0 = m; l0 = a; }
+    }
+    {
+        const bool t01 = qv[0].y >= qv[1].y, t23 = qv[2].y >= qv[3].y;
+        const float m01 = t01 ? qv[1].y : qv[0].y, m23 = t23 ? qv[3].y : qv[2].y;
+        const float a01 = t01 ? lab[1] : lab[0], a23 = t23 ? lab[3] : lab[2];
+        const bool t = m01 >= m23;
+        const float m = t ? m23 : m01, a = t ? a23 : a01;
+        if (b1 >= m) { b1 = m; l1 = a; }
+    }
+    return make_float4(b0, l0, b1, l1);
+}
+
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
 __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -110,11 +168,13 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
     const uint32_t mb_sfull = smem_addr(&sm.sfull[0]), mb_sempty = smem_addr(&sm.sempty[0]);
     const uint32_t slot0 = smem_addr(&sm.slot[0]) + 16 * lane;
     static_assert((NS3 & (NS3 - 1)) == 0 && (NQ3 & (NQ3 - 1)) == 0, "ring indices are taken from the bits of the counters");
+    static_assert(AHEAD3 < NS3, "the ring cannot be filled further ahead than it is deep");
+    static_assert(!RGB3_SPREAD || NS3 == NWARP, "trio p fills slot p");
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int b = 0; b < NS3; b++) {
             mbar_init(mb_sfull + 8 * b, 1);
-            mbar_init(mb_sempty + 8 * b, 3 * NWARP);
+            mbar_init(mb_sempty + 8 * b, (RGB3_SOLVE0 ? 1 : 2) * NWARP);  // released by the warps that read the slot
         }
     }
     if (threadIdx.x == 32) {
@@ -141,18 +201,93 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
     const uint32_t tbase = sm.tmem_base + ((uint32_t)(pair * 32) << 16);
     const uint32_t tA = tbase + T3_RING_A, tP = tbase + T3_RING_P, tH = tbase + T3_HAND, tH2 = tbase + T3_HAND2;
 
+    // operand ring, consumer side: a warp waits for the slot of its iteration K, reads its 16-byte chunks and releases
+    // the slot; `t` is a word of the data read, so the release cannot be issued before the reads have completed
     auto slot_wait = [&](int K) -> uint32_t {
         mbar_wait(mb_sfull + 8 * (K & (NS3 - 1)), (unsigned)(K / NS3) & 1u);
         return slot0 + (uint32_t)(K & (NS3 - 1)) * SLOT3_BYTES;
     };
-    auto slot_release = [&](int K, unsigned t) {  // `t`: a word of the data read, so the release follows the reads
+    auto slot_release = [&](int K, unsigned t) {
         mbar_arrive_lane0(mb_sempty + 8 * (K & (NS3 - 1)) + (t & (unsigned)zero), lane);
     };
     constexpr uint32_t OFF_G = offsetof(Slot3, g), OFF_CN = offsetof(Slot3, cn), OFF_CO = offsetof(Slot3, co),
-                       OFF_CQ = offsetof(Slot3, cq), OFF_ST = offsetof(Slot3, st);
+                       OFF_ST = offsetof(Slot3, st);
+    // operand ring, producer side (stage-1 warps): fill the slot of iteration Kf, row iteration itf of its group, with
+    // 4 TMA bulk copies of the strip-tiled planes
+    const int Ktotal = ngroups * niter;
+    auto fill_slot = [&](int Kf, int itf) {
+        const int sl = Kf & (NS3 - 1);
+        if (Kf >= NS3) mbar_wait(mb_sempty + 8 * sl, (unsigned)(Kf / NS3 - 1) & 1u);  // its 8 readers released it
+        if (lane == 0) {
+            const uint32_t full = mb_sfull + 8 * sl;
+            const uint32_t dst = smem_addr(&sm.slot[0]) + (uint32_t)sl * SLOT3_BYTES;
+            const long long rec = (long long)strip * A.rows_pad + PADY + y_first + itf;  // record of row yi
+            mbar_expect_tx(full, SLOT3_BYTES);
+            bulk_g2s(dst + OFF_G, A.Tg[view] + rec * 64, 1024, full);
+            bulk_g2s(dst + OFF_CN, A.TC[view] + rec * 96, 1536, full);
+            bulk_g2s(dst + OFF_CO, A.TC[view] + (rec - WIN) * 96, 1536, full);
+            bulk_g2s(dst + OFF_ST, A.TS[view] + (rec - RAD) * 576, 9216, full);
+        }
+        __syncwarp();
+    };
+    // this warp's next fill: iteration fillK (row iteration fill_it of its group); after a fill it moves on by
+    // fill_step iterations (4 when the trios share the work: trio p fills the iterations K = p mod 4)
+    constexpr int fill_step = RGB3_SPREAD ? NWARP : 1;
+    int fillK = RGB3_SPREAD ? pair : 0, fill_it = fillK;
+    const bool filler = (stage == 1) && (RGB3_SPREAD || pair == 0);
+    // called by a filling warp at the start of its iteration K: fill what is due up to K + AHEAD3
+    auto fill_due = [&](int K) {
+        while (fillK <= K + AHEAD3 && fillK < Ktotal) {
+            fill_slot(fillK, fill_it);
+            fillK += fill_step;
+            fill_it += fill_step;
+            if (fill_it >= niter) fill_it -= niter;
+        }
+    };
+    if (filler) fill_due(-1);  // the slots of iterations 0 .. AHEAD3-1
+
+    // a = M cov, b = mp - a.mu at row ya = yi - 9 from the four first-stage sums; the statistics come from the operand
+    // ring, half a lane's pixels at a time.  On return the arrays hold (a_r, a_g, a_b, b).
+    auto solve = [&](int K, float (&SP)[KPX], float (&SR)[KPX], float (&SG)[KPX], float (&SB)[KPX], const float (&rx)[KPX],
+                     float ry1, uint32_t sa, unsigned t) {
+#pragma unroll
+        for (int hq = 0; hq < 2; hq++) {
+            uint4 q1[4], q2[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                q1[jj] = lds128(sa + OFF_ST + (2 * (4 * hq + jj)) * 512);
+                q2[jj] = lds128(sa + OFF_ST + (2 * (4 * hq + jj) + 1) * 512);
+                t |= q1[jj].x | q2[jj].x;
+            }
+            const uint4 q3 = lds128(sa + OFF_ST + (16 + hq) * 512);
+            t |= q3.x;
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                const int j = 4 * hq + jj;
+                const float mr = __uint_as_float(q1[jj].x), mg = __uint_as_float(q1[jj].y), mb = __uint_as_float(q1[jj].z);
+                const float Mrr = __uint_as_float(q1[jj].w);
+                const float Mrg = __uint_as_float(q2[jj].x), Mrb = __uint_as_float(q2[jj].y);
+                const float Mgg = __uint_as_float(q2[jj].z), Mgb = __uint_as_float(q2[jj].w);
+                const float Mbb = __uint_as_float(word_of(q3, jj));
+                const float cx = fmaf(-mr, SP[j], SR[j]);
+                const float cy = fmaf(-mg, SP[j], SG[j]);
+                const float cz = fmaf(-mb, SP[j], SB[j]);
+                const float ar = fmaf(Mrr, cx, fmaf(Mrg, cy, Mrb * cz));
+                const float ag = fmaf(Mrg, cx, fmaf(Mgg, cy, Mgb * cz));
+                const float ab = fmaf(Mrb, cx, fmaf(Mgb, cy, Mbb * cz));
+                const float mp = SP[j] * (rx[j] * ry1);
+                SP[j] = ar;
+                SR[j] = ag;
+                SG[j] = ab;
+                SB[j] = mp - fmaf(ar, mr, fmaf(ag, mg, ab * mb));
+            }
+        }
+        slot_release(K, t);
+    };
 
     if (stage == 0) {
         // ====== STAGE 0: lattice cost; vertical and horizontal window sums of p, R p, G p, B p ======
+        if (RGB3_MERGE_WG) reg_inc<R3_REGS0>();
         const unsigned* __restrict__ IGm = A.IG[1 - view];
         __half2 wm[KPX];
 #pragma unroll
@@ -161,6 +296,15 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
             wm[j] = (x >= 0 && x < A.w) ? u2h2(A.wpack) : __float2half2_rn(0.0f);
         }
         const __half2 th = u2h2(A.thpack);
+#if RGB3_SOLVE0
+        float rx[KPX];
+#pragma unroll
+        for (int j = 0; j < KPX; j++) {
+            int x = xl + j;
+            int ax = min(A.w - 1, x + RAD) - max(0, x - RAD) + 1;
+            rx[j] = (x >= 0 && x < A.w) ? __frcp_rn((float)ax) : 0.0f;
+        }
+#endif
         for (int g = 0; g < ngroups; g++) {
             const int dk = g * NWARP + pair;
             const bool active = dk < dcnt;
@@ -189,10 +333,10 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
                     const uint4 n1 = __ldg(reinterpret_cast<const uint4*>(pm + dep) + 1);
                     pm += pitch;
                     uint4 gq[2], cn[3], co[3];
+                    const int K = g * niter + it;
+                    const uint32_t sa = slot_wait(K);
+                    unsigned t = 0;
                     {
-                        const int K = g * niter + it;
-                        const uint32_t sa = slot_wait(K);
-                        unsigned t = 0;
                         gq[0] = lds128(sa + OFF_G);
                         gq[1] = lds128(sa + OFF_G + 512);
                         t |= gq[0].x | gq[1].x;
@@ -202,7 +346,7 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
                             co[c] = lds128(sa + OFF_CO + c * 512);
                             t |= cn[c].x | co[c].x;
                         }
-                        slot_release(K, t);
+                        if (!RGB3_SOLVE0) slot_release(K, t);
                     }
                     uint32_t pold[4];  // the NEGATED lattice costs of row yi-19
                     tm_ld4(tP + 4 * slot, pold);
@@ -248,6 +392,9 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
                     hsum19(VR, SR);
                     hsum19(VG, SG);
                     hsum19(VB, SB);
+#if RGB3_SOLVE0
+                    solve(K, SP, SR, SG, SB, rx, inv_rows(sm.ry_lut[0], y_first + it - RAD, A.y_global0, A.frame_h), sa, t);
+#endif
                     if (it > 0) {  // stage 1 has copied the previous row out of the hand-off columns
                         named_bar_sync(BAR_EMPTY, 64);
                         tm_fence_after();
@@ -270,6 +417,8 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
         }
     } else if (stage == 1) {
         // ====== STAGE 1: a = M cov, b = mp - a.mu; their vertical sums; horizontal sums of a_r, a_g ======
+        if (RGB3_MERGE_WG) reg_inc<R3_REGS1>();
+#if !RGB3_SOLVE0
         float rx[KPX];
 #pragma unroll
         for (int j = 0; j < KPX; j++) {
@@ -277,30 +426,7 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
             int ax = min(A.w - 1, x + RAD) - max(0, x - RAD) + 1;
             rx[j] = (x >= 0 && x < A.w) ? __frcp_rn((float)ax) : 0.0f;
         }
-        // operand ring, producer side: the stage-1 warp of trio 0 (always active) fills the slot of K + AHEAD3
-        const int Ktotal = ngroups * niter;
-        int fillK = 0, fill_it = 0;
-        auto fill_next = [&]() {
-            if (fillK >= Ktotal) return;
-            const int sl = fillK & (NS3 - 1);
-            if (fillK >= NS3) mbar_wait(mb_sempty + 8 * sl, (unsigned)(fillK / NS3 - 1) & 1u);
-            if (lane == 0) {
-                const uint32_t full = mb_sfull + 8 * sl;
-                const uint32_t dst = smem_addr(&sm.slot[0]) + (uint32_t)sl * SLOT3_BYTES;
-                const long long rec = (long long)strip * A.rows_pad + PADY + y_first + fill_it;  // record of row yi
-                mbar_expect_tx(full, SLOT3_BYTES);
-                bulk_g2s(dst + OFF_G, A.Tg[view] + rec * 64, 1024, full);
-                bulk_g2s(dst + OFF_CN, A.TC[view] + rec * 96, 1536, full);
-                bulk_g2s(dst + OFF_CO, A.TC[view] + (rec - WIN) * 96, 1536, full);
-                bulk_g2s(dst + OFF_CQ, A.TC[view] + (rec - 2 * RAD) * 96, 1536, full);
-                bulk_g2s(dst + OFF_ST, A.TS[view] + (rec - RAD) * 576, 9216, full);
-            }
-            __syncwarp();
-            fillK++;
-            fill_it = (fill_it + 1 == niter) ? 0 : fill_it + 1;
-        };
-        if (pair == 0)
-            for (int i = 0; i < AHEAD3; i++) fill_next();
+#endif
         for (int g = 0; g < ngroups; g++) {
             const int dk = g * NWARP + pair;
             const bool active = dk < dcnt;
@@ -318,9 +444,10 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
             int slot = 0;
             auto iter = [&](auto emit_tag, int it) {
                 constexpr bool EMIT = decltype(emit_tag)::value;
-                if (pair == 0) fill_next();
-                const int yi = y_first + it;
-                const float ry1 = inv_rows(sm.ry_lut[0], yi - RAD, A.y_global0, A.frame_h);
+                if (filler) fill_due(g * niter + it);
+#if !RGB3_SOLVE0
+                const float ry1 = inv_rows(sm.ry_lut[0], y_first + it - RAD, A.y_global0, A.frame_h);
+#endif
                 named_bar_sync(BAR_FULL, 64);  // stage 0 has published row yi
                 tm_fence_after();
                 float SP[KPX], SR[KPX], SG[KPX], SB[KPX];
@@ -331,43 +458,14 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
                     tm_fence_before();
                     named_bar_arrive(BAR_EMPTY, 64);
                 }
-                // ---- a, b at row ya = yi - 9; the statistics come from the operand ring, half a lane's pixels at a time
-                float ar[KPX], ag[KPX], ab[KPX], bb[KPX];
+                // ---- (a, b) at row ya = yi - 9: solved here or, with RGB3_SOLVE0, already by stage 0
+#if !RGB3_SOLVE0
                 {
                     const int K = g * niter + it;
-                    const uint32_t sa = slot_wait(K);
-                    unsigned t = 0;
-#pragma unroll
-                    for (int hq = 0; hq < 2; hq++) {
-                        uint4 q1[4], q2[4];
-#pragma unroll
-                        for (int jj = 0; jj < 4; jj++) {
-                            q1[jj] = lds128(sa + OFF_ST + (2 * (4 * hq + jj)) * 512);
-                            q2[jj] = lds128(sa + OFF_ST + (2 * (4 * hq + jj) + 1) * 512);
-                            t |= q1[jj].x | q2[jj].x;
-                        }
-                        const uint4 q3 = lds128(sa + OFF_ST + (16 + hq) * 512);
-                        t |= q3.x;
-#pragma unroll
-                        for (int jj = 0; jj < 4; jj++) {
-                            const int j = 4 * hq + jj;
-                            const float mr = __uint_as_float(q1[jj].x), mg = __uint_as_float(q1[jj].y), mb = __uint_as_float(q1[jj].z);
-                            const float Mrr = __uint_as_float(q1[jj].w);
-                            const float Mrg = __uint_as_float(q2[jj].x), Mrb = __uint_as_float(q2[jj].y);
-                            const float Mgg = __uint_as_float(q2[jj].z), Mgb = __uint_as_float(q2[jj].w);
-                            const float Mbb = __uint_as_float(word_of(q3, jj));
-                            const float cx = fmaf(-mr, SP[j], SR[j]);
-                            const float cy = fmaf(-mg, SP[j], SG[j]);
-                            const float cz = fmaf(-mb, SP[j], SB[j]);
-                            ar[j] = fmaf(Mrr, cx, fmaf(Mrg, cy, Mrb * cz));
-                            ag[j] = fmaf(Mrg, cx, fmaf(Mgg, cy, Mgb * cz));
-                            ab[j] = fmaf(Mrb, cx, fmaf(Mgb, cy, Mbb * cz));
-                            const float mp = SP[j] * (rx[j] * ry1);
-                            bb[j] = mp - fmaf(ar[j], mr, fmaf(ag[j], mg, ab[j] * mb));
-                        }
-                    }
-                    slot_release(K, t);
+                    solve(K, SP, SR, SG, SB, rx, ry1, slot_wait(K), 0u);
                 }
+#endif
+                float (&ar)[KPX] = SP, (&ag)[KPX] = SR, (&ab)[KPX] = SG, (&bb)[KPX] = SB;
                 // ---- second stage: row ya enters, row ya-19 leaves (read from the rings only now: the solve above
                 //      needs the registers)
                 float aro[KPX], ago[KPX];
@@ -428,15 +526,20 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
 #pragma unroll 1
                 for (; it < niter; it++) iter(std::true_type{}, it);
             } else {
-                for (int it = 0; it < niter; it++) {  // (never trio 0, which fills the ring)
+                for (int it = 0; it < niter; it++) {  // a trio without a disparity still fills and releases its share
+                    if (filler) fill_due(g * niter + it);
+#if !RGB3_SOLVE0
                     slot_wait(g * niter + it);
                     slot_release(g * niter + it, 0u);
+#endif
                 }
             }
             __syncthreads();  // group end
         }
-    } else {
-        // ====== STAGE 2: horizontal sums of a_b and b, q = SS_a . I + SS_b, merge of the 4 disparities ======
+    } else if (stage == 2) {
+        // ====== STAGE 2: horizontal sums of a_b and b, q = SS_a . I + SS_b
+        // ====== and, without RGB3_MERGE_WG, the merge of the block's 4 disparities
+        if (RGB3_MERGE_WG) reg_inc<R3_REGS2>();
         float rx[KPX];
 #pragma unroll
         for (int j = 0; j < KPX; j++) {
@@ -444,7 +547,8 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
             int ax = min(A.w - 1, x + RAD) - max(0, x - RAD) + 1;
             rx[j] = (x >= 0 && x < A.w) ? __frcp_rn((float)ax) : 0.0f;
         }
-        const int mc = 2 * (threadIdx.x - 2 * NWARP * 32);  // merge role: strip-local columns mc, mc+1
+        // merge role (without RGB3_MERGE_WG): strip-local columns mc, mc+1
+        const int mc = 2 * (threadIdx.x - 2 * NWARP * 32);
         const int mx = xs + mc;
         const bool mvalid = (mc >= HALO) && (mc < HALO + VALID_W) && (mx < A.w);
         const int qoff = (((mc & 7) >> 2) * 32 + (mc >> 3)) * 4 + (mc & 3);
@@ -469,29 +573,8 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
                 const int E = g * n_emit + e;
                 const int qb = E & (NQ3 - 1);
                 mbar_wait(mb_qfull + 8 * qb, (unsigned)(E / NQ3) & 1u);
-                const float* qp = reinterpret_cast<const float*>(&sm.qbuf[qb][0][0][0]);
-                float b0 = pb.x, l0 = pb.y, b1 = pb.z, l1 = pb.w;
-                float2 qv[NWARP];
-#pragma unroll
-                for (int wv = 0; wv < NWARP; wv++) qv[wv] = *reinterpret_cast<const float2*>(qp + wv * 256 + qoff);
-                static_assert(NWARP == 4, "tournament written for 4 disparities per group");
-                {
-                    const bool t01 = qv[0].x >= qv[1].x, t23 = qv[2].x >= qv[3].x;
-                    const float m01 = t01 ? qv[1].x : qv[0].x, m23 = t23 ? qv[3].x : qv[2].x;
-                    const float a01 = t01 ? lab[1] : lab[0], a23 = t23 ? lab[3] : lab[2];
-                    const bool t = m01 >= m23;
-                    const float m = t ? m23 : m01, a = t ? a23 : a01;
-                    if (b0 >= m) { b0 = m; l0 = a; }
-                }
-                {
-                    const bool t01 = qv[0].y >= qv[1].y, t23 = qv[2].y >= qv[3].y;
-                    const float m01 = t01 ? qv[1].y : qv[0].y, m23 = t23 ? qv[3].y : qv[2].y;
-                    const float a01 = t01 ? lab[1] : lab[0], a23 = t23 ? lab[3] : lab[2];
-                    const bool t = m01 >= m23;
-                    const float m = t ? m23 : m01, a = t ? a23 : a01;
-                    if (b1 >= m) { b1 = m; l1 = a; }
-                }
-                if (mvalid && mrows > 0) *blp = make_float4(b0, l0, b1, l1);
+                const float4 nb = merge4(reinterpret_cast<const float*>(&sm.qbuf[qb][0][0][0]) + qoff, lab, pb);
+                if (mvalid && mrows > 0) *blp = nb;
                 __syncwarp();
                 mbar_arrive_lane0(mb_qempty + 8 * qb, lane);
                 blp += bl_row;
@@ -505,26 +588,23 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
                     for (int v = 0; v < 2; v++) sm.qbuf[b][pair][v][lane] = make_float4(inf, inf, inf, inf);
             }
             __syncthreads();  // group start
-            for (int it = 0; it < WARM3; it++) {  // the warm-up iterations only release this warp's share of the ring
-                slot_wait(g * niter + it);
-                slot_release(g * niter + it, 0u);
-            }
             if (active) {
+                // colour at the output row yq = yb0 + e: three 128-bit loads per lane from the strip-tiled plane, fetched
+                // one row ahead (the next loads are issued behind the wait for the current ones, see touch())
+                const uint4* pc = A.TC[view] + ((long long)strip * A.rows_pad + PADY + yb0) * 96 + lane;
+                uint4 cq[3];
+#pragma unroll
+                for (int c = 0; c < 3; c++) cq[c] = __ldg(pc + c * 32);
 #pragma unroll 1
                 for (int e = 0; e < n_emit; e++) {
-                    uint4 cq[3];  // colour at the output row yq = yb0 + e
+                    uint4 cqn[3];
                     {
-                        const int K = g * niter + WARM3 + e;
-                        const uint32_t sa = slot_wait(K);
-                        unsigned t = 0;
+                        pc += 96;
+                        const int dep = (int)(cq[0].x | cq[1].x | cq[2].x) & zero;
 #pragma unroll
-                        for (int c = 0; c < 3; c++) {
-                            cq[c] = lds128(sa + OFF_CQ + c * 512);
-                            t |= cq[c].x;
-                        }
-                        slot_release(K, t);
+                        for (int c = 0; c < 3; c++) cqn[c] = __ldg(pc + c * 32 + dep);
                     }
-                    const int em = e - MLAG3;
+                    const int em = RGB3_MERGE_WG ? -1 : e - MLAG3;
                     float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (em >= 0) pb = prefetch_best();
                     const int E = g * n_emit + e;
@@ -571,23 +651,64 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
                     __syncwarp();
                     mbar_arrive_lane0(mb_qfull + 8 * qb, lane);
                     if (em >= 0) merge(em, pb);
+#pragma unroll
+                    for (int c = 0; c < 3; c++) cq[c] = cqn[c];
                 }
             } else {
                 // no disparity for this trio in the (last, partial) group: its q slots hold +inf
                 for (int e = 0; e < n_emit; e++) {
-                    slot_wait(g * niter + WARM3 + e);
-                    slot_release(g * niter + WARM3 + e, 0u);
                     const int E = g * n_emit + e;
                     const int qb = E & (NQ3 - 1);
                     if (E >= NQ3) mbar_wait(mb_qempty + 8 * qb, (unsigned)(E / NQ3 - 1) & 1u);
                     if (lane == 0) mbar_arrive(mb_qfull + 8 * qb);
                     __syncwarp();
-                    merge(e, prefetch_best());
+                    if (!RGB3_MERGE_WG) merge(e, prefetch_best());
                 }
             }
-            if (active) {  // the emissions not merged inside the loop
+            if (active && !RGB3_MERGE_WG) {  // the emissions not merged inside the loop
 #pragma unroll 1
                 for (int e = max(0, n_emit - MLAG3); e < n_emit; e++) merge(e, prefetch_best());
+            }
+            __syncthreads();  // group end
+        }
+    } else {
+        // ====== STAGE 3 (RGB3_MERGE_WG): merge of the block's 4 disparities into the running (best,label) ======
+        // Thread t of these 4 warps folds strip-local columns 2t, 2t+1 of the rows the stage-2 warps publish in the q
+        // ring; the (best,label) of the previous groups is fetched two rows ahead.
+        reg_dec<R3_REGS3>();
+        const int mc = 2 * (threadIdx.x - 3 * NWARP * 32);
+        const int mx = xs + mc;
+        const bool mvalid = (mc >= HALO) && (mc < HALO + VALID_W) && (mx < A.w);
+        const int qoff = (((mc & 7) >> 2) * 32 + (mc >> 3)) * 4 + (mc & 3);
+        const size_t planeS = (size_t)A.rows_out * A.pitchS;
+        float2* __restrict__ BL = A.BL + (size_t)(chunk * 2 + view) * planeS;
+        const size_t bl_row = (size_t)A.pitchS / 2;  // 16-byte units per row of the plane
+        float4* const bl0 = reinterpret_cast<float4*>(BL + (size_t)(yb0 - A.y_out0) * A.pitchS + mx);
+        for (int g = 0; g < ngroups; g++) {
+            const int dbase = dlo + g * NWARP;
+            const float lab[NWARP] = {(float)dbase, (float)(dbase + 1), (float)(dbase + 2), (float)(dbase + 3)};
+            const bool ld_ok = (g > 0) && mvalid;
+            auto prefetch_at = [&](int r) -> float4 {  // row r of the band
+                float4 pb = make_float4(BEST_INIT_BITS_F, 0.0f, BEST_INIT_BITS_F, 0.0f);
+                if (ld_ok && r < n_emit) pb = ld_early_f4(bl0 + (size_t)r * bl_row);
+                return pb;
+            };
+            __syncthreads();  // group start
+            float4 pbA = prefetch_at(0), pbB = prefetch_at(1);
+            float4* blp = bl0;
+#pragma unroll 1
+            for (int e = 0; e < n_emit; e++) {
+                const float4 pb = pbA;
+                pbA = pbB;
+                pbB = prefetch_at(e + 2);
+                const int E = g * n_emit + e;
+                const int qb = E & (NQ3 - 1);
+                mbar_wait(mb_qfull + 8 * qb, (unsigned)(E / NQ3) & 1u);
+                const float4 nb = merge4(reinterpret_cast<const float*>(&sm.qbuf[qb][0][0][0]) + qoff, lab, pb);
+                if (mvalid) *blp = nb;
+                __syncwarp();
+                mbar_arrive_lane0(mb_qempty + 8 * qb, lane);
+                blp += bl_row;
             }
             __syncthreads();  // group end
         }

@@ -2,7 +2,7 @@
 """A/B the fused RGB-guide kernels on one box, no torch needed (host-pointer pipeline + the library's own CUDA-event
 timing of the fused kernel):
     python tools/ab_rgb.py [name=path/to/lib.so[:kernel] ...]
-Each variant runs in a child process (SB200_LIB / SB200_RGB_KERNEL are read at load / context creation).  Prints the
+AB_GUIDE=gray times the gray-guide kernel k_fused_cvf instead.  Each variant runs in a child process (SB200_LIB / SB200_RGB_KERNEL are read at load / context creation).  Prints the
 fused-kernel ms (min and median of 5 runs at 1920x1080 D=256) and a CRC of the outputs (equal CRCs = bit-identical)."""
 import json
 import os
@@ -23,7 +23,11 @@ def child(npz):
 
     d = np.load(npz)
     L, R, size_d = d["L"], d["R"], int(d["size_d"])
-    p = api.default_params(dmin=-(size_d - 1), dmax=0, guide_mode=S.GUIDE_RGB)
+    gray = os.environ.get("AB_GUIDE", "rgb") == "gray"
+    if gray:  # the gray-guide kernel on the gray versions of the same pair
+        with S.Context(0) as c0:
+            L, R = c0.rgb_to_grayscale(L), c0.rgb_to_grayscale(R)
+    p = api.default_params(dmin=-(size_d - 1), dmax=0, guide_mode=S.GUIDE_GRAY if gray else S.GUIDE_RGB)
     with S.Context(0) as ctx:
         ctx.enable_timing()
         ms = []
@@ -54,7 +58,7 @@ if __name__ == "__main__":
         if kern:
             env["SB200_RGB_KERNEL"] = kern
         try:
-            r = subprocess.run([sys.executable, __file__, "--child", npz], env=env, capture_output=True, text=True, timeout=120)
+            r = subprocess.run([sys.executable, __file__, "--child", npz], env=env, capture_output=True, text=True, timeout=45)
             print(name, r.stdout.strip() or ("FAILED: " + r.stderr.strip()[-400:]), flush=True)
         except subprocess.TimeoutExpired:
-            print(name, "TIMEOUT (120 s)", flush=True)
+            print(name, "TIMEOUT (45 s)", flush=True)
