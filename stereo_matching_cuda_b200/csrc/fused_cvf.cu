@@ -74,12 +74,35 @@ struct FusedArgs {
     int zero;               // always 0; opaque to the compiler (see touch_ops)
 };
 
-constexpr int K3_THREADS = 3 * NWARP * 32;  // three pipeline stages (warps p, p+4, p+8) per disparity
+#ifndef FUSED_MERGE_WG
+#define FUSED_MERGE_WG 1      // 1: a fourth group of 4 warps merges the block's disparities (stage 3); 0: stage 2 does
+#endif
+// three pipeline stages (warps p, p+4, p+8) per disparity, and optionally the 4 merge warps
+constexpr int K3_THREADS = (3 + FUSED_MERGE_WG) * NWARP * 32;
+// register budgets of the warp roles with the merge warps (16 warps x 128 registers at launch, traded with setmaxnreg)
+#ifndef FUSED_REGS0
+#define FUSED_REGS0 152
+#endif
+#ifndef FUSED_REGS1
+#define FUSED_REGS1 168
+#endif
+#ifndef FUSED_REGS2
+#define FUSED_REGS2 136
+#endif
+#ifndef FUSED_REGS3
+#define FUSED_REGS3 56
+#endif
+constexpr int K3_REGS3 = FUSED_REGS3;
+static_assert(FUSED_REGS0 + FUSED_REGS1 + FUSED_REGS2 + K3_REGS3 <= 512, "register file: 64 K registers per SM");
 constexpr uint32_t TM_HAND2 = 416;          // TMEM columns [416,480): stage 1 -> stage 2 hand-off rows, 2 slots
 #ifndef FUSED_HS1_ROWS
 #define FUSED_HS1_ROWS 1
 #endif
-constexpr int HS1_ROWS = FUSED_HS1_ROWS;  // rows of an iteration whose horizontal sums of b are taken in stage 1 (the rest: stage 2)
+constexpr int HS1_ROWS = FUSED_HS1_ROWS;
+#ifndef FUSED_HSA1_ROWS
+#define FUSED_HSA1_ROWS 1
+#endif
+constexpr int HSA1_ROWS = FUSED_HSA1_ROWS;  // the same for the horizontal sums of a  // rows of an iteration whose horizontal sums of b are taken in stage 1 (the rest: stage 2)
 constexpr int NQ = 4;     // depth of the ring of filtered rows between the consumer and the merging warps
 constexpr int MLAG = 2;   // a producer merges the rows its consumer emitted MLAG iterations ago
 constexpr int NS = 16;        // slots of the operand ring (one per pipeline iteration)
@@ -88,7 +111,7 @@ constexpr int LOAD_AHEAD = 5; // the loading warps fill the slot of iteration K 
 #define FUSED_AB0 0           // 1: the coefficients a, b are computed by stage 0 (which has slack), not stage 1
 #endif
 #ifndef FUSED_SPREAD
-#define FUSED_SPREAD 0        // 1: the stage-1 warp of trio p fills the iterations K = p mod 4; 0: trio 0 fills them all
+#define FUSED_SPREAD 1        // 1: the stage-1 warp of trio p fills the iterations K = p mod 4; 0: trio 0 fills them all
 #endif
 struct Slot {                 // guide operands of one iteration, filled by 4 bulk copies (8 KB)
     uint4 g[ROWS][2][32];     // (I,G) at rows yi
@@ -223,6 +246,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
 
     if (stage == 0) {
         // ====== STAGE 0: lattice cost, vertical window sums of P and I*P, their horizontal sums ======
+        if (FUSED_MERGE_WG) reg_inc<FUSED_REGS0>();
         const unsigned* __restrict__ IGm = A.IG[1 - view];
         __half2 wm[KPX];  // lattice weights (nI, nG), 0 outside the image (masks the cost)
 #pragma unroll
@@ -395,6 +419,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
         }
     } else if (stage == 1) {
         // ====== STAGE 1: a, b; their vertical and horizontal window sums ======
+        if (FUSED_MERGE_WG) reg_inc<FUSED_REGS1>();
 #if !FUSED_AB0
         float rx[KPX];  // 1 / clipped window width, 0 outside the image
 #pragma unroll
@@ -518,7 +543,12 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                         Vb[j] += b[j] - bo[r][j];
                     }
                     if (EMIT) {
-                        hsum19(Va, SA[r]);
+                        if (r < HSA1_ROWS) {
+                            hsum19(Va, SA[r]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < KPX; j++) SA[r][j] = Va[j];
+                        }
                         // balance of the pipeline: the horizontal sums of b are taken here for the rows below
                         // HS1_ROWS and in stage 2 for the others
                         if (r < HS1_ROWS) {
@@ -562,8 +592,9 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
             }
             __syncthreads();  // group end
         }
-    } else {
-        // ====== STAGE 2: q = mean_a * I + mean_b, merge of the 4 disparities ======
+    } else if (stage == 2) {
+        // ====== STAGE 2: q = mean_a * I + mean_b and, without FUSED_MERGE_WG, the merge of the 4 disparities ======
+        if (FUSED_MERGE_WG) reg_inc<FUSED_REGS2>();
         float rx[KPX];
 #pragma unroll
         for (int j = 0; j < KPX; j++) {
@@ -668,7 +699,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                         }
                         slot_release(K, t);
                     }
-                    const int em = e - MLAG;
+                    const int em = FUSED_MERGE_WG ? -1 : e - MLAG;
                     Best pb[ROWS];
                     if (em >= 0) prefetch_best(pb);
                     const int E = g * n_emit + e;
@@ -685,6 +716,12 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                     if (E >= NQ) mbar_wait(mb_qempty + 8 * qb, (unsigned)(E / NQ - 1) & 1u);  // merged NQ emissions ago
 #pragma unroll
                     for (int r = 0; r < ROWS; r++) {
+                        if (r >= HSA1_ROWS) {
+                            float ha[KPX];
+                            hsum19(SA[r], ha);
+#pragma unroll
+                            for (int j = 0; j < KPX; j++) SA[r][j] = ha[j];
+                        }
                         if (r >= HS1_ROWS) {
                             float hb[KPX];
                             hsum19(SB[r], hb);
@@ -714,19 +751,75 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                     const int qb = E & (NQ - 1);
                     if (E >= NQ) mbar_wait(mb_qempty + 8 * qb, (unsigned)(E / NQ - 1) & 1u);
                     if (lane == 0) mbar_arrive(mb_qfull + 8 * qb);
-                    Best pb[ROWS];
-                    prefetch_best(pb);
-                    merge(e, pb);
+                    __syncwarp();
+                    if (!FUSED_MERGE_WG) {
+                        Best pb[ROWS];
+                        prefetch_best(pb);
+                        merge(e, pb);
+                    }
                 }
             }
             // the emissions not merged inside the loop
-            if (active) {
+            if (active && !FUSED_MERGE_WG) {
 #pragma unroll 1
                 for (int e = max(0, n_emit - MLAG); e < n_emit; e++) {
                     Best pb[ROWS];
                     prefetch_best(pb);
                     merge(e, pb);
                 }
+            }
+            __syncthreads();  // group end
+        }
+    } else {
+        // ====== STAGE 3 (FUSED_MERGE_WG): merge of the block's 4 disparities into the running (best,label) ======
+        // Thread t of these 4 warps folds strip-local columns 2t, 2t+1 of the rows the stage-2 warps publish in the q
+        // ring; the (best,label) of the previous groups is fetched two emissions ahead.
+        reg_dec<K3_REGS3>();
+        const int mc = 2 * (threadIdx.x - 3 * NWARP * 32);
+        const int mx = xs + mc;
+        const bool mvalid = (mc >= HALO) && (mc < HALO + VALID_W) && (mx < A.w);
+        const int qoff = (((mc & 7) >> 2) * 32 + (mc >> 3)) * 4 + (mc & 3);
+        const size_t planeS = (size_t)A.rows_out * A.pitchS;
+        float2* __restrict__ BL = A.BL + (size_t)(chunk * 2 + view) * planeS;
+        const size_t bl_row = (size_t)A.pitchS / 2;  // 16-byte units per row of the plane
+        float4* const bl0 = reinterpret_cast<float4*>(BL + (size_t)(yb0 - A.y_out0) * A.pitchS + mx);
+        const int band_rows = yb1 - yb0;
+        for (int g = 0; g < ngroups; g++) {
+            const int dbase = dlo + g * NWARP;
+            const float lab[NWARP] = {(float)dbase, (float)(dbase + 1), (float)(dbase + 2), (float)(dbase + 3)};
+            const bool ld_ok = (g > 0) && mvalid;
+            auto prefetch_at = [&](int e, float4 (&pb)[ROWS]) {  // the rows of emission e
+#pragma unroll
+                for (int r = 0; r < ROWS; r++) {
+                    pb[r] = make_float4(BEST_INIT_BITS_F, 0.0f, BEST_INIT_BITS_F, 0.0f);
+                    if (ld_ok && e * ROWS + r < band_rows) pb[r] = ld_early_f4(bl0 + (size_t)(e * ROWS + r) * bl_row);
+                }
+            };
+            __syncthreads();  // group start
+            float4 pbA[ROWS], pbB[ROWS];
+            prefetch_at(0, pbA);
+            prefetch_at(1, pbB);
+            float4* blp = bl0;
+#pragma unroll 1
+            for (int e = 0; e < n_emit; e++) {
+                float4 pb[ROWS];
+#pragma unroll
+                for (int r = 0; r < ROWS; r++) {
+                    pb[r] = pbA[r];
+                    pbA[r] = pbB[r];
+                }
+                prefetch_at(e + 2, pbB);
+                const int E = g * n_emit + e;
+                const int qb = E & (NQ - 1);
+                mbar_wait(mb_qfull + 8 * qb, (unsigned)(E / NQ) & 1u);
+#pragma unroll
+                for (int r = 0; r < ROWS; r++) {
+                    const float4 nb = merge4(reinterpret_cast<const float*>(&sm.qbuf[qb][0][r][0][0]) + qoff, ROWS * 256, lab, pb[r]);
+                    if (mvalid && e * ROWS + r < band_rows) blp[r * bl_row] = nb;
+                }
+                __syncwarp();
+                mbar_arrive_lane0(mb_qempty + 8 * qb, lane);
+                blp += ROWS * bl_row;
             }
             __syncthreads();  // group end
         }

@@ -98,40 +98,6 @@ static_assert(sizeof(Smem3) <= 232448, "Smem3 exceeds the 227 KB a block may opt
 
 __device__ __forceinline__ unsigned word_of(const uint4& v, int k) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; }
 
-// Fold the 4 disparities of a group into the running (best,label) of two columns: ascending d, `best >= q` (the last
-// slice wins ties, guidedFilter.cu:406).  "Minimum, the later index on a tie" is associative, so a 2-level tournament
-// gives what the reference's sequential scan gives, with a shorter dependency chain.  qp: this thread's two columns
-// in the q row of the group's first warp (the other warps follow at 256 floats).
-__device__ __forceinline__ float4 merge4(const float* qp, const float (&lab)[NWARP], const float4 pb) {
-    static_assert(NWARP == 4, "tournament written for 4 disparities per group");
-    float b0 = pb.x, l0 = pb.y, b1 = pb.z, l1 = pb.w;
-    float2 qv[NWARP];
-#pragma unroll
-    for (int wv = 0; wv < NWARP; wv++) qv[wv] = *reinterpret_cast<const float2*>(qp + wv * 256);
-    {
-        const bool t01 = qv[0].x >= qv[1].x, t23 = qv[2].x >= qv[3].x;
-        const float m01 = t01 ? qv[1].x : qv[0].x, m23 = t23 ? qv[3].x : qv[2].x;
-        const float a01 = t01 ? lab[1] : lab[0], a23 = t23 ? lab[3] : lab[2];
-        const bool t = m01 >= m23;
-        const float m = t ? m23 : m01, a = t ? a23 : a01;
-        if (b0 >= m) { b0 = m; l0 = a; }
-    }
-    {
-        const bool t01 = qv[0].y >= qv[1].y, t23 = qv[2].y >= qv[3].y;
-        const float m01 = t01 ? qv[1].y : qv[0].y, m23 = t23 ? qv[3].y : qv[2].y;
-        const float a01 = t01 ? lab[1] : lab[0], a23 = t23 ? lab[3] : lab[2];
-        const bool t = m01 >= m23;
-        const float m = t ? m23 : m01, a = t ? a23 : a01;
-        if (b1 >= m) { b1 = m; l1 = a; }
-    }
-    return make_float4(b0, l0, b1, l1);
-}
-
-template <int N>
-__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N>
-__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-
 __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Smem3& sm = *reinterpret_cast<Smem3*>(smem_raw);
@@ -573,7 +539,7 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
                 const int E = g * n_emit + e;
                 const int qb = E & (NQ3 - 1);
                 mbar_wait(mb_qfull + 8 * qb, (unsigned)(E / NQ3) & 1u);
-                const float4 nb = merge4(reinterpret_cast<const float*>(&sm.qbuf[qb][0][0][0]) + qoff, lab, pb);
+                const float4 nb = merge4(reinterpret_cast<const float*>(&sm.qbuf[qb][0][0][0]) + qoff, 256, lab, pb);
                 if (mvalid && mrows > 0) *blp = nb;
                 __syncwarp();
                 mbar_arrive_lane0(mb_qempty + 8 * qb, lane);
@@ -704,7 +670,7 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
                 const int E = g * n_emit + e;
                 const int qb = E & (NQ3 - 1);
                 mbar_wait(mb_qfull + 8 * qb, (unsigned)(E / NQ3) & 1u);
-                const float4 nb = merge4(reinterpret_cast<const float*>(&sm.qbuf[qb][0][0][0]) + qoff, lab, pb);
+                const float4 nb = merge4(reinterpret_cast<const float*>(&sm.qbuf[qb][0][0][0]) + qoff, 256, lab, pb);
                 if (mvalid) *blp = nb;
                 __syncwarp();
                 mbar_arrive_lane0(mb_qempty + 8 * qb, lane);

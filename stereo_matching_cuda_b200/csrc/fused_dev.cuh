@@ -203,6 +203,42 @@ __device__ __forceinline__ float inv_rows(const float* lut, int y, int y_global0
     return lut[ay];
 }
 
+// Fold the 4 disparities of a group into the running (best,label) of two columns: ascending d, `best >= q` (the last
+// slice wins ties, guidedFilter.cu:406).  "Minimum, the later index on a tie" is associative, so a 2-level tournament
+// gives what the reference's sequential scan gives, with a shorter dependency chain.  qp: this thread's two columns
+// in the q row of the group's first warp (the other warps follow at `stride` floats).
+__device__ __forceinline__ float4 merge4(const float* qp, int stride, const float (&lab)[NWARP], const float4 pb) {
+    static_assert(NWARP == 4, "tournament written for 4 disparities per group");
+    float b0 = pb.x, l0 = pb.y, b1 = pb.z, l1 = pb.w;
+    float2 qv[NWARP];
+#pragma unroll
+    for (int wv = 0; wv < NWARP; wv++) qv[wv] = *reinterpret_cast<const float2*>(qp + wv * stride);
+    {
+        const bool t01 = qv[0].x >= qv[1].x, t23 = qv[2].x >= qv[3].x;
+        const float m01 = t01 ? qv[1].x : qv[0].x, m23 = t23 ? qv[3].x : qv[2].x;
+        const float a01 = t01 ? lab[1] : lab[0], a23 = t23 ? lab[3] : lab[2];
+        const bool t = m01 >= m23;
+        const float m = t ? m23 : m01, a = t ? a23 : a01;
+        if (b0 >= m) { b0 = m; l0 = a; }
+    }
+    {
+        const bool t01 = qv[0].y >= qv[1].y, t23 = qv[2].y >= qv[3].y;
+        const float m01 = t01 ? qv[1].y : qv[0].y, m23 = t23 ? qv[3].y : qv[2].y;
+        const float a01 = t01 ? lab[1] : lab[0], a23 = t23 ? lab[3] : lab[2];
+        const bool t = m01 >= m23;
+        const float m = t ? m23 : m01, a = t ? a23 : a01;
+        if (b1 >= m) { b1 = m; l1 = a; }
+    }
+    return make_float4(b0, l0, b1, l1);
+}
+
+// register budget of a warp role: one warpgroup (4 consecutive warps) grows or shrinks its per-thread register count;
+// ptxas allocates the code dominated by the instruction against the new count
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // Chunk merge, interleaved (best,label) planes: fold the per-chunk (best,label) planes in chunk order with the same rule.
 __global__ void k_merge_chunks_bl(const float2* __restrict__ BL, int n_chunks, int view, int rows, int w, int pitchS,
                                   float* __restrict__ best, float* __restrict__ disp) {
