@@ -96,17 +96,20 @@ constexpr int K3_REGS3 = FUSED_REGS3;
 static_assert(FUSED_REGS0 + FUSED_REGS1 + FUSED_REGS2 + K3_REGS3 <= 512, "register file: 64 K registers per SM");
 constexpr uint32_t TM_HAND2 = 416;          // TMEM columns [416,480): stage 1 -> stage 2 hand-off rows, 2 slots
 #ifndef FUSED_HS1_ROWS
-#define FUSED_HS1_ROWS 1
+#define FUSED_HS1_ROWS 0
 #endif
 constexpr int HS1_ROWS = FUSED_HS1_ROWS;
 #ifndef FUSED_HSA1_ROWS
-#define FUSED_HSA1_ROWS 1
+#define FUSED_HSA1_ROWS 0
 #endif
 constexpr int HSA1_ROWS = FUSED_HSA1_ROWS;  // the same for the horizontal sums of a  // rows of an iteration whose horizontal sums of b are taken in stage 1 (the rest: stage 2)
 constexpr int NQ = 4;     // depth of the ring of filtered rows between the consumer and the merging warps
 constexpr int MLAG = 2;   // a producer merges the rows its consumer emitted MLAG iterations ago
 constexpr int NS = 16;        // slots of the operand ring (one per pipeline iteration)
 constexpr int LOAD_AHEAD = 5; // the loading warps fill the slot of iteration K + LOAD_AHEAD while they work on K
+#ifndef FUSED_HS0_IP_ROWS
+#define FUSED_HS0_IP_ROWS 0   // rows of an iteration whose horizontal sums of I*P are taken in stage 0 (the rest: stage 1)
+#endif
 #ifndef FUSED_AB0
 #define FUSED_AB0 0           // 1: the coefficients a, b are computed by stage 0 (which has slack), not stage 1
 #endif
@@ -375,7 +378,12 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                         }
                         tm_st4(tP + 4 * slots[r], pneg[r]);
                         hsum19(VP, SP[r]);
-                        hsum19(VIP, SIP[r]);
+                        if (r < FUSED_HS0_IP_ROWS) {
+                            hsum19(VIP, SIP[r]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < KPX; j++) SIP[r][j] = VIP[j];
+                        }
 #if FUSED_AB0
                         {   // a, b at row ya = yi - 9 (guidedFilter.cu:345-354), handed over in place of the sums
                             const float ry1 = inv_rows(sm.ry_lut[0], y_first + it * ROWS + r - RAD, A.y_global0, A.frame_h);
@@ -515,6 +523,12 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                 float SA[ROWS][KPX], SB[ROWS][KPX];
 #pragma unroll
                 for (int r = 0; r < ROWS; r++) {
+                    if (r >= FUSED_HS0_IP_ROWS) {  // stage 0 left this row's I*P sums to this stage
+                        float hs[KPX];
+                        hsum19(SIP[r], hs);
+#pragma unroll
+                        for (int j = 0; j < KPX; j++) SIP[r][j] = hs[j];
+                    }
                     // ---- a, b at row ya = yi - 9
                     float a[KPX], b[KPX];
 #if FUSED_AB0
