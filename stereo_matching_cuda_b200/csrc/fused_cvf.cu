@@ -126,7 +126,7 @@ constexpr uint32_t SLOT_BYTES = sizeof(Slot);
 struct SmemLayout {
     Slot slot[NS];
     uint64_t sfull[NS], sempty[NS];       // mbarriers of the operand ring: bulk copies -> 12 warps and back
-    float4 qbuf[NQ][NWARP][ROWS][2][32];  // filtered rows of each consumer warp
+    float4 qbuf[NQ][NWARP][ROWS][2][QV];  // filtered rows of each consumer warp
     uint64_t qfull[NQ], qempty[NQ];       // mbarriers of the q ring (4 stage-2 warps write, the same 4 warps merge)
     uint64_t full2[NWARP][2], empty2[NWARP][2];  // mbarriers of the 2-slot stage 1 -> stage 2 hand-off of each pair
     float ry_lut[2][WIN + 1];             // [0][n] = 1/(S*n), [1][n] = 1/n for a clipped window of n rows; [.][0] = 0
@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
         // (HALO, VALID_W and mc are even: the two columns are inside the strip's valid range together; for an odd
         //  image width the second one may be the first padding column of the plane, which is never read)
         const bool mvalid = (mc >= HALO) && (mc < HALO + VALID_W) && (mx < A.w);
-        const int qoff = (((mc & 7) >> 2) * 32 + (mc >> 3)) * 4 + (mc & 3);
+        const int qoff = (((mc & 7) >> 2) * QV + (mc >> 3)) * 4 + (mc & 3);
         const size_t planeS = (size_t)A.rows_out * A.pitchS;
         float2* __restrict__ BL = A.BL + (size_t)(chunk * 2 + view) * planeS;
         const size_t bl_row = (size_t)A.pitchS / 2;  // 16-byte units per row of the plane (pitchS is a multiple of 4)
@@ -655,7 +655,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                     float b0 = pb[r].x, l0 = pb[r].y, b1 = pb[r].z, l1 = pb[r].w;
                     float2 qv[NWARP];
 #pragma unroll
-                    for (int wv = 0; wv < NWARP; wv++) qv[wv] = *reinterpret_cast<const float2*>(qp + wv * (ROWS * 256) + qoff);
+                    for (int wv = 0; wv < NWARP; wv++) qv[wv] = *reinterpret_cast<const float2*>(qp + wv * (ROWS * 2 * QV * 4) + qoff);
                     // "minimum, the later disparity on a tie" is associative: a 2-level tournament
                     // gives what the reference's sequential `best >= q` scan gives, with a shorter chain
                     static_assert(NWARP == 4, "tournament written for 4 disparities per group");
@@ -792,7 +792,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
         const int mc = 2 * (threadIdx.x - 3 * NWARP * 32);
         const int mx = xs + mc;
         const bool mvalid = (mc >= HALO) && (mc < HALO + VALID_W) && (mx < A.w);
-        const int qoff = (((mc & 7) >> 2) * 32 + (mc >> 3)) * 4 + (mc & 3);
+        const int qoff = (((mc & 7) >> 2) * QV + (mc >> 3)) * 4 + (mc & 3);
         const size_t planeS = (size_t)A.rows_out * A.pitchS;
         float2* __restrict__ BL = A.BL + (size_t)(chunk * 2 + view) * planeS;
         const size_t bl_row = (size_t)A.pitchS / 2;  // 16-byte units per row of the plane
@@ -828,7 +828,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                 mbar_wait(mb_qfull + 8 * qb, (unsigned)(E / NQ) & 1u);
 #pragma unroll
                 for (int r = 0; r < ROWS; r++) {
-                    const float4 nb = merge4(reinterpret_cast<const float*>(&sm.qbuf[qb][0][r][0][0]) + qoff, ROWS * 256, lab, pb[r]);
+                    const float4 nb = merge4(reinterpret_cast<const float*>(&sm.qbuf[qb][0][r][0][0]) + qoff, ROWS * 2 * QV * 4, lab, pb[r]);
                     if (mvalid && e * ROWS + r < band_rows) blp[r * bl_row] = nb;
                 }
                 __syncwarp();
@@ -913,7 +913,10 @@ __global__ void __launch_bounds__(256) k_prep(const PrepArgs P) {
     const int x0 = blockIdx.x * PT - P.padx;
     const int y0 = blockIdx.y * PT - PADY;
     const int tid = threadIdx.x;
-    for (int i = tid; i < PP * PP; i += 256) {
+    // a tile that lies entirely in the padding only stores the padding values
+    const bool tile_in = x0 + PT > 0 && x0 < P.w && y0 + PT > 0 && y0 < P.h_held && y0 + PT + P.y_global0 > 0 &&
+                         y0 + P.y_global0 < P.frame_h;
+    for (int i = tid; tile_in && i < PP * PP; i += 256) {
         int py = i / PP, px = i - py * PP;
         int x = x0 + px - RAD, y = y0 + py - RAD;
         int yg = y + P.y_global0;
@@ -921,7 +924,7 @@ __global__ void __launch_bounds__(256) k_prep(const PrepArgs P) {
         sI[py][px] = in ? (int)P.gray[(size_t)y * P.w + x] : 0;
     }
     __syncthreads();
-    for (int i = tid; i < PP * PT; i += 256) {
+    for (int i = tid; tile_in && i < PP * PT; i += 256) {
         int py = i / PT, tx = i - py * PT;
         int s1 = 0, s2 = 0;
 #pragma unroll

@@ -87,7 +87,7 @@ constexpr uint32_t SLOT3_BYTES = sizeof(Slot3);
 struct Smem3 {
     Slot3 slot[NS3];                   // operand ring of stages 0 and 1
     float4 ringB[NWARP][WIN][4][32];   // stage-1 private rings: a_b (planes 0,1) and b (planes 2,3)
-    float4 qbuf[NQ3][NWARP][2][32];    // filtered row of each stage-2 warp
+    float4 qbuf[NQ3][NWARP][2][QV];    // filtered row of each stage-2 warp
     uint64_t sfull[NS3], sempty[NS3];
     uint64_t qfull[NQ3], qempty[NQ3];
     uint64_t full2[NWARP][2], empty2[NWARP][2];
@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
         const int mc = 2 * (threadIdx.x - 2 * NWARP * 32);
         const int mx = xs + mc;
         const bool mvalid = (mc >= HALO) && (mc < HALO + VALID_W) && (mx < A.w);
-        const int qoff = (((mc & 7) >> 2) * 32 + (mc >> 3)) * 4 + (mc & 3);
+        const int qoff = (((mc & 7) >> 2) * QV + (mc >> 3)) * 4 + (mc & 3);
         const size_t planeS = (size_t)A.rows_out * A.pitchS;
         float2* __restrict__ BL = A.BL + (size_t)(chunk * 2 + view) * planeS;
         const size_t bl_row = (size_t)A.pitchS / 2;  // 16-byte units per row of the plane
@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
                 const int E = g * n_emit + e;
                 const int qb = E & (NQ3 - 1);
                 mbar_wait(mb_qfull + 8 * qb, (unsigned)(E / NQ3) & 1u);
-                const float4 nb = merge4(reinterpret_cast<const float*>(&sm.qbuf[qb][0][0][0]) + qoff, 256, lab, pb);
+                const float4 nb = merge4(reinterpret_cast<const float*>(&sm.qbuf[qb][0][0][0]) + qoff, 2 * QV * 4, lab, pb);
                 if (mvalid && mrows > 0) *blp = nb;
                 __syncwarp();
                 mbar_arrive_lane0(mb_qempty + 8 * qb, lane);
@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
         const int mc = 2 * (threadIdx.x - 3 * NWARP * 32);
         const int mx = xs + mc;
         const bool mvalid = (mc >= HALO) && (mc < HALO + VALID_W) && (mx < A.w);
-        const int qoff = (((mc & 7) >> 2) * 32 + (mc >> 3)) * 4 + (mc & 3);
+        const int qoff = (((mc & 7) >> 2) * QV + (mc >> 3)) * 4 + (mc & 3);
         const size_t planeS = (size_t)A.rows_out * A.pitchS;
         float2* __restrict__ BL = A.BL + (size_t)(chunk * 2 + view) * planeS;
         const size_t bl_row = (size_t)A.pitchS / 2;  // 16-byte units per row of the plane
@@ -670,7 +670,7 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
                 const int E = g * n_emit + e;
                 const int qb = E & (NQ3 - 1);
                 mbar_wait(mb_qfull + 8 * qb, (unsigned)(E / NQ3) & 1u);
-                const float4 nb = merge4(reinterpret_cast<const float*>(&sm.qbuf[qb][0][0][0]) + qoff, 256, lab, pb);
+                const float4 nb = merge4(reinterpret_cast<const float*>(&sm.qbuf[qb][0][0][0]) + qoff, 2 * QV * 4, lab, pb);
                 if (mvalid) *blp = nb;
                 __syncwarp();
                 mbar_arrive_lane0(mb_qempty + 8 * qb, lane);
@@ -734,7 +734,10 @@ __global__ void __launch_bounds__(256) k_prep_rgb3(const Rgb3PrepArgs P) {
     const int x0 = blockIdx.x * RPT3 - P.padx;
     const int y0 = blockIdx.y * RPT3 - PADY;
     const int tid = threadIdx.x;
-    for (int i = tid; i < RPP3 * RPP3; i += 256) {
+    // a tile that lies entirely in the padding (29 % of them at 1080p D=256) only stores zeros
+    const bool tile_in = x0 + RPT3 > 0 && x0 < P.w && y0 + RPT3 > 0 && y0 < P.h_held && y0 + RPT3 + P.y_global0 > 0 &&
+                         y0 + P.y_global0 < P.frame_h;
+    for (int i = tid; tile_in && i < RPP3 * RPP3; i += 256) {
         int py = i / RPP3, px = i - py * RPP3;
         int x = x0 + px - RAD, y = y0 + py - RAD;
         int yg = y + P.y_global0;
@@ -745,7 +748,7 @@ __global__ void __launch_bounds__(256) k_prep_rgb3(const Rgb3PrepArgs P) {
         sC[2][py][px] = in ? (int)q[2] : 0;
     }
     __syncthreads();
-    for (int i = tid; i < RPP3 * RPT3; i += 256) {
+    for (int i = tid; tile_in && i < RPP3 * RPT3; i += 256) {
         int py = i / RPT3, tx = i - py * RPT3;
         int s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll

@@ -18,6 +18,13 @@ constexpr int NTHREADS = 2 * NWARP * 32;
 constexpr int ROWS = 2;           // image rows per pipeline iteration: independent horizontal work for ILP
 constexpr int PADY = 40;          // padding rows above/below the prepared planes
 constexpr float BEST_INIT_BITS_F = 3.3961514e38f;  // 0x7F7F7F7F, main.cu:112
+// A filtered row in the q ring: pixels 0..3 and 4..7 of every lane as two planes of float4.  The planes are 36 float4
+// apart (4 of padding): a merging thread reads 8 bytes of one plane, and with 32 float4 per plane the two planes of a
+// half-warp's reads fell on the same 16 banks (ncu: twice the ideal wavefronts on these loads)
+#ifndef FUSED_QV
+#define FUSED_QV 36
+#endif
+constexpr int QV = FUSED_QV;
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
