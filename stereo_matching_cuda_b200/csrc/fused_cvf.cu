@@ -48,9 +48,10 @@ namespace {
 
 
 struct FusedArgs {
-    const unsigned* IG[2];  // per IMAGE (0 left, 1 right): padded half2 (I, G=I[x-1]-I[x+1]); -> element (0,0)
-    size_t shift_stride;    // IG[i] + s*shift_stride (s = 0..3) is the same plane moved left by s elements, so the
-                            // match operands at x+d are two aligned 16 B loads from copy (d & 3)
+    const unsigned* IG[2];  // per IMAGE (0 left, 1 right): padded half2 (I, G=I[x-1]-I[x+1]), 4 copies: copy s at
+    size_t shift_stride;    // IG[i] + s*shift_stride is the plane moved left by s elements, stored de-interleaved
+    size_t ig_origin;       // (fused_dev.cuh, match_ptrs); linear element index of pixel (0,0) in a copy; the match
+                            // operands at x+d are two aligned, fully coalesced 16 B loads from copy (d & 3)
     // Guide operands, STRIP-TILED (see k_prep): record (strip, padded row) of each plane holds the 256 columns of the
     // strip as [16-byte chunk c][lane][16 B], i.e. exactly the bytes lane L reads with its c-th 128-bit load, so one
     // bulk copy per plane and row pair fills the shared-memory operand ring without bank conflicts on the read side.
@@ -84,10 +85,10 @@ constexpr int K3_THREADS = (3 + FUSED_MERGE_WG) * NWARP * 32;
 #define FUSED_REGS0 152
 #endif
 #ifndef FUSED_REGS1
-#define FUSED_REGS1 168
+#define FUSED_REGS1 176
 #endif
 #ifndef FUSED_REGS2
-#define FUSED_REGS2 136
+#define FUSED_REGS2 128
 #endif
 #ifndef FUSED_REGS3
 #define FUSED_REGS3 56
@@ -139,13 +140,12 @@ struct ProdOps {
     uint4 m0, m1;     // match (I,G) half2 x8 at row yi, columns x+d (from the copy shifted by d & 3)
 };
 struct ProdPtrs {
-    const unsigned* m;
+    const unsigned *m0, *m1;  // pixels 0..3 and 4..7 of this lane (see match_ptrs)
 };
 
 __device__ __forceinline__ void load_prod(ProdOps& o, const ProdPtrs& p, int dep) {
-    const uint4* pm = reinterpret_cast<const uint4*>(p.m + dep);
-    o.m0 = __ldg(pm);
-    o.m1 = __ldg(pm + 1);
+    o.m0 = __ldg(reinterpret_cast<const uint4*>(p.m0 + dep));
+    o.m1 = __ldg(reinterpret_cast<const uint4*>(p.m1 + dep));
 }
 // One word of every load of `o`, OR-ed together.  The next step's loads are made to depend on
 // it (masked to zero by a kernel argument the compiler cannot see through), so the scoreboard
@@ -283,13 +283,15 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
             if (active) {
                 ProdPtrs rp;
                 const long long r0 = (long long)y_first * pitch + xl;
-                rp.m = IGm + (size_t)(d & 3) * A.shift_stride + r0 + (d - (d & 3));
+                match_ptrs(IGm + (size_t)(d & 3) * A.shift_stride, (long long)A.ig_origin + r0 + (d - (d & 3)),
+                           A.shift_stride / 2, rp.m0, rp.m1);
                 int slot = 0;
                 ProdOps opsA[ROWS], opsB[ROWS];
 #pragma unroll
                 for (int r = 0; r < ROWS; r++) {
                     load_prod(opsA[r], rp, 0);
-                    rp.m += pitch;
+                    rp.m0 += pitch / 2;
+                        rp.m1 += pitch / 2;
                 }
                 auto iter = [&](const ProdOps (&o)[ROWS], ProdOps (&nxt)[ROWS], int it) {
                     int dep = 0;
@@ -299,7 +301,8 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
 #pragma unroll
                     for (int r = 0; r < ROWS; r++) {
                         load_prod(nxt[r], rp, dep);
-                        rp.m += pitch;
+                        rp.m0 += pitch / 2;
+                        rp.m1 += pitch / 2;
                     }
                     // guide operands of this iteration from the shared-memory ring
                     uint4 gq[ROWS][2], ioq[ROWS];
@@ -877,11 +880,12 @@ struct PrepArgs {
 };
 
 __device__ __forceinline__ void store_ig(const PrepArgs& P, size_t o, unsigned v) {
-    P.IG[o] = v;
-    if (P.shift_stride) {
+    if (P.shift_stride) {  // 4 copies moved left by 0..3 elements, each de-interleaved (fused_dev.cuh, match_ptrs)
 #pragma unroll
-        for (int s = 1; s < 4; s++)
-            if (o >= (size_t)s) P.IG[s * P.shift_stride + o - s] = v;
+        for (int s = 0; s < 4; s++)
+            if (o >= (size_t)s) P.IG[s * P.shift_stride + deint_index(o - s, P.shift_stride / 2)] = v;
+    } else {
+        P.IG[o] = v;
     }
 }
 
@@ -1092,13 +1096,14 @@ static int run_fused(sb200_ctx* ctx, const sb200_params* p, const uint8_t* const
     FusedArgs A;
     const size_t origin = (size_t)PADY * pitch + padx;
     for (int i = 0; i < 2; i++) {
-        A.IG[i] = IG[i] + origin;
+        A.IG[i] = IG[i];
         A.Tg[i] = reinterpret_cast<const uint4*>(Tg[i]);
         A.TI[i] = reinterpret_cast<const uint4*>(TI[i]);
         A.Tst[i] = reinterpret_cast<const uint4*>(Tst[i]);
         A.dmin[i] = dmin[i];
     }
     A.shift_stride = plane;
+    A.ig_origin = origin;
     A.rows_pad = rows_pad;
     A.pitch = pitch;
     A.w = g.w;

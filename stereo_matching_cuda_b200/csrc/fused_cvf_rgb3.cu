@@ -24,8 +24,9 @@
 namespace {
 
 struct Rgb3Args {
-    const unsigned* IG[2];  // per IMAGE: padded half2 (I, G); + s*shift_stride = the plane moved left by s elements
-    size_t shift_stride;
+    const unsigned* IG[2];  // per IMAGE: padded half2 (I, G); + s*shift_stride = the plane moved left by s elements,
+    size_t shift_stride;    // de-interleaved (fused_dev.cuh, match_ptrs)
+    size_t ig_origin;       // linear element index of pixel (0,0) in a copy
     // strip-tiled planes, record (strip, padded row) = [16-byte chunk][lane][16 B] (see fused_cvf.cu, k_prep)
     const uint4* Tg[2];     // per IMAGE: (I,G) half2, 2 chunks, 1 KB per record
     const uint4* TC[2];     // per IMAGE: colour as halves, chunk c = channel c of the lane's 8 pixels, 1.5 KB per record
@@ -286,18 +287,22 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
             __syncthreads();  // group start
             if (active) {
                 const long long r0 = (long long)y_first * pitch + xl;
-                const unsigned* pm = IGm + (size_t)(d & 3) * A.shift_stride + r0 + (d - (d & 3));
-                uint4 m0 = __ldg(reinterpret_cast<const uint4*>(pm));
-                uint4 m1 = __ldg(reinterpret_cast<const uint4*>(pm) + 1);
-                pm += pitch;
+                const unsigned *pm0, *pm1;
+                match_ptrs(IGm + (size_t)(d & 3) * A.shift_stride, (long long)A.ig_origin + r0 + (d - (d & 3)),
+                           A.shift_stride / 2, pm0, pm1);
+                uint4 m0 = __ldg(reinterpret_cast<const uint4*>(pm0));
+                uint4 m1 = __ldg(reinterpret_cast<const uint4*>(pm1));
+                pm0 += pitch / 2;
+                pm1 += pitch / 2;
                 int slot = 0;
 #pragma unroll 1
                 for (int it = 0; it < niter; it++) {
                     // next row's match operands, issued behind the wait for this row's (see touch() in fused_cvf.cu)
                     const int dep = (int)(m0.x | m1.x) & zero;
-                    const uint4 n0 = __ldg(reinterpret_cast<const uint4*>(pm + dep));
-                    const uint4 n1 = __ldg(reinterpret_cast<const uint4*>(pm + dep) + 1);
-                    pm += pitch;
+                    const uint4 n0 = __ldg(reinterpret_cast<const uint4*>(pm0 + dep));
+                    const uint4 n1 = __ldg(reinterpret_cast<const uint4*>(pm1 + dep));
+                    pm0 += pitch / 2;
+                    pm1 += pitch / 2;
                     uint4 gq[2], cn[3], co[3];
                     const int K = g * niter + it;
                     const uint32_t sa = slot_wait(K);
@@ -886,13 +891,14 @@ int sbf_pair_disparity_rgb3(sb200_ctx* ctx, const sb200_params* p, const uint8_t
     Rgb3Args A;
     const size_t origin = (size_t)PADY * pitch + padx;
     for (int i = 0; i < 2; i++) {
-        A.IG[i] = IG[i] + origin;
+        A.IG[i] = IG[i];
         A.Tg[i] = reinterpret_cast<const uint4*>(Tg[i]);
         A.TC[i] = reinterpret_cast<const uint4*>(TC[i]);
         A.TS[i] = reinterpret_cast<const uint4*>(TS[i]);
         A.dmin[i] = dmin[i];
     }
     A.shift_stride = plane;
+    A.ig_origin = origin;
     A.rows_pad = rows_pad;
     A.pitch = pitch;
     A.w = g.w;

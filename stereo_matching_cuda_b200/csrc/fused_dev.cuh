@@ -164,6 +164,27 @@ __device__ __forceinline__ void hsum19(const float (&v)[KPX], float (&h)[KPX]) {
     h[7] = ((C - l[5]) + Tp1) + vp2;
 }
 
+// Match operands.  A warp reads, per row, the 8 pixels x 32 lanes at columns x + d: 32 B per lane.  From a linear
+// plane that is two 128-bit loads whose lanes are 32 B apart (half of every sector fetched by each, 8.75 L1 tag
+// requests per load in ncu).  The shifted copies of the (I,G) plane are therefore stored DE-INTERLEAVED: the even
+// groups of 4 pixels in the first half of a copy, the odd groups in the second half, so that the first 4 pixels of all
+// lanes are 512 contiguous bytes, and the next 4 likewise.  match_ptrs() returns the two pointers for linear element
+// index e (a multiple of 4) of a copy; both advance by pitch/2 elements per row.
+__device__ __host__ __forceinline__ size_t deint_index(size_t i, size_t half_plane) {  // linear element -> stored element
+    const size_t g4 = i >> 2;
+    return (g4 & 1 ? half_plane : 0) + (g4 >> 1) * 4 + (i & 3);
+}
+__device__ __forceinline__ void match_ptrs(const unsigned* copy, long long e, size_t half_plane, const unsigned*& p0,
+                                           const unsigned*& p1) {
+    if ((e >> 2) & 1) {
+        p0 = copy + half_plane + (e - 4) / 2;
+        p1 = copy + (e + 4) / 2;
+    } else {
+        p0 = copy + e / 2;
+        p1 = copy + half_plane + e / 2;
+    }
+}
+
 __device__ __forceinline__ __half2 u2h2(unsigned u) { return *reinterpret_cast<__half2*>(&u); }
 __device__ __forceinline__ unsigned h22u(__half2 h) { return *reinterpret_cast<unsigned*>(&h); }
 
