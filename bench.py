@@ -137,10 +137,10 @@ def make_inputs(w, h, size_d, channels, n_sets, y0=0, rows=None, seed0=0):
     return [synth.make_pair(w, h, size_d, channels=channels, seed=seed0 + s, y0=y0, rows=rows) for s in range(n_sets)]
 
 
-def ncu_traffic():
-    """DRAM bytes per launch of the dominant kernel, from the committed ncu --set full capture"""
+def ncu_traffic(guide="gray"):
+    """DRAM bytes per launch (and pipe utilisations) of the dominant kernel, from the committed ncu --set full capture"""
     try:
-        with open(os.path.join(ROOT, "profiles", "fused_ncu.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "fused_ncu.json" if guide == "gray" else "fused_rgb3_ncu.json")) as f:
             return json.load(f)
     except Exception:
         return None
@@ -434,7 +434,7 @@ def main():
         peak_instr = 148 * 128 * pk["sm_max_mhz"] * 1e6  # FP32 lane-instructions/s at the max SM clock
         ipc = INSTR_PER_CELL if args.guide == "gray" else 71
         achieved = ipc * cells_per_launch / (fk * 1e-3)
-        tr = ncu_traffic()
+        tr = ncu_traffic(args.guide)
         line = {
             "metric": "pixel-disparities/sec", "value": value, "unit": "px*d/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -460,6 +460,11 @@ def main():
                 "note": "north_star names the FP32 CUDA-core pipe as this kernel's roofline (no dense contraction; see "
                         "hbm_frac_of_kernel_time for how little of the kernel's time its DRAM traffic explains)",
                 "hbm_frac_of_kernel_time": (tr["dram_bytes_per_launch"] / (pk["hbm_gbs"] * 1e9)) / (fk * 1e-3) if tr and mode == "dp" and args.workload == "c3" else None,
+                "ncu": {k: tr.get(k) for k in ("l1tex_data_pipe_pct", "issue_active_pct", "fma_pipe_pct", "alu_pipe_pct",
+                                               "kernel_ms_under_ncu")} if tr and mode == "dp" and args.workload == "c3" else None,
+                "ncu_note": "the kernel's busiest unit is the L1TEX/shared-memory data pipe (warp shuffles of the horizontal window "
+                            "sums + 128-bit shared loads of the operand ring), not the FP32 pipe: l1tex_data_pipe_pct is its "
+                            "utilisation in the committed ncu capture",
                 "other_kernels_ms": {"k_prep_x2": statistics.mean(prep_ms), "k_merge_chunks_x2": statistics.mean(merge_ms),
                                      "k_lr_check_fill": statistics.mean(occl_ms)},
                 "lr_check_fill_hbm": {"bound": "hbm", "achieved": 16.0 * w * rows_local / (statistics.mean(occl_ms) * 1e-3) / 1e9,

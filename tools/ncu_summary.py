@@ -3,7 +3,7 @@
 
     python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r1_prof_fused_final_summary.txt [--json profiles/fused_ncu.json]
 
-Writes the headline raw metrics, the per-pipeline-stage stall totals (the kernel's three warp roles are three hot
+Writes the headline raw metrics, the per-pipeline-stage stall totals (the kernel's warp roles are its hot
 loops, found by their execution counts) and the most-sampled instructions.  With --json it also refreshes the
 numbers bench.py quotes in `roofline.traffic`.
 """
@@ -75,7 +75,18 @@ def main():
         if len(sel) < 40:
             continue
         ops = " ".join(x[1] for x in sel)
-        role = "stage 0 (cost, first box filter)" if "FHFMA" in ops else ("stage 2 (q, merge)" if "FSETP" in ops else "stage 1 (a, b, second box filter)")
+        # warp roles by what only they execute: FHFMA = first-stage accumulation, FSETP without shuffles = the merge
+        # warps, half->float conversions with shuffles = q, LDTM + STTM with FFMA = coefficients and rings
+        if "FHFMA" in ops:
+            role = "stage 0 (cost, first box filter)"
+        elif "FSETP" in ops and "SHFL" not in ops:
+            role = "stage 3 (merge warps)"
+        elif "FSETP" in ops:
+            role = "stage 2 (q, merge)"
+        elif "HADD2.F32" in ops or "STS.128" in ops and "LDTM" in ops and "STTM" not in ops:
+            role = "stage 2 (second box filter, q)"
+        else:
+            role = "stage 1 (a, b, rings)"
         lines.append("  [0x%04x, 0x%04x] %-34s instr %4d  samples %6d  %s" % (
             lo, hi, role, len(sel), sum(int(x[ix["# Samples"]]) for x in sel),
             " ".join("%s:%d" % (c[6:], sum(int(x[ix[c]]) for x in sel)) for c in STALLS)))
