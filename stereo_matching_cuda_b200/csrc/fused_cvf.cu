@@ -20,28 +20,30 @@
 //    held in fp32 -- exact, order independent, identical on every tiling or GPU split.  The
 //    half-precision costs enter the fp32 sums through the f16 x f16 + f32 instructions of
 //    sm_100 (FHFMA / FHADD), without conversions.
-//  * Warp specialisation: a block is 4 TRIOS of warps (p, p+4, p+8: same SM sub-partition,
-//    same Tensor-Memory lane quarter), one trio per disparity, a 3-stage pipeline down the rows:
-//      stage 0  cost, vertical sums of P and I*P, their horizontal sums      -> (S_P, S_IP)
-//      stage 1  a, b, their vertical sums, horizontal sums                   -> (S_a, S_b)
-//      stage 2  q = mean_a*I + mean_b, merge of the block's 4 disparities into (best,label)
-//    Rows travel between stages through Tensor-Memory columns (tcgen05.st / tcgen05.ld) guarded
-//    by named barriers (0 -> 1) and mbarriers (1 -> 2, two slots); three warps per scheduler
-//    fill the issue slots one warp left empty (ncu: 27 % -> 44 % -> 58 % issue utilisation for
-//    1, 2, 3 warps per scheduler).
-//  * The guide operands every trio of a block needs -- (I,G), I, (mean_I, c2) of the strip's
-//    rows -- are fetched ONCE per block: one warp issues TMA bulk copies (cp.async.bulk) from
-//    strip-tiled planes into a 16-slot shared-memory ring, one slot (8 KB) per pipeline
-//    iteration, 5 iterations ahead; all 12 warps read their 16-byte chunks conflict-free and
-//    release the slot through an mbarrier.  Only the match operands (per disparity) are read
-//    through L1, as two aligned 128-bit loads from the copy of the (I,G) plane shifted by d&3.
-//  * The stage-2 warps leave their filtered rows in a 4-deep shared-memory ring; two iterations
-//    later each stage-2 thread folds the 4 disparities for 2 columns into the running
-//    (best,label) with the reference's `best >= q` rule (last slice wins ties; a 2-level
-//    tournament, which is the same function), one 16-byte load and store per row.
-//  * Blocks tile (column strip x row band x disparity chunk x view); per-chunk (best,label)
-//    planes are merged in chunk order by a small second kernel.
-// The kernel is latency/issue bound (58 % issue, L1TEX data pipe 65 %, DRAM ~20 % of its time).
+//  * Warp specialisation: a block is 4 TRIOS of warps (p, p+4, p+8: same SM sub-partition, same Tensor-Memory lane
+//    quarter), one trio per disparity, a 3-stage pipeline down the rows, plus 4 MERGE warps (p+12):
+//      stage 0  cost, vertical sums of P and I*P, horizontal sums of P          -> (S_P, V_IP)
+//      stage 1  horizontal sums of I*P, a, b, their vertical sums and rings     -> (V_a, V_b)
+//      stage 2  horizontal sums of a and b, q = mean_a*I + mean_b               -> q ring (shared memory)
+//      stage 3  merge of the block's 4 disparities into the running (best,label)
+//    Rows travel between stages through Tensor-Memory columns (tcgen05.st / tcgen05.ld) guarded by named barriers
+//    (0 -> 1) and mbarriers (1 -> 2, two slots).  The block is launched with 16 warps x 128 registers and every role
+//    (one warpgroup) trades registers with setmaxnreg (152 / 176 / 128 / 56); four warps per scheduler fill the issue
+//    slots one warp left empty (ncu: 27 % -> 44 % -> 58 % -> 74 % issue utilisation for 1, 2, 3, 4 warps per scheduler).
+//  * The guide operands every trio of a block needs -- (I,G), I, (mean_I, c2) of the strip's rows -- are fetched ONCE
+//    per block: TMA bulk copies (cp.async.bulk) from strip-tiled planes into a 16-slot shared-memory ring, one slot
+//    (8 KB) per pipeline iteration, 5 iterations ahead (the stage-1 warp of trio p fills the iterations K = p mod 4);
+//    the 12 stage warps read their 16-byte chunks conflict-free and release the slot through an mbarrier.  Only the
+//    match operands (per disparity) are read through L1, as two aligned, fully coalesced 128-bit loads from the
+//    de-interleaved copy of the (I,G) plane shifted by d&3.
+//  * The stage-2 warps leave their filtered rows in a 4-deep shared-memory ring; each merge thread folds the 4
+//    disparities for 2 columns into the running (best,label) with the reference's `best >= q` rule (last slice wins
+//    ties; a 2-level tournament, which is the same function), one 16-byte load and store per row.
+//  * Blocks tile (column strip x row band x disparity chunk x view); per-chunk (best,label) planes are merged in chunk
+//    order by a small second kernel.
+// The busiest unit is the L1TEX/shared-memory data pipe (72 %: shuffles + 128-bit shared loads), then the issue slots
+// (74 %); DRAM explains ~20 % of the kernel's time.  The FUSED_* macros are the switches of the A/B experiments
+// recorded in DESIGN.md 5, at their measured defaults.
 #include "fused_dev.cuh"
 
 namespace {
