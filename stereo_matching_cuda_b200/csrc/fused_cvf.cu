@@ -77,12 +77,11 @@ struct FusedArgs {
     int zero;               // always 0; opaque to the compiler (see touch_ops)
 };
 
-#ifndef FUSED_MERGE_WG
-#define FUSED_MERGE_WG 1      // 1: a fourth group of 4 warps merges the block's disparities (stage 3); 0: stage 2 does
-#endif
-// three pipeline stages (warps p, p+4, p+8) per disparity, and optionally the 4 merge warps
-constexpr int K3_THREADS = (3 + FUSED_MERGE_WG) * NWARP * 32;
-// register budgets of the warp roles with the merge warps (16 warps x 128 registers at launch, traded with setmaxnreg)
+// three pipeline stages (warps p, p+4, p+8) per disparity and the 4 merge warps (p+12)
+constexpr int K3_THREADS = 4 * NWARP * 32;
+// Register budgets of the four warp roles: the block is launched with 16 warps x 128 registers and every role (one
+// warpgroup) trades with setmaxnreg at the top of its branch; 152 + 176 + 128 + 56 = 512 = the whole register file.
+// (Overridable for A/B builds: tools/build_variant.sh ... -DFUSED_REGS1=168)
 #ifndef FUSED_REGS0
 #define FUSED_REGS0 152
 #endif
@@ -95,30 +94,11 @@ constexpr int K3_THREADS = (3 + FUSED_MERGE_WG) * NWARP * 32;
 #ifndef FUSED_REGS3
 #define FUSED_REGS3 56
 #endif
-constexpr int K3_REGS3 = FUSED_REGS3;
-static_assert(FUSED_REGS0 + FUSED_REGS1 + FUSED_REGS2 + K3_REGS3 <= 512, "register file: 64 K registers per SM");
-constexpr uint32_t TM_HAND2 = 416;          // TMEM columns [416,480): stage 1 -> stage 2 hand-off rows, 2 slots
-#ifndef FUSED_HS1_ROWS
-#define FUSED_HS1_ROWS 0
-#endif
-constexpr int HS1_ROWS = FUSED_HS1_ROWS;
-#ifndef FUSED_HSA1_ROWS
-#define FUSED_HSA1_ROWS 0
-#endif
-constexpr int HSA1_ROWS = FUSED_HSA1_ROWS;  // the same for the horizontal sums of a  // rows of an iteration whose horizontal sums of b are taken in stage 1 (the rest: stage 2)
-constexpr int NQ = 4;     // depth of the ring of filtered rows between the consumer and the merging warps
-constexpr int MLAG = 2;   // a producer merges the rows its consumer emitted MLAG iterations ago
-constexpr int NS = 16;        // slots of the operand ring (one per pipeline iteration)
-constexpr int LOAD_AHEAD = 5; // the loading warps fill the slot of iteration K + LOAD_AHEAD while they work on K
-#ifndef FUSED_HS0_IP_ROWS
-#define FUSED_HS0_IP_ROWS 0   // rows of an iteration whose horizontal sums of I*P are taken in stage 0 (the rest: stage 1)
-#endif
-#ifndef FUSED_AB0
-#define FUSED_AB0 0           // 1: the coefficients a, b are computed by stage 0 (which has slack), not stage 1
-#endif
-#ifndef FUSED_SPREAD
-#define FUSED_SPREAD 1        // 1: the stage-1 warp of trio p fills the iterations K = p mod 4; 0: trio 0 fills them all
-#endif
+static_assert(FUSED_REGS0 + FUSED_REGS1 + FUSED_REGS2 + FUSED_REGS3 <= 512, "register file: 64 K registers per SM");
+constexpr uint32_t TM_HAND2 = 416;  // TMEM columns [416,480): stage 1 -> stage 2 hand-off rows, 2 slots
+constexpr int NQ = 4;               // depth of the ring of filtered rows between stage 2 and the merge warps
+constexpr int NS = 16;              // slots of the operand ring (one per pipeline iteration)
+constexpr int LOAD_AHEAD = 5;       // the loading warps fill the slot of iteration K + LOAD_AHEAD while they work on K
 struct Slot {                 // guide operands of one iteration, filled by 4 bulk copies (8 KB)
     uint4 g[ROWS][2][32];     // (I,G) at rows yi
     uint4 io[ROWS][32];       // I at rows yi-19 (leave the first-stage window)
@@ -130,7 +110,7 @@ struct SmemLayout {
     Slot slot[NS];
     uint64_t sfull[NS], sempty[NS];       // mbarriers of the operand ring: bulk copies -> 12 warps and back
     float4 qbuf[NQ][NWARP][ROWS][2][QV];  // filtered rows of each consumer warp
-    uint64_t qfull[NQ], qempty[NQ];       // mbarriers of the q ring (4 stage-2 warps write, the same 4 warps merge)
+    uint64_t qfull[NQ], qempty[NQ];       // mbarriers of the q ring (the 4 stage-2 warps write, the 4 merge warps read)
     uint64_t full2[NWARP][2], empty2[NWARP][2];  // mbarriers of the 2-slot stage 1 -> stage 2 hand-off of each pair
     float ry_lut[2][WIN + 1];             // [0][n] = 1/(S*n), [1][n] = 1/n for a clipped window of n rows; [.][0] = 0
     uint32_t tmem_base;
@@ -209,7 +189,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
 #pragma unroll
         for (int b = 0; b < NS; b++) {
             mbar_init(mb_sfull + 8 * b, 1);
-            mbar_init(mb_sempty + 8 * b, (FUSED_AB0 ? 2 : 3) * NWARP);  // the warps that read the slot
+            mbar_init(mb_sempty + 8 * b, 3 * NWARP);  // the 12 stage warps read every slot
         }
     }
     if (threadIdx.x == 32) {
@@ -251,7 +231,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
 
     if (stage == 0) {
         // ====== STAGE 0: lattice cost, vertical window sums of P and I*P, their horizontal sums ======
-        if (FUSED_MERGE_WG) reg_inc<FUSED_REGS0>();
+        reg_inc<FUSED_REGS0>();
         const unsigned* __restrict__ IGm = A.IG[1 - view];
         __half2 wm[KPX];  // lattice weights (nI, nG), 0 outside the image (masks the cost)
 #pragma unroll
@@ -260,15 +240,6 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
             wm[j] = (x >= 0 && x < A.w) ? u2h2(A.wpack) : __float2half2_rn(0.0f);
         }
         const __half2 th = u2h2(A.thpack);
-#if FUSED_AB0
-        float rx[KPX];  // 1 / clipped window width, 0 outside the image
-#pragma unroll
-        for (int j = 0; j < KPX; j++) {
-            int x = xl + j;
-            int ax = min(A.w - 1, x + RAD) - max(0, x - RAD) + 1;
-            rx[j] = (x >= 0 && x < A.w) ? __frcp_rn((float)ax) : 0.0f;
-        }
-#endif
         for (int g = 0; g < ngroups; g++) {
             const int dk = g * NWARP + pair;
             const bool active = dk < dcnt;
@@ -308,9 +279,6 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                     }
                     // guide operands of this iteration from the shared-memory ring
                     uint4 gq[ROWS][2], ioq[ROWS];
-#if FUSED_AB0
-                    uint4 sq[ROWS][4];
-#endif
                     {
                         const int K = g * niter + it;
                         const uint32_t sa = slot_wait(K);
@@ -321,13 +289,6 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                             gq[r][1] = lds128(sa + OFF_G + (r * 2 + 1) * 512);
                             ioq[r] = lds128(sa + OFF_IO + r * 512);
                             t |= gq[r][0].x | gq[r][1].x | ioq[r].x;
-#if FUSED_AB0
-#pragma unroll
-                            for (int c = 0; c < 4; c++) {
-                                sq[r][c] = lds128(sa + OFF_ST + (r * 4 + c) * 512);
-                                t |= sq[r][c].x;
-                            }
-#endif
                         }
                         slot_release(K, t);
                     }
@@ -383,28 +344,9 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                         }
                         tm_st4(tP + 4 * slots[r], pneg[r]);
                         hsum19(VP, SP[r]);
-                        if (r < FUSED_HS0_IP_ROWS) {
-                            hsum19(VIP, SIP[r]);
-                        } else {
+                        // (the horizontal sums of I*P are taken by stage 1: this stage was the long pole with them)
 #pragma unroll
-                            for (int j = 0; j < KPX; j++) SIP[r][j] = VIP[j];
-                        }
-#if FUSED_AB0
-                        {   // a, b at row ya = yi - 9 (guidedFilter.cu:345-354), handed over in place of the sums
-                            const float ry1 = inv_rows(sm.ry_lut[0], y_first + it * ROWS + r - RAD, A.y_global0, A.frame_h);
-                            const unsigned stt[16] = {sq[r][0].x, sq[r][0].y, sq[r][0].z, sq[r][0].w, sq[r][1].x, sq[r][1].y, sq[r][1].z, sq[r][1].w,
-                                                      sq[r][2].x, sq[r][2].y, sq[r][2].z, sq[r][2].w, sq[r][3].x, sq[r][3].y, sq[r][3].z, sq[r][3].w};
-#pragma unroll
-                            for (int j = 0; j < KPX; j++) {
-                                const float mI = __uint_as_float(stt[2 * j]), c2 = __uint_as_float(stt[2 * j + 1]);
-                                const float cov = fmaf(-mI, SP[r][j], SIP[r][j]);
-                                const float a = cov * c2;
-                                const float mp = SP[r][j] * (rx[j] * ry1);
-                                SP[r][j] = a;
-                                SIP[r][j] = fmaf(-mI, a, mp);
-                            }
-                        }
-#endif
+                        for (int j = 0; j < KPX; j++) SIP[r][j] = VIP[j];
                     }
                     // stage 1 has copied the previous rows out of the hand-off columns
                     if (it > 0) {
@@ -432,8 +374,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
         }
     } else if (stage == 1) {
         // ====== STAGE 1: a, b; their vertical and horizontal window sums ======
-        if (FUSED_MERGE_WG) reg_inc<FUSED_REGS1>();
-#if !FUSED_AB0
+        reg_inc<FUSED_REGS1>();
         float rx[KPX];  // 1 / clipped window width, 0 outside the image
 #pragma unroll
         for (int j = 0; j < KPX; j++) {
@@ -441,15 +382,13 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
             int ax = min(A.w - 1, x + RAD) - max(0, x - RAD) + 1;
             rx[j] = (x >= 0 && x < A.w) ? __frcp_rn((float)ax) : 0.0f;
         }
-#endif
         // Operand ring, producer side: the stage-1 warps fill the slot of iteration K + LOAD_AHEAD, for the whole block,
-        // while they work on K: 4 bulk copies of the strip-tiled guide planes.  With FUSED_SPREAD the warp of trio p
-        // fills the iterations K = p mod 4, so the ~100 instructions of a fill are shared by the four trios instead of
-        // slowing trio 0 (the trios run in step through the merge ring: the slowest one sets the pace).
+        // while they work on K: 4 bulk copies of the strip-tiled guide planes.  The warp of trio p fills the iterations
+        // K = p mod 4, so the ~100 instructions of a fill are shared by the four trios instead of slowing trio 0 (the
+        // trios run in step through the merge ring: the slowest one sets the pace).
         const int Ktotal = ngroups * niter;
-        constexpr int fill_step = FUSED_SPREAD ? NWARP : 1;
-        int fillK = FUSED_SPREAD ? pair : 0, fill_it = fillK;  // this warp's next iteration to fill, and its row iteration inside its group
-        const bool filler = FUSED_SPREAD || pair == 0;
+        constexpr int fill_step = NWARP;
+        int fillK = pair, fill_it = fillK;  // this warp's next iteration to fill, and its row iteration inside its group
         auto fill_due = [&](int K) {  // called at the start of iteration K: fill what is due up to K + LOAD_AHEAD
             while (fillK <= K + LOAD_AHEAD && fillK < Ktotal) {
                 const int sl = fillK & (NS - 1);
@@ -470,7 +409,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                 if (fill_it >= niter) fill_it -= niter;
             }
         };
-        if (filler) fill_due(-1);  // the slots of iterations 0 .. LOAD_AHEAD-1
+        fill_due(-1);  // the slots of iterations 0 .. LOAD_AHEAD-1
         for (int g = 0; g < ngroups; g++) {
             const int dk = g * NWARP + pair;
             const bool active = dk < dcnt;
@@ -484,8 +423,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
             int slot = 0;
             auto iter = [&](auto emit_tag, int it) {
                 constexpr bool EMIT = decltype(emit_tag)::value;
-                if (filler) fill_due(g * niter + it);
-#if !FUSED_AB0
+                fill_due(g * niter + it);
                 // (mean_I, c2) of rows ya from the shared-memory ring
                 uint4 sq[ROWS][4];
                 {
@@ -505,7 +443,6 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                 float ry1[ROWS];
 #pragma unroll
                 for (int r = 0; r < ROWS; r++) ry1[r] = inv_rows(sm.ry_lut[0], yi0 + r - RAD, A.y_global0, A.frame_h);
-#endif
                 // the (a,b) rows that leave the second-stage window, from this pair's TMEM ring
                 float ao[ROWS][KPX], bo[ROWS][KPX];
                 int slots[ROWS];
@@ -528,7 +465,7 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                 float SA[ROWS][KPX], SB[ROWS][KPX];
 #pragma unroll
                 for (int r = 0; r < ROWS; r++) {
-                    if (r >= FUSED_HS0_IP_ROWS) {  // stage 0 left this row's I*P sums to this stage
+                    {   // stage 0 hands the vertical sums of I*P over: their horizontal sums are taken here
                         float hs[KPX];
                         hsum19(SIP[r], hs);
 #pragma unroll
@@ -536,13 +473,6 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                     }
                     // ---- a, b at row ya = yi - 9
                     float a[KPX], b[KPX];
-#if FUSED_AB0
-#pragma unroll
-                    for (int j = 0; j < KPX; j++) {  // computed by stage 0
-                        a[j] = SP[r][j];
-                        b[j] = SIP[r][j];
-                    }
-#else
                     const unsigned stt[16] = {sq[r][0].x, sq[r][0].y, sq[r][0].z, sq[r][0].w, sq[r][1].x, sq[r][1].y, sq[r][1].z, sq[r][1].w,
                                               sq[r][2].x, sq[r][2].y, sq[r][2].z, sq[r][2].w, sq[r][3].x, sq[r][3].y, sq[r][3].z, sq[r][3].w};
 #pragma unroll
@@ -553,7 +483,6 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                         float mp = SP[r][j] * (rx[j] * ry1[r]);
                         b[j] = fmaf(-mI, a[j], mp);
                     }
-#endif
                     // ---- second stage: (a,b) of row ya enter, row ya-19 leaves
                     tm_st16(tAB + 16 * slots[r], a, b);
 #pragma unroll
@@ -561,20 +490,11 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                         Va[j] += a[j] - ao[r][j];
                         Vb[j] += b[j] - bo[r][j];
                     }
-                    if (EMIT) {
-                        if (r < HSA1_ROWS) {
-                            hsum19(Va, SA[r]);
-                        } else {
+                    if (EMIT) {  // (the horizontal sums of a and b are taken by stage 2)
 #pragma unroll
-                            for (int j = 0; j < KPX; j++) SA[r][j] = Va[j];
-                        }
-                        // balance of the pipeline: the horizontal sums of b are taken here for the rows below
-                        // HS1_ROWS and in stage 2 for the others
-                        if (r < HS1_ROWS) {
-                            hsum19(Vb, SB[r]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < KPX; j++) SB[r][j] = Vb[j];
+                        for (int j = 0; j < KPX; j++) {
+                            SA[r][j] = Va[j];
+                            SB[r][j] = Vb[j];
                         }
                     }
                 }
@@ -602,18 +522,16 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                 for (; it < niter; it++) iter(std::true_type{}, it);
             } else {
                 for (int it = 0; it < niter; it++) {  // a trio without a disparity still fills and releases its share
-                    if (filler) fill_due(g * niter + it);
-#if !FUSED_AB0
+                    fill_due(g * niter + it);
                     slot_wait(g * niter + it);
                     slot_release(g * niter + it, 0u);
-#endif
                 }
             }
             __syncthreads();  // group end
         }
     } else if (stage == 2) {
-        // ====== STAGE 2: q = mean_a * I + mean_b and, without FUSED_MERGE_WG, the merge of the 4 disparities ======
-        if (FUSED_MERGE_WG) reg_inc<FUSED_REGS2>();
+        // ====== STAGE 2: horizontal sums of a and b, q = mean_a * I + mean_b ======
+        reg_inc<FUSED_REGS2>();
         float rx[KPX];
 #pragma unroll
         for (int j = 0; j < KPX; j++) {
@@ -621,72 +539,9 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
             int ax = min(A.w - 1, x + RAD) - max(0, x - RAD) + 1;
             rx[j] = (x >= 0 && x < A.w) ? __frcp_rn((float)ax) : 0.0f;
         }
-        // merge role of this thread: strip-local columns 2t, 2t+1 of all 4 disparities of a group
-        const int mc = 2 * (threadIdx.x - 2 * NWARP * 32);
-        const int mx = xs + mc;
-        // (HALO, VALID_W and mc are even: the two columns are inside the strip's valid range together; for an odd
-        //  image width the second one may be the first padding column of the plane, which is never read)
-        const bool mvalid = (mc >= HALO) && (mc < HALO + VALID_W) && (mx < A.w);
-        const int qoff = (((mc & 7) >> 2) * QV + (mc >> 3)) * 4 + (mc & 3);
-        const size_t planeS = (size_t)A.rows_out * A.pitchS;
-        float2* __restrict__ BL = A.BL + (size_t)(chunk * 2 + view) * planeS;
-        const size_t bl_row = (size_t)A.pitchS / 2;  // 16-byte units per row of the plane (pitchS is a multiple of 4)
         for (int g = 0; g < ngroups; g++) {
             const int dk = g * NWARP + pair;
             const bool active = dk < dcnt;
-            const int dbase = dlo + g * NWARP;
-            const float lab[NWARP] = {(float)dbase, (float)(dbase + 1), (float)(dbase + 2), (float)(dbase + 3)};
-            typedef float4 Best;  // (best, label) of columns mx and mx+1
-            // running (best,label) of the rows of emission e, from the previous groups of this chunk
-            // merge cursor: the emissions are merged in order, so the rows of the next one to merge are at blp
-            float4* blp = reinterpret_cast<float4*>(BL + (size_t)(yb0 - A.y_out0) * A.pitchS + mx);
-            int mrows = yb1 - yb0;  // rows of the band not merged yet
-            const bool ld_ok = (g > 0) && mvalid;
-            auto prefetch_best = [&](Best (&pb)[ROWS]) {
-#pragma unroll
-                for (int r = 0; r < ROWS; r++) {
-                    pb[r] = make_float4(BEST_INIT_BITS_F, 0.0f, BEST_INIT_BITS_F, 0.0f);
-                    if (ld_ok && r < mrows) pb[r] = ld_early_f4(blp + r * bl_row);
-                }
-            };
-            // fold the 4 disparities of this group into (best,label): ascending d, `>=` (last slice wins ties)
-            auto merge = [&](int e, const Best (&pb)[ROWS]) {
-                const int E = g * n_emit + e;
-                const int qb = E & (NQ - 1);
-                mbar_wait(mb_qfull + 8 * qb, (unsigned)(E / NQ) & 1u);
-#pragma unroll
-                for (int r = 0; r < ROWS; r++) {
-                    const float* qp = reinterpret_cast<const float*>(&sm.qbuf[qb][0][r][0][0]);
-                    float b0 = pb[r].x, l0 = pb[r].y, b1 = pb[r].z, l1 = pb[r].w;
-                    float2 qv[NWARP];
-#pragma unroll
-                    for (int wv = 0; wv < NWARP; wv++) qv[wv] = *reinterpret_cast<const float2*>(qp + wv * (ROWS * 2 * QV * 4) + qoff);
-                    // "minimum, the later disparity on a tie" is associative: a 2-level tournament
-                    // gives what the reference's sequential `best >= q` scan gives, with a shorter chain
-                    static_assert(NWARP == 4, "tournament written for 4 disparities per group");
-                    {
-                        const bool t01 = qv[0].x >= qv[1].x, t23 = qv[2].x >= qv[3].x;
-                        const float m01 = t01 ? qv[1].x : qv[0].x, m23 = t23 ? qv[3].x : qv[2].x;
-                        const float a01 = t01 ? lab[1] : lab[0], a23 = t23 ? lab[3] : lab[2];
-                        const bool t = m01 >= m23;
-                        const float m = t ? m23 : m01, a = t ? a23 : a01;
-                        if (b0 >= m) { b0 = m; l0 = a; }
-                    }
-                    {
-                        const bool t01 = qv[0].y >= qv[1].y, t23 = qv[2].y >= qv[3].y;
-                        const float m01 = t01 ? qv[1].y : qv[0].y, m23 = t23 ? qv[3].y : qv[2].y;
-                        const float a01 = t01 ? lab[1] : lab[0], a23 = t23 ? lab[3] : lab[2];
-                        const bool t = m01 >= m23;
-                        const float m = t ? m23 : m01, a = t ? a23 : a01;
-                        if (b1 >= m) { b1 = m; l1 = a; }
-                    }
-                    if (mvalid && r < mrows) blp[r * bl_row] = make_float4(b0, l0, b1, l1);
-                }
-                __syncwarp();
-                mbar_arrive_lane0(mb_qempty + 8 * qb, lane);
-                blp += ROWS * bl_row;
-                mrows -= ROWS;
-            };
             if (!active) {  // the previous group's merges have drained (group-end barrier)
                 const float inf = __int_as_float(0x7f800000);
 #pragma unroll
@@ -718,9 +573,6 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                         }
                         slot_release(K, t);
                     }
-                    const int em = FUSED_MERGE_WG ? -1 : e - MLAG;
-                    Best pb[ROWS];
-                    if (em >= 0) prefetch_best(pb);
                     const int E = g * n_emit + e;
                     mbar_wait(mb_full2 + 8 * (E & 1), (unsigned)(E / 2) & 1u);  // stage 1 has published this emission
                     tm_fence_after();
@@ -735,13 +587,13 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                     if (E >= NQ) mbar_wait(mb_qempty + 8 * qb, (unsigned)(E / NQ - 1) & 1u);  // merged NQ emissions ago
 #pragma unroll
                     for (int r = 0; r < ROWS; r++) {
-                        if (r >= HSA1_ROWS) {
+                        {
                             float ha[KPX];
                             hsum19(SA[r], ha);
 #pragma unroll
                             for (int j = 0; j < KPX; j++) SA[r][j] = ha[j];
                         }
-                        if (r >= HS1_ROWS) {
+                        {
                             float hb[KPX];
                             hsum19(SB[r], hb);
 #pragma unroll
@@ -759,10 +611,9 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                     }
                     __syncwarp();
                     mbar_arrive_lane0(mb_qfull + 8 * qb, lane);
-                    if (em >= 0) merge(em, pb);
                 }
             } else {
-                // no disparity for this pair in the (last, partial) group: its slots hold +inf
+                // no disparity for this pair in the (last, partial) group: its slots of the q ring hold +inf
                 for (int e = 0; e < n_emit; e++) {
                     slot_wait(g * niter + WARM_IT + e);
                     slot_release(g * niter + WARM_IT + e, 0u);
@@ -771,29 +622,15 @@ __global__ void __launch_bounds__(K3_THREADS, 1) k_fused_cvf(const FusedArgs A) 
                     if (E >= NQ) mbar_wait(mb_qempty + 8 * qb, (unsigned)(E / NQ - 1) & 1u);
                     if (lane == 0) mbar_arrive(mb_qfull + 8 * qb);
                     __syncwarp();
-                    if (!FUSED_MERGE_WG) {
-                        Best pb[ROWS];
-                        prefetch_best(pb);
-                        merge(e, pb);
-                    }
-                }
-            }
-            // the emissions not merged inside the loop
-            if (active && !FUSED_MERGE_WG) {
-#pragma unroll 1
-                for (int e = max(0, n_emit - MLAG); e < n_emit; e++) {
-                    Best pb[ROWS];
-                    prefetch_best(pb);
-                    merge(e, pb);
                 }
             }
             __syncthreads();  // group end
         }
     } else {
-        // ====== STAGE 3 (FUSED_MERGE_WG): merge of the block's 4 disparities into the running (best,label) ======
+        // ====== STAGE 3: merge of the block's 4 disparities into the running (best,label) ======
         // Thread t of these 4 warps folds strip-local columns 2t, 2t+1 of the rows the stage-2 warps publish in the q
         // ring; the (best,label) of the previous groups is fetched two emissions ahead.
-        reg_dec<K3_REGS3>();
+        reg_dec<FUSED_REGS3>();
         const int mc = 2 * (threadIdx.x - 3 * NWARP * 32);
         const int mx = xs + mc;
         const bool mvalid = (mc >= HALO) && (mc < HALO + VALID_W) && (mx < A.w);
