@@ -8,8 +8,9 @@
 //      stage 0  lattice cost, vertical sums of p, R p, G p, B p (exact integers, FHFMA/FHADD accumulation),
 //               their four horizontal sums                                         -> (S_p, S_Rp, S_Gp, S_Bp)
 //      stage 1  3x3 solve a = M cov, b = mp - a.mu, vertical sums of a_r, a_g, a_b, b    -> (V_ar, V_ag, V_ab, V_b)
-//      stage 2  their horizontal sums, q = SS_a . I + SS_b, merge of the block's 4 disparities
-//               (RGB3_HS1 moves the first one or two horizontal sums into stage 1)
+//      stage 2  their horizontal sums, q = SS_a . I + SS_b                               -> q ring (shared memory)
+//      stage 3  (4 merge warps) merge of the block's 4 disparities into the running (best,label)
+//    16 warps x 128 registers at launch; every role trades registers with setmaxnreg (152 / 168 / 152 / 40);
 //    hand-offs through Tensor-Memory columns: named barriers (0 -> 1), mbarriers with two slots (1 -> 2);
 //  * the guide operands of stages 0 and 1 -- (I,G) of the row and the colour rows entering and leaving the first
 //    window; the 72 statistics words per lane (mu, scaled inverse covariance) -- are fetched ONCE per block by
@@ -43,17 +44,13 @@ struct Rgb3Args {
     int zero;               // always 0, opaque to the compiler
 };
 
-#ifndef RGB3_MERGE_WG
-#define RGB3_MERGE_WG 1    // 1: a fourth group of 4 warps does the merge of the block's disparities (stage 3); 0: stage 2 does
-#endif
-constexpr int R3_THREADS = (3 + RGB3_MERGE_WG) * NWARP * 32;
-// Register budget per warp role when the merge has its own warps (16 warps x 128 registers at launch; the roles
-// trade registers with setmaxnreg, one warpgroup = the 4 warps of a role): 152 + 168 + 152 + 40 = 512 = 4 x 128
+constexpr int R3_THREADS = 4 * NWARP * 32;  // three pipeline stages per disparity (warps p, p+4, p+8) + 4 merge warps
+// Register budget per warp role (16 warps x 128 registers at launch; the roles trade registers with setmaxnreg, one
+// warpgroup = the 4 warps of a role): 152 + 168 + 152 + 40 = 512 = 4 x 128
 constexpr int R3_REGS0 = 152, R3_REGS1 = 168, R3_REGS2 = 152, R3_REGS3 = 40;
 static_assert(R3_REGS0 + R3_REGS1 + R3_REGS2 + R3_REGS3 <= 512, "register file: 64 K registers per SM");
 constexpr uint32_t T3_RING_A = 0, T3_RING_P = 304, T3_HAND = 384, T3_HAND2 = 416;  // TMEM columns of a lane
-constexpr int NQ3 = 4;     // depth of the ring of filtered rows between stage 2 and the merge
-constexpr int MLAG3 = 2;   // the merge runs MLAG3 iterations behind
+constexpr int NQ3 = 4;     // depth of the ring of filtered rows between stage 2 and the merge warps
 // Operand ring of stages 0 and 1: slot K & 3 holds the guide operands of iteration K.  The stage-1 warp of trio p
 // fills slot p (iterations K = p mod 4), RGB3_AHEAD iterations ahead of its own position, so the cost of issuing
 // the bulk copies (~100 instructions) is shared by the four trios instead of slowing one of them -- the trios run in
@@ -67,15 +64,6 @@ constexpr int NS3 = 4;
 #endif
 constexpr int AHEAD3 = RGB3_AHEAD;
 constexpr int WARM3 = 4 * RAD;   // warm-up iterations (one row each) before the first output row
-#ifndef RGB3_HS1
-#define RGB3_HS1 0         // horizontal sums (of a_r, a_g) taken in stage 1; the rest in stage 2
-#endif
-#ifndef RGB3_SOLVE0
-#define RGB3_SOLVE0 0      // 1: the 3x3 solve (a, b) runs in stage 0, which then reads the statistics; 0: in stage 1
-#endif
-#ifndef RGB3_SPREAD
-#define RGB3_SPREAD 1      // 1: trio p fills slot p; 0: trio 0 fills every slot
-#endif
 
 struct Slot3 {          // guide operands of one iteration (one row) of stages 0 and 1, 4 bulk copies (13 KB)
     uint4 g[2][32];     // (I,G) at row yi
@@ -136,12 +124,12 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
     const uint32_t slot0 = smem_addr(&sm.slot[0]) + 16 * lane;
     static_assert((NS3 & (NS3 - 1)) == 0 && (NQ3 & (NQ3 - 1)) == 0, "ring indices are taken from the bits of the counters");
     static_assert(AHEAD3 < NS3, "the ring cannot be filled further ahead than it is deep");
-    static_assert(!RGB3_SPREAD || NS3 == NWARP, "trio p fills slot p");
+    static_assert(NS3 == NWARP, "trio p fills slot p");
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int b = 0; b < NS3; b++) {
             mbar_init(mb_sfull + 8 * b, 1);
-            mbar_init(mb_sempty + 8 * b, (RGB3_SOLVE0 ? 1 : 2) * NWARP);  // released by the warps that read the slot
+            mbar_init(mb_sempty + 8 * b, 2 * NWARP);  // released by the stage-0 and stage-1 warps
         }
     }
     if (threadIdx.x == 32) {
@@ -197,11 +185,11 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
         }
         __syncwarp();
     };
-    // this warp's next fill: iteration fillK (row iteration fill_it of its group); after a fill it moves on by
-    // fill_step iterations (4 when the trios share the work: trio p fills the iterations K = p mod 4)
-    constexpr int fill_step = RGB3_SPREAD ? NWARP : 1;
-    int fillK = RGB3_SPREAD ? pair : 0, fill_it = fillK;
-    const bool filler = (stage == 1) && (RGB3_SPREAD || pair == 0);
+    // this warp's next fill: iteration fillK (row iteration fill_it of its group); after a fill it moves on by 4
+    // iterations (trio p fills the iterations K = p mod 4)
+    constexpr int fill_step = NWARP;
+    int fillK = pair, fill_it = fillK;
+    const bool filler = (stage == 1);  // (the other roles never call fill_due)
     // called by a filling warp at the start of its iteration K: fill what is due up to K + AHEAD3
     auto fill_due = [&](int K) {
         while (fillK <= K + AHEAD3 && fillK < Ktotal) {
@@ -254,7 +242,7 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
 
     if (stage == 0) {
         // ====== STAGE 0: lattice cost; vertical and horizontal window sums of p, R p, G p, B p ======
-        if (RGB3_MERGE_WG) reg_inc<R3_REGS0>();
+        reg_inc<R3_REGS0>();
         const unsigned* __restrict__ IGm = A.IG[1 - view];
         __half2 wm[KPX];
 #pragma unroll
@@ -263,15 +251,6 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
             wm[j] = (x >= 0 && x < A.w) ? u2h2(A.wpack) : __float2half2_rn(0.0f);
         }
         const __half2 th = u2h2(A.thpack);
-#if RGB3_SOLVE0
-        float rx[KPX];
-#pragma unroll
-        for (int j = 0; j < KPX; j++) {
-            int x = xl + j;
-            int ax = min(A.w - 1, x + RAD) - max(0, x - RAD) + 1;
-            rx[j] = (x >= 0 && x < A.w) ? __frcp_rn((float)ax) : 0.0f;
-        }
-#endif
         for (int g = 0; g < ngroups; g++) {
             const int dk = g * NWARP + pair;
             const bool active = dk < dcnt;
@@ -317,7 +296,7 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
                             co[c] = lds128(sa + OFF_CO + c * 512);
                             t |= cn[c].x | co[c].x;
                         }
-                        if (!RGB3_SOLVE0) slot_release(K, t);
+                        slot_release(K, t);
                     }
                     uint32_t pold[4];  // the NEGATED lattice costs of row yi-19
                     tm_ld4(tP + 4 * slot, pold);
@@ -363,9 +342,6 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
                     hsum19(VR, SR);
                     hsum19(VG, SG);
                     hsum19(VB, SB);
-#if RGB3_SOLVE0
-                    solve(K, SP, SR, SG, SB, rx, inv_rows(sm.ry_lut[0], y_first + it - RAD, A.y_global0, A.frame_h), sa, t);
-#endif
                     if (it > 0) {  // stage 1 has copied the previous row out of the hand-off columns
                         named_bar_sync(BAR_EMPTY, 64);
                         tm_fence_after();
@@ -388,8 +364,7 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
         }
     } else if (stage == 1) {
         // ====== STAGE 1: a = M cov, b = mp - a.mu; their vertical sums; horizontal sums of a_r, a_g ======
-        if (RGB3_MERGE_WG) reg_inc<R3_REGS1>();
-#if !RGB3_SOLVE0
+        reg_inc<R3_REGS1>();
         float rx[KPX];
 #pragma unroll
         for (int j = 0; j < KPX; j++) {
@@ -397,7 +372,6 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
             int ax = min(A.w - 1, x + RAD) - max(0, x - RAD) + 1;
             rx[j] = (x >= 0 && x < A.w) ? __frcp_rn((float)ax) : 0.0f;
         }
-#endif
         for (int g = 0; g < ngroups; g++) {
             const int dk = g * NWARP + pair;
             const bool active = dk < dcnt;
@@ -416,9 +390,7 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
             auto iter = [&](auto emit_tag, int it) {
                 constexpr bool EMIT = decltype(emit_tag)::value;
                 if (filler) fill_due(g * niter + it);
-#if !RGB3_SOLVE0
                 const float ry1 = inv_rows(sm.ry_lut[0], y_first + it - RAD, A.y_global0, A.frame_h);
-#endif
                 named_bar_sync(BAR_FULL, 64);  // stage 0 has published row yi
                 tm_fence_after();
                 float SP[KPX], SR[KPX], SG[KPX], SB[KPX];
@@ -429,13 +401,11 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
                     tm_fence_before();
                     named_bar_arrive(BAR_EMPTY, 64);
                 }
-                // ---- (a, b) at row ya = yi - 9: solved here or, with RGB3_SOLVE0, already by stage 0
-#if !RGB3_SOLVE0
+                // ---- (a, b) at row ya = yi - 9
                 {
                     const int K = g * niter + it;
                     solve(K, SP, SR, SG, SB, rx, ry1, slot_wait(K), 0u);
                 }
-#endif
                 float (&ar)[KPX] = SP, (&ag)[KPX] = SR, (&ab)[KPX] = SG, (&bb)[KPX] = SB;
                 // ---- second stage: row ya enters, row ya-19 leaves (read from the rings only now: the solve above
                 //      needs the registers)
@@ -459,28 +429,13 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
                     Vab[j] += ab[j] - abo[j];
                     Vb[j] += bb[j] - bbo[j];
                 }
-                if (EMIT) {
-                    // balance of the pipeline: the first RGB3_HS1 of the four horizontal sums are taken here, the
-                    // others in stage 2
-                    float SAr[KPX], SAg[KPX];
-                    if (RGB3_HS1 >= 1) {
-                        hsum19(Var, SAr);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < KPX; j++) SAr[j] = Var[j];
-                    }
-                    if (RGB3_HS1 >= 2) {
-                        hsum19(Vag, SAg);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < KPX; j++) SAg[j] = Vag[j];
-                    }
+                if (EMIT) {  // (the four horizontal sums are taken by stage 2: the hand-off carries the vertical sums)
                     const int E = g * n_emit + (it - WARM3);
                     if (E > 1) {  // stage 2 has copied emission E-2 out of this hand-off slot
                         mbar_wait(mb_empty2 + 8 * (E & 1), (unsigned)(E / 2 - 1) & 1u);
                         tm_fence_after();
                     }
-                    tm_st16(tH2 + 32 * (E & 1), SAr, SAg);
+                    tm_st16(tH2 + 32 * (E & 1), Var, Vag);
                     tm_st16(tH2 + 32 * (E & 1) + 16, Vab, Vb);
                     tm_wait_st();
                     tm_fence_before();
@@ -499,18 +454,15 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
             } else {
                 for (int it = 0; it < niter; it++) {  // a trio without a disparity still fills and releases its share
                     if (filler) fill_due(g * niter + it);
-#if !RGB3_SOLVE0
                     slot_wait(g * niter + it);
                     slot_release(g * niter + it, 0u);
-#endif
                 }
             }
             __syncthreads();  // group end
         }
     } else if (stage == 2) {
-        // ====== STAGE 2: horizontal sums of a_b and b, q = SS_a . I + SS_b
-        // ====== and, without RGB3_MERGE_WG, the merge of the block's 4 disparities
-        if (RGB3_MERGE_WG) reg_inc<R3_REGS2>();
+        // ====== STAGE 2: the four horizontal sums of a_r, a_g, a_b, b; q = SS_a . I + SS_b ======
+        reg_inc<R3_REGS2>();
         float rx[KPX];
 #pragma unroll
         for (int j = 0; j < KPX; j++) {
@@ -518,39 +470,9 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
             int ax = min(A.w - 1, x + RAD) - max(0, x - RAD) + 1;
             rx[j] = (x >= 0 && x < A.w) ? __frcp_rn((float)ax) : 0.0f;
         }
-        // merge role (without RGB3_MERGE_WG): strip-local columns mc, mc+1
-        const int mc = 2 * (threadIdx.x - 2 * NWARP * 32);
-        const int mx = xs + mc;
-        const bool mvalid = (mc >= HALO) && (mc < HALO + VALID_W) && (mx < A.w);
-        const int qoff = (((mc & 7) >> 2) * QV + (mc >> 3)) * 4 + (mc & 3);
-        const size_t planeS = (size_t)A.rows_out * A.pitchS;
-        float2* __restrict__ BL = A.BL + (size_t)(chunk * 2 + view) * planeS;
-        const size_t bl_row = (size_t)A.pitchS / 2;  // 16-byte units per row of the plane
         for (int g = 0; g < ngroups; g++) {
             const int dk = g * NWARP + pair;
             const bool active = dk < dcnt;
-            const int dbase = dlo + g * NWARP;
-            const float lab[NWARP] = {(float)dbase, (float)(dbase + 1), (float)(dbase + 2), (float)(dbase + 3)};
-            float4* blp = reinterpret_cast<float4*>(BL + (size_t)(yb0 - A.y_out0) * A.pitchS + mx);  // merge cursor
-            int mrows = yb1 - yb0;
-            const bool ld_ok = (g > 0) && mvalid;
-            auto prefetch_best = [&]() -> float4 {
-                float4 pb = make_float4(BEST_INIT_BITS_F, 0.0f, BEST_INIT_BITS_F, 0.0f);
-                if (ld_ok && mrows > 0) pb = ld_early_f4(blp);
-                return pb;
-            };
-            // fold the 4 disparities of this group into (best,label): ascending d, `>=` (last slice wins ties)
-            auto merge = [&](int e, const float4 pb) {
-                const int E = g * n_emit + e;
-                const int qb = E & (NQ3 - 1);
-                mbar_wait(mb_qfull + 8 * qb, (unsigned)(E / NQ3) & 1u);
-                const float4 nb = merge4(reinterpret_cast<const float*>(&sm.qbuf[qb][0][0][0]) + qoff, 2 * QV * 4, lab, pb);
-                if (mvalid && mrows > 0) *blp = nb;
-                __syncwarp();
-                mbar_arrive_lane0(mb_qempty + 8 * qb, lane);
-                blp += bl_row;
-                mrows -= 1;
-            };
             if (!active) {  // the previous group's merges have drained (group-end barrier)
                 const float inf = __int_as_float(0x7f800000);
 #pragma unroll
@@ -575,9 +497,6 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
 #pragma unroll
                         for (int c = 0; c < 3; c++) cqn[c] = __ldg(pc + c * 32 + dep);
                     }
-                    const int em = RGB3_MERGE_WG ? -1 : e - MLAG3;
-                    float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (em >= 0) pb = prefetch_best();
                     const int E = g * n_emit + e;
                     mbar_wait(mb_full2 + 8 * (E & 1), (unsigned)(E / 2) & 1u);  // stage 1 has published this emission
                     tm_fence_after();
@@ -591,13 +510,13 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
                     const int qb = E & (NQ3 - 1);
                     if (E >= NQ3) mbar_wait(mb_qempty + 8 * qb, (unsigned)(E / NQ3 - 1) & 1u);  // merged NQ3 emissions ago
                     float SAb[KPX], SBb[KPX];
-                    if (RGB3_HS1 < 1) {
+                    {
                         float t[KPX];
                         hsum19(SAr, t);
 #pragma unroll
                         for (int j = 0; j < KPX; j++) SAr[j] = t[j];
                     }
-                    if (RGB3_HS1 < 2) {
+                    {
                         float t[KPX];
                         hsum19(SAg, t);
 #pragma unroll
@@ -621,7 +540,6 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
                     sm.qbuf[qb][pair][1][lane] = make_float4(q[4], q[5], q[6], q[7]);
                     __syncwarp();
                     mbar_arrive_lane0(mb_qfull + 8 * qb, lane);
-                    if (em >= 0) merge(em, pb);
 #pragma unroll
                     for (int c = 0; c < 3; c++) cq[c] = cqn[c];
                 }
@@ -633,17 +551,12 @@ __global__ void __launch_bounds__(R3_THREADS, 1) k_fused_cvf_rgb3(const Rgb3Args
                     if (E >= NQ3) mbar_wait(mb_qempty + 8 * qb, (unsigned)(E / NQ3 - 1) & 1u);
                     if (lane == 0) mbar_arrive(mb_qfull + 8 * qb);
                     __syncwarp();
-                    if (!RGB3_MERGE_WG) merge(e, prefetch_best());
                 }
-            }
-            if (active && !RGB3_MERGE_WG) {  // the emissions not merged inside the loop
-#pragma unroll 1
-                for (int e = max(0, n_emit - MLAG3); e < n_emit; e++) merge(e, prefetch_best());
             }
             __syncthreads();  // group end
         }
     } else {
-        // ====== STAGE 3 (RGB3_MERGE_WG): merge of the block's 4 disparities into the running (best,label) ======
+        // ====== STAGE 3: merge of the block's 4 disparities into the running (best,label) ======
         // Thread t of these 4 warps folds strip-local columns 2t, 2t+1 of the rows the stage-2 warps publish in the q
         // ring; the (best,label) of the previous groups is fetched two rows ahead.
         reg_dec<R3_REGS3>();
