@@ -731,20 +731,20 @@ __device__ __forceinline__ void store_ig(const PrepArgs& P, size_t o, unsigned v
 // One pixel of the padded frame into the strip-tiled planes.  Strip s covers columns [216 s - 20, 216 s + 236); the
 // 40 columns two strips share are stored in both.  Inside a record the 256 columns are laid out as
 // [16-byte chunk c][lane][16 B] with column = 8*lane + j: the c-th 128-bit load of lane L is uint4 c*32 + L.
+// One pixel of the padded frame into the strip-tiled planes (fused_dev.cuh: strips_of_column, tg/ti/tst_index).
 __device__ __forceinline__ void store_tiled(const PrepArgs& P, int x, int yrow, unsigned ig, __half ih, float2 st) {
     const int xa = x + HALO;
     if (xa < 0) return;
     const int s1 = xa / VALID_W;
     const int c1 = xa - s1 * VALID_W;
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < 2; k++) {  // (strips_of_column, unrolled)
         const int s = s1 - k, cl = c1 + k * VALID_W;
         if (s < 0 || s >= P.n_strips || cl >= SW) continue;
         const size_t rec = (size_t)s * P.rows_pad + yrow;
-        const int L = cl >> 3, j = cl & 7;
-        P.Tg[(rec * 64 + (j >> 2) * 32 + L) * 4 + (j & 3)] = ig;
-        P.TI[(rec * 32 + L) * 8 + j] = ih;
-        P.Tst[(rec * 128 + (j >> 1) * 32 + L) * 2 + (j & 1)] = st;
+        P.Tg[tg_index(rec, cl)] = ig;
+        P.TI[ti_index(rec, cl)] = ih;
+        P.Tst[tst_index(rec, cl)] = st;
     }
 }
 

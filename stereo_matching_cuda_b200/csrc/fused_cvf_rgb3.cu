@@ -623,6 +623,8 @@ struct Rgb3PrepArgs {
     float S;
 };
 
+// (the index arithmetic of tc_index / ts_s1_index / ts_s2_index / ts_s3_index in fused_dev.cuh, which
+// tests/layout_check.cu checks against the pixel order the kernel assumes, written out per record)
 __device__ __forceinline__ void store_tiled3(const Rgb3PrepArgs& P, int x, int yrow, __half r, __half g, __half b,
                                              float4 s1, float4 s2, float s3) {
     const int xa = x + HALO;

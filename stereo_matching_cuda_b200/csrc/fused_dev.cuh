@@ -164,6 +164,56 @@ __device__ __forceinline__ void hsum19(const float (&v)[KPX], float (&h)[KPX]) {
     h[7] = ((C - l[5]) + Tp1) + vp2;
 }
 
+// ---- strip-tiled planes ------------------------------------------------------------------
+// Strip s covers frame columns [VALID_W*s - HALO, VALID_W*s - HALO + SW); the 2*HALO columns two neighbouring strips
+// share are stored in both.  A record = one padded row of one strip, laid out as [16-byte chunk][lane][16 B] so that
+// the c-th 128-bit load of lane L (pixels 8L .. 8L+7 of the strip) is 16-byte unit c*32 + L of the record: one bulk
+// copy fills a shared-memory slot and every read of it is conflict-free.  The functions below say where strip-local
+// column cl (lane cl>>3, pixel j = cl&7) of record rec lives in each plane; the prep kernels store through them and
+// tests/layout_check.cu checks them on the CPU against the pixel order the fused kernels assume.
+__device__ __host__ __forceinline__ int strips_of_column(int x, int n_strips, int (&strip)[2], int (&cl)[2]) {
+    const int xa = x + HALO;
+    if (xa < 0) return 0;
+    const int s1 = xa / VALID_W, c1 = xa - s1 * VALID_W;
+    int n = 0;
+    for (int k = 0; k < 2; k++) {
+        const int s = s1 - k, c = c1 + k * VALID_W;
+        if (s < 0 || s >= n_strips || c >= SW) continue;
+        strip[n] = s;
+        cl[n] = c;
+        n++;
+    }
+    return n;
+}
+// (I,G) words: chunk = j>>2 (pixels 0..3 | 4..7), 64 16-byte units per record; index in 4-byte words
+__device__ __host__ __forceinline__ size_t tg_index(size_t rec, int cl) {
+    const int L = cl >> 3, j = cl & 7;
+    return (rec * 64 + (j >> 2) * 32 + L) * 4 + (j & 3);
+}
+// I as half: one chunk of 8 halves per lane, 32 units per record; index in halves
+__device__ __host__ __forceinline__ size_t ti_index(size_t rec, int cl) { return (rec * 32 + (cl >> 3)) * 8 + (cl & 7); }
+// (mean_I, c2) float2: chunk = j>>1, 128 units per record; index in float2
+__device__ __host__ __forceinline__ size_t tst_index(size_t rec, int cl) {
+    const int L = cl >> 3, j = cl & 7;
+    return (rec * 128 + (j >> 1) * 32 + L) * 2 + (j & 1);
+}
+// colour as halves: chunk = channel, 96 units per record; index in halves
+__device__ __host__ __forceinline__ size_t tc_index(size_t rec, int ch, int cl) {
+    return rec * 768 + (size_t)((ch * 32 + (cl >> 3)) * 8 + (cl & 7));
+}
+// RGB statistics: chunk 2j = (mu_r, mu_g, mu_b, M_rr), 2j+1 = (M_rg, M_rb, M_gg, M_gb) of pixel j (index in float4),
+// chunks 16, 17 = M_bb of pixels 0..3, 4..7 (index in floats); 576 units per record
+__device__ __host__ __forceinline__ size_t ts_s1_index(size_t rec, int cl) {
+    return rec * 576 + (size_t)((2 * (cl & 7)) * 32 + (cl >> 3));
+}
+__device__ __host__ __forceinline__ size_t ts_s2_index(size_t rec, int cl) {
+    return rec * 576 + (size_t)((2 * (cl & 7) + 1) * 32 + (cl >> 3));
+}
+__device__ __host__ __forceinline__ size_t ts_s3_index(size_t rec, int cl) {
+    const int L = cl >> 3, j = cl & 7;
+    return rec * 2304 + (size_t)(((16 + (j >> 2)) * 32 + L) * 4 + (j & 3));
+}
+
 // Match operands.  A warp reads, per row, the 8 pixels x 32 lanes at columns x + d: 32 B per lane.  From a linear
 // plane that is two 128-bit loads whose lanes are 32 B apart (half of every sector fetched by each, 8.75 L1 tag
 // requests per load in ncu).  The shifted copies of the (I,G) plane are therefore stored DE-INTERLEAVED: the even
@@ -174,8 +224,8 @@ __device__ __host__ __forceinline__ size_t deint_index(size_t i, size_t half_pla
     const size_t g4 = i >> 2;
     return (g4 & 1 ? half_plane : 0) + (g4 >> 1) * 4 + (i & 3);
 }
-__device__ __forceinline__ void match_ptrs(const unsigned* copy, long long e, size_t half_plane, const unsigned*& p0,
-                                           const unsigned*& p1) {
+__device__ __host__ __forceinline__ void match_ptrs(const unsigned* copy, long long e, size_t half_plane, const unsigned*& p0,
+                                                    const unsigned*& p1) {
     if ((e >> 2) & 1) {
         p0 = copy + half_plane + (e - 4) / 2;
         p1 = copy + (e + 4) / 2;
