@@ -75,8 +75,8 @@ int sb200_ctx_synchronize(sb200_ctx* ctx);
 const char* sb200_last_error(const sb200_ctx* ctx);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 uint64_t sb200_launch_count(const sb200_ctx* ctx);
-/* which fused RGB-guide kernel this context runs: 2 = k_fused_cvf_rgb (two warp roles), 3 = k_fused_cvf_rgb3 (three
- * roles + TMA operand ring).  Results are bit-identical; the environment variable SB200_RGB_KERNEL=2|3, read by
+/* which fused RGB-guide kernel this context runs: 2 = k_fused_cvf_rgb (two warp roles), 3 = k_fused_cvf_rgb3 (four
+ * roles + TMA operand ring; the default).  Results are bit-identical; the environment variable SB200_RGB_KERNEL=2|3, read by
  * sb200_ctx_create, overrides the default (A/B measurements). */
 int sb200_ctx_rgb_kernel(const sb200_ctx* ctx);
 const char* sb200_version(void);
