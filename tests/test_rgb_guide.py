@@ -114,3 +114,34 @@ def test_gpu_rgb_three_stage_kernel_full_size_1080p_d256(monkeypatch):
     inner[:, size_d + 20:w - 20] = True
     ok = (b["disp_left"] == truth) & inner
     assert ok.sum() / inner.sum() > 0.9
+
+
+@pytest.mark.gpu
+def test_gpu_rgb_strip_mode_matches_whole_frame():
+    """Row strips with 2*radius halo rows and the RGB guide: the strips' labels, concatenated, equal the whole frame's
+    (first-stage sums are exact; window areas and statistics use frame rows, so only second-stage float order differs)."""
+    S = pytest.importorskip("stereo_matching_cuda_b200")
+    torch = pytest.importorskip("torch")
+    from stereo_matching_cuda_b200 import api
+
+    w, h, size_d = 300, 200, 24
+    L, R = synth.make_pair(w, h, size_d, channels=3, seed=11)
+    p = api.default_params(dmin=-(size_d - 1), dmax=0, guide_mode=S.GUIDE_RGB)
+    with S.Context(0) as ctx:
+        whole = ctx.pipeline(L, R, p, want=("disp_left", "disp_right", "filled", "best_left"))
+        halo = ctx.strip_halo_rows(p)
+        ctx.set_stream(torch.cuda.current_stream())
+        parts = {k: [] for k in ("disp_left", "disp_right", "filled", "best_left")}
+        bounds = [0, 64, 128, 200]
+        for y0, y1 in zip(bounds[:-1], bounds[1:]):
+            top, bot = min(halo, y0), min(halo, h - y1)
+            dl = torch.from_numpy(L[y0 - top:y1 + bot].copy()).cuda()
+            dr = torch.from_numpy(R[y0 - top:y1 + bot].copy()).cuda()
+            outs = {k: torch.empty((y1 - y0, w), dtype=torch.float32, device="cuda") for k in parts}
+            ctx.pipeline_strip_dev(dl, dr, 3, w, dict(y0=y0, rows=y1 - y0, halo_top=top, halo_bot=bot, frame_h=h), outs, p)
+            torch.cuda.synchronize()
+            for k in parts:
+                parts[k].append(outs[k].cpu().numpy())
+    for k in ("disp_left", "disp_right", "filled"):
+        assert (np.concatenate(parts[k], 0) == whole[k]).mean() > 0.9999, k
+    assert np.allclose(np.concatenate(parts["best_left"], 0), whole["best_left"], rtol=1e-5, atol=1e-6)
