@@ -79,6 +79,11 @@ uint64_t sb200_launch_count(const sb200_ctx* ctx);
  * roles + TMA operand ring; the default).  Results are bit-identical; the environment variable SB200_RGB_KERNEL=2|3, read by
  * sb200_ctx_create, overrides the default (A/B measurements). */
 int sb200_ctx_rgb_kernel(const sb200_ctx* ctx);
+/* which fused gray-guide kernel this context runs: 1 = k_fused_mma (horizontal window sums on the tensor cores; the
+ * default), 0 = k_fused_cvf (warp-shuffle window sums).  Same contract, results equal within the parity tolerance (their
+ * second-stage float sums are ordered differently).  SB200_GRAY_KERNEL=mma|shfl, read by sb200_ctx_create, overrides. */
+int sb200_ctx_gray_kernel(const sb200_ctx* ctx);
+int sb200_ctx_set_gray_kernel(sb200_ctx* ctx, int which);
 const char* sb200_version(void);
 
 /* ---- stage drop-ins, HOST pointers, blocking ----------------------------------------- */

@@ -84,6 +84,8 @@ def load_library(path=None):
         "sb200_last_error": (C.c_char_p, [vp]),
         "sb200_launch_count": (C.c_uint64, [vp]),
         "sb200_ctx_rgb_kernel": (ip, [vp]),
+        "sb200_ctx_gray_kernel": (ip, [vp]),
+        "sb200_ctx_set_gray_kernel": (ip, [vp, ip]),
         "sb200_version": (C.c_char_p, []),
         "sb200_rgb_to_grayscale": (ip, [vp, PP, vp, ip, ip, vp]),
         "sb200_compute_cost": (ip, [vp, PP, vp, vp, vp, ip, ip, ip, ip, ip]),
@@ -203,6 +205,15 @@ class Context:
     def rgb_kernel(self):
         """2: k_fused_cvf_rgb, 3: k_fused_cvf_rgb3 (SB200_RGB_KERNEL overrides the library default)"""
         return int(self.lib.sb200_ctx_rgb_kernel(self.h))
+
+    @property
+    def gray_kernel(self):
+        """1: k_fused_mma (tensor-core window sums), 0: k_fused_cvf (warp-shuffle window sums)"""
+        return int(self.lib.sb200_ctx_gray_kernel(self.h))
+
+    @gray_kernel.setter
+    def gray_kernel(self, which):
+        self._ck(self.lib.sb200_ctx_set_gray_kernel(self.h, int(which)))
 
     def enable_timing(self, on=True):
         self._ck(self.lib.sb200_ctx_enable_timing(self.h, int(on)))

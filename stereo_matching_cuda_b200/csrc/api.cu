@@ -36,7 +36,7 @@ int sb200_ctx_create(int device, sb200_ctx** out) {
         return sb_fail(nullptr, SB200_ERR_CUDA, "no CUDA device: %s (this library has no CPU fallback)",
                        e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
     if (device < 0 || device >= ndev) return sb_fail(nullptr, SB200_ERR_INVALID, "device %d of %d", device, ndev);
-    SB_CUDA(nullptr, cudaSetDevice(device));
+    DevGuard dev_guard__(device);
     sb200_ctx* ctx = new (std::nothrow) sb200_ctx();
     if (!ctx) return sb_fail(nullptr, SB200_ERR_NOMEM, "ctx alloc");
     ctx->device = device;
@@ -55,16 +55,20 @@ int sb200_ctx_create(int device, sb200_ctx** out) {
     bool ok = true;
     for (int i = 0; i < 5; i++) ok = ok && (cudaEventCreate(&ctx->ev[i]) == cudaSuccess);
     ctx->ev_valid = ok;
+    if (cudaEventCreateWithFlags(&ctx->ev_stream, cudaEventDisableTiming) != cudaSuccess) ctx->ev_stream = nullptr;
     // A/B switch for the RGB-guide kernel: "2" = two-stage (fused_cvf_rgb.cu), "3" = three-stage (fused_cvf_rgb3.cu)
     if (const char* e = getenv("SB200_RGB_KERNEL")) ctx->rgb_kernel = (e[0] == '3') ? 3 : (e[0] == '2') ? 2 : ctx->rgb_kernel;
+    // A/B switch for the gray-guide kernel: "shfl" = warp-shuffle box sums (fused_cvf.cu), "mma" = tensor-core box sums
+    if (const char* e = getenv("SB200_GRAY_KERNEL")) ctx->gray_kernel = (e[0] == 's') ? 0 : (e[0] == 'm') ? 1 : ctx->gray_kernel;
     *out = ctx;
     return SB200_OK;
 }
 
 void sb200_ctx_destroy(sb200_ctx* ctx) {
+    DevGuard dev_guard__(ctx);
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->ev_stream) cudaEventDestroy(ctx->ev_stream);
     if (ctx->ws) cudaFree(ctx->ws);
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->ev_valid)
@@ -73,12 +77,25 @@ void sb200_ctx_destroy(sb200_ctx* ctx) {
 }
 
 int sb200_ctx_set_stream(sb200_ctx* ctx, void* stream) {
+    DevGuard dev_guard__(ctx);
     if (!ctx) return SB200_ERR_INVALID;
-    ctx->stream = (cudaStream_t)stream;
+    cudaStream_t next = (cudaStream_t)stream;
+    if (next != ctx->stream) {
+        // the arena is shared by all calls and rewound by each: work queued on the old stream must be done with it
+        // before work on the new stream overwrites it.  One in-flight stream per context.
+        if (ctx->ev_stream) {
+            SB_CUDA(ctx, cudaEventRecord(ctx->ev_stream, ctx->stream));
+            SB_CUDA(ctx, cudaStreamWaitEvent(next, ctx->ev_stream, 0));
+        } else {
+            SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    ctx->stream = next;
     return SB200_OK;
 }
 
 int sb200_ctx_synchronize(sb200_ctx* ctx) {
+    DevGuard dev_guard__(ctx);
     if (!ctx) return SB200_ERR_INVALID;
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SB200_OK;
@@ -87,14 +104,22 @@ int sb200_ctx_synchronize(sb200_ctx* ctx) {
 const char* sb200_last_error(const sb200_ctx* ctx) { return ctx ? ctx->err : g_sb200_global_err; }
 uint64_t sb200_launch_count(const sb200_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int sb200_ctx_rgb_kernel(const sb200_ctx* ctx) { return ctx ? ctx->rgb_kernel : 0; }
+int sb200_ctx_gray_kernel(const sb200_ctx* ctx) { return ctx ? ctx->gray_kernel : -1; }
+int sb200_ctx_set_gray_kernel(sb200_ctx* ctx, int which) {
+    if (!ctx || (which != 0 && which != 1)) return SB200_ERR_INVALID;
+    ctx->gray_kernel = which;
+    return SB200_OK;
+}
 
 int sb200_ctx_enable_timing(sb200_ctx* ctx, int on) {
+    DevGuard dev_guard__(ctx);
     if (!ctx) return SB200_ERR_INVALID;
     ctx->timing = on;
     return SB200_OK;
 }
 
 int sb200_last_timing(sb200_ctx* ctx, float* ms_prep, float* ms_fused, float* ms_merge, float* ms_occl) {
+    DevGuard dev_guard__(ctx);
     if (!ctx || !ctx->ev_valid) return SB200_ERR_INVALID;
     SB_CUDA(ctx, cudaEventSynchronize(ctx->ev[4]));
     float* outs[4] = {ms_prep, ms_fused, ms_merge, ms_occl};
@@ -105,8 +130,7 @@ int sb200_last_timing(sb200_ctx* ctx, float* ms_prep, float* ms_fused, float* ms
 
 }  // extern "C"
 
-int sb_ws_reserve(sb200_ctx* ctx, size_t bytes) {
-    SB_CUDA(ctx, cudaSetDevice(ctx->device));
+int sb_ws_reserve(sb200_ctx* ctx, size_t bytes) {  // (called under the entry point's DevGuard)
     bytes = sb_align(bytes, 1 << 20);
     if (bytes > ctx->ws_cap) {
         SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -317,6 +341,7 @@ int pipeline_core(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, 
         size_t bytes = p->guide_mode != SB200_GUIDE_RGB ? (sbf_fused_supported(p) ? sbf_workspace_bytes(ctx, w, g.h, g.rows_out, dabs, size_d, 2) : gf_ws_bytes(n_held) + 2 * sb_align(n_held))
                        : (p->box_mode == SB200_BOX_SAT ? rgb_ws_bytes(n_held) : rgb_fused_ws_bytes(ctx, w, g.h, g.rows_out, dabs, size_d));
         bytes += 2 * sb_align(n_held) + 4 * sb_align(n_out * 4) + 4096;
+        if (g.rows_out != g.h) bytes += 2 * sb_align(n_held);  // strips stage the mean images on held rows
         SB_TRY(sb_ws_reserve(ctx, bytes));
     }
     const bool full = (g.rows_out == g.h);
@@ -407,6 +432,7 @@ extern "C" {
 // ---- device-pointer stage entry points -------------------------------------------------
 int sb200_rgb_to_grayscale_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_rgb, int n, int channels,
                                uint8_t* d_gray) {
+    DevGuard dev_guard__(ctx);
     SB_TRY(check_params(ctx, p));
     REQUIRE(ctx, d_rgb && d_gray && n > 0, "null pointer or n <= 0");
     REQUIRE(ctx, channels >= 3, "channels must be >= 3 (the reference reads image[ch*i+{0,1,2}])");
@@ -415,6 +441,7 @@ int sb200_rgb_to_grayscale_dev(sb200_ctx* ctx, const sb200_params* p, const uint
 
 int sb200_compute_cost_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_i1, const uint8_t* d_i2,
                            float* d_cost, int w, int h, int dmin) {
+    DevGuard dev_guard__(ctx);
     SB_TRY(check_params(ctx, p));
     REQUIRE(ctx, d_i1 && d_i2 && d_cost && w > 0 && h > 0, "null pointer or empty image");
     const size_t n = (size_t)w * h;
@@ -428,6 +455,7 @@ int sb200_compute_cost_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t*
 }
 
 int sb200_integral_dev(sb200_ctx* ctx, const float* d_image, float* d_integral, int w, int h) {
+    DevGuard dev_guard__(ctx);
     REQUIRE(ctx, d_image && d_integral && w > 0 && h > 0, "null pointer or empty image");
     const size_t n = (size_t)w * h;
     SB_TRY(sb_ws_reserve(ctx, sb_align(n * 4) + 4096));
@@ -437,6 +465,7 @@ int sb200_integral_dev(sb200_ctx* ctx, const float* d_image, float* d_integral, 
 }
 
 int sb200_box_filter_dev(sb200_ctx* ctx, const sb200_params* p, const float* d_image, float* d_mean, int w, int h) {
+    DevGuard dev_guard__(ctx);
     SB_TRY(check_params(ctx, p));
     REQUIRE(ctx, d_image && d_mean && w > 0 && h > 0, "null pointer or empty image");
     const size_t n = (size_t)w * h;
@@ -449,6 +478,7 @@ int sb200_box_filter_dev(sb200_ctx* ctx, const sb200_params* p, const float* d_i
 int sb200_compute_guided_filter_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_i, const float* d_cost,
                                     float* d_filter_cost, float* d_disp_map, uint8_t* d_mean, int w, int h,
                                     int size_d, int dmin) {
+    DevGuard dev_guard__(ctx);
     SB_TRY(check_params(ctx, p));
     REQUIRE(ctx, d_i && d_cost && d_filter_cost && d_disp_map && w > 0 && h > 0 && size_d > 0, "null pointer or empty");
     SB_TRY(sb_ws_reserve(ctx, gf_ws_bytes((size_t)w * h)));
@@ -456,24 +486,28 @@ int sb200_compute_guided_filter_dev(sb200_ctx* ctx, const sb200_params* p, const
 }
 
 int sb200_winner_take_all_dev(sb200_ctx* ctx, const float* d_q, float* d_filter_cost, float* d_dmap, int n, int label) {
+    DevGuard dev_guard__(ctx);
     REQUIRE(ctx, d_q && d_filter_cost && d_dmap && n > 0, "null pointer or n <= 0");
     return sbk_disp_select(ctx, d_q, d_filter_cost, d_dmap, (size_t)n, label);
 }
 
 int sb200_detect_occlusion_dev(sb200_ctx* ctx, const sb200_params* p, float* d_dL, const float* d_dR, int dOcclusion,
                                int w, int h) {
+    DevGuard dev_guard__(ctx);
     SB_TRY(check_params(ctx, p));
     REQUIRE(ctx, d_dL && d_dR && w > 0 && h > 0, "null pointer or empty image");
     return sbk_detect_occlusion(ctx, d_dL, d_dR, dOcclusion, p->d_lr, w, h);
 }
 
 int sb200_fill_occlusion_dev(sb200_ctx* ctx, float* d_disparity, int w, int h, float vMin) {
+    DevGuard dev_guard__(ctx);
     REQUIRE(ctx, d_disparity && w > 0 && h > 0, "null pointer or empty image");
     return sbk_fill_occlusion(ctx, d_disparity, w, h, vMin);
 }
 
 int sb200_lr_check_fill_dev(sb200_ctx* ctx, const sb200_params* p, const float* d_dL, const float* d_dR, int w, int h,
                             int dOcclusion, float vMin, float* d_occlusion, float* d_filled) {
+    DevGuard dev_guard__(ctx);
     SB_TRY(check_params(ctx, p));
     REQUIRE(ctx, d_dL && d_dR && w > 0 && h > 0 && (d_occlusion || d_filled), "null pointer or empty image");
     return sbk_lr_check_fill(ctx, d_dL, d_dR, w, h, dOcclusion, p->d_lr, vMin, d_occlusion, d_filled);
@@ -481,6 +515,7 @@ int sb200_lr_check_fill_dev(sb200_ctx* ctx, const sb200_params* p, const float* 
 
 int sb200_view_disparity_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_guide, const uint8_t* d_other,
                              int w, int h, int dmin, int size_d, float* d_best, float* d_disp, uint8_t* d_mean) {
+    DevGuard dev_guard__(ctx);
     SB_TRY(check_params(ctx, p));
     REQUIRE(ctx, d_guide && d_other && w > 1 && h > 0 && size_d > 0 && (d_best || d_disp), "null pointer or empty");
     const int dabs = max(abs(dmin), abs(dmin + size_d - 1));
@@ -499,6 +534,7 @@ int sb200_strip_halo_rows(const sb200_params* p) { return p ? 2 * p->radius : 0;
 
 int sb200_pipeline_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, const uint8_t* d_right,
                        int channels, int w, int h, const sb200_outputs* d_out) {
+    DevGuard dev_guard__(ctx);
     SB_TRY(check_params(ctx, p));
     REQUIRE(ctx, d_left && d_right && d_out && w > 1 && h > 0, "null pointer or empty image");
     REQUIRE(ctx, channels == 1 || channels >= 3, "channels must be 1 (gray) or >= 3");
@@ -508,6 +544,7 @@ int sb200_pipeline_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_l
 
 int sb200_pipeline_strip_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, const uint8_t* d_right,
                              int channels, int w, const sb200_strip* s, const sb200_outputs* d_out) {
+    DevGuard dev_guard__(ctx);
     SB_TRY(check_params(ctx, p));
     REQUIRE(ctx, d_left && d_right && d_out && s && w > 1, "null pointer or empty image");
     REQUIRE(ctx, channels == 1 || channels >= 3, "channels must be 1 (gray) or >= 3");
@@ -524,6 +561,7 @@ int sb200_pipeline_strip_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_
 
 int sb200_pipeline_batch_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, const uint8_t* d_right,
                              int channels, int w, int h, int n_pairs, const sb200_outputs* d_out) {
+    DevGuard dev_guard__(ctx);
     SB_TRY(check_params(ctx, p));
     REQUIRE(ctx, d_left && d_right && d_out && w > 1 && h > 0 && n_pairs > 0, "null pointer or empty batch");
     REQUIRE(ctx, channels == 1 || channels >= 3, "channels must be 1 (gray) or >= 3");
@@ -546,6 +584,7 @@ int sb200_pipeline_batch_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_
 
 int sb200_pipeline(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h_left, const uint8_t* h_right, int channels,
                    int w, int h, const sb200_outputs* h_out) {
+    DevGuard dev_guard__(ctx);
     SB_TRY(check_params(ctx, p));
     REQUIRE(ctx, h_left && h_right && h_out && w > 1 && h > 0, "null pointer or empty image");
     REQUIRE(ctx, channels == 1 || channels >= 3, "channels must be 1 (gray) or >= 3");
@@ -584,6 +623,7 @@ int sb200_pipeline(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h_left,
 // ---- host-pointer stage entry points (blocking, reference calling convention) -------------
 int sb200_rgb_to_grayscale(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h_rgb, int n, int channels,
                            uint8_t* h_gray) {
+    DevGuard dev_guard__(ctx);
     SB_TRY(check_params(ctx, p));
     REQUIRE(ctx, h_rgb && h_gray && n > 0, "null pointer or n <= 0");
     REQUIRE(ctx, channels >= 3, "channels must be >= 3 (the reference reads image[ch*i+{0,1,2}])");
@@ -599,6 +639,7 @@ int sb200_rgb_to_grayscale(sb200_ctx* ctx, const sb200_params* p, const uint8_t*
 }
 
 int sb200_x_derivative(sb200_ctx* ctx, const uint8_t* img, float* grad, int w, int h) {
+    DevGuard dev_guard__(ctx);
     REQUIRE(ctx, img && grad && w > 0 && h > 0, "null pointer or empty image");
     const size_t n = (size_t)w * h;
     SB_TRY(sb_ws_reserve(ctx, sb_align(n) + sb_align(n * 4) + 4096));
@@ -615,6 +656,7 @@ int sb200_x_derivative(sb200_ctx* ctx, const uint8_t* img, float* grad, int w, i
 
 int sb200_compute_cost(sb200_ctx* ctx, const sb200_params* p, const uint8_t* i1, const uint8_t* i2, float* cost, int w1,
                        int w2, int h1, int h2, int dmin) {
+    DevGuard dev_guard__(ctx);
     SB_TRY(check_params(ctx, p));
     REQUIRE(ctx, i1 && i2 && cost && w1 > 0 && h1 > 0, "null pointer or empty image");
     REQUIRE(ctx, w1 == w2 && h1 == h2, "the two images must have the same size (costVolume.cu assumes it)");
@@ -639,6 +681,7 @@ int sb200_compute_cost(sb200_ctx* ctx, const sb200_params* p, const uint8_t* i1,
 }
 
 int sb200_integral(sb200_ctx* ctx, const float* image, float* integral, int width, int height) {
+    DevGuard dev_guard__(ctx);
     REQUIRE(ctx, image && integral && width > 0 && height > 0, "null pointer or empty image");
     const size_t n = (size_t)width * height;
     SB_TRY(sb_ws_reserve(ctx, 3 * sb_align(n * 4) + 4096));
@@ -654,6 +697,7 @@ int sb200_integral(sb200_ctx* ctx, const float* image, float* integral, int widt
 }
 
 int sb200_box_filter_sat(sb200_ctx* ctx, const sb200_params* p, const float* integral, float* mean, int w, int h) {
+    DevGuard dev_guard__(ctx);
     SB_TRY(check_params(ctx, p));
     REQUIRE(ctx, integral && mean && w > 0 && h > 0, "null pointer or empty image");
     const size_t n = (size_t)w * h;
@@ -669,6 +713,7 @@ int sb200_box_filter_sat(sb200_ctx* ctx, const sb200_params* p, const float* int
 }
 
 int sb200_box_filter(sb200_ctx* ctx, const sb200_params* p, const float* image, float* mean, int w, int h) {
+    DevGuard dev_guard__(ctx);
     SB_TRY(check_params(ctx, p));
     REQUIRE(ctx, image && mean && w > 0 && h > 0, "null pointer or empty image");
     const size_t n = (size_t)w * h;
@@ -687,6 +732,7 @@ int sb200_box_filter(sb200_ctx* ctx, const sb200_params* p, const float* image, 
 
 int sb200_filter(sb200_ctx* ctx, const sb200_params* p, const uint8_t* image, int width, int height, uint8_t* mean,
                  float* var) {
+    DevGuard dev_guard__(ctx);
     SB_TRY(check_params(ctx, p));
     REQUIRE(ctx, image && (mean || var) && width > 0 && height > 0, "null pointer or empty image");
     const size_t n = (size_t)width * height;
@@ -712,6 +758,7 @@ int sb200_filter(sb200_ctx* ctx, const sb200_params* p, const uint8_t* image, in
 
 int sb200_compute_guided_filter(sb200_ctx* ctx, const sb200_params* p, const uint8_t* i, const float* cost,
                                 float* filter_cost, float* disp_map, uint8_t* mean, int w, int h, int size_d, int dmin) {
+    DevGuard dev_guard__(ctx);
     SB_TRY(check_params(ctx, p));
     REQUIRE(ctx, i && cost && filter_cost && disp_map && w > 0 && h > 0 && size_d > 0, "null pointer or empty");
     const size_t n = (size_t)w * h;
@@ -736,6 +783,7 @@ int sb200_compute_guided_filter(sb200_ctx* ctx, const sb200_params* p, const uin
 }
 
 int sb200_winner_take_all(sb200_ctx* ctx, const float* q, float* filter_cost, float* dmap, int n, int label) {
+    DevGuard dev_guard__(ctx);
     REQUIRE(ctx, q && filter_cost && dmap && n > 0, "null pointer or n <= 0");
     const size_t nn = (size_t)n;
     SB_TRY(sb_ws_reserve(ctx, 3 * sb_align(nn * 4) + 4096));
@@ -755,6 +803,7 @@ int sb200_winner_take_all(sb200_ctx* ctx, const float* q, float* filter_cost, fl
 
 int sb200_detect_occlusion(sb200_ctx* ctx, const sb200_params* p, float* disparityLeft, const float* disparityRight,
                            int dOcclusion, uint8_t* dmapl, uint8_t* dmapr, int w, int h) {
+    DevGuard dev_guard__(ctx);
     (void)dmapl;  // passed through untouched by the reference (occlusion.cu:40-41,55-56)
     (void)dmapr;
     SB_TRY(check_params(ctx, p));
@@ -773,6 +822,7 @@ int sb200_detect_occlusion(sb200_ctx* ctx, const sb200_params* p, float* dispari
 }
 
 int sb200_fill_occlusion(sb200_ctx* ctx, float* disparity, int w, int h, float vMin) {
+    DevGuard dev_guard__(ctx);
     REQUIRE(ctx, disparity && w > 0 && h > 0, "null pointer or empty image");
     const size_t n = (size_t)w * h;
     SB_TRY(sb_ws_reserve(ctx, sb_align(n * 4) + 4096));

@@ -30,10 +30,31 @@ struct sb200_ctx {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_valid = false;
     bool fused_attr_set = false;
+    bool mma_attr_set = false;
+    int gray_kernel = 1;  // gray-guide fused kernel: 0 = warp-shuffle box sums (fused_cvf.cu), 1 = tensor-core box sums (fused_mma.cu)
+    cudaEvent_t ev_stream = nullptr;  // orders a new stream after the work queued on the previous one (set_stream)
     int rgb_kernel = 3;  // RGB-guide fused kernel: 2 = two-stage (fused_cvf_rgb.cu), 3 = three-stage (fused_cvf_rgb3.cu)
 };
 
 extern char g_sb200_global_err[512];
+
+// Every extern "C" entry point runs on the context's device and leaves the caller's current device as it found it
+// (a process may hold several contexts, or have torch's current device elsewhere).
+struct DevGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DevGuard(const sb200_ctx* c) {
+        if (c && cudaGetDevice(&prev) == cudaSuccess && prev != c->device) switched = (cudaSetDevice(c->device) == cudaSuccess);
+    }
+    explicit DevGuard(int device) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = (cudaSetDevice(device) == cudaSuccess);
+    }
+    ~DevGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+    DevGuard(const DevGuard&) = delete;
+    DevGuard& operator=(const DevGuard&) = delete;
+};
 
 inline int sb_fail(sb200_ctx* ctx, int code, const char* fmt, ...) {
     char* dst = ctx ? ctx->err : g_sb200_global_err;
@@ -132,6 +153,12 @@ int sbf_pair_disparity(sb200_ctx* ctx, const sb200_params* p, const uint8_t* gra
 // single view (guide, other, dmin)
 int sbf_view_disparity(sb200_ctx* ctx, const sb200_params* p, const uint8_t* guide, const uint8_t* other,
                        const SbFusedGeom& g, int dmin, int size_d, float* best, float* disp, uint8_t* mean);
+// tensor-core variant (fused_mma.cu): same contract as run_fused of fused_cvf.cu
+int sbf_mma_supported(const sb200_params* p);
+size_t sbf_mma_workspace_bytes(const sb200_ctx* ctx, int w, int h_held, int rows_out, int dabs, int size_d, int n_views);
+int sbf_run_fused_mma(sb200_ctx* ctx, const sb200_params* p, const uint8_t* const gray[2], const SbFusedGeom& g,
+                      const int dmin[2], int size_d, int n_views, float* const best[2], float* const disp[2],
+                      uint8_t* const mean[2]);
 // RGB guide, fused (fused_cvf_rgb.cu): colour images (interleaved, `channels` bytes per pixel) + their gray versions
 size_t sbf_rgb_workspace_bytes(const sb200_ctx* ctx, int w, int h_held, int rows_out, int dabs, int size_d);
 int sbf_pair_disparity_rgb(sb200_ctx* ctx, const sb200_params* p, const uint8_t* rgb_l, const uint8_t* rgb_r, int channels,

@@ -844,7 +844,8 @@ size_t sbf_workspace_bytes(const sb200_ctx* ctx, int w, int h_held, int rows_out
     bytes += 2 * sb_align(plane * 4 * 4);  // IG x2, 4 shifted copies each
     bytes += 2 * (sb_align(recs * 1024) + sb_align(recs * 512) + sb_align(recs * 2048));  // strip-tiled Tg, TI, Tst x2
     bytes += sb_align((size_t)plan.n_chunks * 2 * rows_out * pitchS * 8);  // BL
-    return bytes + 4096;
+    const size_t mma = sbf_mma_workspace_bytes(ctx, w, h_held, rows_out, dabs, size_d, n_views);
+    return (bytes > mma ? bytes : mma) + 4096;
 }
 
 static int launch_prep(sb200_ctx* ctx, const sb200_params* p, const uint8_t* gray, const SbFusedGeom& g, int pitch, int padx,
@@ -890,6 +891,8 @@ int sbf_prep_gray_tiled(sb200_ctx* ctx, const sb200_params* p, const uint8_t* gr
 static int run_fused(sb200_ctx* ctx, const sb200_params* p, const uint8_t* const gray[2], const SbFusedGeom& g,
                      const int dmin[2], int size_d, int n_views, float* const best[2], float* const disp[2],
                      uint8_t* const mean[2]) {
+    if (ctx->gray_kernel == 1 && p->guide_mode == SB200_GUIDE_GRAY && sbf_mma_supported(p))
+        return sbf_run_fused_mma(ctx, p, gray, g, dmin, size_d, n_views, best, disp, mean);
     if (p->radius != RAD)
         return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "fused kernel is built for radius %d (got %d): use box_mode stages", RAD,
                        p->radius);
