@@ -41,45 +41,53 @@ constexpr int M_KB = 160;       // cost columns per strip = K of MMA 1 (146 used
 constexpr int M_KC = M_TW + 2 * RAD;  // 146 cost columns that feed the 128 a/b lanes
 constexpr int M_K2 = 128;       // K of MMA 2 (8 K-steps)
 constexpr int M_ND = 8;         // disparities per group
-constexpr int M_NWA = 10;       // role-A warps: 5 per image row of an iteration
-constexpr int M_THREADS = 640;  // 4 B + 4 C + 10 A + MMA + TMA warps
-constexpr int M_NGA = 16;       // guide ring: iterations kept in shared memory (history of 11 + prefetch)
-constexpr int M_NOP = 4;        // operand ring (a/b statistics + match rows): iterations in flight
+constexpr int MR = 4;           // image rows per pipeline iteration (one hand-off between the roles per MR rows)
+constexpr int M_NWA = 5;        // role-A warps: one thread per cost column, all MR rows
+constexpr int M_THREADS = 768;  // 8 B + 8 C + 5 A + MMA + TMA warps (+ 1 idle: whole warpgroups)
+constexpr int M_NOP = 4;        // operand ring (guide rows, a/b statistics, match rows): iterations in flight
+constexpr int M_NGC = 8;        // ring of the output rows' intensities (role C runs behind the others)
 constexpr int M_MTC = 42;       // match chunks (4 pixels x 4 shifted copies, 64 B) per row in an operand slot
-constexpr int M_RESUM = 16;     // role C re-sums its ring every M_RESUM iterations
+constexpr int M_RESUM = 8;      // role C re-sums its ring every M_RESUM iterations (32 rows)
+constexpr float I_CENTER = 128.0f;  // q = mean_a * (I - I_CENTER) + mean(b + I_CENTER * a)
+static_assert((4 * RAD) % MR == 0, "MR must divide the warm-up length");
 
 constexpr uint32_t GA_ROW = M_KB * 8;             // (I, G, I&15, I&240) as 4 halves per cost column
 constexpr uint32_t GB_ROW = M_TW * 8;             // (mean_I, c2 * scale) per a/b lane
+constexpr uint32_t GC_ROW = M_TW * 2;             // I - I_CENTER as half per output lane
 constexpr uint32_t MT_ROW = M_MTC * 64;
-constexpr uint32_t OP_GB = 0, OP_MT = ROWS * GB_ROW, OP_BYTES = OP_MT + ROWS * MT_ROW;
+constexpr uint32_t OP_GA = 0, OP_GB = MR * GA_ROW, OP_MT = OP_GB + MR * GB_ROW, OP_BYTES = OP_MT + MR * MT_ROW;
 constexpr uint32_t B1_GROUP = M_KB * 16;          // one N-group (8 columns) of B1: 160 rows x 16 B
-constexpr uint32_t B1_BYTES = 6 * B1_GROUP;       // dP (2 rows), d(lo) (2), d(hi) (2)
+constexpr uint32_t B1_BYTES = 3 * MR * B1_GROUP;  // dP (MR rows), d(lo) (MR), d(hi) (MR)
 constexpr uint32_t B2_GROUP = M_K2 * 16;
-constexpr uint32_t B2_BYTES = 8 * B2_GROUP;       // hi: (row, d-quad) x 4, lo likewise
-constexpr uint32_t PR_SLOT = M_KB * 16;           // P of 8 disparities (halves) per cost column
+constexpr uint32_t B2_BYTES = 4 * MR * B2_GROUP;  // hi: (row, d-quad) x 2 MR, lo likewise
+constexpr uint32_t PR_IL = M_KB * 16;             // a ring slot: P of 8 disparities (halves) per cost column, then the
+constexpr uint32_t PR_SLOT = PR_IL + M_KB * 4;    // row's (I&15, I&240) per cost column (needed again when the row leaves)
 
 struct MSmem {
-    unsigned char b1[2][B1_BYTES];
-    unsigned char b2[2][B2_BYTES];
+    unsigned char b1[B1_BYTES];
+    unsigned char b2[B2_BYTES];
     unsigned char pring[WIN][PR_SLOT];
-    unsigned char ga[M_NGA][ROWS * GA_ROW];
     unsigned char op[M_NOP][OP_BYTES];
+    unsigned char gc[M_NGC][MR * GC_ROW];
+    float2 xb[2][MR][M_TW];    // [emission parity][row][lane] (cost, label): 4-disparity winners between the halves of role C
     float ry_lut[2][WIN + 1];  // [0][n] = scale/(S*n), [1][n] = 1/(scale*n); [.][0] = 0
-    uint64_t ga_full[M_NGA], ga_empty[M_NGA], op_full[M_NOP], op_empty[M_NOP];
-    uint64_t b1_full[2], b1_empty[2], d1_full[2], d1_empty[2], b2_full[2], b2_empty[2], d2_full[2], d2_empty[2];
+    uint64_t op_full[M_NOP], op_empty[M_NOP], gc_full[M_NGC], gc_empty[M_NGC];
+    uint64_t b1_full, b1_empty, d1_full, d1_empty, b2_full, b2_empty, d2_full, d2_empty;
+    uint64_t x_full[2][2], x_empty[2][2];  // [emission parity][receiving half]
     uint32_t tmem_base;
 };
 static_assert(sizeof(MSmem) <= 227 * 1024, "shared memory budget");
 
 // Tensor-Memory column map of a lane (512 columns)
 constexpr uint32_t TC_BAND = 0;     // 80 columns: Band[lane][0..159] as packed halves
-constexpr uint32_t TC_D1 = 80;      // 2 x 32: dH_p (row, d) | dH_Ip (row, d)
-constexpr uint32_t TC_D2 = 144;     // 2 x 32: (row, d, {a,b})
+constexpr uint32_t TC_D1 = 80;      // 64: dH_p (row, d) | dH_Ip (row, d)
+constexpr uint32_t TC_D2 = 144;     // 64: (row, d, {a,b})
 constexpr uint32_t TC_RING = 208;   // 19 x 16: (H_a, H_b) x 8 d of the last 19 rows
 
 struct MmaArgs {
     const uint2* GA[2];    // per IMAGE: [strip][rows_pad][160] (I, G, I&15, I&240) halves; pad (1024,1024,0,0)
     const float2* GB[2];   // per IMAGE: [strip][rows_pad][128] (mean_I, scale * c/(S*area)); 0 outside
+    const __half* GC[2];   // per IMAGE: [strip][rows_pad][128] I - I_CENTER of the output lanes
     const uint4* MT[2];    // per IMAGE: [rows_pad][n_chunk][4] chunk i, copy s: I halves of X = 4i+s..+3, then G halves
     int rows_pad, n_chunk, padm;
     int w;
@@ -119,26 +127,6 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint3
 __host__ __device__ constexpr uint32_t instr_desc(int N, int b_neg) {
     return (1u << 4) | ((uint32_t)b_neg << 14) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
-__device__ __forceinline__ void tm_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tm_ld16u(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
-        "[%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
 __device__ __forceinline__ void tm_st16u(uint32_t taddr, const uint32_t* r) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -147,8 +135,22 @@ __device__ __forceinline__ void tm_st16u(uint32_t taddr, const uint32_t* r) {
         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
+__device__ __forceinline__ void tm_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tm_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+                 "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t a) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
 }
 __device__ __forceinline__ uint2 lds64(uint32_t addr) {
     uint2 v;
@@ -160,6 +162,11 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint32_t lds16(uint32_t addr) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ float2 ld_early_f2(const void* p) {  // coherent: written by this thread one group earlier
     float2 v;
     asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
@@ -169,12 +176,12 @@ __device__ __forceinline__ float2 ld_early_f2(const void* p) {  // coherent: wri
 __device__ __forceinline__ float fhadd_lo(unsigned h2, float c) { return fhadd(__low2half(u2h2(h2)), c); }
 __device__ __forceinline__ float fhadd_hi(unsigned h2, float c) { return fhadd(__high2half(u2h2(h2)), c); }
 
-// Register budgets of the warpgroups.  setmaxnreg only moves registers inside the pool the block got at launch: 640 threads
-// x 96 registers (what __launch_bounds__(640, 1) lets ptxas use) = 61440, NOT the whole 64 K file -- budgets that add up
+// Register budgets of the warpgroups.  setmaxnreg only moves registers inside the pool the block got at launch: 768 threads
+// x 80 registers (what __launch_bounds__(768, 1) lets ptxas use) = 61440, NOT the whole 64 K file -- budgets that add up
 // to more leave the last setmaxnreg.inc waiting forever.
-constexpr int M_REGS_LAUNCH = 96;
-constexpr int M_REGS_B = 160, M_REGS_C = 152, M_REGS_A = 56;
-static_assert(128 * M_REGS_B + 128 * M_REGS_C + 384 * M_REGS_A <= M_THREADS * M_REGS_LAUNCH, "register pool of the block");
+constexpr int M_REGS_LAUNCH = 80;
+constexpr int M_REGS_B = 88, M_REGS_C = 80, M_REGS_A = 72;
+static_assert(256 * M_REGS_B + 256 * M_REGS_C + 256 * M_REGS_A <= M_THREADS * M_REGS_LAUNCH, "register pool of the block");
 
 __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -199,31 +206,37 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
     const int yb0 = A.y_out0 + band * A.band_rows;
     const int yb1 = min(yb0 + A.band_rows, A.y_out0 + A.rows_out);
     const int y_first = yb0 - 2 * RAD;
-    const int niter = ((yb1 - yb0) + 4 * RAD + ROWS - 1) / ROWS;
-    constexpr int WARM_IT = 4 * RAD / ROWS;
+    // 36 warm-up rows fill both windows, then one output row per input row; iterations take MR rows (the last one may run
+    // past the band: those rows read zero padding and are not stored)
+    const int niter = ((yb1 - yb0) + 4 * RAD + MR - 1) / MR;
+    constexpr int WARM_IT = 4 * RAD / MR;
     const int Ktotal = ngroups * niter;
 
-    // ---- set-up: Tensor Memory, barriers, tables, a finite guide ring ----
+    // ---- set-up: Tensor Memory, barriers, tables, zeroed shared memory ----
     if (warp == 0) tm_alloc(&sm.tmem_base);
+    auto bar = [&](const uint64_t* b) { return smem_addr(b); };
     if (threadIdx.x == 32) {
-        for (int i = 0; i < M_NGA; i++) {
-            mbar_init(smem_addr(&sm.ga_full[i]), 1);
-            mbar_init(smem_addr(&sm.ga_empty[i]), M_NWA + 4);  // role A at K+10, role C at K+9
-        }
         for (int i = 0; i < M_NOP; i++) {
-            mbar_init(smem_addr(&sm.op_full[i]), 1);
-            mbar_init(smem_addr(&sm.op_empty[i]), M_NWA + 4);  // role A (match rows), role B (statistics)
+            mbar_init(bar(&sm.op_full[i]), 1);
+            mbar_init(bar(&sm.op_empty[i]), M_NWA + 8);  // role A (guide and match rows), role B (statistics)
         }
-        for (int i = 0; i < 2; i++) {
-            mbar_init(smem_addr(&sm.b1_full[i]), M_NWA);
-            mbar_init(smem_addr(&sm.b1_empty[i]), 1);
-            mbar_init(smem_addr(&sm.d1_full[i]), 1);
-            mbar_init(smem_addr(&sm.d1_empty[i]), 4);
-            mbar_init(smem_addr(&sm.b2_full[i]), 4);
-            mbar_init(smem_addr(&sm.b2_empty[i]), 1);
-            mbar_init(smem_addr(&sm.d2_full[i]), 1);
-            mbar_init(smem_addr(&sm.d2_empty[i]), 4);
+        for (int i = 0; i < M_NGC; i++) {
+            mbar_init(bar(&sm.gc_full[i]), 1);
+            mbar_init(bar(&sm.gc_empty[i]), 8);
         }
+        mbar_init(bar(&sm.b1_full), M_NWA);
+        mbar_init(bar(&sm.b1_empty), 1);
+        mbar_init(bar(&sm.d1_full), 1);
+        mbar_init(bar(&sm.d1_empty), 8);
+        mbar_init(bar(&sm.b2_full), 8);
+        mbar_init(bar(&sm.b2_empty), 1);
+        mbar_init(bar(&sm.d2_full), 1);
+        mbar_init(bar(&sm.d2_empty), 8);
+        for (int i = 0; i < 2; i++)
+            for (int r = 0; r < 2; r++) {
+                mbar_init(bar(&sm.x_full[i][r]), 4);
+                mbar_init(bar(&sm.x_empty[i][r]), 4);
+            }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x >= 64 && threadIdx.x < 64 + 2 * (WIN + 1)) {
@@ -232,8 +245,7 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
         if (n > 0) v = (t < WIN + 1) ? A.scale * __frcp_rn(A.S * (float)n) : A.inv_scale * __frcp_rn((float)n);
         sm.ry_lut[t / (WIN + 1)][n] = v;
     }
-    {   // the guide ring is read 10 iterations back before those rows exist (times a zero cost): keep it finite;
-        // cost columns 146..159 of B1 and everything else start from zero as well
+    {   // cost columns 146..159 of B1 are never written and are multiplied by zero band entries: they must be finite
         uint4* z = reinterpret_cast<uint4*>(smem_raw);
         const int n16 = (int)(offsetof(MSmem, ry_lut) / 16);
         for (int i = threadIdx.x; i < n16; i += M_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -244,14 +256,14 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
     tm_fence_after();
     const uint32_t tmem = sm.tmem_base;
 
-    auto bar = [&](const uint64_t* b) { return smem_addr(b); };
-
-    if (warp < 4) {
+    if (warp < 8) {
         // ================= role B: 2-D box sums of P and I*P, a and b, fp16 hi/lo split =================
+        // warp = (lane quarter, disparity half h): 4 disparities x MR rows per thread and iteration
         reg_inc<M_REGS_B>();
-        const int l = warp * 32 + lane;
-        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
-        {   // this lane's row of the band matrix: Band[l][k] = 1 for l <= k <= l + 18
+        const int q4 = warp & 3, h = warp >> 2;
+        const int l = q4 * 32 + lane;
+        const uint32_t tl = tmem + ((uint32_t)(q4 * 32) << 16);
+        if (h == 0) {  // this lane's row of the band matrix: Band[l][k] = 1 for l <= k <= l + 18
             for (int j0 = 0; j0 < M_KB / 2; j0 += 16) {
                 uint32_t v[16];
 #pragma unroll
@@ -265,358 +277,399 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
             }
             tm_wait_st();
             tm_fence_before();
+            named_bar_arrive(1, 128 + 32);  // the MMA warp waits for the band
         }
-        named_bar_arrive(1, 128 + 32);  // the MMA warp waits for the band
         const int x = xa0 + l;
         const bool xin = x >= 0 && x < A.w;
         const float rx = xin ? __frcp_rn((float)(min(A.w - 1, x + RAD) - max(0, x - RAD) + 1)) : 0.0f;
-        const uint32_t b2_lane = (uint32_t)((l >> 3) * 128 + (l & 7) * 16);
+        const uint32_t td1 = tl + TC_D1 + 4 * h;
+        const uint32_t b2a = smem_addr(&sm.b2[0]) + (uint32_t)((l >> 3) * 128 + (l & 7) * 16) + (uint32_t)h * B2_GROUP;
+        const uint32_t ops = smem_addr(&sm.op[0][0]) + OP_GB + (uint32_t)l * 8;
+        const uint32_t mb_d1f = bar(&sm.d1_full), mb_d1e = bar(&sm.d1_empty), mb_b2f = bar(&sm.b2_full),
+                       mb_b2e = bar(&sm.b2_empty), mb_opf = bar(&sm.op_full[0]), mb_ope = bar(&sm.op_empty[0]);
+        int K = 0;
         for (int g = 0; g < ngroups; g++) {
-            float Sp[M_ND], Sip[M_ND];
+            float Sp[4], Sip[4];
 #pragma unroll
-            for (int d = 0; d < M_ND; d++) Sp[d] = Sip[d] = 0.0f;
+            for (int d = 0; d < 4; d++) Sp[d] = Sip[d] = 0.0f;
 #pragma unroll 1
-            for (int it = 0; it < niter; it++) {
-                const int K = g * niter + it;
-                const int yi0 = y_first + it * ROWS;
-                mbar_wait(bar(&sm.d1_full[K & 1]), (unsigned)(K >> 1) & 1u);
+            for (int it = 0; it < niter; it++, K++) {
+                const int yi0 = y_first + it * MR;
+                const int ko = K & (M_NOP - 1);
+                mbar_wait(mb_d1f, (unsigned)K & 1u);
                 tm_fence_after();
-                uint32_t dh[32];
-                tm_ld32(tl + TC_D1 + 32 * (K & 1), dh);
-                mbar_wait(bar(&sm.op_full[K & (M_NOP - 1)]), (unsigned)(K / M_NOP) & 1u);
-                const uint32_t opa = smem_addr(&sm.op[K & (M_NOP - 1)][0]) + OP_GB + (uint32_t)l * 8;
-                uint2 st[ROWS];
+                uint32_t dp[MR][4], dip[MR][4];
 #pragma unroll
-                for (int r = 0; r < ROWS; r++) st[r] = lds64(opa + r * GB_ROW);
+                for (int r = 0; r < MR; r++) {
+                    tm_ld4(td1 + 8 * r, dp[r]);
+                    tm_ld4(td1 + 8 * MR + 8 * r, dip[r]);
+                }
+                mbar_wait(mb_opf + 8 * ko, (unsigned)(K / M_NOP) & 1u);
+                uint2 st[MR];
+#pragma unroll
+                for (int r = 0; r < MR; r++) st[r] = lds64(ops + ko * OP_BYTES + r * GB_ROW);
                 tm_wait_ld();
                 tm_fence_before();
                 __syncwarp();
-                mbar_arrive_lane0(bar(&sm.d1_empty[K & 1]), lane);
-                uint32_t hi[ROWS][M_ND], lo[ROWS][M_ND];
+                mbar_arrive_lane0(mb_d1e, lane);
 #pragma unroll
-                for (int r = 0; r < ROWS; r++) {
+                for (int r = 0; r < MR; r++) {
                     const float mI = __uint_as_float(st[r].x), c2 = __uint_as_float(st[r].y);
+                    const float mIc = I_CENTER - mI;
                     const float r1 = rx * inv_rows(sm.ry_lut[0], yi0 + r - RAD, A.y_global0, A.frame_h);
+                    uint32_t hi[4], lo[4];
 #pragma unroll
-                    for (int d = 0; d < M_ND; d++) {
-                        Sp[d] += __uint_as_float(dh[r * 8 + d]);
-                        Sip[d] += __uint_as_float(dh[16 + r * 8 + d]);
+                    for (int d = 0; d < 4; d++) {
+                        Sp[d] += __uint_as_float(dp[r][d]);
+                        Sip[d] += __uint_as_float(dip[r][d]);
                         const float cov = fmaf(-mI, Sp[d], Sip[d]);
                         const float a = cov * c2;
-                        const float b = fmaf(-mI, a, Sp[d] * r1);
+                        // b + 128 a: role C evaluates q = mean_a * (I - 128) + mean(b + 128 a), which halves the magnitudes
+                        // that cancel in mean_a * I + mean_b (guidedFilter.cu:363-369) and with them the rounding error
+                        const float b = fmaf(mIc, a, Sp[d] * r1);
                         const unsigned h2 = h22u(__floats2half2_rn(a, b));
                         // hi - value = -(lo part); MMA 2 takes the lo pass with B negated
                         const float na = fhadd_lo(h2, -a), nb = fhadd_hi(h2, -b);
-                        hi[r][d] = h2;
-                        lo[r][d] = h22u(__floats2half2_rn(na, nb));
+                        hi[d] = h2;
+                        lo[d] = h22u(__floats2half2_rn(na, nb));
                     }
-                }
-                if (K >= 2) mbar_wait(bar(&sm.b2_empty[K & 1]), (unsigned)((K >> 1) - 1) & 1u);
-                const uint32_t b2a = smem_addr(&sm.b2[K & 1][0]) + b2_lane;
-#pragma unroll
-                for (int r = 0; r < ROWS; r++) {
-#pragma unroll
-                    for (int q4 = 0; q4 < 2; q4++) {
-                        sts128(b2a + (uint32_t)(r * 2 + q4) * B2_GROUP, hi[r][4 * q4], hi[r][4 * q4 + 1], hi[r][4 * q4 + 2],
-                               hi[r][4 * q4 + 3]);
-                        sts128(b2a + (uint32_t)(4 + r * 2 + q4) * B2_GROUP, lo[r][4 * q4], lo[r][4 * q4 + 1],
-                               lo[r][4 * q4 + 2], lo[r][4 * q4 + 3]);
-                    }
+                    if (r == 0 && K >= 1) mbar_wait(mb_b2e, (unsigned)(K - 1) & 1u);  // MMA 2 of the previous iteration has read B2
+                    sts128(b2a + (uint32_t)(r * 2) * B2_GROUP, hi[0], hi[1], hi[2], hi[3]);
+                    sts128(b2a + (uint32_t)(2 * MR + r * 2) * B2_GROUP, lo[0], lo[1], lo[2], lo[3]);
                 }
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    mbar_arrive(bar(&sm.b2_full[K & 1]));
-                    mbar_arrive(bar(&sm.op_empty[K & (M_NOP - 1)]));
+                    mbar_arrive(mb_b2f);
+                    mbar_arrive(mb_ope + 8 * ko);
                 }
             }
         }
-    } else if (warp < 8) {
+    } else if (warp < 16) {
         // ================= role C: vertical sums of H_a, H_b, q, winner-take-all =================
+        // warp = (lane quarter, disparity half h); the warps of half h finish rows 2h, 2h+1 of every iteration: they receive
+        // the other half's 4-disparity winners of those rows through shared memory and read-modify-write the (best,label) plane
         reg_inc<M_REGS_C>();
-        const int w4 = warp - 4;
-        const int l = w4 * 32 + lane;
-        const uint32_t tl = tmem + ((uint32_t)(w4 * 32) << 16);
+        const int q4 = warp & 3, h = (warp - 8) >> 2;
+        const int l = q4 * 32 + lane;
+        const uint32_t tl = tmem + ((uint32_t)(q4 * 32) << 16);
         const int x = xo0 + l;
         const bool valid = l < M_VW && x < A.w;
         const float rx = valid ? __frcp_rn((float)(min(A.w - 1, x + RAD) - max(0, x - RAD) + 1)) : 0.0f;
         const size_t planeS = (size_t)A.rows_out * A.pitchS;
-        float2* const bl0 = A.BL + (size_t)(chunk * 2 + view) * planeS + (size_t)(yb0 - A.y_out0) * A.pitchS + x;
+        // this thread finishes rows yb0 + MR e + 2h + {0, 1}
+        float2* const bl0 = A.BL + (size_t)(chunk * 2 + view) * planeS + (size_t)(yb0 - A.y_out0 + 2 * h) * A.pitchS + x;
+        const size_t bl_step = (size_t)MR * A.pitchS;
         const int band_rows = yb1 - yb0;
-        const uint32_t ga_I = smem_addr(&sm.ga[0][0]) + (uint32_t)(l + 2 * RAD) * 8;  // I of this thread's column in a guide row
+        const uint32_t td2 = tl + TC_D2 + 8 * h, tring = tl + TC_RING + 8 * h;
+        const uint32_t gcs = smem_addr(&sm.gc[0][0]) + (uint32_t)l * 2;
+        const uint32_t xs_send = smem_addr(&sm.xb[0][2 * (1 - h)][0]) + (uint32_t)l * 8, xs_recv = smem_addr(&sm.xb[0][2 * h][0]) + (uint32_t)l * 8;
+        const uint32_t mb_d2f = bar(&sm.d2_full), mb_d2e = bar(&sm.d2_empty), mb_gcf = bar(&sm.gc_full[0]), mb_gce = bar(&sm.gc_empty[0]);
+        const uint32_t mb_xf_send = bar(&sm.x_full[0][1 - h]), mb_xe_send = bar(&sm.x_empty[0][1 - h]);
+        const uint32_t mb_xf_recv = bar(&sm.x_full[0][h]), mb_xe_recv = bar(&sm.x_empty[0][h]);
+        int K = 0, E = 0;
         for (int g = 0; g < ngroups; g++) {
-            float Sa[M_ND], Sb[M_ND];
+            float Sa[4], Sb[4];
 #pragma unroll
-            for (int d = 0; d < M_ND; d++) Sa[d] = Sb[d] = 0.0f;
+            for (int d = 0; d < 4; d++) Sa[d] = Sb[d] = 0.0f;
             {
-                uint32_t z[16];
-#pragma unroll
-                for (int i = 0; i < 16; i++) z[i] = 0u;
-                for (int s = 0; s < WIN; s++) tm_st16u(tl + TC_RING + 16 * s, z);
+                const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                for (int s = 0; s < WIN; s++) tm_st8(tring + 16 * s, z);
                 tm_wait_st();
             }
-            const int dbase = dlo + g * M_ND;
-            const int dact = min(M_ND, dcnt - g * M_ND);  // disparities of this group that exist
+            const float dbase = (float)(dlo + g * M_ND + 4 * h);
+            const int dact = min(M_ND, dcnt - g * M_ND) - 4 * h;  // disparities of this thread's half that exist
             const bool ld_ok = (g > 0) && valid;
-            auto prefetch = [&](int e, float2 (&pb)[ROWS]) {
+            const float2 binit = make_float2(BEST_INIT_BITS_F, 0.0f);
+            // (best,label) of the rows this thread finishes, fetched two emissions ahead
+            float2 pbA[2], pbB[2];
 #pragma unroll
-                for (int r = 0; r < ROWS; r++) {
-                    pb[r] = make_float2(BEST_INIT_BITS_F, 0.0f);
-                    if (ld_ok && e >= 0 && e * ROWS + r < band_rows) pb[r] = ld_early_f2(bl0 + (size_t)(e * ROWS + r) * A.pitchS);
-                }
-            };
-            float2 pbA[ROWS], pbB[ROWS];
-            prefetch(0, pbA);
-            prefetch(1, pbB);
+            for (int j = 0; j < 2; j++) {
+                pbA[j] = pbB[j] = binit;
+                if (ld_ok && 2 * h + j < band_rows) pbA[j] = ld_early_f2(bl0 + (size_t)j * A.pitchS);
+                if (ld_ok && MR + 2 * h + j < band_rows) pbB[j] = ld_early_f2(bl0 + bl_step + (size_t)j * A.pitchS);
+            }
+            float2* blp = bl0;
             int slot = 0;
 #pragma unroll 1
-            for (int it = 0; it < niter; it++) {
-                const int K = g * niter + it;
+            for (int it = 0; it < niter; it++, K++) {
                 const int e = it - WARM_IT;
-                float2 pb[ROWS];
-                if (e >= 0) {
+                const int kc = K & (M_NGC - 1);
+                int slots[MR];
 #pragma unroll
-                    for (int r = 0; r < ROWS; r++) {
-                        pb[r] = pbA[r];
-                        pbA[r] = pbB[r];
-                    }
-                    prefetch(e + 2, pbB);
-                }
-                int slots[ROWS];
-#pragma unroll
-                for (int r = 0; r < ROWS; r++) {
+                for (int r = 0; r < MR; r++) {
                     slots[r] = slot;
                     slot = (slot + 1 == WIN) ? 0 : slot + 1;
                 }
-                mbar_wait(bar(&sm.d2_full[K & 1]), (unsigned)(K >> 1) & 1u);
+                mbar_wait(mb_d2f, (unsigned)K & 1u);
                 tm_fence_after();
-                uint32_t h[32], o[ROWS][16];
-                tm_ld32(tl + TC_D2 + 32 * (K & 1), h);
+                mbar_wait(mb_gcf + 8 * kc, (unsigned)(K / M_NGC) & 1u);
+                float wm[MR], wa[MR];  // winner of this thread's 4 disparities in each row: cost, label
 #pragma unroll
-                for (int r = 0; r < ROWS; r++) tm_ld16u(tl + TC_RING + 16 * slots[r], o[r]);
-                tm_wait_ld();
-                tm_fence_before();
-                __syncwarp();
-                mbar_arrive_lane0(bar(&sm.d2_empty[K & 1]), lane);
+                for (int half = 0; half < 2; half++) {
+                    uint32_t hh[2][8], o[2][8];
 #pragma unroll
-                for (int r = 0; r < ROWS; r++) tm_st16u(tl + TC_RING + 16 * slots[r], &h[16 * r]);
-                // I of the output rows: guide rows of iteration K - 9
-                uint32_t iw[ROWS];
-                if (e >= 0) {
-                    const uint32_t ga = ga_I + (uint32_t)((K - 9) & (M_NGA - 1)) * (ROWS * GA_ROW);
-#pragma unroll
-                    for (int r = 0; r < ROWS; r++) iw[r] = lds32(ga + r * GA_ROW);
-                }
-#pragma unroll
-                for (int r = 0; r < ROWS; r++) {
-#pragma unroll
-                    for (int d = 0; d < M_ND; d++) {
-                        Sa[d] += __uint_as_float(h[16 * r + 2 * d]) - __uint_as_float(o[r][2 * d]);
-                        Sb[d] += __uint_as_float(h[16 * r + 2 * d + 1]) - __uint_as_float(o[r][2 * d + 1]);
+                    for (int j = 0; j < 2; j++) {
+                        tm_ld8(td2 + 16 * (2 * half + j), hh[j]);
+                        tm_ld8(tring + 16 * slots[2 * half + j], o[j]);
                     }
-                    if (e >= 0) {
-                        const int yq = yb0 + e * ROWS + r;
-                        const float rxy = rx * inv_rows(sm.ry_lut[1], yq, A.y_global0, A.frame_h);
-                        const float I = __low2float(u2h2(iw[r]));
-                        float q[M_ND];
+                    tm_wait_ld();
+                    if (half == 1) {  // all of D2 is in registers: MMA 2 of the next iteration may overwrite it
+                        tm_fence_before();
+                        __syncwarp();
+                        mbar_arrive_lane0(mb_d2e, lane);
+                    }
 #pragma unroll
-                        for (int d = 0; d < M_ND; d++) {
-                            q[d] = fmaf(Sa[d], I, Sb[d]) * rxy;
-                            if (d >= dact) q[d] = __int_as_float(0x7f800000);
-                        }
-                        // ascending d, `best >= q`: minimum, the later index on a tie (guidedFilter.cu:406), as a tournament
-                        float m1[4], a1[4];
+                    for (int j = 0; j < 2; j++) {
+                        const int r = 2 * half + j;
+                        tm_st8(tring + 16 * slots[r], hh[j]);
 #pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            const bool t = q[2 * i] >= q[2 * i + 1];
-                            m1[i] = t ? q[2 * i + 1] : q[2 * i];
-                            a1[i] = t ? (float)(2 * i + 1) : (float)(2 * i);
+                        for (int d = 0; d < 4; d++) {
+                            Sa[d] += __uint_as_float(hh[j][2 * d]) - __uint_as_float(o[j][2 * d]);
+                            Sb[d] += __uint_as_float(hh[j][2 * d + 1]) - __uint_as_float(o[j][2 * d + 1]);
                         }
-                        const bool t01 = m1[0] >= m1[1], t23 = m1[2] >= m1[3];
-                        const float m01 = t01 ? m1[1] : m1[0], a01 = t01 ? a1[1] : a1[0];
-                        const float m23 = t23 ? m1[3] : m1[2], a23 = t23 ? a1[3] : a1[2];
-                        const bool tt = m01 >= m23;
-                        const float m = tt ? m23 : m01, am = tt ? a23 : a01;
-                        float2 nb = pb[r];
+                        if (e >= 0) {
+                            const int yq = yb0 + e * MR + r;
+                            const float rxy = rx * inv_rows(sm.ry_lut[1], yq, A.y_global0, A.frame_h);
+                            const float I = __half2float(__ushort_as_half((unsigned short)lds16(gcs + kc * (MR * GC_ROW) + r * GC_ROW)));
+                            float q[4];
+#pragma unroll
+                            for (int d = 0; d < 4; d++) q[d] = fmaf(Sa[d], I, Sb[d]) * rxy;
+                            if (dact < 4) {  // last, partial group
+#pragma unroll
+                                for (int d = 0; d < 4; d++)
+                                    if (d >= dact) q[d] = __int_as_float(0x7f800000);
+                            }
+                            // ascending d, `best >= q`: minimum, the later index on a tie (guidedFilter.cu:406), as a tournament
+                            const bool t01 = q[0] >= q[1], t23 = q[2] >= q[3];
+                            const float m01 = t01 ? q[1] : q[0], a01 = t01 ? 1.0f : 0.0f;
+                            const float m23 = t23 ? q[3] : q[2], a23 = t23 ? 3.0f : 2.0f;
+                            const bool tt = m01 >= m23;
+                            wm[r] = tt ? m23 : m01;
+                            wa[r] = (tt ? a23 : a01) + dbase;
+                        }
+                    }
+                }
+                if (e >= 0) {
+                    // hand the winners of the other half's rows over, take its winners of this half's rows
+                    const uint32_t xo = (uint32_t)(E & 1) * (MR * M_TW * 8);
+                    if (E >= 2) mbar_wait(mb_xe_send + 16 * (E & 1), (unsigned)((E >> 1) - 1) & 1u);
+#pragma unroll
+                    for (int j = 0; j < 2; j++)
+                        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(xs_send + xo + j * (M_TW * 8)), "f"(h ? wm[j] : wm[2 + j]),
+                                     "f"(h ? wa[j] : wa[2 + j])
+                                     : "memory");
+                    __syncwarp();
+                    mbar_arrive_lane0(mb_xf_send + 16 * (E & 1), lane);
+                    mbar_wait(mb_xf_recv + 16 * (E & 1), (unsigned)(E >> 1) & 1u);
+                    float om[2], oa[2];
+#pragma unroll
+                    for (int j = 0; j < 2; j++)
+                        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(om[j]), "=f"(oa[j]) : "r"(xs_recv + xo + j * (M_TW * 8)) : "memory");
+                    __syncwarp();
+                    mbar_arrive_lane0(mb_xe_recv + 16 * (E & 1), lane);
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        // fold in ascending d: half 0 first
+                        const float mine_m = h ? wm[2 + j] : wm[j], mine_a = h ? wa[2 + j] : wa[j];
+                        const float m0 = h ? om[j] : mine_m, a0 = h ? oa[j] : mine_a;
+                        const float m1 = h ? mine_m : om[j], a1 = h ? mine_a : oa[j];
+                        const bool t = m0 >= m1;
+                        const float m = t ? m1 : m0, am = t ? a1 : a0;
+                        float2 nb = pbA[j];
                         if (nb.x >= m) {
                             nb.x = m;
-                            nb.y = am + (float)dbase;
+                            nb.y = am;
                         }
-                        if (valid && e * ROWS + r < band_rows) bl0[(size_t)(e * ROWS + r) * A.pitchS] = nb;
+                        const int rowb = e * MR + 2 * h + j;  // row of the band
+                        if (valid && rowb < band_rows) blp[(size_t)j * A.pitchS] = nb;
+                        pbA[j] = pbB[j];
+                        pbB[j] = binit;
+                        if (ld_ok && rowb + 2 * MR < band_rows) pbB[j] = ld_early_f2(blp + 2 * bl_step + (size_t)j * A.pitchS);
                     }
+                    blp += bl_step;
+                    E++;
                 }
                 tm_wait_st();
                 if ((it & (M_RESUM - 1)) == M_RESUM - 1) {
                     // re-sum the ring: bounds the rounding drift of the running sums to M_RESUM iterations
 #pragma unroll
-                    for (int d = 0; d < M_ND; d++) Sa[d] = Sb[d] = 0.0f;
+                    for (int d = 0; d < 4; d++) Sa[d] = Sb[d] = 0.0f;
                     for (int s = 0; s < WIN; s++) {
-                        uint32_t v[16];
-                        tm_ld16u(tl + TC_RING + 16 * s, v);
+                        uint32_t v[8];
+                        tm_ld8(tring + 16 * s, v);
                         tm_wait_ld();
 #pragma unroll
-                        for (int d = 0; d < M_ND; d++) {
+                        for (int d = 0; d < 4; d++) {
                             Sa[d] += __uint_as_float(v[2 * d]);
                             Sb[d] += __uint_as_float(v[2 * d + 1]);
                         }
                     }
                 }
-                if (K >= 9) {
-                    __syncwarp();
-                    mbar_arrive_lane0(bar(&sm.ga_empty[(K - 9) & (M_NGA - 1)]), lane);
-                }
+                __syncwarp();
+                mbar_arrive_lane0(mb_gce + 8 * kc, lane);
             }
         }
     } else {
-    reg_dec<M_REGS_A>();  // warpgroups 2..4 (role A, MMA issue, TMA producer) give their registers to roles B and C
-    if (warp < 8 + M_NWA) {
+    reg_dec<M_REGS_A>();  // warpgroups 4, 5 (role A, MMA issue, TMA producer) give registers to roles B and C
+    if (warp < 16 + M_NWA) {
         // ================= role A: lattice cost, exact fp16 pieces, vertical differences =================
-        const int wa = warp - 8;
-        const int r = wa / 5;                   // image row of the iteration this warp works on
-        const int k = (wa % 5) * 32 + lane;     // cost column
+        // one thread per cost column: 8 disparities x MR rows per iteration
+        const int k = (warp - 16) * 32 + lane;
         const int x = xc0 + k;
         const bool used = k < M_KC && x >= 0 && x < A.w;
         const __half2 wI = used ? u2h2(A.wI2) : __float2half2_rn(0.0f);
         const __half2 wG = used ? u2h2(A.wG2) : __float2half2_rn(0.0f);
         const __half2 tc = u2h2(A.tc2), tg = u2h2(A.tg2);
-        const uint32_t b1_lane = (uint32_t)((k >> 3) * 128 + (k & 7) * 16);
+        const uint32_t b1a = smem_addr(&sm.b1[0]) + (uint32_t)((k >> 3) * 128 + (k & 7) * 16);
         const uint32_t pr0 = smem_addr(&sm.pring[0][0]) + (uint32_t)k * 16;
-        const uint32_t ga0 = smem_addr(&sm.ga[0][0]) + (uint32_t)k * 8;
+        const uint32_t pi0 = smem_addr(&sm.pring[0][0]) + PR_IL + (uint32_t)k * 4;
+        const uint32_t ops = smem_addr(&sm.op[0][0]);
+        const uint32_t mb_opf = bar(&sm.op_full[0]), mb_ope = bar(&sm.op_empty[0]), mb_b1f = bar(&sm.b1_full), mb_b1e = bar(&sm.b1_empty);
+        int K = 0;
         for (int g = 0; g < ngroups; g++) {
-            // ring of P: zero at group start (the two threads of a column -- one per row of an iteration -- share it, so
-            // both must have left the previous group before it is cleared, and see it cleared before they go on)
-            named_bar_sync(2, M_NWA * 32);
-            for (int s = r; s < WIN; s += 2) sts128(pr0 + (uint32_t)s * PR_SLOT, 0u, 0u, 0u, 0u);
-            named_bar_sync(2, M_NWA * 32);
+            // ring of P (and of the rows' guide pieces): zero at group start; a thread owns its column of the ring
+            for (int s = 0; s < WIN; s++) {
+                sts128(pr0 + (uint32_t)s * PR_SLOT, 0u, 0u, 0u, 0u);
+                sts32(pi0 + (uint32_t)s * PR_SLOT, 0u);
+            }
             // match operands of this thread: padded column X0 = x + d0 + padm, 8 consecutive pixels from copy X0 & 3
             const int d0 = dlo + g * M_ND;
             const int X0 = x + d0 + A.padm;
             const int i0 = (xc0 + d0 + A.padm) >> 2;  // first chunk of the slot (warp-uniform)
-            const uint32_t mt_off = OP_MT + (uint32_t)r * MT_ROW + (uint32_t)((X0 >> 2) - i0) * 64 + (uint32_t)(X0 & 3) * 16;
-            int slot = r;  // ring slot of row (2*it + r) mod 19
+            const uint32_t mt_off = OP_MT + (uint32_t)((X0 >> 2) - i0) * 64 + (uint32_t)(X0 & 3) * 16;
+            int slot = 0;  // ring slot of the iteration's first row: row (MR*it + r) mod 19
 #pragma unroll 1
-            for (int it = 0; it < niter; it++) {
-                const int K = g * niter + it;
-                mbar_wait(bar(&sm.ga_full[K & (M_NGA - 1)]), (unsigned)(K / M_NGA) & 1u);
-                mbar_wait(bar(&sm.op_full[K & (M_NOP - 1)]), (unsigned)(K / M_NOP) & 1u);
-                // guide (I, G | I&15, I&240) of the entering row; (I&15, I&240) of the row that leaves (19 rows up):
-                // row r = 0: second row of iteration K-10, r = 1: first row of iteration K-9
-                const uint2 gn = lds64(ga0 + (uint32_t)(K & (M_NGA - 1)) * (ROWS * GA_ROW) + (uint32_t)r * GA_ROW);
-                const uint32_t go = lds32(ga0 + (uint32_t)((K - 10 + r) & (M_NGA - 1)) * (ROWS * GA_ROW) +
-                                          (uint32_t)(1 - r) * GA_ROW + 4);
-                const uint32_t opa = smem_addr(&sm.op[K & (M_NOP - 1)][0]) + mt_off;
-                const uint4 m0 = lds128(opa), m1 = lds128(opa + 64);
-                const uint4 po = lds128(pr0 + (uint32_t)slot * PR_SLOT);
-                const __half2 gI = __low2half2(u2h2(gn.x)), gG = __high2half2(u2h2(gn.x));
-                const __half2 gl = __low2half2(u2h2(gn.y)), gh = __high2half2(u2h2(gn.y));
-                const __half2 ol = __hneg2(__low2half2(u2h2(go))), oh = __hneg2(__high2half2(u2h2(go)));
-                const unsigned mi[4] = {m0.x, m0.y, m1.x, m1.y}, mg[4] = {m0.z, m0.w, m1.z, m1.w};
-                const unsigned pold[4] = {po.x, po.y, po.z, po.w};
-                unsigned pn[4], dp[4], dl[4], dh[4];
+            for (int it = 0; it < niter; it++, K++) {
+                const int ko = K & (M_NOP - 1);
+                mbar_wait(mb_opf + 8 * ko, (unsigned)(K / M_NOP) & 1u);
+                const uint32_t opa = ops + ko * OP_BYTES;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const __half2 cI = __hmin2(__habs2(__hsub2(u2h2(mi[j]), gI)), tc);
-                    const __half2 cG = __hmin2(__habs2(__hsub2(u2h2(mg[j]), gG)), tg);
-                    const __half2 P = __hfma2(cG, wG, __hmul2(cI, wI));
-                    const __half2 Po = u2h2(pold[j]);
-                    pn[j] = h22u(P);
-                    dp[j] = h22u(__hsub2(P, Po));
-                    dl[j] = h22u(__hfma2(Po, ol, __hmul2(P, gl)));
-                    dh[j] = h22u(__hfma2(Po, oh, __hmul2(P, gh)));
+                for (int r = 0; r < MR; r++) {
+                    const uint32_t so = (uint32_t)slot * PR_SLOT;
+                    // guide (I, G | I&15, I&240) of the entering row; (I&15, I&240) of the row that leaves (19 rows up) and its
+                    // costs come from this thread's ring slot, which the entering row then takes
+                    const uint2 gn = lds64(opa + OP_GA + r * GA_ROW + (uint32_t)k * 8);
+                    const uint4 m0 = lds128(opa + mt_off + r * MT_ROW), m1 = lds128(opa + mt_off + r * MT_ROW + 64);
+                    const uint4 po = lds128(pr0 + so);
+                    const uint32_t go = lds32(pi0 + so);
+                    const __half2 gI = __low2half2(u2h2(gn.x)), gG = __high2half2(u2h2(gn.x));
+                    const __half2 gl = __low2half2(u2h2(gn.y)), gh = __high2half2(u2h2(gn.y));
+                    const __half2 ol = __hneg2(__low2half2(u2h2(go))), oh = __hneg2(__high2half2(u2h2(go)));
+                    const unsigned mi[4] = {m0.x, m0.y, m1.x, m1.y}, mg[4] = {m0.z, m0.w, m1.z, m1.w};
+                    const unsigned pold[4] = {po.x, po.y, po.z, po.w};
+                    unsigned pn[4], dp[4], dl[4], dh[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const __half2 cI = __hmin2(__habs2(__hsub2(u2h2(mi[j]), gI)), tc);
+                        const __half2 cG = __hmin2(__habs2(__hsub2(u2h2(mg[j]), gG)), tg);
+                        const __half2 P = __hfma2(cG, wG, __hmul2(cI, wI));
+                        const __half2 Po = u2h2(pold[j]);
+                        pn[j] = h22u(P);
+                        dp[j] = h22u(__hsub2(P, Po));
+                        dl[j] = h22u(__hfma2(Po, ol, __hmul2(P, gl)));
+                        dh[j] = h22u(__hfma2(Po, oh, __hmul2(P, gh)));
+                    }
+                    sts128(pr0 + so, pn[0], pn[1], pn[2], pn[3]);
+                    sts32(pi0 + so, gn.y);
+                    slot = (slot + 1 == WIN) ? 0 : slot + 1;
+                    if (r == 0 && K >= 1) mbar_wait(mb_b1e, (unsigned)(K - 1) & 1u);  // MMA 1 of the previous iteration has read B1
+                    sts128(b1a + (uint32_t)r * B1_GROUP, dp[0], dp[1], dp[2], dp[3]);
+                    sts128(b1a + (uint32_t)(MR + r) * B1_GROUP, dl[0], dl[1], dl[2], dl[3]);
+                    sts128(b1a + (uint32_t)(2 * MR + r) * B1_GROUP, dh[0], dh[1], dh[2], dh[3]);
                 }
-                sts128(pr0 + (uint32_t)slot * PR_SLOT, pn[0], pn[1], pn[2], pn[3]);
-                slot += 2;
-                if (slot >= WIN) slot -= WIN;
-                if (K >= 2) mbar_wait(bar(&sm.b1_empty[K & 1]), (unsigned)((K >> 1) - 1) & 1u);
-                const uint32_t b1a = smem_addr(&sm.b1[K & 1][0]) + b1_lane + (uint32_t)r * B1_GROUP;
-                sts128(b1a, dp[0], dp[1], dp[2], dp[3]);
-                sts128(b1a + 2 * B1_GROUP, dl[0], dl[1], dl[2], dl[3]);
-                sts128(b1a + 4 * B1_GROUP, dh[0], dh[1], dh[2], dh[3]);
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    mbar_arrive(bar(&sm.b1_full[K & 1]));
-                    mbar_arrive(bar(&sm.op_empty[K & (M_NOP - 1)]));
-                    if (K >= 10) mbar_arrive(bar(&sm.ga_empty[(K - 10) & (M_NGA - 1)]));
+                    mbar_arrive(mb_b1f);
+                    mbar_arrive(mb_ope + 8 * ko);
                 }
             }
         }
-    } else if (warp == 8 + M_NWA) {
+    } else if (warp == 16 + M_NWA) {
         // ================= MMA issue: warp-uniform descriptors, one elected lane =================
         named_bar_sync(1, 128 + 32);  // the band matrix is in Tensor Memory
         tm_fence_after();
-        constexpr uint32_t ID32 = instr_desc(32, 0), ID16 = instr_desc(16, 0), ID32N = instr_desc(32, 1);
-        const uint64_t db1 = smem_desc(smem_addr(&sm.b1[0][0]), 128, B1_GROUP);
-        const uint64_t db2 = smem_desc(smem_addr(&sm.b2[0][0]), 128, B2_GROUP);
-        const uint32_t ta = tmem + TC_BAND;
+        constexpr uint32_t ID64 = instr_desc(8 * 2 * MR, 0), ID32 = instr_desc(8 * MR, 0), ID64N = instr_desc(8 * 2 * MR, 1);
+        const uint64_t db1 = smem_desc(smem_addr(&sm.b1[0]), 128, B1_GROUP);
+        const uint64_t db1h = db1 + (uint64_t)((2 * MR * B1_GROUP) >> 4);
+        const uint64_t db2 = smem_desc(smem_addr(&sm.b2[0]), 128, B2_GROUP);
+        const uint64_t db2l = db2 + (uint64_t)((2 * MR * B2_GROUP) >> 4);
+        const uint32_t ta = tmem + TC_BAND, td1 = tmem + TC_D1, td2 = tmem + TC_D2;
+        const uint32_t mb_b1f = bar(&sm.b1_full), mb_b1e = bar(&sm.b1_empty), mb_d1f = bar(&sm.d1_full), mb_d1e = bar(&sm.d1_empty);
+        const uint32_t mb_b2f = bar(&sm.b2_full), mb_b2e = bar(&sm.b2_empty), mb_d2f = bar(&sm.d2_full), mb_d2e = bar(&sm.d2_empty);
         auto stage2 = [&](int K) {
-            mbar_wait(bar(&sm.b2_full[K & 1]), (unsigned)(K >> 1) & 1u);
-            if (K >= 2) mbar_wait(bar(&sm.d2_empty[K & 1]), (unsigned)((K >> 1) - 1) & 1u);
+            mbar_wait(mb_b2f, (unsigned)K & 1u);
+            if (K >= 1) mbar_wait(mb_d2e, (unsigned)(K - 1) & 1u);
             tm_fence_after();
             if (elect_one()) {
-                const uint64_t dh = db2 + (uint64_t)((K & 1) * (B2_BYTES >> 4));
-                const uint64_t dl = dh + (uint64_t)((4 * B2_GROUP) >> 4);
-                const uint32_t td = tmem + TC_D2 + 32 * (K & 1);
 #pragma unroll
-                for (int j = 0; j < M_K2 / 16; j++) umma_ts(td, ta + 8 * j, dh + (uint64_t)(j * 16), ID32, j > 0);
+                for (int j = 0; j < M_K2 / 16; j++) umma_ts(td2, ta + 8 * j, db2 + (uint64_t)(j * 16), ID64, j > 0);
 #pragma unroll
-                for (int j = 0; j < M_K2 / 16; j++) umma_ts(td, ta + 8 * j, dl + (uint64_t)(j * 16), ID32N, 1);
-                umma_commit(bar(&sm.d2_full[K & 1]));
-                umma_commit(bar(&sm.b2_empty[K & 1]));
+                for (int j = 0; j < M_K2 / 16; j++) umma_ts(td2, ta + 8 * j, db2l + (uint64_t)(j * 16), ID64N, 1);
+                umma_commit(mb_d2f);
+                umma_commit(mb_b2e);
             }
             __syncwarp();
         };
 #pragma unroll 1
         for (int K = 0; K < Ktotal; K++) {
-            mbar_wait(bar(&sm.b1_full[K & 1]), (unsigned)(K >> 1) & 1u);
-            if (K >= 2) mbar_wait(bar(&sm.d1_empty[K & 1]), (unsigned)((K >> 1) - 1) & 1u);
+            mbar_wait(mb_b1f, (unsigned)K & 1u);
+            if (K >= 1) mbar_wait(mb_d1e, (unsigned)(K - 1) & 1u);
             tm_fence_after();
             if (elect_one()) {
-                const uint64_t dp = db1 + (uint64_t)((K & 1) * (B1_BYTES >> 4));
-                const uint64_t dhi = dp + (uint64_t)((4 * B1_GROUP) >> 4);
-                const uint32_t td = tmem + TC_D1 + 32 * (K & 1);
 #pragma unroll
-                for (int j = 0; j < M_KB / 16; j++) umma_ts(td, ta + 8 * j, dp + (uint64_t)(j * 16), ID32, j > 0);
+                for (int j = 0; j < M_KB / 16; j++) umma_ts(td1, ta + 8 * j, db1 + (uint64_t)(j * 16), ID64, j > 0);
 #pragma unroll
-                for (int j = 0; j < M_KB / 16; j++) umma_ts(td + 16, ta + 8 * j, dhi + (uint64_t)(j * 16), ID16, 1);
-                umma_commit(bar(&sm.d1_full[K & 1]));
-                umma_commit(bar(&sm.b1_empty[K & 1]));
+                for (int j = 0; j < M_KB / 16; j++) umma_ts(td1 + 8 * MR, ta + 8 * j, db1h + (uint64_t)(j * 16), ID32, 1);
+                umma_commit(mb_d1f);
+                umma_commit(mb_b1e);
             }
             __syncwarp();
             if (K >= 1) stage2(K - 1);
         }
         if (Ktotal > 0) stage2(Ktotal - 1);
-    } else {
-        // ================= TMA producer =================
-        if (lane == 0) {
-            const uint2* GAp = A.GA[view] + (size_t)strip * A.rows_pad * M_KB;
-            const float2* GBp = A.GB[view] + (size_t)strip * A.rows_pad * M_TW;
-            const uint4* MTp = A.MT[1 - view];
-            int K = 0;
-            for (int g = 0; g < ngroups; g++) {
-                const int d0 = dlo + g * M_ND;
-                const int i0 = (xc0 + d0 + A.padm) >> 2;
-                for (int it = 0; it < niter; it++, K++) {
-                    const long long row = (long long)PADY + y_first + it * ROWS;  // padded row of the entering rows
-                    {
-                        const int sl = K & (M_NGA - 1);
-                        if (K >= M_NGA) mbar_wait(bar(&sm.ga_empty[sl]), (unsigned)(K / M_NGA - 1) & 1u);
-                        const uint32_t full = bar(&sm.ga_full[sl]);
-                        mbar_expect_tx(full, ROWS * GA_ROW);
-                        bulk_g2s(smem_addr(&sm.ga[sl][0]), GAp + row * M_KB, ROWS * GA_ROW, full);
-                    }
-                    {
-                        const int sl = K & (M_NOP - 1);
-                        if (K >= M_NOP) mbar_wait(bar(&sm.op_empty[sl]), (unsigned)(K / M_NOP - 1) & 1u);
-                        const uint32_t full = bar(&sm.op_full[sl]);
-                        const uint32_t dst = smem_addr(&sm.op[sl][0]);
-                        mbar_expect_tx(full, OP_BYTES);
-                        bulk_g2s(dst + OP_GB, GBp + (row - RAD) * M_TW, ROWS * GB_ROW, full);
+    } else if (warp == 17 + M_NWA) {
+        // ================= TMA producer (warp-uniform addresses, one elected lane issues) =================
+        const char* GAp = reinterpret_cast<const char*>(A.GA[view] + (size_t)strip * A.rows_pad * M_KB);
+        const char* GBp = reinterpret_cast<const char*>(A.GB[view] + (size_t)strip * A.rows_pad * M_TW);
+        const char* GCp = reinterpret_cast<const char*>(A.GC[view] + (size_t)strip * A.rows_pad * M_TW);
+        const char* MTp = reinterpret_cast<const char*>(A.MT[1 - view]);
+        const size_t mt_pitch = (size_t)A.n_chunk * 64;
+        const long long row0 = (long long)PADY + y_first;  // padded row of the first entering row of a group
+        const uint32_t op_s = smem_addr(&sm.op[0][0]), gc_s = smem_addr(&sm.gc[0][0]);
+        const uint32_t op_f = bar(&sm.op_full[0]), op_e = bar(&sm.op_empty[0]), gc_f = bar(&sm.gc_full[0]), gc_e = bar(&sm.gc_empty[0]);
+        int K = 0;
+        for (int g = 0; g < ngroups; g++) {
+            const int d0 = dlo + g * M_ND;
+            const int i0 = (xc0 + d0 + A.padm) >> 2;
+            const char* ga_src = GAp + row0 * GA_ROW;
+            const char* gb_src = GBp + (row0 - RAD) * GB_ROW;
+            const char* gc_src = GCp + (row0 - 2 * RAD) * GC_ROW;
+            const char* mt_src = MTp + row0 * mt_pitch + (size_t)i0 * 64;
+#pragma unroll 1
+            for (int it = 0; it < niter; it++, K++) {
+                const int so = K & (M_NOP - 1), sc = K & (M_NGC - 1);
+                if (K >= M_NOP) mbar_wait(op_e + 8 * so, (unsigned)(K / M_NOP - 1) & 1u);
+                if (elect_one()) {
+                    const uint32_t dst = op_s + so * OP_BYTES;
+                    mbar_expect_tx(op_f + 8 * so, OP_BYTES);
+                    bulk_g2s(dst + OP_GA, ga_src, MR * GA_ROW, op_f + 8 * so);
+                    bulk_g2s(dst + OP_GB, gb_src, MR * GB_ROW, op_f + 8 * so);
 #pragma unroll
-                        for (int r = 0; r < ROWS; r++)
-                            bulk_g2s(dst + OP_MT + r * MT_ROW, MTp + ((row + r) * A.n_chunk + i0) * 4, MT_ROW, full);
-                    }
+                    for (int r = 0; r < MR; r++) bulk_g2s(dst + OP_MT + r * MT_ROW, mt_src + r * mt_pitch, MT_ROW, op_f + 8 * so);
                 }
+                __syncwarp();
+                if (K >= M_NGC) mbar_wait(gc_e + 8 * sc, (unsigned)(K / M_NGC - 1) & 1u);
+                if (elect_one()) {
+                    mbar_expect_tx(gc_f + 8 * sc, MR * GC_ROW);
+                    bulk_g2s(gc_s + sc * (MR * GC_ROW), gc_src, MR * GC_ROW, gc_f + 8 * sc);
+                }
+                __syncwarp();
+                ga_src += MR * GA_ROW;
+                gb_src += MR * GB_ROW;
+                gc_src += MR * GC_ROW;
+                mt_src += MR * mt_pitch;
             }
         }
     }
@@ -638,6 +691,7 @@ struct PrepM {
     int n_strips, rows_pad;
     uint2* GA;
     float2* GB;
+    __half* GC;
     uint4* MT;
     int n_chunk, padm;
     uint8_t* mean_u8;
@@ -677,6 +731,9 @@ __global__ void __launch_bounds__(160) k_prep_ga(const PrepM P) {
     v.x = h22u(__floats2half2_rn(I, G));
     v.y = h22u(__floats2half2_rn((float)(ii & 15), (float)(ii & 240)));
     P.GA[((size_t)strip * P.rows_pad + yrow) * M_KB + k] = v;
+    // the output lanes' intensities, centred (role C): lane l is cost column l + 18
+    if (k >= 2 * RAD && k < 2 * RAD + M_TW)
+        P.GC[((size_t)strip * P.rows_pad + yrow) * M_TW + (k - 2 * RAD)] = __float2half(in ? I - I_CENTER : 0.0f);
 }
 
 // MT: thread per (padded row, chunk, copy)
@@ -812,6 +869,7 @@ size_t sbf_mma_workspace_bytes(const sb200_ctx* ctx, int w, int h_held, int rows
     size_t bytes = 0;
     bytes += 2 * sb_align((size_t)plan.n_strips * rows_pad * M_KB * 8);
     bytes += 2 * sb_align((size_t)plan.n_strips * rows_pad * M_TW * 8);
+    bytes += 2 * sb_align((size_t)plan.n_strips * rows_pad * M_TW * 2);
     bytes += 2 * sb_align((size_t)rows_pad * mg.n_chunk * 64);
     bytes += sb_align((size_t)plan.n_chunks * 2 * rows_out * pitchS * 8);
     return bytes + 4096;
@@ -842,15 +900,17 @@ int sbf_run_fused_mma(sb200_ctx* ctx, const sb200_params* p, const uint8_t* cons
 
     uint2* GA[2];
     float2* GB[2];
+    __half* GC[2];
     uint4* MT[2];
     for (int i = 0; i < 2; i++) {
         GA[i] = sb_ws_alloc<uint2>(ctx, (size_t)plan.n_strips * rows_pad * M_KB);
         GB[i] = sb_ws_alloc<float2>(ctx, (size_t)plan.n_strips * rows_pad * M_TW);
+        GC[i] = sb_ws_alloc<__half>(ctx, (size_t)plan.n_strips * rows_pad * M_TW);
         MT[i] = sb_ws_alloc<uint4>(ctx, (size_t)rows_pad * mg.n_chunk * 4);
     }
     const size_t planeS = (size_t)g.rows_out * pitchS;
     float2* BL = sb_ws_alloc<float2>(ctx, planeS * 2 * plan.n_chunks);
-    if (!GA[0] || !GA[1] || !GB[0] || !GB[1] || !MT[0] || !MT[1] || !BL)
+    if (!GA[0] || !GA[1] || !GB[0] || !GB[1] || !GC[0] || !GC[1] || !MT[0] || !MT[1] || !BL)
         return sb_fail(ctx, SB200_ERR_NOMEM, "fused (mma): workspace arena too small (internal)");
 
     if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -865,6 +925,7 @@ int sbf_run_fused_mma(sb200_ctx* ctx, const sb200_params* p, const uint8_t* cons
         P.rows_pad = rows_pad;
         P.GA = GA[i];
         P.GB = GB[i];
+        P.GC = GC[i];
         P.MT = MT[i];
         P.n_chunk = mg.n_chunk;
         P.padm = mg.padm;
@@ -882,6 +943,7 @@ int sbf_run_fused_mma(sb200_ctx* ctx, const sb200_params* p, const uint8_t* cons
     for (int i = 0; i < 2; i++) {
         A.GA[i] = GA[i];
         A.GB[i] = GB[i];
+        A.GC[i] = GC[i];
         A.MT[i] = MT[i];
         A.dmin[i] = dmin[i];
     }

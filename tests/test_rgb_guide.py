@@ -117,6 +117,42 @@ def test_gpu_rgb_three_stage_kernel_full_size_1080p_d256(monkeypatch):
 
 
 @pytest.mark.gpu
+def test_gpu_rgb_full_size_1080p_d256_against_the_oracle(oracle):
+    """BASELINE configs[2] as specified (RGB guide, 1920x1080, D=256): BOTH views of the default RGB kernel against the
+    oracle's exact-mode colour guided filter -- labels identical wherever the oracle's margin is decisive and
+    >= 99.9 % overall, best cost within 1e-4 relative (floor 1e-2)."""
+    S = pytest.importorskip("stereo_matching_cuda_b200")
+    from stereo_matching_cuda_b200 import api
+
+    w, h, size_d = 1920, 1080, 256
+    L, R = synth.make_pair(w, h, size_d, channels=3, seed=3)
+    p = api.default_params(dmin=-(size_d - 1), dmax=0, guide_mode=S.GUIDE_RGB)
+    with S.Context(0) as ctx:
+        out = ctx.pipeline(L, R, p, want=("gray_left", "gray_right", "disp_left", "disp_right", "best_left", "best_right"))
+    gl, gr = oracle.rgb_to_gray(L), oracle.rgb_to_gray(R)
+    assert np.array_equal(out["gray_left"], gl) and np.array_equal(out["gray_right"], gr)
+    po = oracle.params(box_mode=O.BOX_EXACT, nthreads=oracle.max_threads())
+    record = {}
+    for view, (rgb, g_guide, g_other, dmin, kd, kb) in {"left": (L, gl, gr, -(size_d - 1), "disp_left", "best_left"),
+                                                        "right": (R, gr, gl, 0, "disp_right", "best_right")}.items():
+        best, dmap, second = oracle.view_disparity_rgb(rgb, g_guide, g_other, size_d, dmin, po, want_second=True)
+        same = out[kd] == dmap
+        err = np.abs(out[kb] - best)
+        rel = err / np.maximum(np.abs(best), 1e-2)
+        record[view] = {"label_agreement": float(same.mean()), "max_abs_err": float(err.max()),
+                        "max_rel_err_floor1e-2": float(rel.max()), "median_best": float(np.median(best))}
+        assert same.mean() >= 0.999, (view, same.mean())
+        assert np.all(same[(second - best) > 2e-4]), view
+        assert rel.max() < 1e-4, (view, rel.max(), err.max())
+    import json
+    import os
+    out_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, "fullsize_parity_rgb.json"), "w") as f:
+        json.dump(record, f)
+
+
+@pytest.mark.gpu
 def test_gpu_rgb_strip_mode_matches_whole_frame():
     """Row strips with 2*radius halo rows and the RGB guide: the strips' labels, concatenated, equal the whole frame's
     (first-stage sums are exact; window areas and statistics use frame rows, so only second-stage float order differs)."""

@@ -35,8 +35,10 @@ def main():
     orc = O.load_oracle()
     ctx = S.Context(0)
     want = ("disp_left", "disp_right", "best_left", "best_right", "filled")
-    shapes = [(384, 288, -15, 0), (500, 150, -33, 0),
+    shapes = [(384, 288, -15, 0), (500, 150, -33, 0), (230, 90, -20, 0), (300, 30, 2, 9), (19, 19, -2, 0), (97, 11, 0, 0),
               (640, 256, -63, 0)]
+    if len(sys.argv) > 1 and sys.argv[1] == "time":
+        shapes = shapes[:1]
     for (w, h, dmin, dmax) in shapes:
         size_d = dmax - dmin + 1
         L, R = synth.make_pair(w, h, max(size_d, 2), seed=w + h)
