@@ -43,7 +43,7 @@ constexpr int M_K2 = 128;       // K of MMA 2 (8 K-steps)
 constexpr int M_ND = 8;         // disparities per group
 constexpr int MR = 4;           // image rows per pipeline iteration (one hand-off between the roles per MR rows)
 constexpr int M_NWA = 5;        // role-A warps: one thread per cost column, all MR rows
-constexpr int M_THREADS = 768;  // 8 B + 8 C + 5 A + MMA + TMA warps (+ 1 idle: whole warpgroups)
+constexpr int M_THREADS = 512;  // 4 B + 4 C + 5 A + MMA + TMA warps (+ 1 idle: whole warpgroups)
 constexpr int M_NOP = 4;        // operand ring (guide rows, a/b statistics, match rows): iterations in flight
 constexpr int M_NGC = 8;        // ring of the output rows' intensities (role C runs behind the others)
 constexpr int M_MTC = 42;       // match chunks (4 pixels x 4 shifted copies, 64 B) per row in an operand slot
@@ -69,11 +69,9 @@ struct MSmem {
     unsigned char pring[WIN][PR_SLOT];
     unsigned char op[M_NOP][OP_BYTES];
     unsigned char gc[M_NGC][MR * GC_ROW];
-    float2 xb[2][MR][M_TW];    // [emission parity][row][lane] (cost, label): 4-disparity winners between the halves of role C
     float ry_lut[2][WIN + 1];  // [0][n] = scale/(S*n), [1][n] = 1/(scale*n); [.][0] = 0
     uint64_t op_full[M_NOP], op_empty[M_NOP], gc_full[M_NGC], gc_empty[M_NGC];
     uint64_t b1_full, b1_empty, d1_full, d1_empty, b2_full, b2_empty, d2_full, d2_empty;
-    uint64_t x_full[2][2], x_empty[2][2];  // [emission parity][receiving half]
     uint32_t tmem_base;
 };
 static_assert(sizeof(MSmem) <= 227 * 1024, "shared memory budget");
@@ -135,6 +133,15 @@ __device__ __forceinline__ void tm_st16u(uint32_t taddr, const uint32_t* r) {
         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
+__device__ __forceinline__ void tm_ld16u(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+        "[%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tm_ld8(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -176,12 +183,12 @@ __device__ __forceinline__ float2 ld_early_f2(const void* p) {  // coherent: wri
 __device__ __forceinline__ float fhadd_lo(unsigned h2, float c) { return fhadd(__low2half(u2h2(h2)), c); }
 __device__ __forceinline__ float fhadd_hi(unsigned h2, float c) { return fhadd(__high2half(u2h2(h2)), c); }
 
-// Register budgets of the warpgroups.  setmaxnreg only moves registers inside the pool the block got at launch: 768 threads
-// x 80 registers (what __launch_bounds__(768, 1) lets ptxas use) = 61440, NOT the whole 64 K file -- budgets that add up
+// Register budgets of the warpgroups.  setmaxnreg only moves registers inside the pool the block got at launch: the launch-time
+// register count x threads (here 128 x 512 = the whole 64 K file; with 640 threads it is 96 x 640 = 61440) -- budgets that add up
 // to more leave the last setmaxnreg.inc waiting forever.
-constexpr int M_REGS_LAUNCH = 80;
-constexpr int M_REGS_B = 88, M_REGS_C = 80, M_REGS_A = 72;
-static_assert(256 * M_REGS_B + 256 * M_REGS_C + 256 * M_REGS_A <= M_THREADS * M_REGS_LAUNCH, "register pool of the block");
+constexpr int M_REGS_LAUNCH = 128;
+constexpr int M_REGS_B = 160, M_REGS_C = 176, M_REGS_A = 88;
+static_assert(128 * M_REGS_B + 128 * M_REGS_C + 256 * M_REGS_A <= M_THREADS * M_REGS_LAUNCH, "register pool of the block");
 
 __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -218,25 +225,20 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
     if (threadIdx.x == 32) {
         for (int i = 0; i < M_NOP; i++) {
             mbar_init(bar(&sm.op_full[i]), 1);
-            mbar_init(bar(&sm.op_empty[i]), M_NWA + 8);  // role A (guide and match rows), role B (statistics)
+            mbar_init(bar(&sm.op_empty[i]), M_NWA + 4);  // role A (guide and match rows), role B (statistics)
         }
         for (int i = 0; i < M_NGC; i++) {
             mbar_init(bar(&sm.gc_full[i]), 1);
-            mbar_init(bar(&sm.gc_empty[i]), 8);
+            mbar_init(bar(&sm.gc_empty[i]), 4);
         }
         mbar_init(bar(&sm.b1_full), M_NWA);
         mbar_init(bar(&sm.b1_empty), 1);
         mbar_init(bar(&sm.d1_full), 1);
-        mbar_init(bar(&sm.d1_empty), 8);
-        mbar_init(bar(&sm.b2_full), 8);
+        mbar_init(bar(&sm.d1_empty), 4);
+        mbar_init(bar(&sm.b2_full), 4);
         mbar_init(bar(&sm.b2_empty), 1);
         mbar_init(bar(&sm.d2_full), 1);
-        mbar_init(bar(&sm.d2_empty), 8);
-        for (int i = 0; i < 2; i++)
-            for (int r = 0; r < 2; r++) {
-                mbar_init(bar(&sm.x_full[i][r]), 4);
-                mbar_init(bar(&sm.x_empty[i][r]), 4);
-            }
+        mbar_init(bar(&sm.d2_empty), 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x >= 64 && threadIdx.x < 64 + 2 * (WIN + 1)) {
@@ -256,14 +258,13 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
     tm_fence_after();
     const uint32_t tmem = sm.tmem_base;
 
-    if (warp < 8) {
+    if (warp < 4) {
         // ================= role B: 2-D box sums of P and I*P, a and b, fp16 hi/lo split =================
-        // warp = (lane quarter, disparity half h): 4 disparities x MR rows per thread and iteration
+        // one thread per a/b lane: 8 disparities x MR rows per iteration
         reg_inc<M_REGS_B>();
-        const int q4 = warp & 3, h = warp >> 2;
-        const int l = q4 * 32 + lane;
-        const uint32_t tl = tmem + ((uint32_t)(q4 * 32) << 16);
-        if (h == 0) {  // this lane's row of the band matrix: Band[l][k] = 1 for l <= k <= l + 18
+        const int l = warp * 32 + lane;
+        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+        {   // this lane's row of the band matrix: Band[l][k] = 1 for l <= k <= l + 18
             for (int j0 = 0; j0 < M_KB / 2; j0 += 16) {
                 uint32_t v[16];
 #pragma unroll
@@ -282,60 +283,73 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
         const int x = xa0 + l;
         const bool xin = x >= 0 && x < A.w;
         const float rx = xin ? __frcp_rn((float)(min(A.w - 1, x + RAD) - max(0, x - RAD) + 1)) : 0.0f;
-        const uint32_t td1 = tl + TC_D1 + 4 * h;
-        const uint32_t b2a = smem_addr(&sm.b2[0]) + (uint32_t)((l >> 3) * 128 + (l & 7) * 16) + (uint32_t)h * B2_GROUP;
+        const uint32_t td1 = tl + TC_D1;
+        const uint32_t b2a = smem_addr(&sm.b2[0]) + (uint32_t)((l >> 3) * 128 + (l & 7) * 16);
         const uint32_t ops = smem_addr(&sm.op[0][0]) + OP_GB + (uint32_t)l * 8;
         const uint32_t mb_d1f = bar(&sm.d1_full), mb_d1e = bar(&sm.d1_empty), mb_b2f = bar(&sm.b2_full),
                        mb_b2e = bar(&sm.b2_empty), mb_opf = bar(&sm.op_full[0]), mb_ope = bar(&sm.op_empty[0]);
         int K = 0;
         for (int g = 0; g < ngroups; g++) {
-            float Sp[4], Sip[4];
+            float Sp[M_ND], Sip[M_ND];
 #pragma unroll
-            for (int d = 0; d < 4; d++) Sp[d] = Sip[d] = 0.0f;
+            for (int d = 0; d < M_ND; d++) Sp[d] = Sip[d] = 0.0f;
 #pragma unroll 1
             for (int it = 0; it < niter; it++, K++) {
                 const int yi0 = y_first + it * MR;
                 const int ko = K & (M_NOP - 1);
-                mbar_wait(mb_d1f, (unsigned)K & 1u);
-                tm_fence_after();
-                uint32_t dp[MR][4], dip[MR][4];
-#pragma unroll
-                for (int r = 0; r < MR; r++) {
-                    tm_ld4(td1 + 8 * r, dp[r]);
-                    tm_ld4(td1 + 8 * MR + 8 * r, dip[r]);
-                }
                 mbar_wait(mb_opf + 8 * ko, (unsigned)(K / M_NOP) & 1u);
                 uint2 st[MR];
 #pragma unroll
                 for (int r = 0; r < MR; r++) st[r] = lds64(ops + ko * OP_BYTES + r * GB_ROW);
-                tm_wait_ld();
-                tm_fence_before();
-                __syncwarp();
-                mbar_arrive_lane0(mb_d1e, lane);
+                float r1[MR];
 #pragma unroll
-                for (int r = 0; r < MR; r++) {
-                    const float mI = __uint_as_float(st[r].x), c2 = __uint_as_float(st[r].y);
-                    const float mIc = I_CENTER - mI;
-                    const float r1 = rx * inv_rows(sm.ry_lut[0], yi0 + r - RAD, A.y_global0, A.frame_h);
-                    uint32_t hi[4], lo[4];
+                for (int r = 0; r < MR; r++) r1[r] = rx * inv_rows(sm.ry_lut[0], yi0 + r - RAD, A.y_global0, A.frame_h);
+                mbar_wait(mb_d1f, (unsigned)K & 1u);
+                tm_fence_after();
 #pragma unroll
-                    for (int d = 0; d < 4; d++) {
-                        Sp[d] += __uint_as_float(dp[r][d]);
-                        Sip[d] += __uint_as_float(dip[r][d]);
-                        const float cov = fmaf(-mI, Sp[d], Sip[d]);
-                        const float a = cov * c2;
-                        // b + 128 a: role C evaluates q = mean_a * (I - 128) + mean(b + 128 a), which halves the magnitudes
-                        // that cancel in mean_a * I + mean_b (guidedFilter.cu:363-369) and with them the rounding error
-                        const float b = fmaf(mIc, a, Sp[d] * r1);
-                        const unsigned h2 = h22u(__floats2half2_rn(a, b));
-                        // hi - value = -(lo part); MMA 2 takes the lo pass with B negated
-                        const float na = fhadd_lo(h2, -a), nb = fhadd_hi(h2, -b);
-                        hi[d] = h2;
-                        lo[d] = h22u(__floats2half2_rn(na, nb));
+                for (int half = 0; half < 2; half++) {
+                    uint32_t dp[2][8], dip[2][8];
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        tm_ld8(td1 + 8 * (2 * half + j), dp[j]);
+                        tm_ld8(td1 + 8 * MR + 8 * (2 * half + j), dip[j]);
                     }
-                    if (r == 0 && K >= 1) mbar_wait(mb_b2e, (unsigned)(K - 1) & 1u);  // MMA 2 of the previous iteration has read B2
-                    sts128(b2a + (uint32_t)(r * 2) * B2_GROUP, hi[0], hi[1], hi[2], hi[3]);
-                    sts128(b2a + (uint32_t)(2 * MR + r * 2) * B2_GROUP, lo[0], lo[1], lo[2], lo[3]);
+                    tm_wait_ld();
+                    if (half == 1) {  // all of D1 is in registers: MMA 1 of the next iteration may overwrite it
+                        tm_fence_before();
+                        __syncwarp();
+                        mbar_arrive_lane0(mb_d1e, lane);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {
+                        const int r = 2 * half + j;
+                        const float mI = __uint_as_float(st[r].x), c2 = __uint_as_float(st[r].y);
+                        const float mIc = I_CENTER - mI;
+                        uint32_t hi[M_ND], lo[M_ND];
+#pragma unroll
+                        for (int d = 0; d < M_ND; d++) {
+                            Sp[d] += __uint_as_float(dp[j][d]);
+                            Sip[d] += __uint_as_float(dip[j][d]);
+                            const float cov = fmaf(-mI, Sp[d], Sip[d]);
+                            const float a = cov * c2;
+                            // b + 128 a: role C evaluates q = mean_a * (I - 128) + mean(b + 128 a), which halves the
+                            // magnitudes that cancel in mean_a * I + mean_b (guidedFilter.cu:363-369) and with them the
+                            // rounding error
+                            const float b = fmaf(mIc, a, Sp[d] * r1[r]);
+                            const unsigned h2 = h22u(__floats2half2_rn(a, b));
+                            // hi - value = -(lo part); MMA 2 takes the lo pass with B negated
+                            const float na = fhadd_lo(h2, -a), nb = fhadd_hi(h2, -b);
+                            hi[d] = h2;
+                            lo[d] = h22u(__floats2half2_rn(na, nb));
+                        }
+                        if (r == 0 && K >= 1) mbar_wait(mb_b2e, (unsigned)(K - 1) & 1u);  // MMA 2 of the previous iteration has read B2
+#pragma unroll
+                        for (int q4 = 0; q4 < 2; q4++) {
+                            sts128(b2a + (uint32_t)(r * 2 + q4) * B2_GROUP, hi[4 * q4], hi[4 * q4 + 1], hi[4 * q4 + 2], hi[4 * q4 + 3]);
+                            sts128(b2a + (uint32_t)(2 * MR + r * 2 + q4) * B2_GROUP, lo[4 * q4], lo[4 * q4 + 1], lo[4 * q4 + 2],
+                                   lo[4 * q4 + 3]);
+                        }
+                    }
                 }
                 fence_async_smem();
                 __syncwarp();
@@ -345,49 +359,44 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
                 }
             }
         }
-    } else if (warp < 16) {
+    } else if (warp < 8) {
         // ================= role C: vertical sums of H_a, H_b, q, winner-take-all =================
-        // warp = (lane quarter, disparity half h); the warps of half h finish rows 2h, 2h+1 of every iteration: they receive
-        // the other half's 4-disparity winners of those rows through shared memory and read-modify-write the (best,label) plane
+        // one thread per output lane: 8 disparities x MR rows per iteration
         reg_inc<M_REGS_C>();
-        const int q4 = warp & 3, h = (warp - 8) >> 2;
+        const int q4 = warp - 4;
         const int l = q4 * 32 + lane;
         const uint32_t tl = tmem + ((uint32_t)(q4 * 32) << 16);
         const int x = xo0 + l;
         const bool valid = l < M_VW && x < A.w;
         const float rx = valid ? __frcp_rn((float)(min(A.w - 1, x + RAD) - max(0, x - RAD) + 1)) : 0.0f;
         const size_t planeS = (size_t)A.rows_out * A.pitchS;
-        // this thread finishes rows yb0 + MR e + 2h + {0, 1}
-        float2* const bl0 = A.BL + (size_t)(chunk * 2 + view) * planeS + (size_t)(yb0 - A.y_out0 + 2 * h) * A.pitchS + x;
-        const size_t bl_step = (size_t)MR * A.pitchS;
+        float2* const bl0 = A.BL + (size_t)(chunk * 2 + view) * planeS + (size_t)(yb0 - A.y_out0) * A.pitchS + x;
         const int band_rows = yb1 - yb0;
-        const uint32_t td2 = tl + TC_D2 + 8 * h, tring = tl + TC_RING + 8 * h;
+        const uint32_t td2 = tl + TC_D2, tring = tl + TC_RING;
         const uint32_t gcs = smem_addr(&sm.gc[0][0]) + (uint32_t)l * 2;
-        const uint32_t xs_send = smem_addr(&sm.xb[0][2 * (1 - h)][0]) + (uint32_t)l * 8, xs_recv = smem_addr(&sm.xb[0][2 * h][0]) + (uint32_t)l * 8;
         const uint32_t mb_d2f = bar(&sm.d2_full), mb_d2e = bar(&sm.d2_empty), mb_gcf = bar(&sm.gc_full[0]), mb_gce = bar(&sm.gc_empty[0]);
-        const uint32_t mb_xf_send = bar(&sm.x_full[0][1 - h]), mb_xe_send = bar(&sm.x_empty[0][1 - h]);
-        const uint32_t mb_xf_recv = bar(&sm.x_full[0][h]), mb_xe_recv = bar(&sm.x_empty[0][h]);
-        int K = 0, E = 0;
+        int K = 0;
         for (int g = 0; g < ngroups; g++) {
-            float Sa[4], Sb[4];
+            float Sa[M_ND], Sb[M_ND];
 #pragma unroll
-            for (int d = 0; d < 4; d++) Sa[d] = Sb[d] = 0.0f;
+            for (int d = 0; d < M_ND; d++) Sa[d] = Sb[d] = 0.0f;
             {
-                const uint32_t z[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-                for (int s = 0; s < WIN; s++) tm_st8(tring + 16 * s, z);
+                uint32_t z[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) z[i] = 0u;
+                for (int s = 0; s < WIN; s++) tm_st16u(tring + 16 * s, z);
                 tm_wait_st();
             }
-            const float dbase = (float)(dlo + g * M_ND + 4 * h);
-            const int dact = min(M_ND, dcnt - g * M_ND) - 4 * h;  // disparities of this thread's half that exist
+            const float dbase = (float)(dlo + g * M_ND);
+            const int dact = min(M_ND, dcnt - g * M_ND);  // disparities of this group that exist
             const bool ld_ok = (g > 0) && valid;
             const float2 binit = make_float2(BEST_INIT_BITS_F, 0.0f);
-            // (best,label) of the rows this thread finishes, fetched two emissions ahead
-            float2 pbA[2], pbB[2];
+            // (best,label) of this emission's rows, fetched one emission ahead
+            float2 pbN[MR];
 #pragma unroll
-            for (int j = 0; j < 2; j++) {
-                pbA[j] = pbB[j] = binit;
-                if (ld_ok && 2 * h + j < band_rows) pbA[j] = ld_early_f2(bl0 + (size_t)j * A.pitchS);
-                if (ld_ok && MR + 2 * h + j < band_rows) pbB[j] = ld_early_f2(bl0 + bl_step + (size_t)j * A.pitchS);
+            for (int r = 0; r < MR; r++) {
+                pbN[r] = binit;
+                if (ld_ok && r < band_rows) pbN[r] = ld_early_f2(bl0 + (size_t)r * A.pitchS);
             }
             float2* blp = bl0;
             int slot = 0;
@@ -401,17 +410,28 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
                     slots[r] = slot;
                     slot = (slot + 1 == WIN) ? 0 : slot + 1;
                 }
+                float2 pb[MR];
+                float rxy[MR], Ic[MR];
+                if (e >= 0) {
+                    mbar_wait(mb_gcf + 8 * kc, (unsigned)(K / M_NGC) & 1u);
+#pragma unroll
+                    for (int r = 0; r < MR; r++) {
+                        pb[r] = pbN[r];
+                        pbN[r] = binit;
+                        if (ld_ok && (e + 1) * MR + r < band_rows) pbN[r] = ld_early_f2(blp + (size_t)(MR + r) * A.pitchS);
+                        rxy[r] = rx * inv_rows(sm.ry_lut[1], yb0 + e * MR + r, A.y_global0, A.frame_h);
+                        Ic[r] = __half2float(__ushort_as_half((unsigned short)lds16(gcs + kc * (MR * GC_ROW) + r * GC_ROW)));
+                    }
+                }
                 mbar_wait(mb_d2f, (unsigned)K & 1u);
                 tm_fence_after();
-                mbar_wait(mb_gcf + 8 * kc, (unsigned)(K / M_NGC) & 1u);
-                float wm[MR], wa[MR];  // winner of this thread's 4 disparities in each row: cost, label
 #pragma unroll
                 for (int half = 0; half < 2; half++) {
-                    uint32_t hh[2][8], o[2][8];
+                    uint32_t hh[2][16], o[2][16];
 #pragma unroll
                     for (int j = 0; j < 2; j++) {
-                        tm_ld8(td2 + 16 * (2 * half + j), hh[j]);
-                        tm_ld8(tring + 16 * slots[2 * half + j], o[j]);
+                        tm_ld16u(td2 + 16 * (2 * half + j), hh[j]);
+                        tm_ld16u(tring + 16 * slots[2 * half + j], o[j]);
                     }
                     tm_wait_ld();
                     if (half == 1) {  // all of D2 is in registers: MMA 2 of the next iteration may overwrite it
@@ -422,85 +442,55 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
 #pragma unroll
                     for (int j = 0; j < 2; j++) {
                         const int r = 2 * half + j;
-                        tm_st8(tring + 16 * slots[r], hh[j]);
+                        tm_st16u(tring + 16 * slots[r], hh[j]);
 #pragma unroll
-                        for (int d = 0; d < 4; d++) {
+                        for (int d = 0; d < M_ND; d++) {
                             Sa[d] += __uint_as_float(hh[j][2 * d]) - __uint_as_float(o[j][2 * d]);
                             Sb[d] += __uint_as_float(hh[j][2 * d + 1]) - __uint_as_float(o[j][2 * d + 1]);
                         }
                         if (e >= 0) {
-                            const int yq = yb0 + e * MR + r;
-                            const float rxy = rx * inv_rows(sm.ry_lut[1], yq, A.y_global0, A.frame_h);
-                            const float I = __half2float(__ushort_as_half((unsigned short)lds16(gcs + kc * (MR * GC_ROW) + r * GC_ROW)));
-                            float q[4];
+                            float q[M_ND];
 #pragma unroll
-                            for (int d = 0; d < 4; d++) q[d] = fmaf(Sa[d], I, Sb[d]) * rxy;
-                            if (dact < 4) {  // last, partial group
+                            for (int d = 0; d < M_ND; d++) q[d] = fmaf(Sa[d], Ic[r], Sb[d]) * rxy[r];
+                            if (dact < M_ND) {  // last, partial group
 #pragma unroll
-                                for (int d = 0; d < 4; d++)
+                                for (int d = 0; d < M_ND; d++)
                                     if (d >= dact) q[d] = __int_as_float(0x7f800000);
                             }
                             // ascending d, `best >= q`: minimum, the later index on a tie (guidedFilter.cu:406), as a tournament
-                            const bool t01 = q[0] >= q[1], t23 = q[2] >= q[3];
-                            const float m01 = t01 ? q[1] : q[0], a01 = t01 ? 1.0f : 0.0f;
-                            const float m23 = t23 ? q[3] : q[2], a23 = t23 ? 3.0f : 2.0f;
+                            float m1[4], a1[4];
+#pragma unroll
+                            for (int i = 0; i < 4; i++) {
+                                const bool t = q[2 * i] >= q[2 * i + 1];
+                                m1[i] = t ? q[2 * i + 1] : q[2 * i];
+                                a1[i] = t ? (float)(2 * i + 1) : (float)(2 * i);
+                            }
+                            const bool t01 = m1[0] >= m1[1], t23 = m1[2] >= m1[3];
+                            const float m01 = t01 ? m1[1] : m1[0], a01 = t01 ? a1[1] : a1[0];
+                            const float m23 = t23 ? m1[3] : m1[2], a23 = t23 ? a1[3] : a1[2];
                             const bool tt = m01 >= m23;
-                            wm[r] = tt ? m23 : m01;
-                            wa[r] = (tt ? a23 : a01) + dbase;
+                            const float m = tt ? m23 : m01, am = tt ? a23 : a01;
+                            float2 nb = pb[r];
+                            if (nb.x >= m) {
+                                nb.x = m;
+                                nb.y = am + dbase;
+                            }
+                            if (valid && e * MR + r < band_rows) blp[(size_t)r * A.pitchS] = nb;
                         }
                     }
                 }
-                if (e >= 0) {
-                    // hand the winners of the other half's rows over, take its winners of this half's rows
-                    const uint32_t xo = (uint32_t)(E & 1) * (MR * M_TW * 8);
-                    if (E >= 2) mbar_wait(mb_xe_send + 16 * (E & 1), (unsigned)((E >> 1) - 1) & 1u);
-#pragma unroll
-                    for (int j = 0; j < 2; j++)
-                        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(xs_send + xo + j * (M_TW * 8)), "f"(h ? wm[j] : wm[2 + j]),
-                                     "f"(h ? wa[j] : wa[2 + j])
-                                     : "memory");
-                    __syncwarp();
-                    mbar_arrive_lane0(mb_xf_send + 16 * (E & 1), lane);
-                    mbar_wait(mb_xf_recv + 16 * (E & 1), (unsigned)(E >> 1) & 1u);
-                    float om[2], oa[2];
-#pragma unroll
-                    for (int j = 0; j < 2; j++)
-                        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(om[j]), "=f"(oa[j]) : "r"(xs_recv + xo + j * (M_TW * 8)) : "memory");
-                    __syncwarp();
-                    mbar_arrive_lane0(mb_xe_recv + 16 * (E & 1), lane);
-#pragma unroll
-                    for (int j = 0; j < 2; j++) {
-                        // fold in ascending d: half 0 first
-                        const float mine_m = h ? wm[2 + j] : wm[j], mine_a = h ? wa[2 + j] : wa[j];
-                        const float m0 = h ? om[j] : mine_m, a0 = h ? oa[j] : mine_a;
-                        const float m1 = h ? mine_m : om[j], a1 = h ? mine_a : oa[j];
-                        const bool t = m0 >= m1;
-                        const float m = t ? m1 : m0, am = t ? a1 : a0;
-                        float2 nb = pbA[j];
-                        if (nb.x >= m) {
-                            nb.x = m;
-                            nb.y = am;
-                        }
-                        const int rowb = e * MR + 2 * h + j;  // row of the band
-                        if (valid && rowb < band_rows) blp[(size_t)j * A.pitchS] = nb;
-                        pbA[j] = pbB[j];
-                        pbB[j] = binit;
-                        if (ld_ok && rowb + 2 * MR < band_rows) pbB[j] = ld_early_f2(blp + 2 * bl_step + (size_t)j * A.pitchS);
-                    }
-                    blp += bl_step;
-                    E++;
-                }
+                if (e >= 0) blp += (size_t)MR * A.pitchS;
                 tm_wait_st();
                 if ((it & (M_RESUM - 1)) == M_RESUM - 1) {
                     // re-sum the ring: bounds the rounding drift of the running sums to M_RESUM iterations
 #pragma unroll
-                    for (int d = 0; d < 4; d++) Sa[d] = Sb[d] = 0.0f;
+                    for (int d = 0; d < M_ND; d++) Sa[d] = Sb[d] = 0.0f;
                     for (int s = 0; s < WIN; s++) {
-                        uint32_t v[8];
-                        tm_ld8(tring + 16 * s, v);
+                        uint32_t v[16];
+                        tm_ld16u(tring + 16 * s, v);
                         tm_wait_ld();
 #pragma unroll
-                        for (int d = 0; d < 4; d++) {
+                        for (int d = 0; d < M_ND; d++) {
                             Sa[d] += __uint_as_float(v[2 * d]);
                             Sb[d] += __uint_as_float(v[2 * d + 1]);
                         }
@@ -511,11 +501,11 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
             }
         }
     } else {
-    reg_dec<M_REGS_A>();  // warpgroups 4, 5 (role A, MMA issue, TMA producer) give registers to roles B and C
-    if (warp < 16 + M_NWA) {
+    reg_dec<M_REGS_A>();  // warpgroups 2, 3 (role A, MMA issue, TMA producer) give registers to roles B and C
+    if (warp < 8 + M_NWA) {
         // ================= role A: lattice cost, exact fp16 pieces, vertical differences =================
         // one thread per cost column: 8 disparities x MR rows per iteration
-        const int k = (warp - 16) * 32 + lane;
+        const int k = (warp - 8) * 32 + lane;
         const int x = xc0 + k;
         const bool used = k < M_KC && x >= 0 && x < A.w;
         const __half2 wI = used ? u2h2(A.wI2) : __float2half2_rn(0.0f);
@@ -586,7 +576,7 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
                 }
             }
         }
-    } else if (warp == 16 + M_NWA) {
+    } else if (warp == 8 + M_NWA) {
         // ================= MMA issue: warp-uniform descriptors, one elected lane =================
         named_bar_sync(1, 128 + 32);  // the band matrix is in Tensor Memory
         tm_fence_after();
@@ -629,7 +619,7 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
             if (K >= 1) stage2(K - 1);
         }
         if (Ktotal > 0) stage2(Ktotal - 1);
-    } else if (warp == 17 + M_NWA) {
+    } else if (warp == 9 + M_NWA) {
         // ================= TMA producer (warp-uniform addresses, one elected lane issues) =================
         const char* GAp = reinterpret_cast<const char*>(A.GA[view] + (size_t)strip * A.rows_pad * M_KB);
         const char* GBp = reinterpret_cast<const char*>(A.GB[view] + (size_t)strip * A.rows_pad * M_TW);
