@@ -43,7 +43,17 @@ constexpr int M_K2 = 128;       // K of MMA 2 (8 K-steps)
 constexpr int M_ND = 8;         // disparities per group
 constexpr int MR = 4;           // image rows per pipeline iteration (one hand-off between the roles per MR rows)
 constexpr int M_NWA = 5;        // role-A warps: one thread per cost column, all MR rows
-constexpr int M_THREADS = 512;  // 4 B + 4 C + 5 A + MMA + TMA warps (+ 1 idle: whole warpgroups)
+#ifndef MMA_BSPLIT
+#define MMA_BSPLIT 1   // role B: 1 = one thread per a/b lane (8 disparities), 2 = two threads (4 disparities each)
+#endif
+#ifndef MMA_CSPLIT
+#define MMA_CSPLIT 1   // role C: 1 = one thread per output lane (MR rows), 2 = two threads (MR/2 rows each)
+#endif
+constexpr int NWB = 4 * MMA_BSPLIT, NWC = 4 * MMA_CSPLIT;  // warps of roles B and C
+constexpr int BD = M_ND / MMA_BSPLIT;                      // disparities per role-B thread
+constexpr int CR = MR / MMA_CSPLIT;                        // rows per role-C thread
+constexpr int M_WARPS = (NWB + NWC + M_NWA + 2 + 3) / 4 * 4;  // + MMA + TMA warps, rounded up to whole warpgroups
+constexpr int M_THREADS = 32 * M_WARPS;
 constexpr int M_NOP = 4;        // operand ring (guide rows, a/b statistics, match rows): iterations in flight
 constexpr int M_NGC = 8;        // ring of the output rows' intensities (role C runs behind the others)
 constexpr int M_MTC = 42;       // match chunks (4 pixels x 4 shifted copies, 64 B) per row in an operand slot
@@ -153,6 +163,19 @@ __device__ __forceinline__ void tm_st8(uint32_t taddr, const uint32_t (&r)[8]) {
                  "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
 }
+template <int N>
+__device__ __forceinline__ void tm_ldN(uint32_t taddr, uint32_t (&r)[N]) {
+    static_assert(N == 4 || N == 8 || N == 16, "tcgen05.ld shape");
+    if constexpr (N == 4) tm_ld4(taddr, r);
+    else if constexpr (N == 8) tm_ld8(taddr, r);
+    else tm_ld16u(taddr, r);
+}
+template <int N>
+__device__ __forceinline__ void tm_stN(uint32_t taddr, const uint32_t (&r)[N]) {
+    static_assert(N == 8 || N == 16, "tcgen05.st shape");
+    if constexpr (N == 8) tm_st8(taddr, r);
+    else tm_st16u(taddr, r);
+}
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -186,9 +209,12 @@ __device__ __forceinline__ float fhadd_hi(unsigned h2, float c) { return fhadd(_
 // Register budgets of the warpgroups.  setmaxnreg only moves registers inside the pool the block got at launch: the launch-time
 // register count x threads (here 128 x 512 = the whole 64 K file; with 640 threads it is 96 x 640 = 61440) -- budgets that add up
 // to more leave the last setmaxnreg.inc waiting forever.
-constexpr int M_REGS_LAUNCH = 128;
-constexpr int M_REGS_B = 160, M_REGS_C = 176, M_REGS_A = 88;
-static_assert(128 * M_REGS_B + 128 * M_REGS_C + 256 * M_REGS_A <= M_THREADS * M_REGS_LAUNCH, "register pool of the block");
+constexpr int M_REGS_LAUNCH = (65536 / M_THREADS) / 8 * 8;
+constexpr int M_REGS_B = MMA_BSPLIT == 1 ? 168 : 96;
+constexpr int M_REGS_C = MMA_CSPLIT == 1 ? 120 : 72;
+constexpr int M_REGS_A = (M_WARPS == 16) ? 112 : (M_WARPS == 20 ? 80 : 72);
+static_assert(32 * NWB * M_REGS_B + 32 * NWC * M_REGS_C + 32 * (M_WARPS - NWB - NWC) * M_REGS_A <= M_THREADS * M_REGS_LAUNCH,
+              "register pool of the block");
 
 __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -225,20 +251,20 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
     if (threadIdx.x == 32) {
         for (int i = 0; i < M_NOP; i++) {
             mbar_init(bar(&sm.op_full[i]), 1);
-            mbar_init(bar(&sm.op_empty[i]), M_NWA + 4);  // role A (guide and match rows), role B (statistics)
+            mbar_init(bar(&sm.op_empty[i]), M_NWA + NWB);  // role A (guide and match rows), role B (statistics)
         }
         for (int i = 0; i < M_NGC; i++) {
             mbar_init(bar(&sm.gc_full[i]), 1);
-            mbar_init(bar(&sm.gc_empty[i]), 4);
+            mbar_init(bar(&sm.gc_empty[i]), NWC);
         }
         mbar_init(bar(&sm.b1_full), M_NWA);
         mbar_init(bar(&sm.b1_empty), 1);
         mbar_init(bar(&sm.d1_full), 1);
-        mbar_init(bar(&sm.d1_empty), 4);
-        mbar_init(bar(&sm.b2_full), 4);
+        mbar_init(bar(&sm.d1_empty), NWB);
+        mbar_init(bar(&sm.b2_full), NWB);
         mbar_init(bar(&sm.b2_empty), 1);
         mbar_init(bar(&sm.d2_full), 1);
-        mbar_init(bar(&sm.d2_empty), 4);
+        mbar_init(bar(&sm.d2_empty), NWC);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x >= 64 && threadIdx.x < 64 + 2 * (WIN + 1)) {
@@ -258,13 +284,16 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
     tm_fence_after();
     const uint32_t tmem = sm.tmem_base;
 
-    if (warp < 4) {
-        // ================= role B: 2-D box sums of P and I*P, a and b, fp16 hi/lo split =================
-        // one thread per a/b lane: 8 disparities x MR rows per iteration
+    if (warp < NWB) {
+        // ================= role B: 2-D box sums of P and I*P, a and b, their vertical window sums, fp16 hi/lo split ====
+        // warp = (lane quarter, disparity part h): BD disparities x MR rows per thread and iteration.  The vertical 19-row
+        // sums of a and b are running sums (ring of the last 19 rows in Tensor Memory, re-summed every M_RESUM iterations:
+        // that bounds the rounding drift); MMA 2 then takes their horizontal sums, so role C receives finished window sums.
         reg_inc<M_REGS_B>();
-        const int l = warp * 32 + lane;
-        const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
-        {   // this lane's row of the band matrix: Band[l][k] = 1 for l <= k <= l + 18
+        const int q4 = warp & 3, h = warp >> 2;
+        const int l = q4 * 32 + lane;
+        const uint32_t tl = tmem + ((uint32_t)(q4 * 32) << 16);
+        if (h == 0) {  // this lane's row of the band matrix: Band[l][k] = 1 for l <= k <= l + 18
             for (int j0 = 0; j0 < M_KB / 2; j0 += 16) {
                 uint32_t v[16];
 #pragma unroll
@@ -283,16 +312,25 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
         const int x = xa0 + l;
         const bool xin = x >= 0 && x < A.w;
         const float rx = xin ? __frcp_rn((float)(min(A.w - 1, x + RAD) - max(0, x - RAD) + 1)) : 0.0f;
-        const uint32_t td1 = tl + TC_D1;
-        const uint32_t b2a = smem_addr(&sm.b2[0]) + (uint32_t)((l >> 3) * 128 + (l & 7) * 16);
+        const float r1_whole = rx * sm.ry_lut[0][WIN];
+        const uint32_t td1 = tl + TC_D1 + BD * h, tring = tl + TC_RING + 2 * BD * h;
+        const uint32_t b2a = smem_addr(&sm.b2[0]) + (uint32_t)((l >> 3) * 128 + (l & 7) * 16) + (uint32_t)h * (BD / 4) * B2_GROUP;
         const uint32_t ops = smem_addr(&sm.op[0][0]) + OP_GB + (uint32_t)l * 8;
         const uint32_t mb_d1f = bar(&sm.d1_full), mb_d1e = bar(&sm.d1_empty), mb_b2f = bar(&sm.b2_full),
                        mb_b2e = bar(&sm.b2_empty), mb_opf = bar(&sm.op_full[0]), mb_ope = bar(&sm.op_empty[0]);
         int K = 0;
         for (int g = 0; g < ngroups; g++) {
-            float Sp[M_ND], Sip[M_ND];
+            float Sp[BD], Sip[BD], Va[BD], Vb[BD];
 #pragma unroll
-            for (int d = 0; d < M_ND; d++) Sp[d] = Sip[d] = 0.0f;
+            for (int d = 0; d < BD; d++) Sp[d] = Sip[d] = Va[d] = Vb[d] = 0.0f;
+            {
+                uint32_t z[2 * BD];
+#pragma unroll
+                for (int i = 0; i < 2 * BD; i++) z[i] = 0u;
+                for (int s = 0; s < WIN; s++) tm_stN(tring + 16 * s, z);
+                tm_wait_st();
+            }
+            int slot = 0;
 #pragma unroll 1
             for (int it = 0; it < niter; it++, K++) {
                 const int yi0 = y_first + it * MR;
@@ -302,17 +340,29 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
 #pragma unroll
                 for (int r = 0; r < MR; r++) st[r] = lds64(ops + ko * OP_BYTES + r * GB_ROW);
                 float r1[MR];
+                {   // 1 / (S * clipped window area) of the a/b rows: a constant while the rows' windows are whole
+                    const int yg = yi0 - RAD + A.y_global0;
+                    if (yg >= RAD && yg + MR - 1 + RAD < A.frame_h) {
 #pragma unroll
-                for (int r = 0; r < MR; r++) r1[r] = rx * inv_rows(sm.ry_lut[0], yi0 + r - RAD, A.y_global0, A.frame_h);
+                        for (int r = 0; r < MR; r++) r1[r] = r1_whole;
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < MR; r++) r1[r] = rx * inv_rows(sm.ry_lut[0], yi0 + r - RAD, A.y_global0, A.frame_h);
+                    }
+                }
                 mbar_wait(mb_d1f, (unsigned)K & 1u);
                 tm_fence_after();
 #pragma unroll
                 for (int half = 0; half < 2; half++) {
-                    uint32_t dp[2][8], dip[2][8];
+                    uint32_t dp[2][BD], dip[2][BD], o[2][2 * BD];
+                    int slots[2];
 #pragma unroll
                     for (int j = 0; j < 2; j++) {
-                        tm_ld8(td1 + 8 * (2 * half + j), dp[j]);
-                        tm_ld8(td1 + 8 * MR + 8 * (2 * half + j), dip[j]);
+                        slots[j] = slot;
+                        slot = (slot + 1 == WIN) ? 0 : slot + 1;
+                        tm_ldN(td1 + 8 * (2 * half + j), dp[j]);
+                        tm_ldN(td1 + 8 * MR + 8 * (2 * half + j), dip[j]);
+                        tm_ldN(tring + 16 * slots[j], o[j]);  // the (a,b) row that leaves the vertical window
                     }
                     tm_wait_ld();
                     if (half == 1) {  // all of D1 is in registers: MMA 1 of the next iteration may overwrite it
@@ -325,32 +375,59 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
                         const int r = 2 * half + j;
                         const float mI = __uint_as_float(st[r].x), c2 = __uint_as_float(st[r].y);
                         const float mIc = I_CENTER - mI;
-                        uint32_t hi[M_ND], lo[M_ND];
+                        uint32_t ab[2 * BD];
 #pragma unroll
-                        for (int d = 0; d < M_ND; d++) {
+                        for (int d = 0; d < BD; d++) {
                             Sp[d] += __uint_as_float(dp[j][d]);
                             Sip[d] += __uint_as_float(dip[j][d]);
                             const float cov = fmaf(-mI, Sp[d], Sip[d]);
                             const float a = cov * c2;
-                            // b + 128 a: role C evaluates q = mean_a * (I - 128) + mean(b + 128 a), which halves the
-                            // magnitudes that cancel in mean_a * I + mean_b (guidedFilter.cu:363-369) and with them the
-                            // rounding error
+                            // b + 128 a: role C evaluates q = mean_a * (I - 128) + mean(b + 128 a), which halves the magnitudes
+                            // that cancel in mean_a * I + mean_b (guidedFilter.cu:363-369) and with them the rounding error
                             const float b = fmaf(mIc, a, Sp[d] * r1[r]);
-                            const unsigned h2 = h22u(__floats2half2_rn(a, b));
-                            // hi - value = -(lo part); MMA 2 takes the lo pass with B negated
-                            const float na = fhadd_lo(h2, -a), nb = fhadd_hi(h2, -b);
-                            hi[d] = h2;
-                            lo[d] = h22u(__floats2half2_rn(na, nb));
+                            ab[d] = __float_as_uint(a);
+                            ab[BD + d] = __float_as_uint(b);
+                            Va[d] += a - __uint_as_float(o[j][d]);
+                            Vb[d] += b - __uint_as_float(o[j][BD + d]);
+                        }
+                        tm_stN(tring + 16 * slots[j], ab);
+                        if (r == MR - 1 && (it & (M_RESUM - 1)) == M_RESUM - 1) {
+                            // re-sum the ring (it now ends with this row): bounds the drift of the running sums
+                            tm_wait_st();
+#pragma unroll
+                            for (int d = 0; d < BD; d++) Va[d] = Vb[d] = 0.0f;
+                            for (int s = 0; s < WIN; s++) {
+                                uint32_t v[2 * BD];
+                                tm_ldN(tring + 16 * s, v);
+                                tm_wait_ld();
+#pragma unroll
+                                for (int d = 0; d < BD; d++) {
+                                    Va[d] += __uint_as_float(v[d]);
+                                    Vb[d] += __uint_as_float(v[BD + d]);
+                                }
+                            }
                         }
                         if (r == 0 && K >= 1) mbar_wait(mb_b2e, (unsigned)(K - 1) & 1u);  // MMA 2 of the previous iteration has read B2
+                        // fp16 hi + lo of the vertical sums: hi - value = -(lo part); MMA 2 takes the lo pass with B negated.
+                        // A B2 group (8 columns of D2) = a of 4 disparities, then b of the same 4.
 #pragma unroll
-                        for (int q4 = 0; q4 < 2; q4++) {
-                            sts128(b2a + (uint32_t)(r * 2 + q4) * B2_GROUP, hi[4 * q4], hi[4 * q4 + 1], hi[4 * q4 + 2], hi[4 * q4 + 3]);
-                            sts128(b2a + (uint32_t)(2 * MR + r * 2 + q4) * B2_GROUP, lo[4 * q4], lo[4 * q4 + 1], lo[4 * q4 + 2],
-                                   lo[4 * q4 + 3]);
+                        for (int q = 0; q < BD / 4; q++) {
+                            uint32_t hi[4], lo[4];
+#pragma unroll
+                            for (int d = 0; d < 2; d++) {
+                                const float a0 = Va[4 * q + 2 * d], a1 = Va[4 * q + 2 * d + 1], b0 = Vb[4 * q + 2 * d], b1 = Vb[4 * q + 2 * d + 1];
+                                const unsigned ha = h22u(__floats2half2_rn(a0, a1)), hb = h22u(__floats2half2_rn(b0, b1));
+                                hi[d] = ha;
+                                hi[2 + d] = hb;
+                                lo[d] = h22u(__floats2half2_rn(fhadd_lo(ha, -a0), fhadd_hi(ha, -a1)));
+                                lo[2 + d] = h22u(__floats2half2_rn(fhadd_lo(hb, -b0), fhadd_hi(hb, -b1)));
+                            }
+                            sts128(b2a + (uint32_t)(r * 2 + q) * B2_GROUP, hi[0], hi[1], hi[2], hi[3]);
+                            sts128(b2a + (uint32_t)(2 * MR + r * 2 + q) * B2_GROUP, lo[0], lo[1], lo[2], lo[3]);
                         }
                     }
                 }
+                tm_wait_st();
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) {
@@ -359,153 +436,131 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
                 }
             }
         }
-    } else if (warp < 8) {
-        // ================= role C: vertical sums of H_a, H_b, q, winner-take-all =================
-        // one thread per output lane: 8 disparities x MR rows per iteration
-        reg_inc<M_REGS_C>();
-        const int q4 = warp - 4;
+    } else if (warp < NWB + NWC) {
+        // ================= role C: q = mean_a * I + mean_b, winner-take-all =================
+        // warp = (lane quarter, row part c): CR rows of every iteration, all 8 disparities; no state between iterations
+        if (M_REGS_C < M_REGS_LAUNCH) reg_dec<M_REGS_C>(); else if (M_REGS_C > M_REGS_LAUNCH) reg_inc<M_REGS_C>();
+        const int q4 = warp & 3, c = (warp - NWB) >> 2;
         const int l = q4 * 32 + lane;
         const uint32_t tl = tmem + ((uint32_t)(q4 * 32) << 16);
         const int x = xo0 + l;
         const bool valid = l < M_VW && x < A.w;
         const float rx = valid ? __frcp_rn((float)(min(A.w - 1, x + RAD) - max(0, x - RAD) + 1)) : 0.0f;
-        const size_t planeS = (size_t)A.rows_out * A.pitchS;
-        float2* const bl0 = A.BL + (size_t)(chunk * 2 + view) * planeS + (size_t)(yb0 - A.y_out0) * A.pitchS + x;
+        const float rxy_whole = rx * sm.ry_lut[1][WIN];
+        const int pitchS = A.pitchS;
+        const size_t planeS = (size_t)A.rows_out * pitchS;
+        // this thread finishes rows yb0 + MR e + CR c + {0 .. CR-1}
+        float2* const bl0 = A.BL + (size_t)(chunk * 2 + view) * planeS + (size_t)(yb0 - A.y_out0 + CR * c) * pitchS + x;
         const int band_rows = yb1 - yb0;
-        const uint32_t td2 = tl + TC_D2, tring = tl + TC_RING;
-        const uint32_t gcs = smem_addr(&sm.gc[0][0]) + (uint32_t)l * 2;
+        const uint32_t td2 = tl + TC_D2 + 16 * CR * c;
+        const uint32_t gcs = smem_addr(&sm.gc[0][0]) + (uint32_t)(CR * c) * GC_ROW + (uint32_t)l * 2;
         const uint32_t mb_d2f = bar(&sm.d2_full), mb_d2e = bar(&sm.d2_empty), mb_gcf = bar(&sm.gc_full[0]), mb_gce = bar(&sm.gc_empty[0]);
         int K = 0;
         for (int g = 0; g < ngroups; g++) {
-            float Sa[M_ND], Sb[M_ND];
-#pragma unroll
-            for (int d = 0; d < M_ND; d++) Sa[d] = Sb[d] = 0.0f;
-            {
-                uint32_t z[16];
-#pragma unroll
-                for (int i = 0; i < 16; i++) z[i] = 0u;
-                for (int s = 0; s < WIN; s++) tm_st16u(tring + 16 * s, z);
-                tm_wait_st();
-            }
             const float dbase = (float)(dlo + g * M_ND);
             const int dact = min(M_ND, dcnt - g * M_ND);  // disparities of this group that exist
             const bool ld_ok = (g > 0) && valid;
             const float2 binit = make_float2(BEST_INIT_BITS_F, 0.0f);
             // (best,label) of this emission's rows, fetched one emission ahead
-            float2 pbN[MR];
+            float2 pbN[CR];
 #pragma unroll
-            for (int r = 0; r < MR; r++) {
-                pbN[r] = binit;
-                if (ld_ok && r < band_rows) pbN[r] = ld_early_f2(bl0 + (size_t)r * A.pitchS);
+            for (int j = 0; j < CR; j++) {
+                pbN[j] = binit;
+                if (ld_ok && CR * c + j < band_rows) pbN[j] = ld_early_f2(bl0 + (size_t)j * pitchS);
             }
             float2* blp = bl0;
-            int slot = 0;
 #pragma unroll 1
             for (int it = 0; it < niter; it++, K++) {
                 const int e = it - WARM_IT;
                 const int kc = K & (M_NGC - 1);
-                int slots[MR];
-#pragma unroll
-                for (int r = 0; r < MR; r++) {
-                    slots[r] = slot;
-                    slot = (slot + 1 == WIN) ? 0 : slot + 1;
+                const int row0 = e * MR + CR * c;  // first of this thread's rows in the band
+                mbar_wait(mb_gcf + 8 * kc, (unsigned)(K / M_NGC) & 1u);
+                if (e < 0) {
+                    // warm-up iterations produce no output rows; the barriers still advance in step with the other roles
+                    mbar_wait(mb_d2f, (unsigned)K & 1u);
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(mb_d2e);
+                        mbar_arrive(mb_gce + 8 * kc);
+                    }
+                    continue;
                 }
-                float2 pb[MR];
-                float rxy[MR], Ic[MR];
-                if (e >= 0) {
-                    mbar_wait(mb_gcf + 8 * kc, (unsigned)(K / M_NGC) & 1u);
+                float2 pb[CR];
+                float rxy[CR], Ic[CR];
+                bool st_ok[CR];
+                {
+                    const int yg = yb0 + row0 + A.y_global0;
+                    const bool whole = yg >= RAD && yg + CR - 1 + RAD < A.frame_h;  // the rows' windows are not clipped
 #pragma unroll
-                    for (int r = 0; r < MR; r++) {
-                        pb[r] = pbN[r];
-                        pbN[r] = binit;
-                        if (ld_ok && (e + 1) * MR + r < band_rows) pbN[r] = ld_early_f2(blp + (size_t)(MR + r) * A.pitchS);
-                        rxy[r] = rx * inv_rows(sm.ry_lut[1], yb0 + e * MR + r, A.y_global0, A.frame_h);
-                        Ic[r] = __half2float(__ushort_as_half((unsigned short)lds16(gcs + kc * (MR * GC_ROW) + r * GC_ROW)));
+                    for (int j = 0; j < CR; j++) {
+                        pb[j] = pbN[j];
+                        pbN[j] = binit;
+                        if (ld_ok && row0 + MR + j < band_rows) pbN[j] = ld_early_f2(blp + (size_t)(MR + j) * pitchS);
+                        rxy[j] = whole ? rxy_whole : rx * inv_rows(sm.ry_lut[1], yb0 + row0 + j, A.y_global0, A.frame_h);
+                        Ic[j] = __half2float(__ushort_as_half((unsigned short)lds16(gcs + kc * (MR * GC_ROW) + j * GC_ROW)));
+                        st_ok[j] = valid && row0 + j < band_rows;
                     }
                 }
                 mbar_wait(mb_d2f, (unsigned)K & 1u);
                 tm_fence_after();
 #pragma unroll
-                for (int half = 0; half < 2; half++) {
-                    uint32_t hh[2][16], o[2][16];
+                for (int jj = 0; jj < CR; jj += 2) {
+                    uint32_t hh[2][16];
 #pragma unroll
-                    for (int j = 0; j < 2; j++) {
-                        tm_ld16u(td2 + 16 * (2 * half + j), hh[j]);
-                        tm_ld16u(tring + 16 * slots[2 * half + j], o[j]);
-                    }
+                    for (int j = 0; j < 2; j++) tm_ld16u(td2 + 16 * (jj + j), hh[j]);
                     tm_wait_ld();
-                    if (half == 1) {  // all of D2 is in registers: MMA 2 of the next iteration may overwrite it
+                    if (jj + 2 == CR) {  // this warp's part of D2 is in registers
                         tm_fence_before();
                         __syncwarp();
                         mbar_arrive_lane0(mb_d2e, lane);
                     }
 #pragma unroll
-                    for (int j = 0; j < 2; j++) {
-                        const int r = 2 * half + j;
-                        tm_st16u(tring + 16 * slots[r], hh[j]);
+                    for (int j2 = 0; j2 < 2; j2++) {
+                        const int j = jj + j2;
+                        // columns of a row: per group of 4 disparities, the window sums of a, then of b
+                        float q[M_ND];
 #pragma unroll
                         for (int d = 0; d < M_ND; d++) {
-                            Sa[d] += __uint_as_float(hh[j][2 * d]) - __uint_as_float(o[j][2 * d]);
-                            Sb[d] += __uint_as_float(hh[j][2 * d + 1]) - __uint_as_float(o[j][2 * d + 1]);
+                            const float sa = __uint_as_float(hh[j2][8 * (d >> 2) + (d & 3)]), sb = __uint_as_float(hh[j2][8 * (d >> 2) + 4 + (d & 3)]);
+                            q[d] = fmaf(sa, Ic[j], sb) * rxy[j];
                         }
-                        if (e >= 0) {
-                            float q[M_ND];
+                        if (dact < M_ND) {  // last, partial group
 #pragma unroll
-                            for (int d = 0; d < M_ND; d++) q[d] = fmaf(Sa[d], Ic[r], Sb[d]) * rxy[r];
-                            if (dact < M_ND) {  // last, partial group
-#pragma unroll
-                                for (int d = 0; d < M_ND; d++)
-                                    if (d >= dact) q[d] = __int_as_float(0x7f800000);
-                            }
-                            // ascending d, `best >= q`: minimum, the later index on a tie (guidedFilter.cu:406), as a tournament
-                            float m1[4], a1[4];
-#pragma unroll
-                            for (int i = 0; i < 4; i++) {
-                                const bool t = q[2 * i] >= q[2 * i + 1];
-                                m1[i] = t ? q[2 * i + 1] : q[2 * i];
-                                a1[i] = t ? (float)(2 * i + 1) : (float)(2 * i);
-                            }
-                            const bool t01 = m1[0] >= m1[1], t23 = m1[2] >= m1[3];
-                            const float m01 = t01 ? m1[1] : m1[0], a01 = t01 ? a1[1] : a1[0];
-                            const float m23 = t23 ? m1[3] : m1[2], a23 = t23 ? a1[3] : a1[2];
-                            const bool tt = m01 >= m23;
-                            const float m = tt ? m23 : m01, am = tt ? a23 : a01;
-                            float2 nb = pb[r];
-                            if (nb.x >= m) {
-                                nb.x = m;
-                                nb.y = am + dbase;
-                            }
-                            if (valid && e * MR + r < band_rows) blp[(size_t)r * A.pitchS] = nb;
+                            for (int d = 0; d < M_ND; d++)
+                                if (d >= dact) q[d] = __int_as_float(0x7f800000);
                         }
+                        // ascending d, `best >= q`: minimum, the later index on a tie (guidedFilter.cu:406), as a tournament
+                        float m1[4], a1[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const bool t = q[2 * i] >= q[2 * i + 1];
+                            m1[i] = t ? q[2 * i + 1] : q[2 * i];
+                            a1[i] = t ? (float)(2 * i + 1) : (float)(2 * i);
+                        }
+                        const bool t01 = m1[0] >= m1[1], t23 = m1[2] >= m1[3];
+                        const float m01 = t01 ? m1[1] : m1[0], a01 = t01 ? a1[1] : a1[0];
+                        const float m23 = t23 ? m1[3] : m1[2], a23 = t23 ? a1[3] : a1[2];
+                        const bool tt = m01 >= m23;
+                        const float m = tt ? m23 : m01, am = tt ? a23 : a01;
+                        float2 nb = pb[j];
+                        if (nb.x >= m) {
+                            nb.x = m;
+                            nb.y = am + dbase;
+                        }
+                        if (st_ok[j]) blp[(size_t)j * pitchS] = nb;
                     }
                 }
-                if (e >= 0) blp += (size_t)MR * A.pitchS;
-                tm_wait_st();
-                if ((it & (M_RESUM - 1)) == M_RESUM - 1) {
-                    // re-sum the ring: bounds the rounding drift of the running sums to M_RESUM iterations
-#pragma unroll
-                    for (int d = 0; d < M_ND; d++) Sa[d] = Sb[d] = 0.0f;
-                    for (int s = 0; s < WIN; s++) {
-                        uint32_t v[16];
-                        tm_ld16u(tring + 16 * s, v);
-                        tm_wait_ld();
-#pragma unroll
-                        for (int d = 0; d < M_ND; d++) {
-                            Sa[d] += __uint_as_float(v[2 * d]);
-                            Sb[d] += __uint_as_float(v[2 * d + 1]);
-                        }
-                    }
-                }
+                blp += (size_t)MR * pitchS;
                 __syncwarp();
                 mbar_arrive_lane0(mb_gce + 8 * kc, lane);
             }
         }
     } else {
-    reg_dec<M_REGS_A>();  // warpgroups 2, 3 (role A, MMA issue, TMA producer) give registers to roles B and C
-    if (warp < 8 + M_NWA) {
+    if (M_REGS_A < M_REGS_LAUNCH) reg_dec<M_REGS_A>();  // the last warpgroups: role A, MMA issue, TMA producer
+    if (warp < NWB + NWC + M_NWA) {
         // ================= role A: lattice cost, exact fp16 pieces, vertical differences =================
         // one thread per cost column: 8 disparities x MR rows per iteration
-        const int k = (warp - 8) * 32 + lane;
+        const int k = (warp - NWB - NWC) * 32 + lane;
         const int x = xc0 + k;
         const bool used = k < M_KC && x >= 0 && x < A.w;
         const __half2 wI = used ? u2h2(A.wI2) : __float2half2_rn(0.0f);
@@ -576,7 +631,7 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
                 }
             }
         }
-    } else if (warp == 8 + M_NWA) {
+    } else if (warp == NWB + NWC + M_NWA) {
         // ================= MMA issue: warp-uniform descriptors, one elected lane =================
         named_bar_sync(1, 128 + 32);  // the band matrix is in Tensor Memory
         tm_fence_after();
@@ -619,7 +674,7 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
             if (K >= 1) stage2(K - 1);
         }
         if (Ktotal > 0) stage2(Ktotal - 1);
-    } else if (warp == 9 + M_NWA) {
+    } else if (warp == NWB + NWC + M_NWA + 1) {
         // ================= TMA producer (warp-uniform addresses, one elected lane issues) =================
         const char* GAp = reinterpret_cast<const char*>(A.GA[view] + (size_t)strip * A.rows_pad * M_KB);
         const char* GBp = reinterpret_cast<const char*>(A.GB[view] + (size_t)strip * A.rows_pad * M_TW);
