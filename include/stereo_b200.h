@@ -59,7 +59,8 @@ typedef struct sb200_params {
     double g_w;      /* G_W  0.587  :8 */
     double b_w;      /* B_W 0.0721  :9 */
     int guide_mode;  /* SB200_GUIDE_* */
-    int box_mode;    /* SB200_BOX_*   (stage entry points only; the fused pipeline is SLIDING) */
+    int box_mode;    /* SB200_BOX_*   (stage entry points; the fused gray pipeline ignores it; with guide_mode RGB,
+                        SB200_BOX_SAT selects the staged colour path, which materialises every slice and is ~50x slower) */
 } sb200_params;
 
 void sb200_default_params(sb200_params* p);
@@ -141,7 +142,7 @@ int sb200_detect_occlusion_dev(sb200_ctx* ctx, const sb200_params* p, float* d_d
 int sb200_fill_occlusion_dev(sb200_ctx* ctx, float* d_disparity, int w, int h, float vMin);
 
 /* ---- fused pipeline (replaces main.cu:65-155 as one call) -------------------------------- */
-/* Outputs; any pointer may be NULL.  All arrays are w*h. */
+/* Outputs; any pointer may be NULL.  All arrays are w*h (w*rows for a row strip, n_pairs*w*h for a batch). */
 typedef struct sb200_outputs {
     float* disp_left;      /* dmapl  main.cu:133 : WTA labels of the left view, in [dmin, dmax]  */
     float* disp_right;     /* dmapr  main.cu:134 : WTA labels of the right view, in [-dmax, -dmin] */
@@ -177,12 +178,29 @@ int sb200_pipeline_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_l
 /* same with HOST pointers, blocking (pageable or pinned; copies happen inside) */
 int sb200_pipeline(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h_left, const uint8_t* h_right, int channels,
                    int w, int h, const sb200_outputs* h_out);
+/* n_pairs pairs with HOST pointers (left + i*w*h*channels, outputs + i*w*h), blocking, OVERLAPPED: the upload of pair
+ * i+1 and the download of pair i-1 run on their own streams under the kernels of pair i.  Use page-locked host buffers
+ * (cudaHostAlloc / cudaHostRegister); pageable buffers work but the driver stages their copies and the overlap is lost.
+ * Replaces the reference's per-stage cudaMemcpy round trips (guidedFilter.cu:39-56, costVolume.cu:23-53). */
+int sb200_pipeline_batch(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h_left, const uint8_t* h_right, int channels,
+                         int w, int h, int n_pairs, const sb200_outputs* h_out);
 /* n_pairs pairs of identical shape, contiguous: left + i*w*h*channels, outputs + i*w*h */
 int sb200_pipeline_batch_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, const uint8_t* d_right,
                              int channels, int w, int h, int n_pairs, const sb200_outputs* d_out);
 /* one row strip of a taller frame; h = halo_top + rows + halo_bot rows are passed in */
 int sb200_pipeline_strip_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, const uint8_t* d_right,
                              int channels, int w, const sb200_strip* strip, const sb200_outputs* d_out);
+/* Row strips across the GPUs of a box in ONE call per rank: `d_own_*` are this rank's rows [y0, y0+rows) of the frame
+ * (device pointers); the 2*radius input rows each neighbouring rank holds are fetched with one grouped
+ * ncclSend/ncclRecv on the context's stream, then the strip runs as sb200_pipeline_strip_dev does.  `nccl_comm` is
+ * the caller's ncclComm_t (ranks hold consecutive strips in rank order, as sb200_strip_rows deals them out); libnccl
+ * is loaded with dlopen on first use, the library does not link against it.  Asynchronous.  Outputs cover the own
+ * rows.  Replaces the single-device assumption of main.cu:44-48 for frames too large for one GPU's time budget. */
+int sb200_pipeline_strips_nccl(sb200_ctx* ctx, const sb200_params* p, void* nccl_comm, int rank, int world,
+                               const uint8_t* d_own_left, const uint8_t* d_own_right, int channels, int w, int frame_h,
+                               int y0, int rows, const sb200_outputs* d_out);
+/* the balanced split sb200_pipeline_strips_nccl expects: rows [y0, y0+rows) of rank `rank` of `world` */
+int sb200_strip_rows(int frame_h, int rank, int world, int* y0, int* rows);
 /* halo rows each side that sb200_pipeline_strip_dev needs: 2*radius (two cascaded boxes) */
 int sb200_strip_halo_rows(const sb200_params* p);
 

@@ -108,6 +108,9 @@ def load_library(path=None):
         "sb200_fill_occlusion_dev": (ip, [vp, vp, ip, ip, fp]),
         "sb200_pipeline_dev": (ip, [vp, PP, vp, vp, ip, ip, ip, C.POINTER(_Outputs)]),
         "sb200_pipeline": (ip, [vp, PP, vp, vp, ip, ip, ip, C.POINTER(_Outputs)]),
+        "sb200_pipeline_strips_nccl": (ip, [vp, PP, vp, ip, ip, vp, vp, ip, ip, ip, ip, ip, C.POINTER(_Outputs)]),
+        "sb200_strip_rows": (ip, [ip, ip, ip, C.POINTER(ip), C.POINTER(ip)]),
+        "sb200_pipeline_batch": (ip, [vp, PP, vp, vp, ip, ip, ip, ip, C.POINTER(_Outputs)]),
         "sb200_pipeline_batch_dev": (ip, [vp, PP, vp, vp, ip, ip, ip, ip, C.POINTER(_Outputs)]),
         "sb200_pipeline_strip_dev": (ip, [vp, PP, vp, vp, ip, ip, C.POINTER(_Strip), C.POINTER(_Outputs)]),
         "sb200_strip_halo_rows": (ip, [PP]),
@@ -291,9 +294,14 @@ class Context:
         p = params or default_params()
         i = _np(i, np.uint8)
         cost = _np(cost, np.float32)
+        if cost.ndim != 3:
+            raise StereoB200Error(f"cost {cost.shape}: expected the planar (size_d, h, w) volume")
         size_d, h, w = cost.shape
-        assert filter_cost.dtype == np.float32 and disp_map.dtype == np.float32
-        assert filter_cost.flags.c_contiguous and disp_map.flags.c_contiguous
+        for name, a in (("filter_cost", filter_cost), ("disp_map", disp_map)):
+            if not isinstance(a, np.ndarray) or a.dtype != np.float32 or not a.flags.c_contiguous or a.shape != (h, w):
+                raise StereoB200Error(f"{name}: expected a C-contiguous float32 array of shape {(h, w)} (updated in place)")
+        if i.shape != (h, w):
+            raise StereoB200Error(f"guide image {i.shape} does not match the cost volume's {(h, w)}")
         mean = np.empty((h, w), np.uint8)
         self._ck(self.lib.sb200_compute_guided_filter(self.h, C.byref(p), _ptr(i), _ptr(cost), _ptr(filter_cost),
                                                       _ptr(disp_map), _ptr(mean), w, h, size_d, dmin))
@@ -328,6 +336,8 @@ class Context:
         """main.cu:65-155 as one call on HOST arrays: (h,w[,ch]) uint8 -> dict of numpy arrays"""
         p = params or default_params()
         left, right = _np(left, np.uint8), _np(right, np.uint8)
+        if left.shape != right.shape:
+            raise StereoB200Error(f"left {left.shape} and right {right.shape} must have the same shape")
         h, w = left.shape[:2]
         ch = 1 if left.ndim == 2 else left.shape[2]
         if want is None:
@@ -341,33 +351,94 @@ class Context:
         self._ck(self.lib.sb200_pipeline(self.h, C.byref(p), _ptr(left), _ptr(right), ch, w, h, C.byref(o)))
         return res
 
-    def _dev_outputs(self, outs):
+    def pipeline_batch(self, lefts, rights, params=None, want=("disp_left", "disp_right", "occlusion", "filled"), out=None):
+        """n pairs on HOST arrays (n,h,w[,ch]) uint8 through sb200_pipeline_batch: uploads, kernels and downloads of
+        consecutive pairs overlap (page-locked arrays, e.g. torch pin_memory().numpy(), are needed for the overlap).
+        `out`: optional dict of preallocated (n,h,w) arrays (float32 / uint8) to fill instead of fresh ones."""
+        p = params or default_params()
+        lefts, rights = _np(lefts, np.uint8), _np(rights, np.uint8)
+        if lefts.shape != rights.shape or lefts.ndim not in (3, 4):
+            raise StereoB200Error(f"lefts {lefts.shape} / rights {rights.shape}: expected two (n,h,w[,ch]) arrays of one shape")
+        n, h, w = lefts.shape[:3]
+        ch = 1 if lefts.ndim == 3 else lefts.shape[3]
+        res, o = {}, _Outputs()
+        for k in want:
+            dt = np.float32 if k in self._F32 else np.uint8
+            if out is not None and k in out:
+                a = out[k]
+                if a.shape != (n, h, w) or a.dtype != dt or not a.flags.c_contiguous:
+                    raise StereoB200Error(f"out[{k!r}]: expected a C-contiguous {np.dtype(dt).name} array of shape {(n, h, w)}")
+            else:
+                a = np.empty((n, h, w), dt)
+            res[k] = a
+            setattr(o, k, a.ctypes.data)
+        self._ck(self.lib.sb200_pipeline_batch(self.h, C.byref(p), _ptr(lefts), _ptr(rights), ch, w, h, n, C.byref(o)))
+        return res
+
+    def _dev_check(self, t, name, numel, dtype_name):
+        """a device tensor handed to the C ABI as a raw pointer: right device, dtype, contiguous, large enough"""
+        if t is None or isinstance(t, int):
+            return
+        if not t.is_cuda or t.device.index != self.device:
+            raise StereoB200Error(f"{name}: expected a tensor on cuda:{self.device}, got {t.device}")
+        if str(t.dtype) != "torch." + dtype_name:
+            raise StereoB200Error(f"{name}: expected dtype {dtype_name}, got {t.dtype}")
+        if not t.is_contiguous():
+            raise StereoB200Error(f"{name}: tensor must be contiguous")
+        if t.numel() < numel:
+            raise StereoB200Error(f"{name}: {t.numel()} elements, need {numel}")
+
+    def _dev_outputs(self, outs, numel=0):
         o = _Outputs()
         for k, t in outs.items():
             if k not in self._F32 + self._U8:
                 raise TypeError(f"unknown output {k}")
+            self._dev_check(t, k, numel, "float32" if k in self._F32 else "uint8")
             setattr(o, k, t if isinstance(t, int) else t.data_ptr())
         return o
 
     def pipeline_dev(self, d_left, d_right, channels, w, h, outs, params=None):
         """device tensors in, device tensors out (dict name -> tensor), asynchronous"""
         p = params or default_params()
-        o = self._dev_outputs(outs)
+        for name, t in (("left", d_left), ("right", d_right)):
+            self._dev_check(t, name, w * h * channels, "uint8")
+        o = self._dev_outputs(outs, w * h)
         self._ck(self.lib.sb200_pipeline_dev(self.h, C.byref(p), _ptr(d_left), _ptr(d_right), channels, w, h, C.byref(o)))
 
     def pipeline_batch_dev(self, d_left, d_right, channels, w, h, n_pairs, outs, params=None):
         p = params or default_params()
-        o = self._dev_outputs(outs)
+        for name, t in (("left", d_left), ("right", d_right)):
+            self._dev_check(t, name, n_pairs * w * h * channels, "uint8")
+        o = self._dev_outputs(outs, n_pairs * w * h)
         self._ck(self.lib.sb200_pipeline_batch_dev(self.h, C.byref(p), _ptr(d_left), _ptr(d_right), channels, w, h,
                                                    n_pairs, C.byref(o)))
 
     def pipeline_strip_dev(self, d_left, d_right, channels, w, strip, outs, params=None):
         """strip: dict(y0, rows, halo_top, halo_bot, frame_h)"""
         p = params or default_params()
-        o = self._dev_outputs(outs)
         s = _Strip(**strip)
+        held = s.halo_top + s.rows + s.halo_bot
+        for name, t in (("left", d_left), ("right", d_right)):
+            self._dev_check(t, name, held * w * channels, "uint8")
+        o = self._dev_outputs(outs, s.rows * w)
         self._ck(self.lib.sb200_pipeline_strip_dev(self.h, C.byref(p), _ptr(d_left), _ptr(d_right), channels, w,
                                                    C.byref(s), C.byref(o)))
+
+    def pipeline_strips_nccl(self, comm, d_own_left, d_own_right, channels, w, frame_h, y0, rows, outs, params=None):
+        """this rank's rows [y0, y0+rows) of a frame_h-row frame (device tensors) -> outputs for those rows; the halo rows
+        come from the neighbouring ranks over NCCL inside the call.  comm: sharding.NcclComm (or a raw ncclComm_t int)."""
+        p = params or default_params()
+        for name, t in (("left", d_own_left), ("right", d_own_right)):
+            self._dev_check(t, name, rows * w * channels, "uint8")
+        o = self._dev_outputs(outs, rows * w)
+        handle, rank, world = (comm.handle, comm.rank, comm.world) if hasattr(comm, "handle") else comm
+        self._ck(self.lib.sb200_pipeline_strips_nccl(self.h, C.byref(p), handle, rank, world, _ptr(d_own_left),
+                                                     _ptr(d_own_right), channels, w, frame_h, y0, rows, C.byref(o)))
+
+    def strip_rows(self, frame_h, rank, world):
+        y0, rows = C.c_int(), C.c_int()
+        self._ck(self.lib.sb200_strip_rows(frame_h, rank, world, C.byref(y0), C.byref(rows)))
+        return y0.value, rows.value
 
     def strip_halo_rows(self, params=None):
         p = params or default_params()
@@ -375,16 +446,26 @@ class Context:
 
     def view_disparity_dev(self, d_guide, d_other, w, h, dmin, size_d, d_best, d_disp, d_mean=None, params=None):
         p = params or default_params()
+        for name, t, dt in (("guide", d_guide, "uint8"), ("other", d_other, "uint8"), ("best", d_best, "float32"),
+                            ("disp", d_disp, "float32"), ("mean", d_mean, "uint8")):
+            self._dev_check(t, name, w * h, dt)
         self._ck(self.lib.sb200_view_disparity_dev(self.h, C.byref(p), _ptr(d_guide), _ptr(d_other), w, h, dmin, size_d,
                                                    _ptr(d_best), _ptr(d_disp), _ptr(d_mean)))
 
     def lr_check_fill_dev(self, d_dl, d_dr, w, h, d_occlusion, v_min, d_occ, d_filled, params=None):
         p = params or default_params()
+        for name, t in (("dL", d_dl), ("dR", d_dr), ("occlusion", d_occ), ("filled", d_filled)):
+            self._dev_check(t, name, w * h, "float32")
         self._ck(self.lib.sb200_lr_check_fill_dev(self.h, C.byref(p), _ptr(d_dl), _ptr(d_dr), w, h, d_occlusion,
                                                   float(v_min), _ptr(d_occ), _ptr(d_filled)))
 
     def compute_guided_filter_dev(self, d_i, d_cost, d_filter_cost, d_disp_map, d_mean, w, h, size_d, dmin, params=None):
         p = params or default_params()
+        self._dev_check(d_i, "i", w * h, "uint8")
+        self._dev_check(d_cost, "cost", w * h * size_d, "float32")
+        self._dev_check(d_filter_cost, "filter_cost", w * h, "float32")
+        self._dev_check(d_disp_map, "disp_map", w * h, "float32")
+        self._dev_check(d_mean, "mean", w * h, "uint8")
         self._ck(self.lib.sb200_compute_guided_filter_dev(self.h, C.byref(p), _ptr(d_i), _ptr(d_cost),
                                                           _ptr(d_filter_cost), _ptr(d_disp_map), _ptr(d_mean), w, h,
                                                           size_d, dmin))

@@ -1,5 +1,7 @@
 // api.cu -- the C ABI of include/stereo_b200.h: context, workspace, stage entry points and the
 // fused pipeline.  Host C++ driving CUDA; no torch types, no CPU fallback.
+#include <dlfcn.h>
+
 #include <new>
 
 #include "common.cuh"
@@ -70,6 +72,18 @@ void sb200_ctx_destroy(sb200_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->ev_stream) cudaEventDestroy(ctx->ev_stream);
     if (ctx->ws) cudaFree(ctx->ws);
+    if (ctx->stage) cudaFree(ctx->stage);
+    if (ctx->batch_ready) {
+        cudaStreamSynchronize(ctx->s_in);
+        cudaStreamSynchronize(ctx->s_out);
+        cudaStreamDestroy(ctx->s_in);
+        cudaStreamDestroy(ctx->s_out);
+        for (int i = 0; i < 2; i++) {
+            cudaEventDestroy(ctx->ev_in[i]);
+            cudaEventDestroy(ctx->ev_comp[i]);
+            cudaEventDestroy(ctx->ev_out[i]);
+        }
+    }
     if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->ev_valid)
         for (int i = 0; i < 5; i++) cudaEventDestroy(ctx->ev[i]);
@@ -330,20 +344,26 @@ size_t rgb_fused_ws_bytes(const sb200_ctx* ctx, int w, int h_held, int rows_out,
                                 : sbf_rgb_workspace_bytes(ctx, w, h_held, rows_out, dabs, size_d);
 }
 
+// arena bytes pipeline_core needs for one call
+size_t pipeline_ws_bytes(const sb200_ctx* ctx, const sb200_params* p, int w, const SbFusedGeom& g) {
+    const int size_d = p->dmax - p->dmin + 1;
+    const size_t n_held = (size_t)w * g.h, n_out = (size_t)w * g.rows_out;
+    const int dabs = max(abs(p->dmin), abs(p->dmax));
+    size_t bytes = p->guide_mode != SB200_GUIDE_RGB
+                       ? (sbf_fused_supported(p) ? sbf_workspace_bytes(ctx, w, g.h, g.rows_out, dabs, size_d, 2) : gf_ws_bytes(n_held) + 2 * sb_align(n_held))
+                       : (p->box_mode == SB200_BOX_SAT ? rgb_ws_bytes(n_held) : rgb_fused_ws_bytes(ctx, w, g.h, g.rows_out, dabs, size_d));
+    bytes += 2 * sb_align(n_held) + 4 * sb_align(n_out * 4) + 4096;
+    if (g.rows_out != g.h) bytes += 2 * sb_align(n_held);  // strips stage the mean images on held rows
+    return bytes;
+}
+
 // pipeline core on device buffers; `held` geometry for strips
 int pipeline_core(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, const uint8_t* d_right, int channels,
                   int w, const SbFusedGeom& g, const sb200_outputs* o, bool reserve) {
     const int size_d = p->dmax - p->dmin + 1;
     const size_t n_held = (size_t)w * g.h;
     const size_t n_out = (size_t)w * g.rows_out;
-    const int dabs = max(abs(p->dmin), abs(p->dmax));
-    if (reserve) {
-        size_t bytes = p->guide_mode != SB200_GUIDE_RGB ? (sbf_fused_supported(p) ? sbf_workspace_bytes(ctx, w, g.h, g.rows_out, dabs, size_d, 2) : gf_ws_bytes(n_held) + 2 * sb_align(n_held))
-                       : (p->box_mode == SB200_BOX_SAT ? rgb_ws_bytes(n_held) : rgb_fused_ws_bytes(ctx, w, g.h, g.rows_out, dabs, size_d));
-        bytes += 2 * sb_align(n_held) + 4 * sb_align(n_out * 4) + 4096;
-        if (g.rows_out != g.h) bytes += 2 * sb_align(n_held);  // strips stage the mean images on held rows
-        SB_TRY(sb_ws_reserve(ctx, bytes));
-    }
+    if (reserve) SB_TRY(sb_ws_reserve(ctx, pipeline_ws_bytes(ctx, p, w, g)));
     const bool full = (g.rows_out == g.h);
     const bool rgb_guide = (p->guide_mode == SB200_GUIDE_RGB);
     // RGB guide: fused kernel (fused_cvf_rgb.cu); box_mode SAT selects the staged, materialising path instead
@@ -616,6 +636,194 @@ int sb200_pipeline(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h_left,
         if (hf[i]) SB_TRY(d2h(ctx, hf[i], *df[i], n * 4));
     for (int i = 0; i < 4; i++)
         if (hu[i]) SB_TRY(d2h(ctx, hu[i], *du[i], n));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB200_OK;
+}
+
+// ---- row strips over NCCL (what main.cu:44-48's single device becomes on an 8-GPU box) ------------------
+// The library talks to NCCL through dlopen/dlsym: nothing links against it, a process that never calls this entry
+// point never loads it, and the communicator is whatever the host application already has (ncclCommInitRank in a C++
+// host, or the raw communicator sharding.py builds in Python).
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi g_nccl;
+int nccl_load(sb200_ctx* ctx) {
+    if (g_nccl.ok) return SB200_OK;
+    const char* names[] = {getenv("SB200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        if (!nm) continue;
+        g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "libnccl.so.2 not found (set SB200_NCCL_LIB): %s", dlerror());
+    g_nccl.GroupStart = (int (*)())dlsym(g_nccl.lib, "ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())dlsym(g_nccl.lib, "ncclGroupEnd");
+    g_nccl.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclSend");
+    g_nccl.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclRecv");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+    if (!g_nccl.GroupStart || !g_nccl.GroupEnd || !g_nccl.Send || !g_nccl.Recv)
+        return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "libnccl lacks ncclSend/ncclRecv/ncclGroupStart/ncclGroupEnd");
+    g_nccl.ok = true;
+    return SB200_OK;
+}
+#define SB_NCCL(ctx, call)                                                                                   \
+    do {                                                                                                     \
+        int r__ = (call);                                                                                    \
+        if (r__ != 0)                                                                                        \
+            return sb_fail(ctx, SB200_ERR_CUDA, "%s -> NCCL error %d (%s)", #call, r__,                      \
+                           g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "?");                        \
+    } while (0)
+}  // namespace
+
+int sb200_strip_rows(int frame_h, int rank, int world, int* y0, int* rows) {
+    // balanced split, multiples of 4 rows (the fused kernel's row step) except for the last strip
+    if (frame_h < 1 || world < 1 || rank < 0 || rank >= world || !y0 || !rows) return SB200_ERR_INVALID;
+    const int units = (frame_h + 3) / 4;
+    const int base = units / world, extra = units % world;
+    const int u0 = rank * base + (rank < extra ? rank : extra);
+    const int un = base + (rank < extra ? 1 : 0);
+    *y0 = min(frame_h, 4 * u0);
+    *rows = min(frame_h, 4 * (u0 + un)) - *y0;
+    return SB200_OK;
+}
+
+int sb200_pipeline_strips_nccl(sb200_ctx* ctx, const sb200_params* p, void* nccl_comm, int rank, int world,
+                               const uint8_t* d_own_left, const uint8_t* d_own_right, int channels, int w, int frame_h,
+                               int y0, int rows, const sb200_outputs* d_out) {
+    DevGuard dev_guard__(ctx);
+    SB_TRY(check_params(ctx, p));
+    REQUIRE(ctx, d_own_left && d_own_right && d_out && w > 1, "null pointer or empty image");
+    REQUIRE(ctx, channels == 1 || channels >= 3, "channels must be 1 (gray) or >= 3");
+    REQUIRE(ctx, world >= 1 && rank >= 0 && rank < world, "rank outside the communicator");
+    REQUIRE(ctx, rows > 0 && y0 >= 0 && y0 + rows <= frame_h, "strip outside the frame");
+    const int halo = 2 * p->radius;
+    REQUIRE(ctx, world == 1 || rows >= halo, "a strip must be at least 2*radius rows tall (its neighbours need that many)");
+    REQUIRE(ctx, (rank == 0) == (y0 == 0) && (rank == world - 1) == (y0 + rows == frame_h), "strips must tile the frame in rank order");
+    REQUIRE(ctx, world == 1 || nccl_comm, "communicator is NULL");
+    const int top = rank > 0 ? halo : 0, bot = rank < world - 1 ? halo : 0;
+    if (world > 1) SB_TRY(nccl_load(ctx));
+    const size_t row_bytes = (size_t)w * channels;
+    const int held = top + rows + bot;
+    SbFusedGeom g{w, held, top, rows, y0 - top, frame_h};
+    SB_TRY(sb_ws_reserve(ctx, pipeline_ws_bytes(ctx, p, w, g) + 2 * sb_align(row_bytes * held) + 4096));
+    uint8_t *hl, *hr;
+    SB_TRY(ws_get(ctx, &hl, row_bytes * held));
+    SB_TRY(ws_get(ctx, &hr, row_bytes * held));
+    const uint8_t* own[2] = {d_own_left, d_own_right};
+    uint8_t* hld[2] = {hl, hr};
+    for (int i = 0; i < 2; i++)
+        SB_CUDA(ctx, cudaMemcpyAsync(hld[i] + row_bytes * top, own[i], row_bytes * rows, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (world > 1) {
+        // one grouped exchange: 2*radius INPUT rows of both images with each neighbour (ncclUint8 = 1)
+        SB_NCCL(ctx, g_nccl.GroupStart());
+        for (int i = 0; i < 2; i++) {
+            if (top) {
+                SB_NCCL(ctx, g_nccl.Recv(hld[i], row_bytes * top, 1, rank - 1, nccl_comm, ctx->stream));
+                SB_NCCL(ctx, g_nccl.Send(own[i], row_bytes * halo, 1, rank - 1, nccl_comm, ctx->stream));
+            }
+            if (bot) {
+                SB_NCCL(ctx, g_nccl.Send(own[i] + row_bytes * (rows - halo), row_bytes * halo, 1, rank + 1, nccl_comm, ctx->stream));
+                SB_NCCL(ctx, g_nccl.Recv(hld[i] + row_bytes * (top + rows), row_bytes * bot, 1, rank + 1, nccl_comm, ctx->stream));
+            }
+        }
+        SB_NCCL(ctx, g_nccl.GroupEnd());
+    }
+    return pipeline_core(ctx, p, hl, hr, channels, w, g, d_out, false);
+}
+
+// Host pointers, n_pairs pairs, OVERLAPPED: the upload of pair i+1 and the download of pair i-1 run on their own
+// streams under the kernels of pair i (two device staging slots, events between the three streams).  This is what the
+// reference's per-stage cudaMemcpy round trips (guidedFilter.cu:39-56, costVolume.cu:23-53) become on a bus that is
+// 100x slower than HBM.  Host buffers should be page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory): with
+// pageable memory the copies still work but the driver stages them and the overlap is lost.
+int sb200_pipeline_batch(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h_left, const uint8_t* h_right, int channels,
+                         int w, int h, int n_pairs, const sb200_outputs* h_out) {
+    DevGuard dev_guard__(ctx);
+    SB_TRY(check_params(ctx, p));
+    REQUIRE(ctx, h_left && h_right && h_out && w > 1 && h > 0 && n_pairs > 0, "null pointer or empty batch");
+    REQUIRE(ctx, channels == 1 || channels >= 3, "channels must be 1 (gray) or >= 3");
+    const size_t n = (size_t)w * h;
+    if (!ctx->batch_ready) {
+        SB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+        SB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            SB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+            SB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming));
+            SB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
+        }
+        ctx->batch_ready = true;
+    }
+    float* const hf[] = {h_out->disp_left, h_out->disp_right, h_out->occlusion, h_out->filled, h_out->best_left, h_out->best_right};
+    uint8_t* const hu[] = {h_out->gray_left, h_out->gray_right, h_out->mean_left, h_out->mean_right};
+    size_t slot_bytes = 2 * sb_align(n * channels);
+    for (int i = 0; i < 6; i++)
+        if (hf[i]) slot_bytes += sb_align(n * 4);
+    for (int i = 0; i < 4; i++)
+        if (hu[i]) slot_bytes += sb_align(n);
+    if (2 * slot_bytes > ctx->stage_cap) {
+        SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        SB_CUDA(ctx, cudaStreamSynchronize(ctx->s_in));
+        SB_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
+        if (ctx->stage) SB_CUDA(ctx, cudaFree(ctx->stage));
+        ctx->stage = nullptr;
+        ctx->stage_cap = 0;
+        cudaError_t e = cudaMalloc(&ctx->stage, 2 * slot_bytes);
+        if (e != cudaSuccess) return sb_fail(ctx, SB200_ERR_NOMEM, "staging of %zu bytes: %s", 2 * slot_bytes, cudaGetErrorString(e));
+        ctx->stage_cap = 2 * slot_bytes;
+    }
+    // the copy streams start after whatever the caller queued on the compute stream
+    if (ctx->ev_stream) {
+        SB_CUDA(ctx, cudaEventRecord(ctx->ev_stream, ctx->stream));
+        SB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_stream, 0));
+        SB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_stream, 0));
+    }
+    SbFusedGeom g{w, h, 0, h, 0, h};
+    for (int i = 0; i < n_pairs; i++) {
+        const int slot = i & 1;
+        char* base = ctx->stage + (size_t)slot * slot_bytes;
+        uint8_t* dl = reinterpret_cast<uint8_t*>(base);
+        uint8_t* dr = dl + sb_align(n * channels);
+        char* o = reinterpret_cast<char*>(dr) + sb_align(n * channels);
+        sb200_outputs d{};
+        float** const df[] = {&d.disp_left, &d.disp_right, &d.occlusion, &d.filled, &d.best_left, &d.best_right};
+        uint8_t** const du[] = {&d.gray_left, &d.gray_right, &d.mean_left, &d.mean_right};
+        for (int k = 0; k < 6; k++)
+            if (hf[k]) {
+                *df[k] = reinterpret_cast<float*>(o);
+                o += sb_align(n * 4);
+            }
+        for (int k = 0; k < 4; k++)
+            if (hu[k]) {
+                *du[k] = reinterpret_cast<uint8_t*>(o);
+                o += sb_align(n);
+            }
+        // upload pair i once the kernels of pair i-2 are done with this slot's inputs
+        if (i >= 2) SB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_comp[slot], 0));
+        SB_CUDA(ctx, cudaMemcpyAsync(dl, h_left + (size_t)i * n * channels, n * channels, cudaMemcpyHostToDevice, ctx->s_in));
+        SB_CUDA(ctx, cudaMemcpyAsync(dr, h_right + (size_t)i * n * channels, n * channels, cudaMemcpyHostToDevice, ctx->s_in));
+        SB_CUDA(ctx, cudaEventRecord(ctx->ev_in[slot], ctx->s_in));
+        // kernels of pair i: after its upload, and after pair i-2's results have left this slot
+        SB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[slot], 0));
+        if (i >= 2) SB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[slot], 0));
+        SB_TRY(pipeline_core(ctx, p, dl, dr, channels, w, g, &d, true));
+        SB_CUDA(ctx, cudaEventRecord(ctx->ev_comp[slot], ctx->stream));
+        // download the results of pair i
+        SB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp[slot], 0));
+        for (int k = 0; k < 6; k++)
+            if (hf[k]) SB_CUDA(ctx, cudaMemcpyAsync(hf[k] + (size_t)i * n, *df[k], n * 4, cudaMemcpyDeviceToHost, ctx->s_out));
+        for (int k = 0; k < 4; k++)
+            if (hu[k]) SB_CUDA(ctx, cudaMemcpyAsync(hu[k] + (size_t)i * n, *du[k], n, cudaMemcpyDeviceToHost, ctx->s_out));
+        SB_CUDA(ctx, cudaEventRecord(ctx->ev_out[slot], ctx->s_out));
+    }
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SB200_OK;
 }

@@ -33,6 +33,12 @@ struct sb200_ctx {
     bool mma_attr_set = false;
     int gray_kernel = 1;  // gray-guide fused kernel: 0 = warp-shuffle box sums (fused_cvf.cu), 1 = tensor-core box sums (fused_mma.cu)
     cudaEvent_t ev_stream = nullptr;  // orders a new stream after the work queued on the previous one (set_stream)
+    // overlapped host-pointer batch entry (sb200_pipeline_batch): copy streams, per-slot events, device staging
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    bool batch_ready = false;
+    char* stage = nullptr;
+    size_t stage_cap = 0;
     int rgb_kernel = 3;  // RGB-guide fused kernel: 2 = two-stage (fused_cvf_rgb.cu), 3 = three-stage (fused_cvf_rgb3.cu)
 };
 

@@ -12,6 +12,8 @@ Two ways the path shards, both absent from the reference (single device, main.cu
 Everything here is host logic over torch.distributed, so it runs unchanged on the gloo
 backend with CPU tensors (tests/test_sharding_gloo.py) and on NCCL with CUDA tensors.
 """
+import ctypes
+import os
 from typing import List, Tuple
 
 import torch
@@ -23,23 +25,32 @@ def batch_shard(n_pairs: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_pairs, world))
 
 
-def strip_bounds(height: int, world: int, align: int = 64) -> List[Tuple[int, int]]:
-    """[y0, y1) of every rank's output strip.  Boundaries are multiples of `align` rows so that
-    the same global rows start a strip no matter how many ranks there are."""
-    units = (height + align - 1) // align
+def strip_rows(height: int, rank: int, world: int) -> Tuple[int, int]:
+    """(y0, rows) of rank `rank`: the balanced split of sb200_strip_rows (include/stereo_b200.h) -- whole units of 4 rows
+    (the fused kernel's row step), the remainder units dealt to the first ranks, the last strip takes the odd rows."""
+    units = (height + 3) // 4
     base, extra = divmod(units, world)
-    bounds, y = [], 0
+    u0 = rank * base + min(rank, extra)
+    un = base + (1 if rank < extra else 0)
+    y0 = min(height, 4 * u0)
+    return y0, min(height, 4 * (u0 + un)) - y0
+
+
+def strip_bounds(height: int, world: int, halo: int = 0) -> List[Tuple[int, int]]:
+    """[y0, y1) of every rank's output strip.  With `halo` given, every rank raises the same error when the frame is
+    too short for `world` strips of at least `halo` rows (a neighbour could not serve the halo)."""
+    bounds = []
     for r in range(world):
-        n = (base + (1 if r < extra else 0)) * align
-        y1 = min(height, y + n)
-        bounds.append((y, y1))
-        y = y1
+        y0, rows = strip_rows(height, r, world)
+        bounds.append((y0, y0 + rows))
+    if world > 1 and min(y1 - y0 for y0, y1 in bounds) < max(halo, 1):
+        raise ValueError(f"a {height}-row frame cannot be split into {world} strips of at least {max(halo, 1)} rows")
     return bounds
 
 
-def strip_geometry(height: int, rank: int, world: int, halo: int, align: int = 64) -> dict:
+def strip_geometry(height: int, rank: int, world: int, halo: int) -> dict:
     """sb200_strip for this rank: rows held = halo_top + rows + halo_bot"""
-    y0, y1 = strip_bounds(height, world, align)[rank]
+    y0, y1 = strip_bounds(height, world, halo)[rank]
     return dict(y0=y0, rows=y1 - y0, halo_top=min(halo, y0), halo_bot=min(halo, height - y1), frame_h=height)
 
 
@@ -67,12 +78,55 @@ def exchange_halo_rows(own: torch.Tensor, geom: dict, rank: int, world: int, hal
     return torch.cat(parts, 0) if len(parts) > 1 else own
 
 
-def gather_strips(local: torch.Tensor, rank: int, world: int, height: int, align: int = 64, group=None):
+def gather_strips(local: torch.Tensor, rank: int, world: int, height: int, group=None):
     """optional collection of output strips on every rank (ncclAllGather of padded strips)"""
-    bounds = strip_bounds(height, world, align)
+    bounds = strip_bounds(height, world)
     max_rows = max(y1 - y0 for y0, y1 in bounds)
     pad = local.new_zeros((max_rows,) + tuple(local.shape[1:]))
     pad[: local.shape[0]] = local
     out = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(out, pad, group=group)
     return torch.cat([o[: y1 - y0] for o, (y0, y1) in zip(out, bounds)], 0)
+
+
+class NcclComm:
+    """A raw ncclComm_t for sb200_pipeline_strips_nccl, built with ctypes on the libnccl this process already has
+    (torch's): rank 0 draws the unique id, torch.distributed broadcasts its 128 bytes, every rank calls
+    ncclCommInitRank on its current CUDA device.  A C++ host passes its own communicator instead."""
+
+    class _Id(ctypes.Structure):
+        _fields_ = [("internal", ctypes.c_ubyte * 128)]  # (c_char arrays would be cut at the first NUL byte)
+
+    def __init__(self, rank: int, world: int, group=None, lib_path: str = None):
+        self.lib = ctypes.CDLL(lib_path or os.environ.get("SB200_NCCL_LIB") or "libnccl.so.2")
+        self.lib.ncclGetUniqueId.argtypes = [ctypes.POINTER(self._Id)]
+        self.lib.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, self._Id, ctypes.c_int]
+        self.lib.ncclCommDestroy.argtypes = [ctypes.c_void_p]
+        self.lib.ncclGetErrorString.restype = ctypes.c_char_p
+        uid = self._Id()
+        if rank == 0:
+            self._ck(self.lib.ncclGetUniqueId(ctypes.byref(uid)))
+        backend = dist.get_backend(group)
+        dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        t = torch.tensor(list(uid.internal), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, 0, group=group)
+        raw = t.cpu().numpy().tobytes()
+        ctypes.memmove(ctypes.byref(uid), raw, 128)
+        self.handle = ctypes.c_void_p()
+        self.rank, self.world = rank, world
+        self._ck(self.lib.ncclCommInitRank(ctypes.byref(self.handle), world, uid, rank))
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise RuntimeError("NCCL: " + self.lib.ncclGetErrorString(rc).decode())
+
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self.lib.ncclCommDestroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()

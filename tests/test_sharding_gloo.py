@@ -60,15 +60,17 @@ def test_halo_exchange_gloo(world, height):
 
 
 def test_strip_bounds_and_batch_shard():
-    for h, w in ((4320, 8), (1080, 4), (200, 2), (64, 2), (1000, 3)):
-        b = sharding.strip_bounds(h, w)
+    for h, w in ((4320, 8), (1080, 8), (1080, 4), (200, 2), (64, 2), (1000, 3), (288, 8), (4321, 8)):
+        b = sharding.strip_bounds(h, w, halo=18)
         assert b[0][0] == 0 and b[-1][1] == h
         assert all(a[1] == c[0] for a, c in zip(b[:-1], b[1:]))
-        assert all(y0 % 64 == 0 for y0, _ in b)
-    # the same global rows start a strip whatever the rank count: 8-way bounds refine 4-way bounds
-    b4 = {y0 for y0, _ in sharding.strip_bounds(4320, 4)}
-    b8 = {y0 for y0, _ in sharding.strip_bounds(4352, 8)}
-    assert {0} <= b4 and {0} <= b8
+        assert all(y0 % 4 == 0 for y0, _ in b)
+        rows = [y1 - y0 for y0, y1 in b]
+        assert max(rows) - min(rows) <= 7 and min(rows) >= 18  # balanced (1080 rows / 8 ranks used to be 192 vs 120)
+    # a frame too short for the rank count is refused on EVERY rank alike, before any communication
+    for r in range(8):
+        with pytest.raises(ValueError):
+            sharding.strip_geometry(100, r, 8, 18)
     idx = [sharding.batch_shard(64, r, 8) for r in range(8)]
     assert sorted(sum(idx, [])) == list(range(64)) and all(len(i) == 8 for i in idx)
     assert sharding.batch_shard(5, 3, 4) == [3]
