@@ -141,6 +141,16 @@ int sb200_detect_occlusion_dev(sb200_ctx* ctx, const sb200_params* p, float* d_d
                                int w, int h);
 int sb200_fill_occlusion_dev(sb200_ctx* ctx, float* d_disparity, int w, int h, float vMin);
 
+/* ---- 8-bit visualisation (main.cu:13-35 write_mat, occlusion.cu:230-237 flToCh2OnGPU) ---------------------------
+ * write_mat: out = (uchar)(int)((v - min) * 255 / (max - min)) with the reference's sequential min/max scan, whose
+ * `else if` never considers a value that raises the running maximum as a minimum; the device version reproduces that
+ * with a prefix-max, so a driver can download 8-bit images instead of float maps.  The reference writes the PNG itself
+ * (stb); here the caller gets the 8-bit image. */
+int sb200_write_mat(sb200_ctx* ctx, const float* h_mat, uint8_t* h_out, int w, int h);
+int sb200_write_mat_dev(sb200_ctx* ctx, const float* d_mat, uint8_t* d_out, int w, int h);
+/* flToCh2OnGPU: result = min(255, (uchar)(160 * (pix - vmin) / (vmax - vmin))) */
+int sb200_fl_to_ch2_dev(sb200_ctx* ctx, const float* d_image, uint8_t* d_result, int vmin, int vmax, int len);
+
 /* ---- fused pipeline (replaces main.cu:65-155 as one call) -------------------------------- */
 /* Outputs; any pointer may be NULL.  All arrays are w*h (w*rows for a row strip, n_pairs*w*h for a batch). */
 typedef struct sb200_outputs {

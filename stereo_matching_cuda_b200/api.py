@@ -108,6 +108,9 @@ def load_library(path=None):
         "sb200_fill_occlusion_dev": (ip, [vp, vp, ip, ip, fp]),
         "sb200_pipeline_dev": (ip, [vp, PP, vp, vp, ip, ip, ip, C.POINTER(_Outputs)]),
         "sb200_pipeline": (ip, [vp, PP, vp, vp, ip, ip, ip, C.POINTER(_Outputs)]),
+        "sb200_write_mat": (ip, [vp, vp, vp, ip, ip]),
+        "sb200_write_mat_dev": (ip, [vp, vp, vp, ip, ip]),
+        "sb200_fl_to_ch2_dev": (ip, [vp, vp, vp, ip, ip, ip]),
         "sb200_pipeline_strips_nccl": (ip, [vp, PP, vp, ip, ip, vp, vp, ip, ip, ip, ip, ip, C.POINTER(_Outputs)]),
         "sb200_strip_rows": (ip, [ip, ip, ip, C.POINTER(ip), C.POINTER(ip)]),
         "sb200_pipeline_batch": (ip, [vp, PP, vp, vp, ip, ip, ip, ip, C.POINTER(_Outputs)]),
@@ -331,6 +334,26 @@ class Context:
     # ---- fused pipeline -----------------------------------------------------------------
     _F32 = ("disp_left", "disp_right", "occlusion", "filled", "best_left", "best_right")
     _U8 = ("gray_left", "gray_right", "mean_left", "mean_right")
+
+    def write_mat(self, mat):
+        """main.cu:13-35: the reference's min/max normalisation of a float map to 8 bits, on the GPU"""
+        mat = _np(mat, np.float32)
+        if mat.ndim != 2:
+            raise StereoB200Error(f"write_mat: expected a 2-D float map, got {mat.shape}")
+        out = np.empty(mat.shape, np.uint8)
+        self._ck(self.lib.sb200_write_mat(self.h, _ptr(mat), _ptr(out), mat.shape[1], mat.shape[0]))
+        return out
+
+    def write_mat_dev(self, d_mat, d_out, w, h):
+        self._dev_check(d_mat, "mat", w * h, "float32")
+        self._dev_check(d_out, "out", w * h, "uint8")
+        self._ck(self.lib.sb200_write_mat_dev(self.h, _ptr(d_mat), _ptr(d_out), w, h))
+
+    def fl_to_ch2_dev(self, d_image, d_result, vmin, vmax, n):
+        """occlusion.cu:230-237 (flToCh2OnGPU)"""
+        self._dev_check(d_image, "image", n, "float32")
+        self._dev_check(d_result, "result", n, "uint8")
+        self._ck(self.lib.sb200_fl_to_ch2_dev(self.h, _ptr(d_image), _ptr(d_result), vmin, vmax, n))
 
     def pipeline(self, left, right, params=None, want=None):
         """main.cu:65-155 as one call on HOST arrays: (h,w[,ch]) uint8 -> dict of numpy arrays"""

@@ -18,7 +18,8 @@ from .api import default_params
 
 
 def write_mat(mat):
-    """main.cu:13-35: min/max scan with its `else if (<=)` quirk, then (v-min)*255/(max-min) truncated"""
+    """main.cu:13-35 on the host (numpy): min/max scan with its `else if (<=)` quirk, then (v-min)*255/(max-min)
+    truncated.  The driver below uses the device version (Context.write_mat); this one is kept as its cross-check."""
     flat = np.ascontiguousarray(mat, np.float32).ravel()
     mx, mn = np.float32(-150000000.0), np.float32(150000000.0)
     # sequential semantics: a value that raises the max is never considered for the min
@@ -53,14 +54,16 @@ def run(left_rgb, right_rgb, dmin=-15, dmax=0, fused=False, device=0):
             ctx.detect_occlusion(occ, dr, dmin - 100, p)                   # main.cu:149-150
             filled = occ.copy()
             ctx.fill_occlusion(filled, dmin)                               # main.cu:153-155
-    tag = f"minus{-dmin}" if dmin < 0 else str(dmin)
-    return {
-        "image_left.png": gl, "image_right.png": gr, "image_mean_left.png": ml, "image_mean_right.png": mr,
-        "best_costl.png": write_mat(bl), "best_costr.png": write_mat(br),
-        f"cost_l{tag}.png": write_mat(costl[0]), f"cost_r{tag}.png": write_mat(costr[0]),
-        "occlu_mapl.png": write_mat(occ), "disparity_mapl.png": write_mat(dl), "disparity_mapr.png": write_mat(dr),
-        "occlu_mapl_filled.png": write_mat(filled),
-    }
+        # main.cu:162-181: the float maps are normalised to 8 bits on the device (sb200_write_mat)
+        wm = ctx.write_mat
+        tag = f"minus{-dmin}" if dmin < 0 else str(dmin)
+        return {
+            "image_left.png": gl, "image_right.png": gr, "image_mean_left.png": ml, "image_mean_right.png": mr,
+            "best_costl.png": wm(bl), "best_costr.png": wm(br),
+            f"cost_l{tag}.png": wm(costl[0]), f"cost_r{tag}.png": wm(costr[0]),
+            "occlu_mapl.png": wm(occ), "disparity_mapl.png": wm(dl), "disparity_mapr.png": wm(dr),
+            "occlu_mapl_filled.png": wm(filled),
+        }
 
 
 def main():

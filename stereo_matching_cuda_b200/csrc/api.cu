@@ -549,6 +549,40 @@ int sb200_view_disparity_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_
     return sbf_view_disparity(ctx, p, d_guide, d_other, g, dmin, size_d, d_best, d_disp, d_mean);
 }
 
+// ---- 8-bit visualisation on the device ----------------------------------------
+int sb200_write_mat_dev(sb200_ctx* ctx, const float* d_mat, uint8_t* d_out, int w, int h) {
+    DevGuard dev_guard__(ctx);
+    REQUIRE(ctx, d_mat && d_out && w > 0 && h > 0, "null pointer or empty image");
+    const size_t n = (size_t)w * h;
+    const size_t nb = (n + 1023) / 1024;
+    SB_TRY(sb_ws_reserve(ctx, sb_align((2 * nb + 2) * 4) + 4096));
+    float* scratch;
+    SB_TRY(ws_get(ctx, &scratch, 2 * nb + 2));
+    return sbk_write_mat(ctx, d_mat, d_out, n, scratch);
+}
+int sb200_write_mat(sb200_ctx* ctx, const float* h_mat, uint8_t* h_out, int w, int h) {
+    DevGuard dev_guard__(ctx);
+    REQUIRE(ctx, h_mat && h_out && w > 0 && h > 0, "null pointer or empty image");
+    const size_t n = (size_t)w * h;
+    const size_t nb = (n + 1023) / 1024;
+    SB_TRY(sb_ws_reserve(ctx, sb_align(n * 4) + sb_align(n) + sb_align((2 * nb + 2) * 4) + 4096));
+    float *d_m, *scratch;
+    uint8_t* d_o;
+    SB_TRY(ws_get(ctx, &d_m, n));
+    SB_TRY(ws_get(ctx, &d_o, n));
+    SB_TRY(ws_get(ctx, &scratch, 2 * nb + 2));
+    SB_TRY(h2d(ctx, d_m, h_mat, n * 4));
+    SB_TRY(sbk_write_mat(ctx, d_m, d_o, n, scratch));
+    SB_TRY(d2h(ctx, h_out, d_o, n));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB200_OK;
+}
+int sb200_fl_to_ch2_dev(sb200_ctx* ctx, const float* d_image, uint8_t* d_result, int vmin, int vmax, int len) {
+    DevGuard dev_guard__(ctx);
+    REQUIRE(ctx, d_image && d_result && len > 0 && vmax != vmin, "null pointer, empty image or max == min");
+    return sbk_fl_to_ch2(ctx, d_image, d_result, vmin, vmax, (size_t)len);
+}
+
 // ---- fused pipeline ---------------------------------------------------------------------
 int sb200_strip_halo_rows(const sb200_params* p) { return p ? 2 * p->radius : 0; }
 

@@ -135,6 +135,8 @@ int sbk_fill_occlusion(sb200_ctx* ctx, float* disp, int w, int h, float vMin);
 int sbk_lr_check_fill(sb200_ctx* ctx, const float* dL, const float* dR, int w, int h, int dOcc, int d_lr, float vMin,
                       float* occ, float* filled);
 int sbk_fill_f32(sb200_ctx* ctx, float* dst, float v, size_t n);
+int sbk_write_mat(sb200_ctx* ctx, const float* mat, uint8_t* out, size_t n, float* scratch);  // scratch: 2*ceil(n/1024)+2 words
+int sbk_fl_to_ch2(sb200_ctx* ctx, const float* image, uint8_t* result, int mn, int mx, size_t len);
 int sbk_rgb_split(sb200_ctx* ctx, const uint8_t* rgb, int ch, float* r, float* g, float* b, size_t n);
 int sbk_rgb_inverse(sb200_ctx* ctx, float* const mu[3], float* const cov[6], size_t n, double eps);
 int sbk_rgb_ab(sb200_ctx* ctx, float* const mu[3], float* const M[6], float* const mIp[3], const float* mp,

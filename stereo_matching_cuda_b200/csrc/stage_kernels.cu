@@ -287,104 +287,128 @@ int sbk_detect_occlusion(sb200_ctx* ctx, float* dL, const float* dR, int dOcc, i
     return SB200_OK;
 }
 
-// Block-wide inclusive max-scan over one value per thread, with a carry from earlier tiles.
-// Returns the scanned value for this thread; *carry_out (same for all threads) is the
-// maximum over the whole tile and the carry.
+// L/R consistency check (occlusion.cu:3-15) + scan-line fill (occlusion.cu:134-176), one image row per block.
+// The reference walks left and right from every occluded pixel; here the nearest valid value at-or-left and at-or-right
+// of every pixel comes from a segmented scan of the row held in shared memory (a gather from the unfilled row, which
+// SURVEY.md A.6 shows is what every schedule of the reference's in-place kernel computes):
+//   1. the rows of dL and dR arrive with coalesced 128-bit loads; the check gathers dR[x+d] from shared memory;
+//   2. every thread owns one contiguous segment of the row (odd length: conflict-free) and finds its right-most and
+//      left-most valid pixel; ONE block scan (two barriers) turns those into the carries from all segments to the left
+//      and to the right; a forward and a backward pass over the own segment then produce the filled values;
+//   3. the filled row leaves with coalesced 128-bit stores.
+// Six block barriers per row whatever its width (the previous version: three per 256-pixel tile and pass, 180 at 8K).
+//   do_check = 0: `dL` is taken as the already-checked map.  occ_out / filled_out may be NULL; dL may alias filled_out.
 #define FILL_THREADS 256
-__device__ __forceinline__ int block_scan_max(int v, int carry, int* swarp, int* carry_out) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+__global__ void __launch_bounds__(FILL_THREADS)
+k_lr_check_fill(const float* dL, const float* __restrict__ dR, int w, int seg, int dOcc, int d_lr, float vMin,
+                float* occ_out, float* filled_out, int do_check) {
+    extern __shared__ __align__(16) float srow[];  // [0,w4): the checked row; [w4, 2 w4): dR, later the filled row
+    const int w4 = (w + 3) & ~3;
+    float* sv = srow;
+    float* so = srow + w4;
+    __shared__ int s_hi[FILL_THREADS / 32], s_lo[FILL_THREADS / 32];
+    const int y = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const size_t base = (size_t)y * w;
+    const bool vec = (w & 3) == 0;
+    // 1. load
+    if (vec) {
+        const float4* l4 = reinterpret_cast<const float4*>(dL + base);
+        const float4* r4 = reinterpret_cast<const float4*>(dR + base);
+        for (int i = tid; i < w / 4; i += FILL_THREADS) {
+            reinterpret_cast<float4*>(sv)[i] = l4[i];
+            if (do_check) reinterpret_cast<float4*>(so)[i] = __ldg(r4 + i);
+        }
+    } else {
+        for (int x = tid; x < w; x += FILL_THREADS) {
+            sv[x] = dL[base + x];
+            if (do_check) so[x] = dR[base + x];
+        }
+    }
+    __syncthreads();
+    if (do_check) {
+        // a pixel's check reads its own dL and gathers dR[x+d]: the checked value can replace dL[x] at once
+        for (int x = tid; x < w; x += FILL_THREADS) {
+            float v = sv[x];
+            const int d = (int)v;
+            if (x + d < 0 || x + d >= w || fabsf((float)d + so[x + d]) > (float)d_lr) v = (float)dOcc;
+            sv[x] = v;
+        }
+        __syncthreads();
+        if (occ_out) {
+            if (vec) {
+                float4* o4 = reinterpret_cast<float4*>(occ_out + base);
+                for (int i = tid; i < w / 4; i += FILL_THREADS) o4[i] = reinterpret_cast<float4*>(sv)[i];
+            } else {
+                for (int x = tid; x < w; x += FILL_THREADS) occ_out[base + x] = sv[x];
+            }
+        }
+    }
+    if (!filled_out) return;
+    // 2. segmented scan: thread t owns [t*seg, min(w, (t+1)*seg))
+    const int x0 = tid * seg, x1 = min(w, x0 + seg);
+    int hi = -1, lo = INT_MAX;  // right-most / left-most valid pixel of the segment
+    for (int x = x0; x < x1; x++)
+        if (sv[x] >= vMin) {
+            hi = x;
+            lo = min(lo, x);
+        }
+    // exclusive scans over the threads: max of hi from the left, min of lo from the right
+    int ph = hi, pl = lo;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
-        int n = __shfl_up_sync(0xffffffffu, v, off);
-        if (lane >= off) v = max(v, n);
+        const int a = __shfl_up_sync(0xffffffffu, ph, off), b2 = __shfl_down_sync(0xffffffffu, pl, off);
+        if (lane >= off) ph = max(ph, a);
+        if (lane + off < 32) pl = min(pl, b2);
     }
-    if (lane == 31) swarp[wid] = v;
+    if (lane == 31) s_hi[wid] = ph;
+    if (lane == 0) s_lo[wid] = pl;
     __syncthreads();
-    if (wid == 0) {
-        int t = lane < FILL_THREADS / 32 ? swarp[lane] : INT_MIN;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            int n = __shfl_up_sync(0xffffffffu, t, off);
-            if (lane >= off) t = max(t, n);
-        }
-        swarp[lane] = t;
+    int carry_l = -1, carry_r = INT_MAX;
+    for (int k = 0; k < FILL_THREADS / 32; k++) {
+        if (k < wid) carry_l = max(carry_l, s_hi[k]);
+        if (k > wid) carry_r = min(carry_r, s_lo[k]);
     }
-    __syncthreads();
-    int pre = wid > 0 ? swarp[wid - 1] : INT_MIN;
-    int total = swarp[FILL_THREADS / 32 - 1];
-    v = max(v, max(pre, carry));
-    *carry_out = max(total, carry);
-    __syncthreads();
-    return v;
-}
-
-// L/R consistency check (occlusion.cu:3-15) + scan-line fill (occlusion.cu:134-176) for one
-// image row per block.  The reference walks left and right from every occluded pixel; here the
-// nearest valid pixel at-or-left and at-or-right of every pixel comes from two block scans
-// over the row held in shared memory (a gather from the unfilled row, which SURVEY.md A.6
-// shows is what every schedule of the reference's in-place kernel computes).
-//   mode bit 0: run the L/R check (else `dL` is taken as the already-checked map)
-//   occ_out / filled_out may be NULL.
-__global__ void __launch_bounds__(FILL_THREADS)
-k_lr_check_fill(const float* dL, const float* __restrict__ dR, int w, int dOcc, int d_lr, float vMin,
-                float* occ_out, float* filled_out, int do_check) {  // dL may alias filled_out (in-place fill)
-    extern __shared__ float srow[];                 // w floats: the (checked) row
-    int* sleft = reinterpret_cast<int*>(srow + w);  // w ints: nearest valid index at-or-left
-    __shared__ int swarp[32];
-    const int y = blockIdx.x;
-    const size_t base = (size_t)y * w;
-    for (int x = threadIdx.x; x < w; x += FILL_THREADS) {
-        float v = dL[base + x];
-        if (do_check) {
-            int d = (int)v;
-            if (x + d < 0 || x + d >= w || fabsf((float)d + dR[base + x + d]) > (float)d_lr) v = (float)dOcc;
-            if (occ_out) occ_out[base + x] = v;
-        }
-        srow[x] = v;
+    {   // inclusive -> exclusive inside the warp
+        const int a = __shfl_up_sync(0xffffffffu, ph, 1), b2 = __shfl_down_sync(0xffffffffu, pl, 1);
+        if (lane > 0) carry_l = max(carry_l, a);
+        if (lane < 31) carry_r = min(carry_r, b2);
+    }
+    const float left0 = carry_l >= 0 ? sv[carry_l] : vMin;
+    const float right0 = carry_r != INT_MAX ? sv[carry_r] : vMin;
+    __syncthreads();  // `so` (dR) is free: every thread is past the check
+    float cur = left0;
+    for (int x = x0; x < x1; x++) {  // nearest valid value at-or-left
+        const float v = sv[x];
+        if (v >= vMin) cur = v;
+        so[x] = cur;
+    }
+    cur = right0;
+    for (int x = x1 - 1; x >= x0; x--) {  // nearest valid value at-or-right, and the fill
+        const float v = sv[x];
+        if (v >= vMin) cur = v;
+        const int dX = (int)v;  // occlusion.cu:140-142: the self test uses the truncated int
+        so[x] = ((float)dX >= vMin) ? v : fmaxf(so[x], cur);
     }
     __syncthreads();
-    if (!filled_out) return;
-    // forward: nearest valid (v >= vMin) index at-or-left of x
-    int carry = INT_MIN;
-    for (int t0 = 0; t0 < w; t0 += FILL_THREADS) {
-        int x = t0 + threadIdx.x;
-        int v = (x < w && srow[x] >= vMin) ? x : INT_MIN;
-        int nc;
-        v = block_scan_max(v, carry, swarp, &nc);
-        carry = nc;
-        if (x < w) sleft[x] = v;
-    }
-    // backward: nearest valid index at-or-right, as a max-scan over -x from the right end
-    carry = INT_MIN;
-    for (int t0 = 0; t0 < w; t0 += FILL_THREADS) {
-        int x = w - 1 - (t0 + threadIdx.x);
-        int v = (x >= 0 && srow[x] >= vMin) ? -x : INT_MIN;
-        int nc;
-        v = block_scan_max(v, carry, swarp, &nc);
-        carry = nc;
-        if (x >= 0) {
-            float self = srow[x];
-            float out = self;
-            int dX = (int)self;  // occlusion.cu:140-142: the self test uses the truncated int
-            if (!((float)dX >= vMin)) {
-                int l = sleft[x];
-                float dLeft = (l >= 0) ? srow[l] : vMin;
-                float dRight = (v != INT_MIN) ? srow[-v] : vMin;
-                out = fmaxf(dLeft, dRight);
-            }
-            filled_out[base + x] = out;
-        }
+    // 3. store
+    if (vec) {
+        float4* o4 = reinterpret_cast<float4*>(filled_out + base);
+        for (int i = tid; i < w / 4; i += FILL_THREADS) o4[i] = reinterpret_cast<float4*>(so)[i];
+    } else {
+        for (int x = tid; x < w; x += FILL_THREADS) filled_out[base + x] = so[x];
     }
 }
 
 static int launch_lr(sb200_ctx* ctx, const float* dL, const float* dR, int w, int h, int dOcc, int d_lr, float vMin,
                      float* occ, float* filled, int do_check) {
-    size_t smem = (size_t)w * 8;
+    const size_t smem = (size_t)((w + 3) & ~3) * 8;
     if (smem > ctx->smem_optin)
         return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "row of %d pixels does not fit shared memory", w);
     if (smem > 48 * 1024)
         SB_CUDA(ctx, cudaFuncSetAttribute(k_lr_check_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SB_LAUNCH(ctx, k_lr_check_fill, h, FILL_THREADS, smem, dL, dR, w, dOcc, d_lr, vMin, occ, filled, do_check);
+    int seg = (w + FILL_THREADS - 1) / FILL_THREADS;
+    seg |= 1;  // odd segment length: the threads' strided shared-memory accesses fall on different banks
+    SB_LAUNCH(ctx, k_lr_check_fill, h, FILL_THREADS, smem, dL, dR, w, seg, dOcc, d_lr, vMin, occ, filled, do_check);
     return SB200_OK;
 }
 
@@ -397,6 +421,125 @@ int sbk_fill_occlusion(sb200_ctx* ctx, float* disp, int w, int h, float vMin) {
 int sbk_lr_check_fill(sb200_ctx* ctx, const float* dL, const float* dR, int w, int h, int dOcc, int d_lr, float vMin,
                       float* occ, float* filled) {
     return launch_lr(ctx, dL, dR, w, h, dOcc, d_lr, vMin, occ, filled, 1);
+}
+
+// ---------------------------------------------------------------------------------------
+// 8-bit visualisation on the device: write_mat's normalisation (main.cu:13-35) and flToCh2OnGPU
+// (occlusion.cu:230-237), so that a driver downloads 8-bit images instead of float maps.
+// write_mat scans sequentially with `if (v > max) max = v; else if (v <= min) min = v;`: a value that RAISES the running
+// maximum is never a candidate for the minimum.  In parallel: max = the global maximum; min = the minimum over the
+// elements that are not strict prefix maxima (element i with v_i > max(init, v_0..v_{i-1})), found with a block-wise
+// prefix-max: per-block maxima, their exclusive scan, then a block scan inside every block.
+#define WM_BLOCK 1024
+__device__ __forceinline__ int wm_key(float v) {  // order-preserving float -> int
+    int i = __float_as_int(v);
+    return i >= 0 ? i : i ^ 0x7FFFFFFF;
+}
+__device__ __forceinline__ float wm_unkey(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7FFFFFFF); }
+__device__ __forceinline__ float wm_block_scan_max(float v, float* swarp, float* total) {  // inclusive, 1024 threads
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        float n = __shfl_up_sync(0xffffffffu, v, off);
+        if (lane >= off) v = fmaxf(v, n);
+    }
+    if (lane == 31) swarp[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+        float t = swarp[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            float n = __shfl_up_sync(0xffffffffu, t, off);
+            if (lane >= off) t = fmaxf(t, n);
+        }
+        swarp[lane] = t;
+    }
+    __syncthreads();
+    if (wid > 0) v = fmaxf(v, swarp[wid - 1]);
+    *total = swarp[31];
+    return v;
+}
+__global__ void __launch_bounds__(WM_BLOCK) k_wm_blockmax(const float* __restrict__ mat, size_t n, float* __restrict__ bmax) {
+    __shared__ float swarp[32];
+    const size_t i = (size_t)blockIdx.x * WM_BLOCK + threadIdx.x;
+    float tot;
+    wm_block_scan_max(i < n ? mat[i] : -INFINITY, swarp, &tot);
+    if (threadIdx.x == 0) bmax[blockIdx.x] = tot;
+}
+// one block: bpre[b] = max(init, bmax[0..b-1]); mm[0] = key(global max), mm[1] = key(min init)
+__global__ void __launch_bounds__(WM_BLOCK) k_wm_scan(const float* __restrict__ bmax, int nb, float* __restrict__ bpre,
+                                                       int* __restrict__ mm) {
+    __shared__ float swarp[32];
+    float carry = -150000000.0f;
+    for (int b0 = 0; b0 < nb; b0 += WM_BLOCK) {
+        const int b = b0 + threadIdx.x;
+        const float v = b < nb ? bmax[b] : -INFINITY;
+        float tot;
+        const float inc = wm_block_scan_max(v, swarp, &tot);
+        // exclusive = max of the inclusive value of the previous thread and the carry
+        __shared__ float sinc[WM_BLOCK];
+        sinc[threadIdx.x] = inc;
+        __syncthreads();
+        const float prev = threadIdx.x > 0 ? sinc[threadIdx.x - 1] : -INFINITY;
+        if (b < nb) bpre[b] = fmaxf(carry, prev);
+        carry = fmaxf(carry, tot);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        mm[0] = wm_key(carry);
+        mm[1] = wm_key(150000000.0f);
+    }
+}
+__global__ void __launch_bounds__(WM_BLOCK) k_wm_min(const float* __restrict__ mat, size_t n, const float* __restrict__ bpre,
+                                                      int* __restrict__ mm) {
+    __shared__ float swarp[32];
+    __shared__ float sinc[WM_BLOCK];
+    __shared__ int smin;
+    if (threadIdx.x == 0) smin = 0x7FFFFFFF;
+    const size_t i = (size_t)blockIdx.x * WM_BLOCK + threadIdx.x;
+    const float v = i < n ? mat[i] : -INFINITY;
+    float tot;
+    sinc[threadIdx.x] = wm_block_scan_max(v, swarp, &tot);
+    __syncthreads();
+    const float before = fmaxf(bpre[blockIdx.x], threadIdx.x > 0 ? sinc[threadIdx.x - 1] : -INFINITY);
+    int key = 0x7FFFFFFF;
+    if (i < n && !(v > before)) key = wm_key(v);  // not a strict prefix maximum: a candidate for the minimum
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, off));
+    if ((threadIdx.x & 31) == 0 && key != 0x7FFFFFFF) atomicMin(&smin, key);
+    __syncthreads();
+    if (threadIdx.x == 0 && smin != 0x7FFFFFFF) atomicMin(&mm[1], smin);
+}
+__global__ void k_wm_scale(const float* __restrict__ mat, size_t n, const int* __restrict__ mm, uint8_t* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float mx = wm_unkey(mm[0]), mn = wm_unkey(mm[1]);
+    const int c = (int)__fdiv_rn(__fmul_rn(__fsub_rn(mat[i], mn), 255.0f), __fsub_rn(mx, mn));
+    out[i] = (unsigned char)c;
+}
+// scratch: (nb + nb) floats + 2 ints, nb = ceil(n / 1024)
+int sbk_write_mat(sb200_ctx* ctx, const float* mat, uint8_t* out, size_t n, float* scratch) {
+    const int nb = sb_div_up((long long)n, WM_BLOCK);
+    float* bmax = scratch;
+    float* bpre = scratch + nb;
+    int* mm = reinterpret_cast<int*>(scratch + 2 * (size_t)nb);
+    SB_LAUNCH(ctx, k_wm_blockmax, nb, WM_BLOCK, 0, mat, n, bmax);
+    SB_LAUNCH(ctx, k_wm_scan, 1, WM_BLOCK, 0, bmax, nb, bpre, mm);
+    SB_LAUNCH(ctx, k_wm_min, nb, WM_BLOCK, 0, mat, n, bpre, mm);
+    SB_LAUNCH(ctx, k_wm_scale, sb_div_up((long long)n, 256), 256, 0, mat, n, mm, out);
+    return SB200_OK;
+}
+// flToCh2OnGPU, occlusion.cu:230-237
+__global__ void k_fl_to_ch2(const float* __restrict__ image, uint8_t* __restrict__ result, int mn, int mx, size_t len) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    const float pix = image[i];
+    const float c = __fdiv_rn(__fmul_rn(160.0f, __fsub_rn(pix, (float)mn)), (float)(mx - mn));
+    result[i] = (c > 255.0f) ? 255 : (unsigned char)c;
+}
+int sbk_fl_to_ch2(sb200_ctx* ctx, const float* image, uint8_t* result, int mn, int mx, size_t len) {
+    EW_LAUNCH(k_fl_to_ch2, len, image, result, mn, mx, len);
+    return SB200_OK;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -167,6 +167,32 @@ def test_occlusion_and_fill_exact(ctx, oracle):
     assert np.all(got[0] == -15) and np.all(got[1] == -3) and np.all(got[3, 8:30] == -2)
 
 
+def test_write_mat_and_fl_to_ch2_on_device(ctx, oracle):
+    """main.cu:13-35 (write_mat) incl. its quirk -- a value that raises the running maximum is never a candidate for the
+    minimum -- and occlusion.cu:230-237 (flToCh2OnGPU), bit-exact against the oracle / the formula."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(11)
+    cases = [rng.random((37, 53), dtype=np.float32) * 100 - 30,
+             np.arange(5000, dtype=np.float32).reshape(50, 100),           # every element raises the maximum: min stays at its init
+             np.arange(5000, dtype=np.float32)[::-1].reshape(50, 100).copy(),
+             rng.integers(-115, 1, (288, 384)).astype(np.float32),          # a disparity map with the occlusion sentinel
+             rng.random((1, 1023), dtype=np.float32), rng.random((1, 1025), dtype=np.float32),
+             (rng.random((1100, 1000), dtype=np.float32) - 0.5) * 7]        # more than 1024 blocks: the scan kernel loops
+    ramp = np.sort(rng.random(3000).astype(np.float32))
+    ramp[1500] = ramp[1499]                                                # a tie with the running maximum is NOT a raise
+    cases.append(ramp.reshape(30, 100))
+    for m in cases:
+        assert np.array_equal(ctx.write_mat(m), oracle.write_mat(m)), m.shape
+    d = torch.from_numpy(cases[3]).cuda()
+    out = torch.empty(d.shape, dtype=torch.uint8, device="cuda")
+    ctx.set_stream(torch.cuda.current_stream())
+    ctx.fl_to_ch2_dev(d, out, -15, 0, d.numel())
+    c = np.float32(160.0) * (cases[3] - np.float32(-15)) / np.float32(15)
+    # (unsigned char) of a float is cvt.rzi on the device: truncation, negatives (the occlusion sentinel) saturate to 0
+    want = np.where(c > 255, 255, np.clip(np.trunc(c), 0, 255)).astype(np.uint8)
+    assert np.array_equal(out.cpu().numpy(), want)
+
+
 # ---- fused pipeline ---------------------------------------------------------------------------
 def test_fused_pipeline_tsukuba(ctx, oracle, tsukuba):
     L, R, gl, gr = tsukuba
