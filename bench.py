@@ -146,54 +146,85 @@ def ncu_traffic(guide="gray"):
         return None
 
 
+def host_threads():
+    """threads the CPU legs use: the cores this process may run on (torchrun's OMP_NUM_THREADS=1 is NOT taken as a limit:
+    the reference shim passes the count to its `omp parallel num_threads(..)` explicitly), at most 32"""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    return max(1, min(32, n))
+
+
+REF_D_SAMPLE = 32  # disparities the CPU legs run (of 256): the same at every --gpus N
+
+
+def cpu_chain(lib, kind, O, L, R, size_d, d_sample, threads, init):
+    """both views over `d_sample` consecutive disparities around the middle band of the synthetic staircase (so that
+    band passes the L/R check and the fill sees a mixed map, not the all-occluded case), then L/R check + fill"""
+    import synth
+
+    h = L.shape[0]
+    centre = int(synth.delta_rows(h, size_d)[h // 2])          # the left label of the middle rows is -centre
+    d_hi = min(0, -centre + d_sample // 2)                     # left view: d in [d_lo, d_hi]
+    d_lo = d_hi - d_sample + 1
+    if kind == "reference":
+        _, dl, _ = lib.view_disparity_cpu(L, R, d_sample, d_lo, init, nthreads=threads)
+        _, dr, _ = lib.view_disparity_cpu(R, L, d_sample, -d_hi, init, nthreads=threads)
+        with quiet_stdout():
+            occ = lib.detect_occlusion_cpu(dl, dr, d_lo - 100)
+        lib.fill_occlusion_cpu(occ, d_lo)
+    else:
+        p = lib.params(box_mode=O.BOX_FAITHFUL, nthreads=threads)
+        _, dl, _, _ = lib.view_disparity(L, R, d_sample, d_lo, p)
+        _, dr, _, _ = lib.view_disparity(R, L, d_sample, -d_hi, p)
+        occ = lib.detect_occlusion(dl, dr, d_lo - 100)
+        lib.fill_occlusion(occ, d_lo)
+    return d_lo, d_hi, float((occ == d_lo - 100).mean())
+
+
 def run_reference(args, w, h, size_d, desc):
-    """CPU arm: the reference's own functions (oracle/_ref) or the oracle port, all host threads."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """CPU arm: the reference's own functions (oracle/_ref) or the oracle port on the host cores.  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
+    threads = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(threads)  # before the OpenMP runtime of the checker library starts
     import _oracle as O
 
-    threads = os.cpu_count() or 1
     if O.ref_available():
         lib, kind = O.load_ref(), "reference"
-        threads = min(threads, lib.max_threads())
     else:
         lib, kind = O.load_oracle(), "port"
-        threads = min(threads, lib.max_threads())
-    d_sample = int(min(size_d, max(8, 2 * threads)))
-    dmin_full = -(size_d - 1)
+    d_sample = min(size_d, REF_D_SAMPLE)
+    threads = min(threads, d_sample)
     L, R = make_inputs(w, h, size_d, 1, 1)[0]
     init = O.load_oracle().best_init()
-
-    def step():
-        # a contiguous block of the disparity range, both views, then L/R check + fill
-        if kind == "reference":
-            bl, dl, _ = lib.view_disparity_cpu(L, R, d_sample, dmin_full, init, nthreads=threads)
-            br, dr, _ = lib.view_disparity_cpu(R, L, d_sample, 0, init, nthreads=threads)
-            with quiet_stdout():
-                occ = lib.detect_occlusion_cpu(dl, dr, dmin_full - 100)
-            lib.fill_occlusion_cpu(occ, dmin_full)
-        else:
-            p = lib.params(box_mode=O.BOX_FAITHFUL, nthreads=threads)
-            bl, dl, _, _ = lib.view_disparity(L, R, d_sample, dmin_full, p)
-            br, dr, _, _ = lib.view_disparity(R, L, d_sample, 0, p)
-            lib.fill_occlusion(lib.detect_occlusion(dl, dr, dmin_full - 100), dmin_full)
-
+    info = None
     for _ in range(args.warmup):
-        step()
+        info = cpu_chain(lib, kind, O, L, R, size_d, d_sample, threads, init)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        info = cpu_chain(lib, kind, O, L, R, size_d, d_sample, threads, init)
     dt = time.perf_counter() - t0
-    cells = 2.0 * w * h * d_sample * args.steps
-    value = cells / dt
-    sample = f"{w}x{h}, {d_sample} of {size_d} disparities (d={dmin_full}..{dmin_full + d_sample - 1}), both views + L/R check + fill"
+    value = 2.0 * w * h * d_sample * args.steps / dt
+    # the reference's own design is single-threaded (BASELINE.md 4): that figure on a quarter of the sample
+    d1 = max(1, d_sample // 4)
+    t1 = time.perf_counter()
+    cpu_chain(lib, kind, O, L, R, size_d, d1, 1, init)
+    v1 = 2.0 * w * h * d1 / (time.perf_counter() - t1)
+    sample = (f"{w}x{h}, {d_sample} of {size_d} disparities (d={info[0]}..{info[1]}, around the staircase's middle band), both "
+              f"views + L/R check + fill ({100 * info[2]:.0f} % of the pixels occluded in the sample)")
     line = {
         "impl": "reference", "metric": "pixel-disparities/sec", "value": value, "unit": "px*d/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": desc + ", gray guide, r=9, eps=6.5025; CPU arm runs a bounded sample: " + sample},
-        "cpu_baseline": {"value": value, "unit": "px*d/s", "cores": threads, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "px*d/s", "cores": threads, "kind": kind, "sample": sample,
+                         "threads_note": "slices run in parallel (OpenMP in oracle/ref_shim.cu around the reference's own "
+                                         "single-threaded functions); the thread count is pinned by this script, not taken "
+                                         "from OMP_NUM_THREADS"},
+        "single_thread": {"value": v1, "unit": "px*d/s", "cores": 1, "sample": f"{d1} disparities of the same block",
+                          "note": "the reference's own design (BASELINE.md 4: single-threaded)"},
         "e2e": {"value": value, "unit": "px*d/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "fps_equiv_full_workload": value / (2.0 * w * h * size_d),
     }
@@ -205,29 +236,51 @@ def cpu_baseline(w, h, size_d):
     import _oracle as O
 
     L, R = make_inputs(w, h, size_d, 1, 1)[0]
-    dmin_full = -(size_d - 1)
-    # ~10-20 s of single-thread work at ~14 M cells/s
-    d_sample = max(1, min(size_d, int(180e6 / (2.0 * w * h))))
+    d_sample = max(1, min(size_d, int(180e6 / (2.0 * w * h))))  # ~10-20 s of single-thread work at ~14 M cells/s
     init = O.load_oracle().best_init()
     if O.ref_available():
         lib, kind = O.load_ref(), "reference"
-        t0 = time.perf_counter()
-        _, dl, _ = lib.view_disparity_cpu(L, R, d_sample, dmin_full, init, nthreads=1)
-        _, dr, _ = lib.view_disparity_cpu(R, L, d_sample, 0, init, nthreads=1)
-        with quiet_stdout():
-            occ = lib.detect_occlusion_cpu(dl, dr, dmin_full - 100)
-        lib.fill_occlusion_cpu(occ, dmin_full)
-        dt = time.perf_counter() - t0
     else:
         lib, kind = O.load_oracle(), "port"
-        p = lib.params(box_mode=O.BOX_FAITHFUL, nthreads=1)
-        t0 = time.perf_counter()
-        _, dl, _, _ = lib.view_disparity(L, R, d_sample, dmin_full, p)
-        _, dr, _, _ = lib.view_disparity(R, L, d_sample, 0, p)
-        lib.fill_occlusion(lib.detect_occlusion(dl, dr, dmin_full - 100), dmin_full)
-        dt = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    info = cpu_chain(lib, kind, O, L, R, size_d, d_sample, 1, init)
+    dt = time.perf_counter() - t0
     return {"value": 2.0 * w * h * d_sample / dt, "unit": "px*d/s", "cores": 1, "kind": kind,
-            "sample": f"{w}x{h}, {d_sample} of {size_d} disparities, both views + L/R check + fill, {dt:.1f} s"}
+            "sample": f"{w}x{h}, {d_sample} of {size_d} disparities (d={info[0]}..{info[1]}), both views + L/R check + fill, {dt:.1f} s"}
+
+
+def reference_gpu_leg(ctx, api):
+    """The reference's OWN GPU path (its unmodified .cu files recompiled for sm_100a, oracle/_ref) timed on this B200 on
+    its two native shapes, with this library's pipeline beside it.  Runs in a child process under a timeout (the
+    reference's rowSum/colSum call __syncthreads after a divergent return)."""
+    import _oracle as O
+
+    if not O.ref_available():
+        return {"unavailable": "oracle/_ref/libref.so not built (needs /root/reference at build time)"}
+    out = {}
+    for name, (w, h) in {"c1_tsukuba_384x288": (384, 288), "c2_bike_3052x1968": (3052, 1968)}.items():
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "time_ref_gpu.py"), str(w), str(h)],
+                               capture_output=True, text=True, timeout=240)
+            ref = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]) if r.returncode == 0 else \
+                {"error": (r.stderr or r.stdout)[-300:]}
+        except Exception as e:  # timeout or no JSON line
+            ref = {"error": repr(e)[:300]}
+        L, R = make_inputs(w, h, 16, 3, 1)[0]
+        p = api.default_params(dmin=-15, dmax=0)
+        want = ("disp_left", "disp_right", "occlusion", "filled", "best_left", "best_right", "mean_left", "mean_right", "gray_left",
+                "gray_right")
+        for _ in range(2):
+            ctx.pipeline(L, R, p, want=want)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            ctx.pipeline(L, R, p, want=want)
+        ours = (time.perf_counter() - t0) / 5
+        out[name] = {"reference_gpu": ref, "ours_host_call_ms": 1e3 * ours,
+                     "speedup_vs_reference_gpu": (ref["ms_per_pair"] / (1e3 * ours)) if "ms_per_pair" in ref else None}
+    out["note"] = ("D=16 (the reference's compile-time D_MIN/D_MAX), RGB inputs, host buffers in and out on both sides: the "
+                   "reference's stage functions copy per call, ours is the blocking sb200_pipeline call with every output map")
+    return out
 
 
 def main():
@@ -241,9 +294,13 @@ def main():
                     help="dp: one pair per step per GPU, weak scaling (default); batch: a fixed batch of 64 pairs "
                          "split over the GPUs (c4); strips: one frame split into row strips with halo exchange (c5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="skip the extra legs of the default line (rgb_guide, batch_c4, "
+                                                           "strips_c5, reference_gpu)")
+    ap.add_argument("--check", action="store_true", help="strips / batch: compare the ranks' outputs with one GPU's whole run "
+                                                         "(always done at 2 GPUs)")
     ap.add_argument("--guide", default="gray", choices=["gray", "rgb"],
-                    help="gray: the reference's only guide mode (fused kernel, parity pinned to its goldens); rgb: colour "
-                         "guided filter of SURVEY A.8, which the reference does not have (staged path, parity unpinned)")
+                    help="gray: the reference's only guide mode (parity pinned to its goldens); rgb: colour guided filter of "
+                         "SURVEY A.8, which the reference does not have (parity against the oracle's port)")
     args = ap.parse_args()
     w, h, size_d, channels, desc = WORKLOADS[args.workload]
     if args.guide == "rgb":
@@ -252,8 +309,6 @@ def main():
     if args.impl == "reference":
         run_reference(args, w, h, size_d, desc)
         return
-
-    import ctypes as C
 
     import torch
     import torch.distributed as dist
@@ -272,37 +327,96 @@ def main():
         if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("NCCL_DEBUG_FILE"):
             os.environ["NCCL_DEBUG_FILE"] = os.path.join("/tmp", "nccl_bench_%h_%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    mode = args.mode or {"c4": "batch", "c5": "strips" if world > 1 else "dp"}.get(args.workload, "dp")
+    mode = args.mode or {"c4": "batch", "c5": "strips"}.get(args.workload, "dp")
+    default_line = args.workload == "c3" and mode == "dp" and args.guide == "gray" and not args.no_legs
 
-    p = api.default_params(dmin=-(size_d - 1), dmax=0, guide_mode=S.GUIDE_RGB if args.guide == "rgb" else S.GUIDE_GRAY)
-    n = w * h
     dev = torch.device("cuda", local)
     ctx = S.Context(local, stream=torch.cuda.current_stream())
     names = ("disp_left", "disp_right", "occlusion", "filled", "best_left", "best_right")
+    pk = peaks()
+    peak_instr = 148 * 128 * pk["sm_max_mhz"] * 1e6  # FP32 lane-instructions/s at the max SM clock
+    comm = sharding.NcclComm(rank, world) if world > 1 else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(step, steps, warmup):
+        """W warm-up steps, then K steps between barrier + synchronize, CUDA events on the launching stream, max over ranks"""
+        for i in range(warmup):
+            step(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launch_count
+        t0 = time.time()
+        e0.record()
+        for i in range(steps):
+            step(i)
+        e1.record()
+        barrier()
+        return allmax(e0.elapsed_time(e1)), ctx.launch_count - l0, t0, time.time()
+
+    def kernel_times(step, n):
+        ctx.enable_timing(True)
+        acc = {"fused_ms": [], "occl_ms": [], "prep_ms": [], "merge_ms": []}
+        for i in range(n):
+            step(i)
+            tm = ctx.last_timing()  # the step's last pair
+            for k in acc:
+                acc[k].append(tm[k])
+        ctx.enable_timing(False)
+        return {k: statistics.mean(v) for k, v in acc.items()}
+
+    def pinned(a):
+        return torch.from_numpy(a).pin_memory()
+
+    def e2e_batch(pairs, p, ch, ww, hh, dd, n_e2e):
+        """the same pairs through sb200_pipeline_batch: page-locked HOST buffers in and out, uploads / kernels / downloads of
+        consecutive pairs overlapped inside the call; everything inside the timed region"""
+        k = len(pairs)
+        hl = pinned(np.stack([pairs[i % k][0] for i in range(n_e2e)]))
+        hr = pinned(np.stack([pairs[i % k][1] for i in range(n_e2e)]))
+        onames = ("disp_left", "disp_right", "occlusion", "filled")
+        h_out = {nm: torch.empty((n_e2e, hh, ww), dtype=torch.float32).pin_memory() for nm in onames}
+        out_np = {nm: t.numpy() for nm, t in h_out.items()}
+        ctx.pipeline_batch(hl.numpy()[:2], hr.numpy()[:2], p, want=onames, out={nm: a[:2] for nm, a in out_np.items()})
+        barrier()
+        t0 = time.perf_counter()
+        ctx.pipeline_batch(hl.numpy(), hr.numpy(), p, want=onames, out=out_np)
+        dt = allmax(time.perf_counter() - t0)
+        return {"value": world * 2.0 * ww * hh * dd * n_e2e / dt, "unit": "px*d/s", "h2d_bytes_per_step": int(2 * ww * hh * ch),
+                "d2h_bytes_per_step": int(4 * ww * hh * 4), "ms_per_step": 1e3 * dt / n_e2e,
+                "api": f"sb200_pipeline_batch ({n_e2e} pairs per call, page-locked host buffers; H2D of pair i+1 and D2H of 4 "
+                       "float maps of pair i-1 overlap the kernels of pair i on their own streams; all inside the timed region)"}
+
+    kernel_name = {1: "k_fused_mma", 0: "k_fused_cvf"}[ctx.gray_kernel]
+
+    # ------------------------------------------------------------------------------------------------ headline leg
+    p = api.default_params(dmin=-(size_d - 1), dmax=0, guide_mode=S.GUIDE_RGB if args.guide == "rgb" else S.GUIDE_GRAY)
     halo = ctx.strip_halo_rows(p)
+    n = w * h
+    strip_info = None
     if mode == "strips":
-        # one frame, rows split over the ranks; every step exchanges the 2*radius input halo rows
-        geom = sharding.strip_geometry(h, rank, world, halo)
+        y0, rows = sharding.strip_rows(h, rank, world)
         n_sets = 2
-        own = make_inputs(w, h, size_d, channels, n_sets, y0=geom["y0"], rows=geom["rows"])
+        own = make_inputs(w, h, size_d, channels, n_sets, y0=y0, rows=rows)
         d_own = [(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)) for a, b in own]
-        outs = {k: torch.empty((geom["rows"], w), dtype=torch.float32, device=dev) for k in names}
-        pairs_per_step, cells_per_step, scaling = 1, 2.0 * w * h * size_d, "strong"
+        outs = {k: torch.empty((rows, w), dtype=torch.float32, device=dev) for k in names}
+        pairs_per_step, cells_per_step, scaling, rows_local = 1, 2.0 * w * h * size_d, "strong", rows
 
         def step(i):
             a, b = d_own[i % n_sets]
-            if world > 1:
-                a = sharding.exchange_halo_rows(a, geom, rank, world, halo)
-                b = sharding.exchange_halo_rows(b, geom, rank, world, halo)
-            ctx.pipeline_strip_dev(a, b, channels, w, geom, outs, p)
+            ctx.pipeline_strips_nccl(comm if comm else (None, 0, 1), a, b, channels, w, h, y0, rows, outs, p)
     else:
         n_sets = 4 if n * size_d < 3e9 else 2
+        rows_local = h
         if mode == "batch":
             total_pairs = 64
             mine = sharding.batch_shard(total_pairs, rank, world)
@@ -324,124 +438,167 @@ def main():
     if rank == 0:
         sampler.start()
     load0 = time.time()
-    for i in range(max(args.warmup, 3)):
-        step(i)
-    barrier()
-    l0 = ctx.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t0 = time.time()
-    e0.record()
-    for i in range(args.steps):
-        step(i)
-    e1.record()
-    barrier()
-    t1 = time.time()
-    ms = e0.elapsed_time(e1)
-    launches = ctx.launch_count - l0
+    ms_max, launches, t0, t1 = timed(step, args.steps, max(args.warmup, 3))
     clocks = sampler.stop(t0, t1, load0) if rank == 0 else None
-    t = torch.tensor([ms, float(launches)], dtype=torch.float64, device=dev)
-    tl = t.clone()
+    tl = torch.tensor([float(launches)], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tl, op=dist.ReduceOp.SUM)
-    ms_max = float(t[0].item())
-    launches_all = int(tl[1].item())
+    launches_all = int(tl.item())
     value = cells_per_step * args.steps / (ms_max * 1e-3)
     pairs_total_per_step = {"dp": world, "batch": 64, "strips": 1}[mode]
-
-    # --- roofline pass: device time of the dominant kernel (k_fused_cvf) from CUDA events the
-    # library records on the launching stream around that kernel, averaged over up to 10 steps
-    ctx.enable_timing(True)
-    fused_ms, occl_ms, prep_ms, merge_ms = [], [], [], []
-    for i in range(min(args.steps, 10)):
-        step(i)
-        tm = ctx.last_timing()  # the step's last pair
-        fused_ms.append(tm["fused_ms"])
-        occl_ms.append(tm["occl_ms"])
-        prep_ms.append(tm["prep_ms"])
-        merge_ms.append(tm["merge_ms"])
-    ctx.enable_timing(False)
-    fk = statistics.mean(fused_ms)
-    rows_local = h if mode != "strips" else sharding.strip_geometry(h, rank, world, halo)["rows"]
+    kt = kernel_times(step, min(args.steps, 10))
+    fk = kt["fused_ms"]
     cells_per_launch = 2.0 * w * rows_local * size_d
+    if mode == "strips":
+        ctx.enable_timing(True)
+        step(0)
+        strip_info = {"halo_rows": halo, "halo_bytes_per_boundary": 2 * halo * w * channels,
+                      "exchange_ms": ctx.last_exchange_ms() if world > 1 else 0.0}
+        ctx.enable_timing(False)
+        strip_info["exchange_ms"] = allmax(strip_info["exchange_ms"])
+        strip_info["exchange_share_of_step"] = strip_info["exchange_ms"] / (ms_max / args.steps)
 
-    # --- end to end through the host-pointer C-ABI call, pinned host buffers, copies timed
     e2e = None
     if mode == "dp":
-        h_in = [(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()) for a, b in pairs]
-        onames = ("disp_left", "disp_right", "occlusion", "filled")
-        h_out = {k: torch.empty((h, w), dtype=torch.float32).pin_memory() for k in onames}
-        o = api._Outputs()
-        for k in onames:
-            setattr(o, k, h_out[k].data_ptr())
+        e2e = e2e_batch(pairs, p, channels, w, h, size_d, max(4, min(args.steps, 12)))
 
-        def e2e_step(i):
-            a, b = h_in[i % n_sets]
-            ctx._ck(ctx.lib.sb200_pipeline(ctx.h, C.byref(p), C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), channels,
-                                           w, h, C.byref(o)))
-
-        for i in range(2):
-            e2e_step(i)
-        barrier()
-        tt0 = time.perf_counter()
-        n_e2e = max(3, min(args.steps, 10))
-        for i in range(n_e2e):
-            e2e_step(i)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - tt0
-        te = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * 2.0 * w * h * size_d * n_e2e / float(te.item()), "unit": "px*d/s",
-               "h2d_bytes_per_step": int(2 * n * channels), "d2h_bytes_per_step": int(4 * n * 4),
-               "ms_per_step": 1e3 * float(te.item()) / n_e2e,
-               "api": "sb200_pipeline (host pointers, pinned, blocking; H2D of the pair and D2H of 4 float maps inside)"}
-
-    # --- the same shape with the RGB guide BASELINE configs[2] names (the reference has no such
-    # mode, so it is reported beside the gray-guide headline rather than instead of it)
-    rgb_extra = None
-    if mode == "dp" and args.guide == "gray" and args.workload == "c3":
+    # ------------------------------------------------------------------------------------------------ extra legs
+    def rgb_leg():
+        """the same shape with the RGB guide BASELINE configs[2] names (not in the reference)"""
         p_rgb = api.default_params(dmin=-(size_d - 1), dmax=0, guide_mode=S.GUIDE_RGB)
         cpairs = make_inputs(w, h, size_d, 3, 2)
         c_in = [(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)) for a, b in cpairs]
-        for i in range(3):
+
+        def rstep(i):
             ctx.pipeline_dev(c_in[i % 2][0], c_in[i % 2][1], 3, w, h, outs, p_rgb)
-        barrier()
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        smp = ClockSampler(local)
+        if rank == 0:
+            smp.start()
+        l0 = time.time()
         n_rgb = max(3, min(args.steps, 10))
-        r0.record()
-        for i in range(n_rgb):
-            ctx.pipeline_dev(c_in[i % 2][0], c_in[i % 2][1], 3, w, h, outs, p_rgb)
-        r1.record()
-        barrier()
-        tr_ms = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tr_ms, op=dist.ReduceOp.MAX)
+        ms, _, a0, a1 = timed(rstep, n_rgb, 3)
+        clk = smp.stop(a0, a1, l0) if rank == 0 else None
+        k_rgb = kernel_times(rstep, 3)["fused_ms"]
+        tr = ncu_traffic("rgb")
+        ms_rgb = ms / n_rgb
+        name = {3: "k_fused_cvf_rgb3", 2: "k_fused_cvf_rgb"}.get(ctx.rgb_kernel, "k_fused_rgb")
+        return {"value": world * 2.0 * w * h * size_d / (ms_rgb * 1e-3), "unit": "px*d/s", "ms_per_step": ms_rgb,
+                "fps": world / (ms_rgb * 1e-3), "target_fps_c3": 247,
+                "roofline": {"bound": "fp32_pipe", "kernel": name, "kernel_ms": k_rgb, "instr_per_cell": 71,
+                             "frac": 71 * 2.0 * w * h * size_d / (k_rgb * 1e-3) / peak_instr,
+                             "traffic": tr.get("dram_bytes_per_launch") if tr else None, "traffic_src": tr.get("src") if tr else None,
+                             "ncu": {k: tr.get(k) for k in ("l1tex_data_pipe_pct", "issue_active_pct", "fma_pipe_pct", "alu_pipe_pct",
+                                                            "kernel_ms_under_ncu")} if tr else None},
+                "e2e": e2e_batch(cpairs, p_rgb, 3, w, h, size_d, 6), "clocks": clk,
+                "note": "colour guided filter of SURVEY A.8 on 3-channel synthetic pairs: BASELINE configs[2] as specified; not in the "
+                        "reference (parity against the oracle's RGB port at full size: tests/test_rgb_guide.py)"}
+
+    def batch_leg():
+        """BASELINE configs[3]: a batch of 64 1080p pairs, D=128, split over the ranks (pair i -> rank i mod N), no communication"""
+        bw, bh, bd = 1920, 1080, 128
+        pb = api.default_params(dmin=-(bd - 1), dmax=0)
+        mine = sharding.batch_shard(64, rank, world)
+        k = min(4, len(mine))
+        bp = [make_inputs(bw, bh, bd, 1, 1, seed0=mine[j])[0] for j in range(k)]
+        b_in = [(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)) for a, b in bp]
+        bo = {nm: torch.empty((bh, bw), dtype=torch.float32, device=dev) for nm in names}
+
+        def bstep(i):
+            for j in range(len(mine)):
+                a, b = b_in[j % k]
+                ctx.pipeline_dev(a, b, 1, bw, bh, bo, pb)
+
+        ms, _, _, _ = timed(bstep, 2, 1)
+        ms /= 2
+        res = {"ms_per_batch": ms, "value": 64 * 2.0 * bw * bh * bd / (ms * 1e-3), "unit": "px*d/s", "fps": 64 / (ms * 1e-3),
+               "scaling": "strong", "pairs": 64, "pairs_per_rank": len(mine), "size_d": bd,
+               "workload": "64 synthetic 1920x1080 pairs, D=128, gray guide; pair i -> rank i mod N, no communication"}
+        if world > 1 and (args.check or world == 2):
+            # pair `mine[0]` of every rank against rank 0's own run of the same pair
+            a, b = b_in[0]
+            ctx.pipeline_dev(a, b, 1, bw, bh, bo, pb)
+            lab = bo["filled"].clone()
+            gathered = [torch.empty_like(lab) for _ in range(world)]
+            dist.all_gather(gathered, lab)
+            if rank == 0:
+                agree = []
+                for r in range(world):
+                    pr = make_inputs(bw, bh, bd, 1, 1, seed0=sharding.batch_shard(64, r, world)[0])[0]
+                    one = ctx.pipeline(pr[0], pr[1], pb, want=("filled",))["filled"]
+                    agree.append(float((gathered[r].cpu().numpy() == one).mean()))
+                res["check"] = {"what": "every rank's first pair, recomputed on rank 0: fraction of identical filled labels", "agreement": agree}
+        return res
+
+    def strips_leg():
+        """BASELINE configs[4]: one 7680x4320 frame, D=512, rows split over the ranks, 18-row input halos over NCCL inside
+        sb200_pipeline_strips_nccl"""
+        sw, sh, sd = 7680, 4320, 512
+        ps = api.default_params(dmin=-(sd - 1), dmax=0)
+        y0, rows = sharding.strip_rows(sh, rank, world)
+        own = make_inputs(sw, sh, sd, 1, 1, y0=y0, rows=rows)[0]
+        a, b = torch.from_numpy(own[0]).to(dev), torch.from_numpy(own[1]).to(dev)
+        so = {nm: torch.empty((rows, sw), dtype=torch.float32, device=dev) for nm in names}
+        cm = comm if comm else (None, 0, 1)
+
+        def sstep(i):
+            ctx.pipeline_strips_nccl(cm, a, b, 1, sw, sh, y0, rows, so, ps)
+
+        ms, _, _, _ = timed(sstep, 2, 1)
+        ms /= 2
         ctx.enable_timing(True)
-        ctx.pipeline_dev(c_in[0][0], c_in[0][1], 3, w, h, outs, p_rgb)
-        k_rgb = ctx.last_timing()["fused_ms"]
+        sstep(0)
+        ex = ctx.last_exchange_ms() if world > 1 else 0.0
+        kms = ctx.last_timing()["fused_ms"]
         ctx.enable_timing(False)
-        ms_rgb = float(tr_ms.item()) / n_rgb
-        rgb_extra = {"value": world * 2.0 * w * h * size_d / (ms_rgb * 1e-3), "unit": "px*d/s", "ms_per_step": ms_rgb,
-                     "fps": world / (ms_rgb * 1e-3), "kernel": "k_fused_cvf_rgb3" if ctx.rgb_kernel == 3 else "k_fused_cvf_rgb", "kernel_ms": k_rgb, "instr_per_cell": 71,
-                     "roofline_frac": 71 * 2.0 * w * h * size_d / (k_rgb * 1e-3) / (148 * 128 * peaks()["sm_max_mhz"] * 1e6),
-                     "note": "colour guided filter of SURVEY A.8 on 3-channel synthetic pairs; not in the reference "
-                             "(parity unpinned; checked against the oracle's RGB port and the eps/3 identity)"}
+        ex, kms = allmax(ex), allmax(kms)
+        res = {"ms_per_frame": ms, "value": 2.0 * sw * sh * sd / (ms * 1e-3), "unit": "px*d/s", "fps": 1e3 / ms, "scaling": "strong",
+               "rows_per_rank": rows, "halo_rows": 18, "halo_bytes_per_boundary": 2 * 18 * sw, "exchange_ms": ex,
+               "exchange_share_of_step": ex / ms, "fused_kernel_ms_max_rank": kms,
+               "lr_check_fill_hbm_GBps": None,
+               "workload": "one synthetic 7680x4320 frame, D=512, gray guide; balanced row strips, 18-row input halos over NCCL "
+                           "(ncclSend/ncclRecv inside sb200_pipeline_strips_nccl), both views + L/R check + fill"}
+        ctx.enable_timing(True)
+        sstep(0)
+        res["lr_check_fill_hbm_GBps"] = 16.0 * sw * rows / (ctx.last_timing()["occl_ms"] * 1e-3) / 1e9
+        ctx.enable_timing(False)
+        if world > 1 and (args.check or world == 2):
+            # the ranks' label maps, gathered, against ONE GPU's run of the whole frame
+            maxr = max(sharding.strip_rows(sh, r, world)[1] for r in range(world))
+            got = {}
+            for nm in ("disp_left", "disp_right", "filled"):
+                pad = torch.zeros((maxr, sw), dtype=torch.float32, device=dev)
+                pad[:rows] = so[nm]
+                parts = [torch.empty_like(pad) for _ in range(world)]
+                dist.all_gather(parts, pad)
+                if rank == 0:
+                    got[nm] = np.concatenate([parts[r][: sharding.strip_rows(sh, r, world)[1]].cpu().numpy() for r in range(world)], 0)
+            if rank == 0:
+                Lf, Rf = make_inputs(sw, sh, sd, 1, 1)[0]
+                whole = ctx.pipeline(Lf, Rf, ps, want=("disp_left", "disp_right", "filled"))
+                res["check"] = {"what": "gathered strips vs one GPU's whole-frame run: fraction of identical labels",
+                                **{nm: float((got[nm] == whole[nm]).mean()) for nm in got}}
+            barrier()
+        return res
+
+    legs = {}
+    if default_line:
+        legs["rgb_guide"] = rgb_leg()
+        legs["batch_c4"] = batch_leg()
+        legs["strips_c5"] = strips_leg()
 
     if rank == 0:
-        pk = peaks()
-        peak_instr = 148 * 128 * pk["sm_max_mhz"] * 1e6  # FP32 lane-instructions/s at the max SM clock
         ipc = INSTR_PER_CELL if args.guide == "gray" else 71
         achieved = ipc * cells_per_launch / (fk * 1e-3)
         tr = ncu_traffic(args.guide)
+        tr_ok = bool(tr) and mode == "dp" and args.workload == "c3"
         line = {
             "metric": "pixel-disparities/sec", "value": value, "unit": "px*d/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
             "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "fps": pairs_total_per_step * args.steps / (ms_max * 1e-3),
             "config": {
-                "workload": desc + f" (dmin={-(size_d - 1)}), " + ("gray guide (the reference's only guide mode; BASELINE configs[2] names an RGB guide, which the reference does not implement: see --guide rgb)" if args.guide == "gray" else "RGB guide (SURVEY A.8; not in the reference)") + ", r=9, eps=6.5025, both views + L/R check + fill; "
+                "workload": desc + f" (dmin={-(size_d - 1)}), " + ("gray guide (the reference's only guide mode; BASELINE configs[2] names an RGB guide, which the reference does not implement: the `rgb_guide` leg of this line is that configuration)" if args.guide == "gray" else "RGB guide (SURVEY A.8; not in the reference)") + ", r=9, eps=6.5025, both views + L/R check + fill; "
                             + {"dp": "1 pair per step per GPU" + ("" if world == 1 else f", {world} GPUs data-parallel over pairs, no communication"),
                                "batch": f"a batch of 64 pairs per step split over {world} GPU(s), no communication",
                                "strips": f"one frame per step split into {world} row strips, {halo}-row input halos exchanged over NCCL send/recv"}[mode],
@@ -450,36 +607,41 @@ def main():
                       "WTA planes, several hundred MB at 1080p D=256) exceeds the 126 MB L2",
             },
             "roofline": {
-                "bound": "fp32_pipe", "kernel": "k_fused_cvf" if args.guide == "gray" else ("k_fused_cvf_rgb3" if ctx.rgb_kernel == 3 else "k_fused_cvf_rgb"), "achieved": achieved / 1e12, "peak": peak_instr / 1e12,
+                "bound": "fp32_pipe", "kernel": kernel_name if args.guide == "gray" else {3: "k_fused_cvf_rgb3", 2: "k_fused_cvf_rgb"}.get(ctx.rgb_kernel, "k_fused_rgb"),
+                "achieved": achieved / 1e12, "peak": peak_instr / 1e12,
                 "unit": "T lane-instr/s", "frac": achieved / peak_instr,
-                "traffic": tr.get("dram_bytes_per_launch") if tr and mode == "dp" and args.workload == "c3" else None,
-                "traffic_src": tr.get("src") if tr and mode == "dp" and args.workload == "c3" else None,
+                "traffic": tr.get("dram_bytes_per_launch") if tr_ok else None,
+                "traffic_src": tr.get("src") if tr_ok else None,
                 "kernel_ms": fk, "instr_per_cell": ipc,
                 "flop_frac": (FLOP_PER_CELL if args.guide == "gray" else 87) * cells_per_launch / (fk * 1e-3) / (2 * peak_instr),
-                "peak_src": f"148 SMs x 128 FP32 lanes x {pk['sm_max_mhz']:.0f} MHz (sm_max_mhz, {pk['src']})",
-                "note": "north_star names the FP32 CUDA-core pipe as this kernel's roofline (no dense contraction; see "
-                        "hbm_frac_of_kernel_time for how little of the kernel's time its DRAM traffic explains)",
-                "hbm_frac_of_kernel_time": (tr["dram_bytes_per_launch"] / (pk["hbm_gbs"] * 1e9)) / (fk * 1e-3) if tr and mode == "dp" and args.workload == "c3" else None,
-                "ncu": {k: tr.get(k) for k in ("l1tex_data_pipe_pct", "issue_active_pct", "fma_pipe_pct", "alu_pipe_pct",
-                                               "kernel_ms_under_ncu")} if tr and mode == "dp" and args.workload == "c3" else None,
-                "ncu_note": "the kernel's busiest unit is the L1TEX/shared-memory data pipe (warp shuffles of the horizontal window "
-                            "sums + 128-bit shared loads of the operand ring), not the FP32 pipe: l1tex_data_pipe_pct is its "
-                            "utilisation in the committed ncu capture",
-                "other_kernels_ms": {"k_prep_x2": statistics.mean(prep_ms), "k_merge_chunks_x2": statistics.mean(merge_ms),
-                                     "k_lr_check_fill": statistics.mean(occl_ms)},
-                "lr_check_fill_hbm": {"bound": "hbm", "achieved": 16.0 * w * rows_local / (statistics.mean(occl_ms) * 1e-3) / 1e9,
-                                      "peak": pk["hbm_gbs"], "unit": "GB/s", "bytes_per_pixel": 16},
+                "peak_src": f"148 SMs x 128 FP32 lanes x {pk['sm_max_mhz']:.0f} MHz (sm_max_mhz, {pk['src']}); FMA-chain micro-benchmark: profiles/r2_fma_chain.txt",
+                "note": "north_star names the FP32 CUDA-core pipe as this kernel's roofline; achieved = 35 algorithmic FP32 "
+                        "instructions per (pixel, disparity) cell (SURVEY 8d) x cells per launch / kernel time.  k_fused_mma takes "
+                        "the four horizontal window sums per cell on the tensor cores (band-matrix MMAs), so it executes fewer "
+                        "FP32 instructions than the algorithmic count",
+                "hbm_frac_of_kernel_time": (tr["dram_bytes_per_launch"] / (pk["hbm_gbs"] * 1e9)) / (fk * 1e-3) if tr_ok else None,
+                "ncu": {k: tr.get(k) for k in ("l1tex_data_pipe_pct", "issue_active_pct", "fma_pipe_pct", "alu_pipe_pct", "tensor_pipe_pct",
+                                               "kernel_ms_under_ncu")} if tr_ok else None,
+                "other_kernels_ms": {"prep_kernels": kt["prep_ms"], "k_merge_chunks_x2": kt["merge_ms"], "k_lr_check_fill": kt["occl_ms"]},
+                "lr_check_fill_hbm": {"bound": "hbm", "achieved": 16.0 * w * rows_local / (kt["occl_ms"] * 1e-3) / 1e9,
+                                      "peak": pk["hbm_gbs"], "unit": "GB/s", "bytes_per_pixel": 16,
+                                      "frac": 16.0 * w * rows_local / (kt["occl_ms"] * 1e-3) / 1e9 / pk["hbm_gbs"]},
             },
             "gpu_launches": launches_all,
             "clocks": clocks,
         }
         if e2e:
             line["e2e"] = e2e
-        if rgb_extra:
-            line["rgb_guide"] = rgb_extra
+        if strip_info:
+            line["strips"] = strip_info
+        line.update(legs)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(w, h, size_d)
+            if default_line:
+                line["reference_gpu"] = reference_gpu_leg(ctx, api)
         print(json.dumps(line))
+    if comm:
+        comm.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

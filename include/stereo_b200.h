@@ -226,6 +226,8 @@ int sb200_lr_check_fill_dev(sb200_ctx* ctx, const sb200_params* p, const float* 
  * sb200_ctx_enable_timing(ctx,1) before the call; adds event records, no syncs) */
 int sb200_ctx_enable_timing(sb200_ctx* ctx, int on);
 int sb200_last_timing(sb200_ctx* ctx, float* ms_prep, float* ms_fused, float* ms_merge, float* ms_occl);
+/* device time of the last sb200_pipeline_strips_nccl call's halo exchange (timing enabled) */
+int sb200_last_exchange_ms(sb200_ctx* ctx, float* ms);
 
 #ifdef __cplusplus
 }

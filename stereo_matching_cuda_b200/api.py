@@ -108,6 +108,7 @@ def load_library(path=None):
         "sb200_fill_occlusion_dev": (ip, [vp, vp, ip, ip, fp]),
         "sb200_pipeline_dev": (ip, [vp, PP, vp, vp, ip, ip, ip, C.POINTER(_Outputs)]),
         "sb200_pipeline": (ip, [vp, PP, vp, vp, ip, ip, ip, C.POINTER(_Outputs)]),
+        "sb200_last_exchange_ms": (ip, [vp, C.POINTER(C.c_float)]),
         "sb200_write_mat": (ip, [vp, vp, vp, ip, ip]),
         "sb200_write_mat_dev": (ip, [vp, vp, vp, ip, ip]),
         "sb200_fl_to_ch2_dev": (ip, [vp, vp, vp, ip, ip, ip]),
@@ -228,6 +229,11 @@ class Context:
         v = [C.c_float() for _ in range(4)]
         self._ck(self.lib.sb200_last_timing(self.h, *[C.byref(x) for x in v]))
         return dict(zip(("prep_ms", "fused_ms", "merge_ms", "occl_ms"), (x.value for x in v)))
+
+    def last_exchange_ms(self):
+        v = C.c_float()
+        self._ck(self.lib.sb200_last_exchange_ms(self.h, C.byref(v)))
+        return v.value
 
     # ---- reference stage functions, host arrays ------------------------------------------
     def rgb_to_grayscale(self, h_rgb, params=None):

@@ -56,6 +56,7 @@ int sb200_ctx_create(int device, sb200_ctx** out) {
     }
     bool ok = true;
     for (int i = 0; i < 5; i++) ok = ok && (cudaEventCreate(&ctx->ev[i]) == cudaSuccess);
+    for (int i = 0; i < 2; i++) ok = ok && (cudaEventCreate(&ctx->ev_x[i]) == cudaSuccess);
     ctx->ev_valid = ok;
     if (cudaEventCreateWithFlags(&ctx->ev_stream, cudaEventDisableTiming) != cudaSuccess) ctx->ev_stream = nullptr;
     // A/B switch for the RGB-guide kernel: "2" = two-stage (fused_cvf_rgb.cu), "3" = three-stage (fused_cvf_rgb3.cu)
@@ -85,8 +86,10 @@ void sb200_ctx_destroy(sb200_ctx* ctx) {
         }
     }
     if (ctx->pin) cudaFreeHost(ctx->pin);
-    if (ctx->ev_valid)
+    if (ctx->ev_valid) {
         for (int i = 0; i < 5; i++) cudaEventDestroy(ctx->ev[i]);
+        for (int i = 0; i < 2; i++) cudaEventDestroy(ctx->ev_x[i]);
+    }
     delete ctx;
 }
 
@@ -139,6 +142,14 @@ int sb200_last_timing(sb200_ctx* ctx, float* ms_prep, float* ms_fused, float* ms
     float* outs[4] = {ms_prep, ms_fused, ms_merge, ms_occl};
     for (int i = 0; i < 4; i++)
         if (outs[i]) SB_CUDA(ctx, cudaEventElapsedTime(outs[i], ctx->ev[i], ctx->ev[i + 1]));
+    return SB200_OK;
+}
+
+int sb200_last_exchange_ms(sb200_ctx* ctx, float* ms) {
+    DevGuard dev_guard__(ctx);
+    if (!ctx || !ctx->ev_valid || !ms) return SB200_ERR_INVALID;
+    SB_CUDA(ctx, cudaEventSynchronize(ctx->ev_x[1]));
+    SB_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev_x[0], ctx->ev_x[1]));
     return SB200_OK;
 }
 
@@ -755,6 +766,7 @@ int sb200_pipeline_strips_nccl(sb200_ctx* ctx, const sb200_params* p, void* nccl
     uint8_t* hld[2] = {hl, hr};
     for (int i = 0; i < 2; i++)
         SB_CUDA(ctx, cudaMemcpyAsync(hld[i] + row_bytes * top, own[i], row_bytes * rows, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev_x[0], ctx->stream));
     if (world > 1) {
         // one grouped exchange: 2*radius INPUT rows of both images with each neighbour (ncclUint8 = 1)
         SB_NCCL(ctx, g_nccl.GroupStart());
@@ -770,6 +782,7 @@ int sb200_pipeline_strips_nccl(sb200_ctx* ctx, const sb200_params* p, void* nccl
         }
         SB_NCCL(ctx, g_nccl.GroupEnd());
     }
+    if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev_x[1], ctx->stream));
     return pipeline_core(ctx, p, hl, hr, channels, w, g, d_out, false);
 }
 

@@ -28,6 +28,7 @@ struct sb200_ctx {
     // optional timing of the pipeline's phases
     int timing = 0;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_x[2] = {nullptr, nullptr};  // around the NCCL halo exchange of sb200_pipeline_strips_nccl
     bool ev_valid = false;
     bool fused_attr_set = false;
     bool mma_attr_set = false;
