@@ -324,8 +324,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         # NCCL_DEBUG=VERSION/INFO makes NCCL print to STDOUT, which would break the one-JSON-line contract
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("NCCL_DEBUG_FILE"):
-            os.environ["NCCL_DEBUG_FILE"] = os.path.join("/tmp", "nccl_bench_%h_%p.log")
+        # (also the version banner of the raw communicator sharding.NcclComm creates): send all of it to a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join("/tmp", "nccl_bench_%h_%p.log"))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     mode = args.mode or {"c4": "batch", "c5": "strips"}.get(args.workload, "dp")
     default_line = args.workload == "c3" and mode == "dp" and args.guide == "gray" and not args.no_legs

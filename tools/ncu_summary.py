@@ -22,7 +22,10 @@ KEYS = [
     "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum",
     "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__sass_inst_executed_op_tmem_ldt.sum",
-    "smsp__sass_inst_executed_op_tmem_stt.sum",
+    "smsp__sass_inst_executed_op_tmem_stt.sum", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum",
+    "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
 ]
 STALLS = ["stall_barrier", "stall_long_sb", "stall_short_sb", "stall_wait", "stall_not_selected", "stall_selected",
           "stall_branch_resolving", "stall_dispatch", "stall_math", "stall_mio", "stall_no_inst"]
@@ -43,7 +46,8 @@ def main():
     lines.append("kernel: %s   (ncu --set full --clock-control none --import-source on; one launch = both views of one pair)"
                  % vals.get("Kernel Name", "?"))
     for k in head:
-        if k in KEYS or ("issue_stalled" in k and k.endswith("per_issue_active.ratio")) or "TriageCompute.l1tex__data_pipe" in k:
+        if k in KEYS or ("issue_stalled" in k and k.endswith("per_issue_active.ratio")) or "TriageCompute.l1tex__data_pipe" in k \
+                or "pipe_tensor_cycles_active" in k:
             lines.append("%-92s %-16s %s" % (k, unit.get(k, ""), vals[k]))
 
     src = ncu(rep, "source")
@@ -77,7 +81,17 @@ def main():
         ops = " ".join(x[1] for x in sel)
         # warp roles by what only they execute: FHFMA = first-stage accumulation, FSETP without shuffles = the merge
         # warps, half->float conversions with shuffles = q, LDTM + STTM with FFMA = coefficients and rings
-        if "FHFMA" in ops:
+        if "UTCHMMA" in ops:
+            role = "MMA issue warp"
+        elif "UBLKCP" in ops:
+            role = "TMA producer warp"
+        elif "HMNMX2" in ops and "UTCHMMA" in vals.get("Kernel Name", "") + "".join(x[1] for x in rows[:0]) or ("HMNMX2" in ops and "k_fused_mma" in vals.get("Kernel Name", "")):
+            role = "role A (cost, exact fp16 pieces)"
+        elif "FHADD" in ops and "k_fused_mma" in vals.get("Kernel Name", ""):
+            role = "role B (box sums, a, b, hi/lo split)"
+        elif "FSETP" in ops and "k_fused_mma" in vals.get("Kernel Name", ""):
+            role = "role C (q, winner-take-all)"
+        elif "FHFMA" in ops:
             role = "stage 0 (cost, first box filter)"
         elif "FSETP" in ops and "SHFL" not in ops:
             role = "stage 3 (merge warps)"
@@ -115,6 +129,10 @@ def main():
             "issue_active_pct": float(vals["smsp__issue_active.avg.pct_of_peak_sustained_active"]),
             "fma_pipe_pct": float(vals["sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"]),
             "alu_pipe_pct": float(vals["sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"]),
+            "tensor_pipe_pct": next((float(vals[k]) for k in head if "pipe_tensor_cycles_active_realtime.avg.pct" in k), None),
+            "smem_pipe_pct": {"lsu": float(vals.get("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "nan")),
+                              "tensor_operands": float(vals.get("l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "nan"))},
+            "kernel": vals.get("Kernel Name", "?"),
             "kernel_ms_under_ncu": t, "registers": float(vals["launch__registers_per_thread"]),
         }, open(jp, "w"), indent=1)
 
