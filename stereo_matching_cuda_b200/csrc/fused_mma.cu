@@ -52,10 +52,12 @@ constexpr int M_NWA = 5;        // role-A warps: one thread per cost column, all
 constexpr int NWB = 4 * MMA_BSPLIT, NWC = 4 * MMA_CSPLIT;  // warps of roles B and C
 constexpr int BD = M_ND / MMA_BSPLIT;                      // disparities per role-B thread
 constexpr int CR = MR / MMA_CSPLIT;                        // rows per role-C thread
-constexpr int M_WARPS = (NWB + NWC + M_NWA + 2 + 3) / 4 * 4;  // + MMA + TMA warps, rounded up to whole warpgroups
+constexpr int M_WARPS = (NWB + NWC + M_NWA + 3 + 3) / 4 * 4;  // + 2 MMA warps + TMA warp, rounded up to whole warpgroups
+constexpr int HR = 2;           // rows per hand-off between the roles: every buffer between two roles is two halves of HR rows
+constexpr int NH = MR / HR;
 constexpr int M_THREADS = 32 * M_WARPS;
 constexpr int M_NOP = 4;        // operand ring (guide rows, a/b statistics, match rows): iterations in flight
-constexpr int M_NGC = 8;        // ring of the output rows' intensities (role C runs behind the others)
+constexpr int M_NGC = 4;        // ring of the output rows' intensities and previous (best,label) (role C runs behind the others)
 constexpr int M_MTC = 42;       // match chunks (4 pixels x 4 shifted copies, 64 B) per row in an operand slot
 constexpr int M_RESUM = 8;      // role C re-sums its ring every M_RESUM iterations (32 rows)
 constexpr float I_CENTER = 128.0f;  // q = mean_a * (I - I_CENTER) + mean(b + I_CENTER * a)
@@ -64,12 +66,16 @@ static_assert((4 * RAD) % MR == 0, "MR must divide the warm-up length");
 constexpr uint32_t GA_ROW = M_KB * 8;             // (I, G, I&15, I&240) as 4 halves per cost column
 constexpr uint32_t GB_ROW = M_TW * 8;             // (mean_I, c2 * scale) per a/b lane
 constexpr uint32_t GC_ROW = M_TW * 2;             // I - I_CENTER as half per output lane
+constexpr uint32_t PB_ROW = M_TW * 8;             // (best,label) of the output lanes after the chunk's previous group
+constexpr uint32_t GC_SLOT = MR * (GC_ROW + PB_ROW), GC_PB = MR * GC_ROW;
 constexpr uint32_t MT_ROW = M_MTC * 64;
 constexpr uint32_t OP_GA = 0, OP_GB = MR * GA_ROW, OP_MT = OP_GB + MR * GB_ROW, OP_BYTES = OP_MT + MR * MT_ROW;
 constexpr uint32_t B1_GROUP = M_KB * 16;          // one N-group (8 columns) of B1: 160 rows x 16 B
-constexpr uint32_t B1_BYTES = 3 * MR * B1_GROUP;  // dP (MR rows), d(lo) (MR), d(hi) (MR)
+constexpr uint32_t B1_HALF = 3 * HR * B1_GROUP;   // per half: dP (HR rows), d(lo) (HR), d(hi) (HR)
+constexpr uint32_t B1_BYTES = NH * B1_HALF;
 constexpr uint32_t B2_GROUP = M_K2 * 16;
-constexpr uint32_t B2_BYTES = 4 * MR * B2_GROUP;  // hi: (row, d-quad) x 2 MR, lo likewise
+constexpr uint32_t B2_HALF = 4 * HR * B2_GROUP;   // per half: hi (row, d-quad) x 2 HR, lo likewise
+constexpr uint32_t B2_BYTES = NH * B2_HALF;
 constexpr uint32_t PR_IL = M_KB * 16;             // a ring slot: P of 8 disparities (halves) per cost column, then the
 constexpr uint32_t PR_SLOT = PR_IL + M_KB * 4;    // row's (I&15, I&240) per cost column (needed again when the row leaves)
 
@@ -78,10 +84,10 @@ struct MSmem {
     unsigned char b2[B2_BYTES];
     unsigned char pring[WIN][PR_SLOT];
     unsigned char op[M_NOP][OP_BYTES];
-    unsigned char gc[M_NGC][MR * GC_ROW];
+    unsigned char gc[M_NGC][GC_SLOT];
     float ry_lut[2][WIN + 1];  // [0][n] = scale/(S*n), [1][n] = 1/(scale*n); [.][0] = 0
     uint64_t op_full[M_NOP], op_empty[M_NOP], gc_full[M_NGC], gc_empty[M_NGC];
-    uint64_t b1_full, b1_empty, d1_full, d1_empty, b2_full, b2_empty, d2_full, d2_empty;
+    uint64_t b1_full[NH], b1_empty[NH], d1_full[NH], d1_empty[NH], b2_full[NH], b2_empty[NH], d2_full[NH], d2_empty[NH];
     uint32_t tmem_base;
 };
 static_assert(sizeof(MSmem) <= 227 * 1024, "shared memory budget");
@@ -159,14 +165,16 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
             mbar_init(bar(&sm.gc_full[i]), 1);
             mbar_init(bar(&sm.gc_empty[i]), NWC);
         }
-        mbar_init(bar(&sm.b1_full), M_NWA);
-        mbar_init(bar(&sm.b1_empty), 1);
-        mbar_init(bar(&sm.d1_full), 1);
-        mbar_init(bar(&sm.d1_empty), NWB);
-        mbar_init(bar(&sm.b2_full), NWB);
-        mbar_init(bar(&sm.b2_empty), 1);
-        mbar_init(bar(&sm.d2_full), 1);
-        mbar_init(bar(&sm.d2_empty), NWC);
+        for (int i = 0; i < NH; i++) {
+            mbar_init(bar(&sm.b1_full[i]), M_NWA);
+            mbar_init(bar(&sm.b1_empty[i]), 1);
+            mbar_init(bar(&sm.d1_full[i]), 1);
+            mbar_init(bar(&sm.d1_empty[i]), NWB);
+            mbar_init(bar(&sm.b2_full[i]), NWB);
+            mbar_init(bar(&sm.b2_empty[i]), 1);
+            mbar_init(bar(&sm.d2_full[i]), 1);
+            mbar_init(bar(&sm.d2_empty[i]), 4);  // one warp per lane quarter finishes a half
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x >= 64 && threadIdx.x < 64 + 2 * (WIN + 1)) {
@@ -209,7 +217,7 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
             }
             tm_wait_st();
             tm_fence_before();
-            named_bar_arrive(1, 128 + 32);  // the MMA warp waits for the band
+            named_bar_arrive(1, 128 + 64);  // the two MMA warps wait for the band
         }
         const int x = xa0 + l;
         const bool xin = x >= 0 && x < A.w;
@@ -218,8 +226,8 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
         const uint32_t td1 = tl + TC_D1 + BD * h, tring = tl + TC_RING + 2 * BD * h;
         const uint32_t b2a = smem_addr(&sm.b2[0]) + (uint32_t)((l >> 3) * 128 + (l & 7) * 16) + (uint32_t)h * (BD / 4) * B2_GROUP;
         const uint32_t ops = smem_addr(&sm.op[0][0]) + OP_GB + (uint32_t)l * 8;
-        const uint32_t mb_d1f = bar(&sm.d1_full), mb_d1e = bar(&sm.d1_empty), mb_b2f = bar(&sm.b2_full),
-                       mb_b2e = bar(&sm.b2_empty), mb_opf = bar(&sm.op_full[0]), mb_ope = bar(&sm.op_empty[0]);
+        const uint32_t mb_d1f = bar(&sm.d1_full[0]), mb_d1e = bar(&sm.d1_empty[0]), mb_b2f = bar(&sm.b2_full[0]),
+                       mb_b2e = bar(&sm.b2_empty[0]), mb_opf = bar(&sm.op_full[0]), mb_ope = bar(&sm.op_empty[0]);
         int K = 0;
         for (int g = 0; g < ngroups; g++) {
             float Sp[BD], Sip[BD], Va[BD], Vb[BD];
@@ -252,26 +260,25 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
                         for (int r = 0; r < MR; r++) r1[r] = rx * inv_rows(sm.ry_lut[0], yi0 + r - RAD, A.y_global0, A.frame_h);
                     }
                 }
-                mbar_wait(mb_d1f, (unsigned)K & 1u);
-                tm_fence_after();
 #pragma unroll
-                for (int half = 0; half < 2; half++) {
+                for (int half = 0; half < NH; half++) {
                     uint32_t dp[2][BD], dip[2][BD], o[2][2 * BD];
                     int slots[2];
+                    mbar_wait(mb_d1f + 8 * half, (unsigned)K & 1u);
+                    tm_fence_after();
 #pragma unroll
                     for (int j = 0; j < 2; j++) {
                         slots[j] = slot;
                         slot = (slot + 1 == WIN) ? 0 : slot + 1;
-                        tm_ldN(td1 + 8 * (2 * half + j), dp[j]);
-                        tm_ldN(td1 + 8 * MR + 8 * (2 * half + j), dip[j]);
+                        tm_ldN(td1 + 16 * HR * half + 8 * j, dp[j]);
+                        tm_ldN(td1 + 16 * HR * half + 8 * HR + 8 * j, dip[j]);
                         tm_ldN(tring + 16 * slots[j], o[j]);  // the (a,b) row that leaves the vertical window
                     }
                     tm_wait_ld();
-                    if (half == 1) {  // all of D1 is in registers: MMA 1 of the next iteration may overwrite it
-                        tm_fence_before();
-                        __syncwarp();
-                        mbar_arrive_lane0(mb_d1e, lane);
-                    }
+                    // this half of D1 is in registers: MMA 1 of the next iteration may overwrite it
+                    tm_fence_before();
+                    __syncwarp();
+                    mbar_arrive_lane0(mb_d1e + 8 * half, lane);
 #pragma unroll
                     for (int j = 0; j < 2; j++) {
                         const int r = 2 * half + j;
@@ -309,7 +316,7 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
                                 }
                             }
                         }
-                        if (r == 0 && K >= 1) mbar_wait(mb_b2e, (unsigned)(K - 1) & 1u);  // MMA 2 of the previous iteration has read B2
+                        if (j == 0 && K >= 1) mbar_wait(mb_b2e + 8 * half, (unsigned)(K - 1) & 1u);  // MMA 2 of the previous iteration has read this half of B2
                         // fp16 hi + lo of the vertical sums: hi - value = -(lo part); MMA 2 takes the lo pass with B negated.
                         // A B2 group (8 columns of D2) = a of 4 disparities, then b of the same 4.
 #pragma unroll
@@ -324,17 +331,17 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
                                 lo[d] = h22u(__floats2half2_rn(fhadd_lo(ha, -a0), fhadd_hi(ha, -a1)));
                                 lo[2 + d] = h22u(__floats2half2_rn(fhadd_lo(hb, -b0), fhadd_hi(hb, -b1)));
                             }
-                            sts128(b2a + (uint32_t)(r * 2 + q) * B2_GROUP, hi[0], hi[1], hi[2], hi[3]);
-                            sts128(b2a + (uint32_t)(2 * MR + r * 2 + q) * B2_GROUP, lo[0], lo[1], lo[2], lo[3]);
+                            sts128(b2a + half * B2_HALF + (uint32_t)(j * 2 + q) * B2_GROUP, hi[0], hi[1], hi[2], hi[3]);
+                            sts128(b2a + half * B2_HALF + (uint32_t)(2 * HR + j * 2 + q) * B2_GROUP, lo[0], lo[1], lo[2], lo[3]);
                         }
                     }
-                }
-                tm_wait_st();
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(mb_b2f);
-                    mbar_arrive(mb_ope + 8 * ko);
+                    tm_wait_st();
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(mb_b2f + 8 * half);
+                        if (half == NH - 1) mbar_arrive(mb_ope + 8 * ko);
+                    }
                 }
             }
         }
@@ -356,20 +363,16 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
         const int band_rows = yb1 - yb0;
         const uint32_t td2 = tl + TC_D2 + 16 * CR * c;
         const uint32_t gcs = smem_addr(&sm.gc[0][0]) + (uint32_t)(CR * c) * GC_ROW + (uint32_t)l * 2;
-        const uint32_t mb_d2f = bar(&sm.d2_full), mb_d2e = bar(&sm.d2_empty), mb_gcf = bar(&sm.gc_full[0]), mb_gce = bar(&sm.gc_empty[0]);
+        const uint32_t pbs = smem_addr(&sm.gc[0][0]) + GC_PB + (uint32_t)(CR * c) * PB_ROW + (uint32_t)l * 8;
+        const uint32_t mb_d2f = bar(&sm.d2_full[0]), mb_d2e = bar(&sm.d2_empty[0]), mb_gcf = bar(&sm.gc_full[0]), mb_gce = bar(&sm.gc_empty[0]);
         int K = 0;
         for (int g = 0; g < ngroups; g++) {
             const float dbase = (float)(dlo + g * M_ND);
             const int dact = min(M_ND, dcnt - g * M_ND);  // disparities of this group that exist
-            const bool ld_ok = (g > 0) && valid;
+            // (best,label) after the chunk's previous group: the TMA producer brings the rows into the ring slot, M_NGC
+            // iterations ahead (a register prefetch with ld.global put its latency on this role's critical path)
+            const bool ld_ok = g > 0;
             const float2 binit = make_float2(BEST_INIT_BITS_F, 0.0f);
-            // (best,label) of this emission's rows, fetched one emission ahead
-            float2 pbN[CR];
-#pragma unroll
-            for (int j = 0; j < CR; j++) {
-                pbN[j] = binit;
-                if (ld_ok && CR * c + j < band_rows) pbN[j] = ld_early_f2(bl0 + (size_t)j * pitchS);
-            }
             float2* blp = bl0;
 #pragma unroll 1
             for (int it = 0; it < niter; it++, K++) {
@@ -379,10 +382,12 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
                 mbar_wait(mb_gcf + 8 * kc, (unsigned)(K / M_NGC) & 1u);
                 if (e < 0) {
                     // warm-up iterations produce no output rows; the barriers still advance in step with the other roles
-                    mbar_wait(mb_d2f, (unsigned)K & 1u);
+#pragma unroll
+                    for (int jj = 0; jj < CR; jj += HR) mbar_wait(mb_d2f + 8 * ((CR * c + jj) / HR), (unsigned)K & 1u);
                     __syncwarp();
                     if (lane == 0) {
-                        mbar_arrive(mb_d2e);
+#pragma unroll
+                        for (int jj = 0; jj < CR; jj += HR) mbar_arrive(mb_d2e + 8 * ((CR * c + jj) / HR));
                         mbar_arrive(mb_gce + 8 * kc);
                     }
                     continue;
@@ -395,27 +400,29 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
                     const bool whole = yg >= RAD && yg + CR - 1 + RAD < A.frame_h;  // the rows' windows are not clipped
 #pragma unroll
                     for (int j = 0; j < CR; j++) {
-                        pb[j] = pbN[j];
-                        pbN[j] = binit;
-                        if (ld_ok && row0 + MR + j < band_rows) pbN[j] = ld_early_f2(blp + (size_t)(MR + j) * pitchS);
+                        pb[j] = binit;
+                        if (ld_ok) {
+                            const uint2 v = lds64(pbs + kc * GC_SLOT + j * PB_ROW);
+                            pb[j] = make_float2(__uint_as_float(v.x), __uint_as_float(v.y));
+                        }
                         rxy[j] = whole ? rxy_whole : rx * inv_rows(sm.ry_lut[1], yb0 + row0 + j, A.y_global0, A.frame_h);
-                        Ic[j] = __half2float(__ushort_as_half((unsigned short)lds16(gcs + kc * (MR * GC_ROW) + j * GC_ROW)));
+                        Ic[j] = __half2float(__ushort_as_half((unsigned short)lds16(gcs + kc * GC_SLOT + j * GC_ROW)));
                         st_ok[j] = valid && row0 + j < band_rows;
                     }
                 }
-                mbar_wait(mb_d2f, (unsigned)K & 1u);
-                tm_fence_after();
 #pragma unroll
-                for (int jj = 0; jj < CR; jj += 2) {
+                for (int jj = 0; jj < CR; jj += HR) {
                     uint32_t hh[2][16];
+                    const int half = (CR * c + jj) / HR;  // CSPLIT == 1: compile-time; CSPLIT == 2: this warp's half
+                    mbar_wait(mb_d2f + 8 * half, (unsigned)K & 1u);
+                    tm_fence_after();
 #pragma unroll
                     for (int j = 0; j < 2; j++) tm_ld16u(td2 + 16 * (jj + j), hh[j]);
                     tm_wait_ld();
-                    if (jj + 2 == CR) {  // this warp's part of D2 is in registers
-                        tm_fence_before();
-                        __syncwarp();
-                        mbar_arrive_lane0(mb_d2e, lane);
-                    }
+                    // this half of D2 is in registers
+                    tm_fence_before();
+                    __syncwarp();
+                    mbar_arrive_lane0(mb_d2e + 8 * half, lane);
 #pragma unroll
                     for (int j2 = 0; j2 < 2; j2++) {
                         const int j = jj + j2;
@@ -453,6 +460,8 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
                     }
                 }
                 blp += (size_t)MR * pitchS;
+                // the stores above are read back by the TMA producer (async proxy) one group later
+                asm volatile("fence.proxy.async.global;" ::: "memory");
                 __syncwarp();
                 mbar_arrive_lane0(mb_gce + 8 * kc, lane);
             }
@@ -472,7 +481,7 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
         const uint32_t pr0 = smem_addr(&sm.pring[0][0]) + (uint32_t)k * 16;
         const uint32_t pi0 = smem_addr(&sm.pring[0][0]) + PR_IL + (uint32_t)k * 4;
         const uint32_t ops = smem_addr(&sm.op[0][0]);
-        const uint32_t mb_opf = bar(&sm.op_full[0]), mb_ope = bar(&sm.op_empty[0]), mb_b1f = bar(&sm.b1_full), mb_b1e = bar(&sm.b1_empty);
+        const uint32_t mb_opf = bar(&sm.op_full[0]), mb_ope = bar(&sm.op_empty[0]), mb_b1f = bar(&sm.b1_full[0]), mb_b1e = bar(&sm.b1_empty[0]);
         int K = 0;
         for (int g = 0; g < ngroups; g++) {
             // ring of P (and of the rows' guide pieces): zero at group start; a thread owns its column of the ring
@@ -520,62 +529,81 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
                     sts128(pr0 + so, pn[0], pn[1], pn[2], pn[3]);
                     sts32(pi0 + so, gn.y);
                     slot = (slot + 1 == WIN) ? 0 : slot + 1;
-                    if (r == 0 && K >= 1) mbar_wait(mb_b1e, (unsigned)(K - 1) & 1u);  // MMA 1 of the previous iteration has read B1
-                    sts128(b1a + (uint32_t)r * B1_GROUP, dp[0], dp[1], dp[2], dp[3]);
-                    sts128(b1a + (uint32_t)(MR + r) * B1_GROUP, dl[0], dl[1], dl[2], dl[3]);
-                    sts128(b1a + (uint32_t)(2 * MR + r) * B1_GROUP, dh[0], dh[1], dh[2], dh[3]);
-                }
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(mb_b1f);
-                    mbar_arrive(mb_ope + 8 * ko);
+                    const int half = r / HR, rr = r % HR;
+                    // MMA 1 of the previous iteration has read this half of B1
+                    if (rr == 0 && K >= 1) mbar_wait(mb_b1e + 8 * half, (unsigned)(K - 1) & 1u);
+                    const uint32_t bh = b1a + half * B1_HALF + (uint32_t)rr * B1_GROUP;
+                    sts128(bh, dp[0], dp[1], dp[2], dp[3]);
+                    sts128(bh + HR * B1_GROUP, dl[0], dl[1], dl[2], dl[3]);
+                    sts128(bh + 2 * HR * B1_GROUP, dh[0], dh[1], dh[2], dh[3]);
+                    if (rr == HR - 1) {
+                        fence_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            mbar_arrive(mb_b1f + 8 * half);
+                            if (r == MR - 1) mbar_arrive(mb_ope + 8 * ko);
+                        }
+                    }
                 }
             }
         }
     } else if (warp == NWB + NWC + M_NWA) {
-        // ================= MMA issue: warp-uniform descriptors, one elected lane =================
-        named_bar_sync(1, 128 + 32);  // the band matrix is in Tensor Memory
+        // ================= MMA 1 issue: warp-uniform descriptors, one elected lane =================
+        // per half: dH_p and dH_lo of HR rows in one N = 16 HR instruction chain, then dH_hi accumulated onto dH_lo
+        named_bar_sync(1, 128 + 64);  // the band matrix is in Tensor Memory
         tm_fence_after();
-        constexpr uint32_t ID64 = instr_desc(8 * 2 * MR, 0), ID32 = instr_desc(8 * MR, 0), ID64N = instr_desc(8 * 2 * MR, 1);
+        constexpr uint32_t IDPL = instr_desc(16 * HR, 0), IDH = instr_desc(8 * HR, 0);
         const uint64_t db1 = smem_desc(smem_addr(&sm.b1[0]), 128, B1_GROUP);
-        const uint64_t db1h = db1 + (uint64_t)((2 * MR * B1_GROUP) >> 4);
-        const uint64_t db2 = smem_desc(smem_addr(&sm.b2[0]), 128, B2_GROUP);
-        const uint64_t db2l = db2 + (uint64_t)((2 * MR * B2_GROUP) >> 4);
-        const uint32_t ta = tmem + TC_BAND, td1 = tmem + TC_D1, td2 = tmem + TC_D2;
-        const uint32_t mb_b1f = bar(&sm.b1_full), mb_b1e = bar(&sm.b1_empty), mb_d1f = bar(&sm.d1_full), mb_d1e = bar(&sm.d1_empty);
-        const uint32_t mb_b2f = bar(&sm.b2_full), mb_b2e = bar(&sm.b2_empty), mb_d2f = bar(&sm.d2_full), mb_d2e = bar(&sm.d2_empty);
-        auto stage2 = [&](int K) {
-            mbar_wait(mb_b2f, (unsigned)K & 1u);
-            if (K >= 1) mbar_wait(mb_d2e, (unsigned)(K - 1) & 1u);
-            tm_fence_after();
-            if (elect_one()) {
-#pragma unroll
-                for (int j = 0; j < M_K2 / 16; j++) umma_ts(td2, ta + 8 * j, db2 + (uint64_t)(j * 16), ID64, j > 0);
-#pragma unroll
-                for (int j = 0; j < M_K2 / 16; j++) umma_ts(td2, ta + 8 * j, db2l + (uint64_t)(j * 16), ID64N, 1);
-                umma_commit(mb_d2f);
-                umma_commit(mb_b2e);
-            }
-            __syncwarp();
-        };
+        const uint32_t ta = tmem + TC_BAND, td1 = tmem + TC_D1;
+        const uint32_t mb_b1f = bar(&sm.b1_full[0]), mb_b1e = bar(&sm.b1_empty[0]), mb_d1f = bar(&sm.d1_full[0]), mb_d1e = bar(&sm.d1_empty[0]);
 #pragma unroll 1
         for (int K = 0; K < Ktotal; K++) {
-            mbar_wait(mb_b1f, (unsigned)K & 1u);
-            if (K >= 1) mbar_wait(mb_d1e, (unsigned)(K - 1) & 1u);
-            tm_fence_after();
-            if (elect_one()) {
 #pragma unroll
-                for (int j = 0; j < M_KB / 16; j++) umma_ts(td1, ta + 8 * j, db1 + (uint64_t)(j * 16), ID64, j > 0);
+            for (int half = 0; half < NH; half++) {
+                mbar_wait(mb_b1f + 8 * half, (unsigned)K & 1u);
+                if (K >= 1) mbar_wait(mb_d1e + 8 * half, (unsigned)(K - 1) & 1u);
+                tm_fence_after();
+                if (elect_one()) {
+                    const uint64_t dpl = db1 + (uint64_t)((half * B1_HALF) >> 4), dh = dpl + (uint64_t)((2 * HR * B1_GROUP) >> 4);
+                    const uint32_t td = td1 + 16 * HR * half;
 #pragma unroll
-                for (int j = 0; j < M_KB / 16; j++) umma_ts(td1 + 8 * MR, ta + 8 * j, db1h + (uint64_t)(j * 16), ID32, 1);
-                umma_commit(mb_d1f);
-                umma_commit(mb_b1e);
+                    for (int j = 0; j < M_KB / 16; j++) umma_ts(td, ta + 8 * j, dpl + (uint64_t)(j * 16), IDPL, j > 0);
+#pragma unroll
+                    for (int j = 0; j < M_KB / 16; j++) umma_ts(td + 8 * HR, ta + 8 * j, dh + (uint64_t)(j * 16), IDH, 1);
+                    umma_commit(mb_d1f + 8 * half);
+                    umma_commit(mb_b1e + 8 * half);
+                }
+                __syncwarp();
             }
-            __syncwarp();
-            if (K >= 1) stage2(K - 1);
         }
-        if (Ktotal > 0) stage2(Ktotal - 1);
+    } else if (warp == NWB + NWC + M_NWA + 2) {
+        // ================= MMA 2 issue (its own warp: never queued behind a wait of MMA 1) =================
+        named_bar_sync(1, 128 + 64);
+        tm_fence_after();
+        constexpr uint32_t ID = instr_desc(16 * HR, 0), IDN = instr_desc(16 * HR, 1);
+        const uint64_t db2 = smem_desc(smem_addr(&sm.b2[0]), 128, B2_GROUP);
+        const uint32_t ta = tmem + TC_BAND, td2 = tmem + TC_D2;
+        const uint32_t mb_b2f = bar(&sm.b2_full[0]), mb_b2e = bar(&sm.b2_empty[0]), mb_d2f = bar(&sm.d2_full[0]), mb_d2e = bar(&sm.d2_empty[0]);
+#pragma unroll 1
+        for (int K = 0; K < Ktotal; K++) {
+#pragma unroll
+            for (int half = 0; half < NH; half++) {
+                mbar_wait(mb_b2f + 8 * half, (unsigned)K & 1u);
+                if (K >= 1) mbar_wait(mb_d2e + 8 * half, (unsigned)(K - 1) & 1u);
+                tm_fence_after();
+                if (elect_one()) {
+                    const uint64_t dhi = db2 + (uint64_t)((half * B2_HALF) >> 4), dlo = dhi + (uint64_t)((2 * HR * B2_GROUP) >> 4);
+                    const uint32_t td = td2 + 16 * HR * half;
+#pragma unroll
+                    for (int j = 0; j < M_K2 / 16; j++) umma_ts(td, ta + 8 * j, dhi + (uint64_t)(j * 16), ID, j > 0);
+#pragma unroll
+                    for (int j = 0; j < M_K2 / 16; j++) umma_ts(td, ta + 8 * j, dlo + (uint64_t)(j * 16), IDN, 1);
+                    umma_commit(mb_d2f + 8 * half);
+                    umma_commit(mb_b2e + 8 * half);
+                }
+                __syncwarp();
+            }
+        }
     } else if (warp == NWB + NWC + M_NWA + 1) {
         // ================= TMA producer (warp-uniform addresses, one elected lane issues) =================
         const char* GAp = reinterpret_cast<const char*>(A.GA[view] + (size_t)strip * A.rows_pad * M_KB);
@@ -593,6 +621,9 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
             const char* ga_src = GAp + row0 * GA_ROW;
             const char* gb_src = GBp + (row0 - RAD) * GB_ROW;
             const char* gc_src = GCp + (row0 - 2 * RAD) * GC_ROW;
+            const char* pb_src = reinterpret_cast<const char*>(A.BL + (size_t)(chunk * 2 + view) * ((size_t)A.rows_out * A.pitchS) +
+                                                               (size_t)(yb0 - A.y_out0) * A.pitchS + xo0);
+            const size_t pb_pitch = (size_t)A.pitchS * 8;
             const char* mt_src = MTp + row0 * mt_pitch + (size_t)i0 * 64;
 #pragma unroll 1
             for (int it = 0; it < niter; it++, K++) {
@@ -609,8 +640,15 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
                 __syncwarp();
                 if (K >= M_NGC) mbar_wait(gc_e + 8 * sc, (unsigned)(K / M_NGC - 1) & 1u);
                 if (elect_one()) {
-                    mbar_expect_tx(gc_f + 8 * sc, MR * GC_ROW);
-                    bulk_g2s(gc_s + sc * (MR * GC_ROW), gc_src, MR * GC_ROW, gc_f + 8 * sc);
+                    const bool pb = g > 0 && it >= WARM_IT;  // rows past the band's end read the plane's padding; they are not used
+                    mbar_expect_tx(gc_f + 8 * sc, MR * GC_ROW + (pb ? MR * PB_ROW : 0u));
+                    bulk_g2s(gc_s + sc * GC_SLOT, gc_src, MR * GC_ROW, gc_f + 8 * sc);
+                    if (pb) {
+#pragma unroll
+                        for (int r = 0; r < MR; r++)
+                            bulk_g2s(gc_s + sc * GC_SLOT + GC_PB + r * PB_ROW, pb_src + (size_t)((it - WARM_IT) * MR + r) * pb_pitch, PB_ROW,
+                                     gc_f + 8 * sc);
+                    }
                 }
                 __syncwarp();
                 ga_src += MR * GA_ROW;
@@ -818,7 +856,7 @@ size_t sbf_mma_workspace_bytes(const sb200_ctx* ctx, int w, int h_held, int rows
     bytes += 2 * sb_align((size_t)plan.n_strips * rows_pad * M_TW * 8);
     bytes += 2 * sb_align((size_t)plan.n_strips * rows_pad * M_TW * 2);
     bytes += 2 * sb_align((size_t)rows_pad * mg.n_chunk * 64);
-    bytes += sb_align((size_t)plan.n_chunks * 2 * rows_out * pitchS * 8);
+    bytes += sb_align(((size_t)plan.n_chunks * 2 * rows_out + MR + 1) * pitchS * 8 + PB_ROW);
     return bytes + 4096;
 }
 
@@ -856,7 +894,7 @@ int sbf_run_fused_mma(sb200_ctx* ctx, const sb200_params* p, const uint8_t* cons
         MT[i] = sb_ws_alloc<uint4>(ctx, (size_t)rows_pad * mg.n_chunk * 4);
     }
     const size_t planeS = (size_t)g.rows_out * pitchS;
-    float2* BL = sb_ws_alloc<float2>(ctx, planeS * 2 * plan.n_chunks);
+    float2* BL = sb_ws_alloc<float2>(ctx, planeS * 2 * plan.n_chunks + (size_t)(MR + 1) * pitchS + M_TW);  // + what a bulk read of the last rows may touch
     if (!GA[0] || !GA[1] || !GB[0] || !GB[1] || !GC[0] || !GC[1] || !MT[0] || !MT[1] || !BL)
         return sb_fail(ctx, SB200_ERR_NOMEM, "fused (mma): workspace arena too small (internal)");
 
