@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libstereo_b200.so")
-SOURCES = ["api.cu", "stage_kernels.cu", "fused_cvf.cu", "fused_mma.cu", "fused_cvf_rgb.cu", "fused_cvf_rgb3.cu"]
+SOURCES = ["api.cu", "stage_kernels.cu", "fused_cvf.cu", "fused_mma.cu", "fused_mma_rgb.cu", "fused_cvf_rgb.cu", "fused_cvf_rgb3.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

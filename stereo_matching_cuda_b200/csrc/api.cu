@@ -59,8 +59,9 @@ int sb200_ctx_create(int device, sb200_ctx** out) {
     for (int i = 0; i < 2; i++) ok = ok && (cudaEventCreate(&ctx->ev_x[i]) == cudaSuccess);
     ctx->ev_valid = ok;
     if (cudaEventCreateWithFlags(&ctx->ev_stream, cudaEventDisableTiming) != cudaSuccess) ctx->ev_stream = nullptr;
-    // A/B switch for the RGB-guide kernel: "2" = two-stage (fused_cvf_rgb.cu), "3" = three-stage (fused_cvf_rgb3.cu)
-    if (const char* e = getenv("SB200_RGB_KERNEL")) ctx->rgb_kernel = (e[0] == '3') ? 3 : (e[0] == '2') ? 2 : ctx->rgb_kernel;
+    // A/B switch for the RGB-guide kernel: "4" = tensor-core (fused_mma_rgb.cu, the default), "3" = three-stage shuffle
+    // kernel (fused_cvf_rgb3.cu), "2" = two-stage (fused_cvf_rgb.cu)
+    if (const char* e = getenv("SB200_RGB_KERNEL")) ctx->rgb_kernel = (e[0] == '4') ? 4 : (e[0] == '3') ? 3 : (e[0] == '2') ? 2 : ctx->rgb_kernel;
     // A/B switch for the gray-guide kernel: "shfl" = warp-shuffle box sums (fused_cvf.cu), "mma" = tensor-core box sums
     if (const char* e = getenv("SB200_GRAY_KERNEL")) ctx->gray_kernel = (e[0] == 's') ? 0 : (e[0] == 'm') ? 1 : ctx->gray_kernel;
     *out = ctx;
@@ -350,9 +351,12 @@ int check_params(sb200_ctx* ctx, const sb200_params* p) {
     return SB200_OK;
 }
 
-size_t rgb_fused_ws_bytes(const sb200_ctx* ctx, int w, int h_held, int rows_out, int dabs, int size_d) {
-    return ctx->rgb_kernel == 3 ? sbf_rgb3_workspace_bytes(ctx, w, h_held, rows_out, dabs, size_d)
-                                : sbf_rgb_workspace_bytes(ctx, w, h_held, rows_out, dabs, size_d);
+// the tensor-core kernel needs a slightly smaller cost lattice than the shuffle kernels (sbf_mma_supported)
+static inline bool rgb_uses_mma(const sb200_ctx* ctx, const sb200_params* p) { return ctx->rgb_kernel == 4 && sbf_rgb_mma_supported(p); }
+size_t rgb_fused_ws_bytes(const sb200_ctx* ctx, const sb200_params* p, int w, int h_held, int rows_out, int dabs, int size_d) {
+    if (rgb_uses_mma(ctx, p)) return sbf_rgb_mma_workspace_bytes(ctx, w, h_held, rows_out, dabs, size_d);
+    return ctx->rgb_kernel == 2 ? sbf_rgb_workspace_bytes(ctx, w, h_held, rows_out, dabs, size_d)
+                                : sbf_rgb3_workspace_bytes(ctx, w, h_held, rows_out, dabs, size_d);
 }
 
 // arena bytes pipeline_core needs for one call
@@ -362,7 +366,7 @@ size_t pipeline_ws_bytes(const sb200_ctx* ctx, const sb200_params* p, int w, con
     const int dabs = max(abs(p->dmin), abs(p->dmax));
     size_t bytes = p->guide_mode != SB200_GUIDE_RGB
                        ? (sbf_fused_supported(p) ? sbf_workspace_bytes(ctx, w, g.h, g.rows_out, dabs, size_d, 2) : gf_ws_bytes(n_held) + 2 * sb_align(n_held))
-                       : (p->box_mode == SB200_BOX_SAT ? rgb_ws_bytes(n_held) : rgb_fused_ws_bytes(ctx, w, g.h, g.rows_out, dabs, size_d));
+                       : (p->box_mode == SB200_BOX_SAT ? rgb_ws_bytes(n_held) : rgb_fused_ws_bytes(ctx, p, w, g.h, g.rows_out, dabs, size_d));
     bytes += 2 * sb_align(n_held) + 4 * sb_align(n_out * 4) + 4096;
     if (g.rows_out != g.h) bytes += 2 * sb_align(n_held);  // strips stage the mean images on held rows
     return bytes;
@@ -417,7 +421,9 @@ int pipeline_core(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, 
         if (mR) SB_TRY(ws_get(ctx, &mRh, n_held));
     }
     if (rgb_guide && !rgb_staged) {
-        if (ctx->rgb_kernel == 3)
+        if (rgb_uses_mma(ctx, p))
+            SB_TRY(sbf_pair_disparity_rgb_mma(ctx, p, d_left, d_right, channels, gl, gr, g, o->best_left, dL, o->best_right, dR));
+        else if (ctx->rgb_kernel != 2)
             SB_TRY(sbf_pair_disparity_rgb3(ctx, p, d_left, d_right, channels, gl, gr, g, o->best_left, dL, o->best_right, dR));
         else
             SB_TRY(sbf_pair_disparity_rgb(ctx, p, d_left, d_right, channels, gl, gr, g, o->best_left, dL, o->best_right, dR));
@@ -657,7 +663,7 @@ int sb200_pipeline(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h_left,
     const int size_d = p->dmax - p->dmin + 1;
     const int dabs = max(abs(p->dmin), abs(p->dmax));
     size_t bytes = (p->guide_mode != SB200_GUIDE_RGB ? (sbf_fused_supported(p) ? sbf_workspace_bytes(ctx, w, h, h, dabs, size_d, 2) : gf_ws_bytes(n) + 2 * sb_align(n))
-                    : (p->box_mode == SB200_BOX_SAT ? rgb_ws_bytes(n) : rgb_fused_ws_bytes(ctx, w, h, h, dabs, size_d))) +
+                    : (p->box_mode == SB200_BOX_SAT ? rgb_ws_bytes(n) : rgb_fused_ws_bytes(ctx, p, w, h, h, dabs, size_d))) +
                    2 * sb_align(n) + 4 * sb_align(n * 4) + 4096;
     bytes += 2 * sb_align(n * channels) + 6 * sb_align(n * 4) + 4 * sb_align(n) + 4096;
     SB_TRY(sb_ws_reserve(ctx, bytes));

@@ -32,6 +32,7 @@ struct sb200_ctx {
     bool ev_valid = false;
     bool fused_attr_set = false;
     bool mma_attr_set = false;
+    bool rgb_mma_attr_set = false;
     int gray_kernel = 1;  // gray-guide fused kernel: 0 = warp-shuffle box sums (fused_cvf.cu), 1 = tensor-core box sums (fused_mma.cu)
     cudaEvent_t ev_stream = nullptr;  // orders a new stream after the work queued on the previous one (set_stream)
     // overlapped host-pointer batch entry (sb200_pipeline_batch): copy streams, per-slot events, device staging
@@ -40,7 +41,8 @@ struct sb200_ctx {
     bool batch_ready = false;
     char* stage = nullptr;
     size_t stage_cap = 0;
-    int rgb_kernel = 3;  // RGB-guide fused kernel: 2 = two-stage (fused_cvf_rgb.cu), 3 = three-stage (fused_cvf_rgb3.cu)
+    int rgb_kernel = 4;  // RGB-guide fused kernel: 4 = tensor-core (fused_mma_rgb.cu), 3 = three-stage shuffle kernel
+                         // (fused_cvf_rgb3.cu), 2 = its two-stage predecessor (fused_cvf_rgb.cu)
 };
 
 extern char g_sb200_global_err[512];
@@ -174,6 +176,12 @@ int sbf_pair_disparity_rgb(sb200_ctx* ctx, const sb200_params* p, const uint8_t*
                            const uint8_t* gray_l, const uint8_t* gray_r, const SbFusedGeom& g, float* bestL, float* dispL,
                            float* bestR, float* dispR);
 // RGB guide, three-stage kernel (fused_cvf_rgb3.cu): same contract
+// tensor-core RGB-guide kernel (fused_mma_rgb.cu); same contract as the rgb3 pair below
+int sbf_rgb_mma_supported(const sb200_params* p);
+size_t sbf_rgb_mma_workspace_bytes(const sb200_ctx* ctx, int w, int h_held, int rows_out, int dabs, int size_d);
+int sbf_pair_disparity_rgb_mma(sb200_ctx* ctx, const sb200_params* p, const uint8_t* rgb_l, const uint8_t* rgb_r, int channels,
+                               const uint8_t* gray_l, const uint8_t* gray_r, const SbFusedGeom& g, float* bestL, float* dispL,
+                               float* bestR, float* dispR);
 size_t sbf_rgb3_workspace_bytes(const sb200_ctx* ctx, int w, int h_held, int rows_out, int dabs, int size_d);
 int sbf_pair_disparity_rgb3(sb200_ctx* ctx, const sb200_params* p, const uint8_t* rgb_l, const uint8_t* rgb_r, int channels,
                             const uint8_t* gray_l, const uint8_t* gray_r, const SbFusedGeom& g, float* bestL, float* dispL,

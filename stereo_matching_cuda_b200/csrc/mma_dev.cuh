@@ -106,4 +106,101 @@ __device__ __forceinline__ float fhadd_lo(unsigned h2, float c) { return fhadd(_
 __device__ __forceinline__ float fhadd_hi(unsigned h2, float c) { return fhadd(__high2half(u2h2(h2)), c); }
 
 
+
+// ---- geometry and preparation shared by the gray (fused_mma.cu) and RGB (fused_mma_rgb.cu) kernels ----------------
+constexpr int M_TW = 128;       // a/b and output lanes per strip = Tensor-Memory lanes
+constexpr int M_VW = 110;       // valid output columns per strip (128 - 2*RAD)
+constexpr int M_KB = 160;       // cost columns per strip = K of MMA 1 (146 used, 10 K-steps)
+constexpr int M_KC = M_TW + 2 * RAD;  // 146 cost columns that feed the 128 a/b lanes
+constexpr int M_K2 = 128;       // K of MMA 2 (8 K-steps)
+constexpr int M_MTC = 42;       // match chunks (4 pixels x 4 shifted copies, 64 B) per row in an operand slot
+
+struct PrepM {
+    const uint8_t* gray;  // held rows, pitch w
+    int w, h_held, y_global0, frame_h;
+    int n_strips, rows_pad;
+    uint2* GA;
+    float2* GB;
+    __half* GC;
+    uint4* MT;
+    int n_chunk, padm;
+    uint8_t* mean_u8;
+    double eps;
+    float S, scale;
+};
+
+__device__ __forceinline__ bool in_frame(const PrepM& P, int x, int y) {
+    const int yg = y + P.y_global0;
+    return x >= 0 && x < P.w && y >= 0 && y < P.h_held && yg >= 0 && yg < P.frame_h;
+}
+// (I, G = I[x-1] - I[x+1]) with the reference's border rule (costVolume.cu:364-378); (1024, 1024) outside: an
+// out-of-range match saturates both truncated terms, i.e. gives the reference's constant cost (costVolume.cu:184)
+__device__ __forceinline__ void pix_ig(const PrepM& P, int x, int y, float& I, float& G) {
+    if (!in_frame(P, x, y)) {
+        I = 1024.0f;
+        G = 1024.0f;
+        return;
+    }
+    const uint8_t* row = P.gray + (size_t)y * P.w;
+    const int ic = row[x];
+    const int il = (x - 1 >= 0) ? row[x - 1] : ic;
+    const int ir = (x + 1 < P.w) ? row[x + 1] : ic;
+    I = (float)ic;
+    G = (float)(il - ir);
+}
+
+// MT: thread per (padded row, chunk, copy)
+__global__ void __launch_bounds__(256) k_prep_mt(const PrepM P) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int yrow = blockIdx.y;
+    if (idx >= P.n_chunk * 4) return;
+    const int i = idx >> 2, s = idx & 3;
+    const int y = yrow - PADY;
+    float I[4], G[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) pix_ig(P, 4 * i + s + j - P.padm, y, I[j], G[j]);
+    uint4 v;
+    v.x = h22u(__floats2half2_rn(I[0], I[1]));
+    v.y = h22u(__floats2half2_rn(I[2], I[3]));
+    v.z = h22u(__floats2half2_rn(G[0], G[1]));
+    v.w = h22u(__floats2half2_rn(G[2], G[3]));
+    P.MT[((size_t)yrow * P.n_chunk + i) * 4 + s] = v;
+}
+
+Plan make_plan_mma(int w, int rows_out, int size_d, int sm_count, int n_views, int nd) {
+    Plan best{};
+    double best_cost = 1e300;
+    const int n_strips = (w + M_VW - 1) / M_VW;
+    const int groups = (size_d + nd - 1) / nd;
+    for (int n_chunks = 1; n_chunks <= groups; n_chunks++) {
+        const int gpc = (groups + n_chunks - 1) / n_chunks;
+        if ((groups + gpc - 1) / gpc != n_chunks) continue;
+        for (int n_bands = 1; n_bands <= 64; n_bands++) {
+            const int band_rows = (rows_out + n_bands - 1) / n_bands;
+            if (n_bands > 1 && band_rows < 64) break;
+            if ((rows_out + band_rows - 1) / band_rows != n_bands) continue;
+            const long blocks = (long)n_strips * n_bands * n_chunks * n_views;
+            const long waves = (blocks + sm_count - 1) / sm_count;
+            const double t = (double)waves * gpc * (band_rows + 4.0 * RAD) + 0.02 * n_chunks * rows_out / 64.0;
+            if (t < best_cost) {
+                best_cost = t;
+                best = Plan{n_strips, n_bands, band_rows, n_chunks, gpc * nd};
+            }
+        }
+    }
+    return best;
+}
+
+struct MmaGeom {
+    int padm, n_chunk;
+};
+MmaGeom mma_geom(int n_strips, int dlo_all, int dhi_all) {
+    // padded match columns X = x + padm cover x from (first cost column + lowest d) to (last cost column + highest d + 7),
+    // rounded out to whole chunks of the operand slot
+    const int xmin = -2 * RAD + dlo_all, xmax = (n_strips - 1) * M_VW - 2 * RAD + M_KB + dhi_all + 8;
+    const int padm = (max(0, -xmin) + 4 + 3) / 4 * 4;
+    const int n_chunk = (padm + xmax + 4 * (M_MTC + 2) + 3) / 4;
+    return MmaGeom{padm, n_chunk};
+}
+
 }  // namespace

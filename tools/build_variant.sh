@@ -7,7 +7,7 @@ name=$1; src=$2; shift 2
 cd "$(dirname "$0")/../stereo_matching_cuda_b200/csrc"
 mkdir -p ../../gpurun_ab
 objs=""
-for f in api stage_kernels fused_cvf fused_mma fused_cvf_rgb fused_cvf_rgb3; do
+for f in api stage_kernels fused_cvf fused_mma fused_mma_rgb fused_cvf_rgb fused_cvf_rgb3; do
   if [ "$f.cu" == "$src" ]; then
     nvcc -ccbin /usr/bin/g++ -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC \
       --expt-relaxed-constexpr "$@" -c $src -o /tmp/variant_$name.o 2>&1 | grep -v deprecated || true
