@@ -67,6 +67,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t b, unsigned parity) {
         "r"(parity)
         : "memory");
 }
+// non-blocking: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint32_t b, unsigned parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(b), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 
 // ---- Tensor Memory as per-thread scratch -------------------------------------------------
 // The 19-row rings and the producer->consumer hand-off live in TMEM (256 KB per SM, idle in a
@@ -262,6 +276,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(mbar)
                  : "memory");
+}
+// ask L2 for `bytes` (multiple of 16) at a 16-byte aligned global address; no destination, no completion
+__device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t b, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");

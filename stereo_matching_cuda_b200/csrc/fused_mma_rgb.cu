@@ -39,7 +39,15 @@ constexpr int BD = R_ND / RGBM_BSPLIT;   // disparities per role-B thread
 constexpr int NBC = 4 * BD;              // Tensor-Memory columns of a row that a role-B thread owns
 constexpr int R_WARPS = (NWB + NWC + R_NWA + 3 + 3) / 4 * 4;
 constexpr int R_THREADS = 32 * R_WARPS;
-constexpr int R_NOP = 2;         // operand ring: iterations in flight
+constexpr int R_NA = 4;          // role A's operand ring (guide + match rows): slots of HR rows
+constexpr int R_NB = 4;          // role B's operand ring (statistics rows): slots of HR rows
+#ifndef RGBM_PF
+#define RGBM_PF 0
+#endif
+#ifndef RGBM_SLEEP
+#define RGBM_SLEEP 0
+#endif
+constexpr int R_PF = RGBM_PF;    // L2 prefetch distance of the operand rows, in half-steps
 constexpr int R_NGC = 2;         // role C's ring (colours of the output rows, previous (best,label))
 constexpr int R_RESUM = 8;
 constexpr float I_CENTER = 128.0f;
@@ -51,7 +59,8 @@ constexpr uint32_t GB_S2 = M_TW * 16, GB_S3 = M_TW * 32;
 constexpr uint32_t GC_ROW = M_TW * 6;             // [3][128] halves: C - 128 of the output lanes
 constexpr uint32_t PB_ROW = M_TW * 8;
 constexpr uint32_t MT_ROW = M_MTC * 64;
-constexpr uint32_t OP_GA = 0, OP_GB = MR * GA_ROW, OP_MT = OP_GB + MR * GB_ROW, OP_BYTES = OP_MT + MR * MT_ROW;
+constexpr uint32_t A_MT = HR * GA_ROW, A_SLOT = HR * (GA_ROW + MT_ROW);  // role A's slot: HR guide rows, HR match rows
+constexpr uint32_t B_SLOT = HR * GB_ROW;
 constexpr uint32_t GC_SLOT = MR * (GC_ROW + PB_ROW), GC_PB = MR * GC_ROW;
 constexpr uint32_t B1_GROUP = M_KB * 16;          // one N-group (8 columns) of B1: 160 rows x 16 B
 constexpr uint32_t B1_HALF = 8 * B1_GROUP;        // pass 1: (row, d pair) x 4 = 4 groups; pass 2: 4 groups
@@ -66,10 +75,11 @@ struct RSmem {
     unsigned char b1[B1_BYTES];
     unsigned char b2[B2_BYTES];
     unsigned char pring[WIN][PR_SLOT];
-    unsigned char op[R_NOP][OP_BYTES];
+    unsigned char ar[R_NA][A_SLOT];
+    unsigned char br[R_NB][B_SLOT];
     unsigned char gc[R_NGC][GC_SLOT];
     float ry_lut[2][WIN + 1];
-    uint64_t op_full[R_NOP], op_empty[R_NOP], gc_full[R_NGC], gc_empty[R_NGC];
+    uint64_t a_full[R_NA], a_empty[R_NA], s_full[R_NB], s_empty[R_NB], gc_full[R_NGC], gc_empty[R_NGC];
     uint64_t b1_full[NH], b1_empty[NH], d1_full[NH], d1_empty[NH], b2_full[NH], b2_empty[NH], d2_full[NH], d2_empty[NH];
     uint32_t tmem_base;
 };
@@ -141,9 +151,13 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
     if (warp == 0) tm_alloc(&sm.tmem_base);
     auto bar = [&](const uint64_t* b) { return smem_addr(b); };
     if (threadIdx.x == 32) {
-        for (int i = 0; i < R_NOP; i++) {
-            mbar_init(bar(&sm.op_full[i]), 1);
-            mbar_init(bar(&sm.op_empty[i]), R_NWA + NWB);
+        for (int i = 0; i < R_NA; i++) {
+            mbar_init(bar(&sm.a_full[i]), 1);
+            mbar_init(bar(&sm.a_empty[i]), R_NWA);
+        }
+        for (int i = 0; i < R_NB; i++) {
+            mbar_init(bar(&sm.s_full[i]), 1);
+            mbar_init(bar(&sm.s_empty[i]), NWB);
         }
         for (int i = 0; i < R_NGC; i++) {
             mbar_init(bar(&sm.gc_full[i]), 1);
@@ -206,9 +220,9 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
         const float r1_whole = rx * sm.ry_lut[0][WIN];
         const uint32_t td1 = tl + TC_D1 + NBC * h, tring = tl + TC_RING + NBC * h;
         const uint32_t b2a = smem_addr(&sm.b2[0]) + (uint32_t)((l >> 3) * 128 + (l & 7) * 16) + (uint32_t)h * (BD / 2) * B2_GROUP;
-        const uint32_t ops = smem_addr(&sm.op[0][0]) + OP_GB + (uint32_t)l * 16;
+        const uint32_t ops = smem_addr(&sm.br[0][0]) + (uint32_t)l * 16;
         const uint32_t mb_d1f = bar(&sm.d1_full[0]), mb_d1e = bar(&sm.d1_empty[0]), mb_b2f = bar(&sm.b2_full[0]),
-                       mb_b2e = bar(&sm.b2_empty[0]), mb_opf = bar(&sm.op_full[0]), mb_ope = bar(&sm.op_empty[0]);
+                       mb_b2e = bar(&sm.b2_empty[0]), mb_sf = bar(&sm.s_full[0]), mb_se = bar(&sm.s_empty[0]);
         int K = 0;
         for (int g = 0; g < ngroups; g++) {
             float Sp[BD], Sr[BD], Sg[BD], Sb[BD], V[4][BD];
@@ -228,8 +242,6 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
 #pragma unroll 1
             for (int it = 0; it < niter; it++, K++) {
                 const int yi0 = y_first + it * MR;
-                const int ko = K & (R_NOP - 1);
-                mbar_wait(mb_opf + 8 * ko, (unsigned)(K / R_NOP) & 1u);
                 float r1[MR];
                 {
                     const int yg = yi0 - RAD + A.y_global0;
@@ -245,6 +257,18 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                 for (int half = 0; half < NH; half++) {
                     uint32_t dd1[2][NBC], o[2][NBC];
                     int slots[2];
+                    // the statistics of the half's rows: into registers, and the slot goes back to the producer
+                    const int hs = NH * K + half, ks = hs & (R_NB - 1);
+                    mbar_wait(mb_sf + 8 * ks, (unsigned)(hs / R_NB) & 1u);
+                    uint4 st1[HR], st2[HR];
+                    uint32_t st3[HR];
+#pragma unroll
+                    for (int j = 0; j < HR; j++) {
+                        const uint32_t sa = ops + ks * B_SLOT + j * GB_ROW;
+                        st1[j] = lds128(sa);
+                        st2[j] = lds128(sa + GB_S2);
+                        st3[j] = lds32(sa + GB_S3 - (uint32_t)l * 12);  // the third plane is 4 B per lane
+                    }
                     mbar_wait(mb_d1f + 8 * half, (unsigned)K & 1u);
                     tm_fence_after();
 #pragma unroll
@@ -257,13 +281,15 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                     tm_wait_ld();
                     tm_fence_before();
                     __syncwarp();
-                    mbar_arrive_lane0(mb_d1e + 8 * half, lane);
+                    if (lane == 0) {
+                        mbar_arrive(mb_d1e + 8 * half);
+                        mbar_arrive(mb_se + 8 * ks);  // the statistics are in registers
+                    }
 #pragma unroll
                     for (int j = 0; j < 2; j++) {
                         const int r = 2 * half + j;
-                        const uint32_t sa = ops + ko * OP_BYTES + r * GB_ROW;
-                        const uint4 s1 = lds128(sa), s2 = lds128(sa + GB_S2);
-                        const uint32_t s3 = lds32(sa + GB_S3 - (uint32_t)l * 12);  // the third plane is 4 B per lane
+                        const uint4 s1 = st1[j], s2 = st2[j];
+                        const uint32_t s3 = st3[j];
                         const float mr = __uint_as_float(s1.x), mg = __uint_as_float(s1.y), mb = __uint_as_float(s1.z);
                         const float Mrr = __uint_as_float(s1.w), Mrg = __uint_as_float(s2.x), Mrb = __uint_as_float(s2.y);
                         const float Mgg = __uint_as_float(s2.z), Mgb = __uint_as_float(s2.w), Mbb = __uint_as_float(s3);
@@ -332,10 +358,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                     tm_wait_st();
                     fence_async_smem();
                     __syncwarp();
-                    if (lane == 0) {
-                        mbar_arrive(mb_b2f + 8 * half);
-                        if (half == NH - 1) mbar_arrive(mb_ope + 8 * ko);
-                    }
+                    if (lane == 0) mbar_arrive(mb_b2f + 8 * half);
                 }
             }
         }
@@ -461,8 +484,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
         const uint32_t b1a = smem_addr(&sm.b1[0]) + (uint32_t)((k >> 3) * 128 + (k & 7) * 16);
         const uint32_t pr0 = smem_addr(&sm.pring[0][0]) + (uint32_t)k * 8;
         const uint32_t pi0 = smem_addr(&sm.pring[0][0]) + PR_P + (uint32_t)k * 12;
-        const uint32_t ops = smem_addr(&sm.op[0][0]);
-        const uint32_t mb_opf = bar(&sm.op_full[0]), mb_ope = bar(&sm.op_empty[0]), mb_b1f = bar(&sm.b1_full[0]), mb_b1e = bar(&sm.b1_empty[0]);
+        const uint32_t ops = smem_addr(&sm.ar[0][0]);
+        const uint32_t mb_af = bar(&sm.a_full[0]), mb_ae = bar(&sm.a_empty[0]), mb_b1f = bar(&sm.b1_full[0]), mb_b1e = bar(&sm.b1_empty[0]);
         int K = 0;
         for (int g = 0; g < ngroups; g++) {
             for (int s = 0; s < WIN; s++) {
@@ -475,18 +498,19 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
             const int d0 = dlo + g * R_ND;
             const int X0 = x + d0 + A.padm;
             const int i0 = (xc0 + d0 + A.padm) >> 2;
-            const uint32_t mt_off = OP_MT + (uint32_t)((X0 >> 2) - i0) * 64 + (uint32_t)(X0 & 3) * 16;
+            const uint32_t mt_off = A_MT + (uint32_t)((X0 >> 2) - i0) * 64 + (uint32_t)(X0 & 3) * 16;
             int slot = 0;
 #pragma unroll 1
             for (int it = 0; it < niter; it++, K++) {
-                const int ko = K & (R_NOP - 1);
-                mbar_wait(mb_opf + 8 * ko, (unsigned)(K / R_NOP) & 1u);
-                const uint32_t opa = ops + ko * OP_BYTES;
 #pragma unroll
                 for (int r = 0; r < MR; r++) {
+                    const int half = r / HR, rr = r % HR;
+                    const int hs = NH * K + half, ka = hs & (R_NA - 1);
+                    if (rr == 0) mbar_wait(mb_af + 8 * ka, (unsigned)(hs / R_NA) & 1u);
+                    const uint32_t opa = ops + ka * A_SLOT;
                     const uint32_t so = (uint32_t)slot * PR_SLOT;
-                    const uint4 gn = lds128(opa + OP_GA + r * GA_ROW + (uint32_t)k * 16);
-                    const uint4 mt = lds128(opa + mt_off + r * MT_ROW);
+                    const uint4 gn = lds128(opa + rr * GA_ROW + (uint32_t)k * 16);
+                    const uint4 mt = lds128(opa + mt_off + rr * MT_ROW);
                     const uint2 po = lds64(pr0 + so);
                     const uint32_t go[3] = {lds32(pi0 + so), lds32(pi0 + so + 4), lds32(pi0 + so + 8)};
                     const __half2 gI = __low2half2(u2h2(gn.x)), gG = __high2half2(u2h2(gn.x));
@@ -516,7 +540,6 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                     sts32(pi0 + so + 4, gn.z);
                     sts32(pi0 + so + 8, gn.w);
                     slot = (slot + 1 == WIN) ? 0 : slot + 1;
-                    const int half = r / HR, rr = r % HR;
                     if (rr == 0 && K >= 1) mbar_wait(mb_b1e + 8 * half, (unsigned)(K - 1) & 1u);
                     const uint32_t bh = b1a + half * B1_HALF + (uint32_t)(rr * 2) * B1_GROUP;
 #pragma unroll
@@ -529,7 +552,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                         __syncwarp();
                         if (lane == 0) {
                             mbar_arrive(mb_b1f + 8 * half);
-                            if (r == MR - 1) mbar_arrive(mb_ope + 8 * ko);
+                            mbar_arrive(mb_ae + 8 * ka);
                         }
                     }
                 }
@@ -593,56 +616,112 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
         }
     } else if (warp == NWB + NWC + R_NWA + 1) {
         // ================= TMA producer =================
+        // Three rings with different consumers (role A runs ahead of role B, role B ahead of role C): the warp polls the
+        // rings' empty barriers (mbarrier.test_wait) and refills whichever has a free slot, so a ring whose consumer lags
+        // does not hold back the others.
         const char* GAp = reinterpret_cast<const char*>(A.GA[view]) + (size_t)strip * A.rows_pad * GA_ROW;
         const char* GBp = reinterpret_cast<const char*>(A.GB[view]) + (size_t)strip * A.rows_pad * GB_ROW;
         const char* GCp = reinterpret_cast<const char*>(A.GC[view]) + (size_t)strip * A.rows_pad * GC_ROW;
         const char* MTp = reinterpret_cast<const char*>(A.MT[1 - view]);
         const size_t mt_pitch = (size_t)A.n_chunk * 64;
         const long long row0 = (long long)PADY + y_first;
-        const uint32_t op_s = smem_addr(&sm.op[0][0]), gc_s = smem_addr(&sm.gc[0][0]);
-        const uint32_t op_f = bar(&sm.op_full[0]), op_e = bar(&sm.op_empty[0]), gc_f = bar(&sm.gc_full[0]), gc_e = bar(&sm.gc_empty[0]);
+        const uint32_t a_s = smem_addr(&sm.ar[0][0]), b_s = smem_addr(&sm.br[0][0]), gc_s = smem_addr(&sm.gc[0][0]);
+        const uint32_t a_f = bar(&sm.a_full[0]), a_e = bar(&sm.a_empty[0]), s_f = bar(&sm.s_full[0]), s_e = bar(&sm.s_empty[0]);
+        const uint32_t gc_f = bar(&sm.gc_full[0]), gc_e = bar(&sm.gc_empty[0]);
         const char* pb_src = reinterpret_cast<const char*>(A.BL + (size_t)(chunk * 2 + view) * ((size_t)A.rows_out * A.pitchS) +
                                                            (size_t)(yb0 - A.y_out0) * A.pitchS + xo0);
         const size_t pb_pitch = (size_t)A.pitchS * 8;
-        int K = 0;
-        for (int g = 0; g < ngroups; g++) {
-            const int d0 = dlo + g * R_ND;
-            const int i0 = (xc0 + d0 + A.padm) >> 2;
-            const char* ga_src = GAp + row0 * GA_ROW;
-            const char* gb_src = GBp + (row0 - RAD) * GB_ROW;
-            const char* gc_src = GCp + (row0 - 2 * RAD) * GC_ROW;
-            const char* mt_src = MTp + row0 * mt_pitch + (size_t)i0 * 64;
-#pragma unroll 1
-            for (int it = 0; it < niter; it++, K++) {
-                const int so = K & (R_NOP - 1), sc = K & (R_NGC - 1);
-                if (K >= R_NOP) mbar_wait(op_e + 8 * so, (unsigned)(K / R_NOP - 1) & 1u);
-                if (elect_one()) {
-                    const uint32_t dst = op_s + so * OP_BYTES;
-                    mbar_expect_tx(op_f + 8 * so, OP_BYTES);
-                    bulk_g2s(dst + OP_GA, ga_src, MR * GA_ROW, op_f + 8 * so);
-                    bulk_g2s(dst + OP_GB, gb_src, MR * GB_ROW, op_f + 8 * so);
+        const int nhalf = NH * niter;  // half-steps per group
+        // per ring: next step to issue, its position inside the group (g, step in group)
+        int sa = 0, ga = 0, ha = 0;
+        int sb = 0, hb = 0;
+        int sc = 0, gcg = 0, itc = 0;
+        const int SA = NH * Ktotal, SC = Ktotal;
+        // The operand planes of one pass over the rows (about 11 MB per block, 1.6 GB per launch wave) do not stay in L2 from
+        // one disparity group to the next: every bulk load would pay the DRAM latency, which the rings' few slots cannot
+        // cover.  Each refill therefore also asks L2 for the rows R_PF half-steps ahead (cp.async.bulk.prefetch.L2).
+        auto pf_a = [&](int g, int hh) {  // role A's rows of half-step hh of group g
+            if (hh >= nhalf) { hh -= nhalf; g++; }
+            if (g >= ngroups) return;
+            const int i0 = (xc0 + dlo + g * R_ND + A.padm) >> 2;
+            const long long row = row0 + (long long)hh * HR;
+            l2_prefetch(GAp + row * GA_ROW, HR * GA_ROW);
 #pragma unroll
-                    for (int r = 0; r < MR; r++) bulk_g2s(dst + OP_MT + r * MT_ROW, mt_src + r * mt_pitch, MT_ROW, op_f + 8 * so);
-                }
-                __syncwarp();
-                if (K >= R_NGC) mbar_wait(gc_e + 8 * sc, (unsigned)(K / R_NGC - 1) & 1u);
-                if (elect_one()) {
-                    const bool pb = g > 0 && it >= WARM_IT;
-                    mbar_expect_tx(gc_f + 8 * sc, MR * GC_ROW + (pb ? MR * PB_ROW : 0u));
-                    bulk_g2s(gc_s + sc * GC_SLOT, gc_src, MR * GC_ROW, gc_f + 8 * sc);
-                    if (pb) {
-#pragma unroll
-                        for (int r = 0; r < MR; r++)
-                            bulk_g2s(gc_s + sc * GC_SLOT + GC_PB + r * PB_ROW, pb_src + (size_t)((it - WARM_IT) * MR + r) * pb_pitch, PB_ROW,
-                                     gc_f + 8 * sc);
-                    }
-                }
-                __syncwarp();
-                ga_src += MR * GA_ROW;
-                gb_src += MR * GB_ROW;
-                gc_src += MR * GC_ROW;
-                mt_src += MR * mt_pitch;
+            for (int r = 0; r < HR; r++) l2_prefetch(MTp + (row + r) * mt_pitch + (size_t)i0 * 64, MT_ROW);
+        };
+        auto pf_b = [&](int hh) {
+            if (hh >= nhalf) hh -= nhalf;
+            l2_prefetch(GBp + (row0 - RAD + (long long)hh * HR) * GB_ROW, B_SLOT);
+        };
+        if (elect_one()) {
+            for (int i = 0; i < R_PF && i < nhalf; i++) {
+                pf_a(0, i);
+                pf_b(i);
             }
+        }
+        __syncwarp();
+        while (sa < SA || sb < SA || sc < SC) {
+            bool any = false;
+            if (sa < SA) {
+                const int slot = sa & (R_NA - 1);
+                if (sa < R_NA || mbar_test(a_e + 8 * slot, (unsigned)(sa / R_NA - 1) & 1u)) {
+                    if (elect_one()) {
+                        const int d0 = dlo + ga * R_ND;
+                        const int i0 = (xc0 + d0 + A.padm) >> 2;
+                        const long long row = row0 + (long long)ha * HR;
+                        const uint32_t dst = a_s + slot * A_SLOT;
+                        mbar_expect_tx(a_f + 8 * slot, A_SLOT);
+                        bulk_g2s(dst, GAp + row * GA_ROW, HR * GA_ROW, a_f + 8 * slot);
+#pragma unroll
+                        for (int r = 0; r < HR; r++)
+                            bulk_g2s(dst + A_MT + r * MT_ROW, MTp + (row + r) * mt_pitch + (size_t)i0 * 64, MT_ROW, a_f + 8 * slot);
+                        if (R_PF > 0) pf_a(ga, ha + R_PF);
+                    }
+                    __syncwarp();
+                    sa++;
+                    if (++ha == nhalf) { ha = 0; ga++; }
+                    any = true;
+                }
+            }
+            if (sb < SA) {
+                const int slot = sb & (R_NB - 1);
+                if (sb < R_NB || mbar_test(s_e + 8 * slot, (unsigned)(sb / R_NB - 1) & 1u)) {
+                    if (elect_one()) {
+                        const long long row = row0 - RAD + (long long)hb * HR;
+                        mbar_expect_tx(s_f + 8 * slot, B_SLOT);
+                        bulk_g2s(b_s + slot * B_SLOT, GBp + row * GB_ROW, B_SLOT, s_f + 8 * slot);
+                        if (R_PF > 0 && sb + R_PF < SA) pf_b(hb + R_PF);
+                    }
+                    __syncwarp();
+                    sb++;
+                    if (++hb == nhalf) hb = 0;
+                    any = true;
+                }
+            }
+            if (sc < SC) {
+                const int slot = sc & (R_NGC - 1);
+                if (sc < R_NGC || mbar_test(gc_e + 8 * slot, (unsigned)(sc / R_NGC - 1) & 1u)) {
+                    if (elect_one()) {
+                        const bool pb = gcg > 0 && itc >= WARM_IT;  // rows past the band's end read the plane's padding; not used
+                        const long long row = row0 - 2 * RAD + (long long)itc * MR;
+                        mbar_expect_tx(gc_f + 8 * slot, MR * GC_ROW + (pb ? MR * PB_ROW : 0u));
+                        bulk_g2s(gc_s + slot * GC_SLOT, GCp + row * GC_ROW, MR * GC_ROW, gc_f + 8 * slot);
+                        if (pb) {
+#pragma unroll
+                            for (int r = 0; r < MR; r++)
+                                bulk_g2s(gc_s + slot * GC_SLOT + GC_PB + r * PB_ROW, pb_src + (size_t)((itc - WARM_IT) * MR + r) * pb_pitch,
+                                         PB_ROW, gc_f + 8 * slot);
+                        }
+                    }
+                    __syncwarp();
+                    sc++;
+                    if (++itc == niter) { itc = 0; gcg++; }
+                    any = true;
+                }
+            }
+#if RGBM_SLEEP > 0
+            if (!any) __nanosleep(RGBM_SLEEP);
+#endif
         }
     }
     }
