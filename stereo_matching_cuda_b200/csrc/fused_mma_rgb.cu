@@ -24,6 +24,21 @@
 // Hand-offs are per 2 rows (two halves of every buffer), MMA 1 and MMA 2 have their own issuing warps, one warp runs TMA.
 #include "mma_dev.cuh"
 
+#ifdef RGBM_TIMELINE
+// developer instrumentation (tools/timeline_rgb.py): block 0 records, per role and iteration, the start clock and the cycles
+// spent in each kind of barrier wait
+#define TL_N 4096
+__device__ long long g_tl[6][TL_N][4];
+#define TL_DECL long long tl_acc[3] = {0, 0, 0}; long long tl_t0 = 0;
+#define TL_BEGIN() do { tl_acc[0] = tl_acc[1] = tl_acc[2] = 0; tl_t0 = clock64(); } while (0)
+#define TL_WAIT(f, call) do { const long long t_ = clock64(); call; tl_acc[f] += clock64() - t_; } while (0)
+#define TL_END(role, K) do { if (blockIdx.x == 0 && lane == 0 && (K) < TL_N) { g_tl[role][K][0] = tl_t0; g_tl[role][K][1] = tl_acc[0]; g_tl[role][K][2] = tl_acc[1]; g_tl[role][K][3] = tl_acc[2]; } } while (0)
+#else
+#define TL_DECL
+#define TL_BEGIN() do { } while (0)
+#define TL_WAIT(f, call) call
+#define TL_END(role, K) do { } while (0)
+#endif
 namespace {
 
 constexpr int R_ND = 4;          // disparities per group
@@ -39,8 +54,14 @@ constexpr int BD = R_ND / RGBM_BSPLIT;   // disparities per role-B thread
 constexpr int NBC = 4 * BD;              // Tensor-Memory columns of a row that a role-B thread owns
 constexpr int R_WARPS = (NWB + NWC + R_NWA + 3 + 3) / 4 * 4;
 constexpr int R_THREADS = 32 * R_WARPS;
-constexpr int R_NA = 4;          // role A's operand ring (guide + match rows): slots of HR rows
-constexpr int R_NB = 4;          // role B's operand ring (statistics rows): slots of HR rows
+#ifndef RGBM_NA
+#define RGBM_NA 4
+#endif
+#ifndef RGBM_NB
+#define RGBM_NB 2
+#endif
+constexpr int R_NA = RGBM_NA;          // role A's operand ring (guide + match rows): slots of HR rows
+constexpr int R_NB = RGBM_NB;          // role B's operand ring (statistics rows): slots of HR rows
 #ifndef RGBM_PF
 #define RGBM_PF 0
 #endif
@@ -224,6 +245,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
         const uint32_t mb_d1f = bar(&sm.d1_full[0]), mb_d1e = bar(&sm.d1_empty[0]), mb_b2f = bar(&sm.b2_full[0]),
                        mb_b2e = bar(&sm.b2_empty[0]), mb_sf = bar(&sm.s_full[0]), mb_se = bar(&sm.s_empty[0]);
         int K = 0;
+        TL_DECL
         for (int g = 0; g < ngroups; g++) {
             float Sp[BD], Sr[BD], Sg[BD], Sb[BD], V[4][BD];
 #pragma unroll
@@ -242,6 +264,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
 #pragma unroll 1
             for (int it = 0; it < niter; it++, K++) {
                 const int yi0 = y_first + it * MR;
+                TL_BEGIN();
                 float r1[MR];
                 {
                     const int yg = yi0 - RAD + A.y_global0;
@@ -258,8 +281,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                     uint32_t dd1[2][NBC], o[2][NBC];
                     int slots[2];
                     // the statistics of the half's rows: into registers, and the slot goes back to the producer
-                    const int hs = NH * K + half, ks = hs & (R_NB - 1);
-                    mbar_wait(mb_sf + 8 * ks, (unsigned)(hs / R_NB) & 1u);
+                    const int hs = NH * K + half, ks = hs % R_NB;
+                    TL_WAIT(0, mbar_wait(mb_sf + 8 * ks, (unsigned)(hs / R_NB) & 1u));
                     uint4 st1[HR], st2[HR];
                     uint32_t st3[HR];
 #pragma unroll
@@ -269,7 +292,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                         st2[j] = lds128(sa + GB_S2);
                         st3[j] = lds32(sa + GB_S3 - (uint32_t)l * 12);  // the third plane is 4 B per lane
                     }
-                    mbar_wait(mb_d1f + 8 * half, (unsigned)K & 1u);
+                    TL_WAIT(1, mbar_wait(mb_d1f + 8 * half, (unsigned)K & 1u));
                     tm_fence_after();
 #pragma unroll
                     for (int j = 0; j < 2; j++) {
@@ -338,7 +361,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                                 }
                             }
                         }
-                        if (j == 0 && K >= 1) mbar_wait(mb_b2e + 8 * half, (unsigned)(K - 1) & 1u);
+                        if (j == 0 && K >= 1) TL_WAIT(2, mbar_wait(mb_b2e + 8 * half, (unsigned)(K - 1) & 1u));
                         // fp16 hi + lo of the vertical sums: hi - value = -(lo part); MMA 2 takes the lo pass with B negated.
                         // A B2 group (8 columns of D2) = (a_r, a_g, a_b, b') of one disparity pair.
 #pragma unroll
@@ -360,6 +383,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                     __syncwarp();
                     if (lane == 0) mbar_arrive(mb_b2f + 8 * half);
                 }
+                if (warp == 0) TL_END(0, K);
             }
         }
     } else if (warp < NWB + NWC) {
@@ -381,6 +405,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
         const uint32_t pbs = smem_addr(&sm.gc[0][0]) + GC_PB + (uint32_t)l * 8;
         const uint32_t mb_d2f = bar(&sm.d2_full[0]), mb_d2e = bar(&sm.d2_empty[0]), mb_gcf = bar(&sm.gc_full[0]), mb_gce = bar(&sm.gc_empty[0]);
         int K = 0;
+        TL_DECL
         for (int g = 0; g < ngroups; g++) {
             const float dbase = (float)(dlo + g * R_ND);
             const int dact = min(R_ND, dcnt - g * R_ND);
@@ -392,7 +417,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                 const int e = it - WARM_IT;
                 const int kc = K & (R_NGC - 1);
                 const int row0 = e * MR;
-                mbar_wait(mb_gcf + 8 * kc, (unsigned)(K / R_NGC) & 1u);
+                TL_BEGIN();
+                TL_WAIT(0, mbar_wait(mb_gcf + 8 * kc, (unsigned)(K / R_NGC) & 1u));
                 if (e < 0) {
 #pragma unroll
                     for (int hf = 0; hf < NH; hf++) mbar_wait(mb_d2f + 8 * hf, (unsigned)K & 1u);
@@ -427,7 +453,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
 #pragma unroll
                 for (int half = 0; half < NH; half++) {
                     uint32_t hh[2][16];
-                    mbar_wait(mb_d2f + 8 * half, (unsigned)K & 1u);
+                    TL_WAIT(1, mbar_wait(mb_d2f + 8 * half, (unsigned)K & 1u));
                     tm_fence_after();
 #pragma unroll
                     for (int j = 0; j < 2; j++) tm_ld16u(td2 + 16 * (HR * half + j), hh[j]);
@@ -469,6 +495,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                 asm volatile("fence.proxy.async.global;" ::: "memory");  // the TMA producer reads these rows one group later
                 __syncwarp();
                 mbar_arrive_lane0(mb_gce + 8 * kc, lane);
+                if (warp == NWB) TL_END(1, K);
             }
         }
     } else {
@@ -487,6 +514,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
         const uint32_t ops = smem_addr(&sm.ar[0][0]);
         const uint32_t mb_af = bar(&sm.a_full[0]), mb_ae = bar(&sm.a_empty[0]), mb_b1f = bar(&sm.b1_full[0]), mb_b1e = bar(&sm.b1_empty[0]);
         int K = 0;
+        TL_DECL
         for (int g = 0; g < ngroups; g++) {
             for (int s = 0; s < WIN; s++) {
                 const uint32_t so = (uint32_t)s * PR_SLOT;
@@ -502,11 +530,12 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
             int slot = 0;
 #pragma unroll 1
             for (int it = 0; it < niter; it++, K++) {
+                TL_BEGIN();
 #pragma unroll
                 for (int r = 0; r < MR; r++) {
                     const int half = r / HR, rr = r % HR;
-                    const int hs = NH * K + half, ka = hs & (R_NA - 1);
-                    if (rr == 0) mbar_wait(mb_af + 8 * ka, (unsigned)(hs / R_NA) & 1u);
+                    const int hs = NH * K + half, ka = hs % R_NA;
+                    if (rr == 0) TL_WAIT(0, mbar_wait(mb_af + 8 * ka, (unsigned)(hs / R_NA) & 1u));
                     const uint32_t opa = ops + ka * A_SLOT;
                     const uint32_t so = (uint32_t)slot * PR_SLOT;
                     const uint4 gn = lds128(opa + rr * GA_ROW + (uint32_t)k * 16);
@@ -540,7 +569,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                     sts32(pi0 + so + 4, gn.z);
                     sts32(pi0 + so + 8, gn.w);
                     slot = (slot + 1 == WIN) ? 0 : slot + 1;
-                    if (rr == 0 && K >= 1) mbar_wait(mb_b1e + 8 * half, (unsigned)(K - 1) & 1u);
+                    if (rr == 0 && K >= 1) TL_WAIT(1, mbar_wait(mb_b1e + 8 * half, (unsigned)(K - 1) & 1u));
                     const uint32_t bh = b1a + half * B1_HALF + (uint32_t)(rr * 2) * B1_GROUP;
 #pragma unroll
                     for (int j = 0; j < 2; j++) {
@@ -556,6 +585,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                         }
                     }
                 }
+                if (warp == NWB + NWC) TL_END(2, K);
             }
         }
     } else if (warp == NWB + NWC + R_NWA) {
@@ -567,11 +597,13 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
         const uint32_t ta = tmem + TC_BAND, td1 = tmem + TC_D1;
         const uint32_t mb_b1f = bar(&sm.b1_full[0]), mb_b1e = bar(&sm.b1_empty[0]), mb_d1f = bar(&sm.d1_full[0]), mb_d1e = bar(&sm.d1_empty[0]);
 #pragma unroll 1
+        TL_DECL
         for (int K = 0; K < Ktotal; K++) {
+            TL_BEGIN();
 #pragma unroll
             for (int half = 0; half < NH; half++) {
-                mbar_wait(mb_b1f + 8 * half, (unsigned)K & 1u);
-                if (K >= 1) mbar_wait(mb_d1e + 8 * half, (unsigned)(K - 1) & 1u);
+                TL_WAIT(0, mbar_wait(mb_b1f + 8 * half, (unsigned)K & 1u));
+                if (K >= 1) TL_WAIT(1, mbar_wait(mb_d1e + 8 * half, (unsigned)(K - 1) & 1u));
                 tm_fence_after();
                 if (elect_one()) {
                     const uint64_t p1 = db1 + (uint64_t)((half * B1_HALF) >> 4), p2 = p1 + (uint64_t)((4 * B1_GROUP) >> 4);
@@ -585,6 +617,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                 }
                 __syncwarp();
             }
+            TL_END(3, K);
         }
     } else if (warp == NWB + NWC + R_NWA + 2) {
         // ================= MMA 2 issue =================
@@ -595,11 +628,13 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
         const uint32_t ta = tmem + TC_BAND, td2 = tmem + TC_D2;
         const uint32_t mb_b2f = bar(&sm.b2_full[0]), mb_b2e = bar(&sm.b2_empty[0]), mb_d2f = bar(&sm.d2_full[0]), mb_d2e = bar(&sm.d2_empty[0]);
 #pragma unroll 1
+        TL_DECL
         for (int K = 0; K < Ktotal; K++) {
+            TL_BEGIN();
 #pragma unroll
             for (int half = 0; half < NH; half++) {
-                mbar_wait(mb_b2f + 8 * half, (unsigned)K & 1u);
-                if (K >= 1) mbar_wait(mb_d2e + 8 * half, (unsigned)(K - 1) & 1u);
+                TL_WAIT(0, mbar_wait(mb_b2f + 8 * half, (unsigned)K & 1u));
+                if (K >= 1) TL_WAIT(1, mbar_wait(mb_d2e + 8 * half, (unsigned)(K - 1) & 1u));
                 tm_fence_after();
                 if (elect_one()) {
                     const uint64_t dhi = db2 + (uint64_t)((half * B2_HALF) >> 4), dlo2 = dhi + (uint64_t)((4 * B2_GROUP) >> 4);
@@ -613,6 +648,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                 }
                 __syncwarp();
             }
+            TL_END(4, K);
         }
     } else if (warp == NWB + NWC + R_NWA + 1) {
         // ================= TMA producer =================
@@ -663,7 +699,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
         while (sa < SA || sb < SA || sc < SC) {
             bool any = false;
             if (sa < SA) {
-                const int slot = sa & (R_NA - 1);
+                const int slot = sa % R_NA;
                 if (sa < R_NA || mbar_test(a_e + 8 * slot, (unsigned)(sa / R_NA - 1) & 1u)) {
                     if (elect_one()) {
                         const int d0 = dlo + ga * R_ND;
@@ -684,7 +720,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                 }
             }
             if (sb < SA) {
-                const int slot = sb & (R_NB - 1);
+                const int slot = sb % R_NB;
                 if (sb < R_NB || mbar_test(s_e + 8 * slot, (unsigned)(sb / R_NB - 1) & 1u)) {
                     if (elect_one()) {
                         const long long row = row0 - RAD + (long long)hb * HR;
@@ -1025,3 +1061,9 @@ int sbf_pair_disparity_rgb_mma(sb200_ctx* ctx, const sb200_params* p, const uint
     if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     return SB200_OK;
 }
+
+#ifdef RGBM_TIMELINE
+extern "C" int sb200_debug_timeline(long long* host, int n_bytes) {
+    return (int)cudaMemcpyFromSymbol(host, g_tl, (size_t)n_bytes < sizeof(g_tl) ? (size_t)n_bytes : sizeof(g_tl));
+}
+#endif
