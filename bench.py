@@ -137,10 +137,13 @@ def make_inputs(w, h, size_d, channels, n_sets, y0=0, rows=None, seed0=0):
     return [synth.make_pair(w, h, size_d, channels=channels, seed=seed0 + s, y0=y0, rows=rows) for s in range(n_sets)]
 
 
+RGB_KERNEL_NAMES = {4: "k_fused_mma_rgb", 3: "k_fused_cvf_rgb3", 2: "k_fused_cvf_rgb"}
+
+
 def ncu_traffic(guide="gray"):
     """DRAM bytes per launch (and pipe utilisations) of the dominant kernel, from the committed ncu --set full capture"""
     try:
-        with open(os.path.join(ROOT, "profiles", "fused_ncu.json" if guide == "gray" else "fused_rgb3_ncu.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "fused_ncu.json" if guide == "gray" else "fused_rgb_ncu.json")) as f:
             return json.load(f)
     except Exception:
         return None
@@ -482,7 +485,7 @@ def main():
         k_rgb = kernel_times(rstep, 3)["fused_ms"]
         tr = ncu_traffic("rgb")
         ms_rgb = ms / n_rgb
-        name = {3: "k_fused_cvf_rgb3", 2: "k_fused_cvf_rgb"}.get(ctx.rgb_kernel, "k_fused_rgb")
+        name = RGB_KERNEL_NAMES.get(ctx.rgb_kernel, "k_fused_rgb")
         return {"value": world * 2.0 * w * h * size_d / (ms_rgb * 1e-3), "unit": "px*d/s", "ms_per_step": ms_rgb,
                 "fps": world / (ms_rgb * 1e-3), "target_fps_c3": 247,
                 "roofline": {"bound": "fp32_pipe", "kernel": name, "kernel_ms": k_rgb, "instr_per_cell": 71,
@@ -607,7 +610,7 @@ def main():
                       "WTA planes, several hundred MB at 1080p D=256) exceeds the 126 MB L2",
             },
             "roofline": {
-                "bound": "fp32_pipe", "kernel": kernel_name if args.guide == "gray" else {3: "k_fused_cvf_rgb3", 2: "k_fused_cvf_rgb"}.get(ctx.rgb_kernel, "k_fused_rgb"),
+                "bound": "fp32_pipe", "kernel": kernel_name if args.guide == "gray" else RGB_KERNEL_NAMES.get(ctx.rgb_kernel, "k_fused_rgb"),
                 "achieved": achieved / 1e12, "peak": peak_instr / 1e12,
                 "unit": "T lane-instr/s", "frac": achieved / peak_instr,
                 "traffic": tr.get("dram_bytes_per_launch") if tr_ok else None,

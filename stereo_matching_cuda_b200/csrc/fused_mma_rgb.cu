@@ -29,14 +29,16 @@
 // spent in each kind of barrier wait
 #define TL_N 4096
 __device__ long long g_tl[6][TL_N][4];
-#define TL_DECL long long tl_acc[3] = {0, 0, 0}; long long tl_t0 = 0;
+#define TL_DECL long long tl_acc[3] = {0, 0, 0}; long long tl_t0 = 0, tl_m = 0;
 #define TL_BEGIN() do { tl_acc[0] = tl_acc[1] = tl_acc[2] = 0; tl_t0 = clock64(); } while (0)
-#define TL_WAIT(f, call) do { const long long t_ = clock64(); call; tl_acc[f] += clock64() - t_; } while (0)
+#define TL_WAIT(f, call) do { const long long t_ = clock64(); call; const long long d_ = clock64() - t_; tl_acc[f] += d_; tl_m += d_; } while (0)
+#define TL_MARK(seg) do { const long long t_ = clock64(); if ((seg) == 1) tl_m = t_; else if ((seg) == 2) { tl_acc[1] += t_ - tl_m; tl_m = t_; } else { tl_acc[2] += t_ - tl_m; } } while (0)
 #define TL_END(role, K) do { if (blockIdx.x == 0 && lane == 0 && (K) < TL_N) { g_tl[role][K][0] = tl_t0; g_tl[role][K][1] = tl_acc[0]; g_tl[role][K][2] = tl_acc[1]; g_tl[role][K][3] = tl_acc[2]; } } while (0)
 #else
 #define TL_DECL
 #define TL_BEGIN() do { } while (0)
 #define TL_WAIT(f, call) call
+#define TL_MARK(seg) do { } while (0)
 #define TL_END(role, K) do { } while (0)
 #endif
 namespace {
@@ -538,6 +540,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                     if (rr == 0) TL_WAIT(0, mbar_wait(mb_af + 8 * ka, (unsigned)(hs / R_NA) & 1u));
                     const uint32_t opa = ops + ka * A_SLOT;
                     const uint32_t so = (uint32_t)slot * PR_SLOT;
+                    TL_MARK(1);
                     const uint4 gn = lds128(opa + rr * GA_ROW + (uint32_t)k * 16);
                     const uint4 mt = lds128(opa + mt_off + rr * MT_ROW);
                     const uint2 po = lds64(pr0 + so);
@@ -569,7 +572,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                     sts32(pi0 + so + 4, gn.z);
                     sts32(pi0 + so + 8, gn.w);
                     slot = (slot + 1 == WIN) ? 0 : slot + 1;
-                    if (rr == 0 && K >= 1) TL_WAIT(1, mbar_wait(mb_b1e + 8 * half, (unsigned)(K - 1) & 1u));
+                    if (rr == 0 && K >= 1) TL_WAIT(0, mbar_wait(mb_b1e + 8 * half, (unsigned)(K - 1) & 1u));
+                    TL_MARK(2);
                     const uint32_t bh = b1a + half * B1_HALF + (uint32_t)(rr * 2) * B1_GROUP;
 #pragma unroll
                     for (int j = 0; j < 2; j++) {
@@ -584,6 +588,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                             mbar_arrive(mb_ae + 8 * ka);
                         }
                     }
+                    TL_MARK(3);
                 }
                 if (warp == NWB + NWC) TL_END(2, K);
             }

@@ -26,7 +26,7 @@ with S.Context(0) as ctx:
     lib.sb200_debug_timeline.argtypes = [ctypes.c_void_p, ctypes.c_int]
     rc = lib.sb200_debug_timeline(buf.ctypes.data, buf.nbytes)
     assert rc == 0, rc
-names = {0: ("B", "s_full", "d1_full", "b2_empty"), 1: ("C", "gc_full", "d2_full", "-"), 2: ("A", "a_full", "b1_empty", "-"),
+names = {0: ("B", "s_full", "d1_full", "b2_empty"), 1: ("C", "gc_full", "d2_full", "-"), 2: ("A", "a_full+b1_empty", "loads+math+ring", "B1 stores+fence"),
          3: ("MMA1", "b1_full", "d1_empty", "-"), 4: ("MMA2", "b2_full", "d2_empty", "-")}
 np.save("gpurun_out/timeline_rgb.npy", buf)
 t00 = buf[2, 0, 0]
