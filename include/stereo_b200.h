@@ -229,6 +229,28 @@ int sb200_last_timing(sb200_ctx* ctx, float* ms_prep, float* ms_fused, float* ms
 /* device time of the last sb200_pipeline_strips_nccl call's halo exchange (timing enabled) */
 int sb200_last_exchange_ms(sb200_ctx* ctx, float* ms);
 
+/* ---- Post-processing the reference stops short of -------------------------------------------------
+ * NOT in the reference: its pipeline ends at fill_occlusion (occlusion.cu:111-132).  The IPOL pipeline it mirrors goes
+ * on with a weighted median of the filled pixels; this entry provides it with a definition that is exact in integers,
+ * so that the CUDA path and the oracle (oracle/stereo_oracle.c: so_weighted_median) agree bit for bit:
+ *   for every pixel the L/R check marked ((int)occlusion[i] < dmin, the test of fill_occlusion, occlusion.cu:139):
+ *     out[i] = the smallest label l with 2 * sum_{q in window, filled[q] <= l} W(i,q) >= sum_{q in window} W(i,q),
+ *     window = [x-radius, x+radius] x [y-radius, y+radius] clipped to the image,
+ *     W(i,q) = ws[|dy|][|dx|] * wc[|gray[i] - gray[q]|], integer tables
+ *     ws = round(1024 exp(-(dx^2+dy^2)/sigma_space^2)), wc = round(1024 exp(-dI^2/sigma_color^2)) (computed in double);
+ *   every other pixel: out[i] = filled[i].
+ * Labels are the integral floats of the disparity maps, dmin <= label <= dmax.  radius <= 32. */
+typedef struct sb200_wmedian_params {
+    int radius;          /* 19 (IPOL) */
+    float sigma_space;   /* 9 */
+    float sigma_color;   /* 25.5 = 0.1 * 255 */
+} sb200_wmedian_params;
+void sb200_default_wmedian_params(sb200_wmedian_params* wp);
+int sb200_weighted_median(sb200_ctx* ctx, const sb200_params* p, const sb200_wmedian_params* wp, const uint8_t* gray,
+                          const float* occlusion, const float* filled, float* out, int w, int h);
+int sb200_weighted_median_dev(sb200_ctx* ctx, const sb200_params* p, const sb200_wmedian_params* wp, const uint8_t* d_gray,
+                              const float* d_occlusion, const float* d_filled, float* d_out, int w, int h);
+
 #ifdef __cplusplus
 }
 #endif

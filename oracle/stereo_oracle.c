@@ -602,3 +602,56 @@ void so_view_disparity_rgb(const so_params* p, const unsigned char* guide_rgb, i
     free(qs); free(ps); free(scr); free(g1); free(g2);
     so_rgb_stats_free(&s);
 }
+
+/* Weighted median of the pixels the L/R check marked -- NOT in the reference (its pipeline ends at fill_occlusion,
+ * occlusion.cu:111-132); the definition is the one in include/stereo_b200.h (integer weight tables, so that every
+ * implementation gives the same labels).  Marked = (int)occlusion[i] < dmin, the test of fill_occlusion (occlusion.cu:139). */
+void so_weighted_median(const unsigned char* gray, const float* occlusion, const float* filled, float* out, int w, int h,
+                        int dmin, int size_d, int radius, float sigma_space, float sigma_color, int nthreads) {
+    const int R = radius;
+    unsigned* ws = (unsigned*)malloc(sizeof(unsigned) * (size_t)(R + 1) * (R + 1));
+    unsigned wc[256];
+    const double ss = (double)sigma_space * (double)sigma_space, sc = (double)sigma_color * (double)sigma_color;
+    for (int dy = 0; dy <= R; dy++)
+        for (int dx = 0; dx <= R; dx++) ws[(size_t)dy * (R + 1) + dx] = (unsigned)floor(1024.0 * exp(-(double)(dx * dx + dy * dy) / ss) + 0.5);
+    for (int d = 0; d < 256; d++) wc[d] = (unsigned)floor(1024.0 * exp(-(double)(d * d) / sc) + 0.5);
+#ifdef _OPENMP
+    if (nthreads <= 0) nthreads = omp_get_max_threads();
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 4)
+#endif
+    for (int y = 0; y < h; y++) {
+        unsigned long long* hist = (unsigned long long*)malloc(sizeof(unsigned long long) * (size_t)size_d);
+        for (int x = 0; x < w; x++) {
+            const size_t i = (size_t)y * w + x;
+            if (!((float)(int)occlusion[i] < (float)dmin)) {
+                out[i] = filled[i];
+                continue;
+            }
+            memset(hist, 0, sizeof(unsigned long long) * (size_t)size_d);
+            unsigned long long total = 0;
+            const int x0 = x - R < 0 ? 0 : x - R, x1 = x + R > w - 1 ? w - 1 : x + R;
+            const int y0 = y - R < 0 ? 0 : y - R, y1 = y + R > h - 1 ? h - 1 : y + R;
+            for (int qy = y0; qy <= y1; qy++) {
+                for (int qx = x0; qx <= x1; qx++) {
+                    const size_t q = (size_t)qy * w + qx;
+                    const unsigned wgt = ws[(size_t)abs(qy - y) * (R + 1) + abs(qx - x)] * wc[abs((int)gray[i] - (int)gray[q])];
+                    int b = (int)filled[q] - dmin;
+                    if (b < 0) b = 0;
+                    if (b > size_d - 1) b = size_d - 1;
+                    hist[b] += wgt;
+                    total += wgt;
+                }
+            }
+            unsigned long long cum = 0;
+            int b = 0;
+            for (; b < size_d; b++) {
+                cum += hist[b];
+                if (2ull * cum >= total) break;
+            }
+            if (b >= size_d) b = size_d - 1;
+            out[i] = (float)(dmin + b);
+        }
+        free(hist);
+    }
+    free(ws);
+}

@@ -47,6 +47,11 @@ class Params(C.Structure):
         return self.dmax - self.dmin + 1
 
 
+class WMedianParams(C.Structure):
+    """sb200_wmedian_params"""
+    _fields_ = [("radius", C.c_int), ("sigma_space", C.c_float), ("sigma_color", C.c_float)]
+
+
 class _Outputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("disp_left", "disp_right", "occlusion", "filled", "best_left", "best_right",
                                           "gray_left", "gray_right", "mean_left", "mean_right")]
@@ -106,6 +111,9 @@ def load_library(path=None):
         "sb200_winner_take_all_dev": (ip, [vp, vp, vp, vp, ip, ip]),
         "sb200_detect_occlusion_dev": (ip, [vp, PP, vp, vp, ip, ip, ip]),
         "sb200_fill_occlusion_dev": (ip, [vp, vp, ip, ip, fp]),
+        "sb200_default_wmedian_params": (None, [vp]),
+        "sb200_weighted_median": (ip, [vp, vp, vp, vp, vp, vp, vp, ip, ip]),
+        "sb200_weighted_median_dev": (ip, [vp, vp, vp, vp, vp, vp, vp, ip, ip]),
         "sb200_pipeline_dev": (ip, [vp, PP, vp, vp, ip, ip, ip, C.POINTER(_Outputs)]),
         "sb200_pipeline": (ip, [vp, PP, vp, vp, ip, ip, ip, C.POINTER(_Outputs)]),
         "sb200_last_exchange_ms": (ip, [vp, C.POINTER(C.c_float)]),
@@ -336,6 +344,19 @@ class Context:
         assert disparity.dtype == np.float32 and disparity.flags.c_contiguous
         h, w = disparity.shape
         self._ck(self.lib.sb200_fill_occlusion(self.h, _ptr(disparity), w, h, float(v_min)))
+
+    def weighted_median(self, gray, occlusion, filled, params=None, radius=19, sigma_space=9.0, sigma_color=25.5):
+        """Beyond the reference: weighted median of the pixels the L/R check marked; see stereo_b200.h"""
+        p = params or default_params()
+        g = _np(gray, np.uint8)
+        oc, fl = _np(occlusion, np.float32), _np(filled, np.float32)
+        if g.ndim != 2 or oc.shape != g.shape or fl.shape != g.shape:
+            raise StereoB200Error("weighted_median: gray, occlusion and filled must be 2-D arrays of one shape")
+        wp = WMedianParams(int(radius), float(sigma_space), float(sigma_color))
+        out = np.empty(g.shape, np.float32)
+        h, w = g.shape
+        self._ck(self.lib.sb200_weighted_median(self.h, C.byref(p), C.byref(wp), _ptr(g), _ptr(oc), _ptr(fl), _ptr(out), w, h))
+        return out
 
     # ---- fused pipeline -----------------------------------------------------------------
     _F32 = ("disp_left", "disp_right", "occlusion", "filled", "best_left", "best_right")

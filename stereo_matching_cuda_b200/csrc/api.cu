@@ -1,5 +1,6 @@
 // api.cu -- the C ABI of include/stereo_b200.h: context, workspace, stage entry points and the
 // fused pipeline.  Host C++ driving CUDA; no torch types, no CPU fallback.
+#include <vector>
 #include <dlfcn.h>
 
 #include <new>
@@ -1092,6 +1093,75 @@ int sb200_fill_occlusion(sb200_ctx* ctx, float* disparity, int w, int h, float v
     SB_TRY(h2d(ctx, d_d, disparity, n * 4));
     SB_TRY(sbk_fill_occlusion(ctx, d_d, w, h, vMin));
     SB_TRY(d2h(ctx, disparity, d_d, n * 4));
+    SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SB200_OK;
+}
+
+
+// ---- post-processing beyond the reference: weighted median of the marked pixels ----
+void sb200_default_wmedian_params(sb200_wmedian_params* wp) {
+    if (!wp) return;
+    wp->radius = 19;
+    wp->sigma_space = 9.0f;
+    wp->sigma_color = 25.5f;
+}
+
+static int wmedian_tables(sb200_ctx* ctx, const sb200_wmedian_params* wp, unsigned** d_ws, unsigned** d_wc) {
+    // the integer weight tables of the definition in stereo_b200.h (double arithmetic on the host, a few KB)
+    const int R = wp->radius;
+    std::vector<unsigned> t((size_t)(R + 1) * (R + 1) + 256);
+    const double ss = (double)wp->sigma_space * (double)wp->sigma_space, sc = (double)wp->sigma_color * (double)wp->sigma_color;
+    for (int dy = 0; dy <= R; dy++)
+        for (int dx = 0; dx <= R; dx++) t[(size_t)dy * (R + 1) + dx] = (unsigned)floor(1024.0 * exp(-(double)(dx * dx + dy * dy) / ss) + 0.5);
+    for (int d = 0; d < 256; d++) t[(size_t)(R + 1) * (R + 1) + d] = (unsigned)floor(1024.0 * exp(-(double)(d * d) / sc) + 0.5);
+    unsigned* d_t;
+    SB_TRY(ws_get(ctx, &d_t, t.size()));
+    // pageable source: the copy is staged by the runtime before the call returns, so the vector may go out of scope
+    SB_CUDA(ctx, cudaMemcpyAsync(d_t, t.data(), t.size() * sizeof(unsigned), cudaMemcpyHostToDevice, ctx->stream));
+    *d_ws = d_t;
+    *d_wc = d_t + (size_t)(R + 1) * (R + 1);
+    return SB200_OK;
+}
+
+static int wmedian_check(sb200_ctx* ctx, const sb200_params* p, const sb200_wmedian_params* wp) {
+    SB_TRY(check_params(ctx, p));
+    REQUIRE(ctx, wp && wp->radius >= 1 && wp->radius <= 32 && wp->sigma_space > 0.0f && wp->sigma_color > 0.0f,
+            "weighted median: radius in [1, 32], positive sigmas");
+    return SB200_OK;
+}
+
+int sb200_weighted_median_dev(sb200_ctx* ctx, const sb200_params* p, const sb200_wmedian_params* wp, const uint8_t* d_gray,
+                              const float* d_occlusion, const float* d_filled, float* d_out, int w, int h) {
+    DevGuard dev_guard__(ctx);
+    SB_TRY(wmedian_check(ctx, p, wp));
+    REQUIRE(ctx, d_gray && d_occlusion && d_filled && d_out && w > 0 && h > 0, "null pointer or empty image");
+    REQUIRE(ctx, d_out != d_filled, "weighted median: out must not alias filled (the windows read filled)");
+    SB_TRY(sb_ws_reserve(ctx, 64 * 1024));
+    unsigned *ws, *wc;
+    SB_TRY(wmedian_tables(ctx, wp, &ws, &wc));
+    return sbk_weighted_median(ctx, d_gray, d_occlusion, d_filled, d_out, w, h, p->dmin, p->dmax - p->dmin + 1, wp->radius, ws, wc);
+}
+
+int sb200_weighted_median(sb200_ctx* ctx, const sb200_params* p, const sb200_wmedian_params* wp, const uint8_t* gray,
+                          const float* occlusion, const float* filled, float* out, int w, int h) {
+    DevGuard dev_guard__(ctx);
+    SB_TRY(wmedian_check(ctx, p, wp));
+    REQUIRE(ctx, gray && occlusion && filled && out && w > 0 && h > 0, "null pointer or empty image");
+    const size_t n = (size_t)w * h;
+    SB_TRY(sb_ws_reserve(ctx, sb_align(n) + 3 * sb_align(n * 4) + 64 * 1024 + 4096));
+    uint8_t* d_g;
+    float *d_o, *d_f, *d_r;
+    SB_TRY(ws_get(ctx, &d_g, n));
+    SB_TRY(ws_get(ctx, &d_o, n));
+    SB_TRY(ws_get(ctx, &d_f, n));
+    SB_TRY(ws_get(ctx, &d_r, n));
+    SB_TRY(h2d(ctx, d_g, gray, n));
+    SB_TRY(h2d(ctx, d_o, occlusion, n * 4));
+    SB_TRY(h2d(ctx, d_f, filled, n * 4));
+    unsigned *ws, *wc;
+    SB_TRY(wmedian_tables(ctx, wp, &ws, &wc));
+    SB_TRY(sbk_weighted_median(ctx, d_g, d_o, d_f, d_r, w, h, p->dmin, p->dmax - p->dmin + 1, wp->radius, ws, wc));
+    SB_TRY(d2h(ctx, out, d_r, n * 4));
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SB200_OK;
 }

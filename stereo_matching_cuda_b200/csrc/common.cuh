@@ -135,6 +135,9 @@ int sbk_q(sb200_ctx* ctx, const float* im, const float* a, const float* b, float
 int sbk_disp_select(sb200_ctx* ctx, const float* q, float* best, float* dmap, size_t n, int label);
 int sbk_detect_occlusion(sb200_ctx* ctx, float* dL, const float* dR, int dOcc, int d_lr, int w, int h);
 int sbk_fill_occlusion(sb200_ctx* ctx, float* disp, int w, int h, float vMin);
+// weighted median of the pixels the L/R check marked; ws: (radius+1)^2 spatial weights, wc: 256 colour weights (device)
+int sbk_weighted_median(sb200_ctx* ctx, const uint8_t* gray, const float* occ, const float* filled, float* out, int w, int h,
+                        int dmin, int size_d, int radius, const unsigned* ws, const unsigned* wc);
 int sbk_lr_check_fill(sb200_ctx* ctx, const float* dL, const float* dR, int w, int h, int dOcc, int d_lr, float vMin,
                       float* occ, float* filled);
 int sbk_fill_f32(sb200_ctx* ctx, float* dst, float v, size_t n);

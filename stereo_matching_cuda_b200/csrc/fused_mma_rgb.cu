@@ -827,35 +827,34 @@ __global__ void __launch_bounds__(160) k_prep_ga3(const PrepR P) {
     }
 }
 
-// GB: block = (strip, GB3_TR padded rows), thread per a/b lane; horizontal 19-tap sums of the 9 quantities per row from a
-// shared-memory tile, vertical running sums in registers
+// GB: block = (strip, GB3_TR padded rows), thread per a/b lane.  The block's colour tile (GB3_TR + 18 rows x 146 columns)
+// is loaded once; a thread then walks down its column: the window sums are vertical running sums of the rows' horizontal
+// 19-tap sums of the nine quantities (the row that enters adds, the row that leaves is recomputed and subtracted).
 constexpr int GB3_TR = 32;
 __global__ void __launch_bounds__(M_TW) k_prep_gb3(const PrepR P) {
-    __shared__ uchar4 sC[M_TW + 2 * RAD];
+    __shared__ uchar4 sC[GB3_TR + 2 * RAD][M_TW + 2 * RAD];
     const int l = threadIdx.x, strip = blockIdx.y;
     const int yrow0 = blockIdx.x * GB3_TR;
     const int xa0 = strip * M_VW - RAD;
     const int x = xa0 + l;
-    // ring of the horizontal sums of the last 19 rows lives in local arrays indexed modulo 19 -> keep it in registers by
-    // walking the rows twice instead: the entering row adds, the row 19 above subtracts (both recomputed from the tile)
-    int v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    auto hsum = [&](int y, int (&s)[9]) {  // horizontal sums of held row y (zeros outside the frame) at this lane
-        __syncthreads();
-        for (int i = l; i < M_TW + 2 * RAD; i += M_TW) {
-            const int xx = xa0 + i - RAD;
-            uchar4 c = make_uchar4(0, 0, 0, 0);
-            if (in_frame_r(P, xx, y)) {
-                const uint8_t* q = P.rgb + ((size_t)y * P.w + xx) * P.ch;
-                c = make_uchar4(q[0], q[1], q[2], 0);
-            }
-            sC[i] = c;
+    for (int i = l; i < (GB3_TR + 2 * RAD) * (M_TW + 2 * RAD); i += M_TW) {
+        const int py = i / (M_TW + 2 * RAD), px = i - py * (M_TW + 2 * RAD);
+        const int xx = xa0 + px - RAD, yy = yrow0 - PADY + py - RAD;
+        uchar4 c = make_uchar4(0, 0, 0, 0);
+        if (in_frame_r(P, xx, yy)) {
+            const uint8_t* q = P.rgb + ((size_t)yy * P.w + xx) * P.ch;
+            c = make_uchar4(q[0], q[1], q[2], 0);
         }
-        __syncthreads();
+        sC[py][px] = c;
+    }
+    __syncthreads();
+    int v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    auto hsum = [&](int py, int (&s)[9]) {  // horizontal sums of tile row py at this lane
 #pragma unroll
         for (int q = 0; q < 9; q++) s[q] = 0;
 #pragma unroll
         for (int t = 0; t < WIN; t++) {
-            const uchar4 c = sC[l + t];
+            const uchar4 c = sC[py][l + t];
             const int r = c.x, g = c.y, b = c.z;
             s[0] += r; s[1] += g; s[2] += b;
             s[3] += r * r; s[4] += r * g; s[5] += r * b;
@@ -863,15 +862,15 @@ __global__ void __launch_bounds__(M_TW) k_prep_gb3(const PrepR P) {
         }
     };
     int s[9];
-    for (int t = -RAD; t < RAD; t++) {  // rows y0-9 .. y0+8 of the first output row's window
-        hsum(yrow0 - PADY + t, s);
+    for (int t = 0; t < 2 * RAD; t++) {  // tile rows 0 .. 17 = held rows y0-9 .. y0+8 of the first output row's window
+        hsum(t, s);
 #pragma unroll
         for (int q = 0; q < 9; q++) v[q] += s[q];
     }
     for (int ty = 0; ty < GB3_TR; ty++) {
         const int yrow = yrow0 + ty;
         const int y = yrow - PADY, yg = y + P.y_global0;
-        hsum(y + RAD, s);
+        hsum(ty + 2 * RAD, s);
 #pragma unroll
         for (int q = 0; q < 9; q++) v[q] += s[q];
         if (yrow < P.rows_pad) {
@@ -904,7 +903,7 @@ __global__ void __launch_bounds__(M_TW) k_prep_gb3(const PrepR P) {
             *reinterpret_cast<float4*>(dst + M_TW * 4 + l * 4) = make_float4(o[4], o[5], o[6], o[7]);
             dst[M_TW * 8 + l] = o[8];
         }
-        hsum(y - RAD, s);
+        hsum(ty, s);
 #pragma unroll
         for (int q = 0; q < 9; q++) v[q] -= s[q];
     }

@@ -424,6 +424,85 @@ int sbk_lr_check_fill(sb200_ctx* ctx, const float* dL, const float* dR, int w, i
 }
 
 // ---------------------------------------------------------------------------------------
+// Weighted median of the pixels the L/R check marked (beyond the reference, defined in stereo_b200.h).
+// One warp per marked pixel: the window's integer weights go into a per-warp histogram over the labels in shared
+// memory (integer atomics: the sums do not depend on the order), then the warp finds the first label whose cumulated
+// weight reaches half of the total.  Unmarked pixels are copied by their warp's lane 0.
+#define WMED_WARPS 8
+__global__ void __launch_bounds__(32 * WMED_WARPS) k_weighted_median(const uint8_t* __restrict__ gray, const float* __restrict__ occ,
+                                                                      const float* __restrict__ filled, float* __restrict__ out,
+                                                                      int w, int h, int dmin, int size_d, int radius,
+                                                                      const unsigned* __restrict__ ws, const unsigned* __restrict__ wc) {
+    extern __shared__ unsigned wmed_hist[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned* hist = wmed_hist + (size_t)wid * size_d;
+    const long long n = (long long)w * h;
+    for (long long i = (long long)blockIdx.x * WMED_WARPS + wid; i < n; i += (long long)gridDim.x * WMED_WARPS) {
+        const float fo = filled[i];
+        if (!((float)(int)occ[i] < (float)dmin)) {  // not marked (the test of fill_occlusion, occlusion.cu:139)
+            if (lane == 0) out[i] = fo;
+            continue;
+        }
+        const int y = (int)(i / w), x = (int)(i - (long long)y * w);
+        for (int b = lane; b < size_d; b += 32) hist[b] = 0u;
+        __syncwarp();
+        const int x0 = max(0, x - radius), x1 = min(w - 1, x + radius), y0 = max(0, y - radius), y1 = min(h - 1, y + radius);
+        const int ww = x1 - x0 + 1, taps = ww * (y1 - y0 + 1);
+        const int gi = gray[i];
+        unsigned total = 0;
+        for (int t = lane; t < taps; t += 32) {
+            const int ty = t / ww, tx = t - ty * ww;
+            const int qx = x0 + tx, qy = y0 + ty;
+            const size_t q = (size_t)qy * w + qx;
+            const unsigned wgt = ws[abs(qy - y) * (radius + 1) + abs(qx - x)] * wc[abs(gi - (int)gray[q])];
+            int b = (int)filled[q] - dmin;
+            b = min(max(b, 0), size_d - 1);
+            atomicAdd(&hist[b], wgt);
+            total += wgt;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+        __syncwarp();
+        // lane l owns bins [l*per, (l+1)*per): its sum, an exclusive warp scan of the sums, then a walk inside the chunk
+        const int per = (size_d + 31) / 32;
+        unsigned mine = 0;
+        for (int b = lane * per; b < min(size_d, (lane + 1) * per); b++) mine += hist[b];
+        unsigned incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const unsigned long long half2 = total;  // compare 2 * cum >= total in 64 bits
+        const bool here = 2ull * incl >= half2;
+        const unsigned ballot = __ballot_sync(0xffffffffu, here);
+        const int owner = ballot ? __ffs(ballot) - 1 : 31;
+        if (lane == owner) {
+            unsigned cum = incl - mine;
+            int b = lane * per;
+            const int bend = min(size_d, (lane + 1) * per);
+            for (; b < bend; b++) {
+                cum += hist[b];
+                if (2ull * cum >= half2) break;
+            }
+            if (b >= size_d) b = size_d - 1;
+            out[i] = (float)(dmin + b);
+        }
+        __syncwarp();
+    }
+}
+
+int sbk_weighted_median(sb200_ctx* ctx, const uint8_t* gray, const float* occ, const float* filled, float* out, int w, int h,
+                        int dmin, int size_d, int radius, const unsigned* ws, const unsigned* wc) {
+    const size_t smem = (size_t)WMED_WARPS * size_d * sizeof(unsigned);
+    if (smem > 48 * 1024) return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "weighted median: more than %d labels", 48 * 1024 / 4 / WMED_WARPS);
+    const long long n = (long long)w * h;
+    const int blocks = (int)min((long long)ctx->sm_count * 32, (n + WMED_WARPS - 1) / WMED_WARPS);
+    SB_LAUNCH(ctx, k_weighted_median, blocks, 32 * WMED_WARPS, smem, gray, occ, filled, out, w, h, dmin, size_d, radius, ws, wc);
+    return SB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // 8-bit visualisation on the device: write_mat's normalisation (main.cu:13-35) and flToCh2OnGPU
 // (occlusion.cu:230-237), so that a driver downloads 8-bit images instead of float maps.
 // write_mat scans sequentially with `if (v > max) max = v; else if (v <= min) min = v;`: a value that RAISES the running

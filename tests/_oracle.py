@@ -71,6 +71,7 @@ class Oracle:
         L.so_pipeline_gray.argtypes = [C.POINTER(SoParams), u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int] + [f32p] * 6 + [
             C.c_void_p] * 4
         L.so_write_mat.argtypes = [f32p, u8p, C.c_int, C.c_int]
+        L.so_weighted_median.argtypes = [u8p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int]
         L.so_view_disparity_rgb.argtypes = [C.POINTER(SoParams), u8p, C.c_int, u8p, u8p, f32p, f32p, C.c_void_p, C.c_int,
                                             C.c_int, C.c_int, C.c_int]
 
@@ -206,6 +207,16 @@ class Oracle:
         res = dict(zip(keys, outs))
         res.update(meanL=mL, meanR=mR, secondL=sL, secondR=sR)
         return res
+
+    def weighted_median(self, gray, occlusion, filled, dmin, size_d, radius=19, sigma_space=9.0, sigma_color=25.5, nthreads=0):
+        h, w = gray.shape
+        g = np.ascontiguousarray(gray, np.uint8)
+        oc = np.ascontiguousarray(occlusion, np.float32)
+        fl = np.ascontiguousarray(filled, np.float32)
+        out = np.empty((h, w), np.float32)
+        self.lib.so_weighted_median(g, oc, fl, out, w, h, int(dmin), int(size_d), int(radius), float(sigma_space),
+                                    float(sigma_color), int(nthreads))
+        return out
 
     def write_mat(self, mat):
         h, w = mat.shape

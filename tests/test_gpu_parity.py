@@ -643,3 +643,27 @@ def test_fused_vs_staged_random_shapes(ctx):
             ctx.compute_guided_filter(guide, cost, best, dmap, dm, p)  # box_mode SLIDING: double accumulation
             assert (np.abs(out[kb] - best) / np.maximum(np.abs(best), 0.1)).max() < RTOL_BEST, (w, h, dmin, dmax)
             assert (out[kd] == dmap).mean() > 0.998, (w, h, dmin, dmax, (out[kd] == dmap).mean())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,size_d,radius", [(384, 288, 16, 19), (150, 70, 12, 5), (41, 23, 3, 19), (300, 64, 100, 7)])
+def test_weighted_median_equals_the_oracle(oracle, w, h, size_d, radius):
+    """SURVEY 8f.3 (beyond the reference): the weighted median of the marked pixels is defined with integer weights
+    (stereo_b200.h), so the CUDA path must equal the oracle's restatement bit for bit"""
+    S = pytest.importorskip("stereo_matching_cuda_b200")
+    from stereo_matching_cuda_b200 import api
+
+    L, R = synth.make_pair(w, h, max(size_d, 2), seed=w + radius)
+    dmin = -(size_d - 1)
+    p = api.default_params(dmin=dmin, dmax=0)
+    with S.Context(0) as ctx:
+        out = ctx.pipeline(L, R, p, want=("occlusion", "filled", "gray_left"))
+        got = ctx.weighted_median(L, out["occlusion"], out["filled"], p, radius=radius)
+        with pytest.raises(S.StereoB200Error):
+            ctx.weighted_median(L, out["occlusion"], out["filled"], p, radius=40)
+    marked = out["occlusion"].astype(np.int32) < dmin
+    assert marked.any()
+    want = oracle.weighted_median(L, out["occlusion"], out["filled"], dmin, size_d, radius=radius)
+    assert np.array_equal(got, want)
+    assert np.array_equal(got[~marked], out["filled"][~marked])
+    assert got.min() >= dmin and got.max() <= 0

@@ -83,3 +83,25 @@ def test_fma_switch_is_label_neutral(oracle, tsukuba):
     assert (nf["dL"] == tsukuba["dL"]).mean() > 0.9999
     assert np.array_equal(oracle.cost_volume(tsukuba["gl"], tsukuba["gr"], 4, -3, oracle.params(use_fma=0)),
                           oracle.cost_volume(tsukuba["gl"], tsukuba["gr"], 4, -3, oracle.params(use_fma=1)))
+
+
+def test_oracle_weighted_median_properties(oracle):
+    """the beyond-reference weighted median (stereo_b200.h): unmarked pixels pass through, a marked pixel in a constant
+    neighbourhood keeps that constant, and with a huge colour sigma and radius 1 it is the plain median of the 3x3 window"""
+    rng = np.random.default_rng(7)
+    h, w, dmin, size_d = 20, 30, -7, 8
+    gray = rng.integers(0, 255, (h, w)).astype(np.uint8)
+    filled = rng.integers(dmin, 1, (h, w)).astype(np.float32)
+    occ = filled.copy()
+    marked = rng.random((h, w)) < 0.3
+    occ[marked] = dmin - 100
+    out = oracle.weighted_median(gray, occ, filled, dmin, size_d, radius=1, sigma_space=1e6, sigma_color=1e6)
+    assert np.array_equal(out[~marked], filled[~marked])
+    for y, x in zip(*np.nonzero(marked)):
+        win = np.sort(filled[max(0, y - 1):y + 2, max(0, x - 1):x + 2].ravel())
+        # lower weighted median with equal weights: first value whose count reaches half
+        k = next(i for i in range(len(win)) if 2 * (i + 1) >= len(win))
+        assert out[y, x] == win[k]
+    const = np.full((h, w), -3, np.float32)
+    out2 = oracle.weighted_median(gray, occ, const, dmin, size_d)
+    assert np.array_equal(out2, const)
