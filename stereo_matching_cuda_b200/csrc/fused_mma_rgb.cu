@@ -7,8 +7,8 @@
 //   costVolumOnGPU2 (costVolume.cu:163-190) -> pixelMultOnGPU -> 4x box (integral.cu:78-131, guidedFilter.cu:297-318) ->
 //   compute_ak_and_bk (:345-354) -> compute_q (:363-369) -> dispSelectOnGPU (:403-411)
 // generalised as in He et al.'s colour guided filter: cov_c = mean(I_c p) - mu_c mean(p), a = (Sigma + eps U)^-1 cov,
-// b = mean(p) - a.mu, q = mean(a).I + mean(b); the cost stays the reference's gray cost (A.3).  The checker is
-// oracle/stereo_oracle.c: view_disparity_rgb (tests/test_rgb_guide.py).
+// b = mean(p) - a.mu, q = mean(a).I + mean(b); the cost stays the reference's gray cost (A.3).  Parity tests:
+// tests/test_rgb_guide.py (against the CPU checker's port of the same definition).
 //
 // Decomposition (differences to fused_mma.cu): a block owns a strip of 128 columns (110 valid) and a group of FOUR
 // consecutive disparities -- the 19-row ring of (a_r, a_g, a_b, b) takes 16 Tensor-Memory columns per row like gray's
