@@ -231,7 +231,7 @@ def run_reference(args, w, h, size_d, desc):
         "e2e": {"value": value, "unit": "px*d/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "fps_equiv_full_workload": value / (2.0 * w * h * size_d),
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def cpu_baseline(w, h, size_d):
@@ -642,7 +642,7 @@ def main():
             line["cpu_baseline"] = cpu_baseline(w, h, size_d)
             if default_line:
                 line["reference_gpu"] = reference_gpu_leg(ctx, api)
-        print(json.dumps(line))
+        emit(line)
     if comm:
         comm.close()
     ctx.close()
@@ -650,5 +650,26 @@ def main():
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner of a raw communicator,
+    for one), so everything but the final line is sent to stderr: fd 1 is pointed at fd 2 for the whole run and the line
+    is written to a duplicate of the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 if __name__ == "__main__":
+    guard_stdout()
     main()
