@@ -95,6 +95,28 @@ def test_gpu_rgb_three_stage_kernel_equals_two_stage_bitwise(monkeypatch, w, h, 
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("w,h,size_d", [(470, 130, 21), (216, 40, 4), (33, 25, 3), (217, 19, 1), (900, 330, 70)])
+def test_gpu_rgb_tensor_core_kernel_agrees_with_the_shuffle_kernel(monkeypatch, w, h, size_d):
+    """k_fused_mma_rgb (the default, SB200_RGB_KERNEL=4) against k_fused_cvf_rgb3 (=3): the first-stage sums of both are
+    exact integers, the second stage differs in summation order and in the fp16 hi/lo split of the tensor-core path, so the
+    best costs agree to 1e-4 relative (1e-2 floor) and the labels wherever the two best costs are not within that margin"""
+    S = pytest.importorskip("stereo_matching_cuda_b200")
+    from stereo_matching_cuda_b200 import api
+
+    L, R = synth.make_pair(w, h, max(size_d, 2), channels=3, seed=w + 1)
+    p = api.default_params(dmin=-(size_d - 1), dmax=0, guide_mode=S.GUIDE_RGB)
+    monkeypatch.setenv("SB200_RGB_KERNEL", "4")
+    with S.Context(0) as ctx:
+        assert ctx.rgb_kernel == 4
+        a = ctx.pipeline(L, R, p, want=("disp_left", "disp_right", "best_left", "best_right", "occlusion", "filled"))
+    b = _rgb_pipeline_with_kernel(S, api, monkeypatch, 3, L, R, p)
+    for kb, kd in (("best_left", "disp_left"), ("best_right", "disp_right")):
+        rel = np.abs(a[kb] - b[kb]) / np.maximum(np.abs(b[kb]), 1e-2)
+        assert rel.max() < 1e-4, (kb, rel.max())
+        assert (a[kd] == b[kd]).mean() > 0.999
+
+
+@pytest.mark.gpu
 def test_gpu_rgb_three_stage_kernel_full_size_1080p_d256(monkeypatch):
     """BASELINE configs[2] at full size: both RGB kernels agree bit for bit on every output map, and the left labels
     recover the synthetic disparity staircase away from the band edges"""
