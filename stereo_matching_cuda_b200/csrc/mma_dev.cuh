@@ -5,6 +5,25 @@
 #pragma once
 #include "fused_dev.cuh"
 
+#if defined(RGBM_TIMELINE) || defined(MMA_TIMELINE)
+// developer instrumentation (tools/timeline_rgb.py, tools/timeline_gray.py): block 0 records, per role and iteration, the start clock and the cycles
+// spent in each kind of barrier wait
+#define TL_N 4096
+static __device__ long long g_tl[6][TL_N][4];
+#define TL_DECL long long tl_acc[3] = {0, 0, 0}; long long tl_t0 = 0, tl_m = 0;
+#define TL_BEGIN() do { tl_acc[0] = tl_acc[1] = tl_acc[2] = 0; tl_t0 = clock64(); } while (0)
+#define TL_WAIT(f, call) do { const long long t_ = clock64(); call; const long long d_ = clock64() - t_; tl_acc[f] += d_; tl_m += d_; } while (0)
+#define TL_MARK(seg) do { const long long t_ = clock64(); if ((seg) == 1) tl_m = t_; else if ((seg) == 2) { tl_acc[1] += t_ - tl_m; tl_m = t_; } else { tl_acc[2] += t_ - tl_m; } } while (0)
+#define TL_END(role, K) do { if (blockIdx.x == 0 && lane == 0 && (K) < TL_N) { g_tl[role][K][0] = tl_t0; g_tl[role][K][1] = tl_acc[0]; g_tl[role][K][2] = tl_acc[1]; g_tl[role][K][3] = tl_acc[2]; } } while (0)
+#else
+#define TL_DECL
+#define TL_BEGIN() do { } while (0)
+#define TL_WAIT(f, call) call
+#define TL_MARK(seg) do { } while (0)
+#define TL_END(role, K) do { } while (0)
+#endif
+
+
 namespace {
 
 __device__ __forceinline__ bool elect_one() {
