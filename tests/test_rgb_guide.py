@@ -98,8 +98,10 @@ def test_gpu_rgb_three_stage_kernel_equals_two_stage_bitwise(monkeypatch, w, h, 
 @pytest.mark.parametrize("w,h,size_d", [(470, 130, 21), (216, 40, 4), (33, 25, 3), (217, 19, 1), (900, 330, 70)])
 def test_gpu_rgb_tensor_core_kernel_agrees_with_the_shuffle_kernel(monkeypatch, w, h, size_d):
     """k_fused_mma_rgb (the default, SB200_RGB_KERNEL=4) against k_fused_cvf_rgb3 (=3): the first-stage sums of both are
-    exact integers, the second stage differs in summation order and in the fp16 hi/lo split of the tensor-core path, so the
-    best costs agree to 1e-4 relative (1e-2 floor) and the labels wherever the two best costs are not within that margin"""
+    exact integers, the second stage differs in summation order and in the fp16 hi/lo split of the tensor-core path.  Each
+    kernel is held to 1e-4 relative (1e-2 floor) against the ORACLE (tests above and the full-size test below), so against
+    each other the bound is the sum, 2e-4 (observed: 1.08e-4 at 900x330 D=70, nearly all of it the shuffle kernel's float
+    running sums over the 330-row band); labels agree on > 99.9 % of the pixels"""
     S = pytest.importorskip("stereo_matching_cuda_b200")
     from stereo_matching_cuda_b200 import api
 
@@ -112,7 +114,7 @@ def test_gpu_rgb_tensor_core_kernel_agrees_with_the_shuffle_kernel(monkeypatch, 
     b = _rgb_pipeline_with_kernel(S, api, monkeypatch, 3, L, R, p)
     for kb, kd in (("best_left", "disp_left"), ("best_right", "disp_right")):
         rel = np.abs(a[kb] - b[kb]) / np.maximum(np.abs(b[kb]), 1e-2)
-        assert rel.max() < 1e-4, (kb, rel.max())
+        assert rel.max() < 2e-4, (kb, rel.max())
         assert (a[kd] == b[kd]).mean() > 0.999
 
 
