@@ -164,6 +164,9 @@ typedef struct sb200_outputs {
     uint8_t* gray_right;   /* I_r main.cu:66 */
     uint8_t* mean_left;    /* mean1 main.cu:133 : (uchar)min((int)mean_I,255) debug image        */
     uint8_t* mean_right;   /* mean2 main.cu:134 */
+    float* subpixel_left;  /* NOT in the reference: disp_left refined by sb200_subpixel_refine_dev's parabola,
+                              pixels the L/R check marked keep their filled label.  Gray guide, tensor-core kernel;
+                              the call keeps the left view's filtered volume in the arena (size_d*w*h floats). */
 } sb200_outputs;
 
 /* Row-strip geometry for multi-GPU sharding: the images passed in are rows
@@ -218,6 +221,18 @@ int sb200_strip_halo_rows(const sb200_params* p);
  * guide/other are gray images on the device; best/disp are outputs. */
 int sb200_view_disparity_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_guide, const uint8_t* d_other,
                              int w, int h, int dmin, int size_d, float* d_best, float* d_disp, uint8_t* d_mean);
+/* The same kernel, keeping what the reference drops after the winner-take-all: d_volume[k*w*h + y*w + x] = the filtered cost
+ * q (compute_q, guidedFilter.cu:363-369) of disparity dmin + k, in the layout of the reference's cost volume
+ * (costVolume.cu:178).  d_best/d_disp may be NULL.  Tensor-core gray kernel only (SB200_ERR_UNSUPPORTED otherwise). */
+int sb200_view_volume_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_guide, const uint8_t* d_other, int w, int h,
+                          int dmin, int size_d, float* d_volume, float* d_best, float* d_disp);
+/* Sub-pixel refinement, NOT in the reference.  With k = (int)disp[i] - dmin and q-, q0, q+ the volume at
+ * k-1, k, k+1 of pixel i:  den = (q- - q0) + (q+ - q0);  out[i] = disp[i] + clamp(0.5 (q- - q+) / den, -0.5, 0.5) when
+ * 0 < k < size_d-1 and den > 0, else disp[i]; float operations in exactly this order (the oracle's so_subpixel_refine agrees
+ * bit for bit).  With d_occlusion != NULL, pixels the L/R check marked ((int)occlusion[i] < dmin, occlusion.cu:139)
+ * get d_filled[i] (disp[i] when d_filled is NULL) instead. */
+int sb200_subpixel_refine_dev(sb200_ctx* ctx, const float* d_volume, const float* d_disp, const float* d_occlusion,
+                              const float* d_filled, float* d_out, int w, int h, int dmin, int size_d);
 /* L/R check + fill alone: occlusion/filled outputs from the two label maps */
 int sb200_lr_check_fill_dev(sb200_ctx* ctx, const sb200_params* p, const float* d_dL, const float* d_dR, int w, int h,
                             int dOcclusion, float vMin, float* d_occlusion, float* d_filled);

@@ -655,3 +655,34 @@ void so_weighted_median(const unsigned char* gray, const float* occlusion, const
     }
     free(ws);
 }
+
+/* Sub-pixel refinement -- NOT in the reference; the definition is stereo_b200.h's
+ * sb200_subpixel_refine_dev: parabola through the filtered costs at label-1, label, label+1 of a kept volume
+ * vol[k*n + i] (the layout of costVolume.cu:178), float operations in this order, no contraction. */
+void so_subpixel_refine(const float* vol, const float* disp, const float* occlusion, const float* filled, float* out,
+                        int w, int h, int dmin, int size_d) {
+    size_t n = (size_t)w * h;
+    for (size_t i = 0; i < n; i++) {
+        float d = disp[i];
+        if (occlusion && (int)occlusion[i] < dmin) { /* the test of fill_occlusion, occlusion.cu:139 */
+            out[i] = filled ? filled[i] : d;
+            continue;
+        }
+        int k = (int)d - dmin;
+        float r = d;
+        if (k > 0 && k < size_d - 1) {
+            float qm = vol[(size_t)(k - 1) * n + i], q0 = vol[(size_t)k * n + i], qp = vol[(size_t)(k + 1) * n + i];
+            float t1 = qm - q0, t2 = qp - q0;
+            float den = t1 + t2;
+            if (den > 0.0f) {
+                float num = qm - qp;
+                float hn = 0.5f * num;
+                float t = hn / den;
+                if (t < -0.5f) t = -0.5f;
+                if (t > 0.5f) t = 0.5f;
+                r = d + t;
+            }
+        }
+        out[i] = r;
+    }
+}

@@ -54,7 +54,7 @@ class WMedianParams(C.Structure):
 
 class _Outputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("disp_left", "disp_right", "occlusion", "filled", "best_left", "best_right",
-                                          "gray_left", "gray_right", "mean_left", "mean_right")]
+                                          "gray_left", "gray_right", "mean_left", "mean_right", "subpixel_left")]
 
 
 class _Strip(C.Structure):
@@ -127,6 +127,8 @@ def load_library(path=None):
         "sb200_pipeline_strip_dev": (ip, [vp, PP, vp, vp, ip, ip, C.POINTER(_Strip), C.POINTER(_Outputs)]),
         "sb200_strip_halo_rows": (ip, [PP]),
         "sb200_view_disparity_dev": (ip, [vp, PP, vp, vp, ip, ip, ip, ip, vp, vp, vp]),
+        "sb200_view_volume_dev": (ip, [vp, PP, vp, vp, ip, ip, ip, ip, vp, vp, vp]),
+        "sb200_subpixel_refine_dev": (ip, [vp, vp, vp, vp, vp, vp, ip, ip, ip, ip]),
         "sb200_lr_check_fill_dev": (ip, [vp, PP, vp, vp, ip, ip, ip, fp, vp, vp]),
         "sb200_ctx_enable_timing": (ip, [vp, ip]),
         "sb200_last_timing": (ip, [vp] + [C.POINTER(fp)] * 4),
@@ -360,6 +362,7 @@ class Context:
 
     # ---- fused pipeline -----------------------------------------------------------------
     _F32 = ("disp_left", "disp_right", "occlusion", "filled", "best_left", "best_right")
+    _F32_OPT = ("subpixel_left",)  # beyond the reference: only when asked for by name
     _U8 = ("gray_left", "gray_right", "mean_left", "mean_right")
 
     def write_mat(self, mat):
@@ -396,7 +399,9 @@ class Context:
                 want = tuple(k for k in want if not k.startswith("mean_"))
         res, o = {}, _Outputs()
         for k in want:
-            res[k] = np.empty((h, w), np.float32 if k in self._F32 else np.uint8)
+            if k not in self._F32 + self._F32_OPT + self._U8:
+                raise TypeError(f"unknown output {k}")
+            res[k] = np.empty((h, w), np.uint8 if k in self._U8 else np.float32)
             setattr(o, k, res[k].ctypes.data)
         self._ck(self.lib.sb200_pipeline(self.h, C.byref(p), _ptr(left), _ptr(right), ch, w, h, C.byref(o)))
         return res
@@ -441,9 +446,9 @@ class Context:
     def _dev_outputs(self, outs, numel=0):
         o = _Outputs()
         for k, t in outs.items():
-            if k not in self._F32 + self._U8:
+            if k not in self._F32 + self._F32_OPT + self._U8:
                 raise TypeError(f"unknown output {k}")
-            self._dev_check(t, k, numel, "float32" if k in self._F32 else "uint8")
+            self._dev_check(t, k, numel, "uint8" if k in self._U8 else "float32")
             setattr(o, k, t if isinstance(t, int) else t.data_ptr())
         return o
 
@@ -493,6 +498,25 @@ class Context:
     def strip_halo_rows(self, params=None):
         p = params or default_params()
         return self.lib.sb200_strip_halo_rows(C.byref(p))
+
+    def view_volume_dev(self, d_guide, d_other, w, h, dmin, size_d, d_volume, d_best=None, d_disp=None, params=None):
+        """the fused view kernel keeping the filtered cost volume q: d_volume is (size_d, h, w) float32 on the device"""
+        p = params or default_params()
+        for name, t in (("guide", d_guide), ("other", d_other)):
+            self._dev_check(t, name, w * h, "uint8")
+        self._dev_check(d_volume, "volume", size_d * w * h, "float32")
+        for name, t in (("best", d_best), ("disp", d_disp)):
+            self._dev_check(t, name, w * h, "float32")
+        self._ck(self.lib.sb200_view_volume_dev(self.h, C.byref(p), _ptr(d_guide), _ptr(d_other), w, h, dmin, size_d,
+                                                _ptr(d_volume), _ptr(d_best), _ptr(d_disp)))
+
+    def subpixel_refine_dev(self, d_volume, d_disp, d_out, w, h, dmin, size_d, d_occlusion=None, d_filled=None):
+        """parabola through the filtered costs at label-1, label, label+1 (beyond the reference; stereo_b200.h)"""
+        self._dev_check(d_volume, "volume", size_d * w * h, "float32")
+        for name, t in (("disp", d_disp), ("out", d_out), ("occlusion", d_occlusion), ("filled", d_filled)):
+            self._dev_check(t, name, w * h, "float32")
+        self._ck(self.lib.sb200_subpixel_refine_dev(self.h, _ptr(d_volume), _ptr(d_disp), _ptr(d_occlusion), _ptr(d_filled),
+                                                    _ptr(d_out), w, h, dmin, size_d))
 
     def view_disparity_dev(self, d_guide, d_other, w, h, dmin, size_d, d_best, d_disp, d_mean=None, params=None):
         p = params or default_params()

@@ -361,7 +361,7 @@ size_t rgb_fused_ws_bytes(const sb200_ctx* ctx, const sb200_params* p, int w, in
 }
 
 // arena bytes pipeline_core needs for one call
-size_t pipeline_ws_bytes(const sb200_ctx* ctx, const sb200_params* p, int w, const SbFusedGeom& g) {
+size_t pipeline_ws_bytes(const sb200_ctx* ctx, const sb200_params* p, int w, const SbFusedGeom& g, const sb200_outputs* o = nullptr) {
     const int size_d = p->dmax - p->dmin + 1;
     const size_t n_held = (size_t)w * g.h, n_out = (size_t)w * g.rows_out;
     const int dabs = max(abs(p->dmin), abs(p->dmax));
@@ -370,6 +370,7 @@ size_t pipeline_ws_bytes(const sb200_ctx* ctx, const sb200_params* p, int w, con
                        : (p->box_mode == SB200_BOX_SAT ? rgb_ws_bytes(n_held) : rgb_fused_ws_bytes(ctx, p, w, g.h, g.rows_out, dabs, size_d));
     bytes += 2 * sb_align(n_held) + 4 * sb_align(n_out * 4) + 4096;
     if (g.rows_out != g.h) bytes += 2 * sb_align(n_held);  // strips stage the mean images on held rows
+    if (o && o->subpixel_left) bytes += sb_align((size_t)size_d * n_out * 4) + 2 * sb_align(n_out * 4);  // the left view's filtered volume
     return bytes;
 }
 
@@ -379,7 +380,7 @@ int pipeline_core(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, 
     const int size_d = p->dmax - p->dmin + 1;
     const size_t n_held = (size_t)w * g.h;
     const size_t n_out = (size_t)w * g.rows_out;
-    if (reserve) SB_TRY(sb_ws_reserve(ctx, pipeline_ws_bytes(ctx, p, w, g)));
+    if (reserve) SB_TRY(sb_ws_reserve(ctx, pipeline_ws_bytes(ctx, p, w, g, o)));
     const bool full = (g.rows_out == g.h);
     const bool rgb_guide = (p->guide_mode == SB200_GUIDE_RGB);
     // RGB guide: fused kernel (fused_cvf_rgb.cu); box_mode SAT selects the staged, materialising path instead
@@ -394,6 +395,10 @@ int pipeline_core(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, 
     if (rgb_staged && !full) return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "staged RGB guide needs a whole frame");
     if (rgb_guide && (o->mean_left || o->mean_right))
         return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "mean_left/mean_right are gray-guide outputs");
+    // sub-pixel refinement keeps the left view's filtered volume: only the tensor-core gray kernel stores it
+    const bool subpix = o->subpixel_left != nullptr;
+    if (subpix && (rgb_guide || gray_staged || ctx->gray_kernel != 1 || !sbf_mma_supported(p)))
+        return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "subpixel_left: gray guide on the tensor-core fused kernel only");
     const uint8_t* gl = d_left;
     const uint8_t* gr = d_right;
     if (channels != 1) {
@@ -450,13 +455,26 @@ int pipeline_core(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, 
         SB_TRY(guided_filter_staged(ctx, &ps, gl, nullptr, bL, dL, mL, w, g.h, size_d, p->dmin, gr));
         ctx->ws_off = mark;
         SB_TRY(guided_filter_staged(ctx, &ps, gr, nullptr, bR, dR, mR, w, g.h, size_d, -p->dmax, gl));
-    } else
-    SB_TRY(sbf_pair_disparity(ctx, p, gl, gr, g, o->best_left, dL, o->best_right, dR, full ? mL : mLh, full ? mR : mRh));
+    } else {
+        float* vol = nullptr;
+        if (subpix) SB_TRY(ws_get(ctx, &vol, (size_t)size_d * n_out));
+        ctx->qvol[0] = vol;  // for this launch only
+        const int rc = sbf_pair_disparity(ctx, p, gl, gr, g, o->best_left, dL, o->best_right, dR, full ? mL : mLh, full ? mR : mRh);
+        ctx->qvol[0] = nullptr;
+        SB_TRY(rc);
+        if (subpix) {
+            float *occ = o->occlusion, *fil = o->filled;
+            if (!occ) SB_TRY(ws_get(ctx, &occ, n_out));
+            if (!fil) SB_TRY(ws_get(ctx, &fil, n_out));
+            SB_TRY(sbk_lr_check_fill(ctx, dL, dR, w, g.rows_out, p->dmin - 100, p->d_lr, (float)p->dmin, occ, fil));
+            SB_TRY(sbk_subpixel(ctx, vol, dL, occ, fil, o->subpixel_left, n_out, p->dmin, size_d));
+        }
+    }
     if (!full) {
         if (mL) SB_CUDA(ctx, cudaMemcpyAsync(mL, mLh + out_off, n_out, cudaMemcpyDeviceToDevice, ctx->stream));
         if (mR) SB_CUDA(ctx, cudaMemcpyAsync(mR, mRh + out_off, n_out, cudaMemcpyDeviceToDevice, ctx->stream));
     }
-    if (o->occlusion || o->filled)
+    if ((o->occlusion || o->filled) && !subpix)
         SB_TRY(sbk_lr_check_fill(ctx, dL, dR, w, g.rows_out, p->dmin - 100, p->d_lr, (float)p->dmin, o->occlusion,
                                  o->filled));
     if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));
@@ -567,6 +585,32 @@ int sb200_view_disparity_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_
     return sbf_view_disparity(ctx, p, d_guide, d_other, g, dmin, size_d, d_best, d_disp, d_mean);
 }
 
+// the same kernel, keeping the filtered volume (tensor-core gray kernel only)
+int sb200_view_volume_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_guide, const uint8_t* d_other, int w, int h,
+                          int dmin, int size_d, float* d_volume, float* d_best, float* d_disp) {
+    DevGuard dev_guard__(ctx);
+    SB_TRY(check_params(ctx, p));
+    REQUIRE(ctx, d_guide && d_other && d_volume && w > 1 && h > 0 && size_d > 0, "null pointer or empty");
+    if (ctx->gray_kernel != 1 || !sbf_fused_supported(p) || !sbf_mma_supported(p))
+        return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "filtered volume: tensor-core fused kernel only (radius 9, small exact cost lattice)");
+    const int dabs = max(abs(dmin), abs(dmin + size_d - 1));
+    SB_TRY(sb_ws_reserve(ctx, sbf_workspace_bytes(ctx, w, h, h, dabs, size_d, 1) + 2 * sb_align((size_t)w * h * 4) + 4096));
+    float* best = d_best;
+    if (!best && !d_disp) SB_TRY(ws_get(ctx, &best, (size_t)w * h));  // the kernel's merge wants one of the two
+    SbFusedGeom g{w, h, 0, h, 0, h};
+    ctx->qvol[0] = d_volume;
+    const int rc = sbf_view_disparity(ctx, p, d_guide, d_other, g, dmin, size_d, best, d_disp, nullptr);
+    ctx->qvol[0] = nullptr;
+    return rc;
+}
+
+int sb200_subpixel_refine_dev(sb200_ctx* ctx, const float* d_volume, const float* d_disp, const float* d_occlusion,
+                              const float* d_filled, float* d_out, int w, int h, int dmin, int size_d) {
+    DevGuard dev_guard__(ctx);
+    REQUIRE(ctx, d_volume && d_disp && d_out && w > 0 && h > 0 && size_d > 0, "null pointer or empty image");
+    return sbk_subpixel(ctx, d_volume, d_disp, d_occlusion, d_filled, d_out, (size_t)w * h, dmin, size_d);
+}
+
 // ---- 8-bit visualisation on the device ----------------------------------------
 int sb200_write_mat_dev(sb200_ctx* ctx, const float* d_mat, uint8_t* d_out, int w, int h) {
     DevGuard dev_guard__(ctx);
@@ -641,7 +685,7 @@ int sb200_pipeline_batch_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_
     SbFusedGeom g{w, h, 0, h, 0, h};
     for (int i = 0; i < n_pairs; i++) {
         sb200_outputs o = *d_out;
-        float** fp[] = {&o.disp_left, &o.disp_right, &o.occlusion, &o.filled, &o.best_left, &o.best_right};
+        float** fp[] = {&o.disp_left, &o.disp_right, &o.occlusion, &o.filled, &o.best_left, &o.best_right, &o.subpixel_left};
         for (float** f : fp)
             if (*f) *f += (size_t)i * n;
         uint8_t** up[] = {&o.gray_left, &o.gray_right, &o.mean_left, &o.mean_right};
@@ -666,7 +710,8 @@ int sb200_pipeline(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h_left,
     size_t bytes = (p->guide_mode != SB200_GUIDE_RGB ? (sbf_fused_supported(p) ? sbf_workspace_bytes(ctx, w, h, h, dabs, size_d, 2) : gf_ws_bytes(n) + 2 * sb_align(n))
                     : (p->box_mode == SB200_BOX_SAT ? rgb_ws_bytes(n) : rgb_fused_ws_bytes(ctx, p, w, h, h, dabs, size_d))) +
                    2 * sb_align(n) + 4 * sb_align(n * 4) + 4096;
-    bytes += 2 * sb_align(n * channels) + 6 * sb_align(n * 4) + 4 * sb_align(n) + 4096;
+    bytes += 2 * sb_align(n * channels) + 7 * sb_align(n * 4) + 4 * sb_align(n) + 4096;
+    if (h_out->subpixel_left) bytes += sb_align((size_t)size_d * n * 4) + 2 * sb_align(n * 4);
     SB_TRY(sb_ws_reserve(ctx, bytes));
     uint8_t *dl, *dr;
     SB_TRY(ws_get(ctx, &dl, n * channels));
@@ -674,9 +719,9 @@ int sb200_pipeline(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h_left,
     SB_TRY(h2d(ctx, dl, h_left, n * channels));
     SB_TRY(h2d(ctx, dr, h_right, n * channels));
     sb200_outputs d{};
-    float* const hf[] = {h_out->disp_left, h_out->disp_right, h_out->occlusion, h_out->filled, h_out->best_left, h_out->best_right};
-    float** const df[] = {&d.disp_left, &d.disp_right, &d.occlusion, &d.filled, &d.best_left, &d.best_right};
-    for (int i = 0; i < 6; i++)
+    float* const hf[] = {h_out->disp_left, h_out->disp_right, h_out->occlusion, h_out->filled, h_out->best_left, h_out->best_right, h_out->subpixel_left};
+    float** const df[] = {&d.disp_left, &d.disp_right, &d.occlusion, &d.filled, &d.best_left, &d.best_right, &d.subpixel_left};
+    for (int i = 0; i < 7; i++)
         if (hf[i]) SB_TRY(ws_get(ctx, df[i], n));
     uint8_t* const hu[] = {h_out->gray_left, h_out->gray_right, h_out->mean_left, h_out->mean_right};
     uint8_t** const du[] = {&d.gray_left, &d.gray_right, &d.mean_left, &d.mean_right};
@@ -684,7 +729,7 @@ int sb200_pipeline(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h_left,
         if (hu[i]) SB_TRY(ws_get(ctx, du[i], n));
     SbFusedGeom g{w, h, 0, h, 0, h};
     SB_TRY(pipeline_core(ctx, p, dl, dr, channels, w, g, &d, false));
-    for (int i = 0; i < 6; i++)
+    for (int i = 0; i < 7; i++)
         if (hf[i]) SB_TRY(d2h(ctx, hf[i], *df[i], n * 4));
     for (int i = 0; i < 4; i++)
         if (hu[i]) SB_TRY(d2h(ctx, hu[i], *du[i], n));
@@ -760,6 +805,7 @@ int sb200_pipeline_strips_nccl(sb200_ctx* ctx, const sb200_params* p, void* nccl
     REQUIRE(ctx, world == 1 || rows >= halo, "a strip must be at least 2*radius rows tall (its neighbours need that many)");
     REQUIRE(ctx, (rank == 0) == (y0 == 0) && (rank == world - 1) == (y0 + rows == frame_h), "strips must tile the frame in rank order");
     REQUIRE(ctx, world == 1 || nccl_comm, "communicator is NULL");
+    REQUIRE(ctx, !d_out->subpixel_left, "subpixel_left: not in the NCCL strip entry (use sb200_pipeline_strip_dev)");
     const int top = rank > 0 ? halo : 0, bot = rank < world - 1 ? halo : 0;
     if (world > 1) SB_TRY(nccl_load(ctx));
     const size_t row_bytes = (size_t)w * channels;
@@ -804,6 +850,7 @@ int sb200_pipeline_batch(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h
     SB_TRY(check_params(ctx, p));
     REQUIRE(ctx, h_left && h_right && h_out && w > 1 && h > 0 && n_pairs > 0, "null pointer or empty batch");
     REQUIRE(ctx, channels == 1 || channels >= 3, "channels must be 1 (gray) or >= 3");
+    REQUIRE(ctx, !h_out->subpixel_left, "subpixel_left: not in the overlapped batch entry (use sb200_pipeline / sb200_pipeline_batch_dev)");
     const size_t n = (size_t)w * h;
     if (!ctx->batch_ready) {
         SB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));

@@ -41,6 +41,9 @@ struct sb200_ctx {
     bool batch_ready = false;
     char* stage = nullptr;
     size_t stage_cap = 0;
+    // optional: the tensor-core gray kernel also stores the filtered cost volume q of view v here (D-major planes of
+    // rows_out x w floats, costVolume.cu:178's layout); set by the entry points that want it for ONE call, then cleared
+    float* qvol[2] = {nullptr, nullptr};
     int rgb_kernel = 4;  // RGB-guide fused kernel: 4 = tensor-core (fused_mma_rgb.cu), 3 = three-stage shuffle kernel
                          // (fused_cvf_rgb3.cu), 2 = its two-stage predecessor (fused_cvf_rgb.cu)
 };
@@ -141,6 +144,8 @@ int sbk_weighted_median(sb200_ctx* ctx, const uint8_t* gray, const float* occ, c
 int sbk_lr_check_fill(sb200_ctx* ctx, const float* dL, const float* dR, int w, int h, int dOcc, int d_lr, float vMin,
                       float* occ, float* filled);
 int sbk_fill_f32(sb200_ctx* ctx, float* dst, float v, size_t n);
+int sbk_subpixel(sb200_ctx* ctx, const float* vol, const float* disp, const float* occ, const float* filled, float* out,
+                 size_t n, int dmin, int size_d);
 int sbk_write_mat(sb200_ctx* ctx, const float* mat, uint8_t* out, size_t n, float* scratch);  // scratch: 2*ceil(n/1024)+2 words
 int sbk_fl_to_ch2(sb200_ctx* ctx, const float* image, uint8_t* result, int mn, int mx, size_t len);
 int sbk_rgb_split(sb200_ctx* ctx, const uint8_t* rgb, int ch, float* r, float* g, float* b, size_t n);

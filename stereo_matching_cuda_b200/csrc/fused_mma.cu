@@ -106,6 +106,7 @@ struct MmaArgs {
     int dmin[2], size_d;
     int n_strips, n_bands, band_rows, n_chunks, chunk_d, n_views;
     float2* BL;
+    float* QV[2];          // optional, per VIEW: filtered cost volume q, [size_d][rows_out][w]; NULL = not stored
     int pitchS;
     float S, scale, inv_scale;
     unsigned wI2, wG2, tc2, tg2;  // half2 broadcasts: lattice weights nI, nG; thresholds th_color, 2*th_grad
@@ -121,6 +122,9 @@ constexpr int M_REGS_A = (M_WARPS == 16) ? 112 : (M_WARPS == 20 ? 80 : 72);
 static_assert(32 * NWB * M_REGS_B + 32 * NWC * M_REGS_C + 32 * (M_WARPS - NWB - NWC) * M_REGS_A <= M_THREADS * M_REGS_LAUNCH,
               "register pool of the block");
 
+// QVOL: role C also stores the filtered cost q of every cell (sb200_view_volume_dev, subpixel_left).  A separate
+// instantiation: the extra stores in the default kernel's role-C loop cost 6 % even when switched off at run time.
+template <bool QVOL>
 __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     MSmem& sm = *reinterpret_cast<MSmem*>(smem_raw);
@@ -367,6 +371,9 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
         // this thread finishes rows yb0 + MR e + CR c + {0 .. CR-1}
         float2* const bl0 = A.BL + (size_t)(chunk * 2 + view) * planeS + (size_t)(yb0 - A.y_out0 + CR * c) * pitchS + x;
         const int band_rows = yb1 - yb0;
+        // optional filtered-cost volume (compute_q per slice, guidedFilter.cu:363-369, kept instead of dropped after the WTA)
+        const size_t qplane = (size_t)A.rows_out * A.w;
+        float* const qv0 = (QVOL && A.QV[view]) ? A.QV[view] + (size_t)(chunk * A.chunk_d) * qplane + (size_t)(yb0 - A.y_out0 + CR * c) * A.w + x : nullptr;
         const uint32_t td2 = tl + TC_D2 + 16 * CR * c;
         const uint32_t gcs = smem_addr(&sm.gc[0][0]) + (uint32_t)(CR * c) * GC_ROW + (uint32_t)l * 2;
         const uint32_t pbs = smem_addr(&sm.gc[0][0]) + GC_PB + (uint32_t)(CR * c) * PB_ROW + (uint32_t)l * 8;
@@ -380,6 +387,7 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
             const bool ld_ok = g > 0;
             const float2 binit = make_float2(BEST_INIT_BITS_F, 0.0f);
             float2* blp = bl0;
+            float* qvp = (QVOL && qv0) ? qv0 + (size_t)(g * M_ND) * qplane : nullptr;
 #pragma unroll 1
             for (int it = 0; it < niter; it++, K++) {
                 const int e = it - WARM_IT;
@@ -444,6 +452,14 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
                             for (int d = 0; d < M_ND; d++)
                                 if (d >= dact) q[d] = __int_as_float(0x7f800000);
                         }
+                        if (QVOL && qvp && st_ok[j]) {
+                            float* qd = qvp + (size_t)j * A.w;
+#pragma unroll
+                            for (int d = 0; d < M_ND; d++) {
+                                if (d < dact) *qd = q[d];
+                                qd += qplane;
+                            }
+                        }
                         // ascending d, `best >= q`: minimum, the later index on a tie (guidedFilter.cu:406), as a tournament
                         float m1[4], a1[4];
 #pragma unroll
@@ -466,6 +482,7 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
                     }
                 }
                 blp += (size_t)MR * pitchS;
+                if (QVOL && qvp) qvp += (size_t)MR * A.w;
                 // the stores above are read back by the TMA producer (async proxy) one group later
                 asm volatile("fence.proxy.async.global;" ::: "memory");
                 __syncwarp();
@@ -870,6 +887,7 @@ int sbf_run_fused_mma(sb200_ctx* ctx, const sb200_params* p, const uint8_t* cons
     A.chunk_d = plan.chunk_d;
     A.n_views = n_views;
     A.BL = BL;
+    for (int v = 0; v < 2; v++) A.QV[v] = v < n_views ? ctx->qvol[v] : nullptr;
     A.pitchS = pitchS;
     A.S = (float)S;
     A.scale = scale;
@@ -885,11 +903,13 @@ int sbf_run_fused_mma(sb200_ctx* ctx, const sb200_params* p, const uint8_t* cons
 
     const size_t smem = sizeof(MSmem);
     if (!ctx->mma_attr_set) {
-        SB_CUDA(ctx, cudaFuncSetAttribute(k_fused_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_CUDA(ctx, cudaFuncSetAttribute(k_fused_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_CUDA(ctx, cudaFuncSetAttribute(k_fused_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->mma_attr_set = true;
     }
     const int nblocks = plan.n_strips * plan.n_bands * plan.n_chunks * n_views;
-    SB_LAUNCH(ctx, k_fused_mma, nblocks, M_THREADS, smem, A);
+    if (A.QV[0] || A.QV[1]) SB_LAUNCH(ctx, k_fused_mma<true>, nblocks, M_THREADS, smem, A);
+    else SB_LAUNCH(ctx, k_fused_mma<false>, nblocks, M_THREADS, smem, A);
     if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     for (int v = 0; v < n_views; v++) {
         if (!best[v] && !disp[v]) continue;

@@ -503,6 +503,38 @@ int sbk_weighted_median(sb200_ctx* ctx, const uint8_t* gray, const float* occ, c
 }
 
 // ---------------------------------------------------------------------------------------
+// Sub-pixel refinement (beyond the reference): the vertex of the parabola through the filtered costs at
+// label-1, label, label+1 of the kept volume.  Float operations in a fixed order (no contraction), so the oracle's
+// so_subpixel_refine agrees bit for bit on the same volume.
+__global__ void k_subpixel(const float* __restrict__ vol, const float* __restrict__ disp, const float* __restrict__ occ,
+                           const float* __restrict__ filled, float* __restrict__ out, size_t n, int dmin, int size_d) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float d = disp[i];
+    if (occ && (int)occ[i] < dmin) {  // marked by the L/R check (the test of fill_occlusion, occlusion.cu:139): keeps its filled label
+        out[i] = filled ? filled[i] : d;
+        return;
+    }
+    const int k = (int)d - dmin;
+    float r = d;
+    if (k > 0 && k < size_d - 1) {
+        const float qm = vol[(size_t)(k - 1) * n + i], q0 = vol[(size_t)k * n + i], qp = vol[(size_t)(k + 1) * n + i];
+        const float den = __fadd_rn(__fsub_rn(qm, q0), __fsub_rn(qp, q0));
+        if (den > 0.0f) {
+            float t = __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(qm, qp)), den);
+            t = fminf(0.5f, fmaxf(-0.5f, t));
+            r = __fadd_rn(d, t);
+        }
+    }
+    out[i] = r;
+}
+int sbk_subpixel(sb200_ctx* ctx, const float* vol, const float* disp, const float* occ, const float* filled, float* out,
+                 size_t n, int dmin, int size_d) {
+    EW_LAUNCH(k_subpixel, n, vol, disp, occ, filled, out, n, dmin, size_d);
+    return SB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // 8-bit visualisation on the device: write_mat's normalisation (main.cu:13-35) and flToCh2OnGPU
 // (occlusion.cu:230-237), so that a driver downloads 8-bit images instead of float maps.
 // write_mat scans sequentially with `if (v > max) max = v; else if (v <= min) min = v;`: a value that RAISES the running

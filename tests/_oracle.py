@@ -71,6 +71,7 @@ class Oracle:
         L.so_pipeline_gray.argtypes = [C.POINTER(SoParams), u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int] + [f32p] * 6 + [
             C.c_void_p] * 4
         L.so_write_mat.argtypes = [f32p, u8p, C.c_int, C.c_int]
+        L.so_subpixel_refine.argtypes = [f32p, f32p, C.c_void_p, C.c_void_p, f32p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.so_weighted_median.argtypes = [u8p, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int]
         L.so_view_disparity_rgb.argtypes = [C.POINTER(SoParams), u8p, C.c_int, u8p, u8p, f32p, f32p, C.c_void_p, C.c_int,
                                             C.c_int, C.c_int, C.c_int]
@@ -216,6 +217,13 @@ class Oracle:
         out = np.empty((h, w), np.float32)
         self.lib.so_weighted_median(g, oc, fl, out, w, h, int(dmin), int(size_d), int(radius), float(sigma_space),
                                     float(sigma_color), int(nthreads))
+        return out
+
+    def subpixel_refine(self, vol, disp, dmin, occlusion=None, filled=None):
+        size_d, h, w = vol.shape
+        out = np.empty((h, w), np.float32)
+        self.lib.so_subpixel_refine(np.ascontiguousarray(vol, np.float32), np.ascontiguousarray(disp, np.float32),
+                                    _opt(occlusion), _opt(filled), out, w, h, dmin, size_d)
         return out
 
     def write_mat(self, mat):

@@ -667,3 +667,73 @@ def test_weighted_median_equals_the_oracle(oracle, w, h, size_d, radius):
     assert np.array_equal(got, want)
     assert np.array_equal(got[~marked], out["filled"][~marked])
     assert got.min() >= dmin and got.max() <= 0
+
+
+def _oracle_filtered_volume(oracle, guide, other, size_d, dmin):
+    """the filtered cost q of every slice (compute_q, guidedFilter.cu:363-369), exact box mode: what the reference's
+    per-slice loop (guidedFilter.cu:171-238) holds before dispSelectOnGPU consumes it"""
+    po = oracle.params(box_mode=O.BOX_EXACT, nthreads=1)
+    I, mI, vI, _ = oracle.guide_stats(guide, po)
+    cost = oracle.cost_volume(guide, other, size_d, dmin, po)
+    return np.stack([oracle.guided_slice(I, mI, vI, cost[k], po)[0] for k in range(size_d)])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,size_d", [(300, 120, 24), (111, 45, 9), (257, 33, 67)])
+def test_filtered_volume_and_subpixel_refinement(oracle, w, h, size_d):
+    """SURVEY 8f.3 (beyond the reference).  (1) The volume the fused kernel keeps on request equals the oracle's filtered
+    slices (1e-4 relative, 1e-2 floor) and its per-pixel minimum IS the best-cost map, bit for bit.  (2) The refinement
+    kernel equals the oracle's restatement bit for bit on that volume.  (3) Through the pipeline: marked pixels keep
+    their filled label, the others move by at most half a label."""
+    import torch
+
+    L, R = synth.make_pair(w, h, max(size_d, 2), seed=3 * w + size_d)
+    dmin = -(size_d - 1)
+    p = api.default_params(dmin=dmin, dmax=0)
+    dev = torch.device("cuda:0")
+    with S.Context(0) as ctx:
+        dl, dr = torch.from_numpy(L).to(dev), torch.from_numpy(R).to(dev)
+        vol = torch.full((size_d, h, w), float("nan"), dtype=torch.float32, device=dev)
+        best, disp = (torch.empty((h, w), dtype=torch.float32, device=dev) for _ in range(2))
+        ctx.view_volume_dev(dl, dr, w, h, dmin, size_d, vol, best, disp, params=p)
+        ref_best, ref_disp = (torch.empty((h, w), dtype=torch.float32, device=dev) for _ in range(2))
+        ctx.view_disparity_dev(dl, dr, w, h, dmin, size_d, ref_best, ref_disp, params=p)
+        sub = torch.empty((h, w), dtype=torch.float32, device=dev)
+        ctx.subpixel_refine_dev(vol, disp, sub, w, h, dmin, size_d)
+        ctx.synchronize()
+        vol_h, best_h, disp_h, sub_h = vol.cpu().numpy(), best.cpu().numpy(), disp.cpu().numpy(), sub.cpu().numpy()
+        # keeping the volume does not change the kernel's other outputs
+        assert np.array_equal(best_h, ref_best.cpu().numpy()) and np.array_equal(disp_h, ref_disp.cpu().numpy())
+        out = ctx.pipeline(L, R, p, want=("disp_left", "occlusion", "filled", "subpixel_left"))
+        plain = ctx.pipeline(L, R, p, want=("disp_left", "occlusion", "filled"))
+    assert not np.isnan(vol_h).any()
+    q = _oracle_filtered_volume(oracle, L, R, size_d, dmin)
+    rel = np.abs(vol_h - q) / np.maximum(np.abs(q), 1e-2)
+    assert rel.max() < RTOL_BEST, rel.max()
+    assert np.array_equal(vol_h.min(axis=0), best_h)
+    k = (disp_h - dmin).astype(np.int64)
+    assert np.array_equal(np.take_along_axis(vol_h, k[None], 0)[0], best_h)
+    # (2) bit-exact refinement on the same volume
+    want = oracle.subpixel_refine(vol_h, disp_h, dmin)
+    assert np.array_equal(sub_h.view(np.uint32), want.view(np.uint32))
+    assert np.abs(sub_h - disp_h).max() <= 0.5
+    assert (sub_h != disp_h).mean() > 0.3  # the synthetic pair has texture: most interior labels do move
+    edge = (k == 0) | (k == size_d - 1)
+    assert np.array_equal(sub_h[edge], disp_h[edge])
+    # (3) pipeline output
+    for name in ("disp_left", "occlusion", "filled"):
+        assert np.array_equal(out[name], plain[name]), name
+    marked = out["occlusion"].astype(np.int32) < dmin
+    assert np.array_equal(out["subpixel_left"][marked], out["filled"][marked])
+    assert np.array_equal(out["subpixel_left"], oracle.subpixel_refine(vol_h, out["disp_left"], dmin, out["occlusion"], out["filled"]))
+
+
+@pytest.mark.gpu
+def test_subpixel_is_refused_where_it_is_not_built(ctx):
+    L, R = synth.make_pair(96, 40, 6, channels=3, seed=1)
+    p = api.default_params(dmin=-5, dmax=0, guide_mode=S.GUIDE_RGB)
+    with pytest.raises(S.StereoB200Error):
+        ctx.pipeline(L, R, p, want=("disp_left", "subpixel_left"))
+    p2 = api.default_params(dmin=-5, dmax=0, radius=4)  # staged path
+    with pytest.raises(S.StereoB200Error):
+        ctx.pipeline(L[..., 0].copy(), R[..., 0].copy(), p2, want=("disp_left", "subpixel_left"))
