@@ -12,23 +12,29 @@
 // H = Band x V with Band[m][k] = 1 for m <= k <= m+18: tcgen05.mma does it off the SM's issue slots and data pipe.
 //
 // Decomposition.  A block owns a strip of 128 columns (110 valid after the two cascaded radius-9 filters) and a group
-// of 8 consecutive disparities, and marches down the rows two at a time.  Tensor Memory lane = image column, so after
-// an MMA every thread holds ITS column for all 8 disparities and 2 rows: guide operands are loaded once per column and
-// row (not per disparity), and the winner-take-all over the 8 disparities is a register tournament.
-//   role A (10 warps)  lattice cost P (packed half, 2 disparities per instruction) for 160 cost columns x 8 d x 2 rows;
+// of 8 consecutive disparities, and marches down the rows four at a time (hand-offs between the roles every two rows:
+// every buffer between two roles is two halves).  Tensor Memory lane = image column, so after an MMA every thread holds
+// ITS column for all 8 disparities: guide operands are loaded once per column and row (not per disparity), and the
+// winner-take-all over the 8 disparities is a register tournament.
+//   role A (5 warps)   lattice cost P (packed half, 2 disparities per instruction) for 160 cost columns x 8 d x 4 rows;
 //                      EXACT fp16 pieces of P and I*P:  P, (I&15)*P, (I&240)*P;  what enters the MMA is the vertical
 //                      difference  piece(y) - piece(y-19)  (exact in fp16), the 19-row ring of P lives in shared memory
 //   MMA 1 (tensor)     dH[x][n] = sum_k Band[x][k] * dPiece[k][n]   (K = 160, fp32 accumulate: exact integers)
-//   role B (4 warps)   S_p += dH_p, S_Ip += dH_Ip  (the 2-D box sums, exact);  a, b (guidedFilter.cu:345-354);
-//                      split into fp16 hi + lo (22 significant bits), scaled by a power of two
-//   MMA 2 (tensor)     H_a, H_b = Band x (hi) + Band x (lo)
-//   role C (4 warps)   vertical running sums of H with a 19-slot ring in Tensor Memory (re-summed every 16 iterations,
-//                      which bounds the float drift), q = mean_a*I + mean_b, tournament over the 8 disparities with the
-//                      reference's `best >= q` rule, read-modify-write of the chunk's (best,label) plane: once per
-//                      8 disparities (fused_cvf.cu: once per 4)
-//   1 warp issues the MMAs (warp-uniform descriptors, one elected lane), 1 warp runs the TMA producer.
+//   role B (4 warps)   S_p += dH_p, S_Ip += dH_Ip  (the 2-D box sums, exact);  a, b (guidedFilter.cu:345-354); their
+//                      vertical 19-row sums as running sums with a 19-slot ring in Tensor Memory (re-summed every 64
+//                      rows, which bounds the float drift); split into fp16 hi + lo (22 significant bits, scaled by a
+//                      power of two)
+//   MMA 2 (tensor)     H_a, H_b = Band x (hi) - Band x (hi - value): the finished 19 x 19 window sums of a and b
+//   role C (4 warps)   q = mean_a*(I-128) + mean(b + 128 a), tournament over the 8 disparities with the reference's
+//                      `best >= q` rule, read-modify-write of the chunk's (best,label) plane: once per 8 disparities
+//                      (fused_cvf.cu: once per 4); stateless between iterations.  The <true> instantiation also
+//                      stores q itself (the filtered cost volume the reference drops after dispSelectOnGPU)
+//   2 warps issue the MMAs (warp-uniform descriptors, one elected lane each), 1 warp runs the TMA producer.
 // Operands come from strip-tiled planes written by three small preparation kernels (k_prep_ga/gb/mt) through
-// cp.async.bulk into shared-memory rings; everything between the roles is mbarrier-synchronised, double-buffered.
+// cp.async.bulk into shared-memory rings; everything between the roles is mbarrier-synchronised.  Roles A and B wait
+// ONCE per hand-off: the barrier they wait on anyway also collects the tensor core's "your output buffer is free"
+// commit (see the barrier set-up) -- the critical warp's run time is the sum of its blocking round trips, not of its
+// instructions (profiles/r2_ablations_k_fused_mma.txt).
 // Layout, descriptor encodings, exactness and the accumulator's rounding (truncation) were measured first with
 // tools/umma_probe.cu on the B200 (profiles/r2_umma_probe.txt).
 #include "mma_dev.cuh"
