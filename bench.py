@@ -463,7 +463,7 @@ def main():
 
     e2e = None
     if mode == "dp":
-        e2e = e2e_batch(pairs, p, channels, w, h, size_d, max(4, min(args.steps, 12)))
+        e2e = e2e_batch(pairs, p, channels, w, h, size_d, max(4, min(args.steps, 32)))
 
     # ------------------------------------------------------------------------------------------------ extra legs
     def rgb_leg():
@@ -493,7 +493,7 @@ def main():
                              "traffic": tr.get("dram_bytes_per_launch") if tr else None, "traffic_src": tr.get("src") if tr else None,
                              "ncu": {k: tr.get(k) for k in ("l1tex_data_pipe_pct", "issue_active_pct", "fma_pipe_pct", "alu_pipe_pct",
                                                             "kernel_ms_under_ncu")} if tr else None},
-                "e2e": e2e_batch(cpairs, p_rgb, 3, w, h, size_d, 6), "clocks": clk,
+                "e2e": e2e_batch(cpairs, p_rgb, 3, w, h, size_d, max(4, min(args.steps, 12))), "clocks": clk,
                 "note": "colour guided filter of SURVEY A.8 on 3-channel synthetic pairs: BASELINE configs[2] as specified; not in the "
                         "reference (parity against the oracle's RGB port at full size: tests/test_rgb_guide.py)"}
 

@@ -16,8 +16,11 @@
 //   role A (5 warps)   lattice cost P (packed half, 2 disparities per instruction) for 160 cost columns x 4 d x 4 rows; the
 //                      exact fp16 pieces P, (C&15) P, (C&240) P for C = R, G, B; what enters MMA 1 is piece(y) - piece(y-19)
 //   MMA 1 (tensor)     dH = Band x dPiece: pass 1 = (lo_r, lo_g, lo_b, P), pass 2 = (hi_r, hi_g, hi_b, 0) accumulated onto it
-//   role B (8 warps)   S += dH (2-D box sums, exact integers); cov, a = M cov (3x3, symmetric, from the preparation), b;
-//                      their vertical 19-row sums (ring in Tensor Memory); fp16 hi + lo
+//   role B (4 warps)   S += dH (2-D box sums, exact integers); cov, a = M cov (3x3, symmetric, from the preparation), b;
+//                      their vertical 19-row sums (ring in Tensor Memory, re-summed every 64 rows); fp16 hi + lo.  One thread
+//                      per a/b lane and ONE barrier wait per hand-off: d1_full collects MMA 1's commit, MMA 2's commit of the
+//                      previous iteration ("your half of B2 is free") and the bulk copy of the half's statistics rows
+//                      (8 warps of 2 disparities with three waits: 6.55 ms; this: 6.14 ms, bit-identical but for the re-sum)
 //   MMA 2 (tensor)     H = Band x hi - Band x (hi - value)
 //   role C (4 warps)   q = (H_ar (R-128) + H_ag (G-128) + H_ab (B-128) + H_b') / area, tournament over the 4 disparities with
 //                      `best >= q`, read-modify-write of the chunk's (best,label) plane (prefetched by the TMA producer)
@@ -32,7 +35,7 @@ constexpr int HR = 2;            // rows per hand-off
 constexpr int NH = MR / HR;
 constexpr int R_NWA = 5;         // role-A warps: one thread per cost column
 #ifndef RGBM_BSPLIT
-#define RGBM_BSPLIT 2            // role B: 2 = two threads per a/b lane (2 disparities each), 1 = one thread (4 disparities)
+#define RGBM_BSPLIT 1            // role B: 1 = one thread per a/b lane (4 disparities), 2 = two threads (2 disparities each)
 #endif
 constexpr int NWB = 4 * RGBM_BSPLIT, NWC = 4;
 constexpr int BD = R_ND / RGBM_BSPLIT;   // disparities per role-B thread
@@ -55,7 +58,17 @@ constexpr int R_NB = RGBM_NB;          // role B's operand ring (statistics rows
 #endif
 constexpr int R_PF = RGBM_PF;    // L2 prefetch distance of the operand rows, in half-steps
 constexpr int R_NGC = 2;         // role C's ring (colours of the output rows, previous (best,label))
-constexpr int R_RESUM = 8;
+#ifndef RGBM_RESUM
+#define RGBM_RESUM 16
+#endif
+#ifndef RGBM_MERGE_BAR
+#define RGBM_MERGE_BAR 1         // 1 = role B waits once per half: d1_full collects MMA 1's commit and MMA 2's of the previous iteration
+#endif
+#ifndef RGBM_S_MERGE
+#define RGBM_S_MERGE 1           // 1 = the statistics rows' bulk copy completes on d1_full as well (slot == half): role B has ONE wait per half
+#endif
+constexpr int R_RESUM = RGBM_RESUM;
+static_assert(!RGBM_S_MERGE || (RGBM_MERGE_BAR && RGBM_NB == 2), "S_MERGE needs the merged d1_full barrier and one statistics slot per half");
 constexpr float I_CENTER = 128.0f;
 static_assert((4 * RAD) % MR == 0, "MR must divide the warm-up length");
 
@@ -172,13 +185,15 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
         for (int i = 0; i < NH; i++) {
             mbar_init(bar(&sm.b1_full[i]), R_NWA);
             mbar_init(bar(&sm.b1_empty[i]), 1);
-            mbar_init(bar(&sm.d1_full[i]), 1);
+            mbar_init(bar(&sm.d1_full[i]), 1 + RGBM_MERGE_BAR + RGBM_S_MERGE);
             mbar_init(bar(&sm.d1_empty[i]), NWB);
             mbar_init(bar(&sm.b2_full[i]), NWB);
             mbar_init(bar(&sm.b2_empty[i]), 1);
             mbar_init(bar(&sm.d2_full[i]), 1);
             mbar_init(bar(&sm.d2_empty[i]), NWC);
         }
+        if (RGBM_MERGE_BAR)  // phase 0 has no previous MMA 2
+            for (int i = 0; i < NH; i++) mbar_arrive(bar(&sm.d1_full[i]));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x >= 64 && threadIdx.x < 64 + 2 * (WIN + 1)) {
@@ -267,7 +282,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                     int slots[2];
                     // the statistics of the half's rows: into registers, and the slot goes back to the producer
                     const int hs = NH * K + half, ks = hs % R_NB;
-                    TL_WAIT(0, mbar_wait(mb_sf + 8 * ks, (unsigned)(hs / R_NB) & 1u));
+                    if (RGBM_S_MERGE) { TL_WAIT(1, mbar_wait(mb_d1f + 8 * half, (unsigned)K & 1u)); }
+                    else TL_WAIT(0, mbar_wait(mb_sf + 8 * ks, (unsigned)(hs / R_NB) & 1u));
                     uint4 st1[HR], st2[HR];
                     uint32_t st3[HR];
 #pragma unroll
@@ -277,7 +293,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                         st2[j] = lds128(sa + GB_S2);
                         st3[j] = lds32(sa + GB_S3 - (uint32_t)l * 12);  // the third plane is 4 B per lane
                     }
-                    TL_WAIT(1, mbar_wait(mb_d1f + 8 * half, (unsigned)K & 1u));
+                    if (!RGBM_S_MERGE) TL_WAIT(1, mbar_wait(mb_d1f + 8 * half, (unsigned)K & 1u));
                     tm_fence_after();
 #pragma unroll
                     for (int j = 0; j < 2; j++) {
@@ -346,7 +362,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                                 }
                             }
                         }
-                        if (j == 0 && K >= 1) TL_WAIT(2, mbar_wait(mb_b2e + 8 * half, (unsigned)(K - 1) & 1u));
+                        if (!RGBM_MERGE_BAR && j == 0 && K >= 1) TL_WAIT(2, mbar_wait(mb_b2e + 8 * half, (unsigned)(K - 1) & 1u));
                         // fp16 hi + lo of the vertical sums: hi - value = -(lo part); MMA 2 takes the lo pass with B negated.
                         // A B2 group (8 columns of D2) = (a_r, a_g, a_b, b') of one disparity pair.
 #pragma unroll
@@ -632,7 +648,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
 #pragma unroll
                     for (int j = 0; j < M_K2 / 16; j++) umma_ts(td, ta + 8 * j, dlo2 + (uint64_t)(j * 16), IDN, 1);
                     umma_commit(mb_d2f + 8 * half);
-                    umma_commit(mb_b2e + 8 * half);
+                    umma_commit((RGBM_MERGE_BAR ? bar(&sm.d1_full[0]) : mb_b2e) + 8 * half);
                 }
                 __syncwarp();
             }
@@ -712,8 +728,9 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                 if (sb < R_NB || mbar_test(s_e + 8 * slot, (unsigned)(sb / R_NB - 1) & 1u)) {
                     if (elect_one()) {
                         const long long row = row0 - RAD + (long long)hb * HR;
-                        mbar_expect_tx(s_f + 8 * slot, B_SLOT);
-                        bulk_g2s(b_s + slot * B_SLOT, GBp + row * GB_ROW, B_SLOT, s_f + 8 * slot);
+                        const uint32_t sbar = RGBM_S_MERGE ? bar(&sm.d1_full[0]) + 8 * slot : s_f + 8 * slot;
+                        mbar_expect_tx(sbar, B_SLOT);
+                        bulk_g2s(b_s + slot * B_SLOT, GBp + row * GB_ROW, B_SLOT, sbar);
                         if (R_PF > 0 && sb + R_PF < SA) pf_b(hb + R_PF);
                     }
                     __syncwarp();
