@@ -165,8 +165,8 @@ typedef struct sb200_outputs {
     uint8_t* mean_left;    /* mean1 main.cu:133 : (uchar)min((int)mean_I,255) debug image        */
     uint8_t* mean_right;   /* mean2 main.cu:134 */
     float* subpixel_left;  /* NOT in the reference: disp_left refined by sb200_subpixel_refine_dev's parabola,
-                              pixels the L/R check marked keep their filled label.  Gray guide, tensor-core kernel;
-                              the call keeps the left view's filtered volume in the arena (size_d*w*h floats). */
+                              pixels the L/R check marked keep their filled label.  Tensor-core fused kernels (either
+                              guide); the call keeps the left view's filtered volume in the arena (size_d*w*h floats). */
 } sb200_outputs;
 
 /* Row-strip geometry for multi-GPU sharding: the images passed in are rows

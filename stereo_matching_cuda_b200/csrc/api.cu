@@ -397,8 +397,10 @@ int pipeline_core(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, 
         return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "mean_left/mean_right are gray-guide outputs");
     // sub-pixel refinement keeps the left view's filtered volume: only the tensor-core gray kernel stores it
     const bool subpix = o->subpixel_left != nullptr;
-    if (subpix && (rgb_guide || gray_staged || ctx->gray_kernel != 1 || !sbf_mma_supported(p)))
-        return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "subpixel_left: gray guide on the tensor-core fused kernel only");
+    if (subpix && (rgb_guide ? (rgb_staged || !rgb_uses_mma(ctx, p)) : (gray_staged || ctx->gray_kernel != 1 || !sbf_mma_supported(p))))
+        return sb_fail(ctx, SB200_ERR_UNSUPPORTED, "subpixel_left: the tensor-core fused kernels only (they keep the filtered volume)");
+    float* vol = nullptr;
+    if (subpix) SB_TRY(ws_get(ctx, &vol, (size_t)size_d * n_out));
     const uint8_t* gl = d_left;
     const uint8_t* gr = d_right;
     if (channels != 1) {
@@ -427,9 +429,12 @@ int pipeline_core(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, 
         if (mR) SB_TRY(ws_get(ctx, &mRh, n_held));
     }
     if (rgb_guide && !rgb_staged) {
-        if (rgb_uses_mma(ctx, p))
-            SB_TRY(sbf_pair_disparity_rgb_mma(ctx, p, d_left, d_right, channels, gl, gr, g, o->best_left, dL, o->best_right, dR));
-        else if (ctx->rgb_kernel != 2)
+        if (rgb_uses_mma(ctx, p)) {
+            ctx->qvol[0] = vol;  // for this launch only
+            const int rc = sbf_pair_disparity_rgb_mma(ctx, p, d_left, d_right, channels, gl, gr, g, o->best_left, dL, o->best_right, dR);
+            ctx->qvol[0] = nullptr;
+            SB_TRY(rc);
+        } else if (ctx->rgb_kernel != 2)
             SB_TRY(sbf_pair_disparity_rgb3(ctx, p, d_left, d_right, channels, gl, gr, g, o->best_left, dL, o->best_right, dR));
         else
             SB_TRY(sbf_pair_disparity_rgb(ctx, p, d_left, d_right, channels, gl, gr, g, o->best_left, dL, o->best_right, dR));
@@ -456,25 +461,22 @@ int pipeline_core(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, 
         ctx->ws_off = mark;
         SB_TRY(guided_filter_staged(ctx, &ps, gr, nullptr, bR, dR, mR, w, g.h, size_d, -p->dmax, gl));
     } else {
-        float* vol = nullptr;
-        if (subpix) SB_TRY(ws_get(ctx, &vol, (size_t)size_d * n_out));
         ctx->qvol[0] = vol;  // for this launch only
         const int rc = sbf_pair_disparity(ctx, p, gl, gr, g, o->best_left, dL, o->best_right, dR, full ? mL : mLh, full ? mR : mRh);
         ctx->qvol[0] = nullptr;
         SB_TRY(rc);
-        if (subpix) {
-            float *occ = o->occlusion, *fil = o->filled;
-            if (!occ) SB_TRY(ws_get(ctx, &occ, n_out));
-            if (!fil) SB_TRY(ws_get(ctx, &fil, n_out));
-            SB_TRY(sbk_lr_check_fill(ctx, dL, dR, w, g.rows_out, p->dmin - 100, p->d_lr, (float)p->dmin, occ, fil));
-            SB_TRY(sbk_subpixel(ctx, vol, dL, occ, fil, o->subpixel_left, n_out, p->dmin, size_d));
-        }
     }
     if (!full) {
         if (mL) SB_CUDA(ctx, cudaMemcpyAsync(mL, mLh + out_off, n_out, cudaMemcpyDeviceToDevice, ctx->stream));
         if (mR) SB_CUDA(ctx, cudaMemcpyAsync(mR, mRh + out_off, n_out, cudaMemcpyDeviceToDevice, ctx->stream));
     }
-    if ((o->occlusion || o->filled) && !subpix)
+    if (subpix) {
+        float *occ = o->occlusion, *fil = o->filled;
+        if (!occ) SB_TRY(ws_get(ctx, &occ, n_out));
+        if (!fil) SB_TRY(ws_get(ctx, &fil, n_out));
+        SB_TRY(sbk_lr_check_fill(ctx, dL, dR, w, g.rows_out, p->dmin - 100, p->d_lr, (float)p->dmin, occ, fil));
+        SB_TRY(sbk_subpixel(ctx, vol, dL, occ, fil, o->subpixel_left, n_out, p->dmin, size_d));
+    } else if (o->occlusion || o->filled)
         SB_TRY(sbk_lr_check_fill(ctx, dL, dR, w, g.rows_out, p->dmin - 100, p->d_lr, (float)p->dmin, o->occlusion,
                                  o->filled));
     if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev[4], ctx->stream));

@@ -122,6 +122,7 @@ struct RgbMmaArgs {
     int dmin[2], size_d;
     int n_strips, n_bands, band_rows, n_chunks, chunk_d, n_views;
     float2* BL;
+    float* QV[2];          // optional, per VIEW: filtered cost volume q, [size_d][rows_out][w]; NULL = not stored
     int pitchS;
     float S, scale, inv_scale;
     unsigned wI2, wG2, tc2, tg2;
@@ -140,6 +141,8 @@ __device__ __forceinline__ void reg_set() {
     else if (N > R_REGS_LAUNCH) reg_inc<N>();
 }
 
+// QVOL: role C also stores q (the filtered cost volume; see k_fused_mma in fused_mma.cu) -- its own instantiation
+template <bool QVOL>
 __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs A) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     RSmem& sm = *reinterpret_cast<RSmem*>(smem_raw);
@@ -404,6 +407,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
         const uint32_t td2 = tl + TC_D2;
         const uint32_t gcs = smem_addr(&sm.gc[0][0]) + (uint32_t)l * 2;
         const uint32_t pbs = smem_addr(&sm.gc[0][0]) + GC_PB + (uint32_t)l * 8;
+        const size_t qplane = (size_t)A.rows_out * A.w;
+        float* const qv0 = (QVOL && A.QV[view]) ? A.QV[view] + (size_t)(chunk * A.chunk_d) * qplane + (size_t)(yb0 - A.y_out0) * A.w + x : nullptr;
         const uint32_t mb_d2f = bar(&sm.d2_full[0]), mb_d2e = bar(&sm.d2_empty[0]), mb_gcf = bar(&sm.gc_full[0]), mb_gce = bar(&sm.gc_empty[0]);
         int K = 0;
         TL_DECL
@@ -413,6 +418,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
             const bool ld_ok = g > 0;
             const float2 binit = make_float2(BEST_INIT_BITS_F, 0.0f);
             float2* blp = bl0;
+            float* qvp = (QVOL && qv0) ? qv0 + (size_t)(g * R_ND) * qplane : nullptr;
 #pragma unroll 1
             for (int it = 0; it < niter; it++, K++) {
                 const int e = it - WARM_IT;
@@ -478,6 +484,14 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                             for (int d = 0; d < R_ND; d++)
                                 if (d >= dact) q[d] = __int_as_float(0x7f800000);
                         }
+                        if (QVOL && qvp && st_ok[j]) {
+                            float* qd = qvp + (size_t)j * A.w;
+#pragma unroll
+                            for (int d = 0; d < R_ND; d++) {
+                                if (d < dact) *qd = q[d];
+                                qd += qplane;
+                            }
+                        }
                         // ascending d, `best >= q`: minimum, the later index on a tie (guidedFilter.cu:406), as a tournament
                         const bool t01 = q[0] >= q[1], t23 = q[2] >= q[3];
                         const float m01 = t01 ? q[1] : q[0], a01 = t01 ? 1.0f : 0.0f;
@@ -493,6 +507,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                     }
                 }
                 blp += (size_t)MR * pitchS;
+                if (QVOL && qvp) qvp += (size_t)MR * A.w;
                 asm volatile("fence.proxy.async.global;" ::: "memory");  // the TMA producer reads these rows one group later
                 __syncwarp();
                 mbar_arrive_lane0(mb_gce + 8 * kc, lane);
@@ -1034,6 +1049,8 @@ int sbf_pair_disparity_rgb_mma(sb200_ctx* ctx, const sb200_params* p, const uint
     A.chunk_d = plan.chunk_d;
     A.n_views = 2;
     A.BL = BL;
+    A.QV[0] = ctx->qvol[0];
+    A.QV[1] = ctx->qvol[1];
     A.pitchS = pitchS;
     A.S = (float)S;
     A.scale = scale;
@@ -1049,11 +1066,13 @@ int sbf_pair_disparity_rgb_mma(sb200_ctx* ctx, const sb200_params* p, const uint
 
     const size_t smem = sizeof(RSmem);
     if (!ctx->rgb_mma_attr_set) {
-        SB_CUDA(ctx, cudaFuncSetAttribute(k_fused_mma_rgb, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_CUDA(ctx, cudaFuncSetAttribute(k_fused_mma_rgb<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SB_CUDA(ctx, cudaFuncSetAttribute(k_fused_mma_rgb<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->rgb_mma_attr_set = true;
     }
     const int nblocks = plan.n_strips * plan.n_bands * plan.n_chunks * 2;
-    SB_LAUNCH(ctx, k_fused_mma_rgb, nblocks, R_THREADS, smem, A);
+    if (A.QV[0] || A.QV[1]) SB_LAUNCH(ctx, k_fused_mma_rgb<true>, nblocks, R_THREADS, smem, A);
+    else SB_LAUNCH(ctx, k_fused_mma_rgb<false>, nblocks, R_THREADS, smem, A);
     if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     float* best[2] = {bestL, bestR};
     float* disp[2] = {dispL, dispR};
