@@ -298,7 +298,9 @@ int sbk_detect_occlusion(sb200_ctx* ctx, float* dL, const float* dR, int dOcc, i
 //   3. the filled row leaves with coalesced 128-bit stores.
 // Six block barriers per row whatever its width (the previous version: three per 256-pixel tile and pass, 180 at 8K).
 //   do_check = 0: `dL` is taken as the already-checked map.  occ_out / filled_out may be NULL; dL may alias filled_out.
+#ifndef FILL_THREADS
 #define FILL_THREADS 256
+#endif
 __global__ void __launch_bounds__(FILL_THREADS)
 k_lr_check_fill(const float* dL, const float* __restrict__ dR, int w, int seg, int dOcc, int d_lr, float vMin,
                 float* occ_out, float* filled_out, int do_check) {
