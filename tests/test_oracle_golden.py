@@ -105,3 +105,35 @@ def test_oracle_weighted_median_properties(oracle):
     const = np.full((h, w), -3, np.float32)
     out2 = oracle.weighted_median(gray, occ, const, dmin, size_d)
     assert np.array_equal(out2, const)
+
+
+def test_oracle_subpixel_refine_against_numpy(oracle):
+    """so_subpixel_refine (beyond the reference; definition in stereo_b200.h) against an independent numpy
+    restatement in float32 with the same operation order, on a random volume: bit for bit; plus the closed form on an exact
+    parabola and the rules at the edges of the label range and on marked pixels"""
+    rng = np.random.default_rng(5)
+    size_d, h, w, dmin = 9, 13, 17, -8
+    vol = rng.random((size_d, h, w), dtype=np.float32)
+    k = vol.argmin(axis=0)
+    disp = (k + dmin).astype(np.float32)
+    got = oracle.subpixel_refine(vol, disp, dmin)
+    f = np.float32
+    qm = np.take_along_axis(vol, np.clip(k - 1, 0, size_d - 1)[None], 0)[0]
+    q0 = np.take_along_axis(vol, k[None], 0)[0]
+    qp = np.take_along_axis(vol, np.clip(k + 1, 0, size_d - 1)[None], 0)[0]
+    den = (qm - q0).astype(f) + (qp - q0).astype(f)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = np.clip(((f(0.5) * (qm - qp).astype(f)).astype(f) / den).astype(f), f(-0.5), f(0.5))
+    want = np.where((k > 0) & (k < size_d - 1) & (den > 0), (disp + t).astype(f), disp)
+    assert np.array_equal(got.view(np.uint32), want.astype(f).view(np.uint32))
+    # an exact parabola with its vertex at -3.25: q(d) = (d + 3.25)^2
+    d = np.arange(dmin, dmin + size_d, dtype=np.float32)
+    par = np.broadcast_to(((d + 3.25) ** 2)[:, None, None], (size_d, 2, 3)).astype(np.float32).copy()
+    r = oracle.subpixel_refine(par, np.full((2, 3), -3.0, np.float32), dmin)
+    assert np.allclose(r, -3.25, atol=1e-6)
+    # edge labels stay; marked pixels take the filled label
+    edge = oracle.subpixel_refine(par, np.full((2, 3), float(dmin), np.float32), dmin)
+    assert np.array_equal(edge, np.full((2, 3), float(dmin), np.float32))
+    occ = np.full((2, 3), float(dmin - 100), np.float32)
+    fil = np.full((2, 3), -5.0, np.float32)
+    assert np.array_equal(oracle.subpixel_refine(par, np.full((2, 3), -3.0, np.float32), dmin, occ, fil), fil)
