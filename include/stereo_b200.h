@@ -197,6 +197,18 @@ int sb200_pipeline(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h_left,
  * Replaces the reference's per-stage cudaMemcpy round trips (guidedFilter.cu:39-56, costVolume.cu:23-53). */
 int sb200_pipeline_batch(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h_left, const uint8_t* h_right, int channels,
                          int w, int h, int n_pairs, const sb200_outputs* h_out);
+/* The same call with the four LABEL maps delivered as int16 (any pointer may be NULL): the reference keeps its labels in
+ * floats (guidedFilter.cu:409), but they are integers in [dmin-100, dmax], and halving the bytes of the device->host copy
+ * is what keeps an end-to-end batch at the device rate on a busy PCIe root.  h_other (may be NULL) carries any further
+ * outputs (best costs, gray/mean images); a map must not be requested in both forms. */
+typedef struct sb200_labels_i16 {
+    int16_t* disp_left;
+    int16_t* disp_right;
+    int16_t* occlusion;
+    int16_t* filled;
+} sb200_labels_i16;
+int sb200_pipeline_batch_i16(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h_left, const uint8_t* h_right, int channels,
+                             int w, int h, int n_pairs, const sb200_labels_i16* h_labels, const sb200_outputs* h_other);
 /* n_pairs pairs of identical shape, contiguous: left + i*w*h*channels, outputs + i*w*h */
 int sb200_pipeline_batch_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, const uint8_t* d_right,
                              int channels, int w, int h, int n_pairs, const sb200_outputs* d_out);

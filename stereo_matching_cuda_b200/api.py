@@ -57,6 +57,10 @@ class _Outputs(C.Structure):
                                           "gray_left", "gray_right", "mean_left", "mean_right", "subpixel_left")]
 
 
+class _LabelsI16(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("disp_left", "disp_right", "occlusion", "filled")]
+
+
 class _Strip(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("y0", "rows", "halo_top", "halo_bot", "frame_h")]
 
@@ -127,6 +131,7 @@ def load_library(path=None):
         "sb200_pipeline_strip_dev": (ip, [vp, PP, vp, vp, ip, ip, C.POINTER(_Strip), C.POINTER(_Outputs)]),
         "sb200_strip_halo_rows": (ip, [PP]),
         "sb200_view_disparity_dev": (ip, [vp, PP, vp, vp, ip, ip, ip, ip, vp, vp, vp]),
+        "sb200_pipeline_batch_i16": (ip, [vp, PP, vp, vp, ip, ip, ip, ip, vp, vp]),
         "sb200_view_volume_dev": (ip, [vp, PP, vp, vp, ip, ip, ip, ip, vp, vp, vp]),
         "sb200_subpixel_refine_dev": (ip, [vp, vp, vp, vp, vp, vp, ip, ip, ip, ip]),
         "sb200_lr_check_fill_dev": (ip, [vp, PP, vp, vp, ip, ip, ip, fp, vp, vp]),
@@ -406,19 +411,25 @@ class Context:
         self._ck(self.lib.sb200_pipeline(self.h, C.byref(p), _ptr(left), _ptr(right), ch, w, h, C.byref(o)))
         return res
 
-    def pipeline_batch(self, lefts, rights, params=None, want=("disp_left", "disp_right", "occlusion", "filled"), out=None):
+    _LABELS = ("disp_left", "disp_right", "occlusion", "filled")
+
+    def pipeline_batch(self, lefts, rights, params=None, want=("disp_left", "disp_right", "occlusion", "filled"), out=None,
+                       labels_i16=False):
         """n pairs on HOST arrays (n,h,w[,ch]) uint8 through sb200_pipeline_batch: uploads, kernels and downloads of
         consecutive pairs overlap (page-locked arrays, e.g. torch pin_memory().numpy(), are needed for the overlap).
-        `out`: optional dict of preallocated (n,h,w) arrays (float32 / uint8) to fill instead of fresh ones."""
+        `out`: optional dict of preallocated (n,h,w) arrays (float32 / uint8) to fill instead of fresh ones.
+        labels_i16: the four label maps come back as int16 (sb200_pipeline_batch_i16: half the device->host bytes)."""
         p = params or default_params()
         lefts, rights = _np(lefts, np.uint8), _np(rights, np.uint8)
         if lefts.shape != rights.shape or lefts.ndim not in (3, 4):
             raise StereoB200Error(f"lefts {lefts.shape} / rights {rights.shape}: expected two (n,h,w[,ch]) arrays of one shape")
         n, h, w = lefts.shape[:3]
         ch = 1 if lefts.ndim == 3 else lefts.shape[3]
-        res, o = {}, _Outputs()
+        res, o, li = {}, _Outputs(), _LabelsI16()
         for k in want:
             dt = np.float32 if k in self._F32 else np.uint8
+            if labels_i16 and k in self._LABELS:
+                dt = np.int16
             if out is not None and k in out:
                 a = out[k]
                 if a.shape != (n, h, w) or a.dtype != dt or not a.flags.c_contiguous:
@@ -426,8 +437,12 @@ class Context:
             else:
                 a = np.empty((n, h, w), dt)
             res[k] = a
-            setattr(o, k, a.ctypes.data)
-        self._ck(self.lib.sb200_pipeline_batch(self.h, C.byref(p), _ptr(lefts), _ptr(rights), ch, w, h, n, C.byref(o)))
+            setattr(li if dt == np.int16 else o, k, a.ctypes.data)
+        if labels_i16:
+            self._ck(self.lib.sb200_pipeline_batch_i16(self.h, C.byref(p), _ptr(lefts), _ptr(rights), ch, w, h, n, C.byref(li),
+                                                       C.byref(o)))
+        else:
+            self._ck(self.lib.sb200_pipeline_batch(self.h, C.byref(p), _ptr(lefts), _ptr(rights), ch, w, h, n, C.byref(o)))
         return res
 
     def _dev_check(self, t, name, numel, dtype_name):

@@ -846,13 +846,25 @@ int sb200_pipeline_strips_nccl(sb200_ctx* ctx, const sb200_params* p, void* nccl
 // reference's per-stage cudaMemcpy round trips (guidedFilter.cu:39-56, costVolume.cu:23-53) become on a bus that is
 // 100x slower than HBM.  Host buffers should be page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory): with
 // pageable memory the copies still work but the driver stages them and the overlap is lost.
-int sb200_pipeline_batch(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h_left, const uint8_t* h_right, int channels,
-                         int w, int h, int n_pairs, const sb200_outputs* h_out) {
+}  // extern "C"
+namespace {
+// h_i16 != NULL: the four label maps leave as int16 (h_out then only carries the non-label outputs, or is NULL)
+int batch_host(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h_left, const uint8_t* h_right, int channels, int w, int h,
+               int n_pairs, const sb200_outputs* h_out_in, const sb200_labels_i16* h_i16) {
     DevGuard dev_guard__(ctx);
     SB_TRY(check_params(ctx, p));
-    REQUIRE(ctx, h_left && h_right && h_out && w > 1 && h > 0 && n_pairs > 0, "null pointer or empty batch");
+    static const sb200_outputs no_outputs{};
+    const sb200_outputs* h_out = h_out_in ? h_out_in : &no_outputs;
+    REQUIRE(ctx, h_left && h_right && (h_out_in || h_i16) && w > 1 && h > 0 && n_pairs > 0, "null pointer or empty batch");
     REQUIRE(ctx, channels == 1 || channels >= 3, "channels must be 1 (gray) or >= 3");
     REQUIRE(ctx, !h_out->subpixel_left, "subpixel_left: not in the overlapped batch entry (use sb200_pipeline / sb200_pipeline_batch_dev)");
+    int16_t* const hi[4] = {h_i16 ? h_i16->disp_left : nullptr, h_i16 ? h_i16->disp_right : nullptr,
+                            h_i16 ? h_i16->occlusion : nullptr, h_i16 ? h_i16->filled : nullptr};
+    if (h_i16) {
+        REQUIRE(ctx, p->dmin - 100 >= -32768 && p->dmax <= 32767 && -p->dmax >= -32768 && -p->dmin <= 32767, "labels do not fit int16");
+        REQUIRE(ctx, !(hi[0] && h_out->disp_left) && !(hi[1] && h_out->disp_right) && !(hi[2] && h_out->occlusion) && !(hi[3] && h_out->filled),
+                "a label map is requested both as float and as int16");
+    }
     const size_t n = (size_t)w * h;
     if (!ctx->batch_ready) {
         SB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
@@ -868,7 +880,9 @@ int sb200_pipeline_batch(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h
     uint8_t* const hu[] = {h_out->gray_left, h_out->gray_right, h_out->mean_left, h_out->mean_right};
     size_t slot_bytes = 2 * sb_align(n * channels);
     for (int i = 0; i < 6; i++)
-        if (hf[i]) slot_bytes += sb_align(n * 4);
+        if (hf[i] || (i < 4 && hi[i])) slot_bytes += sb_align(n * 4);
+    for (int i = 0; i < 4; i++)
+        if (hi[i]) slot_bytes += sb_align(n * 2);
     for (int i = 0; i < 4; i++)
         if (hu[i]) slot_bytes += sb_align(n);
     if (2 * slot_bytes > ctx->stage_cap) {
@@ -899,7 +913,7 @@ int sb200_pipeline_batch(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h
         float** const df[] = {&d.disp_left, &d.disp_right, &d.occlusion, &d.filled, &d.best_left, &d.best_right};
         uint8_t** const du[] = {&d.gray_left, &d.gray_right, &d.mean_left, &d.mean_right};
         for (int k = 0; k < 6; k++)
-            if (hf[k]) {
+            if (hf[k] || (k < 4 && hi[k])) {
                 *df[k] = reinterpret_cast<float*>(o);
                 o += sb_align(n * 4);
             }
@@ -907,6 +921,14 @@ int sb200_pipeline_batch(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h
             if (hu[k]) {
                 *du[k] = reinterpret_cast<uint8_t*>(o);
                 o += sb_align(n);
+            }
+        int16_t* di[4] = {nullptr, nullptr, nullptr, nullptr};
+        const float* fsrc[4] = {nullptr, nullptr, nullptr, nullptr};
+        for (int k = 0; k < 4; k++)
+            if (hi[k]) {
+                di[k] = reinterpret_cast<int16_t*>(o);
+                fsrc[k] = *df[k];
+                o += sb_align(n * 2);
             }
         // upload pair i once the kernels of pair i-2 are done with this slot's inputs
         if (i >= 2) SB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_in, ctx->ev_comp[slot], 0));
@@ -917,9 +939,12 @@ int sb200_pipeline_batch(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h
         SB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_in[slot], 0));
         if (i >= 2) SB_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_out[slot], 0));
         SB_TRY(pipeline_core(ctx, p, dl, dr, channels, w, g, &d, true));
+        if (h_i16) SB_TRY(sbk_labels_i16(ctx, fsrc, di, n));
         SB_CUDA(ctx, cudaEventRecord(ctx->ev_comp[slot], ctx->stream));
         // download the results of pair i
         SB_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp[slot], 0));
+        for (int k = 0; k < 4; k++)
+            if (hi[k]) SB_CUDA(ctx, cudaMemcpyAsync(hi[k] + (size_t)i * n, di[k], n * 2, cudaMemcpyDeviceToHost, ctx->s_out));
         for (int k = 0; k < 6; k++)
             if (hf[k]) SB_CUDA(ctx, cudaMemcpyAsync(hf[k] + (size_t)i * n, *df[k], n * 4, cudaMemcpyDeviceToHost, ctx->s_out));
         for (int k = 0; k < 4; k++)
@@ -929,6 +954,18 @@ int sb200_pipeline_batch(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
     SB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SB200_OK;
+}
+}  // namespace
+extern "C" {
+int sb200_pipeline_batch(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h_left, const uint8_t* h_right, int channels,
+                         int w, int h, int n_pairs, const sb200_outputs* h_out) {
+    if (ctx && !h_out) return sb_fail(ctx, SB200_ERR_INVALID, "outputs is NULL");
+    return batch_host(ctx, p, h_left, h_right, channels, w, h, n_pairs, h_out, nullptr);
+}
+int sb200_pipeline_batch_i16(sb200_ctx* ctx, const sb200_params* p, const uint8_t* h_left, const uint8_t* h_right, int channels,
+                             int w, int h, int n_pairs, const sb200_labels_i16* h_labels, const sb200_outputs* h_other) {
+    if (ctx && !h_labels) return sb_fail(ctx, SB200_ERR_INVALID, "labels is NULL");
+    return batch_host(ctx, p, h_left, h_right, channels, w, h, n_pairs, h_other, h_labels);
 }
 
 // ---- host-pointer stage entry points (blocking, reference calling convention) -------------

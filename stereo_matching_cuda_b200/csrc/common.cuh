@@ -144,6 +144,7 @@ int sbk_weighted_median(sb200_ctx* ctx, const uint8_t* gray, const float* occ, c
 int sbk_lr_check_fill(sb200_ctx* ctx, const float* dL, const float* dR, int w, int h, int dOcc, int d_lr, float vMin,
                       float* occ, float* filled);
 int sbk_fill_f32(sb200_ctx* ctx, float* dst, float v, size_t n);
+int sbk_labels_i16(sb200_ctx* ctx, const float* const src[4], int16_t* const dst[4], size_t n);  // NULL entries are skipped
 int sbk_subpixel(sb200_ctx* ctx, const float* vol, const float* disp, const float* occ, const float* filled, float* out,
                  size_t n, int dmin, int size_d);
 int sbk_write_mat(sb200_ctx* ctx, const float* mat, uint8_t* out, size_t n, float* scratch);  // scratch: 2*ceil(n/1024)+2 words

@@ -702,7 +702,8 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
 // compute_guided_filter, guidedFilter.cu:58-123, like k_prep of fused_cvf.cu).
 
 // GA: thread per (strip, padded row, cost column)
-__global__ void __launch_bounds__(160) k_prep_ga(const PrepM P) {
+__global__ void __launch_bounds__(160) k_prep_ga(const PrepM P0, const PrepM P1) {
+    const PrepM& P = blockIdx.z ? P1 : P0;
     const int k = threadIdx.x, yrow = blockIdx.x, strip = blockIdx.y;
     const int x = strip * M_VW - 2 * RAD + k, y = yrow - PADY;
     float I, G;
@@ -721,7 +722,8 @@ __global__ void __launch_bounds__(160) k_prep_ga(const PrepM P) {
 
 // GB: block = (strip, 32 padded rows), thread per a/b lane; exact integer window sums of I and I^2
 constexpr int GB_TR = 16;
-__global__ void __launch_bounds__(M_TW) k_prep_gb(const PrepM P) {
+__global__ void __launch_bounds__(M_TW) k_prep_gb(const PrepM P0, const PrepM P1) {
+    const PrepM& P = blockIdx.z ? P1 : P0;
     __shared__ unsigned short sI[GB_TR + 2 * RAD][M_TW + 2 * RAD + 2];
     __shared__ int h1[GB_TR + 2 * RAD][M_TW], h2[GB_TR + 2 * RAD][M_TW];
     const int l = threadIdx.x, strip = blockIdx.y;
@@ -844,8 +846,9 @@ int sbf_run_fused_mma(sb200_ctx* ctx, const sb200_params* p, const uint8_t* cons
         return sb_fail(ctx, SB200_ERR_NOMEM, "fused (mma): workspace arena too small (internal)");
 
     if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    PrepM PP[2];
     for (int i = 0; i < 2; i++) {
-        PrepM P;
+        PrepM& P = PP[i];
         P.gray = gray[i];
         P.w = g.w;
         P.h_held = g.h;
@@ -863,10 +866,10 @@ int sbf_run_fused_mma(sb200_ctx* ctx, const sb200_params* p, const uint8_t* cons
         P.eps = p->eps;
         P.S = (float)S;
         P.scale = scale;
-        SB_LAUNCH(ctx, k_prep_ga, dim3(rows_pad, plan.n_strips), M_KB, 0, P);
-        SB_LAUNCH(ctx, k_prep_gb, dim3(sb_div_up(rows_pad, GB_TR), plan.n_strips), M_TW, 0, P);
-        SB_LAUNCH(ctx, k_prep_mt, dim3(sb_div_up(mg.n_chunk * 4, 256), rows_pad), 256, 0, P);
     }
+    SB_LAUNCH(ctx, k_prep_ga, dim3(rows_pad, plan.n_strips, 2), M_KB, 0, PP[0], PP[1]);
+    SB_LAUNCH(ctx, k_prep_gb, dim3(sb_div_up(rows_pad, GB_TR), plan.n_strips, 2), M_TW, 0, PP[0], PP[1]);
+    SB_LAUNCH(ctx, k_prep_mt, dim3(sb_div_up(mg.n_chunk * 4, 256), rows_pad, 2), 256, 0, PP[0], PP[1]);
     if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
 
     MmaArgs A;

@@ -810,7 +810,8 @@ __device__ __forceinline__ bool in_frame_r(const PrepR& P, int x, int y) {
 }
 
 // GA, GC: thread per (strip, padded row, cost column)
-__global__ void __launch_bounds__(160) k_prep_ga3(const PrepR P) {
+__global__ void __launch_bounds__(160) k_prep_ga3(const PrepR P0, const PrepR P1) {
+    const PrepR& P = blockIdx.z ? P1 : P0;
     const int k = threadIdx.x, yrow = blockIdx.x, strip = blockIdx.y;
     const int x = strip * M_VW - 2 * RAD + k, y = yrow - PADY;
     const bool in = in_frame_r(P, x, y);
@@ -846,7 +847,8 @@ __global__ void __launch_bounds__(160) k_prep_ga3(const PrepR P) {
 // is loaded once; a thread then walks down its column: the window sums are vertical running sums of the rows' horizontal
 // 19-tap sums of the nine quantities (the row that enters adds, the row that leaves is recomputed and subtracted).
 constexpr int GB3_TR = 32;
-__global__ void __launch_bounds__(M_TW) k_prep_gb3(const PrepR P) {
+__global__ void __launch_bounds__(M_TW) k_prep_gb3(const PrepR P0, const PrepR P1) {
+    const PrepR& P = blockIdx.z ? P1 : P0;
     __shared__ uchar4 sC[GB3_TR + 2 * RAD][M_TW + 2 * RAD];
     const int l = threadIdx.x, strip = blockIdx.y;
     const int yrow0 = blockIdx.x * GB3_TR;
@@ -984,8 +986,10 @@ int sbf_pair_disparity_rgb_mma(sb200_ctx* ctx, const sb200_params* p, const uint
         return sb_fail(ctx, SB200_ERR_NOMEM, "fused RGB (mma): workspace arena too small (internal)");
 
     if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    PrepR PR[2];
+    PrepM QM[2];
     for (int i = 0; i < 2; i++) {
-        PrepR P;
+        PrepR& P = PR[i];
         P.gray = gray[i];
         P.rgb = rgb[i];
         P.ch = channels;
@@ -1001,9 +1005,7 @@ int sbf_pair_disparity_rgb_mma(sb200_ctx* ctx, const sb200_params* p, const uint
         P.eps = p->eps;
         P.S = (float)S;
         P.scale = scale;
-        SB_LAUNCH(ctx, k_prep_ga3, dim3(rows_pad, plan.n_strips), M_KB, 0, P);
-        SB_LAUNCH(ctx, k_prep_gb3, dim3(sb_div_up(rows_pad, GB3_TR), plan.n_strips), M_TW, 0, P);
-        PrepM Q;
+        PrepM& Q = QM[i];
         Q.gray = gray[i];
         Q.w = g.w;
         Q.h_held = g.h;
@@ -1021,8 +1023,10 @@ int sbf_pair_disparity_rgb_mma(sb200_ctx* ctx, const sb200_params* p, const uint
         Q.eps = p->eps;
         Q.S = (float)S;
         Q.scale = scale;
-        SB_LAUNCH(ctx, k_prep_mt, dim3(sb_div_up(mg.n_chunk * 4, 256), rows_pad), 256, 0, Q);
     }
+    SB_LAUNCH(ctx, k_prep_ga3, dim3(rows_pad, plan.n_strips, 2), M_KB, 0, PR[0], PR[1]);
+    SB_LAUNCH(ctx, k_prep_gb3, dim3(sb_div_up(rows_pad, GB3_TR), plan.n_strips, 2), M_TW, 0, PR[0], PR[1]);
+    SB_LAUNCH(ctx, k_prep_mt, dim3(sb_div_up(mg.n_chunk * 4, 256), rows_pad, 2), 256, 0, QM[0], QM[1]);
     if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
 
     RgbMmaArgs A;

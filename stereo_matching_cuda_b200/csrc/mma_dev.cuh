@@ -169,7 +169,9 @@ __device__ __forceinline__ void pix_ig(const PrepM& P, int x, int y, float& I, f
 }
 
 // MT: thread per (padded row, chunk, copy)
-__global__ void __launch_bounds__(256) k_prep_mt(const PrepM P) {
+// (the preparation kernels take both images of a pair in one launch: blockIdx.z selects the image)
+__global__ void __launch_bounds__(256) k_prep_mt(const PrepM P0, const PrepM P1) {
+    const PrepM& P = blockIdx.z ? P1 : P0;
     const int idx = blockIdx.x * 256 + threadIdx.x;
     const int yrow = blockIdx.y;
     if (idx >= P.n_chunk * 4) return;

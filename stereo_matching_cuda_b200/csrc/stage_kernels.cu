@@ -505,6 +505,41 @@ int sbk_weighted_median(sb200_ctx* ctx, const uint8_t* gray, const float* occ, c
 }
 
 // ---------------------------------------------------------------------------------------
+// Label maps as int16 for the host-pointer batch entry: the reference keeps its labels in floats
+// (guidedFilter.cu:409 `dmap[i] = (float)label`), but they are integers of a few hundred at most, and the device->host copy
+// of four float maps is what an end-to-end batch spends its PCIe time on.  (short)float is exact for them.
+struct LabelMaps {
+    const float* src[4];
+    int16_t* dst[4];
+};
+__global__ void k_labels_i16(const LabelMaps M, size_t n) {
+    const float* __restrict__ s = M.src[blockIdx.y];
+    int16_t* __restrict__ d = M.dst[blockIdx.y];
+    if (!s || !d) return;
+    const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 + 3 < n) {
+        const float4 v = *reinterpret_cast<const float4*>(s + i4);
+        short4 o;
+        o.x = (short)v.x;
+        o.y = (short)v.y;
+        o.z = (short)v.z;
+        o.w = (short)v.w;
+        *reinterpret_cast<short4*>(d + i4) = o;
+    } else {
+        for (size_t i = i4; i < n; i++) d[i] = (int16_t)s[i];
+    }
+}
+int sbk_labels_i16(sb200_ctx* ctx, const float* const src[4], int16_t* const dst[4], size_t n) {
+    LabelMaps M;
+    for (int k = 0; k < 4; k++) {
+        M.src[k] = src[k];
+        M.dst[k] = dst[k];
+    }
+    SB_LAUNCH(ctx, k_labels_i16, dim3((unsigned)sb_div_up((long long)((n + 3) / 4), 256), 4), 256, 0, M, n);
+    return SB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // Sub-pixel refinement (beyond the reference): the vertex of the parabola through the filtered costs at
 // label-1, label, label+1 of the kept volume.  Float operations in a fixed order (no contraction), so the oracle's
 // so_subpixel_refine agrees bit for bit on the same volume.

@@ -754,3 +754,23 @@ def test_subpixel_rgb_guide_and_refusals(ctx):
     p2 = api.default_params(dmin=-5, dmax=0, radius=4)  # staged path
     with pytest.raises(S.StereoB200Error):
         ctx.pipeline(Lg, Rg, p2, want=("disp_left", "subpixel_left"))
+
+
+@pytest.mark.gpu
+def test_batch_int16_labels_equal_the_float_maps(ctx):
+    """sb200_pipeline_batch_i16: the four label maps as int16 are the float maps, value for value; other
+    outputs may ride along as floats; a map asked for in both forms and labels outside int16 are refused"""
+    n, w, h, size_d = 3, 333, 77, 40
+    pairs = [synth.make_pair(w, h, size_d, seed=50 + i) for i in range(n)]
+    Ls, Rs = np.stack([a for a, _ in pairs]), np.stack([b for _, b in pairs])
+    p = api.default_params(dmin=-(size_d - 1), dmax=0)
+    want = ("disp_left", "disp_right", "occlusion", "filled", "best_left")
+    f = ctx.pipeline_batch(Ls, Rs, p, want=want)
+    i16 = ctx.pipeline_batch(Ls, Rs, p, want=want, labels_i16=True)
+    for k in ("disp_left", "disp_right", "occlusion", "filled"):
+        assert i16[k].dtype == np.int16
+        assert np.array_equal(i16[k].astype(np.float32), f[k]), k
+    assert i16["best_left"].dtype == np.float32 and np.array_equal(i16["best_left"], f["best_left"])
+    assert (f["occlusion"] == -(size_d - 1) - 100).any()
+    with pytest.raises(S.StereoB200Error):
+        ctx.pipeline_batch(Ls, Rs, api.default_params(dmin=-40000, dmax=-39990), want=("filled",), labels_i16=True)
