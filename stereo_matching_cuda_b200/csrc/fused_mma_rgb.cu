@@ -64,6 +64,9 @@ constexpr int R_NGC = 2;         // role C's ring (colours of the output rows, p
 #ifndef RGBM_MERGE_BAR
 #define RGBM_MERGE_BAR 1         // 1 = role B waits once per half: d1_full collects MMA 1's commit and MMA 2's of the previous iteration
 #endif
+#ifndef RGBM_OSPLIT
+#define RGBM_OSPLIT 1            // 1 = role B loads the ring rows that leave the window AFTER the D1 rows and under the a/b arithmetic
+#endif
 #ifndef RGBM_S_MERGE
 #define RGBM_S_MERGE 1           // 1 = the statistics rows' bulk copy completes on d1_full as well (slot == half): role B has ONE wait per half
 #endif
@@ -303,7 +306,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                         slots[j] = slot;
                         slot = (slot + 1 == WIN) ? 0 : slot + 1;
                         tm_ldN(td1 + 16 * HR * half + 16 * j, dd1[j]);
-                        tm_ldN(tring + 16 * slots[j], o[j]);  // the (a, b') row that leaves the vertical window
+                        if (!RGBM_OSPLIT) tm_ldN(tring + 16 * slots[j], o[j]);  // the (a, b') row that leaves the vertical window
                     }
                     tm_wait_ld();
                     tm_fence_before();
@@ -312,6 +315,14 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                         mbar_arrive(mb_d1e + 8 * half);
                         mbar_arrive(mb_se + 8 * ks);  // the statistics are in registers
                     }
+                    uint32_t abr[2][NBC];
+                    if (RGBM_OSPLIT) {
+#pragma unroll
+                        for (int j = 0; j < 2; j++) tm_ldN(tring + 16 * slots[j], o[j]);
+                    }
+#pragma unroll
+                    for (int pass = 0; pass < (RGBM_OSPLIT ? 2 : 1); pass++) {
+                    if (RGBM_OSPLIT && pass == 1) tm_wait_ld();
 #pragma unroll
                     for (int j = 0; j < 2; j++) {
                         const int r = 2 * half + j;
@@ -321,7 +332,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                         const float Mrr = __uint_as_float(s1.w), Mrg = __uint_as_float(s2.x), Mrb = __uint_as_float(s2.y);
                         const float Mgg = __uint_as_float(s2.z), Mgb = __uint_as_float(s2.w), Mbb = __uint_as_float(s3);
                         const float cr = I_CENTER - mr, cg = I_CENTER - mg, cb = I_CENTER - mb;
-                        uint32_t ab[NBC];
+                        uint32_t (&ab)[NBC] = abr[j];
+                        if (!RGBM_OSPLIT || pass == 0) {
 #pragma unroll
                         for (int d = 0; d < BD; d++) {
                             const int e = (d >> 1) * 8 + (d & 1);
@@ -342,10 +354,22 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                             ab[e + 2] = __float_as_uint(ag);
                             ab[e + 4] = __float_as_uint(ab_);
                             ab[e + 6] = __float_as_uint(bb);
-                            V[0][d] += ar - __uint_as_float(o[j][e]);
-                            V[1][d] += ag - __uint_as_float(o[j][e + 2]);
-                            V[2][d] += ab_ - __uint_as_float(o[j][e + 4]);
-                            V[3][d] += bb - __uint_as_float(o[j][e + 6]);
+                            if (!RGBM_OSPLIT) {
+                                V[0][d] += ar - __uint_as_float(o[j][e]);
+                                V[1][d] += ag - __uint_as_float(o[j][e + 2]);
+                                V[2][d] += ab_ - __uint_as_float(o[j][e + 4]);
+                                V[3][d] += bb - __uint_as_float(o[j][e + 6]);
+                            }
+                        }
+                        }
+                        if (RGBM_OSPLIT && pass == 0) continue;
+                        if (RGBM_OSPLIT) {
+#pragma unroll
+                            for (int d = 0; d < BD; d++) {
+                                const int e = (d >> 1) * 8 + (d & 1);
+#pragma unroll
+                                for (int c = 0; c < 4; c++) V[c][d] += __uint_as_float(ab[e + 2 * c]) - __uint_as_float(o[j][e + 2 * c]);
+                            }
                         }
                         tm_stN(tring + 16 * slots[j], ab);
                         if (r == MR - 1 && (it & (R_RESUM - 1)) == R_RESUM - 1) {
@@ -382,6 +406,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) k_fused_mma_rgb(const RgbMmaArgs
                             sts128(b2a + half * B2_HALF + (uint32_t)(4 + j * 2 + q) * B2_GROUP, lo[0], lo[1], lo[2], lo[3]);
                         }
                     }
+                    }  // pass
                     tm_wait_st();
                     fence_async_smem();
                     __syncwarp();
