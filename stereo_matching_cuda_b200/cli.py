@@ -1,12 +1,14 @@
 """Command-line driver: the reference's main() (main.cu:37-214) as one command.
 
-    python -m stereo_matching_cuda_b200.cli LEFT.png RIGHT.png OUTDIR [--dmin -15 --dmax 0] [--fused]
+    python -m stereo_matching_cuda_b200.cli LEFT.png RIGHT.png OUTDIR [--dmin -15 --dmax 0] [--fused] [--subpixel]
 
 Reads a rectified pair, runs the pipeline on GPU 0 and writes the same 12 PNGs main.cu:162-181 writes
 (image_left/right, image_mean_left/right, best_costl/r, cost_lminus15 / cost_rminus15 (slice 0 of each
 volume), occlu_mapl, disparity_mapl/r, occlu_mapl_filled).  Default is the stage-by-stage path in SAT
 mode, whose float32 arithmetic is the reference's operation by operation, so on the Tsukuba pair the
 output files decode to exactly the reference's checked-in PNGs; --fused uses the fused kernel instead.
+--subpixel (beyond the reference, implies the fused kernel) adds disparity_mapl_subpixel.png, the sub-pixel refined and
+filled left disparity through the same write_mat normalisation, and disparity_mapl_subpixel.npy with the float values.
 """
 import argparse
 import os
@@ -33,8 +35,9 @@ def write_mat(mat):
     return scaled.astype(np.int32).astype(np.uint8).reshape(mat.shape)
 
 
-def run(left_rgb, right_rgb, dmin=-15, dmax=0, fused=False, device=0):
-    """returns {file name: uint8 image}"""
+def run(left_rgb, right_rgb, dmin=-15, dmax=0, fused=False, device=0, subpixel=False):
+    """returns {file name: uint8 image} (and, with subpixel, one float32 array under a .npy name)"""
+    fused = fused or subpixel
     p = default_params(dmin=dmin, dmax=dmax, box_mode=BOX_SAT)
     init = np.frombuffer(np.array([0x7F7F7F7F], np.uint32).tobytes(), np.float32)[0]  # main.cu:112
     with Context(device) as ctx:
@@ -42,7 +45,8 @@ def run(left_rgb, right_rgb, dmin=-15, dmax=0, fused=False, device=0):
         costl = ctx.compute_cost(gl, gr, dmin, p)          # main.cu:80
         costr = ctx.compute_cost(gr, gl, -dmax, p)         # main.cu:82
         if fused:
-            out = ctx.pipeline(gl, gr, p)
+            want = ctx._F32 + ctx._U8 + (("subpixel_left",) if subpixel else ())
+            out = ctx.pipeline(gl, gr, p, want=want)
             bl, br, dl, dr = out["best_left"], out["best_right"], out["disp_left"], out["disp_right"]
             ml, mr, occ, filled = out["mean_left"], out["mean_right"], out["occlusion"], out["filled"]
         else:
@@ -57,7 +61,11 @@ def run(left_rgb, right_rgb, dmin=-15, dmax=0, fused=False, device=0):
         # main.cu:162-181: the float maps are normalised to 8 bits on the device (sb200_write_mat)
         wm = ctx.write_mat
         tag = f"minus{-dmin}" if dmin < 0 else str(dmin)
+        extra = {}
+        if subpixel:
+            extra = {"disparity_mapl_subpixel.png": wm(out["subpixel_left"]), "disparity_mapl_subpixel.npy": out["subpixel_left"]}
         return {
+            **extra,
             "image_left.png": gl, "image_right.png": gr, "image_mean_left.png": ml, "image_mean_right.png": mr,
             "best_costl.png": wm(bl), "best_costr.png": wm(br),
             f"cost_l{tag}.png": wm(costl[0]), f"cost_r{tag}.png": wm(costr[0]),
@@ -76,12 +84,16 @@ def main():
     ap.add_argument("--dmin", type=int, default=-15)
     ap.add_argument("--dmax", type=int, default=0)
     ap.add_argument("--fused", action="store_true")
+    ap.add_argument("--subpixel", action="store_true", help="also write the sub-pixel refined left disparity (beyond the reference)")
     a = ap.parse_args()
     L = np.array(Image.open(a.left).convert("RGB"))
     R = np.array(Image.open(a.right).convert("RGB"))
     os.makedirs(a.outdir, exist_ok=True)
-    for name, img in run(L, R, a.dmin, a.dmax, a.fused).items():
-        Image.fromarray(img).save(os.path.join(a.outdir, name))
+    for name, img in run(L, R, a.dmin, a.dmax, a.fused, subpixel=a.subpixel).items():
+        if name.endswith(".npy"):
+            np.save(os.path.join(a.outdir, name), img)
+        else:
+            Image.fromarray(img).save(os.path.join(a.outdir, name))
         print("wrote", os.path.join(a.outdir, name))
 
 

@@ -503,6 +503,11 @@ def test_cli_reproduces_the_twelve_golden_pngs(tsukuba):
         assert np.array_equal(fused[name], O.load_png(name)), name
     for name in ("disparity_mapl.png", "disparity_mapr.png", "occlu_mapl_filled.png"):
         assert (fused[name] == O.load_png(name)).mean() > 0.999, name
+    sub = cli.run(L, R, subpixel=True)  # beyond the reference: two more files, the twelve unchanged
+    assert len(sub) == 14 and all(np.array_equal(sub[k], fused[k]) for k in fused)
+    sp = sub["disparity_mapl_subpixel.npy"]
+    assert sp.dtype == np.float32 and sp.shape == L.shape[:2] and sp.min() >= -15.5 and sp.max() <= 0.5
+    assert sub["disparity_mapl_subpixel.png"].dtype == np.uint8
 
 
 @pytest.mark.parametrize("w,h,dmin,dmax", [(2, 1, -1, 0), (5, 3, -2, 1), (40, 1, -3, 0), (3, 50, 0, 2), (433, 65, -9, 0)])
