@@ -704,8 +704,10 @@ __global__ void __launch_bounds__(M_THREADS, 1) k_fused_mma(const MmaArgs A) {
 // GA: thread per (strip, padded row, cost column)
 __global__ void __launch_bounds__(160) k_prep_ga(const PrepM P0, const PrepM P1) {
     const PrepM& P = blockIdx.z ? P1 : P0;
-    const int k = threadIdx.x, yrow = blockIdx.x, strip = blockIdx.y;
-    const int x = strip * M_VW - 2 * RAD + k, y = yrow - PADY;
+    const int k = threadIdx.x, strip = blockIdx.y;
+    const int x = strip * M_VW - 2 * RAD + k;
+    for (int yrow = blockIdx.x * PREP_ROWS; yrow < min(P.rows_pad, (int)(blockIdx.x + 1) * PREP_ROWS); yrow++) {
+    const int y = yrow - PADY;
     float I, G;
     pix_ig(P, x, y, I, G);
     const bool in = in_frame(P, x, y);
@@ -717,6 +719,7 @@ __global__ void __launch_bounds__(160) k_prep_ga(const PrepM P0, const PrepM P1)
     // the output lanes' intensities, centred (role C): lane l is cost column l + 18
     if (k >= 2 * RAD && k < 2 * RAD + M_TW)
         P.GC[((size_t)strip * P.rows_pad + yrow) * M_TW + (k - 2 * RAD)] = __float2half(in ? I - I_CENTER : 0.0f);
+    }
 }
 
 
@@ -867,9 +870,9 @@ int sbf_run_fused_mma(sb200_ctx* ctx, const sb200_params* p, const uint8_t* cons
         P.S = (float)S;
         P.scale = scale;
     }
-    SB_LAUNCH(ctx, k_prep_ga, dim3(rows_pad, plan.n_strips, 2), M_KB, 0, PP[0], PP[1]);
+    SB_LAUNCH(ctx, k_prep_ga, dim3(sb_div_up(rows_pad, PREP_ROWS), plan.n_strips, 2), M_KB, 0, PP[0], PP[1]);
     SB_LAUNCH(ctx, k_prep_gb, dim3(sb_div_up(rows_pad, GB_TR), plan.n_strips, 2), M_TW, 0, PP[0], PP[1]);
-    SB_LAUNCH(ctx, k_prep_mt, dim3(sb_div_up(mg.n_chunk * 4, 256), rows_pad, 2), 256, 0, PP[0], PP[1]);
+    SB_LAUNCH(ctx, k_prep_mt, dim3(sb_div_up(mg.n_chunk, 256), rows_pad, 2), 256, 0, PP[0], PP[1]);
     if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
 
     MmaArgs A;

@@ -837,8 +837,10 @@ __device__ __forceinline__ bool in_frame_r(const PrepR& P, int x, int y) {
 // GA, GC: thread per (strip, padded row, cost column)
 __global__ void __launch_bounds__(160) k_prep_ga3(const PrepR P0, const PrepR P1) {
     const PrepR& P = blockIdx.z ? P1 : P0;
-    const int k = threadIdx.x, yrow = blockIdx.x, strip = blockIdx.y;
-    const int x = strip * M_VW - 2 * RAD + k, y = yrow - PADY;
+    const int k = threadIdx.x, strip = blockIdx.y;
+    const int x = strip * M_VW - 2 * RAD + k;
+    for (int yrow = blockIdx.x * PREP_ROWS; yrow < min(P.rows_pad, (int)(blockIdx.x + 1) * PREP_ROWS); yrow++) {
+    const int y = yrow - PADY;
     const bool in = in_frame_r(P, x, y);
     float I = 1024.0f, G = 1024.0f;
     int c[3] = {0, 0, 0};
@@ -865,6 +867,7 @@ __global__ void __launch_bounds__(160) k_prep_ga3(const PrepR P0, const PrepR P1
         const int l = k - 2 * RAD;
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) P.GC[rec * (3 * M_TW) + ch * M_TW + l] = __float2half(in ? (float)c[ch] - I_CENTER : 0.0f);
+    }
     }
 }
 
@@ -1049,9 +1052,9 @@ int sbf_pair_disparity_rgb_mma(sb200_ctx* ctx, const sb200_params* p, const uint
         Q.S = (float)S;
         Q.scale = scale;
     }
-    SB_LAUNCH(ctx, k_prep_ga3, dim3(rows_pad, plan.n_strips, 2), M_KB, 0, PR[0], PR[1]);
+    SB_LAUNCH(ctx, k_prep_ga3, dim3(sb_div_up(rows_pad, PREP_ROWS), plan.n_strips, 2), M_KB, 0, PR[0], PR[1]);
     SB_LAUNCH(ctx, k_prep_gb3, dim3(sb_div_up(rows_pad, GB3_TR), plan.n_strips, 2), M_TW, 0, PR[0], PR[1]);
-    SB_LAUNCH(ctx, k_prep_mt, dim3(sb_div_up(mg.n_chunk * 4, 256), rows_pad, 2), 256, 0, QM[0], QM[1]);
+    SB_LAUNCH(ctx, k_prep_mt, dim3(sb_div_up(mg.n_chunk, 256), rows_pad, 2), 256, 0, QM[0], QM[1]);
     if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
 
     RgbMmaArgs A;

@@ -168,24 +168,28 @@ __device__ __forceinline__ void pix_ig(const PrepM& P, int x, int y, float& I, f
     G = (float)(il - ir);
 }
 
-// MT: thread per (padded row, chunk, copy)
+// MT: thread per (padded row, chunk): the chunk's four shifted copies are 7 consecutive pixels dealt out four times
 // (the preparation kernels take both images of a pair in one launch: blockIdx.z selects the image)
+constexpr int PREP_ROWS = 8;  // rows per block of the gather kernels (k_prep_ga, k_prep_ga3)
 __global__ void __launch_bounds__(256) k_prep_mt(const PrepM P0, const PrepM P1) {
     const PrepM& P = blockIdx.z ? P1 : P0;
-    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int i = blockIdx.x * 256 + threadIdx.x;
     const int yrow = blockIdx.y;
-    if (idx >= P.n_chunk * 4) return;
-    const int i = idx >> 2, s = idx & 3;
+    if (i >= P.n_chunk) return;
     const int y = yrow - PADY;
-    float I[4], G[4];
+    float I[7], G[7];
 #pragma unroll
-    for (int j = 0; j < 4; j++) pix_ig(P, 4 * i + s + j - P.padm, y, I[j], G[j]);
-    uint4 v;
-    v.x = h22u(__floats2half2_rn(I[0], I[1]));
-    v.y = h22u(__floats2half2_rn(I[2], I[3]));
-    v.z = h22u(__floats2half2_rn(G[0], G[1]));
-    v.w = h22u(__floats2half2_rn(G[2], G[3]));
-    P.MT[((size_t)yrow * P.n_chunk + i) * 4 + s] = v;
+    for (int j = 0; j < 7; j++) pix_ig(P, 4 * i + j - P.padm, y, I[j], G[j]);
+    uint4* dst = P.MT + ((size_t)yrow * P.n_chunk + i) * 4;
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        uint4 v;
+        v.x = h22u(__floats2half2_rn(I[s], I[s + 1]));
+        v.y = h22u(__floats2half2_rn(I[s + 2], I[s + 3]));
+        v.z = h22u(__floats2half2_rn(G[s], G[s + 1]));
+        v.w = h22u(__floats2half2_rn(G[s + 2], G[s + 3]));
+        dst[s] = v;
+    }
 }
 
 Plan make_plan_mma(int w, int rows_out, int size_d, int sm_count, int n_views, int nd) {
