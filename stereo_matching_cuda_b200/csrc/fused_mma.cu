@@ -723,31 +723,45 @@ __global__ void __launch_bounds__(160) k_prep_ga(const PrepM P0, const PrepM P1)
 }
 
 
-// GB: block = (strip, 32 padded rows), thread per a/b lane; exact integer window sums of I and I^2
+// GB: block = (strip, GB_TR padded rows); exact integer window sums of I and I^2.  Horizontal 19-column sums as SLIDING sums
+// along x: a task is (tile row, segment of 32 lanes), 19 taps to start and then +entering -leaving per lane (the first
+// version took 19 taps per lane and row); vertical sums by one thread per a/b lane, sliding down the tile.
 constexpr int GB_TR = 16;
+constexpr int GB_ROWS = GB_TR + 2 * RAD;   // tile rows
+constexpr int GB_SEG = 32, GB_NSEG = M_TW / GB_SEG;
 __global__ void __launch_bounds__(M_TW) k_prep_gb(const PrepM P0, const PrepM P1) {
     const PrepM& P = blockIdx.z ? P1 : P0;
-    __shared__ unsigned short sI[GB_TR + 2 * RAD][M_TW + 2 * RAD + 2];
-    __shared__ int h1[GB_TR + 2 * RAD][M_TW], h2[GB_TR + 2 * RAD][M_TW];
+    __shared__ unsigned short sI[GB_ROWS][M_TW + 2 * RAD + 4];  // pitch 150 halves = 75 words: rows fall on different banks
+    __shared__ int h1[GB_ROWS][M_TW + 1], h2[GB_ROWS][M_TW + 1];
     const int l = threadIdx.x, strip = blockIdx.y;
     const int yrow0 = blockIdx.x * GB_TR;
     const int xa0 = strip * M_VW - RAD;
-    for (int i = l; i < (GB_TR + 2 * RAD) * (M_TW + 2 * RAD); i += M_TW) {
+    for (int i = l; i < GB_ROWS * (M_TW + 2 * RAD); i += M_TW) {
         const int py = i / (M_TW + 2 * RAD), px = i - py * (M_TW + 2 * RAD);
         const int x = xa0 + px - RAD, y = yrow0 - PADY + py - RAD;
         sI[py][px] = in_frame(P, x, y) ? P.gray[(size_t)y * P.w + x] : 0;
     }
     __syncthreads();
-    for (int py = 0; py < GB_TR + 2 * RAD; py++) {
+    for (int t = l; t < GB_NSEG * GB_ROWS; t += M_TW) {  // consecutive threads: consecutive rows of one segment
+        const int seg = t / GB_ROWS, py = t - seg * GB_ROWS;
+        const unsigned short* row = sI[py] + seg * GB_SEG;
         int s1 = 0, s2 = 0;
 #pragma unroll
-        for (int t = 0; t < WIN; t++) {
-            const int v = sI[py][l + t];
+        for (int k = 0; k < WIN; k++) {
+            const int v = row[k];
             s1 += v;
             s2 += v * v;
         }
-        h1[py][l] = s1;
-        h2[py][l] = s2;
+        h1[py][seg * GB_SEG] = s1;
+        h2[py][seg * GB_SEG] = s2;
+#pragma unroll 8
+        for (int i = 1; i < GB_SEG; i++) {
+            const int a = row[i + WIN - 1], b = row[i - 1];
+            s1 += a - b;
+            s2 += a * a - b * b;
+            h1[py][seg * GB_SEG + i] = s1;
+            h2[py][seg * GB_SEG + i] = s2;
+        }
     }
     __syncthreads();
     const int x = xa0 + l;
