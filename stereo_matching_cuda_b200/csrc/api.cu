@@ -87,7 +87,6 @@ void sb200_ctx_destroy(sb200_ctx* ctx) {
             cudaEventDestroy(ctx->ev_out[i]);
         }
     }
-    if (ctx->pin) cudaFreeHost(ctx->pin);
     if (ctx->ev_valid) {
         for (int i = 0; i < 5; i++) cudaEventDestroy(ctx->ev[i]);
         for (int i = 0; i < 2; i++) cudaEventDestroy(ctx->ev_x[i]);
@@ -169,17 +168,6 @@ int sb_ws_reserve(sb200_ctx* ctx, size_t bytes) {  // (called under the entry po
         ctx->ws_cap = bytes;
     }
     ctx->ws_off = 0;
-    return SB200_OK;
-}
-
-int sb_pin_reserve(sb200_ctx* ctx, size_t bytes) {
-    if (bytes > ctx->pin_cap) {
-        if (ctx->pin) SB_CUDA(ctx, cudaFreeHost(ctx->pin));
-        ctx->pin = nullptr;
-        ctx->pin_cap = 0;
-        SB_CUDA(ctx, cudaMallocHost(&ctx->pin, bytes));
-        ctx->pin_cap = bytes;
-    }
     return SB200_OK;
 }
 

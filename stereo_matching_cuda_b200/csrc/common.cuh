@@ -20,9 +20,6 @@ struct sb200_ctx {
     char* ws = nullptr;
     size_t ws_cap = 0;
     size_t ws_off = 0;
-    // pinned staging for the host-pointer entry points
-    char* pin = nullptr;
-    size_t pin_cap = 0;
     uint64_t launches = 0;
     char err[512] = {0};
     // optional timing of the pipeline's phases
@@ -116,7 +113,6 @@ inline T* sb_ws_alloc(sb200_ctx* ctx, size_t count) {
     ctx->ws_off = end;
     return reinterpret_cast<T*>(ctx->ws + off);
 }
-int sb_pin_reserve(sb200_ctx* ctx, size_t bytes);
 
 inline int sb_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
 
