@@ -224,6 +224,16 @@ int sb200_pipeline_strip_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_
 int sb200_pipeline_strips_nccl(sb200_ctx* ctx, const sb200_params* p, void* nccl_comm, int rank, int world,
                                const uint8_t* d_own_left, const uint8_t* d_own_right, int channels, int w, int frame_h,
                                int y0, int rows, const sb200_outputs* d_out);
+/* Which implementation sb200_pipeline* runs for these parameters on this context -- the fused kernels are built for the
+ * reference's RADIUS 9 (SystemIncludes.h:9) and for cost parameters with an exact integer lattice (its ALPHA / TH_* are);
+ * anything else still runs on the GPU, through the stage kernels: same results contract, whole frames only, and of the
+ * order of a second per 1080p D=256 pair instead of milliseconds.  A caller that changes RADIUS can ask first.
+ * Returns SB200_PATH_* (>= 0) or -SB200_ERR_* (e.g. -SB200_ERR_UNSUPPORTED: RGB guide with parameters no fused kernel
+ * covers and box_mode not SAT). */
+#define SB200_PATH_STAGED 0
+#define SB200_PATH_FUSED_SHUFFLE 1
+#define SB200_PATH_FUSED_TENSOR 2
+int sb200_pipeline_path(const sb200_ctx* ctx, const sb200_params* p);
 /* the balanced split sb200_pipeline_strips_nccl expects: rows [y0, y0+rows) of rank `rank` of `world` */
 int sb200_strip_rows(int frame_h, int rank, int world, int* y0, int* rows);
 /* halo rows each side that sb200_pipeline_strip_dev needs: 2*radius (two cascaded boxes) */

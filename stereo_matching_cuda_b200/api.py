@@ -93,6 +93,7 @@ def load_library(path=None):
         "sb200_last_error": (C.c_char_p, [vp]),
         "sb200_launch_count": (C.c_uint64, [vp]),
         "sb200_ctx_rgb_kernel": (ip, [vp]),
+        "sb200_pipeline_path": (ip, [vp, PP]),
         "sb200_ctx_gray_kernel": (ip, [vp]),
         "sb200_ctx_set_gray_kernel": (ip, [vp, ip]),
         "sb200_version": (C.c_char_p, []),
@@ -222,6 +223,14 @@ class Context:
     @property
     def launch_count(self):
         return int(self.lib.sb200_launch_count(self.h))
+
+    def pipeline_path(self, params=None):
+        """0 = staged kernels, 1 = warp-shuffle fused kernel, 2 = tensor-core fused kernel (sb200_pipeline_path)"""
+        p = params or default_params()
+        rc = int(self.lib.sb200_pipeline_path(self.h, C.byref(p)))
+        if rc < 0:
+            raise StereoB200Error(f"no pipeline path for these parameters (code {rc})")
+        return rc
 
     @property
     def rgb_kernel(self):

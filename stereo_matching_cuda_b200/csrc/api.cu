@@ -638,6 +638,18 @@ int sb200_fl_to_ch2_dev(sb200_ctx* ctx, const float* d_image, uint8_t* d_result,
 // ---- fused pipeline ---------------------------------------------------------------------
 int sb200_strip_halo_rows(const sb200_params* p) { return p ? 2 * p->radius : 0; }
 
+// which implementation sb200_pipeline* uses for these parameters (the selection logic of pipeline_core, made visible)
+int sb200_pipeline_path(const sb200_ctx* ctx, const sb200_params* p) {
+    if (!ctx || !p) return -SB200_ERR_INVALID;
+    if (p->guide_mode == SB200_GUIDE_RGB) {
+        if (p->box_mode == SB200_BOX_SAT) return SB200_PATH_STAGED;
+        if (!sbf_fused_supported(p)) return -SB200_ERR_UNSUPPORTED;
+        return rgb_uses_mma(ctx, p) ? SB200_PATH_FUSED_TENSOR : SB200_PATH_FUSED_SHUFFLE;
+    }
+    if (!sbf_fused_supported(p)) return SB200_PATH_STAGED;
+    return (ctx->gray_kernel == 1 && sbf_mma_supported(p)) ? SB200_PATH_FUSED_TENSOR : SB200_PATH_FUSED_SHUFFLE;
+}
+
 int sb200_pipeline_dev(sb200_ctx* ctx, const sb200_params* p, const uint8_t* d_left, const uint8_t* d_right,
                        int channels, int w, int h, const sb200_outputs* d_out) {
     DevGuard dev_guard__(ctx);

@@ -331,6 +331,10 @@ def test_pipeline_other_parameters_run_staged_or_fused(ctx, oracle, kw):
     w, h, size_d = 150, 80, 9
     L, R = synth.make_pair(w, h, size_d, seed=77)
     p = api.default_params(dmin=-(size_d - 1), dmax=0, **kw)
+    # the caller can see which path a parameter set takes: the reference's macros run on the tensor-core kernel
+    assert ctx.pipeline_path(api.default_params()) == 2
+    assert ctx.pipeline_path(p) == (0 if ("radius" in kw or "alpha" in kw) else ctx.pipeline_path(p))
+    assert ctx.pipeline_path(p) in (0, 1, 2)
     out = ctx.pipeline(L, R, p)
     okw = dict(kw)
     ref = oracle.pipeline_gray(L, R, -(size_d - 1), size_d,
