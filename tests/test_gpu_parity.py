@@ -783,3 +783,20 @@ def test_batch_int16_labels_equal_the_float_maps(ctx):
     assert (f["occlusion"] == -(size_d - 1) - 100).any()
     with pytest.raises(S.StereoB200Error):
         ctx.pipeline_batch(Ls, Rs, api.default_params(dmin=-40000, dmax=-39990), want=("filled",), labels_i16=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rgb", [False, True])
+def test_fused_outputs_are_deterministic_over_repeated_runs(ctx, rgb):
+    """The fused kernels hand rows between five warp roles through mbarriers, Tensor Memory and shared-memory rings; a missing
+    ordering would show as run-to-run differences long before it shows as a wrong pixel.  Twelve runs of one pair (several
+    disparity groups, bands and strips) must agree in every bit of every output."""
+    w, h, size_d = 700, 400, 72
+    L, R = synth.make_pair(w, h, size_d, channels=3 if rgb else 1, seed=11)
+    p = api.default_params(dmin=-(size_d - 1), dmax=0, guide_mode=S.GUIDE_RGB if rgb else S.GUIDE_GRAY)
+    want = ("disp_left", "disp_right", "best_left", "best_right", "occlusion", "filled")
+    first = ctx.pipeline(L, R, p, want=want)
+    for _ in range(11):
+        again = ctx.pipeline(L, R, p, want=want)
+        for k in want:
+            assert np.array_equal(first[k].view(np.uint32), again[k].view(np.uint32)), k
