@@ -875,62 +875,81 @@ __global__ void __launch_bounds__(160) k_prep_ga3(const PrepR P0, const PrepR P1
 // is loaded once; a thread then walks down its column: the window sums are vertical running sums of the rows' horizontal
 // 19-tap sums of the nine quantities (the row that enters adds, the row that leaves is recomputed and subtracted).
 constexpr int GB3_TR = 32;
-__global__ void __launch_bounds__(M_TW) k_prep_gb3(const PrepR P0, const PrepR P1) {
+constexpr int GB3_T = 160;  // threads: one per tile column (146 used: the 128 a/b lanes and 9 columns on either side)
+// The nine window sums (R, G, B and their six products; exact integers) of every a/b lane: each thread slides the VERTICAL
+// 19-row sums of its tile column down the block's rows in registers (+ entering pixel, - leaving pixel), a warp prefix sum
+// turns a row of them into prefix sums along x, and a lane's 19-column window is the difference of two prefixes (plus the
+// total of the warp to its left when the window straddles two warps).  The first version took the 19 x 9 taps of a row's
+// horizontal sums twice per output row (0.11 ms per image; this: see DESIGN 6).
+__global__ void __launch_bounds__(GB3_T) k_prep_gb3(const PrepR P0, const PrepR P1) {
     const PrepR& P = blockIdx.z ? P1 : P0;
-    __shared__ uchar4 sC[GB3_TR + 2 * RAD][M_TW + 2 * RAD];
-    const int l = threadIdx.x, strip = blockIdx.y;
+    __shared__ int sP[2][9][GB3_T];       // warp-local inclusive prefix sums along x of the current row (double-buffered)
+    __shared__ int sT[2][9][GB3_T / 32];  // the warps' totals
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5, strip = blockIdx.y;
     const int yrow0 = blockIdx.x * GB3_TR;
     const int xa0 = strip * M_VW - RAD;
-    const int x = xa0 + l;
-    for (int i = l; i < (GB3_TR + 2 * RAD) * (M_TW + 2 * RAD); i += M_TW) {
-        const int py = i / (M_TW + 2 * RAD), px = i - py * (M_TW + 2 * RAD);
-        const int xx = xa0 + px - RAD, yy = yrow0 - PADY + py - RAD;
-        uchar4 c = make_uchar4(0, 0, 0, 0);
-        if (in_frame_r(P, xx, yy)) {
-            const uint8_t* q = P.rgb + ((size_t)yy * P.w + xx) * P.ch;
-            c = make_uchar4(q[0], q[1], q[2], 0);
-        }
-        sC[py][px] = c;
-    }
-    __syncthreads();
-    int v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    auto hsum = [&](int py, int (&s)[9]) {  // horizontal sums of tile row py at this lane
-#pragma unroll
-        for (int q = 0; q < 9; q++) s[q] = 0;
-#pragma unroll
-        for (int t = 0; t < WIN; t++) {
-            const uchar4 c = sC[py][l + t];
-            const int r = c.x, g = c.y, b = c.z;
-            s[0] += r; s[1] += g; s[2] += b;
-            s[3] += r * r; s[4] += r * g; s[5] += r * b;
-            s[6] += g * g; s[7] += g * b; s[8] += b * b;
+    const int xc = xa0 + t - RAD;  // frame column of this thread's tile column
+    auto pixel = [&](int y, int& r, int& g, int& b) {  // held row y of the thread's column; 0 outside the frame
+        r = g = b = 0;
+        if (t < M_TW + 2 * RAD && in_frame_r(P, xc, y)) {
+            const uint8_t* q = P.rgb + ((size_t)y * P.w + xc) * P.ch;
+            r = q[0];
+            g = q[1];
+            b = q[2];
         }
     };
-    int s[9];
-    for (int t = 0; t < 2 * RAD; t++) {  // tile rows 0 .. 17 = held rows y0-9 .. y0+8 of the first output row's window
-        hsum(t, s);
-#pragma unroll
-        for (int q = 0; q < 9; q++) v[q] += s[q];
-    }
+    int v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    auto add = [&](int y, int sgn) {
+        int r, g, b;
+        pixel(y, r, g, b);
+        v[0] += sgn * r; v[1] += sgn * g; v[2] += sgn * b;
+        v[3] += sgn * r * r; v[4] += sgn * r * g; v[5] += sgn * r * b;
+        v[6] += sgn * g * g; v[7] += sgn * g * b; v[8] += sgn * b * b;
+    };
+    const int y0 = yrow0 - PADY;  // held row of the block's first output row
+    for (int dy = -RAD; dy < RAD; dy++) add(y0 + dy, 1);  // rows y0-9 .. y0+8
+    const int x = xa0 + t;  // frame column of a/b lane t (threads 0..127)
     for (int ty = 0; ty < GB3_TR; ty++) {
-        const int yrow = yrow0 + ty;
-        const int y = yrow - PADY, yg = y + P.y_global0;
-        hsum(ty + 2 * RAD, s);
+        const int yrow = yrow0 + ty, y = yrow - PADY, yg = y + P.y_global0;
+        const int buf = ty & 1;
+        add(y + RAD, 1);
+        // warp-local inclusive prefix sums of the nine vertical sums
+        int pre[9];
 #pragma unroll
-        for (int q = 0; q < 9; q++) v[q] += s[q];
-        if (yrow < P.rows_pad) {
+        for (int q = 0; q < 9; q++) {
+            int p = v[q];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, p, off);
+                if (lane >= off) p += n;
+            }
+            pre[q] = p;
+            sP[buf][q][t] = p;
+            if (lane == 31) sT[buf][q][wid] = p;
+        }
+        __syncthreads();  // (one barrier per row: the buffers alternate)
+        if (t < M_TW && yrow < P.rows_pad) {
+            // window of lane t = tile columns t .. t+18: prefix(t+18) - prefix(t-1)
+            const int b = t + 2 * RAD, wb = b >> 5;
+            int s[9];
+#pragma unroll
+            for (int q = 0; q < 9; q++) {
+                int acc = sP[buf][q][b];
+                if (wb != wid) acc += sT[buf][q][wid];       // the window ends in the next warp: this warp's total
+                s[q] = acc - (pre[q] - v[q]);                // minus the exclusive prefix at t (0 at a warp's first lane)
+            }
             float o[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             if (in_frame_r(P, x, y)) {
                 const int ax = min(P.w - 1, x + RAD) - max(0, x - RAD) + 1;
                 const int ay = min(P.frame_h - 1, yg + RAD) - max(0, yg - RAD) + 1;
                 const float area = (float)(ax * ay);
-                const float mr = __fdiv_rn((float)v[0], area), mg = __fdiv_rn((float)v[1], area), mb = __fdiv_rn((float)v[2], area);
-                const double xx = (double)__fsub_rn(__fdiv_rn((float)v[3], area), __fmul_rn(mr, mr)) + P.eps;
-                const double xy = __fsub_rn(__fdiv_rn((float)v[4], area), __fmul_rn(mr, mg));
-                const double xz = __fsub_rn(__fdiv_rn((float)v[5], area), __fmul_rn(mr, mb));
-                const double yy = (double)__fsub_rn(__fdiv_rn((float)v[6], area), __fmul_rn(mg, mg)) + P.eps;
-                const double yz = __fsub_rn(__fdiv_rn((float)v[7], area), __fmul_rn(mg, mb));
-                const double zz = (double)__fsub_rn(__fdiv_rn((float)v[8], area), __fmul_rn(mb, mb)) + P.eps;
+                const float mr = __fdiv_rn((float)s[0], area), mg = __fdiv_rn((float)s[1], area), mb = __fdiv_rn((float)s[2], area);
+                const double xx = (double)__fsub_rn(__fdiv_rn((float)s[3], area), __fmul_rn(mr, mr)) + P.eps;
+                const double xy = __fsub_rn(__fdiv_rn((float)s[4], area), __fmul_rn(mr, mg));
+                const double xz = __fsub_rn(__fdiv_rn((float)s[5], area), __fmul_rn(mr, mb));
+                const double yy = (double)__fsub_rn(__fdiv_rn((float)s[6], area), __fmul_rn(mg, mg)) + P.eps;
+                const double yz = __fsub_rn(__fdiv_rn((float)s[7], area), __fmul_rn(mg, mb));
+                const double zz = (double)__fsub_rn(__fdiv_rn((float)s[8], area), __fmul_rn(mb, mb)) + P.eps;
                 const double a00 = yy * zz - yz * yz, a01 = xz * yz - xy * zz, a02 = xy * yz - xz * yy;
                 const double a11 = xx * zz - xz * xz, a12 = xy * xz - xx * yz, a22 = xx * yy - xy * xy;
                 const double id = 1.0 / (xx * a00 + xy * a01 + xz * a02);
@@ -944,13 +963,11 @@ __global__ void __launch_bounds__(M_TW) k_prep_gb3(const PrepR P0, const PrepR P
                 o[8] = __fmul_rn((float)(a22 * id), rxy);
             }
             float* dst = P.GB + ((size_t)strip * P.rows_pad + yrow) * (GB_ROW / 4);
-            *reinterpret_cast<float4*>(dst + l * 4) = make_float4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<float4*>(dst + M_TW * 4 + l * 4) = make_float4(o[4], o[5], o[6], o[7]);
-            dst[M_TW * 8 + l] = o[8];
+            *reinterpret_cast<float4*>(dst + t * 4) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(dst + M_TW * 4 + t * 4) = make_float4(o[4], o[5], o[6], o[7]);
+            dst[M_TW * 8 + t] = o[8];
         }
-        hsum(ty, s);
-#pragma unroll
-        for (int q = 0; q < 9; q++) v[q] -= s[q];
+        add(y - RAD, -1);
     }
 }
 
@@ -1053,7 +1070,7 @@ int sbf_pair_disparity_rgb_mma(sb200_ctx* ctx, const sb200_params* p, const uint
         Q.scale = scale;
     }
     SB_LAUNCH(ctx, k_prep_ga3, dim3(sb_div_up(rows_pad, PREP_ROWS), plan.n_strips, 2), M_KB, 0, PR[0], PR[1]);
-    SB_LAUNCH(ctx, k_prep_gb3, dim3(sb_div_up(rows_pad, GB3_TR), plan.n_strips, 2), M_TW, 0, PR[0], PR[1]);
+    SB_LAUNCH(ctx, k_prep_gb3, dim3(sb_div_up(rows_pad, GB3_TR), plan.n_strips, 2), GB3_T, 0, PR[0], PR[1]);
     SB_LAUNCH(ctx, k_prep_mt, dim3(sb_div_up(mg.n_chunk, 256), rows_pad, 2), 256, 0, QM[0], QM[1]);
     if (ctx->timing && ctx->ev_valid) SB_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
 
