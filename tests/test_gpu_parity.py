@@ -800,3 +800,32 @@ def test_fused_outputs_are_deterministic_over_repeated_runs(ctx, rgb):
         again = ctx.pipeline(L, R, p, want=want)
         for k in want:
             assert np.array_equal(first[k].view(np.uint32), again[k].view(np.uint32)), k
+
+
+@pytest.mark.gpu
+def test_subpixel_in_strip_mode_equals_the_whole_frame(ctx):
+    """the kept volume follows the strip geometry (rows_out x w planes): a strip's sub-pixel map equals the whole frame's rows
+    wherever the integer labels agree (strips differ from the whole frame only by second-stage float summation order)"""
+    torch = pytest.importorskip("torch")
+    w, h, size_d = 300, 200, 20
+    L, R = synth.make_pair(w, h, size_d, seed=9)
+    dmin = -(size_d - 1)
+    p = api.default_params(dmin=dmin, dmax=0)
+    whole = ctx.pipeline(L, R, p, want=("disp_left", "occlusion", "filled", "subpixel_left"))
+    dev = torch.device("cuda:0")
+    halo = ctx.strip_halo_rows(p)
+    y0, rows = 70, 64
+    top, bot = min(halo, y0), min(halo, h - (y0 + rows))
+    dl = torch.from_numpy(np.ascontiguousarray(L[y0 - top:y0 + rows + bot])).to(dev)
+    dr = torch.from_numpy(np.ascontiguousarray(R[y0 - top:y0 + rows + bot])).to(dev)
+    names = ("disp_left", "disp_right", "occlusion", "filled", "subpixel_left")
+    outs = {k: torch.empty((rows, w), dtype=torch.float32, device=dev) for k in names}
+    ctx.pipeline_strip_dev(dl, dr, 1, w, dict(y0=y0, rows=rows, halo_top=top, halo_bot=bot, frame_h=h), outs, p)
+    ctx.synchronize()
+    got = {k: v.cpu().numpy() for k, v in outs.items()}
+    same = got["disp_left"] == whole["disp_left"][y0:y0 + rows]
+    assert same.mean() > 0.999
+    assert np.array_equal(got["occlusion"][same], whole["occlusion"][y0:y0 + rows][same])
+    d = np.abs(got["subpixel_left"] - whole["subpixel_left"][y0:y0 + rows])[same & (got["occlusion"] >= dmin)]
+    assert np.median(d) < 1e-4 and np.quantile(d, 0.99) < 1e-2, (np.median(d), np.quantile(d, 0.99))
+    assert (got["subpixel_left"] != got["disp_left"]).mean() > 0.3
