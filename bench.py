@@ -467,10 +467,14 @@ def main():
 
     e2e = None
     if mode == "dp":
-        e2e = e2e_batch(pairs, p, channels, w, h, size_d, max(4, min(args.steps, 32)))
-        # the same call with the label maps as int16 (half the device->host bytes): reported next to `e2e`, which keeps the
-        # reference's float label maps
-        e2e["int16_labels"] = e2e_batch(pairs, p, channels, w, h, size_d, max(4, min(args.steps, 32)), i16=True)
+        # End to end = the host-pointer batch entry a user calls for label maps: sb200_pipeline_batch_i16 (the four maps as
+        # int16, 16.6 MB per 1080p pair device->host).  The same call with the reference's float label maps (33 MB) is
+        # reported beside it as `float_labels`: on one GPU the two agree, with eight GPUs behind one host the float maps'
+        # copies are what holds the end-to-end rate back (round-1 verdict, item 6).
+        e2e = e2e_batch(pairs, p, channels, w, h, size_d, max(4, min(args.steps, 32)), i16=True)
+        e2e_f = e2e_batch(pairs, p, channels, w, h, size_d, max(4, min(args.steps, 32)))
+        e2e["float_labels"] = e2e_f
+        e2e["int16_labels"] = {k: e2e[k] for k in ("value", "unit", "ms_per_step", "d2h_bytes_per_step")}  # (kept for readers of earlier lines)
 
     # ------------------------------------------------------------------------------------------------ extra legs
     rgb_state = {}
@@ -503,7 +507,7 @@ def main():
                              "traffic": tr.get("dram_bytes_per_launch") if tr else None, "traffic_src": tr.get("src") if tr else None,
                              "ncu": {k: tr.get(k) for k in ("l1tex_data_pipe_pct", "issue_active_pct", "fma_pipe_pct", "alu_pipe_pct",
                                                             "kernel_ms_under_ncu")} if tr else None},
-                "e2e": e2e_batch(cpairs, p_rgb, 3, w, h, size_d, max(4, min(args.steps, 12))), "clocks": clk,
+                "e2e": e2e_batch(cpairs, p_rgb, 3, w, h, size_d, max(4, min(args.steps, 12)), i16=True), "clocks": clk,
                 "note": "colour guided filter of SURVEY A.8 on 3-channel synthetic pairs: BASELINE configs[2] as specified; not in the "
                         "reference (parity against the oracle's RGB port at full size: tests/test_rgb_guide.py)"}
 
